@@ -1,0 +1,122 @@
+"""In-tree builds: the CUDA C-ABI library (nvcc, sm_100a), the host mesh engine (gcc)
+and -- for tests / the CPU baseline only -- the oracle (gcc).
+
+Everything is compiled to a shared object next to its sources so that the built files
+travel to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "blastamr_b200" / "csrc"
+LIB_CUDA = ROOT / "blastamr_b200" / "libamr_b200.so"
+LIB_MESH = ROOT / "blastamr_b200" / "libamrmesh.so"
+LIB_HOST = ROOT / "blastamr_b200" / "libamrhost.so"
+ORACLE_DIR = ROOT / "oracle"
+LIB_ORACLE = ORACLE_DIR / "liboracle.so"
+
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(target: Path, sources) -> bool:
+    if not target.exists():
+        return False
+    t = target.stat().st_mtime
+    return all(Path(s).stat().st_mtime <= t for s in sources)
+
+
+def _run(cmd, **kw):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(map(str, cmd)) + "\n" + r.stdout + "\n")
+        raise RuntimeError(f"build failed: {cmd[0]} (exit {r.returncode})")
+    return r.stdout
+
+
+def _nccl_paths():
+    """Prefer the NCCL that torch bundles (the one the process has loaded anyway)."""
+    try:
+        import nvidia.nccl as _n  # type: ignore
+
+        base = Path(list(_n.__path__)[0])
+        inc, lib = base / "include", base / "lib"
+        if (inc / "nccl.h").exists() and (lib / "libnccl.so.2").exists():
+            return str(inc), str(lib), "libnccl.so.2"
+    except Exception:
+        pass
+    return "/usr/include", "/usr/lib/x86_64-linux-gnu", "libnccl.so.2"
+
+
+def build_mesh(force: bool = False) -> Path:
+    src = [CSRC / "meshgen.c"]
+    if not force and _newer(LIB_MESH, src):
+        return LIB_MESH
+    _run(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-fvisibility=hidden", "-std=gnu11",
+          "-o", str(LIB_MESH)] + [str(s) for s in src] + ["-lm"])
+    return LIB_MESH
+
+
+def build_oracle(force: bool = False) -> Path:
+    src = sorted(ORACLE_DIR.glob("*.c")) + sorted(ORACLE_DIR.glob("*.h"))
+    csrc = [s for s in src if s.suffix == ".c"]
+    if not force and _newer(LIB_ORACLE, src):
+        return LIB_ORACLE
+    # -ffp-contract=off: no FMA contraction, x86-64 OpenFOAM builds have none either
+    _run(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=gnu11", "-pthread",
+          "-o", str(LIB_ORACLE)] + [str(s) for s in csrc] + ["-lm"])
+    return LIB_ORACLE
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> Path:
+    src = sorted(CSRC.glob("*.cu"))
+    hdr = sorted(CSRC.glob("*.cuh")) + sorted((ROOT / "include").glob("*.h"))
+    if not force and _newer(LIB_CUDA, src + hdr):
+        return LIB_CUDA
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    inc, libdir, libname = _nccl_paths()
+    cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", *NVCC_ARCH,
+           "-fmad=false",                      # bitwise parity of the FP64 estimators with the CPU reference
+           "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
+           "-I", str(ROOT / "include"), "-I", inc,
+           "-o", str(LIB_CUDA)] + [str(s) for s in src] + [
+           "-L", libdir, f"-l:{libname}", "-Xlinker", f"-rpath={libdir}", "-lcudart"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    out = _run(cmd)
+    if verbose:
+        print(out)
+    return LIB_CUDA
+
+
+def build_host(force: bool = False) -> Path:
+    src = sorted((ROOT / "blastamr_b200" / "host").glob("*.cpp"))
+    hdr = sorted((ROOT / "blastamr_b200" / "host").glob("*.H")) + sorted((ROOT / "include").glob("*.h"))
+    if not src:
+        return LIB_HOST
+    if not force and _newer(LIB_HOST, src + hdr + [LIB_CUDA]):
+        return LIB_HOST
+    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", str(ROOT / "include"),
+          "-o", str(LIB_HOST)] + [str(s) for s in src] +
+         ["-L", str(LIB_CUDA.parent), "-l:libamr_b200.so", f"-Wl,-rpath,{LIB_CUDA.parent}"])
+    return LIB_HOST
+
+
+def build_all(force: bool = False):
+    build_mesh(force)
+    build_cuda(force)
+    build_host(force)
+    if ORACLE_DIR.exists():
+        build_oracle(force)
+        ref_mk = ORACLE_DIR / "build_ref.sh"
+        if ref_mk.exists() and Path("/root/reference").exists():
+            subprocess.run(["bash", str(ref_mk)], check=False)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)
+    print("built:", LIB_MESH, LIB_CUDA, LIB_ORACLE)

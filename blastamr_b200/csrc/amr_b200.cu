@@ -1,0 +1,820 @@
+// amr_b200.cu -- C-ABI of the B200-native AMR decision path (see include/amr_b200.h).
+//
+// Host-side orchestration only: argument staging, the sweep loops with their convergence test,
+// processor-patch halo swaps over NCCL, and the ascending-list compaction.  All arithmetic is in
+// kernels.cuh.  There is no CPU code path: every entry point needs a live CUDA context.
+#include "common.cuh"
+#include "scan.cuh"
+#include "sell.cuh"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <new>
+
+// ============================================================================ context
+
+AMR_API int amr_ctx_create(int device, amr_ctx **out) {
+    if (!out) return AMR_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return AMR_ERR_CUDA;   // no CPU fallback by design
+    }
+    amr_ctx *ctx = new (std::nothrow) amr_ctx();
+    if (!ctx) return AMR_ERR_CUDA;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return AMR_ERR_CUDA;
+    }
+    cudaMalloc((void **)&ctx->dFlags, 16 * sizeof(int));
+    cudaMalloc((void **)&ctx->dCount, 4 * sizeof(int64_t));
+    cudaMallocHost((void **)&ctx->hFlags, 16 * sizeof(int));
+    cudaMallocHost((void **)&ctx->hCount, 4 * sizeof(int64_t));
+    if (!ctx->dFlags || !ctx->dCount || !ctx->hFlags || !ctx->hCount) { delete ctx; return AMR_ERR_CUDA; }
+    cudaMemset(ctx->dFlags, 0, 16 * sizeof(int));
+    cudaMemset(ctx->dCount, 0, 4 * sizeof(int64_t));
+    *out = ctx;
+    return AMR_OK;
+}
+
+static void freeMesh(amr_ctx *ctx) {
+    devFree(ctx, &ctx->owner); devFree(ctx, &ctx->neighbour); devFree(ctx, &ctx->bCoupled);
+    sellFree(ctx, ctx->cc); sellFree(ctx, ctx->pc);
+    devFree(ctx, &ctx->bndPoint);
+    devFree(ctx, &ctx->lvl); devFree(ctx, &ctx->lvl8); devFree(ctx, &ctx->parentIdx); devFree(ctx, &ctx->pointLevel);
+    devFree(ctx, &ctx->protCell);
+    devFree(ctx, &ctx->error); devFree(ctx, &ctx->refineCell);
+    devFree(ctx, &ctx->flagA); devFree(ctx, &ctx->flagB); devFree(ctx, &ctx->flagC); devFree(ctx, &ctx->lf);
+    devFree(ctx, &ctx->ghost8); devFree(ctx, &ctx->send8); devFree(ctx, &ctx->ghost64); devFree(ctx, &ctx->send64);
+    devFree(ctx, &ctx->tileCnt); devFree(ctx, &ctx->scanAux);
+    ctx->havePoints = ctx->haveLevels = ctx->haveHistory = false;
+    ctx->refineCellN = 0;
+    ctx->devBytes = 0;
+    for (auto &bf : ctx->arena) ctx->devBytes += (int64_t)bf.cap;
+}
+
+AMR_API int amr_ctx_destroy(amr_ctx *ctx) {
+    if (!ctx) return AMR_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    freeMesh(ctx);
+    for (auto &bf : ctx->arena) cudaFree(bf.p);
+    if (ctx->comm) ncclCommDestroy(ctx->comm);
+    cudaFree(ctx->dFlags); cudaFree(ctx->dCount);
+    cudaFreeHost(ctx->hFlags); cudaFreeHost(ctx->hCount);
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return AMR_OK;
+}
+
+AMR_API const char *amr_last_error(const amr_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+AMR_API int amr_set_stream(amr_ctx *ctx, void *s) {
+    if (!ctx) return AMR_ERR_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)s;
+    ctx->ownStream = false;
+    return AMR_OK;
+}
+
+AMR_API int amr_comm_unique_id(void *id128) {
+    if (!id128) return AMR_ERR_ARG;
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return AMR_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id128, &id, 128);
+    return AMR_OK;
+}
+
+AMR_API int amr_comm_init(amr_ctx *ctx, int nranks, int rank, const void *id128) {
+    if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return AMR_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NCK(ncclCommInitRank(&ctx->comm, nranks, id, rank));
+    ctx->nranks = nranks; ctx->rank = rank;
+    return AMR_OK;
+}
+
+AMR_API int64_t amr_launch_count(const amr_ctx *ctx) { return ctx ? ctx->launches : 0; }
+AMR_API int64_t amr_device_bytes(const amr_ctx *ctx) { return ctx ? ctx->devBytes : 0; }
+
+#define ENTER()                                                                               \
+    if (!ctx) return AMR_ERR_ARG;                                                             \
+    CK(cudaSetDevice(ctx->device));                                                           \
+    arenaReset(ctx);                                                                          \
+    ctx->err.clear()
+
+// ============================================================================ halo swaps
+
+// syncTools::swapBoundaryFaceList / syncFaceList payload exchange: for every processor patch send
+// my boundary-face values [patchStart-f, +size) and receive the neighbour's into the same range
+// of `recv` (processor patch pairs list their faces in the same order on both sides).
+static int haloExchange(amr_ctx *ctx, const void *send, void *recv, size_t elemBytes) {
+    if (ctx->nCoupled == 0) return AMR_OK;
+    if (!ctx->comm) FAIL(AMR_ERR_STATE, "mesh has processor patches but no communicator (amr_comm_init) and no host-side neighbour values");
+    NCK(ncclGroupStart());
+    for (const Patch &q : ctx->patches) {
+        if (q.type != AMR_PATCH_PROCESSOR || q.size == 0) continue;
+        size_t off = (size_t)(q.start - ctx->f) * elemBytes;
+        NCK(ncclSend((const char *)send + off, (size_t)q.size * elemBytes, ncclUint8, q.nbr, ctx->comm, ctx->stream));
+        NCK(ncclRecv((char *)recv + off, (size_t)q.size * elemBytes, ncclUint8, q.nbr, ctx->comm, ctx->stream));
+    }
+    NCK(ncclGroupEnd());
+    return AMR_OK;
+}
+
+// read the device flag (after an all-reduce over ranks when a communicator is attached):
+// the reduce(nChanged, sumOp) / returnReduce(bool, orOp) sites of the reference
+static int globalFlag(amr_ctx *ctx, int slot, int *value) {
+    if (ctx->comm && ctx->nranks > 1)
+        NCK(ncclAllReduce(ctx->dFlags + slot, ctx->dFlags + slot, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->hFlags + slot, ctx->dFlags + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *value = ctx->hFlags[slot];
+    return AMR_OK;
+}
+static int globalSum(amr_ctx *ctx, int slot, int64_t *value) {
+    if (ctx->comm && ctx->nranks > 1)
+        NCK(ncclAllReduce(ctx->dCount + slot, ctx->dCount + slot, 1, ncclInt64, ncclSum, ctx->comm, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->hCount + slot, ctx->dCount + slot, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *value = ctx->hCount[slot];
+    return AMR_OK;
+}
+
+// ============================================================================ mesh state
+
+AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t p, const int32_t *owner,
+                         const int32_t *neighbour, int npatch, const int32_t *patchStart, const int32_t *patchSize,
+                         const int32_t *patchType, const int32_t *patchNbrRank) {
+    ENTER();
+    if (n < 0 || f < 0 || b < 0 || p < 0 || !owner || (f > 0 && !neighbour) || npatch < 0) FAIL(AMR_ERR_ARG, "amr_mesh_set: bad sizes/pointers");
+    if (n >= ((int64_t)1 << 31) - 2 - b) FAIL(AMR_ERR_ARG, "amr_mesh_set: label overflow (n + b must fit int32)");
+    CK(cudaStreamSynchronize(ctx->stream));
+    freeMesh(ctx);
+    ctx->n = n; ctx->f = f; ctx->b = b; ctx->p = p;
+    ctx->patches.clear();
+    std::vector<u8> coupled((size_t)(b > 0 ? b : 1), 0);
+    ctx->nCoupled = 0;
+    for (int i = 0; i < npatch; i++) {
+        Patch q{patchStart[i], patchSize[i], patchType ? patchType[i] : 0, patchNbrRank ? patchNbrRank[i] : -1};
+        if (q.size < 0 || q.start < f || (int64_t)q.start + q.size > f + b) FAIL(AMR_ERR_ARG, "amr_mesh_set: patch range outside boundary faces");
+        if (q.type == AMR_PATCH_PROCESSOR) {
+            for (int32_t k = 0; k < q.size; k++) coupled[(size_t)(q.start - f + k)] = 1;
+            ctx->nCoupled += q.size;
+        }
+        ctx->patches.push_back(q);
+    }
+    TRY(devAlloc(ctx, &ctx->owner, f + b));
+    TRY(devAlloc(ctx, &ctx->neighbour, f));
+    TRY(devAlloc(ctx, &ctx->bCoupled, b));
+    CK(cudaMemcpyAsync(ctx->owner, owner, (size_t)(f + b) * 4, cudaMemcpyDefault, ctx->stream));
+    if (f) CK(cudaMemcpyAsync(ctx->neighbour, neighbour, (size_t)f * 4, cudaMemcpyDefault, ctx->stream));
+    if (b) CK(cudaMemcpyAsync(ctx->bCoupled, coupled.data(), (size_t)b, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    TRY(sellBuildCellCells(ctx));
+    int64_t m = std::max(n, p);
+    TRY(devAlloc(ctx, &ctx->flagA, m + 16)); TRY(devAlloc(ctx, &ctx->flagB, m + 16)); TRY(devAlloc(ctx, &ctx->flagC, m + 16));
+    TRY(devAlloc(ctx, &ctx->lf, n + 16));
+    TRY(devAlloc(ctx, &ctx->error, n));
+    TRY(devAlloc(ctx, &ctx->refineCell, n + 16));
+    TRY(devAlloc(ctx, &ctx->ghost8, b + 16)); TRY(devAlloc(ctx, &ctx->send8, b + 16));
+    TRY(devAlloc(ctx, &ctx->ghost64, b + 2)); TRY(devAlloc(ctx, &ctx->send64, b + 2));
+    ctx->tileCap = (m + kTile - 1) / kTile + 8;
+    TRY(devAlloc(ctx, &ctx->tileCnt, ctx->tileCap));
+    ctx->scanAuxCap = 2 * (ctx->tileCap / kScanTile + 1024);
+    TRY(devAlloc(ctx, &ctx->scanAux, ctx->scanAuxCap));
+    CK(cudaMemsetAsync(ctx->refineCell, 0, (size_t)n + 16, ctx->stream));
+    CK(cudaMemsetAsync(ctx->ghost8, 0, (size_t)b + 16, ctx->stream));
+    CK(cudaMemsetAsync(ctx->ghost64, 0, (size_t)(b + 2) * 8, ctx->stream));
+    ctx->refineCellN = n;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMR_OK;
+}
+
+AMR_API int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_t *pcCells, const uint8_t *bndPoint) {
+    ENTER();
+    if (ctx->n == 0 && ctx->p == 0) FAIL(AMR_ERR_STATE, "amr_mesh_set_points: call amr_mesh_set first");
+    if (!pcOff || !bndPoint) FAIL(AMR_ERR_ARG, "amr_mesh_set_points: null pointer");
+    int64_t p = ctx->p;
+    const int32_t *dOff = nullptr, *dIdx = nullptr;
+    TRY(stageIn(ctx, pcOff, p + 1, &dOff));
+    int32_t nnz = 0;
+    CK(cudaMemcpyAsync(&nnz, dOff + p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (nnz < 0 || (nnz > 0 && !pcCells)) FAIL(AMR_ERR_ARG, "amr_mesh_set_points: bad pointCells CSR");
+    TRY(stageIn(ctx, pcCells, nnz, &dIdx));
+    TRY(sellBuildFromCsr(ctx, ctx->pc, p, dOff, dIdx));
+    devFree(ctx, &ctx->bndPoint);
+    TRY(devAlloc(ctx, &ctx->bndPoint, p));
+    if (p) CK(cudaMemcpyAsync(ctx->bndPoint, bndPoint, (size_t)p, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->havePoints = true;
+    return AMR_OK;
+}
+
+AMR_API int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t *pointLevel, const int32_t *visibleCells,
+                           const int32_t *splitParent, int64_t nSplit) {
+    ENTER();
+    if (!cellLevel) FAIL(AMR_ERR_ARG, "amr_levels_set: cellLevel is null");
+    int64_t n = ctx->n, p = ctx->p;
+    if (!ctx->lvl) { TRY(devAlloc(ctx, &ctx->lvl, n)); TRY(devAlloc(ctx, &ctx->lvl8, n + 16)); TRY(devAlloc(ctx, &ctx->parentIdx, n)); }
+    if (n) CK(cudaMemcpyAsync(ctx->lvl, cellLevel, (size_t)n * 4, cudaMemcpyDefault, ctx->stream));
+    if (n) LAUNCH(k_lvl_to_u8, gridFor(n), kThreads, n, ctx->lvl, ctx->lvl8);
+    if (pointLevel && p) {
+        if (!ctx->pointLevel) TRY(devAlloc(ctx, &ctx->pointLevel, p));
+        CK(cudaMemcpyAsync(ctx->pointLevel, pointLevel, (size_t)p * 4, cudaMemcpyDefault, ctx->stream));
+    }
+    ctx->haveHistory = false;
+    if (visibleCells) {
+        const int32_t *dVis = nullptr, *dPar = nullptr;
+        TRY(stageIn(ctx, visibleCells, n, &dVis));
+        TRY(stageIn(ctx, splitParent, nSplit, &dPar));
+        if (nSplit > 0 && !dPar) FAIL(AMR_ERR_ARG, "amr_levels_set: splitParent is null");
+        if (n) LAUNCH(k_parent_index, gridFor(n), kThreads, n, dVis, dPar, nSplit, ctx->parentIdx);
+        ctx->haveHistory = true;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->haveLevels = true;
+    return AMR_OK;
+}
+
+AMR_API int amr_protected_cells_set(amr_ctx *ctx, const uint8_t *protectedCell) {
+    ENTER();
+    if (!protectedCell) { devFree(ctx, &ctx->protCell); return AMR_OK; }
+    if (!ctx->protCell) TRY(devAlloc(ctx, &ctx->protCell, ctx->n + 16));
+    if (ctx->n) CK(cudaMemcpyAsync(ctx->protCell, protectedCell, (size_t)ctx->n, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMR_OK;
+}
+
+// ============================================================================ stage 1
+
+static Thresholds mkThr(const double *t) {
+    Thresholds r{0, 0, 0, 0};
+    if (t) { r.lowerRefine = t[0]; r.upperRefine = t[1]; r.lowerUnrefine = t[2]; r.upperUnrefine = t[3]; }
+    return r;
+}
+
+AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *nbrValues, double p0, double p1, int scale,
+                         const double *thr, double *errorOut) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_estimate: mesh not set");
+    if (!x) FAIL(AMR_ERR_ARG, "amr_estimate: x is null");
+    if (scale && !thr) FAIL(AMR_ERR_ARG, "amr_estimate: scale requested without thresholds");
+    const int64_t n = ctx->n, b = ctx->b;
+    const double *dx = nullptr;
+    double *dErr = nullptr;
+    TRY(stageIn(ctx, x, n, &dx));
+    TRY(stageOut(ctx, errorOut, n, &dErr));
+    double *target = ctx->error;   // the resident copy is always written; errorOut mirrors it
+    Thresholds t = mkThr(thr);
+    if (n > 0) {
+        if (kind == AMR_EST_FIELD_VALUE) {
+            if (scale) LAUNCH((k_pointwise<true, true>), gridFor(n), kThreads, n, dx, t, target);
+            else LAUNCH((k_pointwise<true, false>), gridFor(n), kThreads, n, dx, t, target);
+        } else if (kind == AMR_EST_DELTA || kind == AMR_EST_SCALED_DELTA || kind == AMR_EST_CODED_DELTA) {
+            const double *ghost = nullptr;
+            if (ctx->nCoupled > 0) {
+                if (nbrValues) TRY(stageIn(ctx, nbrValues, b, &ghost));
+                else {
+                    LAUNCH(k_pack_f64, gridFor(b), kThreads, b, ctx->owner + ctx->f, dx, ctx->send64);
+                    TRY(haloExchange(ctx, ctx->send64, ctx->ghost64, 8));
+                    ghost = ctx->ghost64;
+                }
+            }
+            const int32_t *so = ctx->cc.sliceOff, *col = ctx->cc.col;
+#define EST(K)                                                                                                   \
+    do {                                                                                                         \
+        if (scale) LAUNCH((k_estimate<K, true>), gridFor(n), kThreads, n, so, col, dx, ghost, p0, p1, t, target); \
+        else LAUNCH((k_estimate<K, false>), gridFor(n), kThreads, n, so, col, dx, ghost, p0, p1, t, target);      \
+    } while (0)
+            if (kind == AMR_EST_DELTA) EST(0);
+            else if (kind == AMR_EST_SCALED_DELTA) EST(1);
+            else EST(4);
+#undef EST
+        } else {
+            FAIL(AMR_ERR_ARG, "amr_estimate: estimator kind not available on the device path");
+        }
+        if (dErr) CK(cudaMemcpyAsync(dErr, target, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_normalize(amr_ctx *ctx, double lowerRefine, double upperRefine, double lowerUnrefine, double upperUnrefine,
+                          double *errorInOut) {
+    ENTER();
+    const int64_t n = ctx->n;
+    double *dE = nullptr;
+    TRY(stageInOut(ctx, errorInOut, n, &dE));
+    double *e = dE ? dE : ctx->error;
+    if (!e) FAIL(AMR_ERR_STATE, "amr_normalize: no error field");
+    Thresholds t{lowerRefine, upperRefine, lowerUnrefine, upperUnrefine};
+    if (n) LAUNCH((k_pointwise<false, true>), gridFor(n), kThreads, n, e, t, e);
+    if (dE && n && dE != ctx->error) CK(cudaMemcpyAsync(ctx->error, dE, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+// one face-layer growth of `cur` (n flags) with ping-pong buffer `tmp`; src == cur.  Returns the
+// buffer holding the result in *res.
+static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res) {
+    const int64_t n = ctx->n, b = ctx->b;
+    if (ctx->nCoupled > 0) {
+        LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, src, ctx->send8);
+        TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
+    }
+    LAUNCH(k_extend, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, cur, src, ctx->ghost8, tmp);
+    *res = tmp;
+    return AMR_OK;
+}
+
+AMR_API int amr_protect_patches(amr_ctx *ctx, const int32_t *patchIds, int nPatchIds, int nLayers, double *errorInOut,
+                                int64_t *nProtected) {
+    ENTER();
+    const int64_t n = ctx->n;
+    if (nProtected) *nProtected = 0;
+    if (nPatchIds == 0) return AMR_OK;   // errorEstimator.C:331-334
+    if (!patchIds) FAIL(AMR_ERR_ARG, "amr_protect_patches: patchIds is null");
+    double *dE = nullptr;
+    TRY(stageInOut(ctx, errorInOut, n, &dE));
+    double *e = dE ? dE : ctx->error;
+    u8 *cur = ctx->flagA, *tmp = ctx->flagB;
+    CK(cudaMemsetAsync(cur, 0, (size_t)n, ctx->stream));
+    for (int k = 0; k < nPatchIds; k++) {
+        int q = patchIds[k];
+        if (q < 0 || q >= (int)ctx->patches.size()) FAIL(AMR_ERR_ARG, "amr_protect_patches: patch id out of range");
+        const Patch &pp = ctx->patches[q];
+        if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)1);
+    }
+    for (int i = 0; i < nLayers; i++) {
+        u8 *res;
+        TRY(extendLayer(ctx, cur, cur, tmp, &res));
+        std::swap(cur, tmp);
+    }
+    CK(cudaMemsetAsync(ctx->dCount, 0, sizeof(int64_t), ctx->stream));
+    if (n) LAUNCH(k_zero_protected, gridFor(n), kThreads, n, cur, e, (unsigned long long *)ctx->dCount);
+    if (dE && n && dE != ctx->error) CK(cudaMemcpyAsync(ctx->error, dE, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->hCount, ctx->dCount, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaGetLastError());
+    TRY(flushOuts(ctx));
+    if (nProtected) *nProtected = ctx->hCount[0];
+    return AMR_OK;
+}
+
+// ============================================================================ stages 2+3
+
+// copy an ascending list (device) with a device-side count to a host or device destination
+static int emitList(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *userOut, int64_t *nOut) {
+    int32_t *dList = nullptr;
+    bool hostOut = userOut && !isDevicePtr(userOut);
+    if (userOut) {
+        if (hostOut) { void *q; TRY(arenaAlloc(ctx, &q, (size_t)(N > 0 ? N : 1) * 4)); dList = (int32_t *)q; }
+        else dList = userOut;
+    }
+    int32_t *dTotal = nullptr;
+    TRY(compactFlags(ctx, flags, N, dList, &dTotal));
+    if (nOut || hostOut) {
+        int32_t total = 0;
+        CK(cudaMemcpyAsync(ctx->hFlags + 8, dTotal, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        total = ctx->hFlags[8];
+        if (nOut) *nOut = total;
+        if (hostOut && total > 0) CK(cudaMemcpyAsync(userOut, dList, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return AMR_OK;
+}
+
+// hexRef::consistentRefinement loop (hexRef.C:1421-1437) on set/lf
+static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOut) {
+    const int64_t n = ctx->n, b = ctx->b;
+    int sweeps = 0;
+    while (true) {
+        CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(int), ctx->stream));
+        if (ctx->nCoupled > 0) {
+            LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, lf, ctx->send8);
+            TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
+        }
+        if (n) {
+            if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
+            else LAUNCH(k_refine_sweep_min, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
+        }
+        sweeps++;
+        int changed = 0;
+        TRY(globalFlag(ctx, 0, &changed));
+        if (!changed) break;
+        if (sweeps > 100000) FAIL(AMR_ERR_INVARIANT, "2:1 sweeps did not converge");
+    }
+    if (sweepsOut) *sweepsOut = sweeps;
+    return AMR_OK;
+}
+
+// fvMeshHexRefiner::calculateProtectedCells (fvMeshHexRefiner.C:60-179): closure of protectedCell_
+// over faces towards finer neighbours.  Uses the extend kernel on a source mask that is rebuilt
+// each round: src[q] = unrefineable[q] restricted to "neighbour is finer", which needs the levels
+// of both sides -> dedicated kernel.
+__global__ void __launch_bounds__(kThreads)
+k_protected_spread(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+                   const u8 *__restrict__ lvl8, u8 *__restrict__ u, const u8 *__restrict__ ghostU,
+                   const u8 *__restrict__ ghostLvl, int *changed) {
+    // cell c becomes unrefineable when a face neighbour q is unrefineable and level[c] > level[q]
+    // (seedFace rule, fvMeshHexRefiner.C:101-128, then both cells of a seed face are set :137-170;
+    // the coarser one already is)
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int flip = 0;
+    if (c < n && !u[c]) {
+        const int32_t base = sliceOff[c >> 5];
+        const int w = sliceOff[(c >> 5) + 1] - base;
+        const int32_t *row = col + ((size_t)base << 5) + (c & 31);
+        const int mine = lvl8[c];
+        for (int j = 0; j < w; j++) {
+            int32_t q = row[(size_t)j << 5];
+            if (q == (int32_t)c) continue;
+            int uq, lq;
+            if (q < n) { uq = u[q]; lq = lvl8[q]; } else { uq = ghostU[q - n]; lq = ghostLvl[q - n]; }
+            if (uq && mine > lq) { flip = 1; break; }
+        }
+        if (flip) u[c] = 1;
+    }
+    if (__syncthreads_or(flip) && threadIdx.x == 0) *changed = 1;
+}
+
+static int calcProtected(amr_ctx *ctx, u8 *unrefineable, bool *have) {
+    const int64_t n = ctx->n, b = ctx->b;
+    // returnReduce(protectedCell_.size(), sumOp) == 0 -> empty list (fvMeshHexRefiner.C:65-69)
+    CK(cudaMemsetAsync(ctx->dFlags + 2, 0, sizeof(int), ctx->stream));
+    if (ctx->protCell) { int one = 1; CK(cudaMemcpyAsync(ctx->dFlags + 2, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); }
+    int any = 0;
+    TRY(globalFlag(ctx, 2, &any));
+    *have = any != 0;
+    if (!any) return AMR_OK;
+    if (ctx->protCell) CK(cudaMemcpyAsync(unrefineable, ctx->protCell, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    else CK(cudaMemsetAsync(unrefineable, 0, (size_t)n, ctx->stream));
+    u8 *ghostLvl = ctx->flagC;   // [b] fits: flagC has max(n,p) >= ... guard below
+    if (ctx->nCoupled > 0) {
+        if (b > std::max(ctx->n, ctx->p)) FAIL(AMR_ERR_STATE, "scratch too small for boundary levels");
+        LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, ctx->lvl8, ctx->send8);
+        TRY(haloExchange(ctx, ctx->send8, ghostLvl, 1));
+    }
+    while (true) {
+        CK(cudaMemsetAsync(ctx->dFlags + 1, 0, sizeof(int), ctx->stream));
+        if (ctx->nCoupled > 0) {
+            LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, unrefineable, ctx->send8);
+            TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
+        }
+        if (n) LAUNCH(k_protected_spread, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, unrefineable, ctx->ghost8, ghostLvl, ctx->dFlags + 1);
+        int changed = 0;
+        TRY(globalFlag(ctx, 1, &changed));
+        if (!changed) break;
+    }
+    return AMR_OK;
+}
+
+AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, double hi, const int32_t *maxCellLevel,
+                              int32_t maxLevelUniform, int nBufferLayers, const int32_t *protectedPatchIds,
+                              int nProtectedPatches, int64_t maxCells, int refinerKind, uint8_t *refineCellOut,
+                              int32_t *cellsOut, int64_t *nOut, int *sweepsOut) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_select_refine: mesh not set");
+    if (!ctx->haveLevels) FAIL(AMR_ERR_STATE, "amr_select_refine: levels not set");
+    if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D)
+        FAIL(AMR_ERR_ARG, "amr_select_refine: only the hexRefiner sweeps are on the device path in this round");
+    if (nProtectedPatches > 0 && !protectedPatchIds) FAIL(AMR_ERR_ARG, "amr_select_refine: protectedPatchIds is null");
+    const int64_t n = ctx->n;
+    const double *dErr = nullptr;
+    const int32_t *dMax = nullptr;
+    TRY(stageIn(ctx, error, n, &dErr));
+    if (!dErr) dErr = ctx->error;
+    TRY(stageIn(ctx, maxCellLevel, n, &dMax));
+    u8 *dRcOut = nullptr;
+    TRY(stageOut(ctx, refineCellOut, n, &dRcOut));
+
+    u8 *cur = ctx->flagA, *tmp = ctx->flagB, *src0 = ctx->flagC;
+    // M1 (+ source mask of the first forced layer)
+    if (n) LAUNCH(k_candidates, gridFor(n), kThreads, n, dErr, lo, hi, ctx->lvl, dMax, maxLevelUniform, cur,
+                  nBufferLayers > 0 ? src0 : (u8 *)nullptr);
+    // M2: extendMarkedCells(refineCell, maxRefinement, i == 0, force = true), fvMeshHexRefiner.C:1509-1512
+    for (int i = 0; i < nBufferLayers; i++) {
+        u8 *res;
+        TRY(extendLayer(ctx, cur, i == 0 ? src0 : cur, tmp, &res));
+        std::swap(cur, tmp);
+    }
+    // M3: protections, fvMeshHexRefiner.C:1514-1533
+    for (int k = 0; k < nProtectedPatches; k++) {
+        int q = protectedPatchIds[k];
+        if (q < 0 || q >= (int)ctx->patches.size()) FAIL(AMR_ERR_ARG, "amr_select_refine: patch id out of range");
+        const Patch &pp = ctx->patches[q];
+        if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)0);
+    }
+    if (ctx->protCell && n) LAUNCH(k_masked_set, gridFor(n), kThreads, n, ctx->protCell, cur, (u8)0);
+    // keep the marking (the reference's refineCell) resident for the unrefinement stage
+    if (n) CK(cudaMemcpyAsync(ctx->refineCell, cur, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->refineCellN = n;
+    if (dRcOut && n) CK(cudaMemcpyAsync(dRcOut, cur, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+
+    // M4/M5: selectRefineCells, fvMeshHexRefiner.C:306-391
+    u8 *set = tmp;                    // the other ping-pong buffer is free now
+    u8 *unref = src0;                 // so is the layer-0 source mask
+    bool haveU = false;
+    TRY(calcProtected(ctx, unref, &haveU));
+    // nTotalCells / nCandidates reductions only matter when the maxCells quota can bind
+    int64_t nTotal = n;
+    if (ctx->comm && ctx->nranks > 1) {
+        CK(cudaMemcpyAsync(ctx->dCount + 1, &nTotal, 8, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(globalSum(ctx, 1, &nTotal));
+    }
+    int64_t nTotToRefine = (maxCells - nTotal) / 7;
+    bool quota = false;
+    if (nTotal >= nTotToRefine) {     // otherwise nCandidates <= nTotal < nTotToRefine always holds
+        CK(cudaMemsetAsync(ctx->dCount, 0, 8, ctx->stream));
+        if (n) LAUNCH(k_count_flags, gridFor(n), kThreads, n, cur, (unsigned long long *)ctx->dCount);
+        int64_t nCand = 0;
+        TRY(globalSum(ctx, 0, &nCand));
+        quota = !(nCand < nTotToRefine);
+    }
+    if (!quota) {
+        if (n) LAUNCH(k_select_filter, gridFor(n), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, -1, set, ctx->lf);
+    } else {
+        // level-by-level truncation, fvMeshHexRefiner.C:346-374; gMax(maxRefinement)
+        int32_t maxLevel = maxLevelUniform;
+        if (dMax) {
+            std::vector<int32_t> h((size_t)n);
+            CK(cudaMemcpyAsync(h.data(), dMax, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            maxLevel = n ? *std::max_element(h.begin(), h.end()) : 0;
+        }
+        if (ctx->comm && ctx->nranks > 1) {
+            CK(cudaMemcpyAsync(ctx->dFlags + 3, &maxLevel, 4, cudaMemcpyHostToDevice, ctx->stream));
+            int g = 0; TRY(globalFlag(ctx, 3, &g)); maxLevel = g;
+        }
+        CK(cudaMemsetAsync(set, 0, (size_t)n, ctx->stream));
+        for (int32_t level = 0; level < maxLevel; level++) {
+            if (n) LAUNCH(k_select_filter, gridFor(n), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, level, set, ctx->lf);
+            CK(cudaMemsetAsync(ctx->dCount, 0, 8, ctx->stream));
+            if (n) LAUNCH(k_count_flags, gridFor(n), kThreads, n, set, (unsigned long long *)ctx->dCount);
+            int64_t tot = 0;
+            TRY(globalSum(ctx, 0, &tot));
+            if (tot > nTotToRefine) break;
+        }
+        if (maxLevel <= 0 && n) LAUNCH(k_select_filter, gridFor(n), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, 1 << 20, set, ctx->lf);
+    }
+    // B1: hexRef::consistentRefinement(candidates, true)
+    TRY(refineSweeps(ctx, 1, set, ctx->lf, sweepsOut));
+    TRY(emitList(ctx, set, n, cellsOut, nOut));
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_consistent_refinement(amr_ctx *ctx, const int32_t *cellsIn, int64_t nIn, int maxSet, int32_t *cellsOut,
+                                      int64_t *nOut, int *sweepsOut) {
+    ENTER();
+    if (!ctx->haveLevels) FAIL(AMR_ERR_STATE, "amr_consistent_refinement: levels not set");
+    const int64_t n = ctx->n;
+    const int32_t *dIn = nullptr;
+    TRY(stageIn(ctx, cellsIn, nIn, &dIn));
+    u8 *set = ctx->flagA;
+    CK(cudaMemsetAsync(set, 0, (size_t)n, ctx->stream));
+    if (nIn > 0) LAUNCH(k_list_to_flags, gridFor(nIn), kThreads, nIn, dIn, set);
+    if (n) LAUNCH(k_select_filter, gridFor(n), kThreads, n, set, ctx->lvl, (const label *)nullptr, (label)0x7fffffff, (const u8 *)nullptr, -1, set, ctx->lf);
+    TRY(refineSweeps(ctx, maxSet, set, ctx->lf, sweepsOut));
+    TRY(emitList(ctx, set, n, cellsOut, nOut));
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nNew, const int32_t *cellMap, const int32_t *reverseCellMap,
+                                  const uint8_t *refineCell, uint8_t *newRefineCellOut) {
+    ENTER();
+    if (!cellMap || !reverseCellMap) FAIL(AMR_ERR_ARG, "amr_remap_refine_cell: null map");
+    // Called after amr_mesh_set of the NEW mesh or before it: the old marking is either passed in
+    // or the resident one (which amr_mesh_set preserves in `pendingFlags`) -- to stay simple the
+    // call must come BEFORE amr_mesh_set of the new mesh when the resident marking is used.
+    const int64_t nOld = ctx->refineCellN;
+    const int32_t *dMap = nullptr, *dRev = nullptr;
+    const u8 *dOld = nullptr;
+    TRY(stageIn(ctx, cellMap, nNew, &dMap));
+    TRY(stageIn(ctx, reverseCellMap, nOld, &dRev));
+    TRY(stageIn(ctx, refineCell, nOld, &dOld));
+    if (!dOld) dOld = ctx->refineCell;
+    if (!dOld) FAIL(AMR_ERR_STATE, "amr_remap_refine_cell: no marking");
+    u8 *dNew = nullptr;
+    CK(cudaMalloc((void **)&dNew, (size_t)nNew + 16));
+    if (nNew) LAUNCH(k_remap_refine_cell, gridFor(nNew), kThreads, nNew, dMap, dRev, dOld, dNew);
+    if (newRefineCellOut && nNew) CK(cudaMemcpyAsync(newRefineCellOut, dNew, (size_t)nNew, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->refineCell) { cudaFree(ctx->refineCell); ctx->devBytes -= ctx->refineCellN + 16; }
+    ctx->refineCell = dNew; ctx->refineCellN = nNew; ctx->devBytes += nNew + 16;
+    CK(cudaGetLastError());
+    return AMR_OK;
+}
+
+// hexRef3D::consistentUnrefinement loop (hexRef3D.C:1758-1927) on point flags
+static int unrefineSweeps(amr_ctx *ctx, u8 *pflag, int *sweepsOut) {
+    const int64_t n = ctx->n, b = ctx->b, p = ctx->p;
+    u8 *uc = ctx->flagB;     // unrefineCell
+    u8 *lfm = ctx->lf;
+    int sweeps = 0;
+    while (true) {
+        CK(cudaMemsetAsync(uc, 0, (size_t)n, ctx->stream));
+        if (p) LAUNCH(k_points_to_cells, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, pflag, uc);
+        if (n) LAUNCH(k_level_minus, gridFor(n), kThreads, n, ctx->lvl8, uc, lfm);
+        CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(int), ctx->stream));
+        if (ctx->nCoupled > 0) {
+            LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, lfm, ctx->send8);
+            TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
+        }
+        if (n) LAUNCH(k_unrefine_sweep, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lfm, uc, ctx->ghost8, ctx->dFlags);
+        sweeps++;
+        int changed = 0;
+        TRY(globalFlag(ctx, 0, &changed));
+        if (!changed) break;
+        if (p) LAUNCH(k_knock_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, pflag, uc);
+        if (sweeps > 100000) FAIL(AMR_ERR_INVARIANT, "unrefinement sweeps did not converge");
+    }
+    if (sweepsOut) *sweepsOut = sweeps;
+    return AMR_OK;
+}
+
+AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefineLevel, uint8_t *refineCellInOut,
+                                int nBufferLayers, const int32_t *protectedPatchIds, int nProtectedPatches,
+                                int refinerKind, int32_t *elemsOut, int64_t *nOut, int *sweepsOut) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_select_unrefine: mesh not set");
+    if (!ctx->havePoints) FAIL(AMR_ERR_STATE, "amr_select_unrefine: point addressing not set (amr_mesh_set_points)");
+    if (!ctx->haveLevels || !ctx->haveHistory) FAIL(AMR_ERR_STATE, "amr_select_unrefine: levels/history not set");
+    if (refinerKind != AMR_REFINER_HEX3D) FAIL(AMR_ERR_ARG, "amr_select_unrefine: only hexRef3D is on the device path in this round");
+    if (nProtectedPatches > 0 && !protectedPatchIds) FAIL(AMR_ERR_ARG, "amr_select_unrefine: protectedPatchIds is null");
+    const int64_t n = ctx->n, p = ctx->p;
+    const double *dErr = nullptr;
+    TRY(stageIn(ctx, error, n, &dErr));
+    if (!dErr) dErr = ctx->error;
+    u8 *dRc = nullptr;
+    TRY(stageInOut(ctx, refineCellInOut, n, &dRc));
+    if (!dRc) {
+        if (ctx->refineCellN != n) FAIL(AMR_ERR_STATE, "amr_select_unrefine: resident marking has the wrong size (amr_remap_refine_cell after the topology change)");
+        dRc = ctx->refineCell;
+    }
+    // nUnrefinementBufferLayers x extendMarkedCellsAcrossFaces, fvMeshHexRefiner.C:1595-1598
+    u8 *cur = ctx->flagA, *tmp = ctx->flagB;
+    if (n) CK(cudaMemcpyAsync(cur, dRc, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    for (int i = 0; i < nBufferLayers; i++) {
+        u8 *res;
+        TRY(extendLayer(ctx, cur, cur, tmp, &res));
+        std::swap(cur, tmp);
+    }
+    // protections, fvMeshHexRefiner.C:1600-1622
+    if (ctx->protCell && n) LAUNCH(k_masked_set, gridFor(n), kThreads, n, ctx->protCell, cur, (u8)1);
+    for (int k = 0; k < nProtectedPatches; k++) {
+        int q = protectedPatchIds[k];
+        if (q < 0 || q >= (int)ctx->patches.size()) FAIL(AMR_ERR_ARG, "amr_select_unrefine: patch id out of range");
+        const Patch &pp = ctx->patches[q];
+        if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)1);
+    }
+    if (n) CK(cudaMemcpyAsync(dRc, cur, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    // U1+U2+U3 fused: maxCellField + getSplitElems + filter
+    u8 *pflag = ctx->flagC;
+    if (p) LAUNCH(k_select_unrefine_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, ctx->pc.count, ctx->bndPoint,
+                  ctx->parentIdx, ctx->lvl8, dErr, unrefineLevel, dRc, (u8 *)nullptr, pflag);
+    // B3: consistentUnrefinement(list, false)   (cur/tmp are free again: flagA/flagB)
+    TRY(unrefineSweeps(ctx, pflag, sweepsOut));
+    TRY(emitList(ctx, pflag, p, elemsOut, nOut));
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_get_split_elems(amr_ctx *ctx, int refinerKind, int32_t *elemsOut, int64_t *nOut) {
+    ENTER();
+    if (!ctx->havePoints || !ctx->haveHistory) FAIL(AMR_ERR_STATE, "amr_get_split_elems: points/history not set");
+    if (refinerKind != AMR_REFINER_HEX3D) FAIL(AMR_ERR_ARG, "amr_get_split_elems: only hexRef3D");
+    const int64_t p = ctx->p;
+    u8 *pflag = ctx->flagC;
+    if (p) LAUNCH(k_select_unrefine_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, ctx->pc.count, ctx->bndPoint,
+                  ctx->parentIdx, ctx->lvl8, (const double *)nullptr, 0.0, (const u8 *)nullptr, pflag, (u8 *)nullptr);
+    TRY(emitList(ctx, pflag, p, elemsOut, nOut));
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_max_cell_field(amr_ctx *ctx, const double *vFld, double *pFld) {
+    ENTER();
+    if (!ctx->havePoints) FAIL(AMR_ERR_STATE, "amr_max_cell_field: point addressing not set");
+    if (!pFld) FAIL(AMR_ERR_ARG, "amr_max_cell_field: pFld is null");
+    const double *dV = nullptr;
+    double *dP = nullptr;
+    TRY(stageIn(ctx, vFld, ctx->n, &dV));
+    if (!dV) dV = ctx->error;
+    TRY(stageOut(ctx, pFld, ctx->p, &dP));
+    if (ctx->p) LAUNCH(k_max_cell_field, gridFor(ctx->p), kThreads, ctx->p, ctx->pc.sliceOff, ctx->pc.col, dV, dP);
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_check_levels(amr_ctx *ctx, const int32_t *cellLevel, int64_t *nBad) {
+    ENTER();
+    const int64_t n = ctx->n, b = ctx->b;
+    const int32_t *dL = nullptr;
+    TRY(stageIn(ctx, cellLevel, n, &dL));
+    if (!dL) dL = ctx->lvl;
+    if (!dL) FAIL(AMR_ERR_STATE, "amr_check_levels: no levels");
+    label *ghost = nullptr, *send = nullptr;
+    if (ctx->nCoupled > 0) {
+        void *q;
+        TRY(arenaAlloc(ctx, &q, (size_t)b * 4)); send = (label *)q;
+        TRY(arenaAlloc(ctx, &q, (size_t)b * 4)); ghost = (label *)q;
+        LAUNCH(k_pack_i32, gridFor(b), kThreads, b, ctx->owner + ctx->f, dL, send);
+        TRY(haloExchange(ctx, send, ghost, 4));
+    }
+    CK(cudaMemsetAsync(ctx->dCount, 0, 8, ctx->stream));
+    if (n) LAUNCH(k_check_levels, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, dL, ghost, (unsigned long long *)ctx->dCount);
+    CK(cudaMemcpyAsync(ctx->hCount, ctx->dCount, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (nBad) *nBad = ctx->hCount[0];
+    CK(cudaGetLastError());
+    if (ctx->hCount[0] > 0) FAIL(AMR_ERR_INVARIANT, "Celllevel does not satisfy 2:1 constraint (hexRef.C:2975)");
+    return AMR_OK;
+}
+
+// ============================================================================ stage 4
+
+AMR_API int amr_map_field(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nComp, const double *oldF,
+                          double *newF, int mode, const int32_t *reverseCellMap, const double *volOld) {
+    ENTER();
+    if (!cellMap || !oldF || !newF || nComp < 1) FAIL(AMR_ERR_ARG, "amr_map_field: null pointer / bad nComp");
+    const int32_t *dMap = nullptr;
+    const double *dOld = nullptr;
+    double *dNew = nullptr;
+    TRY(stageIn(ctx, cellMap, nNew, &dMap));
+    TRY(stageIn(ctx, oldF, nOld * nComp, &dOld));
+    TRY(stageOut(ctx, newF, nNew * nComp, &dNew));
+    int64_t items = nNew * nComp;
+    if (items > 0) {
+        switch (nComp) {
+        case 1: LAUNCH((k_map_field<1>), gridFor(items), kThreads, nNew, dMap, dOld, dNew); break;
+        case 3: LAUNCH((k_map_field<3>), gridFor(items), kThreads, nNew, dMap, dOld, dNew); break;
+        case 6: LAUNCH((k_map_field<6>), gridFor(items), kThreads, nNew, dMap, dOld, dNew); break;
+        case 9: LAUNCH((k_map_field<9>), gridFor(items), kThreads, nNew, dMap, dOld, dNew); break;
+        default: LAUNCH(k_map_field_n, gridFor(items), kThreads, nNew, nComp, dMap, dOld, dNew); break;
+        }
+    }
+    if (mode == AMR_MAP_CONSERVATIVE) {
+        if (!reverseCellMap || !volOld) FAIL(AMR_ERR_ARG, "amr_map_field: conservative mode needs reverseCellMap and volOld");
+        // merge lists are tiny compared with the field (8 cells per unrefined parent): build the CSR on the host
+        std::vector<int32_t> rev((size_t)nOld);
+        CK(cudaMemcpyAsync(rev.data(), reverseCellMap, (size_t)nOld * 4, cudaMemcpyDefault, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<int32_t> masters;
+        std::vector<int64_t> pairs;   // (master << 32) | old cell
+        std::vector<char> isMaster((size_t)(nNew > 0 ? nNew : 1), 0);
+        for (int64_t c = 0; c < nOld; c++) if (rev[c] < -1) isMaster[(size_t)(-rev[c] - 2)] = 1;
+        for (int64_t c = 0; c < nOld; c++) {
+            int64_t t = rev[c] < -1 ? -rev[c] - 2 : rev[c];
+            if (t >= 0 && isMaster[(size_t)t]) pairs.push_back((t << 32) | c);
+        }
+        std::sort(pairs.begin(), pairs.end());
+        std::vector<int32_t> off, idx;
+        for (size_t i = 0; i < pairs.size(); i++) {
+            int32_t m = (int32_t)(pairs[i] >> 32);
+            if (masters.empty() || masters.back() != m) { masters.push_back(m); off.push_back((int32_t)idx.size()); }
+            idx.push_back((int32_t)(pairs[i] & 0xffffffff));
+        }
+        off.push_back((int32_t)idx.size());
+        if (!masters.empty()) {
+            const int32_t *dM = nullptr, *dO = nullptr, *dI = nullptr;
+            const double *dV = nullptr;
+            TRY(stageIn(ctx, masters.data(), (int64_t)masters.size(), &dM));
+            TRY(stageIn(ctx, off.data(), (int64_t)off.size(), &dO));
+            TRY(stageIn(ctx, idx.data(), (int64_t)idx.size(), &dI));
+            TRY(stageIn(ctx, volOld, nOld, &dV));
+            int64_t it = (int64_t)masters.size() * nComp;
+            LAUNCH(k_map_conservative, gridFor(it), kThreads, (int64_t)masters.size(), dM, dO, dI, dV, nComp, dOld, dNew);
+            CK(cudaStreamSynchronize(ctx->stream));   // host vectors must outlive the staged copies
+        }
+    }
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_update_levels(amr_ctx *ctx, int64_t nNew, const int32_t *cellMap, const int32_t *oldLevel,
+                              const uint8_t *refinedOld, const uint8_t *unrefinedOld, int32_t *newLevel) {
+    ENTER();
+    if (!cellMap || !newLevel) FAIL(AMR_ERR_ARG, "amr_update_levels: null pointer");
+    const int64_t nOld = ctx->n;
+    const int32_t *dMap = nullptr, *dOldL = nullptr;
+    const u8 *dR = nullptr, *dU = nullptr;
+    int32_t *dNew = nullptr;
+    TRY(stageIn(ctx, cellMap, nNew, &dMap));
+    TRY(stageIn(ctx, oldLevel, nOld, &dOldL));
+    if (!dOldL) dOldL = ctx->lvl;
+    if (!dOldL) FAIL(AMR_ERR_STATE, "amr_update_levels: no levels");
+    TRY(stageIn(ctx, refinedOld, nOld, &dR));
+    TRY(stageIn(ctx, unrefinedOld, nOld, &dU));
+    TRY(stageOut(ctx, newLevel, nNew, &dNew));
+    if (nNew) LAUNCH(k_update_levels, gridFor(nNew), kThreads, nNew, dMap, dOldL, dR, dU, dNew);
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}

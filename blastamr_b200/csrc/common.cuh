@@ -1,0 +1,231 @@
+// common.cuh -- context, device buffers and launch helpers of libamr_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "amr_b200.h"
+
+typedef int32_t label;
+typedef uint8_t u8;
+
+#define AMR_API extern "C" __attribute__((visibility("default")))
+
+constexpr int kThreads = 256;           // CTA size of the cell/point kernels (8 warps)
+constexpr int kSlice = 32;              // SELL slice height = one warp
+constexpr double kSMALL = 1e-15;
+constexpr double kGREAT = 1e15;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Patch {
+    int32_t start, size, type, nbr;
+};
+
+// Sliced-ELL (SELL-32) adjacency: rows of one warp-slice are stored column-major so that
+// column j of 32 consecutive rows is one 128-byte line.  Entries beyond a row's length hold
+// `pad` (the row's own index for cell->cell, -1 for point->cell).
+struct Sell {
+    int64_t rows = 0;
+    int64_t slices = 0;
+    int64_t entries = 0;       // 32 * sum(width)
+    int32_t *sliceOff = nullptr;  // [slices+1], exclusive prefix of the slice widths
+    int32_t *col = nullptr;       // [entries]
+    u8 *count = nullptr;          // [rows] true row length (saturated at 255)
+};
+
+struct amr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = true;
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    std::string err;
+    int64_t launches = 0;
+    int64_t devBytes = 0;
+
+    // mesh
+    int64_t n = 0, f = 0, b = 0, p = 0;
+    label *owner = nullptr, *neighbour = nullptr;
+    std::vector<Patch> patches;
+    int64_t nCoupled = 0;
+    u8 *bCoupled = nullptr;    // [b] boundary face lies on a processor patch
+    Sell cc;                   // cell -> face-neighbour cells (+ ghost slots n + bface for coupled faces)
+    Sell pc;                   // point -> cells
+    bool havePoints = false;
+    u8 *bndPoint = nullptr;
+
+    // levels / history
+    bool haveLevels = false, haveHistory = false;
+    label *lvl = nullptr;      // [n] cellLevel
+    u8 *lvl8 = nullptr;        // [n] cellLevel as bytes (gather-friendly)
+    label *parentIdx = nullptr;// [n] history.parentIndex(c) or -1 (not visible / unrefined)
+    label *pointLevel = nullptr;
+    u8 *protCell = nullptr;    // [n] or null
+
+    // resident results
+    double *error = nullptr;   // [n]
+    u8 *refineCell = nullptr;  // [n] marking kept between the refine and unrefine stages
+    int64_t refineCellN = 0;
+
+    // scratch (sized at mesh_set)
+    u8 *flagA = nullptr, *flagB = nullptr;      // [max(n,p)]
+    u8 *flagC = nullptr;                        // [max(n,p)]
+    u8 *lf = nullptr;                           // [n] level +/- flag
+    u8 *ghost8 = nullptr, *send8 = nullptr;     // [b]
+    double *ghost64 = nullptr, *send64 = nullptr; // [b]
+    int32_t *tileCnt = nullptr;                 // compaction tile counters
+    int64_t tileCap = 0;
+    int32_t *scanAux = nullptr; int64_t scanAuxCap = 0;
+    int *dFlags = nullptr;                      // [16] device scalars (changed flags, counters)
+    int64_t *dCount = nullptr;                  // [4]
+    int *hFlags = nullptr;                      // pinned mirror
+    int64_t *hCount = nullptr;
+
+    // per-call staging arena (host<->device copies for host-pointer arguments)
+    std::vector<DevBuf> arena;
+    size_t arenaUsed = 0;       // within arena.back()
+    struct PendingOut { void *host; const void *dev; size_t bytes; };
+    std::vector<PendingOut> outs;
+};
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+            return AMR_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define NCK(call)                                                                             \
+    do {                                                                                      \
+        ncclResult_t r_ = (call);                                                             \
+        if (r_ != ncclSuccess) {                                                              \
+            ctx->err = std::string(#call) + ": " + ncclGetErrorString(r_);                    \
+            return AMR_ERR_NCCL;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define FAIL(code, msg)                                                                       \
+    do {                                                                                      \
+        ctx->err = (msg);                                                                     \
+        return (code);                                                                        \
+    } while (0)
+
+#define TRY(expr)                                                                             \
+    do {                                                                                      \
+        int rc_ = (expr);                                                                     \
+        if (rc_ != AMR_OK) return rc_;                                                        \
+    } while (0)
+
+// kernel launch with bookkeeping (gpu_launches of bench.py is this counter)
+#define LAUNCH(kern, grid, block, ...)                                                        \
+    do {                                                                                      \
+        kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                               \
+        ctx->launches++;                                                                      \
+    } while (0)
+
+static inline unsigned gridFor(int64_t items, int perBlock = kThreads) {
+    int64_t g = (items + perBlock - 1) / perBlock;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
+template <typename T>
+static int devAlloc(amr_ctx *ctx, T **ptr, int64_t count) {
+    size_t bytes = sizeof(T) * (size_t)(count > 0 ? count : 1);
+    CK(cudaMalloc((void **)ptr, bytes));
+    ctx->devBytes += (int64_t)bytes;
+    return AMR_OK;
+}
+template <typename T>
+static void devFree(amr_ctx *ctx, T **ptr) {
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    (void)ctx;
+}
+
+static inline bool isDevicePtr(const void *ptr) {
+    if (!ptr) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- staging arena ---------------------------------------------------------------------
+static void arenaReset(amr_ctx *ctx) {
+    if (ctx->arena.size() > 1) {
+        size_t total = 0;
+        for (auto &bf : ctx->arena) { total += bf.cap; cudaFree(bf.p); ctx->devBytes -= (int64_t)bf.cap; }
+        ctx->arena.clear();
+        DevBuf nb;
+        if (cudaMalloc(&nb.p, total) == cudaSuccess) { nb.cap = total; ctx->devBytes += (int64_t)total; ctx->arena.push_back(nb); }
+        else cudaGetLastError();
+    }
+    ctx->arenaUsed = 0;
+    ctx->outs.clear();
+}
+static int arenaAlloc(amr_ctx *ctx, void **out, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    if (ctx->arena.empty() || ctx->arenaUsed + bytes > ctx->arena.back().cap) {
+        DevBuf nb;
+        size_t cap = bytes > ((size_t)1 << 20) ? bytes : ((size_t)1 << 20);
+        CK(cudaMalloc(&nb.p, cap));
+        nb.cap = cap; ctx->devBytes += (int64_t)cap;
+        ctx->arena.push_back(nb);
+        ctx->arenaUsed = 0;
+    }
+    *out = (char *)ctx->arena.back().p + ctx->arenaUsed;
+    ctx->arenaUsed += bytes;
+    return AMR_OK;
+}
+// input: device pointer used as is, host pointer staged
+template <typename T>
+static int stageIn(amr_ctx *ctx, const T *ptr, int64_t count, const T **dev) {
+    if (!ptr) { *dev = nullptr; return AMR_OK; }
+    if (isDevicePtr(ptr)) { *dev = ptr; return AMR_OK; }
+    void *q;
+    TRY(arenaAlloc(ctx, &q, sizeof(T) * (size_t)(count > 0 ? count : 1)));
+    if (count > 0) CK(cudaMemcpyAsync(q, ptr, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = (const T *)q;
+    return AMR_OK;
+}
+// output: device pointer written directly, host pointer gets a staged buffer copied back by flushOuts
+template <typename T>
+static int stageOut(amr_ctx *ctx, T *ptr, int64_t count, T **dev) {
+    if (!ptr) { *dev = nullptr; return AMR_OK; }
+    if (isDevicePtr(ptr)) { *dev = ptr; return AMR_OK; }
+    void *q;
+    TRY(arenaAlloc(ctx, &q, sizeof(T) * (size_t)(count > 0 ? count : 1)));
+    *dev = (T *)q;
+    ctx->outs.push_back({(void *)ptr, q, sizeof(T) * (size_t)(count > 0 ? count : 0)});
+    return AMR_OK;
+}
+// in/out: staged copy in, copy back at flush
+template <typename T>
+static int stageInOut(amr_ctx *ctx, T *ptr, int64_t count, T **dev) {
+    if (!ptr) { *dev = nullptr; return AMR_OK; }
+    if (isDevicePtr(ptr)) { *dev = ptr; return AMR_OK; }
+    void *q;
+    TRY(arenaAlloc(ctx, &q, sizeof(T) * (size_t)(count > 0 ? count : 1)));
+    if (count > 0) CK(cudaMemcpyAsync(q, ptr, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = (T *)q;
+    ctx->outs.push_back({(void *)ptr, q, sizeof(T) * (size_t)(count > 0 ? count : 0)});
+    return AMR_OK;
+}
+// copy staged outputs back (optionally only the first `bytesOverride` bytes of the last one) and sync
+static int flushOuts(amr_ctx *ctx) {
+    for (auto &o : ctx->outs)
+        if (o.bytes) CK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->outs.clear();
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMR_OK;
+}

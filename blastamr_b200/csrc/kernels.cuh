@@ -1,0 +1,570 @@
+// kernels.cuh -- the hot kernels of the AMR decision path (sm_100a, HBM-bound gather work).
+//
+// Common shape: one thread per cell (or point), one warp per SELL-32 slice.  Column j of a
+// slice is one coalesced 128-byte load of neighbour labels; the per-neighbour gathers
+// (8-byte field values, 1-byte level/flag bytes) hit L1/L2 for any mesh numbering with
+// locality.  Up to 8 columns are loaded before the dependent gathers are issued so that each
+// thread keeps 8 independent requests in flight.  No floating-point atomics anywhere: every
+// cell reduces its own row (max / OR), which is order-independent and therefore bit-identical
+// to the reference's face loops.
+#pragma once
+#include "common.cuh"
+
+constexpr int kChunk = 8;   // SELL columns fetched per batch (memory-level parallelism per thread)
+
+struct Thresholds {
+    double lowerRefine, upperRefine, lowerUnrefine, upperUnrefine;
+};
+
+// errorEstimator::normalize, errorEstimator.C:204-228
+__device__ __forceinline__ double normalizeValue(double e, const Thresholds &t) {
+    if (e < t.lowerUnrefine || e > t.upperUnrefine) return -1.0;
+    if (e > t.lowerRefine && e < t.upperRefine) return 1.0;
+    return 0.0;
+}
+
+// Foam::max / Foam::min (a > b ? a : b) -- spelled out so NaN handling matches the host code
+__device__ __forceinline__ double fmaxFoam(double a, double b) { return (a > b) ? a : b; }
+__device__ __forceinline__ double fminFoam(double a, double b) { return (a < b) ? a : b; }
+
+// ------------------------------------------------------------------------------------------
+// STAGE 1  delta / scaledDelta / coded delta (+ fused normalize)
+//   delta.C:93-131, scaledDelta.C:78-136, errorEstimator.C:204-228
+// KIND: 0 delta, 1 scaledDelta, 4 coded delta.  Ghost entries (q >= n) are coupled-patch faces:
+// value = patchNeighbourField()[bface]; delta does not clamp there (delta.C:126).
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ double fieldXform(double v, double offset, bool useOffset) {
+    if (KIND == 1) {
+        v = fabs(v);                 // getFieldValue -> mag(field), errorEstimatorTemplates.C:30-46
+        if (useOffset) v -= offset;  // scaledDelta.C:89-93
+    }
+    return v;
+}
+
+template <int KIND, bool SCALE>
+__global__ void __launch_bounds__(kThreads)
+k_estimate(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+           const double *__restrict__ x, const double *__restrict__ ghost, double p0, double p1, Thresholds thr,
+           double *__restrict__ err) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    const int64_t s = c >> 5;
+    const int lane = (int)(c & 31);
+    const int32_t base = sliceOff[s];
+    const int w = sliceOff[s + 1] - base;
+    const int32_t *row = col + ((size_t)base << 5) + lane;
+    const bool useOffset = fabs(p1) > kSMALL;
+    const double xc = fieldXform<KIND>(x[c], p1, useOffset);
+    double e = 0.0;
+    for (int j0 = 0; j0 < w; j0 += kChunk) {
+        int32_t q[kChunk];
+#pragma unroll
+        for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+        double xq[kChunk];
+#pragma unroll
+        for (int k = 0; k < kChunk; k++) {
+            if (q[k] < n) xq[k] = x[q[k]];
+            else xq[k] = ghost[q[k] - n];
+        }
+#pragma unroll
+        for (int k = 0; k < kChunk; k++) {
+            if (q[k] == (int32_t)c) continue;   // padding
+            // local and ghost values get the same mag()/offset transform: the ghost array holds the
+            // neighbour rank's raw cell values (scaledDelta.C:116-124 reads them from the temporary
+            // field whose processor patches carry mag(field) - offset of the other side)
+            double v = fieldXform<KIND>(xq[k], p1, useOffset);
+            double eT;
+            if (KIND == 0) {
+                eT = fabs(xc - v);
+                if (q[k] < n) eT = fminFoam(eT, 0.5);          // delta.C:103 vs :126
+            } else if (KIND == 1) {
+                eT = fabs(xc - v) / fmaxFoam(fminFoam(xc, v), p0);   // scaledDelta.C:103-104,129-131
+            } else {
+                eT = fabs(xc - v);
+            }
+            e = fmaxFoam(e, eT);
+        }
+    }
+    err[c] = SCALE ? normalizeValue(e, thr) : e;
+}
+
+// fieldValue::update, fieldValue.C:68-82 (+ normalize); also the plain normalize pass (ABS=false)
+template <bool ABS, bool SCALE>
+__global__ void __launch_bounds__(kThreads)
+k_pointwise(int64_t n, const double *__restrict__ in, Thresholds thr, double *__restrict__ out) {
+    int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    double v = in[c];
+    if (ABS) v = fabs(v);
+    out[c] = SCALE ? normalizeValue(v, thr) : v;
+}
+
+// patchInternalField of the field for every boundary face: send buffer of the swap
+__global__ void k_pack_f64(int64_t b, const label *__restrict__ bOwner, const double *__restrict__ x,
+                           double *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b) out[i] = x[bOwner[i]];
+}
+
+// ------------------------------------------------------------------------------------------
+// STAGE 2  marking
+// ------------------------------------------------------------------------------------------
+
+// fvMeshRefiner::selectRefineCandidates, fvMeshRefiner.C:170-187 (inclusive compares), fused with
+// the "can still spread" test of the first forced buffer layer (fvMeshRefiner.C:809-813):
+//   mark[c] = lo <= e <= hi ;  src[c] = mark[c] && maxLevel(c) > cellLevel[c]
+__global__ void __launch_bounds__(kThreads)
+k_candidates(int64_t n, const double *__restrict__ err, double lo, double hi, const label *__restrict__ lvl,
+             const label *__restrict__ maxLvl, label maxLvlUniform, u8 *__restrict__ mark, u8 *__restrict__ src) {
+    int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    double e = err[c];
+    u8 m = (e >= lo) && (e <= hi);
+    mark[c] = m;
+    if (src) {
+        label mx = maxLvl ? maxLvl[c] : maxLvlUniform;
+        src[c] = m && (mx > lvl[c]);
+    }
+}
+
+// values of a byte array at the owners of all boundary faces (send buffer of syncFaceList /
+// swapBoundaryFaceList for byte payloads)
+__global__ void k_pack_u8(int64_t b, const label *__restrict__ bOwner, const u8 *__restrict__ v,
+                          u8 *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b) out[i] = v[bOwner[i]];
+}
+
+// One buffer layer: fvMeshRefiner::extendMarkedCells (fvMeshRefiner.C:794-863) and
+// extendMarkedCellsAcrossFaces (:866-921; errorEstimator.C:367-424).
+//   out[c] = in[c] | OR_{q in faceNbrs(c)} src[q]
+// src == in for plain growth; for the first forced layer src = "marked and can still be refined".
+// The syncFaceList(orEqOp) of the reference is the ghost term: ghost[bface] = src of the cell on
+// the other side of a processor face.
+__global__ void __launch_bounds__(kThreads)
+k_extend(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+         const u8 *__restrict__ in, const u8 *__restrict__ src, const u8 *__restrict__ ghost,
+         u8 *__restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const unsigned live = __ballot_sync(0xffffffffu, c < n);
+    if (c >= n) return;
+    const int64_t s = c >> 5;
+    const int lane = (int)(c & 31);
+    const int32_t base = sliceOff[s];
+    const int w = sliceOff[s + 1] - base;
+    const int32_t *row = col + ((size_t)base << 5) + lane;
+    unsigned m = in[c];
+    // a warp whose 32 cells are all marked has nothing to gather
+    if (__all_sync(live, m != 0)) { out[c] = 1; return; }
+    for (int j0 = 0; j0 < w; j0 += kChunk) {
+        int32_t q[kChunk];
+#pragma unroll
+        for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+#pragma unroll
+        for (int k = 0; k < kChunk; k++) {
+            if (q[k] == (int32_t)c) continue;
+            m |= (q[k] < n) ? src[q[k]] : ghost[q[k] - n];
+        }
+    }
+    out[c] = m ? 1 : 0;
+}
+
+// clear / set flags of the cells on the faces of a patch (fvMeshHexRefiner.C:1514-1523, 1612-1621,
+// errorEstimator.C:336-344)
+__global__ void k_patch_cells_set(const label *__restrict__ owner, int64_t start, int64_t size, u8 *__restrict__ flag,
+                                  u8 value) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < size) flag[owner[start + i]] = value;
+}
+
+// flag[c] = value where mask[c]  (protectedCell_ handling, fvMeshHexRefiner.C:1524-1533, 1603-1611)
+__global__ void k_masked_set(int64_t n, const u8 *__restrict__ mask, u8 *__restrict__ flag, u8 value) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n && mask[c]) flag[c] = value;
+}
+
+// error[c] = 0 where prot[c]; counts protected cells (errorEstimator.C:352-361)
+__global__ void __launch_bounds__(kThreads)
+k_zero_protected(int64_t n, const u8 *__restrict__ prot, double *__restrict__ err, unsigned long long *count) {
+    int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int hit = (c < n) && prot[c];
+    if (hit) err[c] = 0.0;
+    int cnt = __syncthreads_count(hit);
+    if (threadIdx.x == 0 && cnt) atomicAdd(count, (unsigned long long)cnt);
+}
+
+// fvMeshHexRefiner::selectRefineCells filter (fvMeshHexRefiner.C:328-345):
+//   set[c] = cellLevel < maxRefinement && candidate && !unrefineable ;  lf[c] = cellLevel + set
+// LEVEL >= 0 restricts to cellLevel == LEVEL and ORs into set (the maxCells truncation loop :346-374).
+__global__ void __launch_bounds__(kThreads)
+k_select_filter(int64_t n, const u8 *__restrict__ cand, const label *__restrict__ lvl, const label *__restrict__ maxLvl,
+                label maxLvlUniform, const u8 *__restrict__ unrefineable, int onlyLevel, u8 *__restrict__ set,
+                u8 *__restrict__ lf) {
+    int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    label l = lvl[c];
+    u8 sel;
+    if (onlyLevel < 0) {
+        label mx = maxLvl ? maxLvl[c] : maxLvlUniform;
+        sel = cand[c] && (l < mx) && !(unrefineable && unrefineable[c]);
+    } else {
+        sel = set[c] || (cand[c] && l == onlyLevel && !(unrefineable && unrefineable[c]));
+    }
+    set[c] = sel;
+    if (lf) lf[c] = (u8)(l + sel);
+}
+
+// sum of a byte-flag array (returnReduce(count(...)) sites: fvMeshHexRefiner.C:323-324,369)
+__global__ void __launch_bounds__(kThreads)
+k_count_flags(int64_t n, const u8 *__restrict__ flag, unsigned long long *count) {
+    int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int cnt = __syncthreads_count((c < n) && flag[c]);
+    if (threadIdx.x == 0 && cnt) atomicAdd(count, (unsigned long long)cnt);
+}
+
+// ------------------------------------------------------------------------------------------
+// STAGE 3  2:1 level-consistency sweeps
+// ------------------------------------------------------------------------------------------
+
+// lf[c] = cellLevel[c] + set[c] at the owners of boundary faces: payload of
+// syncTools::swapBoundaryFaceList(neiLevel), hexRef.C:745-756 -- uses k_pack_u8 on lf.
+
+// hexRef::faceConsistentRefinement (hexRef.C:700-783), maxSet = true, as a chaotic in-place
+// iteration of the same monotone rule: a cell is added when a face neighbour would end up more
+// than one level finer.  Flags only grow and every addition is forced, so any sweep order
+// converges to the reference's (unique, least) closure; only the sweep COUNT differs from the
+// reference's Gauss-Seidel pass.  `changed` receives 1 if any cell of the grid flipped
+// (__syncthreads_or + one store per CTA: the reduce(nChanged) of hexRef.C:1424).
+__global__ void __launch_bounds__(kThreads)
+k_refine_sweep_max(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+                   u8 *__restrict__ lf, u8 *__restrict__ set, const u8 *__restrict__ ghostLf, int *changed) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const unsigned live = __ballot_sync(0xffffffffu, c < n);
+    int flip = 0;
+    if (c < n) {
+        const int64_t s = c >> 5;
+        const int lane = (int)(c & 31);
+        const int32_t base = sliceOff[s];
+        const int w = sliceOff[s + 1] - base;
+        const int32_t *row = col + ((size_t)base << 5) + lane;
+        const int mine = lf[c];
+        const int isSet = set[c];
+        // marked cells cannot change; a warp of 32 marked cells skips its gathers
+        if (!__all_sync(live, isSet != 0)) {
+            int mx = 0;
+            for (int j0 = 0; j0 < w; j0 += kChunk) {
+                int32_t q[kChunk];
+#pragma unroll
+                for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+#pragma unroll
+                for (int k = 0; k < kChunk; k++) {
+                    int v = (q[k] < n) ? lf[q[k]] : ghostLf[q[k] - n];
+                    mx = max(mx, v);
+                }
+            }
+            if (!isSet && mx > mine + 1) { set[c] = 1; lf[c] = (u8)(mine + 1); flip = 1; }
+        }
+    }
+    if (__syncthreads_or(flip) && threadIdx.x == 0) *changed = 1;
+}
+
+// maxSet = false variant (hexRef.C:723-741 else-branches): a marked cell is removed when it would
+// end up more than one level finer than a face neighbour.  Monotone decreasing -> greatest fixed point.
+__global__ void __launch_bounds__(kThreads)
+k_refine_sweep_min(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+                   u8 *__restrict__ lf, u8 *__restrict__ set, const u8 *__restrict__ ghostLf, int *changed) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const unsigned live = __ballot_sync(0xffffffffu, c < n);
+    int flip = 0;
+    if (c < n) {
+        const int64_t s = c >> 5;
+        const int lane = (int)(c & 31);
+        const int32_t base = sliceOff[s];
+        const int w = sliceOff[s + 1] - base;
+        const int32_t *row = col + ((size_t)base << 5) + lane;
+        const int mine = lf[c];
+        const int isSet = set[c];
+        if (__any_sync(live, isSet != 0)) {
+            int mn = 255;
+            for (int j0 = 0; j0 < w; j0 += kChunk) {
+                int32_t q[kChunk];
+#pragma unroll
+                for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+#pragma unroll
+                for (int k = 0; k < kChunk; k++) {
+                    int v = (q[k] < n) ? lf[q[k]] : ghostLf[q[k] - n];
+                    mn = min(mn, v);
+                }
+            }
+            if (isSet && mine > mn + 1) { set[c] = 0; lf[c] = (u8)(mine - 1); flip = 1; }
+        }
+    }
+    if (__syncthreads_or(flip) && threadIdx.x == 0) *changed = 1;
+}
+
+// hexRef::checkRefinementLevels 2:1 part, hexRef.C:2962-3025: count faces with |dL| > 1
+// (each internal face is seen from both cells -> counted once from the lower label; coupled
+// faces once from their owner, like the reference's boundary loop)
+__global__ void __launch_bounds__(kThreads)
+k_check_levels(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+               const label *__restrict__ lvl, const label *__restrict__ ghostLvl, unsigned long long *bad) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int cnt = 0;
+    if (c < n) {
+        const int64_t s = c >> 5;
+        const int lane = (int)(c & 31);
+        const int32_t base = sliceOff[s];
+        const int w = sliceOff[s + 1] - base;
+        const int32_t *row = col + ((size_t)base << 5) + lane;
+        const int mine = lvl[c];
+        for (int j = 0; j < w; j++) {
+            int32_t q = row[(size_t)j << 5];
+            if (q == (int32_t)c) continue;
+            if (q < n) { if (q > c && abs(mine - lvl[q]) > 1) cnt++; }
+            else if (abs(mine - ghostLvl[q - n]) > 1) cnt++;
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(bad, (unsigned long long)cnt);
+}
+__global__ void k_pack_i32(int64_t b, const label *__restrict__ bOwner, const label *__restrict__ v,
+                           label *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b) out[i] = v[bOwner[i]];
+}
+
+// ------------------------------------------------------------------------------------------
+// STAGE 3b  unrefinement selection (3-D hex): point-centric
+// ------------------------------------------------------------------------------------------
+
+// history_.parentIndex(c) (hexRefRefinementHistory.H:299-310) or -1 when the cell is not
+// visible / has no parent: precomputed once per levels_set so the hot kernel gathers 4 bytes.
+__global__ void k_parent_index(int64_t n, const label *__restrict__ visible, const label *__restrict__ splitParent,
+                               int64_t nSplit, label *__restrict__ parentIdx) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    label v = visible[c];
+    label pi = -1;
+    if (v >= 0 && v < nSplit) { pi = splitParent[v]; if (pi < 0) pi = -1; }
+    parentIdx[c] = pi;
+}
+__global__ void k_lvl_to_u8(int64_t n, const label *__restrict__ lvl, u8 *__restrict__ out) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) out[c] = (u8)lvl[c];
+}
+
+// fvMeshRefiner::maxCellField, fvMeshRefiner.C:110-125
+__global__ void __launch_bounds__(kThreads)
+k_max_cell_field(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+                 const double *__restrict__ v, double *__restrict__ out) {
+    const int64_t pt = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (pt >= p) return;
+    const int32_t base = sliceOff[pt >> 5];
+    const int w = sliceOff[(pt >> 5) + 1] - base;
+    const int32_t *row = col + ((size_t)base << 5) + (pt & 31);
+    double m = -kGREAT;
+    for (int j = 0; j < w; j++) {
+        int32_t q = row[(size_t)j << 5];
+        if (q >= 0) m = fmaxFoam(m, v[q]);
+    }
+    out[pt] = m;
+}
+
+// Fused hexRef3D::getSplitElems (hexRef3D.C:2183-2321) + selectUnrefineElems filter
+// (hexRef3D.C:2336-2361) + maxCellField (fvMeshRefiner.C:110-125), one thread per point:
+//   split   <=> |pointCells| == 8, no boundary face uses the point, every cell is visible with
+//               parentIndex >= 0, same parentIndex and same cellLevel for all 8
+//   keep    <=> split && max_{cells} error < unrefineLevel && no cell marked
+// isSplit / keep may be NULL.  Rejects as early as possible: most points of a mesh are not
+// split points and cost one SELL column only.
+__global__ void __launch_bounds__(kThreads)
+k_select_unrefine_points(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+                         const u8 *__restrict__ pcCount, const u8 *__restrict__ bndPoint,
+                         const label *__restrict__ parentIdx, const u8 *__restrict__ lvl8,
+                         const double *__restrict__ err, double unrefineLevel, const u8 *__restrict__ marked,
+                         u8 *__restrict__ isSplit, u8 *__restrict__ keep) {
+    const int64_t pt = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (pt >= p) return;
+    bool split = (pcCount[pt] == 8) && !bndPoint[pt];
+    bool kp = false;
+    if (split) {
+        const int32_t base = sliceOff[pt >> 5];
+        const int32_t *row = col + ((size_t)base << 5) + (pt & 31);
+        int32_t q[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) q[k] = row[(size_t)k << 5];
+        label par[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) par[k] = parentIdx[q[k]];
+        bool same = par[0] >= 0;
+#pragma unroll
+        for (int k = 1; k < 8; k++) same = same && (par[k] == par[0]);
+        if (same) {
+            int l0 = lvl8[q[0]];
+#pragma unroll
+            for (int k = 1; k < 8; k++) same = same && (lvl8[q[k]] == l0);
+        }
+        split = same;
+        if (split && keep) {
+            double m = -kGREAT;
+            unsigned anyMarked = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { m = fmaxFoam(m, err[q[k]]); anyMarked |= marked[q[k]]; }
+            kp = (m < unrefineLevel) && !anyMarked;
+        }
+    }
+    if (isSplit) isSplit[pt] = split;
+    if (keep) keep[pt] = kp;
+}
+
+// unrefineCell = union of pointCells over flagged points (hexRef3D.C:1763-1776); cells pre-zeroed
+__global__ void __launch_bounds__(kThreads)
+k_points_to_cells(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+                  const u8 *__restrict__ pflag, u8 *__restrict__ cflag) {
+    const int64_t pt = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (pt >= p || !pflag[pt]) return;
+    const int32_t base = sliceOff[pt >> 5];
+    const int w = sliceOff[(pt >> 5) + 1] - base;
+    const int32_t *row = col + ((size_t)base << 5) + (pt & 31);
+    for (int j = 0; j < w; j++) {
+        int32_t q = row[(size_t)j << 5];
+        if (q >= 0) cflag[q] = 1;
+    }
+}
+
+// lfm[c] = cellLevel - unrefineCell (payload of the swap at hexRef3D.C:1843-1853)
+__global__ void k_level_minus(int64_t n, const u8 *__restrict__ lvl8, const u8 *__restrict__ uc, u8 *__restrict__ lfm) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) lfm[c] = (u8)(lvl8[c] - uc[c]);
+}
+
+// Face sweep of hexRef3D::consistentUnrefinement (hexRef3D.C:1785-1889, maxSet=false): a cell
+// marked for unrefinement is unmarked when a face neighbour would end up more than one level
+// finer.  lfm = cellLevel - unrefineCell, updated in place (monotone: flags only drop).
+__global__ void __launch_bounds__(kThreads)
+k_unrefine_sweep(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+                 u8 *__restrict__ lfm, u8 *__restrict__ uc, const u8 *__restrict__ ghostLfm, int *changed) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const unsigned live = __ballot_sync(0xffffffffu, c < n);
+    int flip = 0;
+    if (c < n) {
+        const int isSet = uc[c];
+        if (__any_sync(live, isSet != 0)) {
+            const int64_t s = c >> 5;
+            const int lane = (int)(c & 31);
+            const int32_t base = sliceOff[s];
+            const int w = sliceOff[s + 1] - base;
+            const int32_t *row = col + ((size_t)base << 5) + lane;
+            const int mine = lfm[c];
+            int mx = 0;
+            for (int j0 = 0; j0 < w; j0 += kChunk) {
+                int32_t q[kChunk];
+#pragma unroll
+                for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+#pragma unroll
+                for (int k = 0; k < kChunk; k++) {
+                    int v = (q[k] < n) ? lfm[q[k]] : ghostLfm[q[k] - n];
+                    mx = max(mx, v);
+                }
+            }
+            if (isSet && mine < mx - 1) { uc[c] = 0; lfm[c] = (u8)(mine + 1); flip = 1; }
+        }
+    }
+    if (__syncthreads_or(flip) && threadIdx.x == 0) *changed = 1;
+}
+
+// knock out every flagged point that has a cell which cannot be unrefined (hexRef3D.C:1908-1926)
+__global__ void __launch_bounds__(kThreads)
+k_knock_points(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+               u8 *__restrict__ pflag, const u8 *__restrict__ uc) {
+    const int64_t pt = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (pt >= p || !pflag[pt]) return;
+    const int32_t base = sliceOff[pt >> 5];
+    const int w = sliceOff[(pt >> 5) + 1] - base;
+    const int32_t *row = col + ((size_t)base << 5) + (pt & 31);
+    bool ok = true;
+    for (int j = 0; j < w; j++) {
+        int32_t q = row[(size_t)j << 5];
+        if (q >= 0 && !uc[q]) { ok = false; break; }
+    }
+    if (!ok) pflag[pt] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// STAGE 4  field mapping and level update
+// ------------------------------------------------------------------------------------------
+
+// refineCell through the map, fvMeshHexRefiner.C:1562-1586
+__global__ void __launch_bounds__(kThreads)
+k_remap_refine_cell(int64_t nNew, const label *__restrict__ cellMap, const label *__restrict__ reverseCellMap,
+                    const u8 *__restrict__ oldFlag, u8 *__restrict__ newFlag) {
+    int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= nNew) return;
+    label o = cellMap[c];
+    u8 v;
+    if (o < 0) v = 1;
+    else if (reverseCellMap[o] != c) v = 1;
+    else v = oldFlag[o];
+    newFlag[c] = v;
+}
+
+// fvMesh::mapFields direct addressing: new[i][k] = old[cellMap[i]][k]; one thread per scalar
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+k_map_field(int64_t nNew, const label *__restrict__ cellMap, const double *__restrict__ oldF,
+            double *__restrict__ newF) {
+    int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= nNew * NC) return;
+    int64_t i = e / NC;
+    int k = (int)(e - i * NC);
+    newF[e] = oldF[(int64_t)cellMap[i] * NC + k];
+}
+__global__ void __launch_bounds__(kThreads)
+k_map_field_n(int64_t nNew, int nc, const label *__restrict__ cellMap, const double *__restrict__ oldF,
+              double *__restrict__ newF) {
+    int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= nNew * nc) return;
+    int64_t i = e / nc;
+    int k = (int)(e - i * nc);
+    newF[e] = oldF[(int64_t)cellMap[i] * nc + k];
+}
+
+// conservative merge: new master value = sum V_old*old / sum V_old over the 8 merged cells,
+// accumulated in ascending old label.  merged cells of master m are found through mergeOff/mergeIdx
+// (a CSR built from reverseCellMap, rows ascending), so the sum order is deterministic.
+__global__ void __launch_bounds__(kThreads)
+k_map_conservative(int64_t nMasters, const label *__restrict__ masters, const int32_t *__restrict__ mergeOff,
+                   const label *__restrict__ mergeIdx, const double *__restrict__ volOld, int nc,
+                   const double *__restrict__ oldF, double *__restrict__ newF) {
+    int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= nMasters * nc) return;
+    int64_t mi = t / nc;
+    int k = (int)(t - mi * nc);
+    double vs = 0.0, acc = 0.0;
+    for (int32_t j = mergeOff[mi]; j < mergeOff[mi + 1]; j++) {
+        label c = mergeIdx[j];
+        vs += volOld[c];
+        acc += volOld[c] * oldF[(int64_t)c * nc + k];
+    }
+    newF[(int64_t)masters[mi] * nc + k] = acc / vs;
+}
+
+// cellLevel through the map
+__global__ void __launch_bounds__(kThreads)
+k_update_levels(int64_t nNew, const label *__restrict__ cellMap, const label *__restrict__ oldLevel,
+                const u8 *__restrict__ refinedOld, const u8 *__restrict__ unrefinedOld, label *__restrict__ newLevel) {
+    int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= nNew) return;
+    label o = cellMap[c];
+    label l = oldLevel[o];
+    if (refinedOld && refinedOld[o]) l++;
+    if (unrefinedOld && unrefinedOld[o]) l--;
+    newLevel[c] = l;
+}
+
+// flags from an ascending label list (hexRef.C:1415-1419)
+__global__ void k_list_to_flags(int64_t cnt, const label *__restrict__ list, u8 *__restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) flag[list[i]] = 1;
+}

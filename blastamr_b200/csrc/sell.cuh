@@ -1,0 +1,171 @@
+// sell.cuh -- device-side construction of the SELL-32 adjacencies (setup, not on the timed path).
+//
+// The reference walks mesh.cells()[c] -> faces -> owner/neighbour (fvMeshRefiner.C:807-862,
+// hexRef.C:709-741).  Every decision on this path is a max / OR / integer compare over a cell's
+// face neighbours, so the order inside a row never changes a result; the
+// device layout is therefore free: one warp = one slice of 32 consecutive rows, column-major,
+// padded with the row's own index, which is a no-op for every operator used here.
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+
+__global__ void k_deg_internal(const label *__restrict__ owner, const label *__restrict__ neighbour, int64_t f,
+                               int32_t *__restrict__ deg) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f) return;
+    atomicAdd(&deg[owner[i]], 1);
+    atomicAdd(&deg[neighbour[i]], 1);
+}
+__global__ void k_deg_coupled(const label *__restrict__ bOwner, const u8 *__restrict__ bCoupled, int64_t b,
+                              int32_t *__restrict__ deg) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b || !bCoupled[i]) return;
+    atomicAdd(&deg[bOwner[i]], 1);
+}
+// one warp per slice: width = max row length
+__global__ void k_slice_width(const int32_t *__restrict__ deg, int64_t rows, int64_t slices,
+                              int32_t *__restrict__ width) {
+    int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (s >= slices) return;
+    int64_t r = s * 32 + lane;
+    int d = r < rows ? deg[r] : 0;
+    for (int k = 16; k > 0; k >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, k));
+    if (lane == 0) width[s] = d;
+}
+__global__ void k_sell_fill_pad(int32_t *__restrict__ col, const int32_t *__restrict__ sliceOff, int64_t rows,
+                                int selfPad) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t s = r >> 5;
+    if (s * 32 >= ((rows + 31) & ~(int64_t)31)) return;
+    int lane = (int)(r & 31);
+    int32_t base = sliceOff[s], w = sliceOff[s + 1] - base;
+    int32_t v = selfPad ? (int32_t)(r < rows ? r : rows - 1) : -1;
+    for (int j = 0; j < w; j++) col[((size_t)(base + j) << 5) + lane] = v;
+}
+__device__ __forceinline__ void sellPut(int32_t *col, const int32_t *sliceOff, int32_t *cursor, int32_t row,
+                                        int32_t v) {
+    int j = atomicAdd(&cursor[row], 1);
+    col[((size_t)(sliceOff[row >> 5] + j) << 5) + (row & 31)] = v;
+}
+__global__ void k_sell_fill_internal(const label *__restrict__ owner, const label *__restrict__ neighbour, int64_t f,
+                                     const int32_t *__restrict__ sliceOff, int32_t *__restrict__ cursor,
+                                     int32_t *__restrict__ col) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f) return;
+    label o = owner[i], q = neighbour[i];
+    sellPut(col, sliceOff, cursor, o, q);
+    sellPut(col, sliceOff, cursor, q, o);
+}
+__global__ void k_sell_fill_coupled(const label *__restrict__ bOwner, const u8 *__restrict__ bCoupled, int64_t b,
+                                    int64_t n, const int32_t *__restrict__ sliceOff, int32_t *__restrict__ cursor,
+                                    int32_t *__restrict__ col) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b || !bCoupled[i]) return;
+    sellPut(col, sliceOff, cursor, bOwner[i], (int32_t)(n + i));   // ghost slot of boundary face i
+}
+__global__ void k_sell_fill_csr(const int32_t *__restrict__ off, const int32_t *__restrict__ idx, int64_t rows,
+                                const int32_t *__restrict__ sliceOff, int32_t *__restrict__ col) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int32_t s = off[r], e = off[r + 1];
+    int32_t base = sliceOff[r >> 5];
+    int lane = (int)(r & 31);
+    for (int32_t j = 0; j < e - s; j++) col[((size_t)(base + j) << 5) + lane] = idx[s + j];
+}
+__global__ void k_csr_deg(const int32_t *__restrict__ off, int64_t rows, int32_t *__restrict__ deg) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) deg[r] = off[r + 1] - off[r];
+}
+// ascending insertion sort of each row (short rows; makes the layout deterministic and the gathers monotone)
+__global__ void k_sell_sort_rows(int32_t *__restrict__ col, const int32_t *__restrict__ sliceOff,
+                                 const int32_t *__restrict__ deg, int64_t rows) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int32_t *row = col + ((size_t)sliceOff[r >> 5] << 5) + (r & 31);
+    int d = deg[r];
+    for (int i = 1; i < d; i++) {
+        int32_t v = row[(size_t)i << 5];
+        int j = i - 1;
+        while (j >= 0 && row[(size_t)j << 5] > v) { row[(size_t)(j + 1) << 5] = row[(size_t)j << 5]; j--; }
+        row[(size_t)(j + 1) << 5] = v;
+    }
+}
+__global__ void k_deg_to_u8(const int32_t *__restrict__ deg, int64_t rows, u8 *__restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) out[r] = (u8)min(deg[r], 255);
+}
+
+static void sellFree(amr_ctx *ctx, Sell &S) {
+    if (S.sliceOff) { cudaFree(S.sliceOff); ctx->devBytes -= (int64_t)((S.slices + 2) * 4); }
+    if (S.col) { cudaFree(S.col); ctx->devBytes -= (int64_t)(S.entries * 4 > 4 ? S.entries * 4 : 4); }
+    if (S.count) { cudaFree(S.count); ctx->devBytes -= (int64_t)(S.rows > 0 ? S.rows : 1); }
+    S = Sell();
+}
+
+// shared tail of both builders: deg[rows] (device, int32) is known
+static int sellAllocFromDeg(amr_ctx *ctx, Sell &S, int64_t rows, int32_t *deg, int selfPad) {
+    S.rows = rows;
+    S.slices = (rows + 31) / 32;
+    TRY(devAlloc(ctx, &S.sliceOff, S.slices + 2));
+    CK(cudaMemsetAsync(S.sliceOff, 0, (size_t)(S.slices + 2) * 4, ctx->stream));
+    if (S.slices > 0) LAUNCH(k_slice_width, gridFor(S.slices * 32), kThreads, deg, rows, S.slices, S.sliceOff);
+    // scan aux
+    int64_t auxNeed = (S.slices + 1) / kScanTile + 1024;
+    int32_t *aux = nullptr;
+    CK(cudaMalloc((void **)&aux, (size_t)auxNeed * 4 * 2));
+    int rc = deviceExclusiveScan(ctx, S.sliceOff, S.sliceOff, S.slices, aux, auxNeed * 2);
+    if (rc != AMR_OK) { cudaFree(aux); return rc; }
+    int32_t total = 0;
+    CK(cudaMemcpyAsync(&total, S.sliceOff + S.slices, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(aux);
+    S.entries = (int64_t)total * 32;
+    TRY(devAlloc(ctx, &S.col, S.entries));
+    TRY(devAlloc(ctx, &S.count, rows));
+    if (rows > 0) {
+        LAUNCH(k_sell_fill_pad, gridFor(S.slices * 32), kThreads, S.col, S.sliceOff, rows, selfPad);
+        LAUNCH(k_deg_to_u8, gridFor(rows), kThreads, deg, rows, S.count);
+    }
+    return AMR_OK;
+}
+
+// cell -> face-neighbour cells from owner/neighbour (+ ghost slots for coupled boundary faces)
+static int sellBuildCellCells(amr_ctx *ctx) {
+    sellFree(ctx, ctx->cc);
+    int64_t n = ctx->n, f = ctx->f, b = ctx->b;
+    int32_t *deg = nullptr, *cursor = nullptr;
+    CK(cudaMalloc((void **)&deg, (size_t)(n + 1) * 4));
+    CK(cudaMalloc((void **)&cursor, (size_t)(n + 1) * 4));
+    CK(cudaMemsetAsync(deg, 0, (size_t)(n + 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(cursor, 0, (size_t)(n + 1) * 4, ctx->stream));
+    if (f > 0) LAUNCH(k_deg_internal, gridFor(f), kThreads, ctx->owner, ctx->neighbour, f, deg);
+    if (b > 0 && ctx->nCoupled > 0) LAUNCH(k_deg_coupled, gridFor(b), kThreads, ctx->owner + f, ctx->bCoupled, b, deg);
+    int rc = sellAllocFromDeg(ctx, ctx->cc, n, deg, 1);
+    if (rc == AMR_OK) {
+        if (f > 0) LAUNCH(k_sell_fill_internal, gridFor(f), kThreads, ctx->owner, ctx->neighbour, f, ctx->cc.sliceOff, cursor, ctx->cc.col);
+        if (b > 0 && ctx->nCoupled > 0)
+            LAUNCH(k_sell_fill_coupled, gridFor(b), kThreads, ctx->owner + f, ctx->bCoupled, b, n, ctx->cc.sliceOff, cursor, ctx->cc.col);
+        if (n > 0) LAUNCH(k_sell_sort_rows, gridFor(n), kThreads, ctx->cc.col, ctx->cc.sliceOff, deg, n);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("sellBuildCellCells: ") + cudaGetErrorString(e); rc = AMR_ERR_CUDA; }
+    }
+    cudaFree(deg); cudaFree(cursor);
+    return rc;
+}
+
+// point -> cells from the host's pointCells CSR (device copies off/idx)
+static int sellBuildFromCsr(amr_ctx *ctx, Sell &S, int64_t rows, const int32_t *off, const int32_t *idx) {
+    sellFree(ctx, S);
+    int32_t *deg = nullptr;
+    CK(cudaMalloc((void **)&deg, (size_t)(rows + 1) * 4));
+    if (rows > 0) LAUNCH(k_csr_deg, gridFor(rows), kThreads, off, rows, deg);
+    int rc = sellAllocFromDeg(ctx, S, rows, deg, 0);
+    if (rc == AMR_OK && rows > 0) {
+        LAUNCH(k_sell_fill_csr, gridFor(rows), kThreads, off, idx, rows, S.sliceOff, S.col);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("sellBuildFromCsr: ") + cudaGetErrorString(e); rc = AMR_ERR_CUDA; }
+    }
+    cudaFree(deg);
+    return rc;
+}

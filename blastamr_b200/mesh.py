@@ -1,0 +1,243 @@
+"""Host-side mesh container and the synthetic topology engine (ctypes over libamrmesh.so).
+
+`PolyMesh` carries exactly the OpenFOAM arrays the AMR decision path reads
+(owner/neighbour/boundary, pointCells, cellLevel/pointLevel,
+refinement-history visibleCells/parent).  `Octree` plays the role of
+blockMesh + hexRef3D::setRefinement/setUnrefinement + polyTopoChange: it is host
+bookkeeping that turns the *decisions* of the GPU path into the next mesh and the
+`cellMap` used by the field-mapping kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _build
+
+_lib = None
+
+SIDES = {"xmin": 0, "xmax": 1, "ymin": 2, "ymax": 3, "zmin": 4, "zmax": 5}
+PATCH_WALL, PATCH_EMPTY, PATCH_PROCESSOR = 0, 1, 2
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.build_mesh()
+        L = C.CDLL(str(path))
+        L.mg_oct_create.restype = C.c_void_p
+        L.mg_oct_create.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                                     C.c_int, C.c_void_p]
+        L.mg_oct_free.argtypes = [C.c_void_p]
+        L.mg_oct_ncells.restype = C.c_int64
+        L.mg_oct_ncells.argtypes = [C.c_void_p]
+        L.mg_oct_refine.restype = C.c_int64
+        L.mg_oct_refine.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.mg_oct_unrefine.restype = C.c_int64
+        L.mg_oct_unrefine.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.mg_oct_build.restype = C.c_void_p
+        L.mg_oct_build.argtypes = [C.c_void_p, C.c_int]
+        L.mg_mesh_free.argtypes = [C.c_void_p]
+        L.mg_mesh_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        L.mg_mesh_array.restype = C.c_void_p
+        L.mg_mesh_array.argtypes = [C.c_void_p, C.c_int]
+        L.mg_decompose.restype = C.c_int
+        L.mg_decompose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.mg_simple_ranks.argtypes = [C.c_void_p] + [C.c_double] * 3 + [C.c_int] * 3 + [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+@dataclass
+class Patch:
+    name: str
+    type: int          # PATCH_WALL / PATCH_EMPTY / PATCH_PROCESSOR
+    start: int         # absolute face index
+    size: int
+    nbr_rank: int = -1
+
+    @property
+    def coupled(self) -> bool:
+        return self.type == PATCH_PROCESSOR
+
+
+@dataclass
+class PolyMesh:
+    n: int
+    f: int
+    b: int
+    p: int
+    owner: np.ndarray                 # int32 [f+b]
+    neighbour: np.ndarray             # int32 [f]
+    patches: List[Patch]
+    cc: Optional[np.ndarray] = None   # float64 [n,3]
+    vol: Optional[np.ndarray] = None  # float64 [n]
+    pc_off: Optional[np.ndarray] = None   # pointCells CSR
+    pc_cells: Optional[np.ndarray] = None
+    cp_off: Optional[np.ndarray] = None   # cellPoints CSR
+    cp_pts: Optional[np.ndarray] = None
+    bnd_point: Optional[np.ndarray] = None  # uint8 [p]
+    cell_level: Optional[np.ndarray] = None
+    point_level: Optional[np.ndarray] = None
+    visible: Optional[np.ndarray] = None
+    split_parent: Optional[np.ndarray] = None
+    cell_global: Optional[np.ndarray] = None
+    point_global: Optional[np.ndarray] = None
+    face_global: Optional[np.ndarray] = None
+    pxyz: Optional[np.ndarray] = None
+    _handle: Optional[int] = field(default=None, repr=False)
+
+    # patch arrays in the layout the C-ABI takes
+    def patch_arrays(self):
+        st = np.array([q.start for q in self.patches], dtype=np.int32)
+        sz = np.array([q.size for q in self.patches], dtype=np.int32)
+        ty = np.array([q.type for q in self.patches], dtype=np.int32)
+        nb = np.array([q.nbr_rank for q in self.patches], dtype=np.int32)
+        return st, sz, ty, nb
+
+    def patch_id(self, name: str) -> int:
+        for i, q in enumerate(self.patches):
+            if q.name == name:
+                return i
+        raise KeyError(name)
+
+    def __del__(self):
+        h, self._handle = self._handle, None
+        if h is not None and _lib is not None:
+            _lib.mg_mesh_free(h)
+
+
+def _wrap(handle: int, names: Sequence[str], copy: bool = False) -> PolyMesh:
+    L = lib()
+    sz = np.zeros(8, dtype=np.int64)
+    L.mg_mesh_sizes(handle, sz.ctypes.data)
+    n, f, b, p, npatch, nsplit, nnz_pc, nnz_cp = (int(x) for x in sz)
+
+    def arr(idx, dtype, count, shape=None):
+        ptr = L.mg_mesh_array(handle, idx)
+        if not ptr or count == 0:
+            return None if not ptr else np.zeros(shape or (0,), dtype=dtype)
+        ct = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dtype).itemsize,))
+        a = ct.view(dtype)
+        if shape:
+            a = a.reshape(shape)
+        return a.copy() if copy else a
+
+    pst = arr(2, np.int32, npatch); psz = arr(3, np.int32, npatch)
+    pty = arr(4, np.int32, npatch); pnb = arr(5, np.int32, npatch)
+    patches = []
+    for i in range(npatch):
+        nm = names[i] if i < len(names) else f"procBoundaryTo{int(pnb[i])}"
+        patches.append(Patch(nm, int(pty[i]), int(pst[i]), int(psz[i]), int(pnb[i])))
+    m = PolyMesh(
+        n=n, f=f, b=b, p=p,
+        owner=arr(0, np.int32, f + b), neighbour=arr(1, np.int32, f) if f else np.zeros(0, np.int32),
+        patches=patches,
+        cc=arr(6, np.float64, 3 * n, (n, 3)), vol=arr(7, np.float64, n),
+        pc_off=arr(8, np.int32, p + 1), pc_cells=arr(9, np.int32, nnz_pc),
+        cp_off=arr(10, np.int32, n + 1), cp_pts=arr(11, np.int32, nnz_cp),
+        bnd_point=arr(12, np.uint8, p), cell_level=arr(13, np.int32, n), point_level=arr(14, np.int32, p),
+        visible=arr(15, np.int32, n), split_parent=arr(16, np.int32, max(nsplit, 0)),
+        cell_global=arr(17, np.int32, n), point_global=arr(18, np.int32, p), face_global=arr(19, np.int32, f + b),
+        pxyz=arr(20, np.int32, 3 * p, (p, 3)),
+    )
+    if m.split_parent is None:
+        m.split_parent = np.zeros(0, np.int32)
+    if copy:
+        L.mg_mesh_free(handle)
+    else:
+        m._handle = handle
+    return m
+
+
+# default boundary layout = the reference's own fixture tests/testCases/hex3D (blockMeshDict):
+#   movingWall (ymax), fixedWalls (xmin xmax ymin), frontAndBack (zmin zmax)
+CAVITY_SIDES = [("ymax", "movingWall"), ("xmin", "fixedWalls"), ("xmax", "fixedWalls"), ("ymin", "fixedWalls"),
+                ("zmin", "frontAndBack"), ("zmax", "frontAndBack")]
+
+
+class Octree:
+    """A single hex block that can be cut 1->8 and merged 8->1 (the host 'topology engine')."""
+
+    def __init__(self, nx, ny, nz, lengths=(1.0, 1.0, 1.0), max_level=3, sides=None, patch_types=None):
+        sides = sides or CAVITY_SIDES
+        names: List[str] = []
+        for _, nm in sides:
+            if nm not in names:
+                names.append(nm)
+        patch_types = patch_types or {}
+        sid = np.array([SIDES[s] for s, _ in sides], dtype=np.int32)
+        spa = np.array([names.index(nm) for _, nm in sides], dtype=np.int32)
+        pty = np.array([patch_types.get(nm, PATCH_WALL) for nm in names], dtype=np.int32)
+        self.names = names
+        self.dims = (nx, ny, nz)
+        self.lengths = tuple(float(x) for x in lengths)
+        self.max_level = max_level
+        self._h = lib().mg_oct_create(nx, ny, nz, *self.lengths, max_level, len(sid), sid.ctypes.data,
+                                      spa.ctypes.data, len(names), pty.ctypes.data)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.mg_oct_free(h)
+
+    @property
+    def ncells(self) -> int:
+        return int(lib().mg_oct_ncells(self._h))
+
+    def build(self, points: bool = True, copy: bool = False) -> PolyMesh:
+        h = lib().mg_oct_build(self._h, 1 if points else 0)
+        return _wrap(h, self.names, copy=copy)
+
+    def refine(self, cells: np.ndarray) -> np.ndarray:
+        """Cut the listed cells (ascending); returns cellMap (new -> old label)."""
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        n_new = self.ncells + 7 * len(cells)
+        cell_map = np.empty(n_new, dtype=np.int32)
+        r = lib().mg_oct_refine(self._h, cells.ctypes.data, len(cells), cell_map.ctypes.data)
+        if r < 0:
+            raise ValueError("refinement beyond the level cap")
+        return cell_map
+
+    def unrefine(self, mesh: PolyMesh, split_points: np.ndarray):
+        """Merge the 8 cells around each split point of `mesh` (the mesh last built).
+        Returns (cellMap new->old, reverseCellMap old->new | -(master)-2)."""
+        split_points = np.ascontiguousarray(split_points, dtype=np.int32)
+        n_old = self.ncells
+        rows = np.empty((len(split_points), 8), dtype=np.int32)
+        for i, pt in enumerate(split_points):
+            s, e = mesh.pc_off[pt], mesh.pc_off[pt + 1]
+            if e - s != 8:
+                raise ValueError(f"point {pt} is not a split point (|pointCells|={e - s})")
+            rows[i] = mesh.pc_cells[s:e]
+        cell_map = np.empty(n_old - 7 * len(split_points), dtype=np.int32)
+        rev = np.empty(n_old, dtype=np.int32)
+        r = lib().mg_oct_unrefine(self._h, rows.ctypes.data, len(split_points), cell_map.ctypes.data, rev.ctypes.data)
+        if r < 0:
+            raise ValueError("inconsistent split points")
+        return cell_map, rev
+
+
+def box_mesh(nx, ny, nz, lengths=(1.0, 1.0, 1.0), points=True, sides=None, patch_types=None) -> PolyMesh:
+    """blockMesh-equivalent single hex block (level 0)."""
+    return Octree(nx, ny, nz, lengths, 0, sides, patch_types).build(points=points)
+
+
+def simple_ranks(mesh: PolyMesh, lengths, procs) -> np.ndarray:
+    out = np.empty(mesh.n, dtype=np.int32)
+    lib().mg_simple_ranks(mesh._handle, *[float(x) for x in lengths], *[int(x) for x in procs], out.ctypes.data)
+    return out
+
+
+def decompose(mesh: PolyMesh, cell_rank: np.ndarray, nranks: int) -> List[PolyMesh]:
+    """decomposePar stand-in: one local mesh (with processor patches) per rank."""
+    cell_rank = np.ascontiguousarray(cell_rank, dtype=np.int32)
+    outs = (C.c_void_p * nranks)()
+    if mesh._handle is None:
+        raise ValueError("decompose needs a generator-owned mesh")
+    lib().mg_decompose(mesh._handle, cell_rank.ctypes.data, nranks, outs)
+    names = [q.name for q in mesh.patches]
+    return [_wrap(outs[r], names) for r in range(nranks)]

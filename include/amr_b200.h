@@ -1,0 +1,226 @@
+/*
+ * amr_b200.h -- C-ABI of the B200-native AMR decision path (libamr_b200.so).
+ *
+ * This is the drop-in boundary for blastAMR's per-timestep decision path
+ * (estimate -> mark -> 2:1 balance -> map).  Every entry point replaces the body of one
+ * reference method; the host (adaptiveFvMesh / errorEstimator / fvMeshRefiner / hexRef in the
+ * reference, blastamr_b200/host in this repo) keeps its run-time-selectable names and
+ * dynamicMeshDict keywords and calls in here.  Citations are relative to the reference tree.
+ *
+ * Conventions (OpenFOAM, WM_LABEL_SIZE=32, WM_PRECISION_OPTION=DP):
+ *   label  = int32_t, scalar = double, boolList element = uint8_t (0/1).
+ *   n cells, f internal faces, b boundary faces, p points.
+ *   owner[f+b] = mesh.faceOwner(), neighbour[f] = mesh.faceNeighbour(); internal faces first,
+ *   upper-triangular order; boundary faces grouped by patch (polyMesh/boundary startFace,nFaces).
+ *   Arrays "over boundary faces" have length b and are indexed by (face - f), the layout of
+ *   `labelList neiLevel(nFaces-nInternalFaces)` in hexRef.C:745.
+ *
+ * Memory: every data pointer may be a host pointer (the drop-in case; the library stages it
+ * through the context's device buffers on the context's stream) or a device pointer on the
+ * context's device (resident case; used as is, no copy).  The library detects which with
+ * cudaPointerGetAttributes.  Scalar outputs (counts) are always host pointers and may be NULL.
+ *
+ * Errors: every call returns AMR_OK (0) or a negative code; amr_last_error() gives the text.
+ * No C++ exception crosses the boundary.  The host wrapper turns a failure into
+ * FatalErrorInFunction ... abort(FatalError), like the reference's own invariants
+ * (hexRef3D.C:1811-1815).
+ *
+ * Threading: one context per MPI rank / GPU, calls are synchronous with respect to the host
+ * (results are complete on return) exactly like the reference methods they replace.  With a
+ * communicator attached, all ranks must enter the collective-bearing calls together (they
+ * replace syncTools::* / reduce() calls that are already collective).
+ *
+ * There is no CPU fallback: without a CUDA device amr_ctx_create fails.
+ */
+#ifndef AMR_B200_H
+#define AMR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct amr_ctx amr_ctx;
+
+enum {
+    AMR_OK = 0,
+    AMR_ERR_CUDA = -1,      /* CUDA runtime error (text in amr_last_error) */
+    AMR_ERR_ARG = -2,       /* bad argument */
+    AMR_ERR_STATE = -3,     /* call order: mesh / levels / points not set */
+    AMR_ERR_NCCL = -4,      /* NCCL error */
+    AMR_ERR_INVARIANT = -5  /* a reference FatalError condition ("problem", 2:1 violated ...) */
+};
+
+/* estimator kinds == run-time-selection names of the reference (errorEstimators/Make/files:6-14) */
+enum {
+    AMR_EST_DELTA = 0,        /* "delta"        delta.C:70-136 */
+    AMR_EST_SCALED_DELTA = 1, /* "scaledDelta"  scaledDelta.C:71-141 */
+    AMR_EST_LOHNER = 2,       /* "Lohner"       Lohner.C:71-159 (needs amr_mesh_set_geometry) */
+    AMR_EST_FIELD_VALUE = 3,  /* "fieldValue"   fieldValue.C:68-82 */
+    AMR_EST_CODED_DELTA = 4   /* coded delta w/o clamp, tutorials/damBreak2D/constant/dynamicMeshDict:24-65 */
+};
+
+/* patch types for amr_mesh_set (only "coupled" matters on this path) */
+enum { AMR_PATCH_PLAIN = 0, AMR_PATCH_EMPTY = 1, AMR_PATCH_PROCESSOR = 2 };
+
+/* refiner kinds == `refiner` keyword (fvMeshRefinerNew.C:74-103) x hexRef::New dimension switch */
+enum {
+    AMR_REFINER_HEX3D = 0,   /* hexRefiner + hexRef3D */
+    AMR_REFINER_HEX2D = 1,   /* hexRefiner + hexRef2D (split elements are edges)   -- next */
+    AMR_REFINER_POLY3D = 2,  /* polyRefiner + polyhedralRefinement                 -- next */
+    AMR_REFINER_POLY2D = 3   /* polyRefiner + prismatic2DRefinement                -- next */
+};
+
+/* field-map modes */
+enum {
+    AMR_MAP_DIRECT = 0,       /* fvMesh::mapFields direct addressing: new[i] = old[cellMap[i]] (parity mode) */
+    AMR_MAP_CONSERVATIVE = 1  /* volume-weighted merge on unrefinement (extension; no in-tree reference) */
+};
+
+/* ---- context ---------------------------------------------------------------------------- */
+
+/* Create a context on CUDA device `device` (one per MPI rank).  Fails (AMR_ERR_CUDA) when no
+   CUDA device is usable: there is no CPU path. */
+int amr_ctx_create(int device, amr_ctx **out);
+int amr_ctx_destroy(amr_ctx *ctx);
+const char *amr_last_error(const amr_ctx *ctx);
+
+/* Use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+int amr_set_stream(amr_ctx *ctx, void *cuda_stream);
+
+/* Multi-GPU: one rank per GPU, processor patches <-> NCCL send/recv, reduce() <-> allreduce.
+   Replaces the Pstream layer under syncTools::swapBoundaryFaceList / syncFaceList / reduce
+   (call sites: hexRef.C:756,1424; fvMeshRefiner.C:840,894; hexRef3D.C:1853,1891).
+   id128 is an ncclUniqueId created on rank 0 by amr_comm_unique_id and broadcast by the host. */
+int amr_comm_unique_id(void *id128);
+int amr_comm_init(amr_ctx *ctx, int nranks, int rank, const void *id128);
+
+/* ---- mesh / level state (re-sent after every topology change) --------------------------- */
+
+/* primitiveMesh addressing.  patchType[i]==AMR_PATCH_PROCESSOR marks coupled patches;
+   patchNbrRank[i] is the neighbour rank there.  The library derives its own cell->cell
+   adjacency (the reference walks mesh.cells() + owner/neighbour: fvMeshRefiner.C:807-862). */
+int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t p,
+                 const int32_t *owner, const int32_t *neighbour,
+                 int npatch, const int32_t *patchStart, const int32_t *patchSize,
+                 const int32_t *patchType, const int32_t *patchNbrRank);
+
+/* mesh.pointCells() as CSR (pcOff[p+1], pcCells[pcOff[p]]) and the flag "point is used by a
+   boundary face" (what the loop hexRef3D.C:2279-2294 computes from mesh.faces()). */
+int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_t *pcCells,
+                        const uint8_t *bndPoint);
+
+/* hexRef::cellLevel_/pointLevel_ and the refinement history arrays visibleCells_ and
+   splitCells_[i].parent_ (hexRefRefinementHistory.H:299-310).  pointLevel, visibleCells,
+   splitParent may be NULL when no unrefinement is requested. */
+int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t *pointLevel,
+                   const int32_t *visibleCells, const int32_t *splitParent, int64_t nSplit);
+
+/* fvMeshHexRefiner::protectedCell_ (fvMeshHexRefiner.C:1014-1465 computes it on the host);
+   NULL = empty list. */
+int amr_protected_cells_set(amr_ctx *ctx, const uint8_t *protectedCell);
+
+/* ---- stage 1: errorEstimator::update ---------------------------------------------------- */
+
+/* errorEstimator::update(scale) for `kind`.
+     x          cell values [n]; for non-scalar fields the host passes mag(field)
+                (errorEstimatorTemplates.C:30-46)
+     nbrValues  patchNeighbourField() values over boundary faces [b] (only coupled ranges are
+                read) or NULL: then, with a communicator, the library swaps patchInternalField
+                itself; without one there are no coupled faces.
+     p0, p1     scaledDelta: minValue, offset; Lohner: epsilon, unused
+     scale      0: raw error; 1: followed by normalize() with thr[4] =
+                {lowerRefine, upperRefine, lowerUnrefine, upperUnrefine} (errorEstimator.C:204-228)
+     errorOut   [n] or NULL to leave the result resident in the context (used by the later
+                stages when they are passed error == NULL). */
+int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *nbrValues,
+                 double p0, double p1, int scale, const double *thr, double *errorOut);
+
+/* errorEstimator::normalize on its own (errorEstimator.C:204-228).  errorInOut NULL = resident. */
+int amr_normalize(amr_ctx *ctx, double lowerRefine, double upperRefine, double lowerUnrefine,
+                  double upperUnrefine, double *errorInOut);
+
+/* errorEstimator::protectPatches (errorEstimator.C:329-365): seed = owners of the faces of the
+   listed patches, grow nLayers face layers (:347), set error = 0 there.  nProtected (host,
+   nullable) receives the local count (:355-361). */
+int amr_protect_patches(amr_ctx *ctx, const int32_t *patchIds, int nPatchIds, int nLayers,
+                        double *errorInOut, int64_t *nProtected);
+
+/* ---- stages 2+3: refinement selection --------------------------------------------------- */
+
+/* Refinement branch of fvMeshHexRefiner::refine (fvMeshHexRefiner.C:1497-1541):
+   selectRefineCandidates(lo, hi) -> nBufferLayers x extendMarkedCells(force=true) -> clear
+   protectedPatches/protectedCell -> selectRefineCells(maxCells) incl. calculateProtectedCells
+   -> hexRef::consistentRefinement(maxSet=true).
+     error            normalised error [n] or NULL (resident result of amr_estimate)
+     maxCellLevel     per-cell maxRefinement [n] or NULL, then maxLevelUniform applies
+     refineCellOut    [n] the marking after buffer layers/protections (the reference keeps it
+                      for the unrefinement stage); NULL = keep resident only
+     cellsOut, nOut   ascending labelList cellsToRefine (capacity n) and its size
+     sweepsOut        number of 2:1 sweeps executed (diagnostic; differs from the reference's
+                      Gauss-Seidel count by construction) */
+int amr_select_refine(amr_ctx *ctx, const double *error, double lowerRefineLevel,
+                      double upperRefineLevel, const int32_t *maxCellLevel, int32_t maxLevelUniform,
+                      int nBufferLayers, const int32_t *protectedPatchIds, int nProtectedPatches,
+                      int64_t maxCells, int refinerKind, uint8_t *refineCellOut,
+                      int32_t *cellsOut, int64_t *nOut, int *sweepsOut);
+
+/* hexRef::consistentRefinement(cellsToRefine, maxSet) on its own (hexRef.C:1402-1468). */
+int amr_consistent_refinement(amr_ctx *ctx, const int32_t *cellsIn, int64_t nIn, int maxSet,
+                              int32_t *cellsOut, int64_t *nOut, int *sweepsOut);
+
+/* Update of refineCell through the topology change (fvMeshHexRefiner.C:1562-1586).
+   refineCell NULL = the resident marking; result replaces the resident marking and is copied
+   to newRefineCellOut when not NULL. */
+int amr_remap_refine_cell(amr_ctx *ctx, int64_t nNew, const int32_t *cellMap,
+                          const int32_t *reverseCellMap, const uint8_t *refineCell,
+                          uint8_t *newRefineCellOut);
+
+/* Unrefinement branch (fvMeshHexRefiner.C:1591-1633 + hexRef3D::selectUnrefineElems
+   hexRef3D.C:2324-2381): nBufferLayers x extendMarkedCellsAcrossFaces -> set
+   protectedCell/protectedPatches -> maxCellField -> getSplitElems -> filter ->
+   consistentUnrefinement.  refineCellInOut NULL = resident marking.  elemsOut (capacity p)
+   receives the ascending split-point list. */
+int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefineLevel,
+                        uint8_t *refineCellInOut, int nBufferLayers,
+                        const int32_t *protectedPatchIds, int nProtectedPatches, int refinerKind,
+                        int32_t *elemsOut, int64_t *nOut, int *sweepsOut);
+
+/* hexRef3D::getSplitElems (hexRef3D.C:2183-2321): ascending split points. */
+int amr_get_split_elems(amr_ctx *ctx, int refinerKind, int32_t *elemsOut, int64_t *nOut);
+
+/* fvMeshRefiner::maxCellField (fvMeshRefiner.C:110-125): pFld[p] = max over pointCells, init -GREAT */
+int amr_max_cell_field(amr_ctx *ctx, const double *vFld, double *pFld);
+
+/* hexRef::checkRefinementLevels 2:1 part (hexRef.C:2934-3025).  cellLevel NULL = resident.
+   nBad (host) = number of violating faces; returns AMR_ERR_INVARIANT when > 0. */
+int amr_check_levels(amr_ctx *ctx, const int32_t *cellLevel, int64_t *nBad);
+
+/* ---- stage 4: field mapping ------------------------------------------------------------- */
+
+/* fvMesh::mapFields, reached from adaptiveFvMesh.C:293,346-348: direct addressing through
+   mapPolyMesh::cellMap().  nComp interleaved components per cell (scalar 1, vector 3,
+   symmTensor 6, tensor 9).  mode AMR_MAP_CONSERVATIVE additionally needs reverseCellMap[nOld]
+   and volOld[nOld]. */
+int amr_map_field(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nComp,
+                  const double *oldF, double *newF, int mode, const int32_t *reverseCellMap,
+                  const double *volOld);
+
+/* cellLevel through a refinement/unrefinement map (hexRef3D.C:1238,1255,2132-2135 +
+   hexRef.C:2457-2485): new[i] = old[cellMap[i]] + refined[cellMap[i]] - unrefined[cellMap[i]].
+   refinedOld / unrefinedOld: uint8 flags over old cells, nullable. */
+int amr_update_levels(amr_ctx *ctx, int64_t nNew, const int32_t *cellMap, const int32_t *oldLevel,
+                      const uint8_t *refinedOld, const uint8_t *unrefinedOld, int32_t *newLevel);
+
+/* ---- diagnostics ------------------------------------------------------------------------ */
+
+/* number of kernels launched by this context since creation */
+int64_t amr_launch_count(const amr_ctx *ctx);
+/* bytes currently held in device memory by this context */
+int64_t amr_device_bytes(const amr_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMR_B200_H */

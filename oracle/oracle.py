@@ -1,0 +1,208 @@
+"""ctypes binding of the CPU oracle (oracle/amr_oracle.c).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+import sys
+from pathlib import Path
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "liboracle.so"
+_lib = None
+
+SMALL = 1e-15
+GREAT = 1e15
+SQRT_SMALL = float(np.sqrt(1e-15))
+
+KIND = {"delta": 0, "scaledDelta": 1, "Lohner": 2, "fieldValue": 3, "codedDelta": 4}
+
+
+def build(force: bool = False) -> Path:
+    src = sorted(HERE.glob("*.c"))
+    if not force and LIB.exists() and all(s.stat().st_mtime <= LIB.stat().st_mtime for s in src):
+        return LIB
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=gnu11", "-pthread", "-o", str(LIB)] + \
+          [str(s) for s in src] + ["-lm"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("oracle build failed")
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(str(build()))
+        L.or_world_create.restype = C.c_void_p
+        L.or_world_create.argtypes = [C.c_int]
+        L.or_world_free.argtypes = [C.c_void_p]
+        L.or_world_set_mesh.argtypes = [C.c_void_p, C.c_int] + [C.c_int64] * 4 + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 4
+        L.or_world_set_points.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.or_world_set_levels.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        L.or_normalize.argtypes = [C.c_int64, C.c_void_p] + [C.c_double] * 4
+        L.or_estimate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+        L.or_protect_patches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.or_consistent_refinement.restype = C.c_int
+        L.or_consistent_refinement.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.or_hex_select_refine.restype = C.c_int
+        L.or_hex_select_refine.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+        L.or_remap_refine_cell.argtypes = [C.c_int64] + [C.c_void_p] * 4
+        L.or_max_cell_field.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.or_get_split_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.or_consistent_unrefinement.restype = C.c_int
+        L.or_consistent_unrefinement.argtypes = [C.c_void_p, C.c_void_p]
+        L.or_hex_select_unrefine.restype = C.c_int
+        L.or_hex_select_unrefine.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.or_check_levels.restype = C.c_int64
+        L.or_check_levels.argtypes = [C.c_void_p, C.c_void_p]
+        L.or_map_field.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.or_map_field_conservative.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                C.c_void_p, C.c_void_p]
+        L.or_update_levels.argtypes = [C.c_int64] + [C.c_void_p] * 5
+        _lib = L
+    return _lib
+
+
+def _pp(arrs: Sequence[Optional[np.ndarray]]):
+    """array of pointers (one per rank); None -> NULL"""
+    return (C.c_void_p * len(arrs))(*[None if a is None else a.ctypes.data for a in arrs])
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class World:
+    """R emulated MPI ranks (R=1: the serial reference run) over PolyMesh objects."""
+
+    def __init__(self, meshes):
+        L = lib()
+        self.meshes = list(meshes)
+        self.R = len(self.meshes)
+        self._h = L.or_world_create(self.R)
+        self._keep = []
+        for r, m in enumerate(self.meshes):
+            st, sz, ty, nb = m.patch_arrays()
+            own, nei = _i32(m.owner), _i32(m.neighbour)
+            self._keep += [st, sz, ty, nb, own, nei]
+            L.or_world_set_mesh(self._h, r, m.n, m.f, m.b, m.p, own.ctypes.data, nei.ctypes.data, len(st),
+                                st.ctypes.data, sz.ctypes.data, ty.ctypes.data, nb.ctypes.data)
+            if m.pc_off is not None:
+                a = [_i32(m.pc_off), _i32(m.pc_cells), _i32(m.cp_off), _i32(m.cp_pts),
+                     np.ascontiguousarray(m.bnd_point, dtype=np.uint8)]
+                self._keep += a
+                L.or_world_set_points(self._h, r, *[x.ctypes.data for x in a])
+            if m.cell_level is not None:
+                sp = _i32(m.split_parent) if m.split_parent is not None and len(m.split_parent) else np.full(1, -1, np.int32)
+                a = [_i32(m.cell_level), _i32(m.point_level) if m.point_level is not None else np.zeros(max(m.p, 1), np.int32),
+                     _i32(m.visible) if m.visible is not None else np.full(max(m.n, 1), -1, np.int32), sp]
+                self._keep += a
+                L.or_world_set_levels(self._h, r, *[x.ctypes.data for x in a])
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.or_world_free(h)
+
+    # ---- stage 1
+    def estimate(self, kind: str, x: List[np.ndarray], min_val: float = SMALL, offset: float = 0.0):
+        x = [np.ascontiguousarray(a, dtype=np.float64) for a in x]
+        err = [np.empty(m.n, dtype=np.float64) for m in self.meshes]
+        lib().or_estimate(self._h, KIND[kind], _pp(x), _pp(err), min_val, offset)
+        return err
+
+    @staticmethod
+    def normalize(err: List[np.ndarray], lower_refine, upper_refine=GREAT, lower_unrefine=None, upper_unrefine=GREAT):
+        for e in err:
+            lib().or_normalize(len(e), e.ctypes.data, lower_refine, upper_refine, lower_unrefine, upper_unrefine)
+        return err
+
+    def protect_patches(self, err: List[np.ndarray], patch_ids, n_layers: int):
+        ids = _i32(patch_ids)
+        cnt = np.zeros(self.R, dtype=np.int64)
+        lib().or_protect_patches(self._h, ids.ctypes.data, len(ids), n_layers, _pp(err), cnt.ctypes.data)
+        return cnt
+
+    # ---- stage 2/3
+    def consistent_refinement(self, flags: List[np.ndarray], max_set: bool = True) -> int:
+        return lib().or_consistent_refinement(self._h, 1 if max_set else 0, _pp(flags))
+
+    def hex_select_refine(self, err, max_cell_level, n_layers, lower=SQRT_SMALL, upper=GREAT, protected_cell=None,
+                          protected_patch_ids=(), max_cells=2147483647):
+        mcl = [np.full(m.n, max_cell_level, dtype=np.int32) if np.isscalar(max_cell_level) else _i32(max_cell_level[r])
+               for r, m in enumerate(self.meshes)]
+        rc = [np.zeros(m.n, dtype=np.uint8) for m in self.meshes]
+        rs = [np.zeros(m.n, dtype=np.uint8) for m in self.meshes]
+        pc = protected_cell if protected_cell is not None else [None] * self.R
+        ids = _i32(protected_patch_ids)
+        sweeps = lib().or_hex_select_refine(self._h, _pp(err), lower, upper, _pp(mcl), n_layers, _pp(pc), ids.ctypes.data,
+                                            len(ids), max_cells, _pp(rc), _pp(rs))
+        return rc, rs, sweeps
+
+    def hex_select_unrefine(self, err, refine_cell, n_layers, unrefine_level=-SQRT_SMALL, protected_cell=None,
+                            protected_patch_ids=()):
+        up = [np.zeros(m.p, dtype=np.uint8) for m in self.meshes]
+        sp = [np.zeros(m.p, dtype=np.uint8) for m in self.meshes]
+        pc = protected_cell if protected_cell is not None else [None] * self.R
+        ids = _i32(protected_patch_ids)
+        sweeps = lib().or_hex_select_unrefine(self._h, _pp(err), unrefine_level, n_layers, _pp(pc), ids.ctypes.data, len(ids),
+                                              _pp(refine_cell), _pp(up), _pp(sp))
+        if sweeps < 0:
+            raise RuntimeError("reference FatalError 'problem' (hexRef3D.C:1811)")
+        return up, sp, sweeps
+
+    def max_cell_field(self, r, v):
+        out = np.empty(self.meshes[r].p, dtype=np.float64)
+        lib().or_max_cell_field(self._h, r, v.ctypes.data, out.ctypes.data)
+        return out
+
+    def split_points(self, r):
+        out = np.zeros(self.meshes[r].p, dtype=np.uint8)
+        lib().or_get_split_points(self._h, r, out.ctypes.data)
+        return out
+
+    def check_levels(self, levels) -> int:
+        lv = [_i32(a) for a in levels]
+        return int(lib().or_check_levels(self._h, _pp(lv)))
+
+
+def remap_refine_cell(cell_map, reverse_map, refine_cell):
+    cell_map, reverse_map = _i32(cell_map), _i32(reverse_map)
+    out = np.zeros(len(cell_map), dtype=np.uint8)
+    lib().or_remap_refine_cell(len(cell_map), cell_map.ctypes.data, reverse_map.ctypes.data, refine_cell.ctypes.data,
+                               out.ctypes.data)
+    return out
+
+
+def map_field(cell_map, old, ncomp=1):
+    cell_map = _i32(cell_map)
+    old = np.ascontiguousarray(old, dtype=np.float64)
+    new = np.empty((len(cell_map),) + old.shape[1:], dtype=np.float64)
+    lib().or_map_field(len(cell_map), cell_map.ctypes.data, ncomp, old.ctypes.data, new.ctypes.data)
+    return new
+
+
+def map_field_conservative(cell_map, reverse_map, vol_old, old, ncomp=1):
+    cell_map, reverse_map = _i32(cell_map), _i32(reverse_map)
+    old = np.ascontiguousarray(old, dtype=np.float64)
+    vol_old = np.ascontiguousarray(vol_old, dtype=np.float64)
+    new = np.empty((len(cell_map),) + old.shape[1:], dtype=np.float64)
+    lib().or_map_field_conservative(len(reverse_map), len(cell_map), cell_map.ctypes.data, reverse_map.ctypes.data,
+                                    vol_old.ctypes.data, ncomp, old.ctypes.data, new.ctypes.data)
+    return new
+
+
+def update_levels(cell_map, old_level, refined_old=None, unrefined_old=None):
+    cell_map, old_level = _i32(cell_map), _i32(old_level)
+    out = np.empty(len(cell_map), dtype=np.int32)
+    lib().or_update_levels(len(cell_map), cell_map.ctypes.data, old_level.ctypes.data,
+                           None if refined_old is None else refined_old.ctypes.data,
+                           None if unrefined_old is None else unrefined_old.ctypes.data, out.ctypes.data)
+    return out

@@ -1,0 +1,213 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+
+from blastamr_b200 import mesh as M
+from tests import amr_cases as cases
+
+pytestmark = pytest.mark.gpu
+
+SQ = float(np.sqrt(1e-15))
+GREAT = 1e15
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from blastamr_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def flags_to_list(f):
+    return np.flatnonzero(f).astype(np.int32)
+
+
+@pytest.mark.parametrize("kind", ["delta", "scaledDelta", "fieldValue", "codedDelta"])
+@pytest.mark.parametrize("meshname", ["hex3D", "box32", "graded"])
+def test_estimators_bitwise(ctx, O, kind, meshname):
+    if meshname == "hex3D":
+        m = M.box_mesh(20, 20, 5, (0.1, 0.1, 0.01))
+        x = cases.box_field(m.cc)
+    elif meshname == "box32":
+        m = M.box_mesh(32, 32, 32)
+        x = cases.front_field(m.cc, w=2.0 / 32)
+    else:
+        m = cases.graded_octree(8, 2).build()
+        x = cases.front_field(m.cc, w=0.05) - 1.2   # negative values exercise mag()
+    w = O.World([m])
+    ctx.set_mesh(m)
+    kw = dict(p0=1e-3, p1=0.25) if kind == "scaledDelta" else {}
+    ref = w.estimate(kind, [x], min_val=kw.get("p0", 1e-15), offset=kw.get("p1", 0.0))[0]
+    got = ctx.estimate(kind, x, **kw)
+    assert np.array_equal(ref.view(np.int64), got.view(np.int64))
+    thr = (0.01, GREAT, 0.01, GREAT)
+    refn = ref.copy()
+    w.normalize([refn], thr[0], thr[1], thr[2], thr[3])
+    gotn = ctx.estimate(kind, x, thresholds=thr, **kw)
+    assert np.array_equal(refn, gotn)
+    g2 = ctx.normalize(got.copy(), *thr)
+    assert np.array_equal(refn, g2)
+
+
+@pytest.mark.parametrize("layers", [0, 1, 2, 3])
+@pytest.mark.parametrize("maxlev", [1, 3])
+def test_select_refine_box(ctx, O, layers, maxlev):
+    m = M.box_mesh(20, 20, 5, (0.1, 0.1, 0.01))
+    x = cases.box_field(m.cc)
+    w = O.World([m])
+    ctx.set_mesh(m)
+    err = w.estimate("fieldValue", [x])
+    w.normalize(err, 0.01, GREAT, 0.01, GREAT)
+    rc, rs, _ = w.hex_select_refine(err, maxlev, layers)
+    rc_g = np.zeros(m.n, np.uint8)
+    cells, sweeps = ctx.select_refine(err[0], maxlev, layers, refine_cell_out=rc_g)
+    assert np.array_equal(rc[0], rc_g)
+    assert np.array_equal(flags_to_list(rs[0]), cells)
+
+
+def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, protected=(), thr=0.01, kind="delta"):
+    """A multi-step AMR run; every stage is executed by the oracle and by the GPU and compared."""
+    stats = dict(refined=0, unrefined=0, sweeps=[])
+    for step in range(steps):
+        m = oc.build()
+        w = O.World([m])
+        ctx.set_mesh(m)
+        x = field_fn(m.cc, step)
+        e_ref = w.estimate(kind, [x])
+        e_gpu = ctx.estimate(kind, x)
+        assert np.array_equal(e_ref[0], e_gpu), f"step {step}: raw error differs"
+        w.normalize(e_ref, thr, GREAT, thr, GREAT)
+        e_gpu = ctx.estimate(kind, x, thresholds=(thr, GREAT, thr, GREAT))
+        assert np.array_equal(e_ref[0], e_gpu)
+        pid = [m.patch_id(nm) for nm in protected]
+        if pid:
+            c_ref = w.protect_patches(e_ref, pid, 1 + (maxlev - 1) * max(layers_ref, 1))
+            c_gpu = ctx.protect_patches(pid, 1 + (maxlev - 1) * max(layers_ref, 1), e_gpu)
+            assert c_ref[0] == c_gpu
+            assert np.array_equal(e_ref[0], e_gpu)
+        rc, rs, sw_ref = w.hex_select_refine(e_ref, maxlev, layers_ref, protected_patch_ids=pid)
+        rc_g = np.zeros(m.n, np.uint8)
+        cells, sw = ctx.select_refine(e_gpu, maxlev, layers_ref, protected_patch_ids=pid, refine_cell_out=rc_g)
+        assert np.array_equal(rc[0], rc_g), f"step {step}: refineCell differs"
+        ref_cells = flags_to_list(rs[0])
+        assert np.array_equal(ref_cells, cells), f"step {step}: cellsToRefine differs"
+        stats["sweeps"].append((sw_ref, sw))
+        refine_cell = rc[0]
+        err = e_ref[0]
+        fld = np.stack([x, 2 * x, -x], axis=1).copy()
+        if len(cells):
+            cell_map = oc.refine(cells)
+            rev = np.arange(m.n, dtype=np.int32)   # every old cell survives under its own label
+            new_rc = O.remap_refine_cell(cell_map, rev, refine_cell)
+            g_rc = np.zeros(len(cell_map), np.uint8)
+            ctx.remap_refine_cell(cell_map, rev, refine_cell, g_rc)
+            assert np.array_equal(new_rc, g_rc)
+            # field + error mapping, level update
+            assert np.array_equal(O.map_field(cell_map, fld, 3), ctx.map_field(cell_map, fld, ncomp=3))
+            err = O.map_field(cell_map, err, 1)
+            assert np.array_equal(err, ctx.map_field(cell_map, e_ref[0], ncomp=1))
+            lv_ref = O.update_levels(cell_map, m.cell_level, rs[0])
+            lv_gpu = ctx.update_levels(cell_map, m.cell_level, rs[0])
+            assert np.array_equal(lv_ref, lv_gpu)
+            m = oc.build()
+            assert np.array_equal(lv_ref, m.cell_level)     # the topology engine agrees with L2
+            w = O.World([m])
+            ctx.set_mesh(m)
+            assert ctx.check_levels() == 0 and w.check_levels([m.cell_level]) == 0
+            refine_cell = new_rc
+            stats["refined"] += len(cells)
+        # unrefinement on the (possibly new) mesh
+        rc_ref = refine_cell.copy()
+        up, sp, _ = w.hex_select_unrefine([err], [rc_ref], layers_unref, protected_patch_ids=pid)
+        assert np.array_equal(flags_to_list(sp[0]), ctx.split_elems())
+        rc_gpu = refine_cell.copy()
+        pts, _ = ctx.select_unrefine(err, layers_unref, refine_cell=rc_gpu, protected_patch_ids=pid)
+        assert np.array_equal(rc_ref, rc_gpu), f"step {step}: refineCell after unrefine layers differs"
+        ref_pts = flags_to_list(up[0])
+        assert np.array_equal(ref_pts, pts), f"step {step}: split points differ"
+        assert np.array_equal(w.max_cell_field(0, err), ctx.max_cell_field(err))
+        if len(pts):
+            vol = m.vol.copy()
+            n_old = m.n
+            cell_map, rev = oc.unrefine(m, pts)
+            unref_old = np.zeros(n_old, np.uint8)
+            for pt in pts:
+                unref_old[m.pc_cells[m.pc_off[pt]:m.pc_off[pt + 1]]] = 1
+            f_old = np.stack([x, 2 * x, -x], axis=1).copy() if n_old == len(x) else np.random.default_rng(1).random((n_old, 3))
+            assert np.array_equal(O.map_field(cell_map, f_old, 3), ctx.map_field(cell_map, f_old, ncomp=3))
+            c_ref = O.map_field_conservative(cell_map, rev, vol, f_old, 3)
+            c_gpu = ctx.map_field(cell_map, f_old, ncomp=3, mode=1, reverse_map=rev, vol_old=vol)
+            assert np.array_equal(c_ref, c_gpu)
+            lv_ref = O.update_levels(cell_map, m.cell_level, None, unref_old)
+            lv_gpu = ctx.update_levels(cell_map, m.cell_level, None, unref_old)
+            assert np.array_equal(lv_ref, lv_gpu)
+            m2 = oc.build()
+            assert np.array_equal(lv_ref, m2.cell_level)
+            stats["unrefined"] += len(pts)
+    return stats
+
+
+def moving_front(speed):
+    def fn(cc, step):
+        return cases.front_field(cc, centre=(0.35 + speed * step, 0.5, 0.5), r0=0.22, w=0.03)
+    return fn
+
+
+@pytest.mark.parametrize("n0,maxlev,layers", [(8, 2, (1, 1)), (10, 3, (2, 2)), (12, 2, (3, 6))])
+def test_amr_loop_moving_front(ctx, O, n0, maxlev, layers):
+    oc = M.Octree(n0, n0, n0, (1.0, 1.0, 1.0), maxlev)
+    st = amr_loop(ctx, O, oc, moving_front(0.06), steps=6, maxlev=maxlev, layers_ref=layers[0], layers_unref=layers[1])
+    assert st["refined"] > 0 and st["unrefined"] > 0
+
+
+def test_amr_loop_protected_patches(ctx, O):
+    oc = M.Octree(10, 10, 10, (1.0, 1.0, 1.0), 2)
+    st = amr_loop(ctx, O, oc, moving_front(0.08), steps=5, maxlev=2, layers_ref=1, layers_unref=2,
+                  protected=("movingWall",))
+    assert st["refined"] > 0
+
+
+def test_consistent_refinement_standalone(ctx, O):
+    m = cases.graded_octree(8, 3).build()
+    ctx.set_mesh(m)
+    w = O.World([m])
+    rng = np.random.default_rng(7)
+    for max_set in (True, False):
+        flags = (rng.random(m.n) < 0.05).astype(np.uint8)
+        ref = flags.copy()
+        w.consistent_refinement([ref], max_set)
+        got, _ = ctx.consistent_refinement(flags_to_list(flags), max_set)
+        assert np.array_equal(flags_to_list(ref), got)
+        # post-condition of checkWantedRefinementLevels: 2:1 holds for level + flag
+        lv = m.cell_level + ref
+        assert (np.abs(lv[m.owner[:m.f]] - lv[m.neighbour]) <= 1).all()
+
+
+def test_protected_cells_and_quota(ctx, O):
+    m = cases.graded_octree(8, 2).build()
+    ctx.set_mesh(m)
+    w = O.World([m])
+    rng = np.random.default_rng(3)
+    prot = (rng.random(m.n) < 0.02).astype(np.uint8)
+    ctx.set_protected_cells(prot)
+    err = [np.where(rng.random(m.n) < 0.2, 1.0, -1.0)]
+    for max_cells in (2147483647, m.n + 7 * 40):
+        rc, rs, _ = w.hex_select_refine(err, 3, 1, protected_cell=[prot], max_cells=max_cells)
+        rc_g = np.zeros(m.n, np.uint8)
+        cells, _ = ctx.select_refine(err[0], 3, 1, max_cells=max_cells, refine_cell_out=rc_g)
+        assert np.array_equal(rc[0], rc_g)
+        assert np.array_equal(flags_to_list(rs[0]), cells)
+    ctx.set_protected_cells(None)
+
+
+def test_no_cpu_fallback_message():
+    from blastamr_b200 import capi
+    with pytest.raises(capi.AmrError):
+        capi.Context(9999)
