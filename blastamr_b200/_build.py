@@ -67,7 +67,7 @@ def build_oracle(force: bool = False) -> Path:
     if not force and _newer(LIB_ORACLE, src):
         return LIB_ORACLE
     # -ffp-contract=off: no FMA contraction, x86-64 OpenFOAM builds have none either
-    _run(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=gnu11", "-pthread",
+    _run(["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-std=gnu11", "-pthread",
           "-o", str(LIB_ORACLE)] + [str(s) for s in csrc] + ["-lm"])
     return LIB_ORACLE
 

@@ -130,12 +130,12 @@ typedef struct mg_oct {
     i32 *freeSplit; i64 nfreeSplit, capfreeSplit;
     /* boundary: ordered list of (side, patch) ; side 0..5 = xmin xmax ymin ymax zmin zmax */
     int nside; int sideId[6], sidePatch[6];
-    int npatch; int patchType[6];
+    int npatch; int patchType[8]; int patchNbr[8];
 } mg_oct;
 
 MG_API mg_oct *mg_oct_create(int nx, int ny, int nz, double lx, double ly, double lz,
                              int lcap, int nside, const int *sideId, const int *sidePatch,
-                             int npatch, const int *patchType) {
+                             int npatch, const int *patchType, const int *patchNbr) {
     mg_oct *o = (mg_oct *)xcalloc(1, sizeof(mg_oct));
     o->nx = nx; o->ny = ny; o->nz = nz; o->lcap = lcap;
     o->L[0] = lx; o->L[1] = ly; o->L[2] = lz;
@@ -158,7 +158,7 @@ MG_API mg_oct *mg_oct_create(int nx, int ny, int nz, double lx, double ly, doubl
     }
     o->nside = nside; o->npatch = npatch;
     for (int s = 0; s < nside; s++) { o->sideId[s] = sideId[s]; o->sidePatch[s] = sidePatch[s]; }
-    for (int q = 0; q < npatch; q++) o->patchType[q] = patchType[q];
+    for (int q = 0; q < npatch; q++) { o->patchType[q] = patchType[q]; o->patchNbr[q] = patchNbr ? patchNbr[q] : -1; }
     return o;
 }
 
@@ -495,7 +495,7 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
             bside = (u8 *)xrealloc(bside, bcnt ? bcnt : 1);
             for (i64 i = before; i < bcnt; i++) bside[i] = (u8)o->sideId[s];
         }
-        for (int q = 0; q < o->npatch; q++) { m->patchType[q] = o->patchType[q]; m->patchNbr[q] = -1; }
+        for (int q = 0; q < o->npatch; q++) { m->patchType[q] = o->patchType[q]; m->patchNbr[q] = o->patchNbr[q]; }
     }
     i64 b = bcnt;
     m->f = f; m->b = b;

@@ -30,7 +30,7 @@ def lib():
         L = C.CDLL(str(path))
         L.mg_oct_create.restype = C.c_void_p
         L.mg_oct_create.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                                                     C.c_int, C.c_void_p]
+                                                                     C.c_int, C.c_void_p, C.c_void_p]
         L.mg_oct_free.argtypes = [C.c_void_p]
         L.mg_oct_ncells.restype = C.c_int64
         L.mg_oct_ncells.argtypes = [C.c_void_p]
@@ -162,7 +162,8 @@ CAVITY_SIDES = [("ymax", "movingWall"), ("xmin", "fixedWalls"), ("xmax", "fixedW
 class Octree:
     """A single hex block that can be cut 1->8 and merged 8->1 (the host 'topology engine')."""
 
-    def __init__(self, nx, ny, nz, lengths=(1.0, 1.0, 1.0), max_level=3, sides=None, patch_types=None):
+    def __init__(self, nx, ny, nz, lengths=(1.0, 1.0, 1.0), max_level=3, sides=None, patch_types=None,
+                 patch_nbr=None):
         sides = sides or CAVITY_SIDES
         names: List[str] = []
         for _, nm in sides:
@@ -172,12 +173,13 @@ class Octree:
         sid = np.array([SIDES[s] for s, _ in sides], dtype=np.int32)
         spa = np.array([names.index(nm) for _, nm in sides], dtype=np.int32)
         pty = np.array([patch_types.get(nm, PATCH_WALL) for nm in names], dtype=np.int32)
+        pnb = np.array([(patch_nbr or {}).get(nm, -1) for nm in names], dtype=np.int32)
         self.names = names
         self.dims = (nx, ny, nz)
         self.lengths = tuple(float(x) for x in lengths)
         self.max_level = max_level
         self._h = lib().mg_oct_create(nx, ny, nz, *self.lengths, max_level, len(sid), sid.ctypes.data,
-                                      spa.ctypes.data, len(names), pty.ctypes.data)
+                                      spa.ctypes.data, len(names), pty.ctypes.data, pnb.ctypes.data)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -221,9 +223,37 @@ class Octree:
         return cell_map, rev
 
 
-def box_mesh(nx, ny, nz, lengths=(1.0, 1.0, 1.0), points=True, sides=None, patch_types=None) -> PolyMesh:
+def box_mesh(nx, ny, nz, lengths=(1.0, 1.0, 1.0), points=True, sides=None, patch_types=None, patch_nbr=None) -> PolyMesh:
     """blockMesh-equivalent single hex block (level 0)."""
-    return Octree(nx, ny, nz, lengths, 0, sides, patch_types).build(points=points)
+    return Octree(nx, ny, nz, lengths, 0, sides, patch_types, patch_nbr).build(points=points)
+
+
+def subdomain_sides(rank: int, procs):
+    """Boundary layout of rank `rank` of a `simple (px py pz)` split of a box: outer sides are walls,
+    inner sides are processor patches towards the neighbouring rank (one patch per neighbour,
+    faces in the same order on both sides).  Returns (sides, patch_types, patch_nbr, (ix,iy,iz))."""
+    px, py, pz = procs
+    ix, iy, iz = rank % px, (rank // px) % py, rank // (px * py)
+    sides, types, nbr = [], {}, {}
+    walls, procsides = [], []
+    for name, axis, hi, idx, cnt in (("xmin", 0, 0, ix, px), ("xmax", 0, 1, ix, px), ("ymin", 1, 0, iy, py),
+                                     ("ymax", 1, 1, iy, py), ("zmin", 2, 0, iz, pz), ("zmax", 2, 1, iz, pz)):
+        outer = (idx == 0) if not hi else (idx == cnt - 1)
+        if outer:
+            walls.append((name, "walls"))
+        else:
+            d = [0, 0, 0]
+            d[axis] = 1 if hi else -1
+            r2 = (ix + d[0]) + px * ((iy + d[1]) + py * (iz + d[2]))
+            procsides.append((r2, name))
+    sides = walls[:]
+    types["walls"] = PATCH_WALL
+    for r2, name in sorted(procsides):
+        pn = f"procBoundary{rank}to{r2}"
+        sides.append((name, pn))
+        types[pn] = PATCH_PROCESSOR
+        nbr[pn] = r2
+    return sides, types, nbr, (ix, iy, iz)
 
 
 def simple_ranks(mesh: PolyMesh, lengths, procs) -> np.ndarray:

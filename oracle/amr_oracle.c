@@ -38,6 +38,25 @@ typedef uint8_t boolean;   /* boolList element */
 static const scalar SMALL = 1e-15;
 static const scalar GREAT = 1e15;
 
+/* Emulated ranks are independent between two syncTools calls, exactly like MPI ranks; the
+   multi-core CPU baseline runs them on separate threads (one thread per rank, like one MPI
+   process per core).  With or_set_threads(1) (default) everything is serial. */
+#ifdef _OPENMP
+#include <omp.h>
+#define DO_PRAGMA(x) _Pragma(#x)
+#define PAR_RANKS DO_PRAGMA(omp parallel for schedule(dynamic,1))
+#define PAR_RANKS_SUM(v) DO_PRAGMA(omp parallel for schedule(dynamic,1) reduction(+:v))
+#define PAR_RANKS_OR(v) DO_PRAGMA(omp parallel for schedule(dynamic,1) reduction(|:v))
+OR_API void or_set_threads(int t) { omp_set_num_threads(t < 1 ? 1 : t); }
+OR_API int or_max_threads(void) { return omp_get_max_threads(); }
+#else
+#define PAR_RANKS
+#define PAR_RANKS_SUM(v)
+#define PAR_RANKS_OR(v)
+OR_API void or_set_threads(int t) { (void)t; }
+OR_API int or_max_threads(void) { return 1; }
+#endif
+
 static inline scalar smax(scalar a, scalar b) { return (a > b) ? a : b; } /* Foam::max */
 static inline scalar smin(scalar a, scalar b) { return (a < b) ? a : b; } /* Foam::min */
 static inline scalar smag(scalar a) { return fabs(a); }                   /* Foam::mag */
@@ -222,6 +241,7 @@ OR_API void or_estimate(const or_world *w, int kind, const scalar *const *xin, s
                         scalar p0, scalar p1) {
     int R = w->R;
     scalar **x = (scalar **)malloc(sizeof(scalar *) * R);
+    PAR_RANKS
     for (int r = 0; r < R; r++) {
         const or_mesh *m = &w->m[r];
         x[r] = (scalar *)malloc(sizeof(scalar) * (size_t)(m->n ? m->n : 1));
@@ -245,6 +265,7 @@ OR_API void or_estimate(const or_world *w, int kind, const scalar *const *xin, s
         for (int64_t i = 0; i < m->b; i++) fn[r][i] = x[r][m->owner[m->f + i]];
     }
     swap_boundary_scalar(w, fn);
+    PAR_RANKS
     for (int r = 0; r < R; r++) {
         const or_mesh *m = &w->m[r];
         scalar *err = error[r];
@@ -284,6 +305,7 @@ OR_API void or_estimate(const or_world *w, int kind, const scalar *const *xin, s
 static void extend_across_faces(const or_world *w, boolean **markedCells) {
     int R = w->R;
     boolean **markedFace = (boolean **)malloc(sizeof(boolean *) * R);
+    PAR_RANKS
     for (int r = 0; r < R; r++) {
         const or_mesh *m = &w->m[r];
         markedFace[r] = (boolean *)calloc((size_t)(m->f + m->b + 1), 1);
@@ -292,6 +314,7 @@ static void extend_across_faces(const or_world *w, boolean **markedCells) {
                 for (label i = m->cfOff[cellI]; i < m->cfOff[cellI + 1]; i++) markedFace[r][m->cfFaces[i]] = 1;
     }
     sync_face_or(w, markedFace);
+    PAR_RANKS
     for (int r = 0; r < R; r++) {
         const or_mesh *m = &w->m[r];
         for (int64_t faceI = 0; faceI < m->f; faceI++)
@@ -308,6 +331,7 @@ static void extend_marked_cells(const or_world *w, boolean **markedCells, label 
                                 int isTop, int force) {
     int R = w->R;
     boolean **markedFace = (boolean **)malloc(sizeof(boolean *) * R);
+    PAR_RANKS
     for (int r = 0; r < R; r++) {
         const or_mesh *m = &w->m[r];
         markedFace[r] = (boolean *)calloc((size_t)(m->f + m->b + 1), 1);
@@ -320,6 +344,7 @@ static void extend_marked_cells(const or_world *w, boolean **markedCells, label 
         }
     }
     sync_face_or(w, markedFace);
+    PAR_RANKS
     for (int r = 0; r < R; r++) {
         const or_mesh *m = &w->m[r];
         for (int64_t facei = 0; facei < m->f; facei++)
@@ -396,6 +421,7 @@ static int64_t face_consistent_refinement(const or_world *w, int maxSet, boolean
     int R = w->R;
     int64_t nChangedTot = 0;
     label **neiLevel = (label **)malloc(sizeof(label *) * R);
+    PAR_RANKS_SUM(nChangedTot)
     for (int r = 0; r < R; r++) {
         const or_mesh *m = &w->m[r];
         boolean *rc = refineCell[r];
@@ -421,6 +447,7 @@ static int64_t face_consistent_refinement(const or_world *w, int maxSet, boolean
         nChangedTot += nChanged;
     }
     swap_boundary_label(w, neiLevel);
+    PAR_RANKS_SUM(nChangedTot)
     for (int r = 0; r < R; r++) {
         const or_mesh *m = &w->m[r];
         boolean *rc = refineCell[r];
@@ -530,6 +557,7 @@ OR_API int or_hex_select_refine(const or_world *w, const scalar *const *error, s
                                 boolean **refineCell, boolean **refineSet) {
     int R = w->R;
     /* selectRefineCandidates, fvMeshRefiner.C:170-187 (inclusive compares) */
+    PAR_RANKS
     for (int r = 0; r < R; r++)
         for (int64_t cellI = 0; cellI < w->m[r].n; cellI++)
             refineCell[r][cellI] = (error[r][cellI] >= lowerRefineLevel) && (error[r][cellI] <= upperRefineLevel);
@@ -554,10 +582,12 @@ OR_API int or_hex_select_refine(const or_world *w, const scalar *const *error, s
     for (int r = 0; r < R; r++) unrefineable[r] = (boolean *)calloc((size_t)(w->m[r].n + 1), 1);
     int haveU = calculate_protected_cells(w, protectedCell, unrefineable);
     int64_t nCandidates = 0;
+    PAR_RANKS_SUM(nCandidates)
     for (int r = 0; r < R; r++)
         for (int64_t c = 0; c < w->m[r].n; c++) nCandidates += refineCell[r][c] ? 1 : 0;
     for (int r = 0; r < R; r++) memset(refineSet[r], 0, (size_t)w->m[r].n);
     if (nCandidates < nTotToRefine) {
+        PAR_RANKS
         for (int r = 0; r < R; r++) {
             const or_mesh *m = &w->m[r];
             for (int64_t celli = 0; celli < m->n; celli++)
@@ -661,6 +691,7 @@ OR_API int or_consistent_unrefinement(const or_world *w, boolean **unrefinePoint
     int fail = 0;
     while (!fail) {
         int64_t nChanged = 0;
+        _Pragma("omp parallel for schedule(dynamic,1) reduction(+:nChanged) reduction(|:fail)")
         for (int r = 0; r < R; r++) {
             const or_mesh *m = &w->m[r];
             boolean *uc = unrefineCell[r];
@@ -681,7 +712,6 @@ OR_API int or_consistent_unrefinement(const or_world *w, boolean **unrefinePoint
                     uc[nei] = 0; nChanged++;
                 }
             }
-            if (fail) break;
             for (int64_t i = 0; i < m->b; i++) {
                 label own = m->owner[i + m->f];
                 neiLevel[r][i] = m->cellLevel[own] - uc[own];
@@ -743,6 +773,7 @@ OR_API int or_hex_select_unrefine(const or_world *w, const scalar *const *error,
             for (label i = 0; i < m->patchSize[q]; i++) refineCell[r][m->owner[m->patchStart[q] + i]] = 1;
         }
     }
+    PAR_RANKS
     for (int r = 0; r < R; r++) {
         const or_mesh *m = &w->m[r];
         scalar *pFld = (scalar *)malloc(sizeof(scalar) * (size_t)(m->p + 1));

@@ -25,7 +25,7 @@ def build(force: bool = False) -> Path:
     src = sorted(HERE.glob("*.c"))
     if not force and LIB.exists() and all(s.stat().st_mtime <= LIB.stat().st_mtime for s in src):
         return LIB
-    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=gnu11", "-pthread", "-o", str(LIB)] + \
+    cmd = ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-std=gnu11", "-pthread", "-o", str(LIB)] + \
           [str(s) for s in src] + ["-lm"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
@@ -66,6 +66,9 @@ def lib():
         L.or_map_field_conservative.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                 C.c_void_p, C.c_void_p]
         L.or_update_levels.argtypes = [C.c_int64] + [C.c_void_p] * 5
+        L.or_set_threads.argtypes = [C.c_int]
+        L.or_max_threads.restype = C.c_int
+        L.or_set_threads(1)
         _lib = L
     return _lib
 
@@ -206,3 +209,11 @@ def update_levels(cell_map, old_level, refined_old=None, unrefined_old=None):
                            None if refined_old is None else refined_old.ctypes.data,
                            None if unrefined_old is None else unrefined_old.ctypes.data, out.ctypes.data)
     return out
+
+
+def set_threads(t: int):
+    lib().or_set_threads(int(t))
+
+
+def max_threads() -> int:
+    return int(lib().or_max_threads())
