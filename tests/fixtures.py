@@ -1,0 +1,52 @@
+"""Loaders for the committed golden fixtures (tests/golden/*.npz)."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+from blastamr_b200.mesh import Patch, PolyMesh, PATCH_EMPTY, PATCH_WALL
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def load_reference_mesh(case: str) -> PolyMesh:
+    """The reference's own test mesh (tests/testCases/<case>/constant/polyMesh) with the point
+    addressing derived the way primitiveMesh does (pointCells / cellPoints from faces)."""
+    z = np.load(GOLDEN / f"{case}_mesh.npz")
+    owner, nei = z["owner"], z["neighbour"]
+    foff, fpts, pts = z["face_off"], z["face_pts"], z["points"]
+    f, nf = len(nei), len(owner)
+    n, p = int(owner.max()) + 1, len(pts)
+    patches = []
+    for nm, ty, st, sz in zip(z["patch_names"], z["patch_types"], z["patch_start"], z["patch_size"]):
+        patches.append(Patch(str(nm), PATCH_EMPTY if str(ty) == "empty" else PATCH_WALL, int(st), int(sz)))
+    # point -> cells through faces
+    face_of = np.repeat(np.arange(nf), np.diff(foff))
+    pairs = [np.stack([fpts, owner[face_of]], 1)]
+    internal = face_of < f
+    pairs.append(np.stack([fpts[internal], nei[face_of[internal]]], 1))
+    pc = np.unique(np.concatenate(pairs), axis=0)
+    pc_off = np.zeros(p + 1, np.int32)
+    np.add.at(pc_off, pc[:, 0] + 1, 1)
+    pc_off = np.cumsum(pc_off).astype(np.int32)
+    pc_cells = pc[:, 1].astype(np.int32)
+    cp = pc[np.lexsort((pc[:, 0], pc[:, 1]))]
+    cp_off = np.zeros(n + 1, np.int32)
+    np.add.at(cp_off, cp[:, 1] + 1, 1)
+    cp_off = np.cumsum(cp_off).astype(np.int32)
+    cp_pts = cp[:, 0].astype(np.int32)
+    bnd = np.zeros(p, np.uint8)
+    bnd[fpts[foff[f]:]] = 1
+    # cell centres = mean of the cell's points (exact for these hex blocks), volumes not needed
+    cc = np.zeros((n, 3))
+    np.add.at(cc, cp[:, 1], pts[cp[:, 0]])
+    cc /= np.diff(cp_off)[:, None]
+    return PolyMesh(n=n, f=f, b=nf - f, p=p, owner=owner.astype(np.int32), neighbour=nei.astype(np.int32), patches=patches,
+                    cc=cc, vol=None, pc_off=pc_off, pc_cells=pc_cells, cp_off=cp_off, cp_pts=cp_pts, bnd_point=bnd,
+                    cell_level=np.zeros(n, np.int32), point_level=np.zeros(p, np.int32),
+                    visible=np.full(n, -1, np.int32), split_parent=np.zeros(0, np.int32))
+
+
+def golden():
+    return np.load(GOLDEN / "oracle_golden.npz")

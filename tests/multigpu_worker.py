@@ -1,0 +1,92 @@
+"""Launched by torchrun (one rank per GPU): the C-ABI path with NCCL processor-patch halos on a
+decomposed graded mesh; every rank compares its slice with the serial oracle on the global mesh.
+Usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+       --master-port P tests/multigpu_worker.py"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+PROCS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from blastamr_b200 import capi, mesh as M
+    from oracle import oracle as O
+    from tests import amr_cases as cases
+
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    ctx = capi.Context(lr)
+    uid = [capi.Context.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(world, rank, uid[0])
+
+    oc = cases.graded_octree(12, 3, centre=(0.5, 0.5, 0.5), r0=0.3, band=0.1)
+    g = oc.build()
+    loc = M.decompose(g, M.simple_ranks(g, (1, 1, 1), PROCS[world]), world)
+    me = loc[rank]
+    cg = me.cell_global
+    thr = (0.01, 1e15, 0.01, 1e15)
+    w = O.World([g])
+    wR = O.World(loc)
+    ctx.set_mesh(me)
+    fails = []
+    for shift in (0.0, 0.04):
+        x = cases.front_field(g.cc, centre=(0.5 + shift, 0.5, 0.5), r0=0.3, w=0.03)
+        for kind in ("delta", "scaledDelta", "codedDelta"):
+            ref = w.estimate(kind, [x], min_val=1e-3)[0]
+            got = ctx.estimate(kind, x[cg].copy(), p0=1e-3)
+            if not np.array_equal(ref[cg], got):
+                fails.append(f"estimate {kind}")
+        e = w.estimate("delta", [x]); w.normalize(e, *thr)
+        eg = ctx.estimate("delta", x[cg].copy(), thresholds=thr)
+        if not np.array_equal(e[0][cg], eg):
+            fails.append("normalised error")
+        for layers in (1, 3):
+            rc, rs, _ = w.hex_select_refine(e, 3, layers)
+            rc_g = np.zeros(me.n, np.uint8)
+            cells, sweeps = ctx.select_refine(eg, 3, layers, refine_cell_out=rc_g)
+            if not np.array_equal(rc[0][cg], rc_g):
+                fails.append(f"refineCell layers={layers}")
+            if not np.array_equal(np.flatnonzero(rs[0][cg]), cells):
+                fails.append(f"cellsToRefine layers={layers}")
+            # unrefinement: local split points exclude processor-boundary points -> compare with the
+            # multi-rank oracle world (same decomposition), which restates exactly that
+            eR = [e[0][l.cell_global].copy() for l in loc]
+            rcR = [rc[0][l.cell_global].copy() for l in loc]
+            upR, spR, _ = wR.hex_select_unrefine(eR, rcR, layers)
+            rc_in = rc[0][cg].copy()
+            pts, _ = ctx.select_unrefine(eg, layers, refine_cell=rc_in)
+            if not np.array_equal(np.flatnonzero(upR[rank]), pts):
+                fails.append(f"unrefine points layers={layers}")
+            if not np.array_equal(rcR[rank], rc_in):
+                fails.append(f"refineCell after unrefine layers layers={layers}")
+        if ctx.check_levels() != 0:
+            fails.append("check_levels")
+        # protect patches across ranks
+        pid = [me.patch_id("movingWall")]
+        e2 = e[0].copy(); w.protect_patches([e2], pid, 3)
+        e2g = eg.copy(); ctx.protect_patches(pid, 3, e2g)
+        if not np.array_equal(e2[cg], e2g):
+            fails.append("protect_patches")
+    t = torch.tensor([len(fails)], device="cuda")
+    dist.all_reduce(t)
+    if fails:
+        print(f"rank {rank} FAILED: {fails}", flush=True)
+    if rank == 0:
+        print("MULTIGPU_PARITY", "OK" if int(t) == 0 else "FAIL", "world", world, flush=True)
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(1 if int(t) else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,126 @@
+"""Independent numpy restatement ("second opinion") of the order-free parts of the path.
+
+The C oracle follows the reference's in-place face loops (Gauss-Seidel).  The functions here compute
+the same quantities from their mathematical definition -- max over face neighbours, Jacobi fixed-point
+iteration of the 2:1 rule, set-based split-point detection -- so agreement between the two is evidence
+for the claim that the reference's results do not depend on sweep order.
+"""
+import numpy as np
+
+
+def delta(mesh, x, clamp=0.5):
+    own, nei = mesh.owner[:mesh.f], mesh.neighbour
+    d = np.abs(x[own] - x[nei])
+    if clamp is not None:
+        d = np.minimum(d, clamp)
+    e = np.zeros(mesh.n)
+    np.maximum.at(e, own, d)
+    np.maximum.at(e, nei, d)
+    return e
+
+
+def scaled_delta(mesh, x, min_val, offset):
+    x = np.abs(x)
+    if abs(offset) > 1e-15:
+        x = x - offset
+    own, nei = mesh.owner[:mesh.f], mesh.neighbour
+    d = np.abs(x[own] - x[nei]) / np.maximum(np.minimum(x[own], x[nei]), min_val)
+    e = np.zeros(mesh.n)
+    np.maximum.at(e, own, d)
+    np.maximum.at(e, nei, d)
+    return e
+
+
+def normalize(e, lr, ur, lu, uu):
+    out = np.zeros_like(e)
+    ref = (e > lr) & (e < ur)
+    unr = (e < lu) | (e > uu)
+    out[ref] = 1.0
+    out[unr] = -1.0
+    return out
+
+
+def grow(mesh, marked, src=None):
+    """one face layer: cell marked if it or a face neighbour (in src) is marked"""
+    own, nei = mesh.owner[:mesh.f], mesh.neighbour
+    src = marked if src is None else src
+    out = marked.copy()
+    np.logical_or.at(out, own, src[nei])
+    np.logical_or.at(out, nei, src[own])
+    return out
+
+
+def closure_refine(mesh, flags):
+    """least fixed point of the 2:1 rule (maxSet=true), Jacobi iteration"""
+    own, nei = mesh.owner[:mesh.f], mesh.neighbour
+    flags = flags.astype(bool).copy()
+    it = 0
+    while True:
+        lv = mesh.cell_level + flags
+        add_n = lv[own] > lv[nei] + 1
+        add_o = lv[nei] > lv[own] + 1
+        new = flags.copy()
+        new[nei[add_n]] = True
+        new[own[add_o]] = True
+        it += 1
+        if (new == flags).all():
+            return flags, it
+        flags = new
+
+
+def closure_unselect(mesh, flags):
+    """greatest fixed point (maxSet=false)"""
+    own, nei = mesh.owner[:mesh.f], mesh.neighbour
+    flags = flags.astype(bool).copy()
+    while True:
+        lv = mesh.cell_level + flags
+        bad_o = lv[own] > lv[nei] + 1
+        bad_n = lv[nei] > lv[own] + 1
+        new = flags.copy()
+        new[own[bad_o]] = False
+        new[nei[bad_n]] = False
+        if (new == flags).all():
+            return flags
+        flags = new
+
+
+def split_points(mesh):
+    """hexRef3D::getSplitElems from its definition"""
+    p = mesh.p
+    cnt = np.diff(mesh.pc_off)
+    par = np.where(mesh.visible >= 0, mesh.split_parent[np.maximum(mesh.visible, 0)] if len(mesh.split_parent) else -1, -1)
+    par = np.where(par < 0, -1, par)
+    out = np.zeros(p, bool)
+    for pt in np.flatnonzero((cnt == 8) & (mesh.bnd_point == 0)):
+        cs = mesh.pc_cells[mesh.pc_off[pt]:mesh.pc_off[pt + 1]]
+        if par[cs[0]] >= 0 and (par[cs] == par[cs[0]]).all() and (mesh.cell_level[cs] == mesh.cell_level[cs[0]]).all():
+            out[pt] = True
+    return out
+
+
+def max_cell_field(mesh, v):
+    out = np.full(mesh.p, -1e15)
+    pts = np.repeat(np.arange(mesh.p), np.diff(mesh.pc_off))
+    np.maximum.at(out, pts, v[mesh.pc_cells])
+    return out
+
+
+def closure_unrefine(mesh, pflags):
+    """greatest set of points whose merged cells keep 2:1 (Jacobi)"""
+    own, nei = mesh.owner[:mesh.f], mesh.neighbour
+    pts = np.repeat(np.arange(mesh.p), np.diff(mesh.pc_off))
+    pf = pflags.astype(bool).copy()
+    while True:
+        uc = np.zeros(mesh.n, bool)
+        uc[mesh.pc_cells[pf[pts]]] = True
+        lv = mesh.cell_level - uc
+        bad = np.zeros(mesh.n, bool)
+        bad[own[lv[own] < lv[nei] - 1]] = True
+        bad[nei[lv[nei] < lv[own] - 1]] = True
+        if not bad.any():
+            return pf
+        uc &= ~bad
+        # knock out points with a cell that cannot be unrefined
+        ok = np.ones(mesh.p, bool)
+        np.logical_and.at(ok, pts, uc[mesh.pc_cells])
+        pf &= ok

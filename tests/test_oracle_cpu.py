@@ -1,0 +1,241 @@
+"""CPU tests: mesh generator vs the reference's fixtures, oracle vs golden vectors, oracle vs an
+independent numpy restatement, and the order-independence invariants."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from blastamr_b200 import mesh as M
+from oracle import oracle as O
+from tests import amr_cases as cases
+from tests import np_reference as NP
+from tests.fixtures import GOLDEN, golden, load_reference_mesh
+
+GREAT = 1e15
+
+
+def fl(a):
+    return np.flatnonzero(a).astype(np.int32)
+
+
+# ---------------------------------------------------------------- generator vs reference fixture
+
+def test_box_generator_reproduces_reference_hex3D():
+    z = np.load(GOLDEN / "hex3D_mesh.npz")
+    m = M.box_mesh(20, 20, 5, (0.1, 0.1, 0.01))
+    assert np.array_equal(m.owner, z["owner"]) and np.array_equal(m.neighbour, z["neighbour"])
+    assert [q.start for q in m.patches] == list(z["patch_start"]) and [q.size for q in m.patches] == list(z["patch_size"])
+    assert [q.name for q in m.patches] == [str(s) for s in z["patch_names"]]
+    # same point numbering: cell centres computed from the fixture's points agree
+    ref = load_reference_mesh("hex3D")
+    assert np.allclose(ref.cc, m.cc, atol=1e-12)
+    assert np.array_equal(ref.pc_off, m.pc_off) and np.array_equal(ref.pc_cells, m.pc_cells)
+    assert np.array_equal(ref.bnd_point, m.bnd_point)
+
+
+@pytest.mark.skipif(not Path("/root/reference/tests/testCases/hex3D").exists(), reason="reference tree not mounted")
+def test_golden_mesh_fixture_matches_reference_tree():
+    import re
+    t = Path("/root/reference/tests/testCases/hex3D/constant/polyMesh/owner").read_text()
+    body = t[t.index("}") + 1:]
+    m_ = re.search(r"(\d+)\s*\(", body)
+    own = np.array(body[m_.end():body.rindex(")")].split(), dtype=np.int32)
+    assert np.array_equal(own, np.load(GOLDEN / "hex3D_mesh.npz")["owner"])
+
+
+# ---------------------------------------------------------------- oracle vs golden vectors
+
+@pytest.mark.parametrize("case", ["hex3D", "hex2D"])
+def test_oracle_matches_golden_estimators(case):
+    g = golden()
+    m = load_reference_mesh(case)
+    w = O.World([m])
+    x = cases.box_field(m.cc)
+    e = w.estimate("fieldValue", [x])
+    w.normalize(e, 0.01, GREAT, 0.01, GREAT)
+    assert np.array_equal(e[0].astype(np.int8), g[f"{case}_fieldValue_norm"])
+    y = cases.front_field(m.cc, centre=(0.05, 0.05, 0.005), r0=0.03, w=0.01)
+    for kind, kw in (("delta", {}), ("scaledDelta", dict(min_val=1e-3, offset=0.25)), ("codedDelta", {})):
+        got = w.estimate(kind, [y], **kw)[0]
+        assert np.array_equal(got.view(np.int64), g[f"{case}_{kind}_raw"].view(np.int64))
+
+
+@pytest.mark.parametrize("layers", [1, 2])
+@pytest.mark.parametrize("maxlev", [1, 3])
+def test_oracle_matches_golden_selection(layers, maxlev):
+    """the reference's own test matrix (adaptiveFvMeshTest.C:77-80) on its hex3D mesh"""
+    g = golden()
+    m = load_reference_mesh("hex3D")
+    w = O.World([m])
+    e = w.estimate("fieldValue", [cases.box_field(m.cc)])
+    w.normalize(e, 0.01, GREAT, 0.01, GREAT)
+    rc, rs, _ = w.hex_select_refine(e, maxlev, layers)
+    assert np.array_equal(fl(rc[0]), g[f"hex3D_refineCell_L{layers}_M{maxlev}"])
+    assert np.array_equal(fl(rs[0]), g[f"hex3D_cellsToRefine_L{layers}_M{maxlev}"])
+    # the reference asserts only that the box gets refined (cell count grows >= 4x inside the box)
+    inside = cases.box_field(m.cc) > 0
+    assert rs[0][inside].all() and rs[0].sum() > inside.sum()
+
+
+# ---------------------------------------------------------------- oracle vs numpy second opinion
+
+@pytest.fixture(scope="module")
+def graded():
+    oc = cases.graded_octree(8, 3)
+    return oc, oc.build()
+
+
+def test_estimators_vs_numpy(graded):
+    _, m = graded
+    w = O.World([m])
+    x = cases.front_field(m.cc, w=0.05) - 1.2
+    assert np.array_equal(w.estimate("delta", [x])[0], NP.delta(m, x))
+    assert np.array_equal(w.estimate("codedDelta", [x])[0], NP.delta(m, x, clamp=None))
+    assert np.array_equal(w.estimate("scaledDelta", [x], min_val=1e-3, offset=0.2)[0], NP.scaled_delta(m, x, 1e-3, 0.2))
+    assert np.array_equal(w.estimate("fieldValue", [x])[0], np.abs(x))
+    e = [NP.delta(m, x)]
+    ref = NP.normalize(e[0], 0.02, 0.4, 0.01, GREAT)
+    w.normalize(e, 0.02, 0.4, 0.01, GREAT)
+    assert np.array_equal(e[0], ref)
+
+
+def test_normalize_strict_compares():
+    # unrefine test wins; all four compares are strict (errorEstimator.C:208-227)
+    e = [np.array([0.01, 0.02, 0.5, 0.015, 0.005, 0.6])]
+    O.World.normalize(e, 0.02, 0.5, 0.01, 0.55)
+    assert list(e[0]) == [0.0, 0.0, 0.0, 0.0, -1.0, -1.0]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_refine_closure_order_independent(graded, seed):
+    _, m = graded
+    w = O.World([m])
+    rng = np.random.default_rng(seed)
+    f0 = (rng.random(m.n) < 0.03).astype(np.uint8)
+    gs = f0.copy()
+    w.consistent_refinement([gs], True)
+    jac, _ = NP.closure_refine(m, f0)
+    assert np.array_equal(gs.astype(bool), jac)
+    # idempotent, 2:1 after, minimal (dropping any added cell breaks 2:1)
+    again = gs.copy()
+    assert w.consistent_refinement([again], True) == 1 and np.array_equal(again, gs)
+    lv = m.cell_level + gs
+    assert (np.abs(lv[m.owner[:m.f]] - lv[m.neighbour]) <= 1).all()
+    added = fl(gs.astype(bool) & ~f0.astype(bool))
+    for c in added[:25]:
+        t = gs.copy()
+        t[c] = 0
+        lv = m.cell_level + t
+        assert (np.abs(lv[m.owner[:m.f]] - lv[m.neighbour]) > 1).any()
+    # maxSet = false
+    gs2 = f0.copy()
+    w.consistent_refinement([gs2], False)
+    assert np.array_equal(gs2.astype(bool), NP.closure_unselect(m, f0))
+
+
+def test_extend_layers_vs_numpy(graded):
+    _, m = graded
+    w = O.World([m])
+    rng = np.random.default_rng(5)
+    err = [np.where(rng.random(m.n) < 0.02, 1.0, 0.0)]
+    for layers in (0, 1, 3):
+        rc, _, _ = w.hex_select_refine(err, 3, layers)
+        mark = err[0] > 0
+        for i in range(layers):
+            src = mark & (m.cell_level < 3) if i == 0 else mark      # force=true, isTop (fvMeshRefiner.C:809-813)
+            mark = NP.grow(m, mark, src)
+        assert np.array_equal(rc[0].astype(bool), mark)
+
+
+def test_unrefine_stage_vs_numpy(graded):
+    oc, m = graded
+    w = O.World([m])
+    assert np.array_equal(w.split_points(0).astype(bool), NP.split_points(m))
+    assert w.split_points(0).sum() > 0
+    rng = np.random.default_rng(9)
+    err = rng.choice([-1.0, 0.0, 1.0], size=m.n, p=[0.8, 0.1, 0.1])
+    assert np.array_equal(w.max_cell_field(0, err), NP.max_cell_field(m, err))
+    marked = (rng.random(m.n) < 0.01).astype(np.uint8)
+    rc = marked.copy()
+    up, sp, _ = w.hex_select_unrefine([err], [rc], 1)
+    m1 = NP.grow(m, marked.astype(bool))
+    assert np.array_equal(rc.astype(bool), m1)
+    pf = NP.max_cell_field(m, err)
+    pts = np.repeat(np.arange(m.p), np.diff(m.pc_off))
+    any_marked = np.zeros(m.p, bool)
+    np.logical_or.at(any_marked, pts, m1[m.pc_cells])
+    cand = NP.split_points(m) & (pf < -np.sqrt(1e-15)) & ~any_marked
+    assert np.array_equal(up[0].astype(bool), NP.closure_unrefine(m, cand))
+    assert up[0].sum() > 0
+    # post-condition: merging the selected points keeps 2:1 and the lists are ascending/unique
+    uc = np.zeros(m.n, bool)
+    uc[m.pc_cells[up[0].astype(bool)[pts]]] = True
+    lv = m.cell_level - uc
+    assert (np.abs(lv[m.owner[:m.f]] - lv[m.neighbour]) <= 1).all()
+
+
+def test_multirank_world_equals_serial():
+    """decisions do not depend on the decomposition (processor-patch swaps restated)"""
+    oc = cases.graded_octree(8, 2)
+    m = oc.build()
+    x = cases.front_field(m.cc, w=0.05)
+    for procs, R in (((2, 1, 1), 2), ((2, 2, 1), 4), ((1, 3, 2), 6)):
+        loc = M.decompose(m, M.simple_ranks(m, (1, 1, 1), procs), R)
+        assert sum(l.n for l in loc) == m.n
+        w1, wR = O.World([m]), O.World(loc)
+        for kind in ("delta", "scaledDelta"):
+            e1 = w1.estimate(kind, [x], min_val=1e-3)
+            eR = wR.estimate(kind, [x[l.cell_global] for l in loc], min_val=1e-3)
+            for l, e in zip(loc, eR):
+                assert np.array_equal(e1[0][l.cell_global], e)
+        w1.normalize(e1, 0.01, GREAT, 0.01, GREAT)
+        wR.normalize(eR, 0.01, GREAT, 0.01, GREAT)
+        rc1, rs1, _ = w1.hex_select_refine(e1, 3, 2)
+        rcR, rsR, _ = wR.hex_select_refine(eR, 3, 2)
+        for l, a, b in zip(loc, rcR, rsR):
+            assert np.array_equal(rc1[0][l.cell_global], a) and np.array_equal(rs1[0][l.cell_global], b)
+        assert w1.check_levels([m.cell_level]) == 0 and wR.check_levels([l.cell_level for l in loc]) == 0
+
+
+def test_field_map_and_levels():
+    oc = M.Octree(4, 4, 4, max_level=2)
+    m = oc.build()
+    cells = np.array([5, 21, 22], np.int32)
+    cm = oc.refine(cells)
+    x = np.arange(m.n, dtype=np.float64)
+    assert np.array_equal(O.map_field(cm, x), x[cm])
+    v = np.stack([x, -x, 2 * x], 1).copy()
+    assert np.array_equal(O.map_field(cm, v, 3), v[cm])
+    ref = np.zeros(m.n, np.uint8)
+    ref[cells] = 1
+    lv = O.update_levels(cm, m.cell_level, ref)
+    m1 = oc.build()
+    assert np.array_equal(lv, m1.cell_level)
+    # unrefine one parent again: direct map keeps the master's own value; conservative averages
+    w = O.World([m1])
+    sp = fl(w.split_points(0))
+    assert len(sp) == 3
+    vol = m1.vol.copy()
+    y = np.random.default_rng(0).random(m1.n)
+    cm2, rev = oc.unrefine(m1, sp[:1])
+    d = O.map_field(cm2, y)
+    assert np.array_equal(d, y[cm2])
+    c = O.map_field_conservative(cm2, rev, vol, y)
+    master = -rev[rev < -1][0] - 2
+    merged = np.flatnonzero((rev == -master - 2) | (rev == master))
+    assert len(merged) == 8
+    assert np.isclose(c[master], (vol[merged] * y[merged]).sum() / vol[merged].sum(), rtol=1e-15)
+    keep = np.ones(len(cm2), bool)
+    keep[master] = False
+    assert np.array_equal(c[keep], d[keep])
+    # conservation of sum(V phi)
+    m2 = oc.build()
+    assert np.isclose((m2.vol * c).sum(), (vol * y).sum(), rtol=1e-13)
+
+
+def test_amr_loop_on_cpu_runs_both_branches():
+    """the multi-step driver used by the GPU parity tests, answered by the oracle itself"""
+    import tests.test_gpu_parity as T
+    oc = M.Octree(8, 8, 8, (1.0, 1.0, 1.0), 2)
+    st = T.amr_loop(cases.OracleBackend(), O, oc, T.moving_front(0.06), steps=5, maxlev=2, layers_ref=1, layers_unref=1)
+    assert st["refined"] > 0 and st["unrefined"] > 0
