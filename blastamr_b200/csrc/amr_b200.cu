@@ -7,9 +7,40 @@
 #include "scan.cuh"
 #include "sell.cuh"
 #include "kernels.cuh"
+#include "kernels_pipe.cuh"
 
 #include <algorithm>
 #include <new>
+
+// ============================================================================ pipeline launch
+
+constexpr size_t kPipeSmemLimit = 96 * 1024;   // beyond this the ring would cost too much occupancy: direct kernels
+
+static bool pipeOk(const amr_ctx *ctx, const Sell &S) {
+    return ctx->usePipeline && S.rows > 0 && pipeSmemBytes(S.maxTileInts) <= kPipeSmemLimit;
+}
+
+template <class K, class... Args>
+static int launchPipe(amr_ctx *ctx, K kern, const Sell &S, Args... args) {
+    SellView V{S.sliceOff, S.col, S.rows, S.slices, S.maxTileInts};
+    const size_t smem = pipeSmemBytes(V.stageInts);
+    const void *key = (const void *)kern;
+    auto it = ctx->occCache.find(key);
+    int perSM;
+    if (it == ctx->occCache.end()) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemLimit));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kPipeThreads, smem));
+        if (perSM < 1) perSM = 1;
+        ctx->occCache[key] = perSM;
+    } else perSM = it->second;
+    const int64_t ntiles = (S.slices + kTileSlices - 1) / kTileSlices;
+    int64_t grid = (int64_t)ctx->numSMs * perSM;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kPipeThreads, smem, ctx->stream>>>(V, args...);
+    ctx->launches++;
+    return AMR_OK;
+}
 
 // ============================================================================ context
 
@@ -24,6 +55,12 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
     amr_ctx *ctx = new (std::nothrow) amr_ctx();
     if (!ctx) return AMR_ERR_CUDA;
     ctx->device = device;
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->numSMs = sms;
+        const char *np = getenv("AMR_B200_NO_PIPELINE");
+        if (np && np[0] == '1') ctx->usePipeline = false;
+    }
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return AMR_ERR_CUDA;
@@ -50,6 +87,7 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->ghost8); devFree(ctx, &ctx->send8); devFree(ctx, &ctx->ghost64); devFree(ctx, &ctx->send64);
     devFree(ctx, &ctx->tileCnt); devFree(ctx, &ctx->scanAux);
     ctx->havePoints = ctx->haveLevels = ctx->haveHistory = false;
+    ctx->occCache.clear();
     ctx->refineCellN = 0;
     ctx->devBytes = 0;
     for (auto &bf : ctx->arena) ctx->devBytes += (int64_t)bf.cap;
@@ -290,7 +328,10 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
             const int32_t *so = ctx->cc.sliceOff, *col = ctx->cc.col;
 #define EST(K)                                                                                                   \
     do {                                                                                                         \
-        if (scale) LAUNCH((k_estimate<K, true>), gridFor(n), kThreads, n, so, col, dx, ghost, p0, p1, t, target); \
+        if (pipeOk(ctx, ctx->cc)) {                                                                              \
+            if (scale) TRY(launchPipe(ctx, kp_estimate<K, true>, ctx->cc, dx, ghost, p0, p1, t, target));        \
+            else TRY(launchPipe(ctx, kp_estimate<K, false>, ctx->cc, dx, ghost, p0, p1, t, target));             \
+        } else if (scale) LAUNCH((k_estimate<K, true>), gridFor(n), kThreads, n, so, col, dx, ghost, p0, p1, t, target); \
         else LAUNCH((k_estimate<K, false>), gridFor(n), kThreads, n, so, col, dx, ghost, p0, p1, t, target);      \
     } while (0)
             if (kind == AMR_EST_DELTA) EST(0);
@@ -329,7 +370,8 @@ static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res) 
         LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, src, ctx->send8);
         TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
     }
-    LAUNCH(k_extend, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, cur, src, ctx->ghost8, tmp);
+    if (pipeOk(ctx, ctx->cc)) TRY(launchPipe(ctx, kp_extend, ctx->cc, (const u8 *)cur, src, (const u8 *)ctx->ghost8, tmp));
+    else LAUNCH(k_extend, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, cur, src, ctx->ghost8, tmp);
     *res = tmp;
     return AMR_OK;
 }
@@ -401,7 +443,10 @@ static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOu
             TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
         }
         if (n) {
-            if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
+            if (pipeOk(ctx, ctx->cc)) {
+                if (maxSet) TRY(launchPipe(ctx, kp_refine_sweep<true>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
+                else TRY(launchPipe(ctx, kp_refine_sweep<false>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
+            } else if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
             else LAUNCH(k_refine_sweep_min, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
         }
         sweeps++;
@@ -678,8 +723,13 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     if (n) CK(cudaMemcpyAsync(dRc, cur, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     // U1+U2+U3 fused: maxCellField + getSplitElems + filter
     u8 *pflag = ctx->flagC;
-    if (p) LAUNCH(k_select_unrefine_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, ctx->pc.count, ctx->bndPoint,
-                  ctx->parentIdx, ctx->lvl8, dErr, unrefineLevel, dRc, (u8 *)nullptr, pflag);
+    if (p) {
+        if (pipeOk(ctx, ctx->pc))
+            TRY(launchPipe(ctx, kp_select_unrefine_points, ctx->pc, (const u8 *)ctx->pc.count, (const u8 *)ctx->bndPoint,
+                           (const label *)ctx->parentIdx, (const u8 *)ctx->lvl8, dErr, unrefineLevel, (const u8 *)dRc, (u8 *)nullptr, pflag));
+        else LAUNCH(k_select_unrefine_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, ctx->pc.count, ctx->bndPoint,
+                    ctx->parentIdx, ctx->lvl8, dErr, unrefineLevel, dRc, (u8 *)nullptr, pflag);
+    }
     // B3: consistentUnrefinement(list, false)   (cur/tmp are free again: flagA/flagB)
     TRY(unrefineSweeps(ctx, pflag, sweepsOut));
     TRY(emitList(ctx, pflag, p, elemsOut, nOut));

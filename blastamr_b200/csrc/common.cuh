@@ -7,6 +7,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <unordered_map>
 
 #include "amr_b200.h"
 
@@ -39,6 +40,7 @@ struct Sell {
     int32_t *sliceOff = nullptr;  // [slices+1], exclusive prefix of the slice widths
     int32_t *col = nullptr;       // [entries]
     u8 *count = nullptr;          // [rows] true row length (saturated at 255)
+    int maxTileInts = 0;          // largest 8-slice tile, in int32 (ring stage capacity of the TMA pipeline)
 };
 
 struct amr_ctx {
@@ -48,6 +50,9 @@ struct amr_ctx {
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
     std::string err;
+    int numSMs = 148;
+    bool usePipeline = true;                       // TMA-staged SELL kernels (AMR_B200_NO_PIPELINE=1 disables)
+    std::unordered_map<const void *, int> occCache; // kernel -> resident CTAs per SM at the current smem size
     int64_t launches = 0;
     int64_t devBytes = 0;
 

@@ -1,0 +1,116 @@
+// pipeline.cuh -- persistent, warp-specialised SELL tile pipeline for sm_100a.
+//
+// The adjacency (SELL-32 column blocks) is the one large, perfectly sequential stream of every
+// gather kernel on this path (24 B/cell on a hex mesh against 8-16 B/cell of field data), and it is
+// what the per-cell gathers depend on.  Loading it with ordinary LDGs puts two DRAM latencies in
+// series in every thread (labels -> values).  Here a producer warp streams whole tiles
+// (8 slices = 256 rows, contiguous in memory) into a shared-memory ring with the TMA bulk-copy
+// engine (cp.async.bulk, SASS UBLKCP) several tiles ahead, signalled through mbarriers; the 8
+// consumer warps read their labels from shared memory (column-major: conflict-free) and keep only
+// the value gathers in flight.  One CTA per resident slot (persistent grid), tiles round-robin.
+#pragma once
+#include "common.cuh"
+
+constexpr int kTileSlices = 8;                       // slices per tile
+constexpr int kTileRows = kTileSlices * kSlice;      // 256 rows per tile
+constexpr int kPipeThreads = kTileRows + 32;         // 8 consumer warps + 1 producer warp
+constexpr int kStages = 3;
+constexpr int kHdrInts = 12;                         // slice offsets of a tile (9 used), 48 B = 3 x 16 B
+
+__device__ __forceinline__ unsigned smemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarArrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smemAddr(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+
+struct SellView {
+    const int32_t *sliceOff;   // [slices + 16], tail padded
+    const int32_t *col;
+    int64_t rows, slices;
+    int stageInts;             // capacity of one ring stage in int32 (>= largest tile)
+};
+
+// dynamic shared memory layout: [kStages][stageInts] labels | [kStages][kHdrInts] headers | barriers
+__host__ __device__ inline size_t pipeSmemBytes(int stageInts) {
+    return (size_t)kStages * stageInts * 4 + (size_t)kStages * kHdrInts * 4 + 2 * kStages * 8 + 64;
+}
+
+// Body signature: void body(int64_t row, bool valid, const int32_t* rowLabels /*smem, stride 32*/, int width)
+// called by every consumer thread once per tile (valid=false for rows >= S.rows; all 32 lanes of a
+// warp call it together so that warp collectives inside the body are legal).
+template <class Body>
+__device__ __forceinline__ void sellPipeline(const SellView &S, Body body) {
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    int32_t *ring = reinterpret_cast<int32_t *>(smemRaw);
+    int32_t *hdr = ring + (size_t)kStages * S.stageInts;
+    uint64_t *full = reinterpret_cast<uint64_t *>(hdr + kStages * kHdrInts);
+    uint64_t *empty = full + kStages;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) { mbarInit(&full[s], 1); mbarInit(&empty[s], kTileSlices); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t ntiles = (S.slices + kTileSlices - 1) / kTileSlices;
+    if (warp == kTileSlices) {
+        // ---------------- producer warp (one elected lane drives the TMA engine)
+        if (lane == 0) {
+            int stage = 0;
+            unsigned phase = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                mbarWait(&empty[stage], phase ^ 1u);
+                const int64_t s0 = t * kTileSlices;
+                const int64_t s1 = min(s0 + (int64_t)kTileSlices, S.slices);
+                const int32_t b0 = S.sliceOff[s0], b1 = S.sliceOff[s1];
+                const unsigned bytes = (unsigned)(b1 - b0) * 128u;
+                mbarExpectTx(&full[stage], bytes + kHdrInts * 4);
+                bulkLoad(hdr + stage * kHdrInts, S.sliceOff + s0, kHdrInts * 4, &full[stage]);
+                if (bytes) bulkLoad(ring + (size_t)stage * S.stageInts, S.col + ((size_t)b0 << 5), bytes, &full[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ---------------- consumer warps
+        int stage = 0;
+        unsigned phase = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            mbarWait(&full[stage], phase);
+            const int32_t *h = hdr + stage * kHdrInts;
+            const int64_t s = t * kTileSlices + warp;
+            const int64_t row = s * 32 + lane;
+            const bool sliceValid = s < S.slices;
+            int32_t base = 0, w = 0;
+            if (sliceValid) { base = h[warp] - h[0]; w = h[warp + 1] - h[warp]; }
+            body(row, sliceValid && row < S.rows, ring + (size_t)stage * S.stageInts + ((size_t)base << 5) + lane, w);
+            __syncwarp();
+            if (lane == 0) mbarArrive(&empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+    }
+}

@@ -96,8 +96,23 @@ __global__ void k_deg_to_u8(const int32_t *__restrict__ deg, int64_t rows, u8 *_
     if (r < rows) out[r] = (u8)min(deg[r], 255);
 }
 
+// largest tile (kTileSlices consecutive slices) in slice-width units
+__global__ void k_max_tile(const int32_t *__restrict__ sliceOff, int64_t slices, int tileSlices, int *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t s0 = t * tileSlices;
+    if (s0 >= slices) return;
+    int64_t s1 = s0 + tileSlices < slices ? s0 + tileSlices : slices;
+    atomicMax(out, sliceOff[s1] - sliceOff[s0]);
+}
+__global__ void k_fill_tail(int32_t *__restrict__ sliceOff, int64_t slices, int extra) {
+    int i = threadIdx.x;
+    if (i >= 1 && i <= extra) sliceOff[slices + i] = sliceOff[slices];
+}
+
+constexpr int kSliceOffPad = 16;
+
 static void sellFree(amr_ctx *ctx, Sell &S) {
-    if (S.sliceOff) { cudaFree(S.sliceOff); ctx->devBytes -= (int64_t)((S.slices + 2) * 4); }
+    if (S.sliceOff) { cudaFree(S.sliceOff); ctx->devBytes -= (int64_t)((S.slices + kSliceOffPad) * 4); }
     if (S.col) { cudaFree(S.col); ctx->devBytes -= (int64_t)(S.entries * 4 > 4 ? S.entries * 4 : 4); }
     if (S.count) { cudaFree(S.count); ctx->devBytes -= (int64_t)(S.rows > 0 ? S.rows : 1); }
     S = Sell();
@@ -107,8 +122,8 @@ static void sellFree(amr_ctx *ctx, Sell &S) {
 static int sellAllocFromDeg(amr_ctx *ctx, Sell &S, int64_t rows, int32_t *deg, int selfPad) {
     S.rows = rows;
     S.slices = (rows + 31) / 32;
-    TRY(devAlloc(ctx, &S.sliceOff, S.slices + 2));
-    CK(cudaMemsetAsync(S.sliceOff, 0, (size_t)(S.slices + 2) * 4, ctx->stream));
+    TRY(devAlloc(ctx, &S.sliceOff, S.slices + kSliceOffPad));
+    CK(cudaMemsetAsync(S.sliceOff, 0, (size_t)(S.slices + kSliceOffPad) * 4, ctx->stream));
     if (S.slices > 0) LAUNCH(k_slice_width, gridFor(S.slices * 32), kThreads, deg, rows, S.slices, S.sliceOff);
     // scan aux
     int64_t auxNeed = (S.slices + 1) / kScanTile + 1024;
@@ -117,8 +132,14 @@ static int sellAllocFromDeg(amr_ctx *ctx, Sell &S, int64_t rows, int32_t *deg, i
     int rc = deviceExclusiveScan(ctx, S.sliceOff, S.sliceOff, S.slices, aux, auxNeed * 2);
     if (rc != AMR_OK) { cudaFree(aux); return rc; }
     int32_t total = 0;
+    LAUNCH(k_fill_tail, 1, 32, S.sliceOff, S.slices, kSliceOffPad - 1);
+    CK(cudaMemsetAsync(ctx->dFlags + 4, 0, sizeof(int), ctx->stream));
+    if (S.slices > 0) LAUNCH(k_max_tile, gridFor((S.slices + 7) / 8), kThreads, S.sliceOff, S.slices, 8, ctx->dFlags + 4);
     CK(cudaMemcpyAsync(&total, S.sliceOff + S.slices, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int maxTile = 0;
+    CK(cudaMemcpyAsync(&maxTile, ctx->dFlags + 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    S.maxTileInts = maxTile * 32;
     cudaFree(aux);
     S.entries = (int64_t)total * 32;
     TRY(devAlloc(ctx, &S.col, S.entries));
