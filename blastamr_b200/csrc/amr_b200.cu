@@ -329,8 +329,13 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
 #define EST(K)                                                                                                   \
     do {                                                                                                         \
         if (pipeOk(ctx, ctx->cc)) {                                                                              \
-            if (scale) TRY(launchPipe(ctx, kp_estimate<K, true>, ctx->cc, dx, ghost, p0, p1, t, target));        \
-            else TRY(launchPipe(ctx, kp_estimate<K, false>, ctx->cc, dx, ghost, p0, p1, t, target));             \
+            if (ctx->nCoupled > 0) {                                                                             \
+                if (scale) TRY(launchPipe(ctx, kp_estimate<K, true, true>, ctx->cc, dx, ghost, p0, p1, t, target));  \
+                else TRY(launchPipe(ctx, kp_estimate<K, false, true>, ctx->cc, dx, ghost, p0, p1, t, target));       \
+            } else {                                                                                             \
+                if (scale) TRY(launchPipe(ctx, kp_estimate<K, true, false>, ctx->cc, dx, ghost, p0, p1, t, target)); \
+                else TRY(launchPipe(ctx, kp_estimate<K, false, false>, ctx->cc, dx, ghost, p0, p1, t, target));      \
+            }                                                                                                    \
         } else if (scale) LAUNCH((k_estimate<K, true>), gridFor(n), kThreads, n, so, col, dx, ghost, p0, p1, t, target); \
         else LAUNCH((k_estimate<K, false>), gridFor(n), kThreads, n, so, col, dx, ghost, p0, p1, t, target);      \
     } while (0)
@@ -370,7 +375,10 @@ static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res) 
         LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, src, ctx->send8);
         TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
     }
-    if (pipeOk(ctx, ctx->cc)) TRY(launchPipe(ctx, kp_extend, ctx->cc, (const u8 *)cur, src, (const u8 *)ctx->ghost8, tmp));
+    if (pipeOk(ctx, ctx->cc)) {
+        if (ctx->nCoupled > 0) TRY(launchPipe(ctx, kp_extend<true>, ctx->cc, (const u8 *)cur, src, (const u8 *)ctx->ghost8, tmp));
+        else TRY(launchPipe(ctx, kp_extend<false>, ctx->cc, (const u8 *)cur, src, (const u8 *)ctx->ghost8, tmp));
+    }
     else LAUNCH(k_extend, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, cur, src, ctx->ghost8, tmp);
     *res = tmp;
     return AMR_OK;
@@ -444,8 +452,11 @@ static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOu
         }
         if (n) {
             if (pipeOk(ctx, ctx->cc)) {
-                if (maxSet) TRY(launchPipe(ctx, kp_refine_sweep<true>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
-                else TRY(launchPipe(ctx, kp_refine_sweep<false>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
+                const bool g = ctx->nCoupled > 0;
+                if (maxSet && g) TRY(launchPipe(ctx, kp_refine_sweep<true, true>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
+                else if (maxSet) TRY(launchPipe(ctx, kp_refine_sweep<true, false>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
+                else if (g) TRY(launchPipe(ctx, kp_refine_sweep<false, true>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
+                else TRY(launchPipe(ctx, kp_refine_sweep<false, false>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
             } else if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
             else LAUNCH(k_refine_sweep_min, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
         }
@@ -541,8 +552,11 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
 
     u8 *cur = ctx->flagA, *tmp = ctx->flagB, *src0 = ctx->flagC;
     // M1 (+ source mask of the first forced layer)
-    if (n) LAUNCH(k_candidates, gridFor(n), kThreads, n, dErr, lo, hi, ctx->lvl, dMax, maxLevelUniform, cur,
-                  nBufferLayers > 0 ? src0 : (u8 *)nullptr);
+    {
+        const bool al = ((((uintptr_t)dErr) | ((uintptr_t)dMax)) & 15) == 0;
+        if (n) LAUNCH(k_candidates, gridFor(n, kThreads * 4), kThreads, n, dErr, lo, hi, ctx->lvl, dMax, maxLevelUniform, cur,
+                      nBufferLayers > 0 ? src0 : (u8 *)nullptr, al);
+    }
     // M2: extendMarkedCells(refineCell, maxRefinement, i == 0, force = true), fvMeshHexRefiner.C:1509-1512
     for (int i = 0; i < nBufferLayers; i++) {
         u8 *res;
@@ -583,7 +597,7 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
         quota = !(nCand < nTotToRefine);
     }
     if (!quota) {
-        if (n) LAUNCH(k_select_filter, gridFor(n), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, -1, set, ctx->lf);
+        if (n) LAUNCH(k_select_filter, gridFor(n, kThreads * 4), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, -1, set, ctx->lf, ((((uintptr_t)dMax)) & 15) == 0);
     } else {
         // level-by-level truncation, fvMeshHexRefiner.C:346-374; gMax(maxRefinement)
         int32_t maxLevel = maxLevelUniform;
@@ -599,14 +613,14 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
         }
         CK(cudaMemsetAsync(set, 0, (size_t)n, ctx->stream));
         for (int32_t level = 0; level < maxLevel; level++) {
-            if (n) LAUNCH(k_select_filter, gridFor(n), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, level, set, ctx->lf);
+            if (n) LAUNCH(k_select_filter, gridFor(n, kThreads * 4), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, level, set, ctx->lf, ((((uintptr_t)dMax)) & 15) == 0);
             CK(cudaMemsetAsync(ctx->dCount, 0, 8, ctx->stream));
             if (n) LAUNCH(k_count_flags, gridFor(n), kThreads, n, set, (unsigned long long *)ctx->dCount);
             int64_t tot = 0;
             TRY(globalSum(ctx, 0, &tot));
             if (tot > nTotToRefine) break;
         }
-        if (maxLevel <= 0 && n) LAUNCH(k_select_filter, gridFor(n), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, 1 << 20, set, ctx->lf);
+        if (maxLevel <= 0 && n) LAUNCH(k_select_filter, gridFor(n, kThreads * 4), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, 1 << 20, set, ctx->lf, ((((uintptr_t)dMax)) & 15) == 0);
     }
     // B1: hexRef::consistentRefinement(candidates, true)
     TRY(refineSweeps(ctx, 1, set, ctx->lf, sweepsOut));
@@ -625,7 +639,7 @@ AMR_API int amr_consistent_refinement(amr_ctx *ctx, const int32_t *cellsIn, int6
     u8 *set = ctx->flagA;
     CK(cudaMemsetAsync(set, 0, (size_t)n, ctx->stream));
     if (nIn > 0) LAUNCH(k_list_to_flags, gridFor(nIn), kThreads, nIn, dIn, set);
-    if (n) LAUNCH(k_select_filter, gridFor(n), kThreads, n, set, ctx->lvl, (const label *)nullptr, (label)0x7fffffff, (const u8 *)nullptr, -1, set, ctx->lf);
+    if (n) LAUNCH(k_select_filter, gridFor(n, kThreads * 4), kThreads, n, set, ctx->lvl, (const label *)nullptr, (label)0x7fffffff, (const u8 *)nullptr, -1, set, ctx->lf, true);
     TRY(refineSweeps(ctx, maxSet, set, ctx->lf, sweepsOut));
     TRY(emitList(ctx, set, n, cellsOut, nOut));
     CK(cudaGetLastError());
@@ -804,11 +818,11 @@ AMR_API int amr_map_field(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_
     int64_t items = nNew * nComp;
     if (items > 0) {
         switch (nComp) {
-        case 1: LAUNCH((k_map_field<1>), gridFor(items), kThreads, nNew, dMap, dOld, dNew); break;
-        case 3: LAUNCH((k_map_field<3>), gridFor(items), kThreads, nNew, dMap, dOld, dNew); break;
-        case 6: LAUNCH((k_map_field<6>), gridFor(items), kThreads, nNew, dMap, dOld, dNew); break;
-        case 9: LAUNCH((k_map_field<9>), gridFor(items), kThreads, nNew, dMap, dOld, dNew); break;
-        default: LAUNCH(k_map_field_n, gridFor(items), kThreads, nNew, nComp, dMap, dOld, dNew); break;
+        case 1: LAUNCH((k_map_field<1>), gridFor(items, kThreads * kMapItems), kThreads, nNew, dMap, dOld, dNew); break;
+        case 3: LAUNCH((k_map_field<3>), gridFor(items, kThreads * kMapItems), kThreads, nNew, dMap, dOld, dNew); break;
+        case 6: LAUNCH((k_map_field<6>), gridFor(items, kThreads * kMapItems), kThreads, nNew, dMap, dOld, dNew); break;
+        case 9: LAUNCH((k_map_field<9>), gridFor(items, kThreads * kMapItems), kThreads, nNew, dMap, dOld, dNew); break;
+        default: LAUNCH(k_map_field_n, gridFor(items, kThreads * kMapItems), kThreads, nNew, nComp, dMap, dOld, dNew); break;
         }
     }
     if (mode == AMR_MAP_CONSERVATIVE) {

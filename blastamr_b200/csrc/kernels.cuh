@@ -116,15 +116,37 @@ __global__ void k_pack_f64(int64_t b, const label *__restrict__ bOwner, const do
 //   mark[c] = lo <= e <= hi ;  src[c] = mark[c] && maxLevel(c) > cellLevel[c]
 __global__ void __launch_bounds__(kThreads)
 k_candidates(int64_t n, const double *__restrict__ err, double lo, double hi, const label *__restrict__ lvl,
-             const label *__restrict__ maxLvl, label maxLvlUniform, u8 *__restrict__ mark, u8 *__restrict__ src) {
-    int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (c >= n) return;
-    double e = err[c];
-    u8 m = (e >= lo) && (e <= hi);
-    mark[c] = m;
-    if (src) {
-        label mx = maxLvl ? maxLvl[c] : maxLvlUniform;
-        src[c] = m && (mx > lvl[c]);
+             const label *__restrict__ maxLvl, label maxLvlUniform, u8 *__restrict__ mark, u8 *__restrict__ src,
+             bool aligned) {
+    // 4 consecutive cells per thread: 2 x 16 B of error, 16 B of levels in flight, 4 B stores
+    const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (c0 >= n) return;
+    if (aligned && c0 + 4 <= n) {
+        const double2 e01 = *reinterpret_cast<const double2 *>(err + c0);
+        const double2 e23 = *reinterpret_cast<const double2 *>(err + c0 + 2);
+        const double e[4] = {e01.x, e01.y, e23.x, e23.y};
+        uchar4 m;
+        m.x = (e[0] >= lo) && (e[0] <= hi); m.y = (e[1] >= lo) && (e[1] <= hi);
+        m.z = (e[2] >= lo) && (e[2] <= hi); m.w = (e[3] >= lo) && (e[3] <= hi);
+        *reinterpret_cast<uchar4 *>(mark + c0) = m;
+        if (src) {
+            const int4 l = *reinterpret_cast<const int4 *>(lvl + c0);
+            int4 mx = make_int4(maxLvlUniform, maxLvlUniform, maxLvlUniform, maxLvlUniform);
+            if (maxLvl) mx = *reinterpret_cast<const int4 *>(maxLvl + c0);
+            uchar4 sr;
+            sr.x = m.x && (mx.x > l.x); sr.y = m.y && (mx.y > l.y); sr.z = m.z && (mx.z > l.z); sr.w = m.w && (mx.w > l.w);
+            *reinterpret_cast<uchar4 *>(src + c0) = sr;
+        }
+        return;
+    }
+    for (int64_t c = c0; c < n && c < c0 + 4; c++) {
+        double e = err[c];
+        u8 m = (e >= lo) && (e <= hi);
+        mark[c] = m;
+        if (src) {
+            label mx = maxLvl ? maxLvl[c] : maxLvlUniform;
+            src[c] = m && (mx > lvl[c]);
+        }
     }
 }
 
@@ -200,19 +222,43 @@ k_zero_protected(int64_t n, const u8 *__restrict__ prot, double *__restrict__ er
 __global__ void __launch_bounds__(kThreads)
 k_select_filter(int64_t n, const u8 *__restrict__ cand, const label *__restrict__ lvl, const label *__restrict__ maxLvl,
                 label maxLvlUniform, const u8 *__restrict__ unrefineable, int onlyLevel, u8 *__restrict__ set,
-                u8 *__restrict__ lf) {
-    int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (c >= n) return;
-    label l = lvl[c];
-    u8 sel;
-    if (onlyLevel < 0) {
-        label mx = maxLvl ? maxLvl[c] : maxLvlUniform;
-        sel = cand[c] && (l < mx) && !(unrefineable && unrefineable[c]);
+                u8 *__restrict__ lf, bool aligned) {
+    const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (c0 >= n) return;
+    const bool vec = aligned && c0 + 4 <= n;
+    label l[4], mx[4];
+    u8 cd[4], ur[4] = {0, 0, 0, 0}, st[4] = {0, 0, 0, 0};
+    const int cnt = vec ? 4 : (int)min((int64_t)4, n - c0);
+    if (vec) {
+        const int4 lv = *reinterpret_cast<const int4 *>(lvl + c0);
+        l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
+        const uchar4 c4 = *reinterpret_cast<const uchar4 *>(cand + c0);
+        cd[0] = c4.x; cd[1] = c4.y; cd[2] = c4.z; cd[3] = c4.w;
+        if (maxLvl) { const int4 m4 = *reinterpret_cast<const int4 *>(maxLvl + c0); mx[0] = m4.x; mx[1] = m4.y; mx[2] = m4.z; mx[3] = m4.w; }
+        if (unrefineable) { const uchar4 u4 = *reinterpret_cast<const uchar4 *>(unrefineable + c0); ur[0] = u4.x; ur[1] = u4.y; ur[2] = u4.z; ur[3] = u4.w; }
+        if (onlyLevel >= 0) { const uchar4 s4 = *reinterpret_cast<const uchar4 *>(set + c0); st[0] = s4.x; st[1] = s4.y; st[2] = s4.z; st[3] = s4.w; }
     } else {
-        sel = set[c] || (cand[c] && l == onlyLevel && !(unrefineable && unrefineable[c]));
+        for (int k = 0; k < cnt; k++) {
+            l[k] = lvl[c0 + k]; cd[k] = cand[c0 + k];
+            if (maxLvl) mx[k] = maxLvl[c0 + k];
+            if (unrefineable) ur[k] = unrefineable[c0 + k];
+            if (onlyLevel >= 0) st[k] = set[c0 + k];
+        }
     }
-    set[c] = sel;
-    if (lf) lf[c] = (u8)(l + sel);
+    u8 sel[4], lfv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const label m = maxLvl ? mx[k] : maxLvlUniform;
+        if (onlyLevel < 0) sel[k] = cd[k] && (l[k] < m) && !ur[k];
+        else sel[k] = st[k] || (cd[k] && l[k] == onlyLevel && !ur[k]);
+        lfv[k] = (u8)(l[k] + sel[k]);
+    }
+    if (vec) {
+        *reinterpret_cast<uchar4 *>(set + c0) = make_uchar4(sel[0], sel[1], sel[2], sel[3]);
+        if (lf) *reinterpret_cast<uchar4 *>(lf + c0) = make_uchar4(lfv[0], lfv[1], lfv[2], lfv[3]);
+    } else {
+        for (int k = 0; k < cnt; k++) { set[c0 + k] = sel[k]; if (lf) lf[c0 + k] = lfv[k]; }
+    }
 }
 
 // sum of a byte-flag array (returnReduce(count(...)) sites: fvMeshHexRefiner.C:323-324,369)
@@ -509,25 +555,50 @@ k_remap_refine_cell(int64_t nNew, const label *__restrict__ cellMap, const label
     newFlag[c] = v;
 }
 
-// fvMesh::mapFields direct addressing: new[i][k] = old[cellMap[i]][k]; one thread per scalar
+// fvMesh::mapFields direct addressing: new[i][k] = old[cellMap[i]][k].  One thread handles 4 scalars
+// (strided by the CTA so every access instruction stays coalesced); the 4 map loads are issued before
+// the 4 dependent gathers so each thread keeps 4 independent chains in flight.
+constexpr int kMapItems = 4;
 template <int NC>
 __global__ void __launch_bounds__(kThreads)
 k_map_field(int64_t nNew, const label *__restrict__ cellMap, const double *__restrict__ oldF,
             double *__restrict__ newF) {
-    int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (e >= nNew * NC) return;
-    int64_t i = e / NC;
-    int k = (int)(e - i * NC);
-    newF[e] = oldF[(int64_t)cellMap[i] * NC + k];
+    const int64_t total = nNew * NC;
+    const int64_t e0 = (int64_t)blockIdx.x * (kThreads * kMapItems) + threadIdx.x;
+    int64_t src[kMapItems];
+#pragma unroll
+    for (int t = 0; t < kMapItems; t++) {
+        const int64_t e = e0 + (int64_t)t * kThreads;
+        if (e < total) {
+            const int64_t i = e / NC;
+            src[t] = (int64_t)cellMap[i] * NC + (e - i * NC);
+        } else src[t] = -1;
+    }
+    double v[kMapItems];
+#pragma unroll
+    for (int t = 0; t < kMapItems; t++) if (src[t] >= 0) v[t] = oldF[src[t]];
+#pragma unroll
+    for (int t = 0; t < kMapItems; t++) if (src[t] >= 0) newF[e0 + (int64_t)t * kThreads] = v[t];
 }
 __global__ void __launch_bounds__(kThreads)
 k_map_field_n(int64_t nNew, int nc, const label *__restrict__ cellMap, const double *__restrict__ oldF,
               double *__restrict__ newF) {
-    int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (e >= nNew * nc) return;
-    int64_t i = e / nc;
-    int k = (int)(e - i * nc);
-    newF[e] = oldF[(int64_t)cellMap[i] * nc + k];
+    const int64_t total = nNew * nc;
+    const int64_t e0 = (int64_t)blockIdx.x * (kThreads * kMapItems) + threadIdx.x;
+    int64_t src[kMapItems];
+#pragma unroll
+    for (int t = 0; t < kMapItems; t++) {
+        const int64_t e = e0 + (int64_t)t * kThreads;
+        if (e < total) {
+            const int64_t i = e / nc;
+            src[t] = (int64_t)cellMap[i] * nc + (e - i * nc);
+        } else src[t] = -1;
+    }
+    double v[kMapItems];
+#pragma unroll
+    for (int t = 0; t < kMapItems; t++) if (src[t] >= 0) v[t] = oldF[src[t]];
+#pragma unroll
+    for (int t = 0; t < kMapItems; t++) if (src[t] >= 0) newF[e0 + (int64_t)t * kThreads] = v[t];
 }
 
 // conservative merge: new master value = sum V_old*old / sum V_old over the 8 merged cells,

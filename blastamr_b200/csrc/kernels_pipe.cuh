@@ -1,95 +1,141 @@
 // kernels_pipe.cuh -- TMA-pipelined variants of the dense SELL gather kernels (see pipeline.cuh).
 // Same arithmetic as the direct kernels in kernels.cuh (which remain the path for meshes whose
 // tiles do not fit the shared-memory ring and for the sparse sweeps); results are bit-identical.
+//
+// Instruction discipline (the first version was issue-bound, not memory-bound): the slice width is
+// warp-uniform and rows are padded with the row's own label, so a row is walked with a compile-time
+// width (switch on w, fully unrolled), no per-entry predicate, no branch between the gathers -- all
+// W loads of a row are issued back to back.  Labels are compared as 32-bit.  Meshes without
+// processor patches (GHOST=false) never test for ghost slots.
 #pragma once
+#include <type_traits>
+
 #include "kernels.cuh"
 #include "pipeline.cuh"
 
-template <int KIND, bool SCALE>
+template <int W> using WTag = std::integral_constant<int, W>;
+
+// acc(WTag<W>, const int32_t (&q)[W]) is called once (w <= 8) or once per chunk of 4 (w > 8)
+template <class Acc>
+__device__ __forceinline__ void sellRow(const int32_t *row, int w, int32_t self, Acc acc) {
+#define SELL_CASE(W)                                                     \
+    case W: {                                                            \
+        int32_t q[W];                                                    \
+        _Pragma("unroll") for (int k = 0; k < W; k++) q[k] = row[k << 5]; \
+        acc(WTag<W>{}, q);                                               \
+    } break;
+    switch (w) {
+    case 0: break;
+        SELL_CASE(1) SELL_CASE(2) SELL_CASE(3) SELL_CASE(4) SELL_CASE(5) SELL_CASE(6) SELL_CASE(7) SELL_CASE(8)
+    default:
+        for (int j0 = 0; j0 < w; j0 += 4) {
+            int32_t q[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) q[k] = (j0 + k < w) ? row[(j0 + k) << 5] : self;
+            acc(WTag<4>{}, q);
+        }
+    }
+#undef SELL_CASE
+}
+
+// value of a per-cell array at label q, where q >= n addresses the ghost slot of boundary face q-n.
+// ghostBase = ghost - n, so both cases are base[q] with a selected base pointer (branch-free).
+template <bool GHOST, class T>
+__device__ __forceinline__ T gatherAt(const T *__restrict__ local, const T *ghostBase, int32_t q, int32_t n) {
+    if (GHOST) {
+        const T *base = (q < n) ? local : ghostBase;
+        return base[q];
+    }
+    return local[q];
+}
+
+template <int KIND, bool SCALE, bool GHOST>
 __global__ void __launch_bounds__(kPipeThreads)
-kp_estimate(SellView S, const double *__restrict__ x, const double *__restrict__ ghost, double p0, double p1,
-            Thresholds thr, double *__restrict__ err) {
-    const int64_t n = S.rows;
+kp_estimate(SellView S, const double *__restrict__ x, const double *ghost, double p0, double p1, Thresholds thr,
+            double *__restrict__ err) {
+    const int32_t n = (int32_t)S.rows;
     const bool useOffset = fabs(p1) > kSMALL;
-    sellPipeline(S, [&](int64_t c, bool valid, const int32_t *row, int w) {
-        if (!valid) return;
+    const double *ghostBase = ghost - n;
+    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w) {
+        const int32_t c = valid ? (int32_t)c64 : n - 1;
         const double xc = fieldXform<KIND>(x[c], p1, useOffset);
-        double e = 0.0;
-        for (int j0 = 0; j0 < w; j0 += kChunk) {
-            int32_t q[kChunk];
+        double eL = 0.0, eG = 0.0;   // max over internal faces / over coupled-patch faces
+        sellRow(row, w, c, [&](auto W, const int32_t *q) {
+            constexpr int NW = decltype(W)::value;
+            double v[NW];
 #pragma unroll
-            for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(j0 + k) << 5] : (int32_t)c;
-            double xq[kChunk];
+            for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>(x, ghostBase, q[k], n);
 #pragma unroll
-            for (int k = 0; k < kChunk; k++) {
-                if (q[k] < n) xq[k] = x[q[k]];
-                else xq[k] = ghost[q[k] - n];
-            }
-#pragma unroll
-            for (int k = 0; k < kChunk; k++) {
-                if (q[k] == (int32_t)c) continue;
-                double v = fieldXform<KIND>(xq[k], p1, useOffset);
-                double eT;
-                if (KIND == 0) {
-                    eT = fabs(xc - v);
-                    if (q[k] < n) eT = fminFoam(eT, 0.5);
-                } else if (KIND == 1) {
-                    eT = fabs(xc - v) / fmaxFoam(fminFoam(xc, v), p0);
+            for (int k = 0; k < NW; k++) {
+                const double xv = fieldXform<KIND>(v[k], p1, useOffset);
+                double eT = fabs(xc - xv);
+                if (KIND == 1) {
+                    eT = eT / fmaxFoam(fminFoam(xc, xv), p0);     // scaledDelta.C:103-104,129-131
+                    eT = (q[k] == c) ? 0.0 : eT;                  // padding (0/0 guard)
+                }
+                if (GHOST && KIND == 0) {
+                    const bool g = q[k] >= n;
+                    eL = fmaxFoam(eL, g ? 0.0 : eT);
+                    eG = fmaxFoam(eG, g ? eT : 0.0);
                 } else {
-                    eT = fabs(xc - v);
+                    eL = fmaxFoam(eL, eT);
                 }
-                e = fmaxFoam(e, eT);
             }
-        }
-        err[c] = SCALE ? normalizeValue(e, thr) : e;
+        });
+        // delta clamps internal faces only (delta.C:103 vs :126); min(max_j d_j, .5) == max_j min(d_j, .5)
+        double e = (KIND == 0) ? fmaxFoam(fminFoam(eL, 0.5), eG) : eL;
+        if (valid) err[c] = SCALE ? normalizeValue(e, thr) : e;
     });
 }
 
+template <bool GHOST>
 __global__ void __launch_bounds__(kPipeThreads)
-kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, const u8 *__restrict__ ghost,
-          u8 *__restrict__ out) {
-    const int64_t n = S.rows;
-    sellPipeline(S, [&](int64_t c, bool valid, const int32_t *row, int w) {
-        unsigned m = valid ? in[c] : 1u;
-        if (__all_sync(0xffffffffu, m != 0)) { if (valid) out[c] = 1; return; }
-        if (!valid) return;
-        for (int j0 = 0; j0 < w; j0 += kChunk) {
-            int32_t q[kChunk];
+kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, const u8 *ghost, u8 *__restrict__ out) {
+    const int32_t n = (int32_t)S.rows;
+    const u8 *ghostBase = ghost - n;
+    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w) {
+        const int32_t c = valid ? (int32_t)c64 : n - 1;
+        unsigned m = in[c];
+        // a warp whose 32 cells are all marked has nothing to gather
+        if (!__all_sync(0xffffffffu, m != 0)) {
+            sellRow(row, w, c, [&](auto W, const int32_t *q) {
+                constexpr int NW = decltype(W)::value;
+                unsigned v[NW];
 #pragma unroll
-            for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(j0 + k) << 5] : (int32_t)c;
+                for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>(src, ghostBase, q[k], n);
 #pragma unroll
-            for (int k = 0; k < kChunk; k++) {
-                if (q[k] == (int32_t)c) continue;
-                m |= (q[k] < n) ? src[q[k]] : ghost[q[k] - n];
-            }
+                for (int k = 0; k < NW; k++) m |= v[k];   // padding reads src[c] <= in[c]: no-op
+            });
         }
-        out[c] = m ? 1 : 0;
+        if (valid) out[c] = m ? 1 : 0;
     });
 }
 
-template <bool MAXSET>
+template <bool MAXSET, bool GHOST>
 __global__ void __launch_bounds__(kPipeThreads)
-kp_refine_sweep(SellView S, u8 *__restrict__ lf, u8 *__restrict__ set, const u8 *__restrict__ ghostLf, int *changed) {
-    const int64_t n = S.rows;
-    sellPipeline(S, [&](int64_t c, bool valid, const int32_t *row, int w) {
+kp_refine_sweep(SellView S, u8 *lf, u8 *set, const u8 *ghostLf, int *changed) {
+    const int32_t n = (int32_t)S.rows;
+    const u8 *ghostBase = ghostLf - n;
+    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w) {
+        const int32_t c = valid ? (int32_t)c64 : n - 1;
+        const int isSet = set[c];
         int flip = 0;
-        const int isSet = valid ? set[c] : (MAXSET ? 1 : 0);
-        const bool warpIdle = MAXSET ? __all_sync(0xffffffffu, isSet != 0) : !__any_sync(0xffffffffu, isSet != 0);
-        if (!warpIdle && valid) {
+        const bool idle = MAXSET ? __all_sync(0xffffffffu, isSet != 0) : !__any_sync(0xffffffffu, isSet != 0);
+        if (!idle) {
             const int mine = lf[c];
-            int ext = MAXSET ? 0 : 255;
-            for (int j0 = 0; j0 < w; j0 += kChunk) {
-                int32_t q[kChunk];
+            int ext = mine;      // padding contributes the cell's own value: neutral for max and min
+            sellRow(row, w, c, [&](auto W, const int32_t *q) {
+                constexpr int NW = decltype(W)::value;
+                int v[NW];
 #pragma unroll
-                for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(j0 + k) << 5] : (int32_t)c;
+                for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>((const u8 *)lf, ghostBase, q[k], n);
 #pragma unroll
-                for (int k = 0; k < kChunk; k++) {
-                    int v = (q[k] < n) ? lf[q[k]] : ghostLf[q[k] - n];
-                    ext = MAXSET ? max(ext, v) : min(ext, v);
-                }
+                for (int k = 0; k < NW; k++) ext = MAXSET ? max(ext, v[k]) : min(ext, v[k]);
+            });
+            if (valid) {
+                if (MAXSET) { if (!isSet && ext > mine + 1) { set[c] = 1; lf[c] = (u8)(mine + 1); flip = 1; } }
+                else { if (isSet && mine > ext + 1) { set[c] = 0; lf[c] = (u8)(mine - 1); flip = 1; } }
             }
-            if (MAXSET) { if (!isSet && ext > mine + 1) { set[c] = 1; lf[c] = (u8)(mine + 1); flip = 1; } }
-            else { if (isSet && mine > ext + 1) { set[c] = 0; lf[c] = (u8)(mine - 1); flip = 1; } }
         }
         if (__any_sync(0xffffffffu, flip) && (threadIdx.x & 31) == 0) *changed = 1;
     });
@@ -115,16 +161,22 @@ kp_select_unrefine_points(SellView S, const u8 *__restrict__ pcCount, const u8 *
 #pragma unroll
             for (int k = 1; k < 8; k++) same = same && (par[k] == par[0]);
             if (same) {
-                int l0 = lvl8[q[0]];
+                int l[8];
 #pragma unroll
-                for (int k = 1; k < 8; k++) same = same && (lvl8[q[k]] == l0);
+                for (int k = 0; k < 8; k++) l[k] = lvl8[q[k]];
+#pragma unroll
+                for (int k = 1; k < 8; k++) same = same && (l[k] == l[0]);
             }
             split = same;
             if (split && keep) {
+                double e[8];
+                unsigned mk[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) { e[k] = err[q[k]]; mk[k] = marked[q[k]]; }
                 double m = -kGREAT;
                 unsigned anyMarked = 0;
 #pragma unroll
-                for (int k = 0; k < 8; k++) { m = fmaxFoam(m, err[q[k]]); anyMarked |= marked[q[k]]; }
+                for (int k = 0; k < 8; k++) { m = fmaxFoam(m, e[k]); anyMarked |= mk[k]; }
                 kp = (m < unrefineLevel) && !anyMarked;
             }
         }
