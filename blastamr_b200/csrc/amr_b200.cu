@@ -193,7 +193,12 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     if (n < 0 || f < 0 || b < 0 || p < 0 || !owner || (f > 0 && !neighbour) || npatch < 0) FAIL(AMR_ERR_ARG, "amr_mesh_set: bad sizes/pointers");
     if (n >= ((int64_t)1 << 31) - 2 - b) FAIL(AMR_ERR_ARG, "amr_mesh_set: label overflow (n + b must fit int32)");
     CK(cudaStreamSynchronize(ctx->stream));
+    // a marking remapped through the topology change (amr_remap_refine_cell) survives the mesh switch
+    u8 *pending = nullptr;
+    int64_t pendingN = 0;
+    if (ctx->refineCell && ctx->refineCellN == n && n > 0) { pending = ctx->refineCell; pendingN = n; ctx->refineCell = nullptr; }
     freeMesh(ctx);
+    ctx->nTotalCells = -1;
     ctx->n = n; ctx->f = f; ctx->b = b; ctx->p = p;
     ctx->patches.clear();
     std::vector<u8> coupled((size_t)(b > 0 ? b : 1), 0);
@@ -216,17 +221,23 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     CK(cudaStreamSynchronize(ctx->stream));
     TRY(sellBuildCellCells(ctx));
     int64_t m = std::max(n, p);
+    ctx->flagCap = m + 16;
     TRY(devAlloc(ctx, &ctx->flagA, m + 16)); TRY(devAlloc(ctx, &ctx->flagB, m + 16)); TRY(devAlloc(ctx, &ctx->flagC, m + 16));
     TRY(devAlloc(ctx, &ctx->lf, n + 16));
     TRY(devAlloc(ctx, &ctx->error, n));
-    TRY(devAlloc(ctx, &ctx->refineCell, n + 16));
+    TRY(devAlloc(ctx, &ctx->refineCell, m + 16));
     TRY(devAlloc(ctx, &ctx->ghost8, b + 16)); TRY(devAlloc(ctx, &ctx->send8, b + 16));
     TRY(devAlloc(ctx, &ctx->ghost64, b + 2)); TRY(devAlloc(ctx, &ctx->send64, b + 2));
     ctx->tileCap = (m + kTile - 1) / kTile + 8;
     TRY(devAlloc(ctx, &ctx->tileCnt, ctx->tileCap));
     ctx->scanAuxCap = 2 * (ctx->tileCap / kScanTile + 1024);
     TRY(devAlloc(ctx, &ctx->scanAux, ctx->scanAuxCap));
-    CK(cudaMemsetAsync(ctx->refineCell, 0, (size_t)n + 16, ctx->stream));
+    CK(cudaMemsetAsync(ctx->refineCell, 0, (size_t)m + 16, ctx->stream));
+    if (pending) {
+        CK(cudaMemcpyAsync(ctx->refineCell, pending, (size_t)pendingN, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(pending);
+    }
     CK(cudaMemsetAsync(ctx->ghost8, 0, (size_t)b + 16, ctx->stream));
     CK(cudaMemsetAsync(ctx->ghost64, 0, (size_t)(b + 2) * 8, ctx->stream));
     ctx->refineCellN = n;
@@ -419,31 +430,61 @@ AMR_API int amr_protect_patches(amr_ctx *ctx, const int32_t *patchIds, int nPatc
 
 // ============================================================================ stages 2+3
 
-// copy an ascending list (device) with a device-side count to a host or device destination
-static int emitList(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *userOut, int64_t *nOut) {
+// Ascending list from flags.  emitListAsync enqueues the compaction; finishList reads the count back
+// (one sync, shared with the caller's convergence flag when it passes extraFlagSlot >= 0) and copies
+// the entries to a host destination.
+struct ListJob {
     int32_t *dList = nullptr;
-    bool hostOut = userOut && !isDevicePtr(userOut);
-    if (userOut) {
-        if (hostOut) { void *q; TRY(arenaAlloc(ctx, &q, (size_t)(N > 0 ? N : 1) * 4)); dList = (int32_t *)q; }
-        else dList = userOut;
-    }
     int32_t *dTotal = nullptr;
-    TRY(compactFlags(ctx, flags, N, dList, &dTotal));
-    if (nOut || hostOut) {
-        int32_t total = 0;
-        CK(cudaMemcpyAsync(ctx->hFlags + 8, dTotal, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        total = ctx->hFlags[8];
-        if (nOut) *nOut = total;
-        if (hostOut && total > 0) CK(cudaMemcpyAsync(userOut, dList, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t *userOut = nullptr;
+    bool hostOut = false;
+};
+static int emitListAsync(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *userOut, ListJob *job) {
+    job->userOut = userOut;
+    job->hostOut = userOut && !isDevicePtr(userOut);
+    if (userOut) {
+        if (job->hostOut) {
+            if (!job->dList) { void *q; TRY(arenaAlloc(ctx, &q, (size_t)(N > 0 ? N : 1) * 4)); job->dList = (int32_t *)q; }
+        } else job->dList = userOut;
     }
+    TRY(compactFlags(ctx, flags, N, job->dList, &job->dTotal));
     return AMR_OK;
 }
+// flagSlot >= 0: also fetch ctx->dFlags[flagSlot] (all-reduced over ranks) in the same round trip
+static int finishList(amr_ctx *ctx, ListJob *job, int flagSlot, int *flagValue, int64_t *nOut, bool copyOut) {
+    if (flagSlot >= 0) {
+        if (ctx->comm && ctx->nranks > 1)
+            NCK(ncclAllReduce(ctx->dFlags + flagSlot, ctx->dFlags + flagSlot, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->hFlags + flagSlot, ctx->dFlags + flagSlot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->hFlags + 8, job->dTotal, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flagSlot >= 0 && flagValue) *flagValue = ctx->hFlags[flagSlot];
+    const int32_t total = ctx->hFlags[8];
+    if (nOut) *nOut = total;
+    if (copyOut && job->hostOut && total > 0)
+        CK(cudaMemcpyAsync(job->userOut, job->dList, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return AMR_OK;
+}
+static int finishListCopy(amr_ctx *ctx, ListJob *job) {
+    const int32_t total = ctx->hFlags[8];
+    if (job->hostOut && total > 0)
+        CK(cudaMemcpyAsync(job->userOut, job->dList, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return AMR_OK;
+}
+static int emitList(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *userOut, int64_t *nOut) {
+    ListJob job;
+    TRY(emitListAsync(ctx, flags, N, userOut, &job));
+    return finishList(ctx, &job, -1, nullptr, nOut, true);
+}
 
-// hexRef::consistentRefinement loop (hexRef.C:1421-1437) on set/lf
-static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOut) {
+// hexRef::consistentRefinement loop (hexRef.C:1421-1437) on set/lf, followed by the ascending list
+// (hexRef.C:1440-1460).  The list is compacted speculatively after every sweep so that the
+// convergence flag and the list size come back in ONE host round trip per sweep.
+static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut) {
     const int64_t n = ctx->n, b = ctx->b;
     int sweeps = 0;
+    ListJob job;
     while (true) {
         CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(int), ctx->stream));
         if (ctx->nCoupled > 0) {
@@ -461,11 +502,13 @@ static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOu
             else LAUNCH(k_refine_sweep_min, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
         }
         sweeps++;
+        TRY(emitListAsync(ctx, set, n, cellsOut, &job));
         int changed = 0;
-        TRY(globalFlag(ctx, 0, &changed));
+        TRY(finishList(ctx, &job, 0, &changed, nOut, false));
         if (!changed) break;
         if (sweeps > 100000) FAIL(AMR_ERR_INVARIANT, "2:1 sweeps did not converge");
     }
+    TRY(finishListCopy(ctx, &job));
     if (sweepsOut) *sweepsOut = sweeps;
     return AMR_OK;
 }
@@ -554,7 +597,7 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
     // M1 (+ source mask of the first forced layer)
     {
         const bool al = ((((uintptr_t)dErr) | ((uintptr_t)dMax)) & 15) == 0;
-        if (n) LAUNCH(k_candidates, gridFor(n, kThreads * 4), kThreads, n, dErr, lo, hi, ctx->lvl, dMax, maxLevelUniform, cur,
+        if (n) LAUNCH(k_candidates, gridFor(n, kThreads * 4), kThreads, n, dErr, lo, hi, ctx->lvl8, dMax, maxLevelUniform, cur,
                       nBufferLayers > 0 ? src0 : (u8 *)nullptr, al);
     }
     // M2: extendMarkedCells(refineCell, maxRefinement, i == 0, force = true), fvMeshHexRefiner.C:1509-1512
@@ -571,22 +614,30 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
         if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)0);
     }
     if (ctx->protCell && n) LAUNCH(k_masked_set, gridFor(n), kThreads, n, ctx->protCell, cur, (u8)0);
-    // keep the marking (the reference's refineCell) resident for the unrefinement stage
-    if (n) CK(cudaMemcpyAsync(ctx->refineCell, cur, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    // keep the marking (the reference's refineCell) resident for the unrefinement stage: the buffer
+    // that holds it BECOMES ctx->refineCell (pointer swap, no copy)
+    if (cur == ctx->flagA) std::swap(ctx->flagA, ctx->refineCell);
+    else if (cur == ctx->flagB) std::swap(ctx->flagB, ctx->refineCell);
+    else std::swap(ctx->flagC, ctx->refineCell);
+    cur = ctx->refineCell;
     ctx->refineCellN = n;
     if (dRcOut && n) CK(cudaMemcpyAsync(dRcOut, cur, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
 
     // M4/M5: selectRefineCells, fvMeshHexRefiner.C:306-391
-    u8 *set = tmp;                    // the other ping-pong buffer is free now
-    u8 *unref = src0;                 // so is the layer-0 source mask
+    u8 *set = ctx->flagA;             // the ping-pong buffers are free now
+    u8 *unref = ctx->flagB;
     bool haveU = false;
     TRY(calcProtected(ctx, unref, &haveU));
     // nTotalCells / nCandidates reductions only matter when the maxCells quota can bind
-    int64_t nTotal = n;
-    if (ctx->comm && ctx->nranks > 1) {
-        CK(cudaMemcpyAsync(ctx->dCount + 1, &nTotal, 8, cudaMemcpyHostToDevice, ctx->stream));
-        TRY(globalSum(ctx, 1, &nTotal));
+    if (ctx->nTotalCells < 0) {
+        int64_t nTotal = n;
+        if (ctx->comm && ctx->nranks > 1) {
+            CK(cudaMemcpyAsync(ctx->dCount + 1, &nTotal, 8, cudaMemcpyHostToDevice, ctx->stream));
+            TRY(globalSum(ctx, 1, &nTotal));
+        }
+        ctx->nTotalCells = nTotal;
     }
+    const int64_t nTotal = ctx->nTotalCells;
     int64_t nTotToRefine = (maxCells - nTotal) / 7;
     bool quota = false;
     if (nTotal >= nTotToRefine) {     // otherwise nCandidates <= nTotal < nTotToRefine always holds
@@ -597,7 +648,8 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
         quota = !(nCand < nTotToRefine);
     }
     if (!quota) {
-        if (n) LAUNCH(k_select_filter, gridFor(n, kThreads * 4), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, -1, set, ctx->lf, ((((uintptr_t)dMax)) & 15) == 0);
+        if (n && !dMax) LAUNCH(k_select_filter16, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)cur, (const u8 *)ctx->lvl8, (int)maxLevelUniform, haveU ? (const u8 *)unref : (const u8 *)nullptr, set, ctx->lf);
+        else if (n) LAUNCH(k_select_filter, gridFor(n, kThreads * 4), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, -1, set, ctx->lf, ((((uintptr_t)dMax)) & 15) == 0);
     } else {
         // level-by-level truncation, fvMeshHexRefiner.C:346-374; gMax(maxRefinement)
         int32_t maxLevel = maxLevelUniform;
@@ -622,9 +674,8 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
         }
         if (maxLevel <= 0 && n) LAUNCH(k_select_filter, gridFor(n, kThreads * 4), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, haveU ? unref : (u8 *)nullptr, 1 << 20, set, ctx->lf, ((((uintptr_t)dMax)) & 15) == 0);
     }
-    // B1: hexRef::consistentRefinement(candidates, true)
-    TRY(refineSweeps(ctx, 1, set, ctx->lf, sweepsOut));
-    TRY(emitList(ctx, set, n, cellsOut, nOut));
+    // B1: hexRef::consistentRefinement(candidates, true) + ascending list
+    TRY(refineSweeps(ctx, 1, set, ctx->lf, sweepsOut, cellsOut, nOut));
     CK(cudaGetLastError());
     return flushOuts(ctx);
 }
@@ -640,8 +691,7 @@ AMR_API int amr_consistent_refinement(amr_ctx *ctx, const int32_t *cellsIn, int6
     CK(cudaMemsetAsync(set, 0, (size_t)n, ctx->stream));
     if (nIn > 0) LAUNCH(k_list_to_flags, gridFor(nIn), kThreads, nIn, dIn, set);
     if (n) LAUNCH(k_select_filter, gridFor(n, kThreads * 4), kThreads, n, set, ctx->lvl, (const label *)nullptr, (label)0x7fffffff, (const u8 *)nullptr, -1, set, ctx->lf, true);
-    TRY(refineSweeps(ctx, maxSet, set, ctx->lf, sweepsOut));
-    TRY(emitList(ctx, set, n, cellsOut, nOut));
+    TRY(refineSweeps(ctx, maxSet, set, ctx->lf, sweepsOut, cellsOut, nOut));
     CK(cudaGetLastError());
     return flushOuts(ctx);
 }
@@ -662,39 +712,44 @@ AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nNew, const int32_t *cel
     if (!dOld) dOld = ctx->refineCell;
     if (!dOld) FAIL(AMR_ERR_STATE, "amr_remap_refine_cell: no marking");
     u8 *dNew = nullptr;
-    CK(cudaMalloc((void **)&dNew, (size_t)nNew + 16));
+    const int64_t capNew = std::max<int64_t>(nNew + 16, ctx->flagCap);
+    CK(cudaMalloc((void **)&dNew, (size_t)capNew));
     if (nNew) LAUNCH(k_remap_refine_cell, gridFor(nNew), kThreads, nNew, dMap, dRev, dOld, dNew);
     if (newRefineCellOut && nNew) CK(cudaMemcpyAsync(newRefineCellOut, dNew, (size_t)nNew, cudaMemcpyDefault, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->refineCell) { cudaFree(ctx->refineCell); ctx->devBytes -= ctx->refineCellN + 16; }
-    ctx->refineCell = dNew; ctx->refineCellN = nNew; ctx->devBytes += nNew + 16;
+    if (ctx->refineCell) cudaFree(ctx->refineCell);
+    ctx->refineCell = dNew; ctx->refineCellN = nNew;
     CK(cudaGetLastError());
     return AMR_OK;
 }
 
-// hexRef3D::consistentUnrefinement loop (hexRef3D.C:1758-1927) on point flags
-static int unrefineSweeps(amr_ctx *ctx, u8 *pflag, int *sweepsOut) {
+// hexRef3D::consistentUnrefinement loop (hexRef3D.C:1758-1927) on point flags + ascending list
+// (hexRef3D.C:1930-1950), list compacted speculatively after each sweep (one round trip per sweep)
+static int unrefineSweeps(amr_ctx *ctx, u8 *pflag, int *sweepsOut, int32_t *elemsOut, int64_t *nOut) {
     const int64_t n = ctx->n, b = ctx->b, p = ctx->p;
     u8 *uc = ctx->flagB;     // unrefineCell
-    u8 *lfm = ctx->lf;
+    const bool alP = (((uintptr_t)pflag) & 15) == 0, alC = (((uintptr_t)uc) & 15) == 0;
+    const unsigned gP = gridFor(p, kThreads * 16), gC = gridFor(n, kThreads * 16);
     int sweeps = 0;
+    ListJob job;
     while (true) {
         CK(cudaMemsetAsync(uc, 0, (size_t)n, ctx->stream));
-        if (p) LAUNCH(k_points_to_cells, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, pflag, uc);
-        if (n) LAUNCH(k_level_minus, gridFor(n), kThreads, n, ctx->lvl8, uc, lfm);
+        if (p) LAUNCH(k_points_to_cells, gP, kThreads, p, ctx->pc.sliceOff, ctx->pc.col, pflag, alP, uc);
         CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(int), ctx->stream));
         if (ctx->nCoupled > 0) {
-            LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, lfm, ctx->send8);
+            LAUNCH(k_pack_level_minus, gridFor(b), kThreads, b, ctx->owner + ctx->f, ctx->lvl8, uc, ctx->send8);
             TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
         }
-        if (n) LAUNCH(k_unrefine_sweep, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lfm, uc, ctx->ghost8, ctx->dFlags);
+        if (n) LAUNCH(k_unrefine_sweep, gC, kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, uc, alC, ctx->ghost8, ctx->dFlags);
         sweeps++;
+        TRY(emitListAsync(ctx, pflag, p, elemsOut, &job));
         int changed = 0;
-        TRY(globalFlag(ctx, 0, &changed));
+        TRY(finishList(ctx, &job, 0, &changed, nOut, false));
         if (!changed) break;
-        if (p) LAUNCH(k_knock_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, pflag, uc);
+        if (p) LAUNCH(k_knock_points, gP, kThreads, p, ctx->pc.sliceOff, ctx->pc.col, pflag, alP, uc);
         if (sweeps > 100000) FAIL(AMR_ERR_INVARIANT, "unrefinement sweeps did not converge");
     }
+    TRY(finishListCopy(ctx, &job));
     if (sweepsOut) *sweepsOut = sweeps;
     return AMR_OK;
 }
@@ -714,18 +769,21 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     if (!dErr) dErr = ctx->error;
     u8 *dRc = nullptr;
     TRY(stageInOut(ctx, refineCellInOut, n, &dRc));
-    if (!dRc) {
-        if (ctx->refineCellN != n) FAIL(AMR_ERR_STATE, "amr_select_unrefine: resident marking has the wrong size (amr_remap_refine_cell after the topology change)");
-        dRc = ctx->refineCell;
+    // the marking lives in the flag-buffer pool; layers ping-pong and the result becomes ctx->refineCell
+    if (dRc) {
+        if (n) CK(cudaMemcpyAsync(ctx->refineCell, dRc, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->refineCellN = n;
+    } else if (ctx->refineCellN != n) {
+        FAIL(AMR_ERR_STATE, "amr_select_unrefine: resident marking has the wrong size (amr_remap_refine_cell after the topology change)");
     }
     // nUnrefinementBufferLayers x extendMarkedCellsAcrossFaces, fvMeshHexRefiner.C:1595-1598
-    u8 *cur = ctx->flagA, *tmp = ctx->flagB;
-    if (n) CK(cudaMemcpyAsync(cur, dRc, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    u8 *cur = ctx->refineCell, *tmp = ctx->flagA;
     for (int i = 0; i < nBufferLayers; i++) {
         u8 *res;
         TRY(extendLayer(ctx, cur, cur, tmp, &res));
         std::swap(cur, tmp);
     }
+    ctx->refineCell = cur; ctx->flagA = tmp;
     // protections, fvMeshHexRefiner.C:1600-1622
     if (ctx->protCell && n) LAUNCH(k_masked_set, gridFor(n), kThreads, n, ctx->protCell, cur, (u8)1);
     for (int k = 0; k < nProtectedPatches; k++) {
@@ -734,7 +792,8 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
         const Patch &pp = ctx->patches[q];
         if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)1);
     }
-    if (n) CK(cudaMemcpyAsync(dRc, cur, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (dRc && n) CK(cudaMemcpyAsync(dRc, cur, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    dRc = cur;
     // U1+U2+U3 fused: maxCellField + getSplitElems + filter
     u8 *pflag = ctx->flagC;
     if (p) {
@@ -744,9 +803,8 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
         else LAUNCH(k_select_unrefine_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, ctx->pc.count, ctx->bndPoint,
                     ctx->parentIdx, ctx->lvl8, dErr, unrefineLevel, dRc, (u8 *)nullptr, pflag);
     }
-    // B3: consistentUnrefinement(list, false)   (cur/tmp are free again: flagA/flagB)
-    TRY(unrefineSweeps(ctx, pflag, sweepsOut));
-    TRY(emitList(ctx, pflag, p, elemsOut, nOut));
+    // B3: consistentUnrefinement(list, false) + ascending list   (flagA/flagB are free again)
+    TRY(unrefineSweeps(ctx, pflag, sweepsOut, elemsOut, nOut));
     CK(cudaGetLastError());
     return flushOuts(ctx);
 }

@@ -79,6 +79,8 @@ struct amr_ctx {
     double *error = nullptr;   // [n]
     u8 *refineCell = nullptr;  // [n] marking kept between the refine and unrefine stages
     int64_t refineCellN = 0;
+    int64_t flagCap = 0;        // capacity (bytes) of flagA/B/C and refineCell: they are swapped by pointer
+    int64_t nTotalCells = -1;   // mesh_.globalData().nTotalCells(), reduced once per mesh
 
     // scratch (sized at mesh_set)
     u8 *flagA = nullptr, *flagB = nullptr;      // [max(n,p)]

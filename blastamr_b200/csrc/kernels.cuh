@@ -115,7 +115,7 @@ __global__ void k_pack_f64(int64_t b, const label *__restrict__ bOwner, const do
 // the "can still spread" test of the first forced buffer layer (fvMeshRefiner.C:809-813):
 //   mark[c] = lo <= e <= hi ;  src[c] = mark[c] && maxLevel(c) > cellLevel[c]
 __global__ void __launch_bounds__(kThreads)
-k_candidates(int64_t n, const double *__restrict__ err, double lo, double hi, const label *__restrict__ lvl,
+k_candidates(int64_t n, const double *__restrict__ err, double lo, double hi, const u8 *__restrict__ lvl,
              const label *__restrict__ maxLvl, label maxLvlUniform, u8 *__restrict__ mark, u8 *__restrict__ src,
              bool aligned) {
     // 4 consecutive cells per thread: 2 x 16 B of error, 16 B of levels in flight, 4 B stores
@@ -130,11 +130,11 @@ k_candidates(int64_t n, const double *__restrict__ err, double lo, double hi, co
         m.z = (e[2] >= lo) && (e[2] <= hi); m.w = (e[3] >= lo) && (e[3] <= hi);
         *reinterpret_cast<uchar4 *>(mark + c0) = m;
         if (src) {
-            const int4 l = *reinterpret_cast<const int4 *>(lvl + c0);
+            const uchar4 l = *reinterpret_cast<const uchar4 *>(lvl + c0);
             int4 mx = make_int4(maxLvlUniform, maxLvlUniform, maxLvlUniform, maxLvlUniform);
             if (maxLvl) mx = *reinterpret_cast<const int4 *>(maxLvl + c0);
             uchar4 sr;
-            sr.x = m.x && (mx.x > l.x); sr.y = m.y && (mx.y > l.y); sr.z = m.z && (mx.z > l.z); sr.w = m.w && (mx.w > l.w);
+            sr.x = m.x && (mx.x > (int)l.x); sr.y = m.y && (mx.y > (int)l.y); sr.z = m.z && (mx.z > (int)l.z); sr.w = m.w && (mx.w > (int)l.w);
             *reinterpret_cast<uchar4 *>(src + c0) = sr;
         }
         return;
@@ -145,8 +145,42 @@ k_candidates(int64_t n, const double *__restrict__ err, double lo, double hi, co
         mark[c] = m;
         if (src) {
             label mx = maxLvl ? maxLvl[c] : maxLvlUniform;
-            src[c] = m && (mx > lvl[c]);
+            src[c] = m && (mx > (label)lvl[c]);
         }
+    }
+}
+
+// selectRefineCells filter for a uniform maxRefinement (the case of every config): 16 cells per
+// thread on packed bytes (SIMD-in-word compares), lf = level + set.
+__global__ void __launch_bounds__(kThreads)
+k_select_filter16(int64_t n, const u8 *__restrict__ cand, const u8 *__restrict__ lvl8, int maxLvlUniform,
+                  const u8 *__restrict__ unrefineable, u8 *__restrict__ set, u8 *__restrict__ lf) {
+    const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 16;
+    if (c0 >= n) return;
+    const unsigned mxb = (unsigned)min(max(maxLvlUniform, 0), 255) * 0x01010101u;
+    if (c0 + 16 <= n) {
+        const uint4 c4 = *reinterpret_cast<const uint4 *>(cand + c0);
+        const uint4 l4 = *reinterpret_cast<const uint4 *>(lvl8 + c0);
+        uint4 u4 = make_uint4(0, 0, 0, 0);
+        if (unrefineable) u4 = *reinterpret_cast<const uint4 *>(unrefineable + c0);
+        auto one = [&](unsigned c, unsigned l, unsigned u, unsigned &sel, unsigned &lfv) {
+            const unsigned lt = __vcmpltu4(l, mxb) & 0x01010101u;       // level < maxRefinement
+            const unsigned nz = __vcmpne4(c, 0u) & 0x01010101u;         // candidate
+            const unsigned nu = __vcmpeq4(u, 0u) & 0x01010101u;         // !unrefineable
+            sel = lt & nz & nu;
+            lfv = __vadd4(l, sel);
+        };
+        uint4 s4, f4;
+        one(c4.x, l4.x, u4.x, s4.x, f4.x); one(c4.y, l4.y, u4.y, s4.y, f4.y);
+        one(c4.z, l4.z, u4.z, s4.z, f4.z); one(c4.w, l4.w, u4.w, s4.w, f4.w);
+        *reinterpret_cast<uint4 *>(set + c0) = s4;
+        *reinterpret_cast<uint4 *>(lf + c0) = f4;
+        return;
+    }
+    for (int64_t c = c0; c < n; c++) {
+        const u8 sel = cand[c] && ((int)lvl8[c] < maxLvlUniform) && !(unrefineable && unrefineable[c]);
+        set[c] = sel;
+        lf[c] = (u8)(lvl8[c] + sel);
     }
 }
 
@@ -464,77 +498,85 @@ k_select_unrefine_points(int64_t p, const int32_t *__restrict__ sliceOff, const 
     if (keep) keep[pt] = kp;
 }
 
+// ---- sparse passes of consistentUnrefinement --------------------------------------------------
+// Candidate split points / cells marked for unrefinement are a small fraction of the mesh, so these
+// passes scan 16 flags per thread with one 128-bit load and only walk the rows of set entries.
+template <class Fn>
+__device__ __forceinline__ void forEachSet16(const u8 *flags, int64_t N, bool aligned, Fn fn) {
+    const int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 16;
+    if (base >= N) return;
+    if (aligned && base + 16 <= N) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(flags + base);
+        if ((w.x | w.y | w.z | w.w) == 0) return;
+        const unsigned v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if ((v[k >> 2] >> (8 * (k & 3))) & 0xffu) fn(base + k);
+    } else {
+        for (int k = 0; k < 16 && base + k < N; k++)
+            if (flags[base + k]) fn(base + k);
+    }
+}
+
 // unrefineCell = union of pointCells over flagged points (hexRef3D.C:1763-1776); cells pre-zeroed
 __global__ void __launch_bounds__(kThreads)
 k_points_to_cells(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-                  const u8 *__restrict__ pflag, u8 *__restrict__ cflag) {
-    const int64_t pt = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (pt >= p || !pflag[pt]) return;
-    const int32_t base = sliceOff[pt >> 5];
-    const int w = sliceOff[(pt >> 5) + 1] - base;
-    const int32_t *row = col + ((size_t)base << 5) + (pt & 31);
-    for (int j = 0; j < w; j++) {
-        int32_t q = row[(size_t)j << 5];
-        if (q >= 0) cflag[q] = 1;
-    }
+                  const u8 *__restrict__ pflag, bool aligned, u8 *__restrict__ cflag) {
+    forEachSet16(pflag, p, aligned, [&](int64_t pt) {
+        const int32_t base = sliceOff[pt >> 5];
+        const int w = sliceOff[(pt >> 5) + 1] - base;
+        const int32_t *row = col + ((size_t)base << 5) + (pt & 31);
+        for (int j = 0; j < w; j++) {
+            int32_t q = row[(size_t)j << 5];
+            if (q >= 0) cflag[q] = 1;
+        }
+    });
 }
 
-// lfm[c] = cellLevel - unrefineCell (payload of the swap at hexRef3D.C:1843-1853)
-__global__ void k_level_minus(int64_t n, const u8 *__restrict__ lvl8, const u8 *__restrict__ uc, u8 *__restrict__ lfm) {
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n) lfm[c] = (u8)(lvl8[c] - uc[c]);
+// cellLevel - unrefineCell at the owners of the boundary faces (payload of the swap at hexRef3D.C:1843-1853)
+__global__ void k_pack_level_minus(int64_t b, const label *__restrict__ bOwner, const u8 *__restrict__ lvl8,
+                                   const u8 *__restrict__ uc, u8 *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b) { label o = bOwner[i]; out[i] = (u8)(lvl8[o] - uc[o]); }
 }
 
-// Face sweep of hexRef3D::consistentUnrefinement (hexRef3D.C:1785-1889, maxSet=false): a cell
-// marked for unrefinement is unmarked when a face neighbour would end up more than one level
-// finer.  lfm = cellLevel - unrefineCell, updated in place (monotone: flags only drop).
+// Face sweep of hexRef3D::consistentUnrefinement (hexRef3D.C:1785-1889, maxSet=false): a cell marked
+// for unrefinement is unmarked when a face neighbour would end up more than one level finer.
+// In-place on uc (monotone: flags only drop).  Only marked cells can change, so only they are walked.
 __global__ void __launch_bounds__(kThreads)
 k_unrefine_sweep(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-                 u8 *__restrict__ lfm, u8 *__restrict__ uc, const u8 *__restrict__ ghostLfm, int *changed) {
-    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const unsigned live = __ballot_sync(0xffffffffu, c < n);
-    int flip = 0;
-    if (c < n) {
-        const int isSet = uc[c];
-        if (__any_sync(live, isSet != 0)) {
-            const int64_t s = c >> 5;
-            const int lane = (int)(c & 31);
-            const int32_t base = sliceOff[s];
-            const int w = sliceOff[s + 1] - base;
-            const int32_t *row = col + ((size_t)base << 5) + lane;
-            const int mine = lfm[c];
-            int mx = 0;
-            for (int j0 = 0; j0 < w; j0 += kChunk) {
-                int32_t q[kChunk];
-#pragma unroll
-                for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
-#pragma unroll
-                for (int k = 0; k < kChunk; k++) {
-                    int v = (q[k] < n) ? lfm[q[k]] : ghostLfm[q[k] - n];
-                    mx = max(mx, v);
-                }
-            }
-            if (isSet && mine < mx - 1) { uc[c] = 0; lfm[c] = (u8)(mine + 1); flip = 1; }
+                 const u8 *__restrict__ lvl8, u8 *uc, bool aligned, const u8 *__restrict__ ghostLfm, int *changed) {
+    const int32_t n32 = (int32_t)n;
+    forEachSet16(uc, n, aligned, [&](int64_t c) {
+        const int32_t base = sliceOff[c >> 5];
+        const int w = sliceOff[(c >> 5) + 1] - base;
+        const int32_t *row = col + ((size_t)base << 5) + (c & 31);
+        const int mine = (int)lvl8[c] - 1;
+        int mx = 0;
+        for (int j = 0; j < w; j++) {
+            const int32_t q = row[(size_t)j << 5];
+            const int v = (q < n32) ? (int)lvl8[q] - (int)uc[q] : (int)ghostLfm[q - n32];
+            mx = max(mx, v);
         }
-    }
-    if (__syncthreads_or(flip) && threadIdx.x == 0) *changed = 1;
+        if (mine < mx - 1) { uc[c] = 0; *changed = 1; }
+    });
 }
 
 // knock out every flagged point that has a cell which cannot be unrefined (hexRef3D.C:1908-1926)
 __global__ void __launch_bounds__(kThreads)
 k_knock_points(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-               u8 *__restrict__ pflag, const u8 *__restrict__ uc) {
-    const int64_t pt = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (pt >= p || !pflag[pt]) return;
-    const int32_t base = sliceOff[pt >> 5];
-    const int w = sliceOff[(pt >> 5) + 1] - base;
-    const int32_t *row = col + ((size_t)base << 5) + (pt & 31);
-    bool ok = true;
-    for (int j = 0; j < w; j++) {
-        int32_t q = row[(size_t)j << 5];
-        if (q >= 0 && !uc[q]) { ok = false; break; }
-    }
-    if (!ok) pflag[pt] = 0;
+               u8 *pflag, bool aligned, const u8 *__restrict__ uc) {
+    forEachSet16(pflag, p, aligned, [&](int64_t pt) {
+        const int32_t base = sliceOff[pt >> 5];
+        const int w = sliceOff[(pt >> 5) + 1] - base;
+        const int32_t *row = col + ((size_t)base << 5) + (pt & 31);
+        bool ok = true;
+        for (int j = 0; j < w; j++) {
+            int32_t q = row[(size_t)j << 5];
+            if (q >= 0 && !uc[q]) { ok = false; break; }
+        }
+        if (!ok) pflag[pt] = 0;
+    });
 }
 
 // ------------------------------------------------------------------------------------------

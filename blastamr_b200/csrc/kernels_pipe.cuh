@@ -89,7 +89,7 @@ kp_estimate(SellView S, const double *__restrict__ x, const double *ghost, doubl
 }
 
 template <bool GHOST>
-__global__ void __launch_bounds__(kPipeThreads)
+__global__ void __launch_bounds__(kPipeThreads, 7)
 kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, const u8 *ghost, u8 *__restrict__ out) {
     const int32_t n = (int32_t)S.rows;
     const u8 *ghostBase = ghost - n;
@@ -112,7 +112,7 @@ kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, con
 }
 
 template <bool MAXSET, bool GHOST>
-__global__ void __launch_bounds__(kPipeThreads)
+__global__ void __launch_bounds__(kPipeThreads, 7)
 kp_refine_sweep(SellView S, u8 *lf, u8 *set, const u8 *ghostLf, int *changed) {
     const int32_t n = (int32_t)S.rows;
     const u8 *ghostBase = ghostLf - n;
@@ -141,7 +141,7 @@ kp_refine_sweep(SellView S, u8 *lf, u8 *set, const u8 *ghostLf, int *changed) {
     });
 }
 
-__global__ void __launch_bounds__(kPipeThreads)
+__global__ void __launch_bounds__(kPipeThreads, 7)
 kp_select_unrefine_points(SellView S, const u8 *__restrict__ pcCount, const u8 *__restrict__ bndPoint,
                           const label *__restrict__ parentIdx, const u8 *__restrict__ lvl8,
                           const double *__restrict__ err, double unrefineLevel, const u8 *__restrict__ marked,
