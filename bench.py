@@ -142,11 +142,11 @@ def measured_peak():
 def oracle_step(O, w, xs, n_new_maps):
     """The same step on the CPU oracle (all ranks of the world)."""
     e = w.estimate("delta", xs)
-    w.normalize(e, THR, GREAT, THR, GREAT)
+    w.normalize_world(e, THR, GREAT, THR, GREAT)
     rc, rs, sw = w.hex_select_refine(e, MAX_LEVEL, LAYERS_REF)
-    for r, (cm, f1, f3) in enumerate(n_new_maps):
-        O.map_field(cm, f1, 1)
-        O.map_field(cm, f3, 3)
+    cms = [m[0] for m in n_new_maps]
+    w.map_field_world(cms, [m[1] for m in n_new_maps], [m[3] for m in n_new_maps], 1)
+    w.map_field_world(cms, [m[2] for m in n_new_maps], [m[4] for m in n_new_maps], 3)
     up, sp, sw2 = w.hex_select_unrefine(e, rc, LAYERS_UNREF)
     return rs, up, sw, sw2
 
@@ -173,7 +173,7 @@ def cpu_sample(n_side, ranks, threads):
     for l, s, xx in zip(loc, rs, xs):
         cells = np.flatnonzero(s).astype(np.int32)
         cm = np.concatenate([np.arange(l.n, dtype=np.int32), np.repeat(cells, 7)])
-        maps.append((cm, xx, np.stack([xx, xx, xx], axis=1).copy()))
+        maps.append((cm, xx, np.stack([xx, xx, xx], axis=1).copy(), np.empty(len(cm)), np.empty((len(cm), 3))))
     return O, w, xs, maps, g.n
 
 

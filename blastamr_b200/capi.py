@@ -14,7 +14,7 @@ import numpy as np
 from . import _build
 
 AMR_OK = 0
-EST = {"delta": 0, "scaledDelta": 1, "Lohner": 2, "fieldValue": 3, "codedDelta": 4}
+EST = {"delta": 0, "scaledDelta": 1, "Lohner": 2, "fieldValue": 3, "codedDelta": 4, "densityGradient": 5}
 HEX3D, HEX2D, POLY3D, POLY2D = 0, 1, 2, 3
 MAP_DIRECT, MAP_CONSERVATIVE = 0, 1
 
@@ -34,11 +34,14 @@ _SIGS = {
     "amr_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "amr_mesh_set": (C.c_int, [C.c_void_p] + [C.c_int64] * 4 + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 4),
     "amr_mesh_set_points": (C.c_int, [C.c_void_p] * 4),
+    "amr_mesh_set_geometry": (C.c_int, [C.c_void_p] * 6),
+    "amr_estimate_lohner": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "amr_levels_set": (C.c_int, [C.c_void_p] * 5 + [C.c_int64]),
     "amr_protected_cells_set": (C.c_int, [C.c_void_p, C.c_void_p]),
     "amr_estimate": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int,
                                C.c_void_p, C.c_void_p]),
     "amr_normalize": (C.c_int, [C.c_void_p] + [C.c_double] * 4 + [C.c_void_p]),
+    "amr_normalize_range": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_protect_patches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "amr_select_refine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_int,
                                     C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -155,6 +158,9 @@ class Context:
         self.n, self.f, self.b, self.p = mesh.n, mesh.f, mesh.b, mesh.p
         if mesh.pc_off is not None:
             self._ck(self.L.amr_mesh_set_points(self._h, _ptr(mesh.pc_off), _ptr(mesh.pc_cells), _ptr(mesh.bnd_point)))
+        if getattr(mesh, "Sf", None) is not None and mesh.vol is not None:
+            self._ck(self.L.amr_mesh_set_geometry(self._h, _ptr(mesh.weights), _ptr(mesh.Sf), _ptr(mesh.magSf),
+                                                  _ptr(mesh.delta_coeffs), _ptr(mesh.vol)))
         if mesh.cell_level is not None:
             sp = mesh.split_parent
             nsp = 0 if sp is None else len(sp)
@@ -188,9 +194,25 @@ class Context:
                                      _ptr(out)))
         return out
 
+    def estimate_lohner(self, x, epsilon, x_boundary=None, nbr_values=None, thresholds=None, out=None, keep_resident=False):
+        thr = None if thresholds is None else np.asarray(thresholds, dtype=np.float64)
+        if out is None and not keep_resident:
+            out = np.empty(self.n, dtype=np.float64)
+        self._ck(self.L.amr_estimate_lohner(self._h, _ptr(x), _ptr(x_boundary), _ptr(nbr_values), epsilon,
+                                            0 if thr is None else 1, _ptr(thr), _ptr(out)))
+        return out
+
     def normalize(self, err, lower_refine, upper_refine, lower_unrefine, upper_unrefine):
         self._ck(self.L.amr_normalize(self._h, lower_refine, upper_refine, lower_unrefine, upper_unrefine, _ptr(err)))
         return err
+
+    def normalize_range(self, err, refine_threshold=0.5, unrefine_threshold=0.4, scale=True):
+        """gradientRange.C:102-109: thresholds from gMin/gMax of the raw error, then normalize."""
+        thr = np.zeros(4)
+        mm = np.zeros(2)
+        self._ck(self.L.amr_normalize_range(self._h, refine_threshold, unrefine_threshold, 1 if scale else 0, _ptr(err),
+                                            _ptr(thr), _ptr(mm)))
+        return err, thr, mm
 
     def protect_patches(self, patch_ids, n_layers, err=None) -> int:
         ids = np.asarray(patch_ids, dtype=np.int32)

@@ -8,6 +8,7 @@
 #include "sell.cuh"
 #include "kernels.cuh"
 #include "kernels_pipe.cuh"
+#include "lohner.cuh"
 
 #include <algorithm>
 #include <new>
@@ -86,6 +87,10 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->flagA); devFree(ctx, &ctx->flagB); devFree(ctx, &ctx->flagC); devFree(ctx, &ctx->lf);
     devFree(ctx, &ctx->ghost8); devFree(ctx, &ctx->send8); devFree(ctx, &ctx->ghost64); devFree(ctx, &ctx->send64);
     devFree(ctx, &ctx->tileCnt); devFree(ctx, &ctx->scanAux);
+    devFree(ctx, &ctx->gWeights); devFree(ctx, &ctx->gSf); devFree(ctx, &ctx->gMagSf); devFree(ctx, &ctx->gDelta); devFree(ctx, &ctx->gV);
+    devFree(ctx, &ctx->grad); devFree(ctx, &ctx->xbf);
+    sellFree(ctx, ctx->cf);
+    ctx->haveGeom = false;
     ctx->havePoints = ctx->haveLevels = ctx->haveHistory = false;
     ctx->occCache.clear();
     ctx->refineCellN = 0;
@@ -266,6 +271,42 @@ AMR_API int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_
     return AMR_OK;
 }
 
+AMR_API int amr_mesh_set_geometry(amr_ctx *ctx, const double *weights, const double *Sf, const double *magSf,
+                                  const double *nonOrthDeltaCoeffs, const double *V) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_mesh_set_geometry: call amr_mesh_set first");
+    if (!weights || !Sf || !magSf || !nonOrthDeltaCoeffs || !V) FAIL(AMR_ERR_ARG, "amr_mesh_set_geometry: null pointer");
+    const int64_t n = ctx->n, f = ctx->f, b = ctx->b, nf = f + b;
+    devFree(ctx, &ctx->gWeights); devFree(ctx, &ctx->gSf); devFree(ctx, &ctx->gMagSf); devFree(ctx, &ctx->gDelta); devFree(ctx, &ctx->gV);
+    devFree(ctx, &ctx->grad); devFree(ctx, &ctx->xbf);
+    TRY(devAlloc(ctx, &ctx->gWeights, nf)); TRY(devAlloc(ctx, &ctx->gSf, 3 * nf)); TRY(devAlloc(ctx, &ctx->gMagSf, nf));
+    TRY(devAlloc(ctx, &ctx->gDelta, nf)); TRY(devAlloc(ctx, &ctx->gV, n)); TRY(devAlloc(ctx, &ctx->grad, 3 * n)); TRY(devAlloc(ctx, &ctx->xbf, b));
+    CK(cudaMemcpyAsync(ctx->gWeights, weights, (size_t)nf * 8, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->gSf, Sf, (size_t)nf * 24, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->gMagSf, magSf, (size_t)nf * 8, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->gDelta, nonOrthDeltaCoeffs, (size_t)nf * 8, cudaMemcpyDefault, ctx->stream));
+    if (n) CK(cudaMemcpyAsync(ctx->gV, V, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
+    // cell -> faces SELL, rows ascending in face label
+    sellFree(ctx, ctx->cf);
+    int32_t *deg = nullptr, *cursor = nullptr;
+    CK(cudaMalloc((void **)&deg, (size_t)(n + 1) * 4));
+    CK(cudaMalloc((void **)&cursor, (size_t)(n + 1) * 4));
+    CK(cudaMemsetAsync(deg, 0, (size_t)(n + 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(cursor, 0, (size_t)(n + 1) * 4, ctx->stream));
+    if (nf > 0) LAUNCH(k_cf_deg, gridFor(nf), kThreads, ctx->owner, ctx->neighbour, f, b, deg);
+    int rc = sellAllocFromDeg(ctx, ctx->cf, n, deg, 0);
+    if (rc == AMR_OK) {
+        if (nf > 0) LAUNCH(k_cf_fill, gridFor(nf), kThreads, ctx->owner, ctx->neighbour, f, b, ctx->cf.sliceOff, cursor, ctx->cf.col);
+        if (n > 0) LAUNCH(k_sell_sort_rows, gridFor(n), kThreads, ctx->cf.col, ctx->cf.sliceOff, deg, n);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("amr_mesh_set_geometry: ") + cudaGetErrorString(e); rc = AMR_ERR_CUDA; }
+    }
+    cudaFree(deg); cudaFree(cursor);
+    if (rc != AMR_OK) return rc;
+    ctx->haveGeom = true;
+    return AMR_OK;
+}
+
 AMR_API int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t *pointLevel, const int32_t *visibleCells,
                            const int32_t *splitParent, int64_t nSplit) {
     ENTER();
@@ -326,7 +367,8 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
         if (kind == AMR_EST_FIELD_VALUE) {
             if (scale) LAUNCH((k_pointwise<true, true>), gridFor(n), kThreads, n, dx, t, target);
             else LAUNCH((k_pointwise<true, false>), gridFor(n), kThreads, n, dx, t, target);
-        } else if (kind == AMR_EST_DELTA || kind == AMR_EST_SCALED_DELTA || kind == AMR_EST_CODED_DELTA) {
+        } else if (kind == AMR_EST_DELTA || kind == AMR_EST_SCALED_DELTA || kind == AMR_EST_CODED_DELTA ||
+                   kind == AMR_EST_DENSITY_GRADIENT) {
             const double *ghost = nullptr;
             if (ctx->nCoupled > 0) {
                 if (nbrValues) TRY(stageIn(ctx, nbrValues, b, &ghost));
@@ -351,13 +393,50 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
         else LAUNCH((k_estimate<K, false>), gridFor(n), kThreads, n, so, col, dx, ghost, p0, p1, t, target);      \
     } while (0)
             if (kind == AMR_EST_DELTA) EST(0);
-            else if (kind == AMR_EST_SCALED_DELTA) EST(1);
+            else if (kind == AMR_EST_SCALED_DELTA || kind == AMR_EST_DENSITY_GRADIENT) EST(1);
             else EST(4);
 #undef EST
         } else {
             FAIL(AMR_ERR_ARG, "amr_estimate: estimator kind not available on the device path");
         }
         if (dErr) CK(cudaMemcpyAsync(dErr, target, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_estimate_lohner(amr_ctx *ctx, const double *x, const double *xBoundary, const double *nbrValues,
+                                double epsilon, int scale, const double *thr, double *errorOut) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_estimate_lohner: mesh not set");
+    if (!ctx->haveGeom) FAIL(AMR_ERR_STATE, "amr_estimate_lohner: geometry not set (amr_mesh_set_geometry)");
+    if (!x) FAIL(AMR_ERR_ARG, "amr_estimate_lohner: x is null");
+    if (scale && !thr) FAIL(AMR_ERR_ARG, "amr_estimate_lohner: scale requested without thresholds");
+    const int64_t n = ctx->n, f = ctx->f, b = ctx->b;
+    const double *dx = nullptr, *dxb = nullptr, *dxn = nullptr;
+    double *dErr = nullptr;
+    TRY(stageIn(ctx, x, n, &dx));
+    TRY(stageIn(ctx, xBoundary, b, &dxb));
+    TRY(stageOut(ctx, errorOut, n, &dErr));
+    if (ctx->nCoupled > 0) {
+        if (nbrValues) TRY(stageIn(ctx, nbrValues, b, &dxn));
+        else {
+            LAUNCH(k_pack_f64, gridFor(b), kThreads, b, ctx->owner + f, dx, ctx->send64);
+            TRY(haloExchange(ctx, ctx->send64, ctx->ghost64, 8));
+            dxn = ctx->ghost64;
+        }
+    } else dxn = ctx->ghost64;
+    Geom G{ctx->gWeights, ctx->gSf, ctx->gMagSf, ctx->gDelta, ctx->gV};
+    Thresholds t = mkThr(thr);
+    if (b) LAUNCH(k_boundary_field, gridFor(b), kThreads, b, ctx->owner + f, dx, dxb, dxn, ctx->bCoupled, ctx->xbf);
+    if (n) {
+        LAUNCH(k_gauss_grad, gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
+               (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, ctx->grad);
+        if (scale) LAUNCH((k_lohner<true>), gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
+                          (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, ctx->error);
+        else LAUNCH((k_lohner<false>), gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
+                    (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, ctx->error);
+        if (dErr) CK(cudaMemcpyAsync(dErr, ctx->error, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     CK(cudaGetLastError());
     return flushOuts(ctx);
@@ -373,6 +452,45 @@ AMR_API int amr_normalize(amr_ctx *ctx, double lowerRefine, double upperRefine, 
     if (!e) FAIL(AMR_ERR_STATE, "amr_normalize: no error field");
     Thresholds t{lowerRefine, upperRefine, lowerUnrefine, upperUnrefine};
     if (n) LAUNCH((k_pointwise<false, true>), gridFor(n), kThreads, n, e, t, e);
+    if (dE && n && dE != ctx->error) CK(cudaMemcpyAsync(ctx->error, dE, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_normalize_range(amr_ctx *ctx, double refineThreshold, double unrefineThreshold, int scale,
+                                double *errorInOut, double *thrOut, double *minMaxOut) {
+    ENTER();
+    const int64_t n = ctx->n;
+    double *dE = nullptr;
+    TRY(stageInOut(ctx, errorInOut, n, &dE));
+    double *e = dE ? dE : ctx->error;
+    if (!e) FAIL(AMR_ERR_STATE, "amr_normalize_range: no error field");
+    const int nPart = (int)std::min<int64_t>((int64_t)ctx->numSMs * 8, std::max<int64_t>(1, (n + kThreads - 1) / kThreads));
+    void *q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(2 * nPart + 2) * 8));
+    double *part = (double *)q, *res = part + 2 * nPart;
+    double mm[2] = {kGREAT * 1e285, -kGREAT * 1e285};
+    if (n > 0) {
+        LAUNCH(k_minmax_partial, (unsigned)nPart, kThreads, n, (const double *)e, part);
+        LAUNCH(k_minmax_final, 1, 1, nPart, (const double *)part, res);
+    } else {
+        CK(cudaMemcpyAsync(res, mm, 16, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (ctx->comm && ctx->nranks > 1) {      // gMin / gMax
+        NCK(ncclAllReduce(res, res, 1, ncclFloat64, ncclMin, ctx->comm, ctx->stream));
+        NCK(ncclAllReduce(res + 1, res + 1, 1, ncclFloat64, ncclMax, ctx->comm, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(mm, res, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double minE = mm[0], maxE = mm[1];
+    Thresholds t;
+    t.lowerRefine = minE + refineThreshold * (maxE - minE);      // gradientRange.C:105
+    t.upperRefine = kGREAT;
+    t.lowerUnrefine = minE + unrefineThreshold * (maxE - minE);  // gradientRange.C:107
+    t.upperUnrefine = kGREAT;
+    if (thrOut) { thrOut[0] = t.lowerRefine; thrOut[1] = t.upperRefine; thrOut[2] = t.lowerUnrefine; thrOut[3] = t.upperUnrefine; }
+    if (minMaxOut) { minMaxOut[0] = minE; minMaxOut[1] = maxE; }
+    if (scale && n) LAUNCH((k_pointwise<false, true>), gridFor(n), kThreads, n, e, t, e);
     if (dE && n && dE != ctx->error) CK(cudaMemcpyAsync(ctx->error, dE, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaGetLastError());
     return flushOuts(ctx);

@@ -65,6 +65,12 @@ struct amr_ctx {
     Sell cc;                   // cell -> face-neighbour cells (+ ghost slots n + bface for coupled faces)
     Sell pc;                   // point -> cells
     bool havePoints = false;
+    // geometry (Lohner)
+    bool haveGeom = false;
+    double *gWeights = nullptr, *gSf = nullptr, *gMagSf = nullptr, *gDelta = nullptr, *gV = nullptr;
+    Sell cf;                   // cell -> faces (2*face + role), ascending
+    double *grad = nullptr;    // [3n]
+    double *xbf = nullptr;     // [b] boundaryField of x
     u8 *bndPoint = nullptr;
 
     // levels / history

@@ -100,6 +100,33 @@ k_pointwise(int64_t n, const double *__restrict__ in, Thresholds thr, double *__
     out[c] = SCALE ? normalizeValue(v, thr) : v;
 }
 
+// gMin / gMax of a field (gradientRange.C:102-103): per-CTA partials, exact (min/max are order-free)
+__global__ void __launch_bounds__(kThreads)
+k_minmax_partial(int64_t n, const double *__restrict__ v, double *__restrict__ part) {
+    __shared__ double smn[kThreads / 32], smx[kThreads / 32];
+    double mn = kGREAT * 1e285, mx = -kGREAT * 1e285;   // +-1e300: outside any field value
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        const double x = v[i];
+        mn = fminFoam(mn, x);
+        mx = fmaxFoam(mx, x);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        mn = fminFoam(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+        mx = fmaxFoam(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < kThreads / 32; i++) { mn = fminFoam(mn, smn[i]); mx = fmaxFoam(mx, smx[i]); }
+        part[2 * blockIdx.x] = mn; part[2 * blockIdx.x + 1] = mx;
+    }
+}
+__global__ void k_minmax_final(int nPart, const double *__restrict__ part, double *__restrict__ out) {
+    double mn = part[0], mx = part[1];
+    for (int i = 1; i < nPart; i++) { mn = fminFoam(mn, part[2 * i]); mx = fmaxFoam(mx, part[2 * i + 1]); }
+    out[0] = mn; out[1] = mx;
+}
+
 // patchInternalField of the field for every boundary face: send buffer of the swap
 __global__ void k_pack_f64(int64_t b, const label *__restrict__ bOwner, const double *__restrict__ x,
                            double *__restrict__ out) {

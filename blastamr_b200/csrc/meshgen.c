@@ -55,6 +55,11 @@ typedef struct mg_mesh {
     i32 *pointGlobal;     /* p : global point id (decomposed meshes), else NULL */
     i32 *faceGlobal;      /* f+b: global face id (decomposed meshes), else NULL */
     i32 *pxyz;            /* 3p integer point coordinates in fine units (octree meshes) */
+    /* fvMesh geometry (octree meshes): surfaceInterpolation::weights(), Sf(), magSf(), nonOrthDeltaCoeffs() */
+    double *Sf;           /* 3(f+b) face area vectors, owner -> neighbour / outward */
+    double *magSf;        /* f+b */
+    double *weights;      /* f+b owner-side linear weights (1 on boundary faces) */
+    double *deltaCoeffs;  /* f+b nonOrthDeltaCoeffs */
 } mg_mesh;
 
 static void *xmalloc(size_t s) {
@@ -80,7 +85,7 @@ MG_API void mg_mesh_free(mg_mesh *m) {
     free(m->pcOff); free(m->pcCells); free(m->cpOff); free(m->cpPts);
     free(m->bndPoint); free(m->cellLevel); free(m->pointLevel); free(m->visible);
     free(m->splitParent); free(m->cellGlobal); free(m->pointGlobal); free(m->faceGlobal);
-    free(m->pxyz);
+    free(m->pxyz); free(m->Sf); free(m->magSf); free(m->weights); free(m->deltaCoeffs);
     free(m);
 }
 
@@ -106,6 +111,7 @@ MG_API void *mg_mesh_array(const mg_mesh *m, int id) {
     case 16: return m->splitParent; case 17: return m->cellGlobal;
     case 18: return m->pointGlobal; case 19: return m->faceGlobal;
     case 20: return m->pxyz;
+    case 21: return m->Sf; case 22: return m->magSf; case 23: return m->weights; case 24: return m->deltaCoeffs;
     }
     return NULL;
 }
@@ -504,7 +510,7 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
     for (i64 c = 0; c < n; c++) for (i32 i = cnt[c]; i < cnt[c + 1]; i++) own[i] = (i32)c;
     for (i64 i = 0; i < b; i++) own[f + i] = bcell[i];
     m->owner = own; m->neighbour = nei;
-    free(cnt); free(bcell); free(bside);
+    free(cnt); free(bcell);
 
     /* --- geometry, levels, history */
     m->cc = (double *)xmalloc(n * 3 * 8); m->vol = (double *)xmalloc(n * 8);
@@ -523,6 +529,69 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
     m->nsplit = o->nsplit;
     m->splitParent = (i32 *)xmalloc((o->nsplit ? o->nsplit : 1) * 4);
     memcpy(m->splitParent, o->splitParent, o->nsplit * 4);
+
+    if (flags & 2) {
+        /* face geometry from the cells' boxes: the face is the contact rectangle of two cubes */
+        i64 nf = f + b;
+        m->Sf = (double *)xcalloc(nf * 3, 8); m->magSf = (double *)xmalloc(nf * 8);
+        m->weights = (double *)xmalloc(nf * 8); m->deltaCoeffs = (double *)xmalloc(nf * 8);
+        double h0[3] = {h0x, h0y, h0z};
+        #pragma omp parallel for schedule(static)
+        for (i64 i = 0; i < nf; i++) {
+            i64 c = own[i];
+            int lc = o->cellLvl[c];
+            double sc = 1.0 / (double)(1 << lc);
+            double lo_c[3] = {o->cx[c] * sc * h0x, o->cy[c] * sc * h0y, o->cz[c] * sc * h0z};
+            double hi_c[3] = {(o->cx[c] + 1) * sc * h0x, (o->cy[c] + 1) * sc * h0y, (o->cz[c] + 1) * sc * h0z};
+            double Cc[3] = {m->cc[3 * c], m->cc[3 * c + 1], m->cc[3 * c + 2]};
+            double Cf[3], S[3] = {0, 0, 0}, Cn[3];
+            if (i < f) {
+                i64 q = nei[i];
+                int lq = o->cellLvl[q];
+                double sq = 1.0 / (double)(1 << lq);
+                i32 cq[3] = {o->cx[q], o->cy[q], o->cz[q]};
+                i32 ccv[3] = {o->cx[c], o->cy[c], o->cz[c]};
+                int axis = -1, sign = 0;
+                double area = 1.0;
+                for (int a = 0; a < 3; a++) {
+                    /* integer comparison in fine units decides the contact axis */
+                    i64 loC = (i64)ccv[a] << (o->lcap - lc), hiC = (i64)(ccv[a] + 1) << (o->lcap - lc);
+                    i64 loQ = (i64)cq[a] << (o->lcap - lq), hiQ = (i64)(cq[a] + 1) << (o->lcap - lq);
+                    if (hiC == loQ) { axis = a; sign = 1; }
+                    else if (hiQ == loC) { axis = a; sign = -1; }
+                }
+                for (int a = 0; a < 3; a++) {
+                    double loQ = cq[a] * sq * h0[a], hiQ = (cq[a] + 1) * sq * h0[a];
+                    if (a == axis) { Cf[a] = sign > 0 ? hi_c[a] : lo_c[a]; continue; }
+                    double lo = lo_c[a] > loQ ? lo_c[a] : loQ, hi = hi_c[a] < hiQ ? hi_c[a] : hiQ;
+                    area *= (hi - lo); Cf[a] = 0.5 * (lo + hi);
+                }
+                S[axis] = sign * area;
+                Cn[0] = m->cc[3 * q]; Cn[1] = m->cc[3 * q + 1]; Cn[2] = m->cc[3 * q + 2];
+                double magS = fabs(area);
+                double SfdOwn = fabs(S[0] * (Cf[0] - Cc[0]) + S[1] * (Cf[1] - Cc[1]) + S[2] * (Cf[2] - Cc[2]));
+                double SfdNei = fabs(S[0] * (Cn[0] - Cf[0]) + S[1] * (Cn[1] - Cf[1]) + S[2] * (Cn[2] - Cf[2]));
+                m->weights[i] = SfdNei / (SfdOwn + SfdNei);          /* surfaceInterpolation::makeWeights */
+                double d[3] = {Cn[0] - Cc[0], Cn[1] - Cc[1], Cn[2] - Cc[2]};
+                double nd = (S[0] * d[0] + S[1] * d[1] + S[2] * d[2]) / magS;
+                double md = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                m->deltaCoeffs[i] = 1.0 / (nd > 0.05 * md ? nd : 0.05 * md);   /* makeNonOrthDeltaCoeffs */
+                m->magSf[i] = magS;
+            } else {
+                int side = bside[i - f];
+                int axis = side >> 1, hi = side & 1;
+                double area = 1.0;
+                for (int a = 0; a < 3; a++) if (a != axis) area *= (hi_c[a] - lo_c[a]);
+                S[axis] = hi ? area : -area;
+                m->magSf[i] = area;
+                m->weights[i] = 1.0;
+                double dn = 0.5 * (hi_c[axis] - lo_c[axis]);
+                m->deltaCoeffs[i] = 1.0 / dn;
+            }
+            m->Sf[3 * i] = S[0]; m->Sf[3 * i + 1] = S[1]; m->Sf[3 * i + 2] = S[2];
+        }
+    }
+    free(bside);
 
     if (!(flags & 1)) { free(nb); return m; }
 
@@ -661,6 +730,7 @@ MG_API int mg_decompose(const mg_mesh *g, const i32 *cellRank, int nranks, mg_me
         m->f = fl; m->b = bl;
         m->owner = (i32 *)xmalloc((fl + bl) * 4); m->neighbour = (i32 *)xmalloc((fl ? fl : 1) * 4);
         m->faceGlobal = (i32 *)xmalloc((fl + bl) * 4);
+        u8 *flip = (u8 *)xcalloc(fl + bl + 1, 1);   /* local owner is the global neighbour */
         i64 fi = 0;
         i64 *pfill = (i64 *)xmalloc(nranks * 8); memcpy(pfill, pstart, nranks * 8);
         for (i64 i = 0; i < f; i++) {
@@ -668,7 +738,7 @@ MG_API int mg_decompose(const mg_mesh *g, const i32 *cellRank, int nranks, mg_me
             int ro = cellRank[o_], rn = cellRank[n_];
             if (ro == r && rn == r) { m->owner[fi] = loc[o_]; m->neighbour[fi] = loc[n_]; m->faceGlobal[fi] = (i32)i; fi++; }
             else if (ro == r) { i64 k = pfill[rn]++; m->owner[k] = loc[o_]; m->faceGlobal[k] = (i32)i; }
-            else if (rn == r) { i64 k = pfill[ro]++; m->owner[k] = loc[n_]; m->faceGlobal[k] = (i32)i; }
+            else if (rn == r) { i64 k = pfill[ro]++; m->owner[k] = loc[n_]; m->faceGlobal[k] = (i32)i; flip[k] = 1; }
         }
         for (int q = 0; q < g->npatch; q++) {
             i64 k = m->patchStart[q];
@@ -677,6 +747,21 @@ MG_API int mg_decompose(const mg_mesh *g, const i32 *cellRank, int nranks, mg_me
                 if (cellRank[g->owner[gf]] == r) { m->owner[k] = loc[g->owner[gf]]; m->faceGlobal[k] = (i32)gf; k++; }
             }
         }
+        /* face geometry: cut faces seen from the global neighbour get Sf reversed and the
+           complementary weight (coupledFvPatch weights are computed from the local side) */
+        if (g->Sf) {
+            i64 nfl = fl + bl;
+            m->Sf = (double *)xmalloc(nfl * 3 * 8); m->magSf = (double *)xmalloc(nfl * 8);
+            m->weights = (double *)xmalloc(nfl * 8); m->deltaCoeffs = (double *)xmalloc(nfl * 8);
+            for (i64 k = 0; k < nfl; k++) {
+                i64 gf = m->faceGlobal[k];
+                double sg = flip[k] ? -1.0 : 1.0;
+                m->Sf[3 * k] = sg * g->Sf[3 * gf]; m->Sf[3 * k + 1] = sg * g->Sf[3 * gf + 1]; m->Sf[3 * k + 2] = sg * g->Sf[3 * gf + 2];
+                m->magSf[k] = g->magSf[gf]; m->deltaCoeffs[k] = g->deltaCoeffs[gf];
+                m->weights[k] = flip[k] ? 1.0 - g->weights[gf] : g->weights[gf];
+            }
+        }
+        free(flip);
         /* cells */
         m->cc = (double *)xmalloc(nl * 3 * 8); m->vol = (double *)xmalloc(nl * 8);
         m->cellLevel = (i32 *)xmalloc(nl * 4); m->visible = (i32 *)xmalloc(nl * 4);

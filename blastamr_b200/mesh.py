@@ -88,6 +88,10 @@ class PolyMesh:
     point_global: Optional[np.ndarray] = None
     face_global: Optional[np.ndarray] = None
     pxyz: Optional[np.ndarray] = None
+    Sf: Optional[np.ndarray] = None            # float64 [f+b,3]
+    magSf: Optional[np.ndarray] = None
+    weights: Optional[np.ndarray] = None       # owner-side linear weights [f+b]
+    delta_coeffs: Optional[np.ndarray] = None  # nonOrthDeltaCoeffs [f+b]
     _handle: Optional[int] = field(default=None, repr=False)
 
     # patch arrays in the layout the C-ABI takes
@@ -143,6 +147,8 @@ def _wrap(handle: int, names: Sequence[str], copy: bool = False) -> PolyMesh:
         visible=arr(15, np.int32, n), split_parent=arr(16, np.int32, max(nsplit, 0)),
         cell_global=arr(17, np.int32, n), point_global=arr(18, np.int32, p), face_global=arr(19, np.int32, f + b),
         pxyz=arr(20, np.int32, 3 * p, (p, 3)),
+        Sf=arr(21, np.float64, 3 * (f + b), (f + b, 3)), magSf=arr(22, np.float64, f + b),
+        weights=arr(23, np.float64, f + b), delta_coeffs=arr(24, np.float64, f + b),
     )
     if m.split_parent is None:
         m.split_parent = np.zeros(0, np.int32)
@@ -190,8 +196,8 @@ class Octree:
     def ncells(self) -> int:
         return int(lib().mg_oct_ncells(self._h))
 
-    def build(self, points: bool = True, copy: bool = False) -> PolyMesh:
-        h = lib().mg_oct_build(self._h, 1 if points else 0)
+    def build(self, points: bool = True, copy: bool = False, geometry: bool = False) -> PolyMesh:
+        h = lib().mg_oct_build(self._h, (1 if points else 0) | (2 if geometry else 0))
         return _wrap(h, self.names, copy=copy)
 
     def refine(self, cells: np.ndarray) -> np.ndarray:

@@ -58,7 +58,12 @@ enum {
     AMR_EST_SCALED_DELTA = 1, /* "scaledDelta"  scaledDelta.C:71-141 */
     AMR_EST_LOHNER = 2,       /* "Lohner"       Lohner.C:71-159 (needs amr_mesh_set_geometry) */
     AMR_EST_FIELD_VALUE = 3,  /* "fieldValue"   fieldValue.C:68-82 */
-    AMR_EST_CODED_DELTA = 4   /* coded delta w/o clamp, tutorials/damBreak2D/constant/dynamicMeshDict:24-65 */
+    AMR_EST_CODED_DELTA = 4,  /* coded delta w/o clamp, tutorials/damBreak2D/constant/dynamicMeshDict:24-65 */
+    AMR_EST_DENSITY_GRADIENT = 5 /* "densityGradient": named by the north star but ABSENT from the reference tree
+                                    (0 grep hits; upstream blastFoam only).  Defined here as the scaled face
+                                    delta of rho, |rho_o-rho_n| / max(min(rho_o,rho_n), minValue) -- i.e. the
+                                    arithmetic of scaledDelta.C:78-136 applied to the density field.  No in-tree
+                                    oracle: parity unpinned by construction. */
 };
 
 /* patch types for amr_mesh_set (only "coupled" matters on this path) */
@@ -117,6 +122,12 @@ int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_t *pcCel
 int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t *pointLevel,
                    const int32_t *visibleCells, const int32_t *splitParent, int64_t nSplit);
 
+/* fvMesh geometry needed by the Lohner estimator only (Lohner.C:78-82 -> cubic interpolation + Gauss
+   gradient): surfaceInterpolation::weights() [f+b], Sf() [3(f+b)], magSf() [f+b],
+   nonOrthDeltaCoeffs() [f+b], V() [n].  Boundary entries follow the boundary-face order. */
+int amr_mesh_set_geometry(amr_ctx *ctx, const double *weights, const double *Sf, const double *magSf,
+                          const double *nonOrthDeltaCoeffs, const double *V);
+
 /* fvMeshHexRefiner::protectedCell_ (fvMeshHexRefiner.C:1014-1465 computes it on the host);
    NULL = empty list. */
 int amr_protected_cells_set(amr_ctx *ctx, const uint8_t *protectedCell);
@@ -137,9 +148,27 @@ int amr_protected_cells_set(amr_ctx *ctx, const uint8_t *protectedCell);
 int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *nbrValues,
                  double p0, double p1, int scale, const double *thr, double *errorOut);
 
+/* Lohner::update (Lohner.C:71-159).  x [n]; xBoundary [b] = x.boundaryField() values on the physical
+   patches (NULL = zeroGradient, the owner cell value); nbrValues [b] = patchNeighbourField() on coupled
+   faces (NULL = swapped by the library / no coupled faces).  The OpenFOAM-core part (cubic, gaussGrad) is
+   restated from upstream: parity unpinned (see oracle/amr_oracle.c:or_estimate_lohner). */
+int amr_estimate_lohner(amr_ctx *ctx, const double *x, const double *xBoundary, const double *nbrValues,
+                        double epsilon, int scale, const double *thr, double *errorOut);
+
 /* errorEstimator::normalize on its own (errorEstimator.C:204-228).  errorInOut NULL = resident. */
 int amr_normalize(amr_ctx *ctx, double lowerRefine, double upperRefine, double lowerUnrefine,
                   double upperUnrefine, double *errorInOut);
+
+/* Threshold part of gradientEstimator::update (gradientRange.C:102-109) and of the coded selectors of
+   the flame tutorials (tutorials/poly_freelyPropFlame2D_H2/constant/dynamicMeshDict:50-58):
+     maxE = gMax(error), minE = gMin(error)           (all-reduced over ranks with a communicator)
+     lowerRefine = minE + refineThreshold (maxE-minE), lowerUnrefine = minE + unrefineThreshold (maxE-minE),
+     upperRefine = upperUnrefine = GREAT; then normalize() when scale != 0.
+   errorInOut: raw error (e.g. mag(fvc::grad(T)) computed by the host) or NULL for the resident field.
+   thrOut[4] (host, nullable) receives {lowerRefine, upperRefine, lowerUnrefine, upperUnrefine};
+   minMaxOut[2] (host, nullable) receives {minE, maxE}. */
+int amr_normalize_range(amr_ctx *ctx, double refineThreshold, double unrefineThreshold, int scale,
+                        double *errorInOut, double *thrOut, double *minMaxOut);
 
 /* errorEstimator::protectPatches (errorEstimator.C:329-365): seed = owners of the faces of the
    listed patches, grow nLayers face layers (:347), set error = 0 there.  nProtected (host,

@@ -73,6 +73,8 @@ typedef struct {
     const label *cellLevel, *pointLevel;
     const label *visible;           /* history_.visibleCells() */
     const label *splitParent;       /* history_.splitCells()[i].parent_ */
+    /* fvMesh geometry (Lohner only) */
+    const scalar *weights, *Sf, *magSf, *deltaCoeffs, *V;
     /* derived: primitiveMesh::cells() */
     label *cfOff, *cfFaces;
 } or_mesh;
@@ -136,6 +138,12 @@ OR_API void or_world_set_levels(or_world *w, int r, const label *cellLevel, cons
     m->cellLevel = cellLevel; m->pointLevel = pointLevel; m->visible = visible; m->splitParent = splitParent;
 }
 
+OR_API void or_world_set_geometry(or_world *w, int r, const scalar *weights, const scalar *Sf, const scalar *magSf,
+                                  const scalar *deltaCoeffs, const scalar *V) {
+    or_mesh *m = &w->m[r];
+    m->weights = weights; m->Sf = Sf; m->magSf = magSf; m->deltaCoeffs = deltaCoeffs; m->V = V;
+}
+
 /* --- syncTools restated for ranks living in one address space ----------------------------- */
 
 /* patch on rank s that faces rank r (processor patch pairs list their faces in the same order) */
@@ -154,6 +162,7 @@ static void swap_boundary_label(const or_world *w, label **v) {
         snd[r] = (label *)malloc(sizeof(label) * (size_t)(w->m[r].b ? w->m[r].b : 1));
         memcpy(snd[r], v[r], sizeof(label) * (size_t)w->m[r].b);
     }
+    PAR_RANKS
     for (int r = 0; r < R; r++) {
         const or_mesh *m = &w->m[r];
         for (int q = 0; q < m->npatch; q++) if (m->patchType[q] == 2) {
@@ -175,6 +184,7 @@ static void swap_boundary_scalar(const or_world *w, scalar **v) {
         snd[r] = (scalar *)malloc(sizeof(scalar) * (size_t)(w->m[r].b ? w->m[r].b : 1));
         memcpy(snd[r], v[r], sizeof(scalar) * (size_t)w->m[r].b);
     }
+    PAR_RANKS
     for (int r = 0; r < R; r++) {
         const or_mesh *m = &w->m[r];
         for (int q = 0; q < m->npatch; q++) if (m->patchType[q] == 2) {
@@ -225,6 +235,33 @@ OR_API void or_normalize(int64_t n, scalar *error, scalar lowerRefine, scalar up
         else if (error[celli] > lowerRefine && error[celli] < upperRefine) error[celli] = 1.0;
         else error[celli] = 0.0;
     }
+}
+
+/* gradientEstimator::update threshold part, gradientRange.C:102-109: gMax/gMin over all ranks */
+OR_API void or_range_thresholds(const or_world *w, const scalar *const *error, scalar refineThreshold,
+                                scalar unrefineThreshold, scalar *thr /*[4]*/, scalar *minMax /*[2]*/) {
+    int first = 1;
+    scalar maxGrad = 0, minGrad = 0;
+    for (int r = 0; r < w->R; r++)
+        for (int64_t c = 0; c < w->m[r].n; c++) {
+            scalar v = error[r][c];
+            if (first) { maxGrad = minGrad = v; first = 0; }
+            maxGrad = smax(maxGrad, v);
+            minGrad = smin(minGrad, v);
+        }
+    thr[0] = minGrad + refineThreshold * (maxGrad - minGrad);   /* lowerRefine_ */
+    thr[1] = GREAT;                                               /* upperRefine_ */
+    thr[2] = minGrad + unrefineThreshold * (maxGrad - minGrad); /* lowerUnrefine_ */
+    thr[3] = GREAT;                                               /* upperUnrefine_ */
+    if (minMax) { minMax[0] = minGrad; minMax[1] = maxGrad; }
+}
+
+/* normalize on every rank of the world (each MPI rank normalises its own field) */
+OR_API void or_normalize_world(const or_world *w, scalar **error, scalar lowerRefine, scalar upperRefine,
+                               scalar lowerUnrefine, scalar upperUnrefine) {
+    PAR_RANKS
+    for (int r = 0; r < w->R; r++)
+        or_normalize(w->m[r].n, error[r], lowerRefine, upperRefine, lowerUnrefine, upperUnrefine);
 }
 
 /*
@@ -294,6 +331,103 @@ OR_API void or_estimate(const or_world *w, int kind, const scalar *const *xin, s
     }
     for (int r = 0; r < R; r++) { free(x[r]); free(fn[r]); }
     free(x); free(fn);
+}
+
+/*
+ * Lohner::update, Lohner.C:71-159.
+ *
+ * xf = cubic<scalar>(mesh_).interpolate(x) is OpenFOAM core (NOT in the reference tree).  Restated
+ * from upstream OpenFOAM-v2212 -- PARITY UNPINNED, no reference test or fixture pins these values:
+ *   surfaceInterpolationScheme::interpolate(vf, lambdas):   lambda*(vf[P] - vf[N]) + vf[N]
+ *   ... (vf, lambdas, ys):                                  lambda*vf[P] + y*vf[N]
+ *   coupled patch faces:                                    pLambda*patchInternalField + (1 - pLambda)*patchNeighbourField
+ *   linear weights = mesh.weights(); corrected scheme: interpolate = linear + correction
+ *   cubic::correction (cubic.H): kSc = l(1 - l(3 - 2l)), kVecP = sqr(1-l) l, kVecN = sqr(l)(l-1);
+ *       corr = interpolate(vf, kSc, -kSc)
+ *            + (interpolate(gaussGrad(vf), kVecP, kVecN) & Sf)/magSf/nonOrthDeltaCoeffs
+ *       (boundary values of corr are zeroed on non-coupled patches; Lohner never reads xf's boundary)
+ *   fv::gaussGrad::gradf: for internal faces in ascending order  g[own] += Sf*ssf; g[nei] -= Sf*ssf;
+ *       then per patch  g[faceCells] += pSf*pssf;  then g /= V      (ssf = linear interpolate of vf)
+ * xb[r]: boundaryField values of x over boundary faces (NULL = zeroGradient: owner cell value);
+ * on processor patches the patch field holds the received neighbour values.
+ */
+OR_API void or_estimate_lohner(const or_world *w, const scalar *const *x, const scalar *const *xbIn, scalar epsilon,
+                               scalar **error) {
+    int R = w->R;
+    scalar **xn = (scalar **)malloc(sizeof(scalar *) * R);   /* patchNeighbourField over boundary faces */
+    for (int r = 0; r < R; r++) {
+        const or_mesh *m = &w->m[r];
+        xn[r] = (scalar *)malloc(sizeof(scalar) * (size_t)(m->b + 1));
+        for (int64_t i = 0; i < m->b; i++) xn[r][i] = x[r][m->owner[m->f + i]];
+    }
+    swap_boundary_scalar(w, xn);
+    PAR_RANKS
+    for (int r = 0; r < R; r++) {
+        const or_mesh *m = &w->m[r];
+        const scalar *xr = x[r];
+        int64_t n = m->n, f = m->f, b = m->b;
+        unsigned char *coupled = (unsigned char *)calloc((size_t)(b + 1), 1);
+        for (int q = 0; q < m->npatch; q++) if (m->patchType[q] == 2)
+            for (label i = 0; i < m->patchSize[q]; i++) coupled[m->patchStart[q] - f + i] = 1;
+        /* boundaryField of x */
+        scalar *xbf = (scalar *)malloc(sizeof(scalar) * (size_t)(b + 1));
+        for (int64_t i = 0; i < b; i++) {
+            if (coupled[i]) xbf[i] = xn[r][i];
+            else xbf[i] = (xbIn && xbIn[r]) ? xbIn[r][i] : xr[m->owner[f + i]];
+        }
+        /* gaussGrad(linear) */
+        scalar *g = (scalar *)calloc((size_t)(3 * n + 3), sizeof(scalar));
+        for (int64_t facei = 0; facei < f; facei++) {
+            label P = m->owner[facei], N = m->neighbour[facei];
+            scalar ssf = m->weights[facei] * (xr[P] - xr[N]) + xr[N];
+            for (int k = 0; k < 3; k++) {
+                scalar Sfssf = m->Sf[3 * facei + k] * ssf;
+                g[3 * P + k] += Sfssf;
+                g[3 * N + k] -= Sfssf;
+            }
+        }
+        for (int64_t i = 0; i < b; i++) {
+            int64_t facei = f + i;
+            label P = m->owner[facei];
+            scalar pssf;
+            if (coupled[i]) pssf = m->weights[facei] * xr[P] + (1.0 - m->weights[facei]) * xn[r][i];
+            else pssf = xbf[i];
+            for (int k = 0; k < 3; k++) g[3 * P + k] += m->Sf[3 * facei + k] * pssf;
+        }
+        for (int64_t c = 0; c < n; c++) for (int k = 0; k < 3; k++) g[3 * c + k] /= m->V[c];
+        /* Lohner.C:84-110 */
+        scalar *err = error[r];
+        for (int64_t c = 0; c < n; c++) err[c] = 0.0;
+        for (int64_t facei = 0; facei < f; facei++) {
+            label own = m->owner[facei], nei = m->neighbour[facei];
+            scalar l = m->weights[facei];
+            scalar kSc = l * (1.0 - l * (3.0 - 2.0 * l));
+            scalar kVecP = ((1.0 - l) * (1.0 - l)) * l;
+            scalar kVecN = (l * l) * (l - 1.0);
+            scalar corr = kSc * xr[own] + (-kSc) * xr[nei];
+            scalar gi[3];
+            for (int k = 0; k < 3; k++) gi[k] = kVecP * g[3 * own + k] + kVecN * g[3 * nei + k];
+            scalar dot = gi[0] * m->Sf[3 * facei] + gi[1] * m->Sf[3 * facei + 1] + gi[2] * m->Sf[3 * facei + 2];
+            corr = corr + dot / m->magSf[facei] / m->deltaCoeffs[facei];
+            scalar xf = (l * (xr[own] - xr[nei]) + xr[nei]) + corr;
+            scalar eT = sqrt(smag(xr[nei] - 2.0 * xf + xr[own])
+                             / (smag(xr[nei] - xf) + smag(xf - xr[own])
+                                + epsilon * (smag(xr[nei]) + 2.0 * smag(xf) + smag(xr[own]))));
+            err[own] = smax(err[own], eT);
+            err[nei] = smax(err[nei], eT);
+        }
+        /* coupled patches, Lohner.C:113-154 */
+        for (int64_t i = 0; i < b; i++) if (coupled[i]) {
+            label cell = m->owner[f + i];
+            scalar xp = xr[cell], xnv = xn[r][i], xb = xbf[i];
+            scalar eT = sqrt(smag(xnv - 2.0 * xb + xp)
+                             / (smag(xnv - xb) + smag(xb - xp) + epsilon * (smag(xnv) + 2.0 * smag(xb) + smag(xp))));
+            err[cell] = smax(err[cell], eT);
+        }
+        free(coupled); free(xbf); free(g);
+    }
+    for (int r = 0; r < R; r++) free(xn[r]);
+    free(xn);
 }
 
 /* ======================================================================================= */
@@ -828,6 +962,13 @@ OR_API int64_t or_check_levels(const or_world *w, const label *const *cellLevel)
 OR_API void or_map_field(int64_t nNew, const label *cellMap, int nComp, const scalar *oldF, scalar *newF) {
     for (int64_t i = 0; i < nNew; i++)
         for (int k = 0; k < nComp; k++) newF[i * nComp + k] = oldF[(int64_t)cellMap[i] * nComp + k];
+}
+
+/* fvMesh::mapFields on every rank of the world */
+OR_API void or_map_field_world(const or_world *w, const int64_t *nNew, const label *const *cellMap, int nComp,
+                               const scalar *const *oldF, scalar **newF) {
+    PAR_RANKS
+    for (int r = 0; r < w->R; r++) or_map_field(nNew[r], cellMap[r], nComp, oldF[r], newF[r]);
 }
 
 /* Optional conservative (volume-weighted) merge, the north-star's "conservative averaging":

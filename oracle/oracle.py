@@ -18,7 +18,7 @@ SMALL = 1e-15
 GREAT = 1e15
 SQRT_SMALL = float(np.sqrt(1e-15))
 
-KIND = {"delta": 0, "scaledDelta": 1, "Lohner": 2, "fieldValue": 3, "codedDelta": 4}
+KIND = {"delta": 0, "scaledDelta": 1, "Lohner": 2, "fieldValue": 3, "codedDelta": 4, "densityGradient": 1}
 
 
 def build(force: bool = False) -> Path:
@@ -45,6 +45,11 @@ def lib():
         L.or_world_set_points.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.or_world_set_levels.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.or_normalize.argtypes = [C.c_int64, C.c_void_p] + [C.c_double] * 4
+        L.or_world_set_geometry.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.or_estimate_lohner.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        L.or_range_thresholds.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        L.or_normalize_world.argtypes = [C.c_void_p, C.c_void_p] + [C.c_double] * 4
+        L.or_map_field_world.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.or_estimate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
         L.or_protect_patches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.or_consistent_refinement.restype = C.c_int
@@ -102,6 +107,10 @@ class World:
                      np.ascontiguousarray(m.bnd_point, dtype=np.uint8)]
                 self._keep += a
                 L.or_world_set_points(self._h, r, *[x.ctypes.data for x in a])
+            if getattr(m, "Sf", None) is not None and m.vol is not None:
+                a = [np.ascontiguousarray(v, dtype=np.float64) for v in (m.weights, m.Sf, m.magSf, m.delta_coeffs, m.vol)]
+                self._keep += a
+                L.or_world_set_geometry(self._h, r, *[v.ctypes.data for v in a])
             if m.cell_level is not None:
                 sp = _i32(m.split_parent) if m.split_parent is not None and len(m.split_parent) else np.full(1, -1, np.int32)
                 a = [_i32(m.cell_level), _i32(m.point_level) if m.point_level is not None else np.zeros(max(m.p, 1), np.int32),
@@ -121,11 +130,34 @@ class World:
         lib().or_estimate(self._h, KIND[kind], _pp(x), _pp(err), min_val, offset)
         return err
 
+    def estimate_lohner(self, x: List[np.ndarray], epsilon: float, xb=None):
+        """Lohner.C:71-159 (needs meshes built with geometry=True); xb = boundaryField values or None (zeroGradient)"""
+        x = [np.ascontiguousarray(a, dtype=np.float64) for a in x]
+        err = [np.empty(m.n, dtype=np.float64) for m in self.meshes]
+        lib().or_estimate_lohner(self._h, _pp(x), None if xb is None else _pp(xb), epsilon, _pp(err))
+        return err
+
     @staticmethod
     def normalize(err: List[np.ndarray], lower_refine, upper_refine=GREAT, lower_unrefine=None, upper_unrefine=GREAT):
         for e in err:
             lib().or_normalize(len(e), e.ctypes.data, lower_refine, upper_refine, lower_unrefine, upper_unrefine)
         return err
+
+    def range_thresholds(self, err, refine_threshold=0.5, unrefine_threshold=0.4):
+        thr = np.zeros(4)
+        mm = np.zeros(2)
+        lib().or_range_thresholds(self._h, _pp(err), refine_threshold, unrefine_threshold, thr.ctypes.data, mm.ctypes.data)
+        return thr, mm
+
+    def normalize_world(self, err, lower_refine, upper_refine, lower_unrefine, upper_unrefine):
+        """same, all ranks at once (rank-parallel under set_threads)"""
+        lib().or_normalize_world(self._h, _pp(err), lower_refine, upper_refine, lower_unrefine, upper_unrefine)
+        return err
+
+    def map_field_world(self, cell_maps, olds, news, ncomp):
+        nn = np.array([len(c) for c in cell_maps], dtype=np.int64)
+        lib().or_map_field_world(self._h, nn.ctypes.data, _pp(cell_maps), ncomp, _pp(olds), _pp(news))
+        return news
 
     def protect_patches(self, err: List[np.ndarray], patch_ids, n_layers: int):
         ids = _i32(patch_ids)

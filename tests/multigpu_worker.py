@@ -30,7 +30,7 @@ def main():
     ctx.comm_init(world, rank, uid[0])
 
     oc = cases.graded_octree(12, 3, centre=(0.5, 0.5, 0.5), r0=0.3, band=0.1)
-    g = oc.build()
+    g = oc.build(geometry=True)
     loc = M.decompose(g, M.simple_ranks(g, (1, 1, 1), PROCS[world]), world)
     me = loc[rank]
     cg = me.cell_global
@@ -46,6 +46,18 @@ def main():
             got = ctx.estimate(kind, x[cg].copy(), p0=1e-3)
             if not np.array_equal(ref[cg], got):
                 fails.append(f"estimate {kind}")
+        # Lohner against the multi-rank oracle world on the same decomposition
+        refL = wR.estimate_lohner([x[l.cell_global].copy() for l in loc], 0.05)[rank]
+        gotL = ctx.estimate_lohner(x[cg].copy(), 0.05)
+        if not np.array_equal(refL, gotL):
+            fails.append("Lohner")
+        # gradientRange thresholds (gMin/gMax over ranks)
+        raw = w.estimate("delta", [x])[0]
+        thr_g, mm_g = w.range_thresholds([raw], 0.5, 0.4)
+        refn = raw.copy(); w.normalize([refn], *thr_g)
+        gotn, gthr, gmm = ctx.normalize_range(raw[cg].copy(), 0.5, 0.4)
+        if not (np.array_equal(thr_g, gthr) and np.array_equal(refn[cg], gotn)):
+            fails.append("gradientRange thresholds")
         e = w.estimate("delta", [x]); w.normalize(e, *thr)
         eg = ctx.estimate("delta", x[cg].copy(), thresholds=thr)
         if not np.array_equal(e[0][cg], eg):

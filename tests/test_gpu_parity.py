@@ -207,6 +207,55 @@ def test_protected_cells_and_quota(ctx, O):
     ctx.set_protected_cells(None)
 
 
+@pytest.mark.parametrize("meshname", ["uniform", "graded"])
+def test_lohner_bitwise(ctx, O, meshname):
+    """Lohner.C:71-159 incl. the restated cubic/gaussGrad arithmetic: GPU == oracle bit for bit"""
+    if meshname == "uniform":
+        m = M.Octree(12, 10, 8, (1.0, 0.8, 0.7), 0).build(geometry=True)
+    else:
+        m = cases.graded_octree(8, 3).build(geometry=True)
+    w = O.World([m])
+    ctx.set_mesh(m)
+    x = cases.front_field(m.cc, centre=(0.45, 0.4, 0.35), r0=0.25, w=0.06)
+    rng = np.random.default_rng(2)
+    xb = x[m.owner[m.f:]] + 0.01 * rng.standard_normal(m.b)      # fixedValue-like boundary field
+    for eps, xbv in ((0.05, None), (0.2, xb)):
+        ref = w.estimate_lohner([x], eps, None if xbv is None else [xbv])[0]
+        got = ctx.estimate_lohner(x, eps, x_boundary=xbv)
+        assert not np.isnan(ref).any()
+        assert np.array_equal(ref.view(np.int64), got.view(np.int64))
+        thr = (0.3, 1e15, 0.2, 1e15)
+        refn = ref.copy()
+        w.normalize([refn], *thr)
+        assert np.array_equal(refn, ctx.estimate_lohner(x, eps, x_boundary=xbv, thresholds=thr))
+
+
+def test_gradient_range_thresholds(ctx, O):
+    """gradientRange.C:102-109 on a host-computed raw error (the gradient itself stays on the host)"""
+    m = cases.graded_octree(8, 2).build()
+    ctx.set_mesh(m)
+    w = O.World([m])
+    rng = np.random.default_rng(11)
+    raw = rng.random(m.n) ** 3 * 7.0 + 0.25
+    for rt, ut in ((0.5, 0.4), (0.3, 0.06)):
+        thr, mm = w.range_thresholds([raw], rt, ut)
+        ref = raw.copy()
+        w.normalize([ref], *thr)
+        got, gthr, gmm = ctx.normalize_range(raw.copy(), rt, ut)
+        assert np.array_equal(thr, gthr) and np.array_equal(mm, gmm)
+        assert np.array_equal(ref, got)
+        assert (got == 1).sum() > 0 and (got == -1).sum() > 0
+
+
+def test_density_gradient_alias(ctx, O):
+    """densityGradient is absent from the reference; defined here as scaledDelta's arithmetic on rho"""
+    m = cases.graded_octree(8, 2).build()
+    ctx.set_mesh(m)
+    w = O.World([m])
+    rho = cases.front_field(m.cc, w=0.05)
+    assert np.array_equal(w.estimate("densityGradient", [rho], min_val=1e-6)[0], ctx.estimate("densityGradient", rho, p0=1e-6))
+
+
 def test_no_cpu_fallback_message():
     from blastamr_b200 import capi
     with pytest.raises(capi.AmrError):
