@@ -34,6 +34,7 @@ _SIGS = {
     "amr_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "amr_mesh_set": (C.c_int, [C.c_void_p] + [C.c_int64] * 4 + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 4),
     "amr_mesh_set_points": (C.c_int, [C.c_void_p] * 4),
+    "amr_mesh_set_edges": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 4),
     "amr_mesh_set_geometry": (C.c_int, [C.c_void_p] * 6),
     "amr_estimate_lohner": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "amr_levels_set": (C.c_int, [C.c_void_p] * 5 + [C.c_int64]),
@@ -158,6 +159,10 @@ class Context:
         self.n, self.f, self.b, self.p = mesh.n, mesh.f, mesh.b, mesh.p
         if mesh.pc_off is not None:
             self._ck(self.L.amr_mesh_set_points(self._h, _ptr(mesh.pc_off), _ptr(mesh.pc_cells), _ptr(mesh.bnd_point)))
+        self.n_edges = int(getattr(mesh, "n_edges", 0) or 0)
+        if self.n_edges:
+            self._ck(self.L.amr_mesh_set_edges(self._h, mesh.n_edges, _ptr(mesh.edge_pts), _ptr(mesh.ec_off), _ptr(mesh.ec_cells),
+                                               _ptr(mesh.bnd_edge)))
         if getattr(mesh, "Sf", None) is not None and mesh.vol is not None:
             self._ck(self.L.amr_mesh_set_geometry(self._h, _ptr(mesh.weights), _ptr(mesh.Sf), _ptr(mesh.magSf),
                                                   _ptr(mesh.delta_coeffs), _ptr(mesh.vol)))
@@ -256,7 +261,7 @@ class Context:
                         kind=HEX3D, elems_out=None, want_count=True):
         ids = np.asarray(protected_patch_ids, dtype=np.int32)
         if elems_out is None:
-            elems_out = np.empty(max(self.p, 1), dtype=np.int32)
+            elems_out = np.empty(max(self.p, getattr(self, "n_edges", 0), 1), dtype=np.int32)
         cnt = C.c_int64(0)
         sweeps = C.c_int(0)
         self._ck(self.L.amr_select_unrefine(self._h, _ptr(err), unrefine_level, _ptr(refine_cell), n_layers, _ptr(ids),
@@ -267,7 +272,7 @@ class Context:
         return cnt.value, sweeps.value
 
     def split_elems(self, kind=HEX3D):
-        out = np.empty(max(self.p, 1), dtype=np.int32)
+        out = np.empty(max(self.p, getattr(self, "n_edges", 0), 1), dtype=np.int32)
         cnt = C.c_int64(0)
         self._ck(self.L.amr_get_split_elems(self._h, kind, _ptr(out), C.byref(cnt)))
         return out[:cnt.value]

@@ -91,6 +91,8 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->grad); devFree(ctx, &ctx->xbf);
     sellFree(ctx, ctx->cf);
     ctx->haveGeom = false;
+    sellFree(ctx, ctx->ec); devFree(ctx, &ctx->bndEdge); devFree(ctx, &ctx->edgePts);
+    ctx->haveEdges = false; ctx->nEdges = 0;
     ctx->havePoints = ctx->haveLevels = ctx->haveHistory = false;
     ctx->occCache.clear();
     ctx->refineCellN = 0;
@@ -268,6 +270,58 @@ AMR_API int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_
     if (p) CK(cudaMemcpyAsync(ctx->bndPoint, bndPoint, (size_t)p, cudaMemcpyDefault, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->havePoints = true;
+    return AMR_OK;
+}
+
+// grow the pointer-swapped flag pool (flagA/B/C + refineCell) to hold `need` bytes each
+static int growFlagPool(amr_ctx *ctx, int64_t need) {
+    if (need <= ctx->flagCap) return AMR_OK;
+    u8 **bufs[4] = {&ctx->flagA, &ctx->flagB, &ctx->flagC, &ctx->refineCell};
+    for (auto pb : bufs) {
+        u8 *nb = nullptr;
+        CK(cudaMalloc((void **)&nb, (size_t)need));
+        CK(cudaMemsetAsync(nb, 0, (size_t)need, ctx->stream));
+        if (*pb) { CK(cudaMemcpyAsync(nb, *pb, (size_t)ctx->flagCap, cudaMemcpyDeviceToDevice, ctx->stream)); }
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (*pb) cudaFree(*pb);
+        *pb = nb;
+        ctx->devBytes += need - ctx->flagCap;
+    }
+    ctx->flagCap = need;
+    int64_t tiles = (need + kTile - 1) / kTile + 8;
+    if (tiles > ctx->tileCap) {
+        devFree(ctx, &ctx->tileCnt); devFree(ctx, &ctx->scanAux);
+        ctx->tileCap = tiles;
+        TRY(devAlloc(ctx, &ctx->tileCnt, ctx->tileCap));
+        ctx->scanAuxCap = 2 * (ctx->tileCap / kScanTile + 1024);
+        TRY(devAlloc(ctx, &ctx->scanAux, ctx->scanAuxCap));
+    }
+    return AMR_OK;
+}
+
+AMR_API int amr_mesh_set_edges(amr_ctx *ctx, int64_t nEdges, const int32_t *edgePoints, const int32_t *ecOff,
+                               const int32_t *ecCells, const uint8_t *bndEdge) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_mesh_set_edges: call amr_mesh_set first");
+    if (nEdges < 0 || !edgePoints || !ecOff || !bndEdge) FAIL(AMR_ERR_ARG, "amr_mesh_set_edges: bad arguments");
+    const int32_t *dOff = nullptr, *dIdx = nullptr;
+    TRY(stageIn(ctx, ecOff, nEdges + 1, &dOff));
+    int32_t nnz = 0;
+    CK(cudaMemcpyAsync(&nnz, dOff + nEdges, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (nnz < 0 || (nnz > 0 && !ecCells)) FAIL(AMR_ERR_ARG, "amr_mesh_set_edges: bad edgeCells CSR");
+    TRY(stageIn(ctx, ecCells, nnz, &dIdx));
+    TRY(sellBuildFromCsr(ctx, ctx->ec, nEdges, dOff, dIdx));
+    devFree(ctx, &ctx->bndEdge); devFree(ctx, &ctx->edgePts);
+    TRY(devAlloc(ctx, &ctx->bndEdge, nEdges)); TRY(devAlloc(ctx, &ctx->edgePts, 2 * nEdges));
+    if (nEdges) {
+        CK(cudaMemcpyAsync(ctx->bndEdge, bndEdge, (size_t)nEdges, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->edgePts, edgePoints, (size_t)nEdges * 8, cudaMemcpyDefault, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    TRY(growFlagPool(ctx, nEdges + 16));
+    ctx->nEdges = nEdges;
+    ctx->haveEdges = true;
     return AMR_OK;
 }
 
@@ -843,8 +897,8 @@ AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nNew, const int32_t *cel
 
 // hexRef3D::consistentUnrefinement loop (hexRef3D.C:1758-1927) on point flags + ascending list
 // (hexRef3D.C:1930-1950), list compacted speculatively after each sweep (one round trip per sweep)
-static int unrefineSweeps(amr_ctx *ctx, u8 *pflag, int *sweepsOut, int32_t *elemsOut, int64_t *nOut) {
-    const int64_t n = ctx->n, b = ctx->b, p = ctx->p;
+static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOut, int32_t *elemsOut, int64_t *nOut) {
+    const int64_t n = ctx->n, b = ctx->b, p = EL.rows;
     u8 *uc = ctx->flagB;     // unrefineCell
     const bool alP = (((uintptr_t)pflag) & 15) == 0, alC = (((uintptr_t)uc) & 15) == 0;
     const unsigned gP = gridFor(p, kThreads * 16), gC = gridFor(n, kThreads * 16);
@@ -852,7 +906,7 @@ static int unrefineSweeps(amr_ctx *ctx, u8 *pflag, int *sweepsOut, int32_t *elem
     ListJob job;
     while (true) {
         CK(cudaMemsetAsync(uc, 0, (size_t)n, ctx->stream));
-        if (p) LAUNCH(k_points_to_cells, gP, kThreads, p, ctx->pc.sliceOff, ctx->pc.col, pflag, alP, uc);
+        if (p) LAUNCH(k_points_to_cells, gP, kThreads, p, EL.sliceOff, EL.col, pflag, alP, uc);
         CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(int), ctx->stream));
         if (ctx->nCoupled > 0) {
             LAUNCH(k_pack_level_minus, gridFor(b), kThreads, b, ctx->owner + ctx->f, ctx->lvl8, uc, ctx->send8);
@@ -864,7 +918,7 @@ static int unrefineSweeps(amr_ctx *ctx, u8 *pflag, int *sweepsOut, int32_t *elem
         int changed = 0;
         TRY(finishList(ctx, &job, 0, &changed, nOut, false));
         if (!changed) break;
-        if (p) LAUNCH(k_knock_points, gP, kThreads, p, ctx->pc.sliceOff, ctx->pc.col, pflag, alP, uc);
+        if (p) LAUNCH(k_knock_points, gP, kThreads, p, EL.sliceOff, EL.col, pflag, alP, uc);
         if (sweeps > 100000) FAIL(AMR_ERR_INVARIANT, "unrefinement sweeps did not converge");
     }
     TRY(finishListCopy(ctx, &job));
@@ -879,7 +933,9 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_select_unrefine: mesh not set");
     if (!ctx->havePoints) FAIL(AMR_ERR_STATE, "amr_select_unrefine: point addressing not set (amr_mesh_set_points)");
     if (!ctx->haveLevels || !ctx->haveHistory) FAIL(AMR_ERR_STATE, "amr_select_unrefine: levels/history not set");
-    if (refinerKind != AMR_REFINER_HEX3D) FAIL(AMR_ERR_ARG, "amr_select_unrefine: only hexRef3D is on the device path in this round");
+    if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D)
+        FAIL(AMR_ERR_ARG, "amr_select_unrefine: only the hexRefiner cutters (hexRef3D, hexRef2D) are on the device path in this round");
+    if (refinerKind == AMR_REFINER_HEX2D && !ctx->haveEdges) FAIL(AMR_ERR_STATE, "amr_select_unrefine: hexRef2D needs amr_mesh_set_edges");
     if (nProtectedPatches > 0 && !protectedPatchIds) FAIL(AMR_ERR_ARG, "amr_select_unrefine: protectedPatchIds is null");
     const int64_t n = ctx->n, p = ctx->p;
     const double *dErr = nullptr;
@@ -914,6 +970,14 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     dRc = cur;
     // U1+U2+U3 fused: maxCellField + getSplitElems + filter
     u8 *pflag = ctx->flagC;
+    if (refinerKind == AMR_REFINER_HEX2D) {
+        const int64_t ne = ctx->nEdges;
+        if (ne) LAUNCH(k_select_unrefine_edges, gridFor(ne), kThreads, ne, ctx->ec.sliceOff, ctx->ec.col, ctx->ec.count, ctx->bndEdge,
+                       ctx->edgePts, ctx->pc.sliceOff, ctx->pc.col, ctx->parentIdx, ctx->lvl8, dErr, unrefineLevel, dRc, (u8 *)nullptr, pflag);
+        TRY(unrefineSweeps(ctx, ctx->ec, pflag, sweepsOut, elemsOut, nOut));
+        CK(cudaGetLastError());
+        return flushOuts(ctx);
+    }
     if (p) {
         if (pipeOk(ctx, ctx->pc))
             TRY(launchPipe(ctx, kp_select_unrefine_points, ctx->pc, (const u8 *)ctx->pc.count, (const u8 *)ctx->bndPoint,
@@ -922,7 +986,7 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
                     ctx->parentIdx, ctx->lvl8, dErr, unrefineLevel, dRc, (u8 *)nullptr, pflag);
     }
     // B3: consistentUnrefinement(list, false) + ascending list   (flagA/flagB are free again)
-    TRY(unrefineSweeps(ctx, pflag, sweepsOut, elemsOut, nOut));
+    TRY(unrefineSweeps(ctx, ctx->pc, pflag, sweepsOut, elemsOut, nOut));
     CK(cudaGetLastError());
     return flushOuts(ctx);
 }
@@ -930,9 +994,19 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
 AMR_API int amr_get_split_elems(amr_ctx *ctx, int refinerKind, int32_t *elemsOut, int64_t *nOut) {
     ENTER();
     if (!ctx->havePoints || !ctx->haveHistory) FAIL(AMR_ERR_STATE, "amr_get_split_elems: points/history not set");
-    if (refinerKind != AMR_REFINER_HEX3D) FAIL(AMR_ERR_ARG, "amr_get_split_elems: only hexRef3D");
+    if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D) FAIL(AMR_ERR_ARG, "amr_get_split_elems: hexRef3D / hexRef2D only");
     const int64_t p = ctx->p;
     u8 *pflag = ctx->flagC;
+    if (refinerKind == AMR_REFINER_HEX2D) {
+        if (!ctx->haveEdges) FAIL(AMR_ERR_STATE, "amr_get_split_elems: hexRef2D needs amr_mesh_set_edges");
+        const int64_t ne = ctx->nEdges;
+        if (ne) LAUNCH(k_select_unrefine_edges, gridFor(ne), kThreads, ne, ctx->ec.sliceOff, ctx->ec.col, ctx->ec.count, ctx->bndEdge,
+                       ctx->edgePts, ctx->pc.sliceOff, ctx->pc.col, ctx->parentIdx, ctx->lvl8, (const double *)nullptr, 0.0,
+                       (const u8 *)nullptr, pflag, (u8 *)nullptr);
+        TRY(emitList(ctx, pflag, ne, elemsOut, nOut));
+        CK(cudaGetLastError());
+        return flushOuts(ctx);
+    }
     if (p) LAUNCH(k_select_unrefine_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, ctx->pc.count, ctx->bndPoint,
                   ctx->parentIdx, ctx->lvl8, (const double *)nullptr, 0.0, (const u8 *)nullptr, pflag, (u8 *)nullptr);
     TRY(emitList(ctx, pflag, p, elemsOut, nOut));

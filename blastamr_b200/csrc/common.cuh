@@ -65,6 +65,12 @@ struct amr_ctx {
     Sell cc;                   // cell -> face-neighbour cells (+ ghost slots n + bface for coupled faces)
     Sell pc;                   // point -> cells
     bool havePoints = false;
+    // 2-D cutter: edges as split elements
+    bool haveEdges = false;
+    int64_t nEdges = 0;
+    Sell ec;                   // edge -> cells
+    u8 *bndEdge = nullptr;
+    label *edgePts = nullptr;  // [2*nEdges]
     // geometry (Lohner)
     bool haveGeom = false;
     double *gWeights = nullptr, *gSf = nullptr, *gMagSf = nullptr, *gDelta = nullptr, *gV = nullptr;

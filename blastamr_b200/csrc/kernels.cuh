@@ -525,6 +525,53 @@ k_select_unrefine_points(int64_t p, const int32_t *__restrict__ sliceOff, const 
     if (keep) keep[pt] = kp;
 }
 
+// hexRef2D::getSplitElems (hexRef2D.C:2202-2342) + selectUnrefineElems filter (hexRef2D.C:1860-1906), one
+// thread per edge: split <=> |edgeCells| == 4, not an edge of a boundary face, the 4 cells visible with the
+// same parentIndex >= 0 and level; kept when EITHER end point has max error < unrefineLevel and no marked
+// pointCell (the 2-D quirk).  2-D meshes are small: plain gathers, no staging.
+__global__ void __launch_bounds__(kThreads)
+k_select_unrefine_edges(int64_t nEdges, const int32_t *__restrict__ ecOff, const int32_t *__restrict__ ecCol,
+                        const u8 *__restrict__ ecCount, const u8 *__restrict__ bndEdge, const label *__restrict__ edgePts,
+                        const int32_t *__restrict__ pcOff, const int32_t *__restrict__ pcCol,
+                        const label *__restrict__ parentIdx, const u8 *__restrict__ lvl8, const double *__restrict__ err,
+                        double unrefineLevel, const u8 *__restrict__ marked, u8 *__restrict__ isSplit, u8 *__restrict__ keep) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= nEdges) return;
+    bool split = (ecCount[e] == 4) && !bndEdge[e];
+    bool kp = false;
+    if (split) {
+        const int32_t *row = ecCol + ((size_t)ecOff[e >> 5] << 5) + (e & 31);
+        int32_t q[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) q[k] = row[(size_t)k << 5];
+        const label p0 = parentIdx[q[0]];
+        const int l0 = lvl8[q[0]];
+        bool same = p0 >= 0;
+#pragma unroll
+        for (int k = 1; k < 4; k++) same = same && (parentIdx[q[k]] == p0) && (lvl8[q[k]] == l0);
+        split = same;
+        if (split && keep) {
+            for (int k = 0; k < 2 && !kp; k++) {
+                const label pt = edgePts[2 * e + k];
+                const int32_t base = pcOff[pt >> 5];
+                const int w = pcOff[(pt >> 5) + 1] - base;
+                const int32_t *prow = pcCol + ((size_t)base << 5) + (pt & 31);
+                double m = -kGREAT;
+                unsigned anyMarked = 0;
+                for (int j = 0; j < w; j++) {
+                    const int32_t c = prow[(size_t)j << 5];
+                    if (c < 0) continue;
+                    m = fmaxFoam(m, err[c]);
+                    anyMarked |= marked[c];
+                }
+                if (m < unrefineLevel && !anyMarked) kp = true;
+            }
+        }
+    }
+    if (isSplit) isSplit[e] = split;
+    if (keep) keep[e] = kp;
+}
+
 // ---- sparse passes of consistentUnrefinement --------------------------------------------------
 // Candidate split points / cells marked for unrefinement are a small fraction of the mesh, so these
 // passes scan 16 flags per thread with one 128-bit load and only walk the rows of set entries.

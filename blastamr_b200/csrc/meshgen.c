@@ -60,6 +60,11 @@ typedef struct mg_mesh {
     double *magSf;        /* f+b */
     double *weights;      /* f+b owner-side linear weights (1 on boundary faces) */
     double *deltaCoeffs;  /* f+b nonOrthDeltaCoeffs */
+    /* 2-D (one cell thick) meshes: the edges normal to the plane, mesh.edgeCells() restricted to them */
+    i64 nedge;
+    i32 *edgePts;         /* 2*nedge: mesh.edges()[e] */
+    i32 *ecOff, *ecCells; /* edgeCells CSR */
+    u8 *bndEdge;          /* edge belongs to a boundary face of a non-empty patch */
 } mg_mesh;
 
 static void *xmalloc(size_t s) {
@@ -86,6 +91,7 @@ MG_API void mg_mesh_free(mg_mesh *m) {
     free(m->bndPoint); free(m->cellLevel); free(m->pointLevel); free(m->visible);
     free(m->splitParent); free(m->cellGlobal); free(m->pointGlobal); free(m->faceGlobal);
     free(m->pxyz); free(m->Sf); free(m->magSf); free(m->weights); free(m->deltaCoeffs);
+    free(m->edgePts); free(m->ecOff); free(m->ecCells); free(m->bndEdge);
     free(m);
 }
 
@@ -95,6 +101,8 @@ MG_API void mg_mesh_sizes(const mg_mesh *m, i64 *out) {
     out[4] = m->npatch; out[5] = m->nsplit;
     out[6] = m->pcOff ? m->pcOff[m->p] : 0;
     out[7] = m->cpOff ? m->cpOff[m->n] : 0;
+    out[8] = m->nedge;
+    out[9] = m->ecOff ? m->ecOff[m->nedge] : 0;
 }
 
 /* array access by id (Python wraps the pointers without copying) */
@@ -112,6 +120,7 @@ MG_API void *mg_mesh_array(const mg_mesh *m, int id) {
     case 18: return m->pointGlobal; case 19: return m->faceGlobal;
     case 20: return m->pxyz;
     case 21: return m->Sf; case 22: return m->magSf; case 23: return m->weights; case 24: return m->deltaCoeffs;
+    case 25: return m->edgePts; case 26: return m->ecOff; case 27: return m->ecCells; case 28: return m->bndEdge;
     }
     return NULL;
 }
@@ -120,6 +129,7 @@ MG_API void *mg_mesh_array(const mg_mesh *m, int id) {
 
 typedef struct mg_oct {
     int nx, ny, nz, lcap;
+    int dim2;            /* 1: quadtree in (x,y), cells keep their z extent (hexRef2D-style 1->4 cut) */
     double L[3];
     /* nodes */
     i64 nnode, capnode;
@@ -177,6 +187,9 @@ MG_API void mg_oct_free(mg_oct *o) {
 }
 
 MG_API i64 mg_oct_ncells(const mg_oct *o) { return o->n; }
+MG_API void mg_oct_set_2d(mg_oct *o, int on) { o->dim2 = on; }
+/* z extent of a cell in its own level's units */
+static inline i32 zext(const mg_oct *o, i64 c) { return o->dim2 ? (1 << o->cellLvl[c]) : 1; }
 
 /* descend towards the cell (l; ix,iy,iz); returns node, *depth = level reached */
 static inline i32 oct_locate(const mg_oct *o, int l, i32 ix, i32 iy, i32 iz, int *depth) {
@@ -201,7 +214,7 @@ static inline i32 oct_face_nbr(const mg_oct *o, i64 c, int dir) {
     switch (dir) {
     case 0: ix--; break; case 1: ix++; break;
     case 2: iy--; break; case 3: iy++; break;
-    case 4: iz--; break; default: iz++; break;
+    case 4: iz--; break; default: iz += (o->dim2 ? (1 << l) : 1); break;
     }
     if (ix < 0 || iy < 0 || iz < 0 || ix >= (o->nx << l) || iy >= (o->ny << l) || iz >= (o->nz << l))
         return -1;
@@ -266,7 +279,8 @@ static i32 alloc_block(mg_oct *o) {
 MG_API i64 mg_oct_refine(mg_oct *o, const i32 *cells, i64 ncells, i32 *cellMap) {
     for (i64 k = 0; k < ncells; k++)
         if (o->cellLvl[cells[k]] >= o->lcap) return -1;
-    i64 nold = o->n, nnew = nold + 7 * ncells;
+    const int NCH = o->dim2 ? 4 : 8;
+    i64 nold = o->n, nnew = nold + (NCH - 1) * ncells;
     grow_cells(o, nnew);
     if (cellMap) for (i64 c = 0; c < nold; c++) cellMap[c] = (i32)c;
     for (i64 k = 0; k < ncells; k++) {
@@ -276,12 +290,13 @@ MG_API i64 mg_oct_refine(mg_oct *o, const i32 *cells, i64 ncells, i32 *cellMap) 
         i32 px = o->cx[c], py = o->cy[c], pz = o->cz[c];
         i32 base = alloc_block(o);
         o->nodeChild[node] = base; o->nodeCell[node] = -1;
+        for (int j = 0; j < 8; j++) { o->nodeChild[base + j] = -1; o->nodeCell[base + j] = -1; o->nodeParent[base + j] = node; }
         /* history: storeSplit (hexRefRefinementHistory.C:1673-1708) */
         i32 parentIndex;
         if (o->visible[c] != -1) { parentIndex = o->visible[c]; o->visible[c] = -1; }
         else parentIndex = alloc_split(o, -1);
-        for (int j = 0; j < 8; j++) {
-            i32 id = (j == 0) ? c : (i32)(nold + 7 * k + (j - 1));
+        for (int j = 0; j < NCH; j++) {
+            i32 id = (j == 0) ? c : (i32)(nold + (NCH - 1) * k + (j - 1));
             i32 nd = base + j;
             o->nodeChild[nd] = -1; o->nodeCell[nd] = id; o->nodeParent[nd] = node;
             o->cellNode[id] = nd; o->cellLvl[id] = (u8)(l + 1);
@@ -303,21 +318,22 @@ MG_API i64 mg_oct_refine(mg_oct *o, const i32 *cells, i64 ncells, i32 *cellMap) 
  */
 MG_API i64 mg_oct_unrefine(mg_oct *o, const i32 *cells8, i64 nsp, i32 *cellMap, i32 *reverseMap) {
     i64 nold = o->n;
+    const int NCH = o->dim2 ? 4 : 8;
     i32 *master = (i32 *)xmalloc(nold * 4); /* old label -> old master label, or self */
     u8 *removed = (u8 *)xcalloc(nold, 1);
     for (i64 c = 0; c < nold; c++) master[c] = (i32)c;
     for (i64 s = 0; s < nsp; s++) {
-        const i32 *cs = cells8 + 8 * s;
+        const i32 *cs = cells8 + NCH * s;
         i32 pnode = o->nodeParent[o->cellNode[cs[0]]];
         if (pnode < 0) { free(master); free(removed); return -1; }
         i32 m = cs[0];
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < NCH; j++) {
             if (o->nodeParent[o->cellNode[cs[j]]] != pnode) { free(master); free(removed); return -1; }
             if (cs[j] < m) m = cs[j];
         }
         /* history: combineCells (hexRefRefinementHistory.C:1711-1732) */
         i32 parentIndex = o->splitParent[o->visible[m]];
-        for (int j = 0; j < 8; j++) { free_split(o, o->visible[cs[j]]); o->visible[cs[j]] = -1; }
+        for (int j = 0; j < NCH; j++) { free_split(o, o->visible[cs[j]]); o->visible[cs[j]] = -1; }
         o->visible[m] = parentIndex;
         int l = o->cellLvl[m];
         i32 base = o->nodeChild[pnode];
@@ -326,7 +342,7 @@ MG_API i64 mg_oct_unrefine(mg_oct *o, const i32 *cells8, i64 nsp, i32 *cellMap, 
         i32 nx_ = o->cx[cs[0]] >> 1, ny_ = o->cy[cs[0]] >> 1, nz_ = o->cz[cs[0]] >> 1;
         o->cellNode[m] = pnode; o->cellLvl[m] = (u8)(l - 1);
         o->cx[m] = nx_; o->cy[m] = ny_; o->cz[m] = nz_;
-        for (int j = 0; j < 8; j++) if (cs[j] != m) { removed[cs[j]] = 1; master[cs[j]] = m; }
+        for (int j = 0; j < NCH; j++) if (cs[j] != m) { removed[cs[j]] = 1; master[cs[j]] = m; }
         if (o->nfree == o->capfree) {
             o->capfree = o->capfree ? o->capfree * 2 : 1024;
             o->freeBlocks = (i32 *)xrealloc(o->freeBlocks, o->capfree * 4);
@@ -398,9 +414,9 @@ static void side_collect_rec(const mg_oct *o, i32 node, int side, i32 **out, i64
         return;
     }
     int axis = side >> 1, hi = side & 1;
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < (o->dim2 ? 4 : 8); j++) {
         int bit = (j >> axis) & 1;
-        if (bit != hi) continue;
+        if (!(o->dim2 && axis == 2) && bit != hi) continue;
         side_collect_rec(o, o->nodeChild[node] + j, side, out, cnt, cap);
     }
 }
@@ -522,8 +538,8 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
         double s = 1.0 / (double)(1 << l);
         m->cc[3 * c + 0] = (o->cx[c] + 0.5) * s * h0x;
         m->cc[3 * c + 1] = (o->cy[c] + 0.5) * s * h0y;
-        m->cc[3 * c + 2] = (o->cz[c] + 0.5) * s * h0z;
-        m->vol[c] = (h0x * s) * (h0y * s) * (h0z * s);
+        m->cc[3 * c + 2] = (o->cz[c] + 0.5 * zext(o, c)) * s * h0z;
+        m->vol[c] = (h0x * s) * (h0y * s) * (h0z * s * zext(o, c));
         m->cellLevel[c] = l; m->visible[c] = o->visible[c];
     }
     m->nsplit = o->nsplit;
@@ -542,7 +558,7 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
             int lc = o->cellLvl[c];
             double sc = 1.0 / (double)(1 << lc);
             double lo_c[3] = {o->cx[c] * sc * h0x, o->cy[c] * sc * h0y, o->cz[c] * sc * h0z};
-            double hi_c[3] = {(o->cx[c] + 1) * sc * h0x, (o->cy[c] + 1) * sc * h0y, (o->cz[c] + 1) * sc * h0z};
+            double hi_c[3] = {(o->cx[c] + 1) * sc * h0x, (o->cy[c] + 1) * sc * h0y, (o->cz[c] + zext(o, c)) * sc * h0z};
             double Cc[3] = {m->cc[3 * c], m->cc[3 * c + 1], m->cc[3 * c + 2]};
             double Cf[3], S[3] = {0, 0, 0}, Cn[3];
             if (i < f) {
@@ -555,13 +571,13 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
                 double area = 1.0;
                 for (int a = 0; a < 3; a++) {
                     /* integer comparison in fine units decides the contact axis */
-                    i64 loC = (i64)ccv[a] << (o->lcap - lc), hiC = (i64)(ccv[a] + 1) << (o->lcap - lc);
-                    i64 loQ = (i64)cq[a] << (o->lcap - lq), hiQ = (i64)(cq[a] + 1) << (o->lcap - lq);
+                    i64 loC = (i64)ccv[a] << (o->lcap - lc), hiC = (i64)(ccv[a] + (a == 2 ? zext(o, c) : 1)) << (o->lcap - lc);
+                    i64 loQ = (i64)cq[a] << (o->lcap - lq), hiQ = (i64)(cq[a] + (a == 2 ? zext(o, q) : 1)) << (o->lcap - lq);
                     if (hiC == loQ) { axis = a; sign = 1; }
                     else if (hiQ == loC) { axis = a; sign = -1; }
                 }
                 for (int a = 0; a < 3; a++) {
-                    double loQ = cq[a] * sq * h0[a], hiQ = (cq[a] + 1) * sq * h0[a];
+                    double loQ = cq[a] * sq * h0[a], hiQ = (cq[a] + (a == 2 ? zext(o, q) : 1)) * sq * h0[a];
                     if (a == axis) { Cf[a] = sign > 0 ? hi_c[a] : lo_c[a]; continue; }
                     double lo = lo_c[a] > loQ ? lo_c[a] : loQ, hi = hi_c[a] < hiQ ? hi_c[a] : hiQ;
                     area *= (hi - lo); Cf[a] = 0.5 * (lo + hi);
@@ -609,7 +625,7 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
         if (l == 0) continue;
         int s = FS >> l;
         for (int j = 0; j < 8; j++) {
-            i32 X = (o->cx[c] + (j & 1)) * s, Y = (o->cy[c] + ((j >> 1) & 1)) * s, Z = (o->cz[c] + ((j >> 2) & 1)) * s;
+            i32 X = (o->cx[c] + (j & 1)) * s, Y = (o->cy[c] + ((j >> 1) & 1)) * s, Z = (o->cz[c] + ((j >> 2) & 1) * zext(o, c)) * s;
             if (((X | Y | Z) & (FS - 1)) == 0) continue;
             uint64_t k = pkey(X, Y, Z);
             if (ph_get(&H, k) < 0) {
@@ -629,7 +645,7 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
         m->pxyz[3 * q + 2] = (i32)(q / (npx * npy)) * FS;
     }
     if (p > plat) memcpy(m->pxyz + 3 * plat, extra, (p - plat) * 3 * 4);
-    free(extra); ph_free(&H);
+    free(extra);
 
     /* --- pointCells: every leaf whose closed cube contains the point (8 octants) */
     i32 *tmp = (i32 *)xmalloc(p * 8 * 4);
@@ -647,7 +663,7 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
         for (int j = 0; j < 8; j++) {
             i32 fx = X - ((j & 1) ? 0 : 1), fy = Y - (((j >> 1) & 1) ? 0 : 1), fz = Z - (((j >> 2) & 1) ? 0 : 1);
             if (fx < 0 || fy < 0 || fz < 0 || fx >= MX || fy >= MY || fz >= MZ) continue;
-            int d; i32 node = oct_locate(o, lcap, fx, fy, fz, &d);
+            int d; i32 node = oct_locate(o, lcap, fx, fy, o->dim2 ? (fz & ~(FS - 1)) : fz, &d);
             i32 c = o->nodeCell[node];
             int dup = 0; for (int t = 0; t < k; t++) if (row[t] == c) { dup = 1; break; }
             if (!dup) row[k++] = c;
@@ -672,6 +688,44 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
         free(fill);
     }
     m->cpOff = cpo; m->cpPts = cpp;
+    /* --- 2-D: edges normal to the plane (one per point column and layer), edgeCells = cells around it */
+    if (o->dim2) {
+        i64 ne = 0;
+        for (i64 q = 0; q < p; q++) if (m->pxyz[3 * q + 2] < MZ) ne++;
+        m->nedge = ne;
+        m->edgePts = (i32 *)xmalloc((ne ? ne : 1) * 2 * 4);
+        m->bndEdge = (u8 *)xmalloc(ne ? ne : 1);
+        m->ecOff = (i32 *)xcalloc(ne + 1, 4);
+        i64 e = 0;
+        for (i64 q = 0; q < p; q++) {
+            i32 X = m->pxyz[3 * q], Y = m->pxyz[3 * q + 1], Z = m->pxyz[3 * q + 2];
+            if (Z >= MZ) continue;
+            i32 Z2 = Z + FS, partner;
+            if (((X | Y) & (FS - 1)) == 0) partner = (i32)((X / FS) + npx * ((Y / FS) + npy * (i64)(Z2 / FS)));
+            else partner = ph_get(&H, pkey(X, Y, Z2));
+            m->edgePts[2 * e] = (i32)q; m->edgePts[2 * e + 1] = partner;
+            m->bndEdge[e] = (X == 0 || Y == 0 || X == MX || Y == MY);
+            /* cells around the edge = pointCells(q) ^ pointCells(partner) (sorted rows) */
+            i32 a = pcnt[q], ae = pcnt[q + 1], c2 = pcnt[partner], ce = pcnt[partner + 1], k = 0;
+            while (a < ae && c2 < ce) {
+                i32 pa = m->pcCells[a], pc = m->pcCells[c2];
+                if (pa == pc) { k++; a++; c2++; } else if (pa < pc) a++; else c2++;
+            }
+            m->ecOff[e + 1] = k;
+            e++;
+        }
+        for (i64 i = 0; i < ne; i++) m->ecOff[i + 1] += m->ecOff[i];
+        m->ecCells = (i32 *)xmalloc((m->ecOff[ne] ? m->ecOff[ne] : 1) * 4);
+        for (i64 i = 0; i < ne; i++) {
+            i32 q = m->edgePts[2 * i], partner = m->edgePts[2 * i + 1];
+            i32 a = pcnt[q], ae = pcnt[q + 1], c2 = pcnt[partner], ce = pcnt[partner + 1], k = m->ecOff[i];
+            while (a < ae && c2 < ce) {
+                i32 pa = m->pcCells[a], pc = m->pcCells[c2];
+                if (pa == pc) { m->ecCells[k++] = pa; a++; c2++; } else if (pa < pc) a++; else c2++;
+            }
+        }
+    }
+    ph_free(&H);
     free(nb);
     return m;
 }

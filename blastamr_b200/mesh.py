@@ -32,6 +32,7 @@ def lib():
         L.mg_oct_create.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                                      C.c_int, C.c_void_p, C.c_void_p]
         L.mg_oct_free.argtypes = [C.c_void_p]
+        L.mg_oct_set_2d.argtypes = [C.c_void_p, C.c_int]
         L.mg_oct_ncells.restype = C.c_int64
         L.mg_oct_ncells.argtypes = [C.c_void_p]
         L.mg_oct_refine.restype = C.c_int64
@@ -92,6 +93,11 @@ class PolyMesh:
     magSf: Optional[np.ndarray] = None
     weights: Optional[np.ndarray] = None       # owner-side linear weights [f+b]
     delta_coeffs: Optional[np.ndarray] = None  # nonOrthDeltaCoeffs [f+b]
+    n_edges: int = 0                           # 2-D meshes: edges normal to the plane
+    edge_pts: Optional[np.ndarray] = None      # int32 [n_edges,2]
+    ec_off: Optional[np.ndarray] = None        # edgeCells CSR
+    ec_cells: Optional[np.ndarray] = None
+    bnd_edge: Optional[np.ndarray] = None      # uint8 [n_edges]
     _handle: Optional[int] = field(default=None, repr=False)
 
     # patch arrays in the layout the C-ABI takes
@@ -116,9 +122,9 @@ class PolyMesh:
 
 def _wrap(handle: int, names: Sequence[str], copy: bool = False) -> PolyMesh:
     L = lib()
-    sz = np.zeros(8, dtype=np.int64)
+    sz = np.zeros(10, dtype=np.int64)
     L.mg_mesh_sizes(handle, sz.ctypes.data)
-    n, f, b, p, npatch, nsplit, nnz_pc, nnz_cp = (int(x) for x in sz)
+    n, f, b, p, npatch, nsplit, nnz_pc, nnz_cp, nedge, nnz_ec = (int(x) for x in sz)
 
     def arr(idx, dtype, count, shape=None):
         ptr = L.mg_mesh_array(handle, idx)
@@ -149,6 +155,9 @@ def _wrap(handle: int, names: Sequence[str], copy: bool = False) -> PolyMesh:
         pxyz=arr(20, np.int32, 3 * p, (p, 3)),
         Sf=arr(21, np.float64, 3 * (f + b), (f + b, 3)), magSf=arr(22, np.float64, f + b),
         weights=arr(23, np.float64, f + b), delta_coeffs=arr(24, np.float64, f + b),
+        n_edges=nedge, edge_pts=arr(25, np.int32, 2 * nedge, (nedge, 2)) if nedge else None,
+        ec_off=arr(26, np.int32, nedge + 1) if nedge else None, ec_cells=arr(27, np.int32, nnz_ec) if nedge else None,
+        bnd_edge=arr(28, np.uint8, nedge) if nedge else None,
     )
     if m.split_parent is None:
         m.split_parent = np.zeros(0, np.int32)
@@ -169,7 +178,7 @@ class Octree:
     """A single hex block that can be cut 1->8 and merged 8->1 (the host 'topology engine')."""
 
     def __init__(self, nx, ny, nz, lengths=(1.0, 1.0, 1.0), max_level=3, sides=None, patch_types=None,
-                 patch_nbr=None):
+                 patch_nbr=None, two_d=False):
         sides = sides or CAVITY_SIDES
         names: List[str] = []
         for _, nm in sides:
@@ -186,6 +195,9 @@ class Octree:
         self.max_level = max_level
         self._h = lib().mg_oct_create(nx, ny, nz, *self.lengths, max_level, len(sid), sid.ctypes.data,
                                       spa.ctypes.data, len(names), pty.ctypes.data, pnb.ctypes.data)
+        self.two_d = bool(two_d)
+        if two_d:
+            lib().mg_oct_set_2d(self._h, 1)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -203,29 +215,32 @@ class Octree:
     def refine(self, cells: np.ndarray) -> np.ndarray:
         """Cut the listed cells (ascending); returns cellMap (new -> old label)."""
         cells = np.ascontiguousarray(cells, dtype=np.int32)
-        n_new = self.ncells + 7 * len(cells)
+        n_new = self.ncells + (3 if self.two_d else 7) * len(cells)
         cell_map = np.empty(n_new, dtype=np.int32)
         r = lib().mg_oct_refine(self._h, cells.ctypes.data, len(cells), cell_map.ctypes.data)
         if r < 0:
             raise ValueError("refinement beyond the level cap")
         return cell_map
 
-    def unrefine(self, mesh: PolyMesh, split_points: np.ndarray):
-        """Merge the 8 cells around each split point of `mesh` (the mesh last built).
+    def unrefine(self, mesh: PolyMesh, split_elems: np.ndarray):
+        """Merge the cells around each split element of `mesh` (the mesh last built): split points
+        (3-D, 8 cells) or split edges (2-D, 4 cells).
         Returns (cellMap new->old, reverseCellMap old->new | -(master)-2)."""
-        split_points = np.ascontiguousarray(split_points, dtype=np.int32)
+        split_elems = np.ascontiguousarray(split_elems, dtype=np.int32)
         n_old = self.ncells
-        rows = np.empty((len(split_points), 8), dtype=np.int32)
-        for i, pt in enumerate(split_points):
-            s, e = mesh.pc_off[pt], mesh.pc_off[pt + 1]
-            if e - s != 8:
-                raise ValueError(f"point {pt} is not a split point (|pointCells|={e - s})")
-            rows[i] = mesh.pc_cells[s:e]
-        cell_map = np.empty(n_old - 7 * len(split_points), dtype=np.int32)
+        k = 4 if self.two_d else 8
+        off, idx = (mesh.ec_off, mesh.ec_cells) if self.two_d else (mesh.pc_off, mesh.pc_cells)
+        rows = np.empty((len(split_elems), k), dtype=np.int32)
+        for i, el in enumerate(split_elems):
+            s, e = off[el], off[el + 1]
+            if e - s != k:
+                raise ValueError(f"element {el} is not a split element (|cells|={e - s})")
+            rows[i] = idx[s:e]
+        cell_map = np.empty(n_old - (k - 1) * len(split_elems), dtype=np.int32)
         rev = np.empty(n_old, dtype=np.int32)
-        r = lib().mg_oct_unrefine(self._h, rows.ctypes.data, len(split_points), cell_map.ctypes.data, rev.ctypes.data)
+        r = lib().mg_oct_unrefine(self._h, rows.ctypes.data, len(split_elems), cell_map.ctypes.data, rev.ctypes.data)
         if r < 0:
-            raise ValueError("inconsistent split points")
+            raise ValueError("inconsistent split elements")
         return cell_map, rev
 
 

@@ -72,7 +72,7 @@ enum { AMR_PATCH_PLAIN = 0, AMR_PATCH_EMPTY = 1, AMR_PATCH_PROCESSOR = 2 };
 /* refiner kinds == `refiner` keyword (fvMeshRefinerNew.C:74-103) x hexRef::New dimension switch */
 enum {
     AMR_REFINER_HEX3D = 0,   /* hexRefiner + hexRef3D */
-    AMR_REFINER_HEX2D = 1,   /* hexRefiner + hexRef2D (split elements are edges)   -- next */
+    AMR_REFINER_HEX2D = 1,   /* hexRefiner + hexRef2D (split elements are edges; needs amr_mesh_set_edges) */
     AMR_REFINER_POLY3D = 2,  /* polyRefiner + polyhedralRefinement                 -- next */
     AMR_REFINER_POLY2D = 3   /* polyRefiner + prismatic2DRefinement                -- next */
 };
@@ -115,6 +115,12 @@ int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t p,
    boundary face" (what the loop hexRef3D.C:2279-2294 computes from mesh.faces()). */
 int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_t *pcCells,
                         const uint8_t *bndPoint);
+
+/* 2-D cutter (hexRef2D): split elements are mesh EDGES.  mesh.edges() end points [2*nEdges],
+   mesh.edgeCells() as CSR, and the flag "edge belongs to a boundary face" (the loop over
+   mesh_.faceEdges() at hexRef2D.C:2296-2311).  Only needed with AMR_REFINER_HEX2D. */
+int amr_mesh_set_edges(amr_ctx *ctx, int64_t nEdges, const int32_t *edgePoints, const int32_t *ecOff,
+                       const int32_t *ecCells, const uint8_t *bndEdge);
 
 /* hexRef::cellLevel_/pointLevel_ and the refinement history arrays visibleCells_ and
    splitCells_[i].parent_ (hexRefRefinementHistory.H:299-310).  pointLevel, visibleCells,

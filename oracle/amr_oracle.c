@@ -73,6 +73,11 @@ typedef struct {
     const label *cellLevel, *pointLevel;
     const label *visible;           /* history_.visibleCells() */
     const label *splitParent;       /* history_.splitCells()[i].parent_ */
+    /* mesh.edges() / edgeCells() (hexRef2D: split elements are edges) */
+    int64_t nedge;
+    const label *edgePts, *ecOff, *ecCells;
+    const boolean *bndEdge;       /* edge used by a boundary face (mesh_.faceEdges()[bface]) */
+    label *ceOff, *ceEdges;       /* derived: cellEdges() restricted to the listed edges */
     /* fvMesh geometry (Lohner only) */
     const scalar *weights, *Sf, *magSf, *deltaCoeffs, *V;
     /* derived: primitiveMesh::cells() */
@@ -93,7 +98,7 @@ OR_API or_world *or_world_create(int R) {
 
 OR_API void or_world_free(or_world *w) {
     if (!w) return;
-    for (int r = 0; r < w->R; r++) { free(w->m[r].cfOff); free(w->m[r].cfFaces); }
+    for (int r = 0; r < w->R; r++) { free(w->m[r].cfOff); free(w->m[r].cfFaces); free(w->m[r].ceOff); free(w->m[r].ceEdges); }
     free(w->m); free(w);
 }
 
@@ -136,6 +141,22 @@ OR_API void or_world_set_levels(or_world *w, int r, const label *cellLevel, cons
                                 const label *visible, const label *splitParent) {
     or_mesh *m = &w->m[r];
     m->cellLevel = cellLevel; m->pointLevel = pointLevel; m->visible = visible; m->splitParent = splitParent;
+}
+
+OR_API void or_world_set_edges(or_world *w, int r, int64_t nedge, const label *edgePts, const label *ecOff,
+                               const label *ecCells, const boolean *bndEdge) {
+    or_mesh *m = &w->m[r];
+    m->nedge = nedge; m->edgePts = edgePts; m->ecOff = ecOff; m->ecCells = ecCells; m->bndEdge = bndEdge;
+    free(m->ceOff); free(m->ceEdges);
+    m->ceOff = (label *)calloc((size_t)(m->n + 1), sizeof(label));
+    for (int64_t i = 0; i < ecOff[nedge]; i++) m->ceOff[ecCells[i] + 1]++;
+    for (int64_t c = 0; c < m->n; c++) m->ceOff[c + 1] += m->ceOff[c];
+    m->ceEdges = (label *)malloc(sizeof(label) * (size_t)(ecOff[nedge] + 1));
+    label *fill = (label *)malloc(sizeof(label) * (size_t)(m->n + 1));
+    memcpy(fill, m->ceOff, sizeof(label) * (size_t)(m->n + 1));
+    for (int64_t e = 0; e < nedge; e++)
+        for (label i = ecOff[e]; i < ecOff[e + 1]; i++) m->ceEdges[fill[ecCells[i]]++] = (label)e;
+    free(fill);
 }
 
 OR_API void or_world_set_geometry(or_world *w, int r, const scalar *weights, const scalar *Sf, const scalar *magSf,
@@ -813,7 +834,19 @@ OR_API void or_get_split_points(const or_world *w, int r, boolean *isSplit) {
 
 /* hexRef3D::consistentUnrefinement, hexRef3D.C:1719-1953 (maxSet = false).  Returns sweeps,
    or -1 on the reference's "problem" FatalError (hexRef3D.C:1811-1815). */
+/* kind 0: elements are points (hexRef3D.C:1719-1953); kind 1: elements are edges (hexRef2D.C:1929-2164,
+   same body with mesh_.edgeCells() in place of mesh_.pointCells()) */
+static int consistent_unrefinement_elems(const or_world *w, int kind, boolean **unrefinePoint);
 OR_API int or_consistent_unrefinement(const or_world *w, boolean **unrefinePoint) {
+    return consistent_unrefinement_elems(w, 0, unrefinePoint);
+}
+OR_API int or_consistent_unrefinement_edges(const or_world *w, boolean **unrefineEdge) {
+    return consistent_unrefinement_elems(w, 1, unrefineEdge);
+}
+#define EL_N(m) (kind ? (m)->nedge : (m)->p)
+#define EL_OFF(m) (kind ? (m)->ecOff : (m)->pcOff)
+#define EL_CELLS(m) (kind ? (m)->ecCells : (m)->pcCells)
+static int consistent_unrefinement_elems(const or_world *w, int kind, boolean **unrefinePoint) {
     int R = w->R;
     int sweeps = 0;
     boolean **unrefineCell = (boolean **)malloc(sizeof(boolean *) * R);
@@ -830,9 +863,9 @@ OR_API int or_consistent_unrefinement(const or_world *w, boolean **unrefinePoint
             const or_mesh *m = &w->m[r];
             boolean *uc = unrefineCell[r];
             memset(uc, 0, (size_t)m->n);
-            for (int64_t pointi = 0; pointi < m->p; pointi++)
+            for (int64_t pointi = 0; pointi < EL_N(m); pointi++)
                 if (unrefinePoint[r][pointi])
-                    for (label j = m->pcOff[pointi]; j < m->pcOff[pointi + 1]; j++) uc[m->pcCells[j]] = 1;
+                    for (label j = EL_OFF(m)[pointi]; j < EL_OFF(m)[pointi + 1]; j++) uc[EL_CELLS(m)[j]] = 1;
             for (int64_t facei = 0; facei < m->f; facei++) {
                 label own = m->owner[facei];
                 label ownLevel = m->cellLevel[own] - uc[own];
@@ -870,10 +903,10 @@ OR_API int or_consistent_unrefinement(const or_world *w, boolean **unrefinePoint
         if (nChanged == 0) break;
         for (int r = 0; r < R; r++) {
             const or_mesh *m = &w->m[r];
-            for (int64_t pointi = 0; pointi < m->p; pointi++)
+            for (int64_t pointi = 0; pointi < EL_N(m); pointi++)
                 if (unrefinePoint[r][pointi])
-                    for (label j = m->pcOff[pointi]; j < m->pcOff[pointi + 1]; j++)
-                        if (!unrefineCell[r][m->pcCells[j]]) { unrefinePoint[r][pointi] = 0; break; }
+                    for (label j = EL_OFF(m)[pointi]; j < EL_OFF(m)[pointi + 1]; j++)
+                        if (!unrefineCell[r][EL_CELLS(m)[j]]) { unrefinePoint[r][pointi] = 0; break; }
         }
     }
     for (int r = 0; r < R; r++) { free(unrefineCell[r]); free(neiLevel[r]); }
@@ -928,6 +961,86 @@ OR_API int or_hex_select_unrefine(const or_world *w, const scalar *const *error,
         free(pFld); free(isSplit);
     }
     return or_consistent_unrefinement(w, unrefPoint);
+}
+
+/* hexRef2D::getSplitElems, hexRef2D.C:2202-2342 -> flags over edges */
+OR_API void or_get_split_edges(const or_world *w, int r, boolean *isSplit) {
+    const or_mesh *m = &w->m[r];
+    label *splitMaster = (label *)malloc(sizeof(label) * (size_t)(m->nedge + 1));
+    label *splitMasterLevel = (label *)calloc((size_t)(m->nedge + 1), sizeof(label));
+    for (int64_t edgei = 0; edgei < m->nedge; edgei++) {
+        splitMaster[edgei] = -1;
+        if (m->ecOff[edgei + 1] - m->ecOff[edgei] != 4) splitMaster[edgei] = -2;
+    }
+    for (int64_t celli = 0; celli < m->n; celli++) {
+        label vis = m->visible[celli];
+        label parentIndex = (vis != -1) ? m->splitParent[vis] : -1;
+        if (vis != -1 && parentIndex >= 0) {
+            for (label i = m->ceOff[celli]; i < m->ceOff[celli + 1]; i++) {
+                label edgei = m->ceEdges[i];
+                label masterCelli = splitMaster[edgei];
+                if (masterCelli == -1) {
+                    splitMaster[edgei] = parentIndex;
+                    splitMasterLevel[edgei] = m->cellLevel[celli] - 1;
+                } else if (masterCelli == -2) {
+                } else if ((masterCelli != parentIndex) || (splitMasterLevel[edgei] != m->cellLevel[celli] - 1)) {
+                    splitMaster[edgei] = -2;
+                }
+            }
+        } else {
+            for (label i = m->ceOff[celli]; i < m->ceOff[celli + 1]; i++) splitMaster[m->ceEdges[i]] = -2;
+        }
+    }
+    /* "Unmark boundary faces": every edge of every boundary face (hexRef2D.C:2296-2311) */
+    for (int64_t edgei = 0; edgei < m->nedge; edgei++) if (m->bndEdge[edgei]) splitMaster[edgei] = -2;
+    for (int64_t edgei = 0; edgei < m->nedge; edgei++) isSplit[edgei] = splitMaster[edgei] >= 0;
+    free(splitMaster); free(splitMasterLevel);
+}
+
+/*
+ * Unrefinement branch of fvMeshHexRefiner::refine (fvMeshHexRefiner.C:1591-1633) with the 2-D cutter:
+ * hexRef2D::selectUnrefineElems, hexRef2D.C:1860-1927 -- a split edge is kept when EITHER of its end
+ * points has pFld < unrefineLevel and no marked pointCell (the 3-D code tests the single split point).
+ */
+OR_API int or_hex2d_select_unrefine(const or_world *w, const scalar *const *error, scalar unrefineLevel,
+                                    int nUnrefinementBufferLayers, const boolean *const *protectedCell,
+                                    const label *protectedPatchIds, int nProtectedPatches,
+                                    boolean **refineCell, boolean **unrefEdge, boolean **splitEdge) {
+    int R = w->R;
+    for (int i = 0; i < nUnrefinementBufferLayers; i++) extend_across_faces(w, refineCell);
+    for (int r = 0; r < R; r++) {
+        const or_mesh *m = &w->m[r];
+        if (protectedCell && protectedCell[r])
+            for (int64_t c = 0; c < m->n; c++) if (protectedCell[r][c]) refineCell[r][c] = 1;
+        for (int k = 0; k < nProtectedPatches; k++) {
+            int q = protectedPatchIds[k];
+            for (label i = 0; i < m->patchSize[q]; i++) refineCell[r][m->owner[m->patchStart[q] + i]] = 1;
+        }
+    }
+    for (int r = 0; r < R; r++) {
+        const or_mesh *m = &w->m[r];
+        scalar *pFld = (scalar *)malloc(sizeof(scalar) * (size_t)(m->p + 1));
+        boolean *isSplit = (boolean *)malloc((size_t)(m->nedge + 1));
+        or_max_cell_field(w, r, error[r], pFld);
+        or_get_split_edges(w, r, isSplit);
+        for (int64_t edgej = 0; edgej < m->nedge; edgej++) {
+            unrefEdge[r][edgej] = 0;
+            if (!isSplit[edgej]) continue;
+            for (int k = 0; k < 2; k++) {
+                label pointi = m->edgePts[2 * edgej + k];
+                int hasMarked = 1;
+                if (pFld[pointi] < unrefineLevel) {
+                    hasMarked = 0;
+                    for (label j = m->pcOff[pointi]; j < m->pcOff[pointi + 1]; j++)
+                        if (refineCell[r][m->pcCells[j]]) { hasMarked = 1; break; }
+                }
+                if (!hasMarked) { unrefEdge[r][edgej] = 1; break; }
+            }
+        }
+        if (splitEdge && splitEdge[r]) memcpy(splitEdge[r], isSplit, (size_t)m->nedge);
+        free(pFld); free(isSplit);
+    }
+    return or_consistent_unrefinement_edges(w, unrefEdge);
 }
 
 /* hexRef::checkRefinementLevels (2:1 part), hexRef.C:2934-3025.  Returns #violating faces. */

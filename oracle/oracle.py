@@ -45,6 +45,11 @@ def lib():
         L.or_world_set_points.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.or_world_set_levels.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.or_normalize.argtypes = [C.c_int64, C.c_void_p] + [C.c_double] * 4
+        L.or_world_set_edges.argtypes = [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 4
+        L.or_get_split_edges.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.or_hex2d_select_unrefine.restype = C.c_int
+        L.or_hex2d_select_unrefine.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.or_world_set_geometry.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.or_estimate_lohner.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.or_range_thresholds.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
@@ -107,6 +112,10 @@ class World:
                      np.ascontiguousarray(m.bnd_point, dtype=np.uint8)]
                 self._keep += a
                 L.or_world_set_points(self._h, r, *[x.ctypes.data for x in a])
+            if getattr(m, "n_edges", 0):
+                a = [_i32(m.edge_pts), _i32(m.ec_off), _i32(m.ec_cells), np.ascontiguousarray(m.bnd_edge, dtype=np.uint8)]
+                self._keep += a
+                L.or_world_set_edges(self._h, r, m.n_edges, *[v.ctypes.data for v in a])
             if getattr(m, "Sf", None) is not None and m.vol is not None:
                 a = [np.ascontiguousarray(v, dtype=np.float64) for v in (m.weights, m.Sf, m.magSf, m.delta_coeffs, m.vol)]
                 self._keep += a
@@ -192,6 +201,24 @@ class World:
         if sweeps < 0:
             raise RuntimeError("reference FatalError 'problem' (hexRef3D.C:1811)")
         return up, sp, sweeps
+
+    def hex2d_select_unrefine(self, err, refine_cell, n_layers, unrefine_level=-SQRT_SMALL, protected_cell=None,
+                              protected_patch_ids=()):
+        """2-D cutter (hexRef2D): split elements are edges"""
+        ue = [np.zeros(m.n_edges, dtype=np.uint8) for m in self.meshes]
+        se = [np.zeros(m.n_edges, dtype=np.uint8) for m in self.meshes]
+        pc = protected_cell if protected_cell is not None else [None] * self.R
+        ids = _i32(protected_patch_ids)
+        sweeps = lib().or_hex2d_select_unrefine(self._h, _pp(err), unrefine_level, n_layers, _pp(pc), ids.ctypes.data, len(ids),
+                                                _pp(refine_cell), _pp(ue), _pp(se))
+        if sweeps < 0:
+            raise RuntimeError("reference FatalError 'problem' (hexRef2D.C)")
+        return ue, se, sweeps
+
+    def split_edges(self, r):
+        out = np.zeros(self.meshes[r].n_edges, dtype=np.uint8)
+        lib().or_get_split_edges(self._h, r, out.ctypes.data)
+        return out
 
     def max_cell_field(self, r, v):
         out = np.empty(self.meshes[r].p, dtype=np.float64)

@@ -101,11 +101,14 @@ class OracleBackend:
     def check_levels(self, lv=None):
         return self.w.check_levels([self.m.cell_level if lv is None else lv])
 
-    def split_elems(self):
+    def split_elems(self, kind=0):
+        if kind == 1:
+            return np.flatnonzero(self.w.split_edges(0)).astype(np.int32)
         return np.flatnonzero(self.w.split_points(0)).astype(np.int32)
 
-    def select_unrefine(self, err, n_layers, refine_cell=None, protected_patch_ids=(), **_):
-        up, sp, sw = self.w.hex_select_unrefine([err], [refine_cell], n_layers, protected_cell=None if self.prot is None else [self.prot],
+    def select_unrefine(self, err, n_layers, refine_cell=None, protected_patch_ids=(), kind=0, **_):
+        fn = self.w.hex2d_select_unrefine if kind == 1 else self.w.hex_select_unrefine
+        up, sp, sw = fn([err], [refine_cell], n_layers, protected_cell=None if self.prot is None else [self.prot],
                                                 protected_patch_ids=protected_patch_ids)
         return np.flatnonzero(up[0]).astype(np.int32), sw
 

@@ -73,7 +73,10 @@ def test_select_refine_box(ctx, O, layers, maxlev):
 
 
 def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, protected=(), thr=0.01, kind="delta"):
-    """A multi-step AMR run; every stage is executed by the oracle and by the GPU and compared."""
+    """A multi-step AMR run; every stage is executed by the oracle and by the GPU and compared.
+    Works for the 3-D cutter (split points) and the 2-D cutter (split edges, oc.two_d)."""
+    two_d = getattr(oc, "two_d", False)
+    rk = 1 if two_d else 0       # AMR_REFINER_HEX2D / AMR_REFINER_HEX3D
     stats = dict(refined=0, unrefined=0, sweeps=[])
     for step in range(steps):
         m = oc.build()
@@ -104,6 +107,7 @@ def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, prot
         fld = np.stack([x, 2 * x, -x], axis=1).copy()
         if len(cells):
             cell_map = oc.refine(cells)
+            assert len(cell_map) == m.n + (3 if two_d else 7) * len(cells)
             rev = np.arange(m.n, dtype=np.int32)   # every old cell survives under its own label
             new_rc = O.remap_refine_cell(cell_map, rev, refine_cell)
             g_rc = np.zeros(len(cell_map), np.uint8)
@@ -125,10 +129,13 @@ def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, prot
             stats["refined"] += len(cells)
         # unrefinement on the (possibly new) mesh
         rc_ref = refine_cell.copy()
-        up, sp, _ = w.hex_select_unrefine([err], [rc_ref], layers_unref, protected_patch_ids=pid)
-        assert np.array_equal(flags_to_list(sp[0]), ctx.split_elems())
+        if two_d:
+            up, sp, _ = w.hex2d_select_unrefine([err], [rc_ref], layers_unref, protected_patch_ids=pid)
+        else:
+            up, sp, _ = w.hex_select_unrefine([err], [rc_ref], layers_unref, protected_patch_ids=pid)
+        assert np.array_equal(flags_to_list(sp[0]), ctx.split_elems(kind=rk))
         rc_gpu = refine_cell.copy()
-        pts, _ = ctx.select_unrefine(err, layers_unref, refine_cell=rc_gpu, protected_patch_ids=pid)
+        pts, _ = ctx.select_unrefine(err, layers_unref, refine_cell=rc_gpu, protected_patch_ids=pid, kind=rk)
         assert np.array_equal(rc_ref, rc_gpu), f"step {step}: refineCell after unrefine layers differs"
         ref_pts = flags_to_list(up[0])
         assert np.array_equal(ref_pts, pts), f"step {step}: split points differ"
@@ -138,8 +145,9 @@ def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, prot
             n_old = m.n
             cell_map, rev = oc.unrefine(m, pts)
             unref_old = np.zeros(n_old, np.uint8)
+            eoff, ecells = (m.ec_off, m.ec_cells) if two_d else (m.pc_off, m.pc_cells)
             for pt in pts:
-                unref_old[m.pc_cells[m.pc_off[pt]:m.pc_off[pt + 1]]] = 1
+                unref_old[ecells[eoff[pt]:eoff[pt + 1]]] = 1
             f_old = np.stack([x, 2 * x, -x], axis=1).copy() if n_old == len(x) else np.random.default_rng(1).random((n_old, 3))
             assert np.array_equal(O.map_field(cell_map, f_old, 3), ctx.map_field(cell_map, f_old, ncomp=3))
             c_ref = O.map_field_conservative(cell_map, rev, vol, f_old, 3)
@@ -164,6 +172,27 @@ def moving_front(speed):
 def test_amr_loop_moving_front(ctx, O, n0, maxlev, layers):
     oc = M.Octree(n0, n0, n0, (1.0, 1.0, 1.0), maxlev)
     st = amr_loop(ctx, O, oc, moving_front(0.06), steps=6, maxlev=maxlev, layers_ref=layers[0], layers_unref=layers[1])
+    assert st["refined"] > 0 and st["unrefined"] > 0
+
+
+CAVITY2D = [("ymax", "movingWall"), ("xmin", "fixedWalls"), ("xmax", "fixedWalls"), ("ymin", "fixedWalls"),
+            ("zmin", "frontAndBack"), ("zmax", "frontAndBack")]
+
+
+def moving_front_2d(speed):
+    def fn(cc, step):
+        d = np.sqrt((cc[:, 0] - (0.35 + speed * step)) ** 2 + (cc[:, 1] - 0.5) ** 2)
+        return 1.0 + 0.5 * (1.0 + np.tanh((d - 0.22) / 0.03))
+    return fn
+
+
+@pytest.mark.parametrize("n0,maxlev,layers", [(20, 2, (1, 1)), (24, 3, (3, 6))])
+def test_amr_loop_2d_hexRef2D(ctx, O, n0, maxlev, layers):
+    """2-D cutter: one cell thick, `empty` front/back (the layout of the reference's hex2D fixture and of
+    tutorials/damBreak2D with `refiner hexRefiner`); split elements are edges"""
+    oc = M.Octree(n0, n0, 1, (1.0, 1.0, 0.05), maxlev, CAVITY2D, {"frontAndBack": M.PATCH_EMPTY}, two_d=True)
+    st = amr_loop(ctx, O, oc, moving_front_2d(0.06), steps=6, maxlev=maxlev, layers_ref=layers[0], layers_unref=layers[1],
+                  kind="codedDelta")
     assert st["refined"] > 0 and st["unrefined"] > 0
 
 
