@@ -9,9 +9,13 @@ hexRefiner.  One "step" = the per-timestep decision path of adaptiveFvMesh::refi
   E   errorEstimator::update (delta + normalize)
   M   selectRefineCandidates + buffer layer + protections + selectRefineCells
   B   hexRef::consistentRefinement sweeps + ascending list
-  F   fvMesh::mapFields through cellMap (identity + 7 children per refined parent): 1 scalar + 1 vector
-  U   unrefinement branch: buffer layer, maxCellField, getSplitElems, filter, consistentUnrefinement
-Topology change itself is host bookkeeping and outside the timed region (BASELINE.json north_star).
+  F   fvMesh::mapFields through the real cellMap of the cut (hexRef3D numbering: child 0 keeps the label,
+      7 children appended per refined parent): 1 scalar + 1 vector field, plus the error field and the
+      refineCell marking (fvMeshHexRefiner.C:1562-1586), which the unrefinement branch needs on the new mesh
+  U   unrefinement branch ON THE REFINED MESH M1 (what the reference does in the same update()):
+      buffer layer, maxCellField, getSplitElems, filter, consistentUnrefinement
+The topology change itself (M0 -> M1, done once by the host octree engine from the selected cells) is
+host bookkeeping and outside the timed region (BASELINE.json north_star); both meshes stay resident.
 
 `value`   = cells before the step (all ranks) / max-over-ranks CUDA-event time, inputs resident in HBM.
 `e2e`     = same metric through the C-ABI with HOST (pinned) buffers: the field and the mapped fields
@@ -47,7 +51,7 @@ def front_field(cc, n_side):
     return 1.0 + 0.5 * (1.0 + np.tanh((d - 0.3) / (2.0 / n_side)))
 
 
-def algorithmic_bytes(n, f, p, nnz_pc, n_new, sweeps_ref, sweeps_unref):
+def algorithmic_bytes(n, f, p, nnz_pc, n_new, sweeps_ref, sweeps_unref, m1=None):
     """each input array read once and each output written once per logical pass of
     the reference algorithm; label 4 B, scalar 8 B, flag 1 B."""
     E = 8 * f + 16 * n
@@ -55,7 +59,11 @@ def algorithmic_bytes(n, f, p, nnz_pc, n_new, sweeps_ref, sweeps_unref):
     M2 = LAYERS_REF * (8 * f + 2 * n + 8 * n)
     M4 = 10 * n
     B1 = sweeps_ref * (8 * f + 6 * n)
-    F1 = 4 * (4 * n_new + 8 * n + 8 * n_new)
+    F1 = 4 * (4 * n_new + 8 * n + 8 * n_new)          # 1 scalar + 1 vector field
+    F1 += (4 * n_new + 8 * n + 8 * n_new)              # the error field (a registered volScalarField)
+    F1 += (4 * n_new + 4 * n + n + n_new)              # refineCell through cellMap/reverseCellMap
+    if m1 is not None:                                 # unrefinement branch runs on the refined mesh
+        n, f, p, nnz_pc = m1
     csr = 4 * (p + 1) + 4 * nnz_pc
     U0 = LAYERS_UNREF * (8 * f + 2 * n)
     U1 = csr + 8 * n + 8 * p
@@ -139,42 +147,72 @@ def measured_peak():
 
 # ------------------------------------------------------------------------------- CPU arms
 
-def oracle_step(O, w, xs, n_new_maps):
-    """The same step on the CPU oracle (all ranks of the world)."""
-    e = w.estimate("delta", xs)
+def oracle_step(O, S):
+    """The same step on the CPU oracle (all ranks of the world): E, M+B on M0; F through the cellMap;
+    U on the refined mesh M1."""
+    w, w1 = S["w"], S["w1"]
+    e = w.estimate("delta", S["xs"])
     w.normalize_world(e, THR, GREAT, THR, GREAT)
     rc, rs, sw = w.hex_select_refine(e, MAX_LEVEL, LAYERS_REF)
-    cms = [m[0] for m in n_new_maps]
-    w.map_field_world(cms, [m[1] for m in n_new_maps], [m[3] for m in n_new_maps], 1)
-    w.map_field_world(cms, [m[2] for m in n_new_maps], [m[4] for m in n_new_maps], 3)
-    up, sp, sw2 = w.hex_select_unrefine(e, rc, LAYERS_UNREF)
+    cms = S["cms"]
+    w.map_field_world(cms, S["xs"], S["new1"], 1)
+    w.map_field_world(cms, S["f3"], S["new3"], 3)
+    w.map_field_world(cms, e, S["err1"], 1)
+    rc1 = [O.remap_refine_cell(cm, rv, r) for cm, rv, r in zip(cms, S["revs"], rc)]
+    up, sp, sw2 = w1.hex_select_unrefine(S["err1"], rc1, LAYERS_UNREF)
     return rs, up, sw, sw2
 
 
 def cpu_sample(n_side, ranks, threads):
-    """Oracle on a bounded sample of the workload: an n_side^3 box split in `ranks` slabs."""
+    """Oracle on a bounded sample of the workload: an n_side^3 box split in `ranks` slabs (and its
+    refined successor M1 split the same way)."""
     from blastamr_b200 import mesh as M
     from oracle import oracle as O
-    g = M.box_mesh(n_side, n_side, n_side)
+    oc = M.Octree(n_side, n_side, n_side, (1.0, 1.0, 1.0), 1)
+    g = oc.build()
     x = front_field(g.cc, n_side)
-    if ranks > 1:
-        cell_rank = M.simple_ranks(g, (1, 1, 1), (1, 1, ranks))
-        loc = M.decompose(g, cell_rank, ranks)
-        xs = [np.ascontiguousarray(x[l.cell_global]) for l in loc]
-    else:
-        loc, xs = [g], [x]
+
+    def split(mesh):
+        if ranks > 1:
+            cr = M.simple_ranks(mesh, (1, 1, 1), (1, 1, ranks))
+            return M.decompose(mesh, cr, ranks)
+        return [mesh]
+
+    loc = split(g)
+    xs = [np.ascontiguousarray(x[l.cell_global]) if ranks > 1 else x for l in loc]
     w = O.World(loc)
     O.set_threads(threads)
-    # cellMap from a first (untimed) pass
     e = w.estimate("delta", xs)
-    w.normalize(e, THR, GREAT, THR, GREAT)
+    w.normalize_world(e, THR, GREAT, THR, GREAT)
     rc, rs, _ = w.hex_select_refine(e, MAX_LEVEL, LAYERS_REF)
-    maps = []
-    for l, s, xx in zip(loc, rs, xs):
-        cells = np.flatnonzero(s).astype(np.int32)
-        cm = np.concatenate([np.arange(l.n, dtype=np.int32), np.repeat(cells, 7)])
-        maps.append((cm, xx, np.stack([xx, xx, xx], axis=1).copy(), np.empty(len(cm)), np.empty((len(cm), 3))))
-    return O, w, xs, maps, g.n
+    # global list of cells to refine -> the host topology engine -> M1 and the global cellMap
+    if ranks > 1:
+        cells = np.sort(np.concatenate([l.cell_global[np.flatnonzero(s_)] for l, s_ in zip(loc, rs)])).astype(np.int32)
+    else:
+        cells = np.flatnonzero(rs[0]).astype(np.int32)
+    cm_g = oc.refine(cells)
+    g1 = oc.build()
+    loc1 = split(g1)
+    w1 = O.World(loc1)
+    cms, revs = [], []
+    for l0, l1 in zip(loc, loc1):
+        if ranks > 1:
+            old_local = np.full(g.n, -1, np.int32)
+            old_local[l0.cell_global] = np.arange(l0.n, dtype=np.int32)
+            cm = old_local[cm_g[l1.cell_global]]
+            assert (cm >= 0).all()
+            new_local = np.full(g1.n, -1, np.int32)
+            new_local[l1.cell_global] = np.arange(l1.n, dtype=np.int32)
+            rv = new_local[l0.cell_global]          # old cell keeps its global label in M1
+        else:
+            cm, rv = cm_g, np.arange(g.n, dtype=np.int32)
+        cms.append(np.ascontiguousarray(cm, dtype=np.int32))
+        revs.append(np.ascontiguousarray(rv, dtype=np.int32))
+    S = dict(w=w, w1=w1, xs=xs, cms=cms, revs=revs,
+             f3=[np.stack([a, 2 * a, -a], axis=1).copy() for a in xs],
+             new1=[np.empty(len(c)) for c in cms], new3=[np.empty((len(c), 3)) for c in cms],
+             err1=[np.empty(len(c)) for c in cms], keep=(g, g1, loc, loc1, oc))
+    return O, S, g.n
 
 
 def run_reference(args):
@@ -186,12 +224,12 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     ranks = max(1, min(cores, 64))
     n_side = args.cpu_cells
-    O, w, xs, maps, ncells = cpu_sample(n_side, ranks, ranks)
+    O, S, ncells = cpu_sample(n_side, ranks, ranks)
     for _ in range(args.warmup):
-        oracle_step(O, w, xs, maps)
+        oracle_step(O, S)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_step(O, w, xs, maps)
+        oracle_step(O, S)
     dt = (time.perf_counter() - t0) / args.steps
     val = ncells / dt / 1e6
     out = {
@@ -248,9 +286,10 @@ def main():
     t_setup = time.time()
     if world > 1:
         sides, ptypes, pnbr, _ = M.subdomain_sides(rank, procs)
-        mesh = M.box_mesh(N, N, N, sides=sides, patch_types=ptypes, patch_nbr=pnbr)
+        octree = M.Octree(N, N, N, (1.0, 1.0, 1.0), 1, sides, ptypes, pnbr)
     else:
-        mesh = M.box_mesh(N, N, N)
+        octree = M.Octree(N, N, N, (1.0, 1.0, 1.0), 1)
+    mesh = octree.build()
     n, f, b, p = mesh.n, mesh.f, mesh.b, mesh.p
     nnz_pc = int(mesh.pc_off[p])
     x_host = front_field(mesh.cc, N)
@@ -266,24 +305,43 @@ def main():
     x = torch.from_numpy(x_host).to(dev)
     fld3 = torch.stack([x, 2 * x, -x], dim=1).contiguous()
     cells_dev = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    pts_dev = torch.empty(max(p, 1), dtype=torch.int32, device=dev)
     thr = (THR, GREAT, THR, GREAT)
 
-    # first pass: build the synthetic cellMap (identity + 7 children per refined parent)
+    # first pass (untimed): select, then let the host topology engine cut M0 -> M1 and hand back the
+    # real cellMap; M1 goes to a second context so that both meshes are resident
     ctx.estimate("delta", x, thresholds=thr, keep_resident=True)
-    n_ref, _ = ctx.select_refine(None, MAX_LEVEL, LAYERS_REF, cells_out=cells_dev)
-    cell_map = torch.cat([torch.arange(n, dtype=torch.int32, device=dev),
-                          cells_dev[:n_ref].repeat_interleave(7)]).contiguous()
+    cells_h = np.empty(max(n, 1), dtype=np.int32)
+    cells_first, _ = ctx.select_refine(None, MAX_LEVEL, LAYERS_REF, cells_out=cells_h)
+    n_ref = len(cells_first)
+    cell_map_h = octree.refine(cells_first.copy())
+    mesh1 = octree.build()
+    n1, f1, b1, p1 = mesh1.n, mesh1.f, mesh1.b, mesh1.p
+    nnz_pc1 = int(mesh1.pc_off[p1])
+    ctx1 = capi.Context(local_rank)
+    ctx1.set_stream(torch.cuda.current_stream().cuda_stream)
+    if world > 1:
+        uid1 = [capi.Context.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid1, src=0)
+        ctx1.comm_init(world, rank, uid1[0])
+    ctx1.set_mesh(mesh1)
+    cell_map = torch.from_numpy(cell_map_h).to(dev)
+    rev_map = torch.arange(n, dtype=torch.int32, device=dev)      # every old cell survives under its own label
     n_new = int(cell_map.numel())
+    assert n_new == n1
     new1 = torch.empty(n_new, dtype=torch.float64, device=dev)
     new3 = torch.empty((n_new, 3), dtype=torch.float64, device=dev)
+    err0 = torch.empty(n, dtype=torch.float64, device=dev)
+    err1 = torch.empty(n_new, dtype=torch.float64, device=dev)
+    rc0 = torch.empty(n, dtype=torch.uint8, device=dev)
+    pts_dev = torch.empty(max(p1, 1), dtype=torch.int32, device=dev)
+    del mesh1
     torch.cuda.synchronize()
     setup_s = time.time() - t_setup
 
     # one event interval per C-ABI call; F is two calls (scalar field, vector field)
     call_names = ["E:estimate(delta+normalize)", "M+B:select_refine", "F:map_field(scalar)", "F:map_field(vector)",
-                  "U:select_unrefine"]
-    stage_of = [0, 1, 2, 2, 3]
+                  "F:map_field(error)+remap_refine_cell", "U:select_unrefine(on M1)"]
+    stage_of = [0, 1, 2, 2, 2, 3]
     stage_names = ["E", "M+B", "F", "U"]
     NEV = len(call_names) + 1
     info = {}
@@ -293,16 +351,19 @@ def main():
             if evs is not None:
                 evs[i].record()
         mark(0)
-        ctx.estimate("delta", x, thresholds=thr, keep_resident=True)
+        ctx.estimate("delta", x, thresholds=thr, out=err0)
         mark(1)
-        nr, sw = ctx.select_refine(None, MAX_LEVEL, LAYERS_REF, cells_out=cells_dev)
+        nr, sw = ctx.select_refine(None, MAX_LEVEL, LAYERS_REF, cells_out=cells_dev, refine_cell_out=rc0)
         mark(2)
         ctx.map_field(cell_map, x, n_old=n, n_new=n_new, ncomp=1, out=new1)
         mark(3)
         ctx.map_field(cell_map, fld3, n_old=n, n_new=n_new, ncomp=3, out=new3)
         mark(4)
-        npts, sw2 = ctx.select_unrefine(None, LAYERS_UNREF, elems_out=pts_dev)
+        ctx.map_field(cell_map, err0, n_old=n, n_new=n_new, ncomp=1, out=err1)
+        ctx1.remap_refine_cell(cell_map, rev_map, refine_cell=rc0)
         mark(5)
+        npts, sw2 = ctx1.select_unrefine(err1, LAYERS_UNREF, elems_out=pts_dev)
+        mark(6)
         info.update(n_refine=nr, sweeps_refine=sw, n_unrefine=npts, sweeps_unrefine=sw2)
 
     def barrier():
@@ -315,7 +376,7 @@ def main():
     barrier()
     sampler = ClockSampler(physical_device_index(local_rank))
     sampler.start()
-    l0 = ctx.launches
+    l0 = ctx.launches + ctx1.launches
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(NEV)] for _ in range(args.steps)]
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
@@ -326,7 +387,7 @@ def main():
     t_end.record()
     barrier()
     clocks = sampler.stop()
-    launches = ctx.launches - l0
+    launches = ctx.launches + ctx1.launches - l0
     total_ms = t_start.elapsed_time(t_end)
     call_ms = [float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)])) for i in range(NEV - 1)]
     ms_per_step = total_ms / args.steps
@@ -337,17 +398,26 @@ def main():
         xh = torch.from_numpy(x_host).pin_memory()
         f3h = torch.stack([xh, 2 * xh, -xh], dim=1).contiguous().pin_memory()
         cmh = cell_map.cpu().pin_memory()
+        rvh = rev_map.cpu().pin_memory()
         n1h = torch.empty(n_new, dtype=torch.float64).pin_memory()
         n3h = torch.empty((n_new, 3), dtype=torch.float64).pin_memory()
-        cells_h = np.empty(max(n, 1), dtype=np.int32)
-        pts_h = np.empty(max(p, 1), dtype=np.int32)
+        e0h = torch.empty(n, dtype=torch.float64).pin_memory()
+        e1h = torch.empty(n_new, dtype=torch.float64).pin_memory()
+        rc0h = torch.empty(n, dtype=torch.uint8).pin_memory()
+        rc1h = torch.empty(n_new, dtype=torch.uint8).pin_memory()
+        cells_h2 = np.empty(max(n, 1), dtype=np.int32)
+        pts_h = np.empty(max(p1, 1), dtype=np.int32)
 
         def step_host():
-            ctx.estimate("delta", xh.numpy(), thresholds=thr, keep_resident=True)
-            cl, _ = ctx.select_refine(None, MAX_LEVEL, LAYERS_REF, cells_out=cells_h)
+            # every array the reference keeps on the host crosses PCIe: field in, error out, marking out,
+            # fields in / mapped fields out, error + marking in again for the new mesh, lists out
+            ctx.estimate("delta", xh.numpy(), thresholds=thr, out=e0h.numpy())
+            cl, _ = ctx.select_refine(e0h.numpy(), MAX_LEVEL, LAYERS_REF, cells_out=cells_h2, refine_cell_out=rc0h.numpy())
             ctx.map_field(cmh.numpy(), xh.numpy(), n_old=n, n_new=n_new, ncomp=1, out=n1h.numpy())
             ctx.map_field(cmh.numpy(), f3h.numpy(), n_old=n, n_new=n_new, ncomp=3, out=n3h.numpy())
-            pl, _ = ctx.select_unrefine(None, LAYERS_UNREF, elems_out=pts_h)
+            ctx.map_field(cmh.numpy(), e0h.numpy(), n_old=n, n_new=n_new, ncomp=1, out=e1h.numpy())
+            ctx1.remap_refine_cell(cmh.numpy(), rvh.numpy(), refine_cell=rc0h.numpy(), out=rc1h.numpy())
+            pl, _ = ctx1.select_unrefine(e1h.numpy(), LAYERS_UNREF, refine_cell=rc1h.numpy(), elems_out=pts_h)
             return len(cl), len(pl)
 
         step_host()
@@ -360,8 +430,8 @@ def main():
         z.record()
         barrier()
         e2e_ms = a.elapsed_time(z) / args.e2e_steps
-        h2d = 8 * n + 2 * 4 * n_new + 8 * n + 24 * n     # x, cellMap (twice), scalar field, vector field
-        d2h = 4 * ncl + 8 * n_new + 24 * n_new + 4 * npl
+        h2d = (8 * n) + (8 * n) + 3 * (4 * n_new) + (8 * n + 24 * n + 8 * n) + (4 * n_new + 4 * n + n) + (8 * n_new + n_new)
+        d2h = (8 * n) + (n + 4 * ncl) + (8 * n_new + 24 * n_new + 8 * n_new) + n_new + (n_new + 4 * npl)
         e2e = (e2e_ms, h2d, d2h)
 
     # ---- max over ranks
@@ -380,7 +450,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        ab = algorithmic_bytes(n, f, p, nnz_pc, n_new, info["sweeps_refine"], info["sweeps_unrefine"])
+        ab = algorithmic_bytes(n, f, p, nnz_pc, n_new, info["sweeps_refine"], info["sweeps_unrefine"], (n1, f1, p1, nnz_pc1))
         stage_ms = [sum(ms for ms, st in zip(call_ms, stage_of) if st == i) for i in range(4)]
         stage_bytes = [ab["E"], ab["M"] + ab["B"], ab["F"], ab["U"]]
         stages = {nm: {"ms": ms, "GBps": (by / 1e9) / (ms / 1e3) if ms > 0 else None}
@@ -413,6 +483,7 @@ def main():
                                    f"buffer layers {LAYERS_REF}/{LAYERS_UNREF}, hexRefiner; 1 scalar + 1 vector field mapped",
                        "decomposition": f"simple {procs}", "l2_policy": "inputs larger than L2 (>= 0.5 GB per array)",
                        "cells_per_gpu": n, "n_refine": info["n_refine"], "n_new": n_new,
+                       "refined_mesh": {"cells": n1, "internal_faces": f1, "points": p1},
                        "sweeps_refine": info["sweeps_refine"], "sweeps_unrefine": info["sweeps_unrefine"],
                        "n_unrefine": info["n_unrefine"], "setup_s": setup_s},
             "stages": stages, "calls_ms": calls, "roofline": roof, "gpu_launches": int(launches), "clocks": clocks,
@@ -422,12 +493,12 @@ def main():
                           "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2])}
         if not args.no_cpu and world == 1:
             ncpu = args.cpu_cells
-            O, w, xs, maps, nc = cpu_sample(ncpu, 1, 1)
-            oracle_step(O, w, xs, maps)
+            O, S, nc = cpu_sample(ncpu, 1, 1)
+            oracle_step(O, S)
             t0 = time.perf_counter()
             reps = 2
             for _ in range(reps):
-                oracle_step(O, w, xs, maps)
+                oracle_step(O, S)
             dt = (time.perf_counter() - t0) / reps
             out["cpu_baseline"] = {"value": nc / dt / 1e6, "unit": "Mcells/s", "cores": 1, "kind": "port",
                                    "sample": f"{ncpu}^3-cell box ({nc} cells), same field/thresholds, {reps} steps, 1 thread"}
@@ -435,6 +506,7 @@ def main():
     if world > 1:
         dist.barrier()
         ctx.close()
+        ctx1.close()
         dist.destroy_process_group()
 
 

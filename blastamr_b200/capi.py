@@ -49,7 +49,7 @@ _SIGS = {
                                     C.c_void_p]),
     "amr_consistent_refinement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),
-    "amr_remap_refine_cell": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_remap_refine_cell": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_select_unrefine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_get_split_elems": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -253,7 +253,8 @@ class Context:
 
     def remap_refine_cell(self, cell_map, reverse_map, refine_cell=None, out=None):
         n_new = len(cell_map) if isinstance(cell_map, np.ndarray) else cell_map.numel()
-        self._ck(self.L.amr_remap_refine_cell(self._h, n_new, _ptr(cell_map), _ptr(reverse_map), _ptr(refine_cell),
+        n_old = len(reverse_map) if isinstance(reverse_map, np.ndarray) else reverse_map.numel()
+        self._ck(self.L.amr_remap_refine_cell(self._h, n_old, n_new, _ptr(cell_map), _ptr(reverse_map), _ptr(refine_cell),
                                               _ptr(out)))
         return out
 

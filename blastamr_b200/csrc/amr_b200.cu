@@ -868,14 +868,14 @@ AMR_API int amr_consistent_refinement(amr_ctx *ctx, const int32_t *cellsIn, int6
     return flushOuts(ctx);
 }
 
-AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nNew, const int32_t *cellMap, const int32_t *reverseCellMap,
-                                  const uint8_t *refineCell, uint8_t *newRefineCellOut) {
+AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap,
+                                  const int32_t *reverseCellMap, const uint8_t *refineCell, uint8_t *newRefineCellOut) {
     ENTER();
-    if (!cellMap || !reverseCellMap) FAIL(AMR_ERR_ARG, "amr_remap_refine_cell: null map");
+    if (!cellMap || !reverseCellMap || nOld < 0 || nNew < 0) FAIL(AMR_ERR_ARG, "amr_remap_refine_cell: bad arguments");
+    if (!refineCell && nOld != ctx->refineCellN) FAIL(AMR_ERR_STATE, "amr_remap_refine_cell: resident marking has a different size than nOld");
     // Called after amr_mesh_set of the NEW mesh or before it: the old marking is either passed in
     // or the resident one (which amr_mesh_set preserves in `pendingFlags`) -- to stay simple the
     // call must come BEFORE amr_mesh_set of the new mesh when the resident marking is used.
-    const int64_t nOld = ctx->refineCellN;
     const int32_t *dMap = nullptr, *dRev = nullptr;
     const u8 *dOld = nullptr;
     TRY(stageIn(ctx, cellMap, nNew, &dMap));

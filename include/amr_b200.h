@@ -206,9 +206,11 @@ int amr_consistent_refinement(amr_ctx *ctx, const int32_t *cellsIn, int64_t nIn,
                               int32_t *cellsOut, int64_t *nOut, int *sweepsOut);
 
 /* Update of refineCell through the topology change (fvMeshHexRefiner.C:1562-1586).
-   refineCell NULL = the resident marking; result replaces the resident marking and is copied
-   to newRefineCellOut when not NULL. */
-int amr_remap_refine_cell(amr_ctx *ctx, int64_t nNew, const int32_t *cellMap,
+   cellMap [nNew], reverseCellMap [nOld], refineCell [nOld] or NULL = the resident marking of this
+   context (then nOld must equal its size); the result (size nNew) replaces the resident marking
+   (it survives the following amr_mesh_set of the new mesh) and is copied to newRefineCellOut
+   when not NULL. */
+int amr_remap_refine_cell(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap,
                           const int32_t *reverseCellMap, const uint8_t *refineCell,
                           uint8_t *newRefineCellOut);
 
