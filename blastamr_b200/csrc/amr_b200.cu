@@ -412,10 +412,12 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
     if (scale && !thr) FAIL(AMR_ERR_ARG, "amr_estimate: scale requested without thresholds");
     const int64_t n = ctx->n, b = ctx->b;
     const double *dx = nullptr;
-    double *dErr = nullptr;
     TRY(stageIn(ctx, x, n, &dx));
-    TRY(stageOut(ctx, errorOut, n, &dErr));
-    double *target = ctx->error;   // the resident copy is always written; errorOut mirrors it
+    // a device errorOut is written in place (no second copy); a host errorOut is read back from the
+    // resident field, which is what later stages use when they are passed error == NULL
+    const bool devOut = errorOut && isDevicePtr(errorOut);
+    double *target = devOut ? errorOut : ctx->error;
+    ctx->errorResident = !devOut;
     Thresholds t = mkThr(thr);
     if (n > 0) {
         if (kind == AMR_EST_FIELD_VALUE) {
@@ -453,7 +455,7 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
         } else {
             FAIL(AMR_ERR_ARG, "amr_estimate: estimator kind not available on the device path");
         }
-        if (dErr) CK(cudaMemcpyAsync(dErr, target, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (errorOut && !devOut) CK(cudaMemcpyAsync(errorOut, target, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaGetLastError());
     return flushOuts(ctx);
@@ -468,10 +470,11 @@ AMR_API int amr_estimate_lohner(amr_ctx *ctx, const double *x, const double *xBo
     if (scale && !thr) FAIL(AMR_ERR_ARG, "amr_estimate_lohner: scale requested without thresholds");
     const int64_t n = ctx->n, f = ctx->f, b = ctx->b;
     const double *dx = nullptr, *dxb = nullptr, *dxn = nullptr;
-    double *dErr = nullptr;
     TRY(stageIn(ctx, x, n, &dx));
     TRY(stageIn(ctx, xBoundary, b, &dxb));
-    TRY(stageOut(ctx, errorOut, n, &dErr));
+    const bool devOut = errorOut && isDevicePtr(errorOut);
+    double *target = devOut ? errorOut : ctx->error;
+    ctx->errorResident = !devOut;
     if (ctx->nCoupled > 0) {
         if (nbrValues) TRY(stageIn(ctx, nbrValues, b, &dxn));
         else {
@@ -487,10 +490,10 @@ AMR_API int amr_estimate_lohner(amr_ctx *ctx, const double *x, const double *xBo
         LAUNCH(k_gauss_grad, gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
                (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, ctx->grad);
         if (scale) LAUNCH((k_lohner<true>), gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
-                          (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, ctx->error);
+                          (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, target);
         else LAUNCH((k_lohner<false>), gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
-                    (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, ctx->error);
-        if (dErr) CK(cudaMemcpyAsync(dErr, ctx->error, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+                    (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, target);
+        if (errorOut && !devOut) CK(cudaMemcpyAsync(errorOut, target, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaGetLastError());
     return flushOuts(ctx);
@@ -760,7 +763,10 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
     const double *dErr = nullptr;
     const int32_t *dMax = nullptr;
     TRY(stageIn(ctx, error, n, &dErr));
-    if (!dErr) dErr = ctx->error;
+    if (!dErr) {
+        if (!ctx->errorResident) FAIL(AMR_ERR_STATE, "amr_select_refine: error == NULL but the last estimate wrote to a caller-owned device buffer");
+        dErr = ctx->error;
+    }
     TRY(stageIn(ctx, maxCellLevel, n, &dMax));
     u8 *dRcOut = nullptr;
     TRY(stageOut(ctx, refineCellOut, n, &dRcOut));
@@ -883,14 +889,27 @@ AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nOld, int64_t nNew, cons
     TRY(stageIn(ctx, refineCell, nOld, &dOld));
     if (!dOld) dOld = ctx->refineCell;
     if (!dOld) FAIL(AMR_ERR_STATE, "amr_remap_refine_cell: no marking");
-    u8 *dNew = nullptr;
-    const int64_t capNew = std::max<int64_t>(nNew + 16, ctx->flagCap);
-    CK(cudaMalloc((void **)&dNew, (size_t)capNew));
-    if (nNew) LAUNCH(k_remap_refine_cell, gridFor(nNew), kThreads, nNew, dMap, dRev, dOld, dNew);
-    if (newRefineCellOut && nNew) CK(cudaMemcpyAsync(newRefineCellOut, dNew, (size_t)nNew, cudaMemcpyDefault, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->refineCell) cudaFree(ctx->refineCell);
-    ctx->refineCell = dNew; ctx->refineCellN = nNew;
+    if (nNew + 16 <= ctx->flagCap) {
+        // the context already holds the new mesh (or one at least as large): remap into a pool buffer
+        // and make it the resident marking by pointer swap
+        u8 *dNew = ctx->flagA;
+        if (nNew) LAUNCH(k_remap_refine_cell, gridFor(nNew), kThreads, nNew, dMap, dRev, dOld, dNew);
+        if (newRefineCellOut && nNew) CK(cudaMemcpyAsync(newRefineCellOut, dNew, (size_t)nNew, cudaMemcpyDefault, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::swap(ctx->flagA, ctx->refineCell);
+        ctx->refineCellN = nNew;
+    } else {
+        u8 *dNew = nullptr;
+        const int64_t capNew = std::max<int64_t>(nNew + 16, ctx->flagCap);
+        CK(cudaMalloc((void **)&dNew, (size_t)capNew));
+        if (nNew) LAUNCH(k_remap_refine_cell, gridFor(nNew), kThreads, nNew, dMap, dRev, dOld, dNew);
+        if (newRefineCellOut && nNew) CK(cudaMemcpyAsync(newRefineCellOut, dNew, (size_t)nNew, cudaMemcpyDefault, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        // the larger buffer leaves the pool convention; amr_mesh_set of the new mesh adopts its content
+        if (ctx->refineCell) cudaFree(ctx->refineCell);
+        ctx->refineCell = dNew; ctx->refineCellN = nNew;
+        ctx->refineCellOversize = true;
+    }
     CK(cudaGetLastError());
     return AMR_OK;
 }

@@ -91,6 +91,8 @@ struct amr_ctx {
     double *error = nullptr;   // [n]
     u8 *refineCell = nullptr;  // [n] marking kept between the refine and unrefine stages
     int64_t refineCellN = 0;
+    bool refineCellOversize = false;   // marking held in a private (non-pool) buffer until the next amr_mesh_set
+    bool errorResident = false;        // ctx->error holds the last estimate
     int64_t flagCap = 0;        // capacity (bytes) of flagA/B/C and refineCell: they are swapped by pointer
     int64_t nTotalCells = -1;   // mesh_.globalData().nTotalCells(), reduced once per mesh
 
