@@ -353,7 +353,7 @@ def main():
         mark(0)
         ctx.estimate("delta", x, thresholds=thr, out=err0)
         mark(1)
-        nr, sw = ctx.select_refine(None, MAX_LEVEL, LAYERS_REF, cells_out=cells_dev, refine_cell_out=rc0)
+        nr, sw = ctx.select_refine(err0, MAX_LEVEL, LAYERS_REF, cells_out=cells_dev, refine_cell_out=rc0)
         mark(2)
         ctx.map_field(cell_map, x, n_old=n, n_new=n_new, ncomp=1, out=new1)
         mark(3)
