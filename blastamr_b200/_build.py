@@ -100,9 +100,9 @@ def build_host(force: bool = False) -> Path:
         return LIB_HOST
     if not force and _newer(LIB_HOST, src + hdr + [LIB_CUDA]):
         return LIB_HOST
-    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", str(ROOT / "include"),
-          "-o", str(LIB_HOST)] + [str(s) for s in src] +
-         ["-L", str(LIB_CUDA.parent), "-l:libamr_b200.so", f"-Wl,-rpath,{LIB_CUDA.parent}"])
+    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-I", str(ROOT / "include"),
+          "-I", str(ROOT / "blastamr_b200" / "host"), "-o", str(LIB_HOST)] + [str(s) for s in src] +
+         ["-L", str(LIB_CUDA.parent), "-l:libamr_b200.so", "-Wl,-rpath,$ORIGIN"])
     return LIB_HOST
 
 

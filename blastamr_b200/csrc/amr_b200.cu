@@ -893,7 +893,7 @@ AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nOld, int64_t nNew, cons
         // the context already holds the new mesh (or one at least as large): remap into a pool buffer
         // and make it the resident marking by pointer swap
         u8 *dNew = ctx->flagA;
-        if (nNew) LAUNCH(k_remap_refine_cell, gridFor(nNew), kThreads, nNew, dMap, dRev, dOld, dNew);
+        if (nNew) LAUNCH(k_remap_refine_cell, gridFor(nNew, kThreads * 4), kThreads, nNew, dMap, dRev, dOld, dNew);
         if (newRefineCellOut && nNew) CK(cudaMemcpyAsync(newRefineCellOut, dNew, (size_t)nNew, cudaMemcpyDefault, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         std::swap(ctx->flagA, ctx->refineCell);
@@ -902,7 +902,7 @@ AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nOld, int64_t nNew, cons
         u8 *dNew = nullptr;
         const int64_t capNew = std::max<int64_t>(nNew + 16, ctx->flagCap);
         CK(cudaMalloc((void **)&dNew, (size_t)capNew));
-        if (nNew) LAUNCH(k_remap_refine_cell, gridFor(nNew), kThreads, nNew, dMap, dRev, dOld, dNew);
+        if (nNew) LAUNCH(k_remap_refine_cell, gridFor(nNew, kThreads * 4), kThreads, nNew, dMap, dRev, dOld, dNew);
         if (newRefineCellOut && nNew) CK(cudaMemcpyAsync(newRefineCellOut, dNew, (size_t)nNew, cudaMemcpyDefault, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         // the larger buffer leaves the pool convention; amr_mesh_set of the new mesh adopts its content

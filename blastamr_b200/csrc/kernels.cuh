@@ -657,18 +657,30 @@ k_knock_points(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *_
 // STAGE 4  field mapping and level update
 // ------------------------------------------------------------------------------------------
 
-// refineCell through the map, fvMeshHexRefiner.C:1562-1586
+// refineCell through the map, fvMeshHexRefiner.C:1562-1586.  4 cells per thread (strided by the CTA),
+// the three dependent loads (cellMap -> reverseCellMap -> old flag) batched across the 4 chains.
 __global__ void __launch_bounds__(kThreads)
 k_remap_refine_cell(int64_t nNew, const label *__restrict__ cellMap, const label *__restrict__ reverseCellMap,
                     const u8 *__restrict__ oldFlag, u8 *__restrict__ newFlag) {
-    int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (c >= nNew) return;
-    label o = cellMap[c];
-    u8 v;
-    if (o < 0) v = 1;
-    else if (reverseCellMap[o] != c) v = 1;
-    else v = oldFlag[o];
-    newFlag[c] = v;
+    const int64_t c0 = (int64_t)blockIdx.x * (kThreads * 4) + threadIdx.x;
+    label o[4], r[4];
+    u8 v[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) { const int64_t c = c0 + (int64_t)t * kThreads; o[t] = (c < nNew) ? cellMap[c] : -1; }
+#pragma unroll
+    for (int t = 0; t < 4; t++) r[t] = (o[t] >= 0) ? reverseCellMap[o[t]] : -1;
+#pragma unroll
+    for (int t = 0; t < 4; t++) v[t] = (o[t] >= 0) ? oldFlag[o[t]] : (u8)1;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int64_t c = c0 + (int64_t)t * kThreads;
+        if (c >= nNew) continue;
+        u8 out;
+        if (o[t] < 0) out = 1;
+        else if ((int64_t)r[t] != c) out = 1;
+        else out = v[t];
+        newFlag[c] = out;
+    }
 }
 
 // fvMesh::mapFields direct addressing: new[i][k] = old[cellMap[i]][k].  One thread handles 4 scalars

@@ -155,18 +155,12 @@ kp_select_unrefine_points(SellView S, const u8 *__restrict__ pcCount, const u8 *
 #pragma unroll
             for (int k = 0; k < 8; k++) q[k] = row[k << 5];
             label par[8];
+            int l[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) par[k] = parentIdx[q[k]];
+            for (int k = 0; k < 8; k++) { par[k] = parentIdx[q[k]]; l[k] = lvl8[q[k]]; }   // 16 gathers in flight
             bool same = par[0] >= 0;
 #pragma unroll
-            for (int k = 1; k < 8; k++) same = same && (par[k] == par[0]);
-            if (same) {
-                int l[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) l[k] = lvl8[q[k]];
-#pragma unroll
-                for (int k = 1; k < 8; k++) same = same && (l[k] == l[0]);
-            }
+            for (int k = 1; k < 8; k++) same = same && (par[k] == par[0]) && (l[k] == l[0]);
             split = same;
             if (split && keep) {
                 double e[8];

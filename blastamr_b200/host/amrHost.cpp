@@ -1,0 +1,421 @@
+// amrHost.cpp -- see amrHost.H.  Every numerical loop of the reference is ONE call into libamr_b200.so.
+#include "amrHost.H"
+
+#include <algorithm>
+#include <cstring>
+
+namespace amr {
+
+// ------------------------------------------------------------------------------------------------ fvMeshLite
+
+label fvMeshLite::findPatchID(const word &nm) const {
+    for (size_t i = 0; i < patches.size(); i++) if (patches[i].name == nm) return (label)i;
+    return -1;
+}
+volField &fvMeshLite::lookupField(const word &nm) {
+    auto it = fields.find(nm);
+    if (it == fields.end()) throw FatalError("request for volScalarField " + nm + " from objectRegistry failed");
+    return it->second;
+}
+
+// mag(field) for non-scalar fields: errorEstimator::getFieldValueType, errorEstimatorTemplates.C:30-46
+static scalarField magField(const volField &f, int64_t n) {
+    if ((int64_t)f.v.size() != n * f.nComp) throw FatalError("field size does not match the mesh");
+    if (f.nComp == 1) return f.v;
+    scalarField m((size_t)n);
+    for (int64_t c = 0; c < n; c++) {
+        scalar s = 0;
+        for (int k = 0; k < f.nComp; k++) s += f.v[c * f.nComp + k] * f.v[c * f.nComp + k];
+        m[c] = std::sqrt(s);
+    }
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------ errorEstimator
+
+std::map<word, errorEstimator::ctor> &errorEstimator::dictionaryConstructorTable() {
+    static std::map<word, ctor> t;
+    return t;
+}
+
+std::unique_ptr<errorEstimator> errorEstimator::New(fvMeshLite &mesh, amr_ctx *gpu, const dictionary &dict) {
+    const word type = dict.lookupWord("errorEstimator");          // errorEstimatorNew.C:36
+    auto &t = dictionaryConstructorTable();
+    auto it = t.find(type);
+    if (it == t.end()) {
+        std::string valid;
+        for (auto &e : t) valid += e.first + " ";
+        throw FatalError("Unknown errorEstimator type " + type + "\n\nValid errorEstimator types :\n" + valid);
+    }
+    return it->second(mesh, gpu, dict, word());
+}
+
+errorEstimator::errorEstimator(fvMeshLite &mesh, amr_ctx *gpu, const dictionary &dict, const word &name)
+    : mesh_(mesh), gpu_(gpu), name_(name),
+      protectedPatches_(dict.lookupOrDefault("protectedPatches", wordList{})),       // errorEstimator.C:145
+      nPatchesBuffers_((label)dict.lookupOrDefaultLabel("nPatchesBuffers", 1)),      // :146
+      nBufferCells_((label)std::max(dict.lookupOrDefaultLabel("nBufferLayers", 1),
+                                    dict.lookupOrDefaultLabel("nRefinementBufferLayers", 1))),   // :147-154
+      maxRefinementLevel_((label)dict.lookupOrDefaultLabel("maxRefinement", 1)) {}   // :155
+
+void errorEstimator::check(int rc, const char *where) const {
+    if (rc != AMR_OK) throw FatalError(std::string(where) + ": " + amr_last_error(gpu_));
+}
+
+void errorEstimator::read(const dictionary &dict) {          // errorEstimator.C:167-191
+    lowerRefine_ = dict.lookupScalar("lowerRefineLevel");
+    lowerUnrefine_ = dict.lookupScalar("unrefineLevel");
+    upperRefine_ = dict.lookupOrDefault("upperRefineLevel", GREAT);
+    upperUnrefine_ = dict.lookupOrDefault("upperUnrefineLevel", GREAT);
+    if (dict.found("maxRefinement")) maxLevel_ = (label)dict.lookupLabel("maxRefinement");
+    else if (dict.found("minDx")) throw FatalError("minDx needs meshSizeObject (cellSize estimator family): host-side, not on the device path");
+    else throw FatalError("Either maxRefinement or minDx must be specified");
+    protectedPatches_ = dict.lookupOrDefault("protectedPatches", wordList{});
+}
+
+labelList errorEstimator::maxRefinement() const { return labelList((size_t)mesh_.nCells, maxLevel_); }   // errorEstimator.C:264-267
+
+void errorEstimator::normalize(scalarField &error) {
+    check(amr_normalize(gpu_, lowerRefine_, upperRefine_, lowerUnrefine_, upperUnrefine_, error.data()), "errorEstimator::normalize");
+}
+
+label errorEstimator::protectPatches() {
+    if (protectedPatches_.empty()) return 0;                  // errorEstimator.C:331-334
+    labelList ids;
+    for (const word &nm : protectedPatches_) {
+        label id = mesh_.findPatchID(nm);
+        if (id >= 0) ids.push_back(id);
+    }
+    int64_t nProt = 0;
+    const int nLayers = nPatchesBuffers_ + (maxRefinementLevel_ - 1) * nBufferCells_;   // :347
+    check(amr_protect_patches(gpu_, ids.data(), (int)ids.size(), nLayers, error_.data(), &nProt), "errorEstimator::protectPatches");
+    return (label)nProt;
+}
+
+namespace errorEstimators {
+
+#define THR4 const double thr[4] = {lowerRefine_, upperRefine_, lowerUnrefine_, upperUnrefine_}
+
+struct delta : errorEstimator {           // delta.C
+    word fieldName_;
+    delta(fvMeshLite &m, amr_ctx *g, const dictionary &d, const word &n) : errorEstimator(m, g, d, n), fieldName_(d.lookupWord("deltaField")) { read(d); }
+    word type() const override { return "delta"; }
+    void update(const bool scale) override {
+        const volField &x = mesh_.lookupField(fieldName_);
+        if (x.nComp != 1) throw FatalError("delta: " + fieldName_ + " is not a volScalarField");
+        error_.resize((size_t)mesh_.nCells);
+        THR4;
+        check(amr_estimate(gpu_, AMR_EST_DELTA, x.v.data(), nullptr, 0, 0, scale, thr, error_.data()), "delta::update");
+    }
+};
+struct scaledDelta : errorEstimator {     // scaledDelta.C
+    word fieldName_;
+    scalar minVal_, offset_;
+    scaledDelta(fvMeshLite &m, amr_ctx *g, const dictionary &d, const word &n)
+        : errorEstimator(m, g, d, n), fieldName_(d.lookupWord("scaledDeltaField")), minVal_(d.lookupOrDefault("minValue", SMALL)),
+          offset_(d.lookupOrDefault("offset", 0.0)) { read(d); }
+    word type() const override { return "scaledDelta"; }
+    void update(const bool scale) override {
+        const scalarField x = magField(mesh_.lookupField(fieldName_), mesh_.nCells);
+        error_.resize((size_t)mesh_.nCells);
+        THR4;
+        check(amr_estimate(gpu_, AMR_EST_SCALED_DELTA, x.data(), nullptr, minVal_, offset_, scale, thr, error_.data()), "scaledDelta::update");
+    }
+};
+struct densityGradient : errorEstimator { // absent from the reference; see include/amr_b200.h AMR_EST_DENSITY_GRADIENT
+    word fieldName_;
+    scalar minVal_;
+    densityGradient(fvMeshLite &m, amr_ctx *g, const dictionary &d, const word &n)
+        : errorEstimator(m, g, d, n), fieldName_(d.lookupOrDefault("densityField", word("rho"))), minVal_(d.lookupOrDefault("minValue", SMALL)) { read(d); }
+    word type() const override { return "densityGradient"; }
+    void update(const bool scale) override {
+        const scalarField x = magField(mesh_.lookupField(fieldName_), mesh_.nCells);
+        error_.resize((size_t)mesh_.nCells);
+        THR4;
+        check(amr_estimate(gpu_, AMR_EST_DENSITY_GRADIENT, x.data(), nullptr, minVal_, 0.0, scale, thr, error_.data()), "densityGradient::update");
+    }
+};
+struct Lohner : errorEstimator {          // Lohner.C
+    word fieldName_;
+    scalar epsilon_;
+    Lohner(fvMeshLite &m, amr_ctx *g, const dictionary &d, const word &n)
+        : errorEstimator(m, g, d, n), fieldName_(d.lookupWord("deltaField")), epsilon_(d.lookupScalar("epsilon")) { read(d); }
+    word type() const override { return "Lohner"; }
+    void update(const bool scale) override {
+        const volField &x = mesh_.lookupField(fieldName_);
+        if (x.nComp != 1) throw FatalError("Lohner: " + fieldName_ + " is not a volScalarField");
+        error_.resize((size_t)mesh_.nCells);
+        THR4;
+        check(amr_estimate_lohner(gpu_, x.v.data(), nullptr, nullptr, epsilon_, scale, thr, error_.data()), "Lohner::update");
+    }
+};
+struct fieldValue : errorEstimator {      // fieldValue.C
+    word fieldName_;
+    fieldValue(fvMeshLite &m, amr_ctx *g, const dictionary &d, const word &n) : errorEstimator(m, g, d, n), fieldName_(d.lookupWord("fieldName")) { read(d); }
+    word type() const override { return "fieldValue"; }
+    void update(const bool scale) override {
+        const scalarField x = magField(mesh_.lookupField(fieldName_), mesh_.nCells);
+        error_.resize((size_t)mesh_.nCells);
+        THR4;
+        check(amr_estimate(gpu_, AMR_EST_FIELD_VALUE, x.data(), nullptr, 0, 0, scale, thr, error_.data()), "fieldValue::update");
+    }
+};
+struct gradientRange : errorEstimator {   // gradientRange.C ("gradientRange" in the run-time table)
+    word gradField_;
+    scalar refineThreshold_, unrefineThreshold_;
+    gradientRange(fvMeshLite &m, amr_ctx *g, const dictionary &d, const word &n)
+        : errorEstimator(m, g, d, n), gradField_(d.lookupWord("gradField")), refineThreshold_(d.lookupOrDefault("refineThreshold", 0.5)),
+          unrefineThreshold_(d.lookupOrDefault("unrefineThreshold", 0.4)) { read(d); }
+    word type() const override { return "gradientRange"; }
+    void read(const dictionary &d) override {
+        errorEstimator::read(d);
+        refineThreshold_ = d.lookupOrDefault("refineThreshold", 0.5);
+        unrefineThreshold_ = d.lookupOrDefault("unrefineThreshold", 0.4);
+    }
+    void update(const bool scale) override {
+        // fvc::grad stays OpenFOAM core on the host (scheme from fvSchemes); the solver registers mag(grad(f))
+        const volField &g = mesh_.lookupField("mag(grad(" + gradField_ + "))");
+        error_ = magField(g, mesh_.nCells);
+        double thr[4];
+        check(amr_normalize_range(gpu_, refineThreshold_, unrefineThreshold_, scale, error_.data(), thr, nullptr), "gradientEstimator::update");
+        lowerRefine_ = thr[0]; upperRefine_ = thr[1]; lowerUnrefine_ = thr[2]; upperUnrefine_ = thr[3];
+    }
+};
+
+template <class T>
+static void add(const word &nm) {
+    errorEstimator::dictionaryConstructorTable()[nm] = [](fvMeshLite &m, amr_ctx *g, const dictionary &d, const word &n) {
+        return std::unique_ptr<errorEstimator>(new T(m, g, d, n));
+    };
+}
+static bool registered = []() {
+    add<delta>("delta"); add<scaledDelta>("scaledDelta"); add<Lohner>("Lohner"); add<fieldValue>("fieldValue");
+    add<gradientRange>("gradientRange"); add<densityGradient>("densityGradient");
+    errorEstimator::dictionaryConstructorTable()["coded"] = [](fvMeshLite &, amr_ctx *, const dictionary &, const word &) -> std::unique_ptr<errorEstimator> {
+        throw FatalError("coded errorEstimator: user C++ is compiled and run by the host (codedErrorEstimator.C); "
+                         "its error_ field enters the device path through amr_normalize / amr_select_refine");
+    };
+    return true;
+}();
+
+}  // namespace errorEstimators
+
+// ------------------------------------------------------------------------------------------------ fvMeshRefiner
+
+std::map<word, fvMeshRefiner::ctor> &fvMeshRefiner::dictionaryConstructorTable() {
+    static std::map<word, ctor> t;
+    return t;
+}
+std::unique_ptr<fvMeshRefiner> fvMeshRefiner::New(adaptiveFvMesh &mesh, const dictionary &dict) {
+    word type = "hexRefiner";                                   // fvMeshRefinerNew.C:82-86
+    if (dict.found("refiner")) type = dict.lookupWord("refiner");
+    auto &t = dictionaryConstructorTable();
+    auto it = t.find(type);
+    if (it == t.end()) {
+        std::string valid;
+        for (auto &e : t) valid += e.first + " ";
+        throw FatalError("Unknown fvMeshRefiner type " + type + "\n\nValid fvMeshRefiner types :\n" + valid);
+    }
+    return it->second(mesh, dict);
+}
+static bool refinersRegistered = []() {
+    fvMeshRefiner::dictionaryConstructorTable()["hexRefiner"] = [](adaptiveFvMesh &m, const dictionary &d) {
+        return std::unique_ptr<fvMeshRefiner>(new fvMeshHexRefiner(m, d));
+    };
+    auto notYet = [](const char *nm) {
+        return [nm](adaptiveFvMesh &, const dictionary &) -> std::unique_ptr<fvMeshRefiner> {
+            throw FatalError(std::string(nm) + ": this refiner's edge-consistency sweeps are not on the device path yet (SURVEY.md 8a B2/B4)");
+        };
+    };
+    fvMeshRefiner::dictionaryConstructorTable()["polyRefiner"] = notYet("polyRefiner");
+    fvMeshRefiner::dictionaryConstructorTable()["directionalRefiner"] = notYet("directionalRefiner");
+    return true;
+}();
+
+fvMeshRefiner::fvMeshRefiner(adaptiveFvMesh &mesh, const dictionary &dict) : amesh_(mesh), dict_(dict) { readDict(dict); }
+
+void fvMeshRefiner::readDict(const dictionary &dict) {          // fvMeshRefiner.C:526-613
+    dict_ = dict;
+    maxCells_ = (label)dict_.lookupOrDefaultLabel("maxCells", labelMax);
+    if (maxCells_ <= 0) throw FatalError("Illegal maximum number of cells; the maxCells should be > 0.");
+    if (dict.found("nRefinementBufferLayers")) nRefinementBufferLayers_ = (label)dict_.lookupLabel("nRefinementBufferLayers");
+    else if (dict.found("nBufferLayers")) nRefinementBufferLayers_ = (label)dict_.lookupLabel("nBufferLayers");
+    if (dict.found("nUnrefinementBufferLayers")) nUnrefinementBufferLayers_ = (label)dict_.lookupLabel("nUnrefinementBufferLayers");
+    else if (dict.found("nBufferLayers")) nUnrefinementBufferLayers_ = (label)dict_.lookupLabel("nBufferLayers");
+    protectedPatchNames_ = dict_.lookupOrDefault("protectedPatches", wordList());
+    refine_ = dict_.lookupOrDefaultBool("refine", true);
+    unrefine_ = dict_.lookupOrDefaultBool("unrefine", true);
+    refineInterval_ = (label)dict_.lookupOrDefaultLabel("refineInterval", 1);
+    if (refineInterval_ < 0) throw FatalError("Illegal refineInterval; the refineInterval should be >= 1.");
+    unrefineInterval_ = (label)dict_.lookupOrDefaultLabel("unrefineInterval", refineInterval_);
+    if (unrefineInterval_ < 0) throw FatalError("Illegal unrefineInterval; the unrefineInterval should be >= 1.");
+    beginRefine_ = dict_.lookupOrDefault("beginRefine", 0.0);
+    beginUnrefine_ = dict_.lookupOrDefault("beginUnrefine", 0.0);
+    endRefine_ = dict_.lookupOrDefault("endRefine", GREAT);
+    endUnrefine_ = dict_.lookupOrDefault("endUnrefine", GREAT);
+}
+
+bool fvMeshRefiner::canRefine(const bool incr) const {           // fvMeshRefiner.C:274-310
+    const fvMeshLite &m = amesh_.mesh();
+    if (m.timeIndex <= 1) return true;          // force refinement on first timestep (before `refine` is looked at)
+    if (!refine_) return false;
+    if (force_) {
+    } else if (m.timeValue < beginRefine_ || m.timeValue > endRefine_) return false;
+    else if (refineInterval_ > 0 && (m.timeIndex % refineInterval_) > 0) return false;
+    if (incr) nRefinementIterations_++;
+    return m.nCells < maxCells_;                // single rank: globalData().nTotalCells()
+}
+bool fvMeshRefiner::canUnrefine(const bool incr) const {         // fvMeshRefiner.C:313-341
+    const fvMeshLite &m = amesh_.mesh();
+    if (!unrefine_ || m.timeIndex <= 0) return false;
+    if (force_) {
+    } else if (m.timeIndex <= 0 || m.timeValue < beginUnrefine_ || m.timeValue > endUnrefine_) return false;
+    else if (unrefineInterval_ > 0 && (m.timeIndex % unrefineInterval_) > 0) return false;
+    if (incr) nUnrefinementIterations_++;
+    return true;
+}
+
+// fvMeshHexRefiner::refine, fvMeshHexRefiner.C:1476-1684
+bool fvMeshHexRefiner::refine(const scalarField &errorIn, const labelList &maxCellLevel, const scalar lowerRefineLevel,
+                              const scalar upperRefineLevel, const scalar unrefineLevel) {
+    readDict(this->dict_);
+    bool hasChanged = false;
+    fvMeshLite &mesh = amesh_.mesh();
+    amr_ctx *gpu = amesh_.gpu();
+    lastCellsToRefine.clear(); lastElemsToUnrefine.clear();
+    if (!(canRefine() || canUnrefine())) return false;            // preUpdate(), :1487
+    scalarField error(errorIn);
+    boolList refineCell((size_t)mesh.nCells, 0);
+    labelList pp;
+    for (const word &nm : protectedPatchNames_) { label id = mesh.findPatchID(nm); if (id >= 0) pp.push_back(id); }
+    const int kind = amesh_.refinerKind();
+
+    if (canRefine(true)) {
+        labelList maxRefinement(maxCellLevel);
+        if (maxRefinement.empty()) {                              // setMaxCellLevel, fvMeshRefiner.C:222-253
+            if (!dict_.found("maxRefinement")) throw FatalError("maxRefinement was not specified");
+            maxRefinement.assign((size_t)mesh.nCells, (label)dict_.lookupLabel("maxRefinement"));
+        }
+        if (!maxRefinement.empty() && *std::min_element(maxRefinement.begin(), maxRefinement.end()) < 0)
+            throw FatalError("Illegal maximum refinement level; the maxRefinement should be > 0.");
+        if ((int64_t)maxRefinement.size() != mesh.nCells) throw FatalError("Inconsistent number of cells and size of maxCellsLevel");
+        labelList cellsToRefine((size_t)std::max<int64_t>(mesh.nCells, 1));
+        int64_t nCellsToRefine = 0;
+        amesh_.check(amr_select_refine(gpu, error.data(), lowerRefineLevel, upperRefineLevel, maxRefinement.data(), 0,
+                                       nRefinementBufferLayers_, pp.data(), (int)pp.size(), maxCells_, kind, refineCell.data(),
+                                       cellsToRefine.data(), &nCellsToRefine, nullptr),
+                     "fvMeshHexRefiner::refine (selectRefineCells)");
+        cellsToRefine.resize((size_t)nCellsToRefine);
+        lastCellsToRefine = cellsToRefine;
+        if (nCellsToRefine > 0) {
+            if (!amesh_.topo()) throw FatalError("no topology changer attached (polyTopoChange is host bookkeeping)");
+            const int64_t nOld = mesh.nCells;
+            mapPolyMesh map = amesh_.topo()->refine(mesh, cellsToRefine);     // refine(cellsToRefine), :183-246
+            // refineCell through the map, :1562-1586 (before the new mesh is uploaded: the marking survives amr_mesh_set)
+            boolList newRefineCell(map.cellMap.size());
+            amesh_.check(amr_remap_refine_cell(gpu, nOld, (int64_t)map.cellMap.size(), map.cellMap.data(), map.reverseCellMap.data(),
+                                               refineCell.data(), newRefineCell.data()),
+                         "fvMeshHexRefiner::refine (refineCell remap)");
+            refineCell.swap(newRefineCell);
+            // the error field is a registered volScalarField: mapped with the others
+            scalarField newError(map.cellMap.size());
+            amesh_.check(amr_map_field(gpu, nOld, (int64_t)map.cellMap.size(), map.cellMap.data(), 1, error.data(), newError.data(),
+                                       AMR_MAP_DIRECT, nullptr, nullptr), "fvMesh::mapFields(error)");
+            error.swap(newError);
+            amesh_.updateMesh(map);                                            // mesh_.updateMesh(map) -> mapFields
+            int64_t nBad = 0;
+            amesh_.check(amr_check_levels(gpu, nullptr, &nBad), "hexRef::checkRefinementLevels");   // :243
+            hasChanged = true;
+        }
+    }
+
+    if (canUnrefine(true)) {
+        const int64_t nElemMax = std::max<int64_t>(std::max(mesh.nPoints, mesh.nEdges), 1);
+        labelList elems((size_t)nElemMax);
+        int64_t nSplitElems = 0;
+        amesh_.check(amr_select_unrefine(gpu, error.data(), unrefineLevel, refineCell.data(), nUnrefinementBufferLayers_, pp.data(),
+                                         (int)pp.size(), kind, elems.data(), &nSplitElems, nullptr),
+                     "fvMeshHexRefiner::refine (selectUnrefineElems)");
+        elems.resize((size_t)nSplitElems);
+        lastElemsToUnrefine = elems;
+        if (nSplitElems > 0) {
+            if (!amesh_.topo()) throw FatalError("no topology changer attached");
+            mapPolyMesh map = amesh_.topo()->unrefine(mesh, elems);           // unrefine(elems), :249-303
+            amesh_.updateMesh(map);
+            int64_t nBad = 0;
+            amesh_.check(amr_check_levels(gpu, nullptr, &nBad), "hexRef::checkRefinementLevels");   // :300
+            hasChanged = true;
+        }
+    }
+    return hasChanged;
+}
+
+// ------------------------------------------------------------------------------------------------ adaptiveFvMesh
+
+adaptiveFvMesh::adaptiveFvMesh(const std::string &text, int device) {
+    if (amr_ctx_create(device, &gpu_) != AMR_OK)
+        throw FatalError("adaptiveFvMesh: no usable CUDA device (this library has no CPU path)");
+    setDict(text);
+}
+adaptiveFvMesh::~adaptiveFvMesh() {
+    error_.reset(); refiner_.reset();
+    if (gpu_) amr_ctx_destroy(gpu_);
+}
+void adaptiveFvMesh::check(int rc, const char *where) const {
+    if (rc != AMR_OK) throw FatalError(std::string(where) + ": " + amr_last_error(gpu_));
+}
+void adaptiveFvMesh::setDict(const std::string &text) {
+    dictText_ = text;
+    dict_ = dictionary::parse(text);
+    if (dict_.found("dynamicFvMesh") && dict_.lookupWord("dynamicFvMesh") != "adaptiveFvMesh")
+        throw FatalError("Unknown dynamicFvMesh type " + dict_.lookupWord("dynamicFvMesh") + "\n\nValid dynamicFvMesh types :\nadaptiveFvMesh");
+}
+void adaptiveFvMesh::readDict() {                                  // adaptiveFvMesh.C:93-117
+    const dictionary &refineDict = dict_.optionalSubDict("adaptiveFvMeshCoeffs");
+    if (!refiner_) refiner_ = fvMeshRefiner::New(*this, refineDict);
+    if (!error_) error_ = errorEstimator::New(mesh_, gpu_, refineDict);
+    refiner_->readDict(refineDict);
+    error_->read(refineDict);
+}
+void adaptiveFvMesh::meshChanged() {
+    fvMeshLite &m = mesh_;
+    std::vector<label> st, sz, ty, nb;
+    for (auto &q : m.patches) { st.push_back(q.start); sz.push_back(q.size); ty.push_back(q.type); nb.push_back(q.nbrRank); }
+    check(amr_mesh_set(gpu_, m.nCells, m.nInternalFaces, m.nBoundaryFaces, m.nPoints, m.owner.data(), m.neighbour.data(), (int)m.patches.size(),
+                       st.data(), sz.data(), ty.data(), nb.data()), "amr_mesh_set");
+    if (!m.pcOff.empty()) check(amr_mesh_set_points(gpu_, m.pcOff.data(), m.pcCells.data(), m.bndPoint.data()), "amr_mesh_set_points");
+    if (m.nEdges > 0) check(amr_mesh_set_edges(gpu_, m.nEdges, m.edgePts.data(), m.ecOff.data(), m.ecCells.data(), m.bndEdge.data()), "amr_mesh_set_edges");
+    if (!m.Sf.empty()) check(amr_mesh_set_geometry(gpu_, m.weights.data(), m.Sf.data(), m.magSf.data(), m.deltaCoeffs.data(), m.V.data()), "amr_mesh_set_geometry");
+    if (!m.cellLevel.empty())
+        check(amr_levels_set(gpu_, m.cellLevel.data(), m.pointLevel.empty() ? nullptr : m.pointLevel.data(),
+                             m.visibleCells.empty() ? nullptr : m.visibleCells.data(), m.splitParent.empty() ? nullptr : m.splitParent.data(),
+                             (int64_t)m.splitParent.size()), "amr_levels_set");
+    check(amr_protected_cells_set(gpu_, m.protectedCell.empty() ? nullptr : m.protectedCell.data()), "amr_protected_cells_set");
+}
+bool adaptiveFvMesh::update() {                                    // adaptiveFvMesh.C:369-376
+    if (!refiner_ || !error_) readDict();
+    bool changed = (refiner_->canRefine(true) || refiner_->canUnrefine(true)) && refine();
+    return changed;
+}
+bool adaptiveFvMesh::refine() {                                    // adaptiveFvMesh.C:379-393
+    dict_ = dictionary::parse(dictText_);     // "Re-read dictionary"
+    readDict();
+    error_->update();
+    error_->protectPatches();
+    return refiner_->refine(error_->error(), error_->maxRefinement());
+}
+void adaptiveFvMesh::updateMesh(const mapPolyMesh &map) {          // adaptiveFvMesh.C:293 -> fvMesh::mapFields
+    // topoChanger has already replaced the addressing in mesh_; old sizes come from the map
+    const int64_t nOld = (int64_t)map.reverseCellMap.size(), nNew = (int64_t)map.cellMap.size();
+    for (auto &kv : mesh_.fields) {
+        volField &f = kv.second;
+        if ((int64_t)f.v.size() != nOld * f.nComp) continue;       // not a cell field of the old mesh
+        scalarField nf((size_t)(nNew * f.nComp));
+        check(amr_map_field(gpu_, nOld, nNew, map.cellMap.data(), f.nComp, f.v.data(), nf.data(), AMR_MAP_DIRECT, nullptr, nullptr),
+              "fvMesh::mapFields");
+        f.v.swap(nf);
+    }
+    meshChanged();
+}
+
+}  // namespace amr
