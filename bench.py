@@ -313,6 +313,15 @@ def main():
     cells_h = np.empty(max(n, 1), dtype=np.int32)
     cells_first, _ = ctx.select_refine(None, MAX_LEVEL, LAYERS_REF, cells_out=cells_h)
     n_ref = len(cells_first)
+    if world > 1:
+        # each rank cuts its own sub-box: the processor faces of neighbouring ranks stay matched only if no
+        # refined cell touches a processor patch (true for the per-rank front, which stays inside the box)
+        touched = np.zeros(n, bool)
+        for q in mesh.patches:
+            if q.coupled:
+                touched[mesh.owner[q.start:q.start + q.size]] = True
+        if touched[cells_first].any():
+            raise SystemExit("bench: refinement reaches a processor patch; the per-rank topology engine cannot keep patches matched")
     cell_map_h = octree.refine(cells_first.copy())
     mesh1 = octree.build()
     n1, f1, b1, p1 = mesh1.n, mesh1.f, mesh1.b, mesh1.p
