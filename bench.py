@@ -407,26 +407,22 @@ def main():
         xh = torch.from_numpy(x_host).pin_memory()
         f3h = torch.stack([xh, 2 * xh, -xh], dim=1).contiguous().pin_memory()
         cmh = cell_map.cpu().pin_memory()
-        rvh = rev_map.cpu().pin_memory()
         n1h = torch.empty(n_new, dtype=torch.float64).pin_memory()
         n3h = torch.empty((n_new, 3), dtype=torch.float64).pin_memory()
-        e0h = torch.empty(n, dtype=torch.float64).pin_memory()
-        e1h = torch.empty(n_new, dtype=torch.float64).pin_memory()
-        rc0h = torch.empty(n, dtype=torch.uint8).pin_memory()
-        rc1h = torch.empty(n_new, dtype=torch.uint8).pin_memory()
         cells_h2 = np.empty(max(n, 1), dtype=np.int32)
         pts_h = np.empty(max(p1, 1), dtype=np.int32)
 
         def step_host():
-            # every array the reference keeps on the host crosses PCIe: field in, error out, marking out,
-            # fields in / mapped fields out, error + marking in again for the new mesh, lists out
-            ctx.estimate("delta", xh.numpy(), thresholds=thr, out=e0h.numpy())
-            cl, _ = ctx.select_refine(e0h.numpy(), MAX_LEVEL, LAYERS_REF, cells_out=cells_h2, refine_cell_out=rc0h.numpy())
+            # Host buffers for everything the solver owns (the field in, the registered fields in and their
+            # mapped versions out, the decision lists out); the path's own intermediates (error, refineCell)
+            # stay on the device between the calls, as INTEGRATION.md prescribes for the drop-in.
+            ctx.estimate("delta", xh.numpy(), thresholds=thr, out=err0)
+            cl, _ = ctx.select_refine(err0, MAX_LEVEL, LAYERS_REF, cells_out=cells_h2, refine_cell_out=rc0)
             ctx.map_field(cmh.numpy(), xh.numpy(), n_old=n, n_new=n_new, ncomp=1, out=n1h.numpy())
             ctx.map_field(cmh.numpy(), f3h.numpy(), n_old=n, n_new=n_new, ncomp=3, out=n3h.numpy())
-            ctx.map_field(cmh.numpy(), e0h.numpy(), n_old=n, n_new=n_new, ncomp=1, out=e1h.numpy())
-            ctx1.remap_refine_cell(cmh.numpy(), rvh.numpy(), refine_cell=rc0h.numpy(), out=rc1h.numpy())
-            pl, _ = ctx1.select_unrefine(e1h.numpy(), LAYERS_UNREF, refine_cell=rc1h.numpy(), elems_out=pts_h)
+            ctx.map_field(cell_map, err0, n_old=n, n_new=n_new, ncomp=1, out=err1)
+            ctx1.remap_refine_cell(cell_map, rev_map, refine_cell=rc0)
+            pl, _ = ctx1.select_unrefine(err1, LAYERS_UNREF, elems_out=pts_h)
             return len(cl), len(pl)
 
         step_host()
@@ -439,8 +435,8 @@ def main():
         z.record()
         barrier()
         e2e_ms = a.elapsed_time(z) / args.e2e_steps
-        h2d = (8 * n) + (8 * n) + 3 * (4 * n_new) + (8 * n + 24 * n + 8 * n) + (4 * n_new + 4 * n + n) + (8 * n_new + n_new)
-        d2h = (8 * n) + (n + 4 * ncl) + (8 * n_new + 24 * n_new + 8 * n_new) + n_new + (n_new + 4 * npl)
+        h2d = (8 * n) + 2 * (4 * n_new) + (8 * n + 24 * n)      # x; cellMap (per field); scalar + vector field
+        d2h = (4 * ncl) + (8 * n_new + 24 * n_new) + (4 * npl)  # cellsToRefine; mapped fields; split points
         e2e = (e2e_ms, h2d, d2h)
 
     # ---- max over ranks
