@@ -35,6 +35,8 @@ _SIGS = {
     "amr_mesh_set": (C.c_int, [C.c_void_p] + [C.c_int64] * 4 + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 4),
     "amr_mesh_set_points": (C.c_int, [C.c_void_p] * 4),
     "amr_mesh_set_edges": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 4),
+    "amr_mesh_set_faces": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "amr_mesh_set_geometry": (C.c_int, [C.c_void_p] * 6),
     "amr_estimate_lohner": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "amr_levels_set": (C.c_int, [C.c_void_p] * 5 + [C.c_int64]),
@@ -163,6 +165,8 @@ class Context:
         if self.n_edges:
             self._ck(self.L.amr_mesh_set_edges(self._h, mesh.n_edges, _ptr(mesh.edge_pts), _ptr(mesh.ec_off), _ptr(mesh.ec_cells),
                                                _ptr(mesh.bnd_edge)))
+        if getattr(mesh, "face_off", None) is not None:
+            self._ck(self.L.amr_mesh_set_faces(self._h, _ptr(mesh.face_off), _ptr(mesh.face_pts)))
         if getattr(mesh, "Sf", None) is not None and mesh.vol is not None:
             self._ck(self.L.amr_mesh_set_geometry(self._h, _ptr(mesh.weights), _ptr(mesh.Sf), _ptr(mesh.magSf),
                                                   _ptr(mesh.delta_coeffs), _ptr(mesh.vol)))
@@ -184,6 +188,10 @@ class Context:
         nsp = 0 if split_parent is None else len(split_parent)
         self._ck(self.L.amr_levels_set(self._h, _ptr(cell_level), _ptr(point_level), _ptr(visible),
                                        _ptr(split_parent) if nsp else None, nsp))
+
+    def set_option(self, option: int, value: int):
+        """0 = edgeBasedConsistency, 1 = polyRefiner force_"""
+        self._ck(self.L.amr_set_option(self._h, option, value))
 
     def set_protected_cells(self, prot):
         self._ck(self.L.amr_protected_cells_set(self._h, _ptr(prot)))

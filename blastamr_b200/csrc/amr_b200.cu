@@ -92,6 +92,7 @@ static void freeMesh(amr_ctx *ctx) {
     sellFree(ctx, ctx->cf);
     ctx->haveGeom = false;
     sellFree(ctx, ctx->ec); devFree(ctx, &ctx->bndEdge); devFree(ctx, &ctx->edgePts);
+    devFree(ctx, &ctx->faceOff); devFree(ctx, &ctx->facePts); ctx->haveFaces = false;
     ctx->haveEdges = false; ctx->nEdges = 0;
     ctx->havePoints = ctx->haveLevels = ctx->haveHistory = false;
     ctx->occCache.clear();
@@ -322,6 +323,33 @@ AMR_API int amr_mesh_set_edges(amr_ctx *ctx, int64_t nEdges, const int32_t *edge
     TRY(growFlagPool(ctx, nEdges + 16));
     ctx->nEdges = nEdges;
     ctx->haveEdges = true;
+    return AMR_OK;
+}
+
+AMR_API int amr_mesh_set_faces(amr_ctx *ctx, const int32_t *faceOff, const int32_t *facePts) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_mesh_set_faces: call amr_mesh_set first");
+    if (!faceOff || !facePts) FAIL(AMR_ERR_ARG, "amr_mesh_set_faces: null pointer");
+    const int64_t nf = ctx->f + ctx->b;
+    devFree(ctx, &ctx->faceOff); devFree(ctx, &ctx->facePts);
+    TRY(devAlloc(ctx, &ctx->faceOff, nf + 1));
+    CK(cudaMemcpyAsync(ctx->faceOff, faceOff, (size_t)(nf + 1) * 4, cudaMemcpyDefault, ctx->stream));
+    int32_t nnz = 0;
+    CK(cudaMemcpyAsync(&nnz, ctx->faceOff + nf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (nnz < 0) FAIL(AMR_ERR_ARG, "amr_mesh_set_faces: bad CSR");
+    TRY(devAlloc(ctx, &ctx->facePts, nnz));
+    if (nnz) CK(cudaMemcpyAsync(ctx->facePts, facePts, (size_t)nnz * 4, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->haveFaces = true;
+    return AMR_OK;
+}
+
+AMR_API int amr_set_option(amr_ctx *ctx, int option, int64_t value) {
+    if (!ctx) return AMR_ERR_ARG;
+    if (option == AMR_OPT_EDGE_BASED_CONSISTENCY) ctx->optEdgeConsistency = value ? 1 : 0;
+    else if (option == AMR_OPT_POLY_FORCE) ctx->optPolyForce = value ? 1 : 0;
+    else { ctx->err = "amr_set_option: unknown option"; return AMR_ERR_ARG; }
     return AMR_OK;
 }
 
@@ -656,12 +684,18 @@ static int emitList(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *userOut, 
 // hexRef::consistentRefinement loop (hexRef.C:1421-1437) on set/lf, followed by the ascending list
 // (hexRef.C:1440-1460).  The list is compacted speculatively after every sweep so that the
 // convergence flag and the list size come back in ONE host round trip per sweep.
-static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut) {
+static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut,
+                        bool edgeRule = false) {
     const int64_t n = ctx->n, b = ctx->b;
     int sweeps = 0;
     ListJob job;
     while (true) {
         CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(int), ctx->stream));
+        // refinement::consistentRefinement (refinement.C:776-780): the edge rule first, then the face rule
+        if (edgeRule && ctx->nEdges) {
+            if (maxSet) LAUNCH((k_edge_refine_sweep<true>), gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, lf, set, ctx->dFlags);
+            else LAUNCH((k_edge_refine_sweep<false>), gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, lf, set, ctx->dFlags);
+        }
         if (ctx->nCoupled > 0) {
             LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, lf, ctx->send8);
             TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
@@ -756,8 +790,11 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
     ENTER();
     if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_select_refine: mesh not set");
     if (!ctx->haveLevels) FAIL(AMR_ERR_STATE, "amr_select_refine: levels not set");
-    if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D)
-        FAIL(AMR_ERR_ARG, "amr_select_refine: only the hexRefiner sweeps are on the device path in this round");
+    if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D && refinerKind != AMR_REFINER_POLY3D)
+        FAIL(AMR_ERR_ARG, "amr_select_refine: prismatic2DRefinement (polyRefiner in 2-D) is not on the device path");
+    const bool poly = refinerKind == AMR_REFINER_POLY3D;
+    if (poly && ctx->optEdgeConsistency && !ctx->haveEdges)
+        FAIL(AMR_ERR_STATE, "amr_select_refine: polyRefiner with edgeBasedConsistency needs amr_mesh_set_edges");
     if (nProtectedPatches > 0 && !protectedPatchIds) FAIL(AMR_ERR_ARG, "amr_select_refine: protectedPatchIds is null");
     const int64_t n = ctx->n;
     const double *dErr = nullptr;
@@ -772,26 +809,28 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
     TRY(stageOut(ctx, refineCellOut, n, &dRcOut));
 
     u8 *cur = ctx->flagA, *tmp = ctx->flagB, *src0 = ctx->flagC;
+    // hexRefiner always passes force=true (fvMeshHexRefiner.C:1511), polyRefiner passes force_ (fvMeshPolyRefiner.C:338)
+    const bool forced = poly ? (ctx->optPolyForce != 0) : true;
     // M1 (+ source mask of the first forced layer)
     {
         const bool al = ((((uintptr_t)dErr) | ((uintptr_t)dMax)) & 15) == 0;
         if (n) LAUNCH(k_candidates, gridFor(n, kThreads * 4), kThreads, n, dErr, lo, hi, ctx->lvl8, dMax, maxLevelUniform, cur,
-                      nBufferLayers > 0 ? src0 : (u8 *)nullptr, al);
+                      (nBufferLayers > 0 && forced) ? src0 : (u8 *)nullptr, al);
     }
     // M2: extendMarkedCells(refineCell, maxRefinement, i == 0, force = true), fvMeshHexRefiner.C:1509-1512
     for (int i = 0; i < nBufferLayers; i++) {
         u8 *res;
-        TRY(extendLayer(ctx, cur, i == 0 ? src0 : cur, tmp, &res));
+        TRY(extendLayer(ctx, cur, (i == 0 && forced) ? src0 : cur, tmp, &res));
         std::swap(cur, tmp);
     }
-    // M3: protections, fvMeshHexRefiner.C:1514-1533
+    // M3: protections, fvMeshHexRefiner.C:1514-1533 (polyRefiner: patches only, fvMeshPolyRefiner.C:341-350)
     for (int k = 0; k < nProtectedPatches; k++) {
         int q = protectedPatchIds[k];
         if (q < 0 || q >= (int)ctx->patches.size()) FAIL(AMR_ERR_ARG, "amr_select_refine: patch id out of range");
         const Patch &pp = ctx->patches[q];
         if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)0);
     }
-    if (ctx->protCell && n) LAUNCH(k_masked_set, gridFor(n), kThreads, n, ctx->protCell, cur, (u8)0);
+    if (!poly && ctx->protCell && n) LAUNCH(k_masked_set, gridFor(n), kThreads, n, ctx->protCell, cur, (u8)0);
     // keep the marking (the reference's refineCell) resident for the unrefinement stage: the buffer
     // that holds it BECOMES ctx->refineCell (pointer swap, no copy)
     if (cur == ctx->flagA) std::swap(ctx->flagA, ctx->refineCell);
@@ -805,6 +844,14 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
     u8 *set = ctx->flagA;             // the ping-pong buffers are free now
     u8 *unref = ctx->flagB;
     bool haveU = false;
+    if (poly) {
+        // base selectRefineCells (fvMeshRefiner.C:190-219): level < maxRefinement && candidate; no quota, no protected cells
+        if (n && !dMax) LAUNCH(k_select_filter16, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)cur, (const u8 *)ctx->lvl8, (int)maxLevelUniform, (const u8 *)nullptr, set, ctx->lf);
+        else if (n) LAUNCH(k_select_filter, gridFor(n, kThreads * 4), kThreads, n, cur, ctx->lvl, dMax, maxLevelUniform, (u8 *)nullptr, -1, set, ctx->lf, ((((uintptr_t)dMax)) & 15) == 0);
+        TRY(refineSweeps(ctx, 1, set, ctx->lf, sweepsOut, cellsOut, nOut, ctx->optEdgeConsistency != 0));
+        CK(cudaGetLastError());
+        return flushOuts(ctx);
+    }
     TRY(calcProtected(ctx, unref, &haveU));
     // nTotalCells / nCandidates reductions only matter when the maxCells quota can bind
     if (ctx->nTotalCells < 0) {
@@ -916,7 +963,8 @@ AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nOld, int64_t nNew, cons
 
 // hexRef3D::consistentUnrefinement loop (hexRef3D.C:1758-1927) on point flags + ascending list
 // (hexRef3D.C:1930-1950), list compacted speculatively after each sweep (one round trip per sweep)
-static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOut, int32_t *elemsOut, int64_t *nOut) {
+static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOut, int32_t *elemsOut, int64_t *nOut,
+                          bool edgeRule = false) {
     const int64_t n = ctx->n, b = ctx->b, p = EL.rows;
     u8 *uc = ctx->flagB;     // unrefineCell
     const bool alP = (((uintptr_t)pflag) & 15) == 0, alC = (((uintptr_t)uc) & 15) == 0;
@@ -932,6 +980,9 @@ static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOu
             TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
         }
         if (n) LAUNCH(k_unrefine_sweep, gC, kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, uc, alC, ctx->ghost8, ctx->dFlags);
+        // polyhedralRefinement.C:2278-2286: faceConsistentUnrefinement, then edgeConsistentUnrefinement
+        if (edgeRule && ctx->nEdges)
+            LAUNCH(k_edge_unrefine_sweep, gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, (const u8 *)ctx->lvl8, uc, ctx->dFlags);
         sweeps++;
         TRY(emitListAsync(ctx, pflag, p, elemsOut, &job));
         int changed = 0;
@@ -951,9 +1002,16 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     ENTER();
     if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_select_unrefine: mesh not set");
     if (!ctx->havePoints) FAIL(AMR_ERR_STATE, "amr_select_unrefine: point addressing not set (amr_mesh_set_points)");
-    if (!ctx->haveLevels || !ctx->haveHistory) FAIL(AMR_ERR_STATE, "amr_select_unrefine: levels/history not set");
-    if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D)
-        FAIL(AMR_ERR_ARG, "amr_select_unrefine: only the hexRefiner cutters (hexRef3D, hexRef2D) are on the device path in this round");
+    const bool poly = refinerKind == AMR_REFINER_POLY3D;
+    if (!ctx->haveLevels || (!poly && !ctx->haveHistory)) FAIL(AMR_ERR_STATE, "amr_select_unrefine: levels/history not set");
+    if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D && !poly)
+        FAIL(AMR_ERR_ARG, "amr_select_unrefine: prismatic2DRefinement (polyRefiner in 2-D) is not on the device path");
+    if (poly) {
+        if (!ctx->haveFaces || !ctx->pointLevel) FAIL(AMR_ERR_STATE, "amr_select_unrefine: polyRefiner needs amr_mesh_set_faces and pointLevel");
+        if (ctx->optEdgeConsistency && !ctx->haveEdges) FAIL(AMR_ERR_STATE, "amr_select_unrefine: edgeBasedConsistency needs amr_mesh_set_edges");
+        if (ctx->nCoupled > 0 && nBufferLayers > 0)
+            FAIL(AMR_ERR_STATE, "amr_select_unrefine: polyRefiner point buffer layers across processor patches need a shared-point plan (syncPointList); not on the device path yet");
+    }
     if (refinerKind == AMR_REFINER_HEX2D && !ctx->haveEdges) FAIL(AMR_ERR_STATE, "amr_select_unrefine: hexRef2D needs amr_mesh_set_edges");
     if (nProtectedPatches > 0 && !protectedPatchIds) FAIL(AMR_ERR_ARG, "amr_select_unrefine: protectedPatchIds is null");
     const int64_t n = ctx->n, p = ctx->p;
@@ -971,14 +1029,23 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     }
     // nUnrefinementBufferLayers x extendMarkedCellsAcrossFaces, fvMeshHexRefiner.C:1595-1598
     u8 *cur = ctx->refineCell, *tmp = ctx->flagA;
-    for (int i = 0; i < nBufferLayers; i++) {
-        u8 *res;
-        TRY(extendLayer(ctx, cur, cur, tmp, &res));
-        std::swap(cur, tmp);
+    if (poly) {
+        // extendMarkedCellsAcrossPoints (fvMeshRefiner.C:924-977): cells -> points -> cells, in place (flags only grow)
+        for (int i = 0; i < nBufferLayers; i++) {
+            if (p) LAUNCH(k_cells_to_points_or, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const u8 *)cur, ctx->flagC);
+            if (p) LAUNCH(k_points_to_cells, gridFor(p, kThreads * 16), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const u8 *)ctx->flagC,
+                          (((uintptr_t)ctx->flagC) & 15) == 0, cur);
+        }
+    } else {
+        for (int i = 0; i < nBufferLayers; i++) {
+            u8 *res;
+            TRY(extendLayer(ctx, cur, cur, tmp, &res));
+            std::swap(cur, tmp);
+        }
     }
     ctx->refineCell = cur; ctx->flagA = tmp;
     // protections, fvMeshHexRefiner.C:1600-1622
-    if (ctx->protCell && n) LAUNCH(k_masked_set, gridFor(n), kThreads, n, ctx->protCell, cur, (u8)1);
+    if (!poly && ctx->protCell && n) LAUNCH(k_masked_set, gridFor(n), kThreads, n, ctx->protCell, cur, (u8)1);
     for (int k = 0; k < nProtectedPatches; k++) {
         int q = protectedPatchIds[k];
         if (q < 0 || q >= (int)ctx->patches.size()) FAIL(AMR_ERR_ARG, "amr_select_unrefine: patch id out of range");
@@ -989,6 +1056,18 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     dRc = cur;
     // U1+U2+U3 fused: maxCellField + getSplitElems + filter
     u8 *pflag = ctx->flagC;
+    if (poly) {
+        u8 *bad = ctx->flagA;
+        const int64_t nf = ctx->f + ctx->b;
+        CK(cudaMemsetAsync(bad, 0, (size_t)p, ctx->stream));
+        if (nf) LAUNCH(k_face_point_levels, gridFor(nf), kThreads, nf, ctx->f, (const label *)ctx->faceOff, (const label *)ctx->facePts,
+                       (const label *)ctx->pointLevel, bad);
+        if (p) LAUNCH(k_poly_select_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const label *)ctx->pointLevel, (const u8 *)bad,
+                      dErr, unrefineLevel, (const u8 *)dRc, (u8 *)nullptr, pflag);
+        TRY(unrefineSweeps(ctx, ctx->pc, pflag, sweepsOut, elemsOut, nOut, ctx->optEdgeConsistency != 0));
+        CK(cudaGetLastError());
+        return flushOuts(ctx);
+    }
     if (refinerKind == AMR_REFINER_HEX2D) {
         const int64_t ne = ctx->nEdges;
         if (ne) LAUNCH(k_select_unrefine_edges, gridFor(ne), kThreads, ne, ctx->ec.sliceOff, ctx->ec.col, ctx->ec.count, ctx->bndEdge,
@@ -1012,10 +1091,24 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
 
 AMR_API int amr_get_split_elems(amr_ctx *ctx, int refinerKind, int32_t *elemsOut, int64_t *nOut) {
     ENTER();
-    if (!ctx->havePoints || !ctx->haveHistory) FAIL(AMR_ERR_STATE, "amr_get_split_elems: points/history not set");
-    if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D) FAIL(AMR_ERR_ARG, "amr_get_split_elems: hexRef3D / hexRef2D only");
+    if (!ctx->havePoints) FAIL(AMR_ERR_STATE, "amr_get_split_elems: points not set");
     const int64_t p = ctx->p;
     u8 *pflag = ctx->flagC;
+    if (refinerKind == AMR_REFINER_POLY3D) {
+        if (!ctx->haveFaces || !ctx->pointLevel) FAIL(AMR_ERR_STATE, "amr_get_split_elems: polyRefiner needs amr_mesh_set_faces and pointLevel");
+        u8 *bad = ctx->flagA;
+        const int64_t nf = ctx->f + ctx->b;
+        CK(cudaMemsetAsync(bad, 0, (size_t)p, ctx->stream));
+        if (nf) LAUNCH(k_face_point_levels, gridFor(nf), kThreads, nf, ctx->f, (const label *)ctx->faceOff, (const label *)ctx->facePts,
+                       (const label *)ctx->pointLevel, bad);
+        if (p) LAUNCH(k_poly_select_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const label *)ctx->pointLevel, (const u8 *)bad,
+                      (const double *)nullptr, 0.0, (const u8 *)nullptr, pflag, (u8 *)nullptr);
+        TRY(emitList(ctx, pflag, p, elemsOut, nOut));
+        CK(cudaGetLastError());
+        return flushOuts(ctx);
+    }
+    if (!ctx->haveHistory) FAIL(AMR_ERR_STATE, "amr_get_split_elems: history not set");
+    if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D) FAIL(AMR_ERR_ARG, "amr_get_split_elems: unknown refiner kind");
     if (refinerKind == AMR_REFINER_HEX2D) {
         if (!ctx->haveEdges) FAIL(AMR_ERR_STATE, "amr_get_split_elems: hexRef2D needs amr_mesh_set_edges");
         const int64_t ne = ctx->nEdges;

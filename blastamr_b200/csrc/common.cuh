@@ -65,6 +65,10 @@ struct amr_ctx {
     Sell cc;                   // cell -> face-neighbour cells (+ ghost slots n + bface for coupled faces)
     Sell pc;                   // point -> cells
     bool havePoints = false;
+    // polyRefiner
+    bool haveFaces = false;
+    label *faceOff = nullptr, *facePts = nullptr;
+    int optEdgeConsistency = 1, optPolyForce = 0;
     // 2-D cutter: edges as split elements
     bool haveEdges = false;
     int64_t nEdges = 0;

@@ -572,6 +572,125 @@ k_select_unrefine_edges(int64_t nEdges, const int32_t *__restrict__ ecOff, const
     if (keep) keep[e] = kp;
 }
 
+// ---- polyRefiner -------------------------------------------------------------------------------------
+
+// refinement::edgeConsistentRefinement (refinement.C:305-387), one thread per mesh edge: every unordered pair
+// of the edge's cells must satisfy the 2:1 rule on level+flag.  maxSet: a cell more than one level below the
+// edge's maximum is added; !maxSet: a marked cell more than one level above the edge's minimum is removed.
+// Same monotone closure as the face rule, so in-place chaotic iteration reaches the reference's fixed point.
+template <bool MAXSET>
+__global__ void __launch_bounds__(kThreads)
+k_edge_refine_sweep(int64_t nEdges, const int32_t *__restrict__ ecOff, const int32_t *__restrict__ ecCol,
+                    u8 *lf, u8 *set, int *changed) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= nEdges) return;
+    const int32_t base = ecOff[e >> 5];
+    const int w = ecOff[(e >> 5) + 1] - base;
+    const int32_t *row = ecCol + ((size_t)base << 5) + (e & 31);
+    int mx = 0, mn = 255;
+    for (int j = 0; j < w; j++) {
+        const int32_t c = row[(size_t)j << 5];
+        if (c < 0) break;
+        const int v = lf[c];
+        mx = max(mx, v); mn = min(mn, v);
+    }
+    if (mx - mn <= 1) return;
+    for (int j = 0; j < w; j++) {
+        const int32_t c = row[(size_t)j << 5];
+        if (c < 0) break;
+        const int v = lf[c];
+        if (MAXSET) { if (!set[c] && v + 1 < mx) { set[c] = 1; lf[c] = (u8)(v + 1); *changed = 1; } }
+        else { if (set[c] && v > mn + 1) { set[c] = 0; lf[c] = (u8)(v - 1); *changed = 1; } }
+    }
+}
+
+// refinement::edgeConsistentUnrefinement (refinement.C:511-604), maxSet = false: a cell marked for
+// unrefinement is unmarked when it would end up more than one level below another cell of the edge.
+__global__ void __launch_bounds__(kThreads)
+k_edge_unrefine_sweep(int64_t nEdges, const int32_t *__restrict__ ecOff, const int32_t *__restrict__ ecCol,
+                      const u8 *__restrict__ lvl8, u8 *uc, int *changed) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= nEdges) return;
+    const int32_t base = ecOff[e >> 5];
+    const int w = ecOff[(e >> 5) + 1] - base;
+    const int32_t *row = ecCol + ((size_t)base << 5) + (e & 31);
+    int mx = 0;
+    unsigned any = 0;
+    for (int j = 0; j < w; j++) {
+        const int32_t c = row[(size_t)j << 5];
+        if (c < 0) break;
+        const int u = uc[c];
+        any |= u;
+        mx = max(mx, (int)lvl8[c] - u);
+    }
+    if (!any) return;
+    for (int j = 0; j < w; j++) {
+        const int32_t c = row[(size_t)j << 5];
+        if (c < 0) break;
+        if (uc[c] && (int)lvl8[c] - 1 < mx - 1) { uc[c] = 0; *changed = 1; }
+    }
+}
+
+// first half of fvMeshRefiner::extendMarkedCellsAcrossPoints (fvMeshRefiner.C:924-950): a point is marked
+// when any of its cells is (the second half, points -> cells, is k_points_to_cells)
+__global__ void __launch_bounds__(kThreads)
+k_cells_to_points_or(int64_t p, const int32_t *__restrict__ pcOff, const int32_t *__restrict__ pcCol,
+                     const u8 *__restrict__ marked, u8 *__restrict__ pflag) {
+    const int64_t pt = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (pt >= p) return;
+    const int32_t base = pcOff[pt >> 5];
+    const int w = pcOff[(pt >> 5) + 1] - base;
+    const int32_t *row = pcCol + ((size_t)base << 5) + (pt & 31);
+    unsigned m = 0;
+    for (int j = 0; j < w; j++) {
+        const int32_t c = row[(size_t)j << 5];
+        if (c >= 0) m |= marked[c];
+    }
+    pflag[pt] = m ? 1 : 0;
+}
+
+// polyhedralRefinement split-point markup, face-centric (polyhedralRefinement.C:2110-2184): every point of a
+// face whose points do not share one pointLevel, and every point of a boundary face, cannot be a split point
+__global__ void __launch_bounds__(kThreads)
+k_face_point_levels(int64_t nFaces, int64_t f, const label *__restrict__ faceOff, const label *__restrict__ facePts,
+                    const label *__restrict__ pointLevel, u8 *__restrict__ bad) {
+    const int64_t face = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (face >= nFaces) return;
+    const label s = faceOff[face], e = faceOff[face + 1];
+    bool reject = face >= f;
+    const label l0 = pointLevel[facePts[s]];
+    for (label j = s + 1; j < e && !reject; j++) reject = pointLevel[facePts[j]] != l0;
+    if (reject) for (label j = s; j < e; j++) bad[facePts[j]] = 1;
+}
+
+// fvMeshPolyRefiner::selectUnrefinePoints (fvMeshPolyRefiner.C:48-79) intersected with the split points
+// (polyhedralRefinement.C:2196-2205)
+__global__ void __launch_bounds__(kThreads)
+k_poly_select_points(int64_t p, const int32_t *__restrict__ pcOff, const int32_t *__restrict__ pcCol,
+                     const label *__restrict__ pointLevel, const u8 *__restrict__ bad, const double *__restrict__ err,
+                     double unrefineLevel, const u8 *__restrict__ marked, u8 *__restrict__ isSplit, u8 *__restrict__ keep) {
+    const int64_t pt = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (pt >= p) return;
+    const bool split = pointLevel[pt] >= 1 && !bad[pt];
+    bool kp = false;
+    if (split && keep) {
+        const int32_t base = pcOff[pt >> 5];
+        const int w = pcOff[(pt >> 5) + 1] - base;
+        const int32_t *row = pcCol + ((size_t)base << 5) + (pt & 31);
+        double m = -kGREAT;
+        unsigned anyMarked = 0;
+        for (int j = 0; j < w; j++) {
+            const int32_t c = row[(size_t)j << 5];
+            if (c < 0) continue;
+            m = fmaxFoam(m, err[c]);
+            anyMarked |= marked[c];
+        }
+        kp = (m < unrefineLevel) && !anyMarked;
+    }
+    if (isSplit) isSplit[pt] = split;
+    if (keep) keep[pt] = kp;
+}
+
 // ---- sparse passes of consistentUnrefinement --------------------------------------------------
 // Candidate split points / cells marked for unrefinement are a small fraction of the mesh, so these
 // passes scan 16 flags per thread with one 128-bit load and only walk the rows of set entries.

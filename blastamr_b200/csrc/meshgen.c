@@ -65,6 +65,7 @@ typedef struct mg_mesh {
     i32 *edgePts;         /* 2*nedge: mesh.edges()[e] */
     i32 *ecOff, *ecCells; /* edgeCells CSR */
     u8 *bndEdge;          /* edge belongs to a boundary face of a non-empty patch */
+    i32 *faceOff, *facePts; /* mesh.faces() as CSR (f+b+1, nnz): points around each face, hanging nodes included */
 } mg_mesh;
 
 static void *xmalloc(size_t s) {
@@ -91,7 +92,7 @@ MG_API void mg_mesh_free(mg_mesh *m) {
     free(m->bndPoint); free(m->cellLevel); free(m->pointLevel); free(m->visible);
     free(m->splitParent); free(m->cellGlobal); free(m->pointGlobal); free(m->faceGlobal);
     free(m->pxyz); free(m->Sf); free(m->magSf); free(m->weights); free(m->deltaCoeffs);
-    free(m->edgePts); free(m->ecOff); free(m->ecCells); free(m->bndEdge);
+    free(m->edgePts); free(m->ecOff); free(m->ecCells); free(m->bndEdge); free(m->faceOff); free(m->facePts);
     free(m);
 }
 
@@ -103,6 +104,7 @@ MG_API void mg_mesh_sizes(const mg_mesh *m, i64 *out) {
     out[7] = m->cpOff ? m->cpOff[m->n] : 0;
     out[8] = m->nedge;
     out[9] = m->ecOff ? m->ecOff[m->nedge] : 0;
+    out[10] = m->faceOff ? m->faceOff[m->f + m->b] : 0;
 }
 
 /* array access by id (Python wraps the pointers without copying) */
@@ -121,6 +123,7 @@ MG_API void *mg_mesh_array(const mg_mesh *m, int id) {
     case 20: return m->pxyz;
     case 21: return m->Sf; case 22: return m->magSf; case 23: return m->weights; case 24: return m->deltaCoeffs;
     case 25: return m->edgePts; case 26: return m->ecOff; case 27: return m->ecCells; case 28: return m->bndEdge;
+    case 29: return m->faceOff; case 30: return m->facePts;
     }
     return NULL;
 }
@@ -443,6 +446,37 @@ static int cmp_i32(const void *a, const void *b) {
     i32 x = *(const i32 *)a, y = *(const i32 *)b; return (x > y) - (x < y);
 }
 
+/* ---- faces() and edges() of a 3-D octree mesh (polyRefiner needs them) ---------------------------------- */
+typedef struct {
+    const mg_oct *o; const phash *H; i64 npx, npy; int FS;
+    i32 *buf; i64 cnt, cap;
+} facewalk;
+static inline i32 point_id(const facewalk *W, i32 X, i32 Y, i32 Z) {
+    if (((X | Y | Z) & (W->FS - 1)) == 0) return (i32)((X / W->FS) + W->npx * ((Y / W->FS) + W->npy * (i64)(Z / W->FS)));
+    return ph_get(W->H, pkey(X, Y, Z));
+}
+static void walk_push(facewalk *W, i32 id) {
+    if (W->cnt == W->cap) { W->cap = W->cap ? W->cap * 2 : 1 << 16; W->buf = (i32 *)xrealloc(W->buf, W->cap * 4); }
+    W->buf[W->cnt++] = id;
+}
+/* points on the open segment A -> B (hanging nodes), by bisection: a finer point implies the midpoint */
+static void walk_side(facewalk *W, const i32 *A, const i32 *B) {
+    i32 M[3] = {(A[0] + B[0]) / 2, (A[1] + B[1]) / 2, (A[2] + B[2]) / 2};
+    i32 len = abs(B[0] - A[0]) + abs(B[1] - A[1]) + abs(B[2] - A[2]);
+    if (len < 2 || (len & 1)) return;
+    i32 id = point_id(W, M[0], M[1], M[2]);
+    if (id < 0) return;
+    walk_side(W, A, M);
+    walk_push(W, id);
+    walk_side(W, M, B);
+}
+/* integer box of a cell in fine units */
+static inline void cell_box(const mg_oct *o, i64 c, i32 *lo, i32 *hi) {
+    int sh = o->lcap - o->cellLvl[c];
+    lo[0] = o->cx[c] << sh; lo[1] = o->cy[c] << sh; lo[2] = o->cz[c] << sh;
+    hi[0] = (o->cx[c] + 1) << sh; hi[1] = (o->cy[c] + 1) << sh; hi[2] = (o->cz[c] + zext(o, c)) << sh;
+}
+
 /*
  * Build the polyMesh-style arrays for the current octree.
  * flags: bit0 = build point addressing (pointCells, cellPoints, bndPoint, pointLevel).
@@ -607,9 +641,9 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
             m->Sf[3 * i] = S[0]; m->Sf[3 * i + 1] = S[1]; m->Sf[3 * i + 2] = S[2];
         }
     }
-    free(bside);
+    u8 *bsideKeep = bside;
 
-    if (!(flags & 1)) { free(nb); return m; }
+    if (!(flags & 1)) { free(nb); free(bsideKeep); return m; }
 
     /* --- points: lattice points first (blockMesh order), then hanging/new points in order of
            first appearance over ascending cells */
@@ -688,6 +722,83 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
         free(fill);
     }
     m->cpOff = cpo; m->cpPts = cpp;
+    /* --- 3-D faces() and edges() (flag 4): perimeter walk of every face with hanging nodes */
+    if ((flags & 4) && !o->dim2) {
+        facewalk W = {o, &H, npx, npy, FS, NULL, 0, 0};
+        i64 nfaces = f + b;
+        m->faceOff = (i32 *)xcalloc(nfaces + 1, 4);
+        for (i64 i = 0; i < nfaces; i++) {
+            i32 lo[3], hi[3];
+            cell_box(o, own[i], lo, hi);
+            int axis = -1;
+            if (i < f) {
+                i32 lq[3], hq[3];
+                cell_box(o, nei[i], lq, hq);
+                for (int a = 0; a < 3; a++) {
+                    if (hi[a] == lq[a]) { axis = a; lo[a] = hi[a]; }
+                    else if (hq[a] == lo[a]) { axis = a; hi[a] = lo[a]; }
+                    else { if (lq[a] > lo[a]) lo[a] = lq[a]; if (hq[a] < hi[a]) hi[a] = hq[a]; }
+                }
+            }
+            if (i >= f) {
+                int side = bsideKeep[i - f];
+                axis = side >> 1;
+                if (side & 1) lo[axis] = hi[axis]; else hi[axis] = lo[axis];
+            }
+            int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+            i32 C[4][3];
+            for (int k = 0; k < 4; k++) {
+                C[k][axis] = lo[axis];
+                C[k][a1] = (k == 0 || k == 3) ? lo[a1] : hi[a1];
+                C[k][a2] = (k < 2) ? lo[a2] : hi[a2];
+            }
+            for (int k = 0; k < 4; k++) {
+                walk_push(&W, point_id(&W, C[k][0], C[k][1], C[k][2]));
+                walk_side(&W, C[k], C[(k + 1) & 3]);
+            }
+            m->faceOff[i + 1] = (i32)W.cnt;
+        }
+        m->facePts = W.buf;
+        /* edges: consecutive perimeter points, unique */
+        phash E; ph_init(&E, W.cnt + 16);
+        i64 ne = 0, ecap = 0;
+        i32 *ep = NULL; u8 *be = NULL;
+        for (i64 i = 0; i < nfaces; i++) {
+            i32 s0 = m->faceOff[i], s1 = m->faceOff[i + 1];
+            for (i32 k = s0; k < s1; k++) {
+                i32 a = m->facePts[k], c2 = m->facePts[k + 1 < s1 ? k + 1 : s0];
+                i32 lo_ = a < c2 ? a : c2, hi_ = a < c2 ? c2 : a;
+                uint64_t key = ((uint64_t)(uint32_t)lo_ << 32) | (uint32_t)hi_;
+                i32 id = ph_get(&E, key);
+                if (id < 0) {
+                    if (ne == ecap) { ecap = ecap ? ecap * 2 : 1 << 16; ep = (i32 *)xrealloc(ep, ecap * 8); be = (u8 *)xrealloc(be, ecap); }
+                    id = (i32)ne++;
+                    ph_put(&E, key, id);
+                    ep[2 * id] = lo_; ep[2 * id + 1] = hi_; be[id] = 0;
+                }
+                if (i >= f) be[id] = 1;
+            }
+        }
+        ph_free(&E);
+        m->nedge = ne; m->edgePts = ep; m->bndEdge = be;
+        m->ecOff = (i32 *)xcalloc(ne + 1, 4);
+        for (int pass = 0; pass < 2; pass++) {
+            for (i64 e = 0; e < ne; e++) {
+                i32 q = ep[2 * e], partner = ep[2 * e + 1];
+                i32 a = pcnt[q], ae = pcnt[q + 1], c2 = pcnt[partner], ce = pcnt[partner + 1];
+                i32 k = pass ? m->ecOff[e] : 0;
+                while (a < ae && c2 < ce) {
+                    i32 pa = m->pcCells[a], pc = m->pcCells[c2];
+                    if (pa == pc) { if (pass) m->ecCells[k] = pa; k++; a++; c2++; } else if (pa < pc) a++; else c2++;
+                }
+                if (!pass) m->ecOff[e + 1] = k;
+            }
+            if (!pass) {
+                for (i64 e = 0; e < ne; e++) m->ecOff[e + 1] += m->ecOff[e];
+                m->ecCells = (i32 *)xmalloc((m->ecOff[ne] ? m->ecOff[ne] : 1) * 4);
+            }
+        }
+    }
     /* --- 2-D: edges normal to the plane (one per point column and layer), edgeCells = cells around it */
     if (o->dim2) {
         i64 ne = 0;
@@ -726,7 +837,7 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
         }
     }
     ph_free(&H);
-    free(nb);
+    free(nb); free(bsideKeep);
     return m;
 }
 

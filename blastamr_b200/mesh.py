@@ -98,6 +98,8 @@ class PolyMesh:
     ec_off: Optional[np.ndarray] = None        # edgeCells CSR
     ec_cells: Optional[np.ndarray] = None
     bnd_edge: Optional[np.ndarray] = None      # uint8 [n_edges]
+    face_off: Optional[np.ndarray] = None      # faces() CSR [f+b+1]
+    face_pts: Optional[np.ndarray] = None
     _handle: Optional[int] = field(default=None, repr=False)
 
     # patch arrays in the layout the C-ABI takes
@@ -122,9 +124,9 @@ class PolyMesh:
 
 def _wrap(handle: int, names: Sequence[str], copy: bool = False) -> PolyMesh:
     L = lib()
-    sz = np.zeros(10, dtype=np.int64)
+    sz = np.zeros(11, dtype=np.int64)
     L.mg_mesh_sizes(handle, sz.ctypes.data)
-    n, f, b, p, npatch, nsplit, nnz_pc, nnz_cp, nedge, nnz_ec = (int(x) for x in sz)
+    n, f, b, p, npatch, nsplit, nnz_pc, nnz_cp, nedge, nnz_ec, nnz_fp = (int(x) for x in sz)
 
     def arr(idx, dtype, count, shape=None):
         ptr = L.mg_mesh_array(handle, idx)
@@ -158,6 +160,7 @@ def _wrap(handle: int, names: Sequence[str], copy: bool = False) -> PolyMesh:
         n_edges=nedge, edge_pts=arr(25, np.int32, 2 * nedge, (nedge, 2)) if nedge else None,
         ec_off=arr(26, np.int32, nedge + 1) if nedge else None, ec_cells=arr(27, np.int32, nnz_ec) if nedge else None,
         bnd_edge=arr(28, np.uint8, nedge) if nedge else None,
+        face_off=arr(29, np.int32, f + b + 1) if nnz_fp else None, face_pts=arr(30, np.int32, nnz_fp) if nnz_fp else None,
     )
     if m.split_parent is None:
         m.split_parent = np.zeros(0, np.int32)
@@ -208,8 +211,9 @@ class Octree:
     def ncells(self) -> int:
         return int(lib().mg_oct_ncells(self._h))
 
-    def build(self, points: bool = True, copy: bool = False, geometry: bool = False) -> PolyMesh:
-        h = lib().mg_oct_build(self._h, (1 if points else 0) | (2 if geometry else 0))
+    def build(self, points: bool = True, copy: bool = False, geometry: bool = False, faces: bool = False) -> PolyMesh:
+        """faces=True additionally builds mesh.faces() and mesh.edges()/edgeCells() (3-D; polyRefiner inputs)"""
+        h = lib().mg_oct_build(self._h, (1 if points or faces else 0) | (2 if geometry else 0) | (4 if faces else 0))
         return _wrap(h, self.names, copy=copy)
 
     def refine(self, cells: np.ndarray) -> np.ndarray:

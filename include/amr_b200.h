@@ -73,7 +73,9 @@ enum { AMR_PATCH_PLAIN = 0, AMR_PATCH_EMPTY = 1, AMR_PATCH_PROCESSOR = 2 };
 enum {
     AMR_REFINER_HEX3D = 0,   /* hexRefiner + hexRef3D */
     AMR_REFINER_HEX2D = 1,   /* hexRefiner + hexRef2D (split elements are edges; needs amr_mesh_set_edges) */
-    AMR_REFINER_POLY3D = 2,  /* polyRefiner + polyhedralRefinement                 -- next */
+    AMR_REFINER_POLY3D = 2,  /* polyRefiner + polyhedralRefinement (needs amr_mesh_set_edges with ALL mesh edges and
+                                amr_mesh_set_faces; single rank: the point sync of the unrefinement buffer layers,
+                                syncTools::syncPointList fvMeshRefiner.C:952-958, is not on the device path yet) */
     AMR_REFINER_POLY2D = 3   /* polyRefiner + prismatic2DRefinement                -- next */
 };
 
@@ -121,6 +123,17 @@ int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_t *pcCel
    mesh_.faceEdges() at hexRef2D.C:2296-2311).  Only needed with AMR_REFINER_HEX2D. */
 int amr_mesh_set_edges(amr_ctx *ctx, int64_t nEdges, const int32_t *edgePoints, const int32_t *ecOff,
                        const int32_t *ecCells, const uint8_t *bndEdge);
+
+/* mesh.faces() as CSR over all faces (faceOff[f+b+1], facePts): polyhedralRefinement derives its split
+   points from pointLevel and the faces (polyhedralRefinement.C:2110-2184).  Only with AMR_REFINER_POLY3D. */
+int amr_mesh_set_faces(amr_ctx *ctx, const int32_t *faceOff, const int32_t *facePts);
+
+/* options of the refiners that the reference reads from dynamicMeshDict */
+enum {
+    AMR_OPT_EDGE_BASED_CONSISTENCY = 0, /* `edgeBasedConsistency` (refinement.C:700-703), default 1 */
+    AMR_OPT_POLY_FORCE = 1              /* fvMeshRefiner::force_ as passed by fvMeshPolyRefiner.C:338, default 0 */
+};
+int amr_set_option(amr_ctx *ctx, int option, int64_t value);
 
 /* hexRef::cellLevel_/pointLevel_ and the refinement history arrays visibleCells_ and
    splitCells_[i].parent_ (hexRefRefinementHistory.H:299-310).  pointLevel, visibleCells,

@@ -78,6 +78,8 @@ typedef struct {
     const label *edgePts, *ecOff, *ecCells;
     const boolean *bndEdge;       /* edge used by a boundary face (mesh_.faceEdges()[bface]) */
     label *ceOff, *ceEdges;       /* derived: cellEdges() restricted to the listed edges */
+    /* mesh.faces() as CSR (polyhedralRefinement split-point rule) */
+    const label *faceOff, *facePts;
     /* fvMesh geometry (Lohner only) */
     const scalar *weights, *Sf, *magSf, *deltaCoeffs, *V;
     /* derived: primitiveMesh::cells() */
@@ -157,6 +159,10 @@ OR_API void or_world_set_edges(or_world *w, int r, int64_t nedge, const label *e
     for (int64_t e = 0; e < nedge; e++)
         for (label i = ecOff[e]; i < ecOff[e + 1]; i++) m->ceEdges[fill[ecCells[i]]++] = (label)e;
     free(fill);
+}
+
+OR_API void or_world_set_faces(or_world *w, int r, const label *faceOff, const label *facePts) {
+    w->m[r].faceOff = faceOff; w->m[r].facePts = facePts;
 }
 
 OR_API void or_world_set_geometry(or_world *w, int r, const scalar *weights, const scalar *Sf, const scalar *magSf,
@@ -1041,6 +1047,236 @@ OR_API int or_hex2d_select_unrefine(const or_world *w, const scalar *const *erro
         free(pFld); free(isSplit);
     }
     return or_consistent_unrefinement_edges(w, unrefEdge);
+}
+
+/* ======================================================================================= */
+/* polyRefiner (fvMeshPolyRefiner + refinement + polyhedralRefinement), 3-D                */
+/* ======================================================================================= */
+
+/* refinement::faceConsistentRefinement, refinement.C:202-302 (counts real flips: boolList::set/unset
+   return whether the value changed) */
+static int64_t poly_face_consistent_refinement(const or_world *w, int maxSet, boolean **refineCell) {
+    int R = w->R;
+    int64_t nChangedTot = 0;
+    label **neiLevel = (label **)malloc(sizeof(label *) * R);
+    for (int r = 0; r < R; r++) {
+        const or_mesh *m = &w->m[r];
+        boolean *rc = refineCell[r];
+        for (int64_t faceI = 0; faceI < m->f; faceI++) {
+            label own = m->owner[faceI], nei = m->neighbour[faceI];
+            label ownLevel = m->cellLevel[own] + rc[own];
+            label neiL = m->cellLevel[nei] + rc[nei];
+            if (ownLevel > (neiL + 1)) {
+                if (maxSet) { nChangedTot += !rc[nei]; rc[nei] = 1; } else { nChangedTot += rc[own]; rc[own] = 0; }
+            } else if (neiL > (ownLevel + 1)) {
+                if (maxSet) { nChangedTot += !rc[own]; rc[own] = 1; } else { nChangedTot += rc[nei]; rc[nei] = 0; }
+            }
+        }
+        neiLevel[r] = (label *)malloc(sizeof(label) * (size_t)(m->b + 1));
+        for (int64_t i = 0; i < m->b; i++) { label own = m->owner[i + m->f]; neiLevel[r][i] = m->cellLevel[own] + rc[own]; }
+    }
+    swap_boundary_label(w, neiLevel);
+    for (int r = 0; r < R; r++) {
+        const or_mesh *m = &w->m[r];
+        boolean *rc = refineCell[r];
+        for (int64_t i = 0; i < m->b; i++) {
+            label own = m->owner[i + m->f];
+            label ownLevel = m->cellLevel[own] + rc[own];
+            if (ownLevel > (neiLevel[r][i] + 1)) { if (!maxSet) { nChangedTot += rc[own]; rc[own] = 0; } }
+            else if (neiLevel[r][i] > (ownLevel + 1)) { if (maxSet) { nChangedTot += !rc[own]; rc[own] = 1; } }
+        }
+        free(neiLevel[r]);
+    }
+    free(neiLevel);
+    return nChangedTot;
+}
+
+/* refinement::edgeConsistentRefinement, refinement.C:305-387 (local: every unordered pair of edgeCells) */
+static int64_t poly_edge_consistent_refinement(const or_world *w, int maxSet, boolean **refineCell) {
+    int64_t nChanged = 0;
+    for (int r = 0; r < w->R; r++) {
+        const or_mesh *m = &w->m[r];
+        boolean *rc = refineCell[r];
+        for (int64_t edgeI = 0; edgeI < m->nedge; edgeI++)
+            for (label i = m->ecOff[edgeI]; i < m->ecOff[edgeI + 1]; i++) {
+                label cellI = m->ecCells[i];
+                for (label j = i + 1; j < m->ecOff[edgeI + 1]; j++) {
+                    label cellJ = m->ecCells[j];
+                    label cellILevel = m->cellLevel[cellI] + rc[cellI];
+                    label cellJLevel = m->cellLevel[cellJ] + rc[cellJ];
+                    if (cellILevel > (cellJLevel + 1)) {
+                        if (maxSet) { nChanged += !rc[cellJ]; rc[cellJ] = 1; } else { nChanged += rc[cellI]; rc[cellI] = 0; }
+                    } else if (cellJLevel > (cellILevel + 1)) {
+                        if (maxSet) { nChanged += !rc[cellI]; rc[cellI] = 1; } else { nChanged += rc[cellJ]; rc[cellJ] = 0; }
+                    }
+                }
+            }
+    }
+    return nChanged;
+}
+
+/* refinement::consistentRefinement, refinement.C:744-810 */
+OR_API int or_poly_consistent_refinement(const or_world *w, int maxSet, int edgeBasedConsistency, boolean **refineCell) {
+    int sweeps = 0;
+    while (1) {
+        int64_t nChanged = 0;
+        if (edgeBasedConsistency) nChanged += poly_edge_consistent_refinement(w, maxSet, refineCell);
+        nChanged += poly_face_consistent_refinement(w, maxSet, refineCell);
+        sweeps++;
+        if (nChanged == 0) break;
+    }
+    return sweeps;
+}
+
+/* Refinement branch of fvMeshPolyRefiner::refine, fvMeshPolyRefiner.C:321-370: selectRefineCandidates,
+   layers x extendMarkedCells(.., force_), clear protectedPatches, base selectRefineCells
+   (fvMeshRefiner.C:190-219), refinement::consistentRefinement(.., true). */
+OR_API int or_poly_select_refine(const or_world *w, const scalar *const *error, scalar lowerRefineLevel, scalar upperRefineLevel,
+                                 label *const *maxCellLevel, int nRefinementBufferLayers, int force,
+                                 const label *protectedPatchIds, int nProtectedPatches, int edgeBasedConsistency,
+                                 boolean **refineCell, boolean **refineSet) {
+    int R = w->R;
+    for (int r = 0; r < R; r++)
+        for (int64_t c = 0; c < w->m[r].n; c++)
+            refineCell[r][c] = (error[r][c] >= lowerRefineLevel) && (error[r][c] <= upperRefineLevel);
+    for (int i = 0; i < nRefinementBufferLayers; i++) extend_marked_cells(w, refineCell, maxCellLevel, i == 0, force);
+    for (int r = 0; r < R; r++) {
+        const or_mesh *m = &w->m[r];
+        for (int k = 0; k < nProtectedPatches; k++) {
+            int q = protectedPatchIds[k];
+            for (label i = 0; i < m->patchSize[q]; i++) refineCell[r][m->owner[m->patchStart[q] + i]] = 0;
+        }
+        for (int64_t c = 0; c < m->n; c++) refineSet[r][c] = (m->cellLevel[c] < maxCellLevel[r][c]) && refineCell[r][c];
+    }
+    return or_poly_consistent_refinement(w, 1, edgeBasedConsistency, refineSet);
+}
+
+/* polyhedralRefinement::consistentUnrefinement PART 1 (polyhedralRefinement.C:2096-2184): split point <=>
+   pointLevel >= 1, every point of every face using it has the same pointLevel, not on a boundary face */
+OR_API void or_poly_split_points(const or_world *w, int r, boolean *isSplit) {
+    const or_mesh *m = &w->m[r];
+    boolean *bad = (boolean *)calloc((size_t)(m->p + 1), 1);
+    int64_t nf = m->f + m->b;
+    /* a point is rejected iff one of its faces carries a point of a different level <=> it lies on a face
+       whose points do not all share one level (then every point of that face sees a different level) */
+    for (int64_t faceI = 0; faceI < nf; faceI++) {
+        label s = m->faceOff[faceI], e = m->faceOff[faceI + 1];
+        int uniform = 1;
+        for (label j = s + 1; j < e; j++) if (m->pointLevel[m->facePts[j]] != m->pointLevel[m->facePts[s]]) { uniform = 0; break; }
+        if (!uniform) for (label j = s; j < e; j++) bad[m->facePts[j]] = 1;
+        if (faceI >= m->f) for (label j = s; j < e; j++) bad[m->facePts[j]] = 1;   /* boundary faces, :2175-2184 */
+    }
+    for (int64_t pointI = 0; pointI < m->p; pointI++) isSplit[pointI] = (m->pointLevel[pointI] >= 1) && !bad[pointI];
+    free(bad);
+}
+
+/* refinement::faceConsistentUnrefinement (refinement.C:390-508) + edgeConsistentUnrefinement (:511-604),
+   maxSet = false.  Returns nChanged, or -1 on the reference's "problem" FatalError. */
+static int64_t poly_consistent_unrefinement_sweep(const or_world *w, int edgeBasedConsistency, boolean **unrefineCell) {
+    int R = w->R;
+    int64_t nChanged = 0;
+    int fail = 0;
+    label **neiLevel = (label **)malloc(sizeof(label *) * R);
+    for (int r = 0; r < R; r++) {
+        const or_mesh *m = &w->m[r];
+        boolean *uc = unrefineCell[r];
+        for (int64_t faceI = 0; faceI < m->f && !fail; faceI++) {
+            label own = m->owner[faceI], nei = m->neighbour[faceI];
+            label ownLevel = m->cellLevel[own] - uc[own], neiL = m->cellLevel[nei] - uc[nei];
+            if (ownLevel < (neiL - 1)) { if (!uc[own]) fail = 1; else { uc[own] = 0; nChanged++; } }
+            else if (neiL < (ownLevel - 1)) { if (!uc[nei]) fail = 1; else { uc[nei] = 0; nChanged++; } }
+        }
+        neiLevel[r] = (label *)malloc(sizeof(label) * (size_t)(m->b + 1));
+        for (int64_t i = 0; i < m->b; i++) { label own = m->owner[i + m->f]; neiLevel[r][i] = m->cellLevel[own] - uc[own]; }
+    }
+    swap_boundary_label(w, neiLevel);
+    for (int r = 0; r < R; r++) {
+        const or_mesh *m = &w->m[r];
+        boolean *uc = unrefineCell[r];
+        for (int64_t i = 0; i < m->b && !fail; i++) {
+            label own = m->owner[i + m->f];
+            label ownLevel = m->cellLevel[own] - uc[own];
+            if (ownLevel < (neiLevel[r][i] - 1)) { if (!uc[own]) fail = 1; else { uc[own] = 0; nChanged++; } }
+        }
+        free(neiLevel[r]);
+        if (edgeBasedConsistency)
+            for (int64_t edgeI = 0; edgeI < m->nedge && !fail; edgeI++)
+                for (label i = m->ecOff[edgeI]; i < m->ecOff[edgeI + 1] && !fail; i++) {
+                    label cellI = m->ecCells[i];
+                    for (label j = i + 1; j < m->ecOff[edgeI + 1]; j++) {
+                        label cellJ = m->ecCells[j];
+                        label cellILevel = m->cellLevel[cellI] - uc[cellI], cellJLevel = m->cellLevel[cellJ] - uc[cellJ];
+                        if (cellILevel < (cellJLevel - 1)) { if (!uc[cellI]) { fail = 1; break; } uc[cellI] = 0; nChanged++; }
+                        else if (cellJLevel < (cellILevel - 1)) { if (!uc[cellJ]) { fail = 1; break; } uc[cellJ] = 0; nChanged++; }
+                    }
+                }
+    }
+    free(neiLevel);
+    return fail ? -1 : nChanged;
+}
+
+/* Unrefinement branch of fvMeshPolyRefiner::refine (fvMeshPolyRefiner.C:419-472): layers x
+   extendMarkedCellsAcrossPoints, set protectedPatches, selectUnrefinePoints (:48-96) ->
+   polyhedralRefinement::consistentUnrefinement (polyhedralRefinement.C:2077-2362). */
+OR_API int or_poly_select_unrefine(const or_world *w, const scalar *const *error, scalar unrefineLevel,
+                                   int nUnrefinementBufferLayers, const label *protectedPatchIds, int nProtectedPatches,
+                                   int edgeBasedConsistency, const label *const *pointGlobal, int64_t nGlobalPoints,
+                                   boolean **refineCell, boolean **unrefPoint, boolean **splitPoint) {
+    int R = w->R;
+    for (int i = 0; i < nUnrefinementBufferLayers; i++) extend_across_points(w, refineCell, pointGlobal, nGlobalPoints);
+    for (int r = 0; r < R; r++) {
+        const or_mesh *m = &w->m[r];
+        for (int k = 0; k < nProtectedPatches; k++) {
+            int q = protectedPatchIds[k];
+            for (label i = 0; i < m->patchSize[q]; i++) refineCell[r][m->owner[m->patchStart[q] + i]] = 1;
+        }
+    }
+    for (int r = 0; r < R; r++) {
+        const or_mesh *m = &w->m[r];
+        scalar *pFld = (scalar *)malloc(sizeof(scalar) * (size_t)(m->p + 1));
+        boolean *isSplit = (boolean *)malloc((size_t)(m->p + 1));
+        or_max_cell_field(w, r, error[r], pFld);
+        or_poly_split_points(w, r, isSplit);
+        for (int64_t pointI = 0; pointI < m->p; pointI++) {
+            int cand = 0;
+            if (pFld[pointI] < unrefineLevel) {                       /* selectUnrefinePoints */
+                int hasMarked = 0;
+                for (label j = m->pcOff[pointI]; j < m->pcOff[pointI + 1]; j++)
+                    if (refineCell[r][m->pcCells[j]]) { hasMarked = 1; break; }
+                cand = !hasMarked;
+            }
+            unrefPoint[r][pointI] = cand && isSplit[pointI];          /* PART 2 */
+        }
+        if (splitPoint && splitPoint[r]) memcpy(splitPoint[r], isSplit, (size_t)m->p);
+        free(pFld); free(isSplit);
+    }
+    /* PART 4 */
+    boolean **uc = (boolean **)malloc(sizeof(boolean *) * R);
+    for (int r = 0; r < R; r++) uc[r] = (boolean *)malloc((size_t)(w->m[r].n + 1));
+    int sweeps = 0, fail = 0;
+    while (1) {
+        for (int r = 0; r < R; r++) {
+            const or_mesh *m = &w->m[r];
+            memset(uc[r], 0, (size_t)m->n);
+            for (int64_t pointI = 0; pointI < m->p; pointI++)
+                if (unrefPoint[r][pointI])
+                    for (label j = m->pcOff[pointI]; j < m->pcOff[pointI + 1]; j++) uc[r][m->pcCells[j]] = 1;
+        }
+        int64_t nChanged = poly_consistent_unrefinement_sweep(w, edgeBasedConsistency, uc);
+        if (nChanged < 0) { fail = 1; break; }
+        sweeps++;
+        if (nChanged == 0) break;
+        for (int r = 0; r < R; r++) {
+            const or_mesh *m = &w->m[r];
+            for (int64_t pointI = 0; pointI < m->p; pointI++)
+                if (unrefPoint[r][pointI])
+                    for (label j = m->pcOff[pointI]; j < m->pcOff[pointI + 1]; j++)
+                        if (!uc[r][m->pcCells[j]]) { unrefPoint[r][pointI] = 0; break; }
+        }
+    }
+    for (int r = 0; r < R; r++) free(uc[r]);
+    free(uc);
+    return fail ? -1 : sweeps;
 }
 
 /* hexRef::checkRefinementLevels (2:1 part), hexRef.C:2934-3025.  Returns #violating faces. */

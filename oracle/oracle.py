@@ -50,6 +50,16 @@ def lib():
         L.or_hex2d_select_unrefine.restype = C.c_int
         L.or_hex2d_select_unrefine.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.or_world_set_faces.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.or_poly_consistent_refinement.restype = C.c_int
+        L.or_poly_consistent_refinement.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.or_poly_select_refine.restype = C.c_int
+        L.or_poly_select_refine.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.or_poly_split_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.or_poly_select_unrefine.restype = C.c_int
+        L.or_poly_select_unrefine.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.or_world_set_geometry.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.or_estimate_lohner.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.or_range_thresholds.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
@@ -116,6 +126,10 @@ class World:
                 a = [_i32(m.edge_pts), _i32(m.ec_off), _i32(m.ec_cells), np.ascontiguousarray(m.bnd_edge, dtype=np.uint8)]
                 self._keep += a
                 L.or_world_set_edges(self._h, r, m.n_edges, *[v.ctypes.data for v in a])
+            if getattr(m, "face_off", None) is not None:
+                a = [_i32(m.face_off), _i32(m.face_pts)]
+                self._keep += a
+                L.or_world_set_faces(self._h, r, a[0].ctypes.data, a[1].ctypes.data)
             if getattr(m, "Sf", None) is not None and m.vol is not None:
                 a = [np.ascontiguousarray(v, dtype=np.float64) for v in (m.weights, m.Sf, m.magSf, m.delta_coeffs, m.vol)]
                 self._keep += a
@@ -200,6 +214,38 @@ class World:
                                               _pp(refine_cell), _pp(up), _pp(sp))
         if sweeps < 0:
             raise RuntimeError("reference FatalError 'problem' (hexRef3D.C:1811)")
+        return up, sp, sweeps
+
+    # ---- polyRefiner (3-D)
+    def poly_consistent_refinement(self, flags, max_set=True, edge_based=True) -> int:
+        return lib().or_poly_consistent_refinement(self._h, 1 if max_set else 0, 1 if edge_based else 0, _pp(flags))
+
+    def poly_select_refine(self, err, max_cell_level, n_layers, lower=SQRT_SMALL, upper=GREAT, force=False,
+                           protected_patch_ids=(), edge_based=True):
+        mcl = [np.full(m.n, max_cell_level, dtype=np.int32) if np.isscalar(max_cell_level) else _i32(max_cell_level[r])
+               for r, m in enumerate(self.meshes)]
+        rc = [np.zeros(m.n, dtype=np.uint8) for m in self.meshes]
+        rs = [np.zeros(m.n, dtype=np.uint8) for m in self.meshes]
+        ids = _i32(protected_patch_ids)
+        sweeps = lib().or_poly_select_refine(self._h, _pp(err), lower, upper, _pp(mcl), n_layers, 1 if force else 0, ids.ctypes.data,
+                                             len(ids), 1 if edge_based else 0, _pp(rc), _pp(rs))
+        return rc, rs, sweeps
+
+    def poly_split_points(self, r):
+        out = np.zeros(self.meshes[r].p, dtype=np.uint8)
+        lib().or_poly_split_points(self._h, r, out.ctypes.data)
+        return out
+
+    def poly_select_unrefine(self, err, refine_cell, n_layers, unrefine_level=-SQRT_SMALL, protected_patch_ids=(), edge_based=True):
+        up = [np.zeros(m.p, dtype=np.uint8) for m in self.meshes]
+        sp = [np.zeros(m.p, dtype=np.uint8) for m in self.meshes]
+        ids = _i32(protected_patch_ids)
+        if self.R > 1:
+            raise NotImplementedError("poly unrefinement across ranks needs the shared-point plan (syncPointList)")
+        sweeps = lib().or_poly_select_unrefine(self._h, _pp(err), unrefine_level, n_layers, ids.ctypes.data, len(ids),
+                                               1 if edge_based else 0, None, 0, _pp(refine_cell), _pp(up), _pp(sp))
+        if sweeps < 0:
+            raise RuntimeError("reference FatalError 'problem' (refinement.C:417)")
         return up, sp, sweeps
 
     def hex2d_select_unrefine(self, err, refine_cell, n_layers, unrefine_level=-SQRT_SMALL, protected_cell=None,

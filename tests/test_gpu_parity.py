@@ -72,14 +72,17 @@ def test_select_refine_box(ctx, O, layers, maxlev):
     assert np.array_equal(flags_to_list(rs[0]), cells)
 
 
-def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, protected=(), thr=0.01, kind="delta"):
+def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, protected=(), thr=0.01, kind="delta",
+             refiner="hex"):
     """A multi-step AMR run; every stage is executed by the oracle and by the GPU and compared.
     Works for the 3-D cutter (split points) and the 2-D cutter (split edges, oc.two_d)."""
     two_d = getattr(oc, "two_d", False)
-    rk = 1 if two_d else 0       # AMR_REFINER_HEX2D / AMR_REFINER_HEX3D
+    poly = refiner == "poly"
+    rk = 2 if poly else (1 if two_d else 0)       # AMR_REFINER_POLY3D / HEX2D / HEX3D
+    build = (lambda: oc.build(faces=True)) if poly else oc.build
     stats = dict(refined=0, unrefined=0, sweeps=[])
     for step in range(steps):
-        m = oc.build()
+        m = build()
         w = O.World([m])
         ctx.set_mesh(m)
         x = field_fn(m.cc, step)
@@ -95,9 +98,12 @@ def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, prot
             c_gpu = ctx.protect_patches(pid, 1 + (maxlev - 1) * max(layers_ref, 1), e_gpu)
             assert c_ref[0] == c_gpu
             assert np.array_equal(e_ref[0], e_gpu)
-        rc, rs, sw_ref = w.hex_select_refine(e_ref, maxlev, layers_ref, protected_patch_ids=pid)
+        if poly:
+            rc, rs, sw_ref = w.poly_select_refine(e_ref, maxlev, layers_ref, protected_patch_ids=pid)
+        else:
+            rc, rs, sw_ref = w.hex_select_refine(e_ref, maxlev, layers_ref, protected_patch_ids=pid)
         rc_g = np.zeros(m.n, np.uint8)
-        cells, sw = ctx.select_refine(e_gpu, maxlev, layers_ref, protected_patch_ids=pid, refine_cell_out=rc_g)
+        cells, sw = ctx.select_refine(e_gpu, maxlev, layers_ref, protected_patch_ids=pid, refine_cell_out=rc_g, kind=rk)
         assert np.array_equal(rc[0], rc_g), f"step {step}: refineCell differs"
         ref_cells = flags_to_list(rs[0])
         assert np.array_equal(ref_cells, cells), f"step {step}: cellsToRefine differs"
@@ -120,7 +126,7 @@ def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, prot
             lv_ref = O.update_levels(cell_map, m.cell_level, rs[0])
             lv_gpu = ctx.update_levels(cell_map, m.cell_level, rs[0])
             assert np.array_equal(lv_ref, lv_gpu)
-            m = oc.build()
+            m = build()
             assert np.array_equal(lv_ref, m.cell_level)     # the topology engine agrees with L2
             w = O.World([m])
             ctx.set_mesh(m)
@@ -129,7 +135,9 @@ def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, prot
             stats["refined"] += len(cells)
         # unrefinement on the (possibly new) mesh
         rc_ref = refine_cell.copy()
-        if two_d:
+        if poly:
+            up, sp, _ = w.poly_select_unrefine([err], [rc_ref], layers_unref, protected_patch_ids=pid)
+        elif two_d:
             up, sp, _ = w.hex2d_select_unrefine([err], [rc_ref], layers_unref, protected_patch_ids=pid)
         else:
             up, sp, _ = w.hex_select_unrefine([err], [rc_ref], layers_unref, protected_patch_ids=pid)
@@ -194,6 +202,22 @@ def test_amr_loop_2d_hexRef2D(ctx, O, n0, maxlev, layers):
     st = amr_loop(ctx, O, oc, moving_front_2d(0.06), steps=6, maxlev=maxlev, layers_ref=layers[0], layers_unref=layers[1],
                   kind="codedDelta")
     assert st["refined"] > 0 and st["unrefined"] > 0
+
+
+@pytest.mark.parametrize("n0,maxlev,layers", [(8, 2, (1, 2)), (10, 3, (2, 2))])
+def test_amr_loop_polyRefiner(ctx, O, n0, maxlev, layers):
+    """polyRefiner + polyhedralRefinement decision path on 3-D meshes with hanging nodes: face AND edge
+    consistency (refinement.C:202-387, 390-604), point buffer layers, split points from pointLevel"""
+    oc = M.Octree(n0, n0, n0, (1.0, 1.0, 1.0), maxlev)
+    st = amr_loop(ctx, O, oc, moving_front(0.06), steps=6, maxlev=maxlev, layers_ref=layers[0], layers_unref=layers[1],
+                  refiner="poly")
+    assert st["refined"] > 0 and st["unrefined"] > 0
+    # the edge rule really is stronger than the face rule on these meshes
+    m = oc.build(faces=True)
+    lv = m.cell_level
+    for e in range(0, m.n_edges, 7):
+        cs = m.ec_cells[m.ec_off[e]:m.ec_off[e + 1]]
+        assert lv[cs].max() - lv[cs].min() <= 1
 
 
 def test_amr_loop_protected_patches(ctx, O):
