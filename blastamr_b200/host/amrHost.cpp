@@ -227,7 +227,9 @@ static bool refinersRegistered = []() {
             throw FatalError(std::string(nm) + ": this refiner's edge-consistency sweeps are not on the device path yet (SURVEY.md 8a B2/B4)");
         };
     };
-    fvMeshRefiner::dictionaryConstructorTable()["polyRefiner"] = notYet("polyRefiner");
+    fvMeshRefiner::dictionaryConstructorTable()["polyRefiner"] = [](adaptiveFvMesh &m, const dictionary &d) {
+        return std::unique_ptr<fvMeshRefiner>(new fvMeshPolyRefiner(m, d));
+    };
     fvMeshRefiner::dictionaryConstructorTable()["directionalRefiner"] = notYet("directionalRefiner");
     return true;
 }();
@@ -288,7 +290,7 @@ bool fvMeshHexRefiner::refine(const scalarField &errorIn, const labelList &maxCe
     boolList refineCell((size_t)mesh.nCells, 0);
     labelList pp;
     for (const word &nm : protectedPatchNames_) { label id = mesh.findPatchID(nm); if (id >= 0) pp.push_back(id); }
-    const int kind = amesh_.refinerKind();
+    const int kind = amesh_.kindOverride >= 0 ? amesh_.kindOverride : amesh_.refinerKind();
 
     if (canRefine(true)) {
         labelList maxRefinement(maxCellLevel);
@@ -350,6 +352,25 @@ bool fvMeshHexRefiner::refine(const scalarField &errorIn, const labelList &maxCe
     return hasChanged;
 }
 
+// fvMeshPolyRefiner::readDict, fvMeshPolyRefiner.C:260-301
+void fvMeshPolyRefiner::readDict(const dictionary &dict) {
+    fvMeshRefiner::readDict(dict);
+    if (nRefinementBufferLayers_ < 3 && amesh_.mesh().nSolutionD == 2) nRefinementBufferLayers_ = 3;   // :267-283
+    if (nUnrefinementBufferLayers_ < 2) nUnrefinementBufferLayers_ = 2;                                // :287-300
+}
+// fvMeshPolyRefiner::refine, fvMeshPolyRefiner.C:304-489: same driver shape as the hex refiner; the cutter-specific
+// parts (edge consistency, point buffer layers, pointLevel split points) live behind AMR_REFINER_POLY3D
+bool fvMeshPolyRefiner::refine(const scalarField &error, const labelList &maxCellLevel, const scalar lo, const scalar hi,
+                               const scalar unref) {
+    if (amesh_.mesh().nSolutionD == 2)
+        throw FatalError("polyRefiner on a 2-D mesh uses prismatic2DRefinement, which is not on the device path (SURVEY.md 8a B4)");
+    amesh_.check(amr_set_option(amesh_.gpu(), AMR_OPT_EDGE_BASED_CONSISTENCY, dict_.lookupOrDefaultBool("edgeBasedConsistency", true)),
+                 "refinement::edgeBasedConsistency");
+    amesh_.check(amr_set_option(amesh_.gpu(), AMR_OPT_POLY_FORCE, force_ ? 1 : 0), "fvMeshPolyRefiner::force_");
+    amesh_.kindOverride = AMR_REFINER_POLY3D;
+    return fvMeshHexRefiner::refine(error, maxCellLevel, lo, hi, unref);
+}
+
 // ------------------------------------------------------------------------------------------------ adaptiveFvMesh
 
 adaptiveFvMesh::adaptiveFvMesh(const std::string &text, int device) {
@@ -384,6 +405,7 @@ void adaptiveFvMesh::meshChanged() {
     check(amr_mesh_set(gpu_, m.nCells, m.nInternalFaces, m.nBoundaryFaces, m.nPoints, m.owner.data(), m.neighbour.data(), (int)m.patches.size(),
                        st.data(), sz.data(), ty.data(), nb.data()), "amr_mesh_set");
     if (!m.pcOff.empty()) check(amr_mesh_set_points(gpu_, m.pcOff.data(), m.pcCells.data(), m.bndPoint.data()), "amr_mesh_set_points");
+    if (!m.faceOff.empty()) check(amr_mesh_set_faces(gpu_, m.faceOff.data(), m.facePts.data()), "amr_mesh_set_faces");
     if (m.nEdges > 0) check(amr_mesh_set_edges(gpu_, m.nEdges, m.edgePts.data(), m.ecOff.data(), m.ecCells.data(), m.bndEdge.data()), "amr_mesh_set_edges");
     if (!m.Sf.empty()) check(amr_mesh_set_geometry(gpu_, m.weights.data(), m.Sf.data(), m.magSf.data(), m.deltaCoeffs.data(), m.V.data()), "amr_mesh_set_geometry");
     if (!m.cellLevel.empty())

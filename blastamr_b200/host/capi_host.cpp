@@ -64,6 +64,7 @@ API int amrhost_set_mesh(amrhost *h, int64_t n, int64_t f, int64_t b, int64_t p,
         m.pcOff.clear(); m.pcCells.clear(); m.bndPoint.clear();
         m.nEdges = 0; m.edgePts.clear(); m.ecOff.clear(); m.ecCells.clear(); m.bndEdge.clear();
         m.Sf.clear(); m.weights.clear(); m.magSf.clear(); m.deltaCoeffs.clear(); m.V.clear();
+        m.faceOff.clear(); m.facePts.clear();
     })
 }
 API int amrhost_set_points(amrhost *h, const int32_t *off, const int32_t *cells, const uint8_t *bnd) {
@@ -77,6 +78,13 @@ API int amrhost_set_edges(amrhost *h, int64_t ne, const int32_t *ep, const int32
         fvMeshLite &m = h->mesh->mesh();
         m.nEdges = ne; m.edgePts.assign(ep, ep + 2 * ne); m.ecOff.assign(off, off + ne + 1); m.ecCells.assign(cells, cells + off[ne]);
         m.bndEdge.assign(bnd, bnd + ne);
+    })
+}
+API int amrhost_set_faces(amrhost *h, const int32_t *off, const int32_t *pts) {
+    GUARD({
+        fvMeshLite &m = h->mesh->mesh();
+        const int64_t nf = m.nInternalFaces + m.nBoundaryFaces;
+        m.faceOff.assign(off, off + nf + 1); m.facePts.assign(pts, pts + off[nf]);
     })
 }
 API int amrhost_set_geometry(amrhost *h, const double *w, const double *Sf, const double *magSf, const double *dc, const double *V) {

@@ -31,6 +31,7 @@ def lib():
         L.amrhost_set_mesh.argtypes = [vp, i64, i64, i64, i64, vp, vp, C.c_int, C.POINTER(C.c_char_p), vp, vp, vp, vp, C.c_int]
         L.amrhost_set_points.argtypes = [vp, vp, vp, vp]
         L.amrhost_set_edges.argtypes = [vp, i64, vp, vp, vp, vp]
+        L.amrhost_set_faces.argtypes = [vp, vp, vp]
         L.amrhost_set_geometry.argtypes = [vp] * 6
         L.amrhost_set_levels.argtypes = [vp, vp, vp, vp, vp, i64]
         L.amrhost_set_map.argtypes = [vp, i64, i64, vp, vp]
@@ -69,7 +70,7 @@ def selection_table(which: str):
 class AdaptiveFvMesh:
     """adaptiveFvMesh + a solver's time loop, with the octree engine as polyTopoChange."""
 
-    def __init__(self, dict_text: str, octree: Octree, device: int = 0, geometry: bool = False):
+    def __init__(self, dict_text: str, octree: Octree, device: int = 0, geometry: bool = False, faces: bool = False):
         self.L = lib()
         h = C.c_void_p()
         if self.L.amrhost_create(dict_text.encode(), device, C.byref(h)) != 0:
@@ -77,12 +78,13 @@ class AdaptiveFvMesh:
         self._h = h
         self.oc = octree
         self.geometry = geometry
+        self.faces = faces
         self.mesh: Optional[PolyMesh] = None
         self.time_index = 0
         self._cb_r = TOPO_CB(self._on_refine)
         self._cb_u = TOPO_CB(self._on_unrefine)
         self.L.amrhost_set_topo_callbacks(h, self._cb_r, self._cb_u, None)
-        self._install(octree.build(geometry=geometry))
+        self._install(octree.build(geometry=geometry, faces=faces))
         self._ck(self.L.amrhost_mesh_changed(h))
         self.history = []
 
@@ -108,6 +110,8 @@ class AdaptiveFvMesh:
         if m.n_edges:
             self._ck(self.L.amrhost_set_edges(self._h, m.n_edges, m.edge_pts.ctypes.data, m.ec_off.ctypes.data, m.ec_cells.ctypes.data,
                                               m.bnd_edge.ctypes.data))
+        if m.face_off is not None:
+            self._ck(self.L.amrhost_set_faces(self._h, m.face_off.ctypes.data, m.face_pts.ctypes.data))
         if self.geometry:
             self._ck(self.L.amrhost_set_geometry(self._h, m.weights.ctypes.data, m.Sf.ctypes.data, m.magSf.ctypes.data,
                                                  m.delta_coeffs.ctypes.data, m.vol.ctypes.data))
@@ -122,7 +126,7 @@ class AdaptiveFvMesh:
             n_old = self.mesh.n
             cm = self.oc.refine(cells)
             rev = np.arange(n_old, dtype=np.int32)
-            self._install(self.oc.build(geometry=self.geometry))
+            self._install(self.oc.build(geometry=self.geometry, faces=self.faces))
             self._ck(self.L.amrhost_set_map(self._h, n_old, len(cm), cm.ctypes.data, rev.ctypes.data))
             self.history.append(("refine", int(n)))
             return 0
@@ -135,7 +139,7 @@ class AdaptiveFvMesh:
             el = np.ctypeslib.as_array(elems, shape=(n,)).copy()
             n_old = self.mesh.n
             cm, rev = self.oc.unrefine(self.mesh, el)
-            self._install(self.oc.build(geometry=self.geometry))
+            self._install(self.oc.build(geometry=self.geometry, faces=self.faces))
             self._ck(self.L.amrhost_set_map(self._h, n_old, len(cm), cm.ctypes.data, rev.ctypes.data))
             self.history.append(("unrefine", int(n)))
             return 0

@@ -31,6 +31,7 @@ int amrhost_set_mesh(amrhost *h, int64_t n, int64_t f, int64_t b, int64_t p, con
 int amrhost_set_points(amrhost *h, const int32_t *pcOff, const int32_t *pcCells, const uint8_t *bndPoint);
 int amrhost_set_edges(amrhost *h, int64_t nEdges, const int32_t *edgePts, const int32_t *ecOff, const int32_t *ecCells,
                       const uint8_t *bndEdge);
+int amrhost_set_faces(amrhost *h, const int32_t *faceOff, const int32_t *facePts);
 int amrhost_set_geometry(amrhost *h, const double *weights, const double *Sf, const double *magSf, const double *deltaCoeffs,
                          const double *V);
 int amrhost_set_levels(amrhost *h, const int32_t *cellLevel, const int32_t *pointLevel, const int32_t *visibleCells,

@@ -128,6 +128,31 @@ def test_update_matches_oracle_driver():
 
 
 @pytest.mark.gpu
+def test_polyRefiner_keyword_through_update():
+    """`refiner polyRefiner;` (what the reference's tutorials and tests ship) on a 3-D mesh: update() refines the
+    box, keeps face AND edge 2:1, and unrefines again; nUnrefinementBufferLayers is raised to 2 (fvMeshPolyRefiner.C:287-300)"""
+    text = (DICT % dict(layers=1, maxlev=2, prot="")).replace("refiner         hexRefiner;", "refiner         polyRefiner;")
+    oc = M.Octree(20, 20, 5, (0.1, 0.1, 0.01), 2)
+    am = hostapi.AdaptiveFvMesh(text, oc, faces=True)
+    n0 = am.n_cells
+    for _ in range(2):
+        am.set_field("test", cases.box_field(am.mesh.cc))
+        assert am.update()
+    n1 = am.n_cells
+    assert n1 > n0 and am.mesh.cell_level.max() == 2
+    m = am.mesh
+    lv = m.cell_level
+    for e in range(m.n_edges):
+        cs = m.ec_cells[m.ec_off[e]:m.ec_off[e + 1]]
+        assert lv[cs].max() - lv[cs].min() <= 1
+    for _ in range(4):
+        am.set_field("test", np.zeros(am.n_cells))
+        am.update()
+    assert am.n_cells < n1
+    am.close()
+
+
+@pytest.mark.gpu
 def test_unknown_names_and_missing_keywords_raise():
     oc = M.Octree(4, 4, 4, max_level=1)
     am = hostapi.AdaptiveFvMesh("errorEstimator nonsense; lowerRefineLevel 1; unrefineLevel 1; maxRefinement 1;", oc)
