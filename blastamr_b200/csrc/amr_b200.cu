@@ -483,7 +483,7 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
         } else {
             FAIL(AMR_ERR_ARG, "amr_estimate: estimator kind not available on the device path");
         }
-        if (errorOut && !devOut) CK(cudaMemcpyAsync(errorOut, target, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (errorOut && !devOut) { CK(cudaMemcpyAsync(errorOut, target, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream)); ctx->hostTouched = true; }
     }
     CK(cudaGetLastError());
     return flushOuts(ctx);
@@ -521,7 +521,7 @@ AMR_API int amr_estimate_lohner(amr_ctx *ctx, const double *x, const double *xBo
                           (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, target);
         else LAUNCH((k_lohner<false>), gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
                     (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, target);
-        if (errorOut && !devOut) CK(cudaMemcpyAsync(errorOut, target, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (errorOut && !devOut) { CK(cudaMemcpyAsync(errorOut, target, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream)); ctx->hostTouched = true; }
     }
     CK(cudaGetLastError());
     return flushOuts(ctx);
@@ -665,14 +665,18 @@ static int finishList(amr_ctx *ctx, ListJob *job, int flagSlot, int *flagValue, 
     if (flagSlot >= 0 && flagValue) *flagValue = ctx->hFlags[flagSlot];
     const int32_t total = ctx->hFlags[8];
     if (nOut) *nOut = total;
-    if (copyOut && job->hostOut && total > 0)
+    if (copyOut && job->hostOut && total > 0) {
         CK(cudaMemcpyAsync(job->userOut, job->dList, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->hostTouched = true;
+    }
     return AMR_OK;
 }
 static int finishListCopy(amr_ctx *ctx, ListJob *job) {
     const int32_t total = ctx->hFlags[8];
-    if (job->hostOut && total > 0)
+    if (job->hostOut && total > 0) {
         CK(cudaMemcpyAsync(job->userOut, job->dList, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->hostTouched = true;
+    }
     return AMR_OK;
 }
 static int emitList(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *userOut, int64_t *nOut) {
@@ -941,8 +945,11 @@ AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nOld, int64_t nNew, cons
         // and make it the resident marking by pointer swap
         u8 *dNew = ctx->flagA;
         if (nNew) LAUNCH(k_remap_refine_cell, gridFor(nNew, kThreads * 4), kThreads, nNew, dMap, dRev, dOld, dNew);
-        if (newRefineCellOut && nNew) CK(cudaMemcpyAsync(newRefineCellOut, dNew, (size_t)nNew, cudaMemcpyDefault, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        if (newRefineCellOut && nNew) {
+            CK(cudaMemcpyAsync(newRefineCellOut, dNew, (size_t)nNew, cudaMemcpyDefault, ctx->stream));
+            if (!isDevicePtr(newRefineCellOut)) ctx->hostTouched = true;
+        }
+        if (ctx->hostTouched) CK(cudaStreamSynchronize(ctx->stream));
         std::swap(ctx->flagA, ctx->refineCell);
         ctx->refineCellN = nNew;
     } else {

@@ -119,6 +119,7 @@ struct amr_ctx {
     size_t arenaUsed = 0;       // within arena.back()
     struct PendingOut { void *host; const void *dev; size_t bytes; };
     std::vector<PendingOut> outs;
+    bool hostTouched = false;   // this call copied from/to host memory: it must be complete on return
 };
 
 #define CK(call)                                                                              \
@@ -196,6 +197,7 @@ static void arenaReset(amr_ctx *ctx) {
     }
     ctx->arenaUsed = 0;
     ctx->outs.clear();
+    ctx->hostTouched = false;
 }
 static int arenaAlloc(amr_ctx *ctx, void **out, size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
@@ -220,6 +222,7 @@ static int stageIn(amr_ctx *ctx, const T *ptr, int64_t count, const T **dev) {
     void *q;
     TRY(arenaAlloc(ctx, &q, sizeof(T) * (size_t)(count > 0 ? count : 1)));
     if (count > 0) CK(cudaMemcpyAsync(q, ptr, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->hostTouched = true;
     *dev = (const T *)q;
     return AMR_OK;
 }
@@ -246,11 +249,14 @@ static int stageInOut(amr_ctx *ctx, T *ptr, int64_t count, T **dev) {
     ctx->outs.push_back({(void *)ptr, q, sizeof(T) * (size_t)(count > 0 ? count : 0)});
     return AMR_OK;
 }
-// copy staged outputs back (optionally only the first `bytesOverride` bytes of the last one) and sync
+// Copy staged outputs back and make the call complete with respect to the host.  A call whose data
+// pointers were all device pointers is only stream-ordered (normal CUDA semantics for device buffers):
+// no host synchronisation, the next call on the context's stream sees the results.
 static int flushOuts(amr_ctx *ctx) {
+    const bool sync = ctx->hostTouched || !ctx->outs.empty();
     for (auto &o : ctx->outs)
         if (o.bytes) CK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->outs.clear();
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (sync) CK(cudaStreamSynchronize(ctx->stream));
     return AMR_OK;
 }
