@@ -471,8 +471,18 @@ def main():
         dom = max(single, key=lambda k: calls[k])
         kname, kbytes, kform = single[dom]
         k_ms = calls[dom]
+        # DRAM traffic per launch of that kernel from the committed ncu capture of this same command line
+        traffic = None
+        tpath = ROOT / "profiles" / "r1_traffic.json"
+        if tpath.exists() and N == 400 and world == 1:
+            try:
+                tj = json.loads(tpath.read_text())["traffic_bytes_per_launch"]
+                key = {"k_map_field<3>": "k_map_field<3>", "k_map_field<1>": "k_map_field<1>"}.get(kname, "kp_estimate<0, 1, 0>")
+                traffic = tj.get(key)
+            except Exception:
+                traffic = None
         roof = {"bound": "hbm", "kernel": kname, "achieved": (kbytes / 1e9) / (k_ms / 1e3), "peak": peak, "unit": "GB/s",
-                "frac": (kbytes / 1e9) / (k_ms / 1e3) / peak, "traffic": None, "algorithmic_bytes": kbytes,
+                "frac": (kbytes / 1e9) / (k_ms / 1e3) / peak, "traffic": traffic, "algorithmic_bytes": kbytes,
                 "formula": kform, "ms": k_ms, "peak_source": peak_src,
                 "other_kernels": {single[k][0]: {"ms": calls[k], "GBps": (single[k][1] / 1e9) / (calls[k] / 1e3),
                                                  "frac": (single[k][1] / 1e9) / (calls[k] / 1e3) / peak} for k in single if k != dom},

@@ -25,8 +25,11 @@
  * FatalErrorInFunction ... abort(FatalError), like the reference's own invariants
  * (hexRef3D.C:1811-1815).
  *
- * Threading: one context per MPI rank / GPU, calls are synchronous with respect to the host
- * (results are complete on return) exactly like the reference methods they replace.  With a
+ * Threading: one context per MPI rank / GPU.  A call that was given any HOST data pointer is
+ * synchronous (its results are complete on return, exactly like the reference method it replaces);
+ * a call whose data pointers are all device pointers is stream-ordered on the context's stream
+ * (amr_set_stream), the normal CUDA contract for device buffers.  Scalar outputs (counts) always
+ * force completion.  With a
  * communicator attached, all ranks must enter the collective-bearing calls together (they
  * replace syncTools::* / reduce() calls that are already collective).
  *
