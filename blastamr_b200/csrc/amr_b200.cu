@@ -111,6 +111,8 @@ AMR_API int amr_ctx_destroy(amr_ctx *ctx) {
     cudaFree(ctx->dFlags); cudaFree(ctx->dCount);
     cudaFreeHost(ctx->hFlags); cudaFreeHost(ctx->hCount);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->upStream) cudaStreamDestroy(ctx->upStream);
+    if (ctx->downStream) cudaStreamDestroy(ctx->downStream);
     delete ctx;
     return AMR_OK;
 }
@@ -1174,10 +1176,59 @@ AMR_API int amr_check_levels(amr_ctx *ctx, const int32_t *cellLevel, int64_t *nB
 
 // ============================================================================ stage 4
 
+// Host -> host mapping of a large field: the old field goes up in chunks on one stream while mapped
+// chunks of the new field come down on another, so both PCIe directions are busy at once.  A chunk of
+// new cells may start as soon as the old rows it reads (max of cellMap over the chunk) have arrived;
+// for the maps of hexRef (identity prefix + appended children) that is almost immediately.
+static int mapFieldHostPipelined(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nComp,
+                                 const double *oldF, double *newF) {
+    const int64_t chunk = (int64_t)1 << 22;                    // 4 M cells per chunk
+    const int64_t nUp = (nOld + chunk - 1) / chunk, nDown = (nNew + chunk - 1) / chunk;
+    if (!ctx->upStream) CK(cudaStreamCreateWithFlags(&ctx->upStream, cudaStreamNonBlocking));
+    if (!ctx->downStream) CK(cudaStreamCreateWithFlags(&ctx->downStream, cudaStreamNonBlocking));
+    const int32_t *dMap = nullptr;
+    TRY(stageIn(ctx, cellMap, nNew, &dMap));
+    void *q;
+    TRY(arenaAlloc(ctx, &q, (size_t)nOld * nComp * 8)); double *dOld = (double *)q;
+    TRY(arenaAlloc(ctx, &q, (size_t)nNew * nComp * 8)); double *dNew = (double *)q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(nDown + 1) * 4)); int *dMax = (int *)q;
+    CK(cudaMemsetAsync(dMax, 0xff, (size_t)(nDown + 1) * 4, ctx->stream));      // -1
+    LAUNCH(k_chunk_max_src, gridFor(nNew), kThreads, nNew, chunk, dMap, dMax);
+    std::vector<int> hMax((size_t)nDown);
+    CK(cudaMemcpyAsync(hMax.data(), dMax, (size_t)nDown * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<cudaEvent_t> ev((size_t)nUp);
+    for (int64_t k = 0; k < nUp; k++) {
+        const int64_t r0 = k * chunk, r1 = std::min(nOld, r0 + chunk);
+        CK(cudaMemcpyAsync(dOld + r0 * nComp, oldF + r0 * nComp, (size_t)(r1 - r0) * nComp * 8, cudaMemcpyHostToDevice, ctx->upStream));
+        CK(cudaEventCreateWithFlags(&ev[(size_t)k], cudaEventDisableTiming));
+        CK(cudaEventRecord(ev[(size_t)k], ctx->upStream));
+    }
+    int64_t waited = -1;
+    for (int64_t j = 0; j < nDown; j++) {
+        const int64_t i0 = j * chunk, i1 = std::min(nNew, i0 + chunk);
+        const int64_t need = hMax[(size_t)j] < 0 ? -1 : hMax[(size_t)j] / chunk;     // last upload chunk this one reads
+        if (need >= nUp) FAIL(AMR_ERR_ARG, "amr_map_field: cellMap entry out of range");
+        for (int64_t k = waited + 1; k <= need; k++) CK(cudaStreamWaitEvent(ctx->downStream, ev[(size_t)k], 0));
+        if (need > waited) waited = need;
+        const int64_t items = (i1 - i0) * nComp;
+        k_map_field_range<<<gridFor(items, kThreads * kMapItems), kThreads, 0, ctx->downStream>>>(i0, i1, nComp, dMap, dOld, dNew);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(newF + i0 * nComp, dNew + i0 * nComp, (size_t)items * 8, cudaMemcpyDeviceToHost, ctx->downStream));
+    }
+    CK(cudaStreamSynchronize(ctx->upStream));
+    CK(cudaStreamSynchronize(ctx->downStream));
+    for (auto &e : ev) cudaEventDestroy(e);
+    CK(cudaGetLastError());
+    return AMR_OK;
+}
+
 AMR_API int amr_map_field(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nComp, const double *oldF,
                           double *newF, int mode, const int32_t *reverseCellMap, const double *volOld) {
     ENTER();
     if (!cellMap || !oldF || !newF || nComp < 1) FAIL(AMR_ERR_ARG, "amr_map_field: null pointer / bad nComp");
+    if (mode == AMR_MAP_DIRECT && !isDevicePtr(oldF) && !isDevicePtr(newF) && nNew * nComp >= ((int64_t)1 << 23))
+        return mapFieldHostPipelined(ctx, nOld, nNew, cellMap, nComp, oldF, newF);
     const int32_t *dMap = nullptr;
     const double *dOld = nullptr;
     double *dNew = nullptr;

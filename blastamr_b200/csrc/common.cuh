@@ -46,6 +46,7 @@ struct Sell {
 struct amr_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t upStream = nullptr, downStream = nullptr;   // host<->host field mapping: both PCIe directions at once
     bool ownStream = true;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;

@@ -848,6 +848,39 @@ k_map_field_n(int64_t nNew, int nc, const label *__restrict__ cellMap, const dou
     for (int t = 0; t < kMapItems; t++) if (src[t] >= 0) newF[e0 + (int64_t)t * kThreads] = v[t];
 }
 
+// range variant for the host<->host pipeline of amr_map_field: maps new cells [i0, i1)
+__global__ void __launch_bounds__(kThreads)
+k_map_field_range(int64_t i0, int64_t i1, int nc, const label *__restrict__ cellMap, const double *__restrict__ oldF,
+                  double *__restrict__ newF) {
+    const int64_t total = (i1 - i0) * nc;
+    const int64_t t0 = (int64_t)blockIdx.x * (kThreads * kMapItems) + threadIdx.x;
+    int64_t src[kMapItems], dst[kMapItems];
+#pragma unroll
+    for (int t = 0; t < kMapItems; t++) {
+        const int64_t e = t0 + (int64_t)t * kThreads;
+        if (e < total) {
+            const int64_t i = i0 + e / nc;
+            const int64_t k = e % nc;
+            src[t] = (int64_t)cellMap[i] * nc + k;
+            dst[t] = i * nc + k;
+        } else src[t] = -1;
+    }
+    double v[kMapItems];
+#pragma unroll
+    for (int t = 0; t < kMapItems; t++) if (src[t] >= 0) v[t] = oldF[src[t]];
+#pragma unroll
+    for (int t = 0; t < kMapItems; t++) if (src[t] >= 0) newF[dst[t]] = v[t];
+}
+// largest source row of every chunk of new cells (decides how much of the old field must have arrived)
+__global__ void __launch_bounds__(kThreads)
+k_chunk_max_src(int64_t nNew, int64_t chunk, const label *__restrict__ cellMap, int *__restrict__ maxSrc) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int v = (i < nNew) ? cellMap[i] : -1;
+    // all threads of a CTA belong to one chunk when chunk % kThreads == 0
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+    if ((threadIdx.x & 31) == 0 && i < nNew) atomicMax(&maxSrc[i / chunk], v);
+}
+
 // conservative merge: new master value = sum V_old*old / sum V_old over the 8 merged cells,
 // accumulated in ascending old label.  merged cells of master m are found through mergeOff/mergeIdx
 // (a CSR built from reverseCellMap, rows ascending), so the sum order is deterministic.

@@ -147,3 +147,20 @@ def test_device_pointer_arguments(ctx, O):
     ctx.map_field(cm, f3, n_old=m.n, n_new=cm.numel(), ncomp=3, out=out)
     torch.cuda.synchronize()
     assert torch.equal(out, f3[cm.long()])
+
+
+@pytest.mark.parametrize("kind", ["refinement", "random"])
+def test_large_host_map_uses_both_pcie_directions(ctx, kind):
+    """host -> host mapping above the pipelining threshold (chunked upload/download on two streams)"""
+    rng = np.random.default_rng(5)
+    n_old, ncomp = 3_000_000, 3
+    if kind == "refinement":
+        parents = np.sort(rng.choice(n_old, 40_000, replace=False)).astype(np.int32)
+        cm = np.concatenate([np.arange(n_old, dtype=np.int32), np.repeat(parents, 7)])
+    else:
+        cm = rng.integers(0, n_old, size=n_old + 123_457, dtype=np.int32)
+    old = rng.random((n_old, ncomp))
+    got = ctx.map_field(cm, old, ncomp=ncomp)
+    assert np.array_equal(got, old[cm])
+    got1 = ctx.map_field(cm, old[:, 0].copy(), ncomp=1)
+    assert np.array_equal(got1, old[cm, 0])
