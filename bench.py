@@ -418,8 +418,7 @@ def main():
             # stay on the device between the calls, as INTEGRATION.md prescribes for the drop-in.
             ctx.estimate("delta", xh.numpy(), thresholds=thr, out=err0)
             cl, _ = ctx.select_refine(err0, MAX_LEVEL, LAYERS_REF, cells_out=cells_h2, refine_cell_out=rc0)
-            ctx.map_field(cmh.numpy(), xh.numpy(), n_old=n, n_new=n_new, ncomp=1, out=n1h.numpy())
-            ctx.map_field(cmh.numpy(), f3h.numpy(), n_old=n, n_new=n_new, ncomp=3, out=n3h.numpy())
+            ctx.map_fields(cmh.numpy(), [xh.numpy(), f3h.numpy()], n, n_new, [1, 3], [n1h.numpy(), n3h.numpy()])   # fvMesh::mapFields
             ctx.map_field(cell_map, err0, n_old=n, n_new=n_new, ncomp=1, out=err1)
             ctx1.remap_refine_cell(cell_map, rev_map, refine_cell=rc0)
             pl, _ = ctx1.select_unrefine(err1, LAYERS_UNREF, elems_out=pts_h)
@@ -435,7 +434,7 @@ def main():
         z.record()
         barrier()
         e2e_ms = a.elapsed_time(z) / args.e2e_steps
-        h2d = (8 * n) + 2 * (4 * n_new) + (8 * n + 24 * n)      # x; cellMap (per field); scalar + vector field
+        h2d = (8 * n) + (4 * n_new) + (8 * n + 24 * n)          # x; cellMap; scalar + vector field
         d2h = (4 * ncl) + (8 * n_new + 24 * n_new) + (4 * npl)  # cellsToRefine; mapped fields; split points
         e2e = (e2e_ms, h2d, d2h)
 

@@ -59,6 +59,7 @@ _SIGS = {
     "amr_check_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_map_field": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_void_p]),
+    "amr_map_fields": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_update_levels": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5),
     "amr_launch_count": (C.c_int64, [C.c_void_p]),
     "amr_device_bytes": (C.c_int64, [C.c_void_p]),
@@ -310,6 +311,15 @@ class Context:
         self._ck(self.L.amr_map_field(self._h, n_old, n_new, _ptr(cell_map), ncomp, _ptr(old), _ptr(out), mode,
                                       _ptr(reverse_map), _ptr(vol_old)))
         return out
+
+    def map_fields(self, cell_map, olds, n_old, n_new, ncomps, outs):
+        """fvMesh::mapFields over a list of registered fields (one shared cellMap)"""
+        k = len(olds)
+        nc = (C.c_int * k)(*[int(c) for c in ncomps])
+        po = (C.c_void_p * k)(*[_ptr(a) for a in olds])
+        pn = (C.c_void_p * k)(*[_ptr(a) for a in outs])
+        self._ck(self.L.amr_map_fields(self._h, n_old, n_new, _ptr(cell_map), k, nc, po, pn))
+        return outs
 
     def update_levels(self, cell_map, old_level=None, refined_old=None, unrefined_old=None):
         out = np.empty(len(cell_map), dtype=np.int32)

@@ -1180,8 +1180,8 @@ AMR_API int amr_check_levels(amr_ctx *ctx, const int32_t *cellLevel, int64_t *nB
 // chunks of the new field come down on another, so both PCIe directions are busy at once.  A chunk of
 // new cells may start as soon as the old rows it reads (max of cellMap over the chunk) have arrived;
 // for the maps of hexRef (identity prefix + appended children) that is almost immediately.
-static int mapFieldHostPipelined(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nComp,
-                                 const double *oldF, double *newF) {
+static int mapFieldsHostPipelined(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nFields,
+                                  const int *nComps, const double *const *oldFs, double *const *newFs) {
     const int64_t chunk = (int64_t)1 << 22;                    // 4 M cells per chunk
     const int64_t nUp = (nOld + chunk - 1) / chunk, nDown = (nNew + chunk - 1) / chunk;
     if (!ctx->upStream) CK(cudaStreamCreateWithFlags(&ctx->upStream, cudaStreamNonBlocking));
@@ -1189,38 +1189,79 @@ static int mapFieldHostPipelined(amr_ctx *ctx, int64_t nOld, int64_t nNew, const
     const int32_t *dMap = nullptr;
     TRY(stageIn(ctx, cellMap, nNew, &dMap));
     void *q;
-    TRY(arenaAlloc(ctx, &q, (size_t)nOld * nComp * 8)); double *dOld = (double *)q;
-    TRY(arenaAlloc(ctx, &q, (size_t)nNew * nComp * 8)); double *dNew = (double *)q;
     TRY(arenaAlloc(ctx, &q, (size_t)(nDown + 1) * 4)); int *dMax = (int *)q;
     CK(cudaMemsetAsync(dMax, 0xff, (size_t)(nDown + 1) * 4, ctx->stream));      // -1
     LAUNCH(k_chunk_max_src, gridFor(nNew), kThreads, nNew, chunk, dMap, dMax);
     std::vector<int> hMax((size_t)nDown);
     CK(cudaMemcpyAsync(hMax.data(), dMax, (size_t)nDown * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<cudaEvent_t> ev((size_t)nUp);
-    for (int64_t k = 0; k < nUp; k++) {
-        const int64_t r0 = k * chunk, r1 = std::min(nOld, r0 + chunk);
-        CK(cudaMemcpyAsync(dOld + r0 * nComp, oldF + r0 * nComp, (size_t)(r1 - r0) * nComp * 8, cudaMemcpyHostToDevice, ctx->upStream));
-        CK(cudaEventCreateWithFlags(&ev[(size_t)k], cudaEventDisableTiming));
-        CK(cudaEventRecord(ev[(size_t)k], ctx->upStream));
+    for (int64_t j = 0; j < nDown; j++)
+        if (hMax[(size_t)j] >= nOld) FAIL(AMR_ERR_ARG, "amr_map_field: cellMap entry out of range");
+    std::vector<cudaEvent_t> ev;
+    int rc = AMR_OK;
+    for (int fi = 0; fi < nFields && rc == AMR_OK; fi++) {
+        const int nComp = nComps[fi];
+        const double *oldF = oldFs[fi];
+        double *newF = newFs[fi];
+        double *dOld = nullptr, *dNew = nullptr;
+        if ((rc = arenaAlloc(ctx, &q, (size_t)nOld * nComp * 8)) != AMR_OK) break;
+        dOld = (double *)q;
+        if ((rc = arenaAlloc(ctx, &q, (size_t)nNew * nComp * 8)) != AMR_OK) break;
+        dNew = (double *)q;
+        const size_t e0 = ev.size();
+        for (int64_t k = 0; k < nUp; k++) {
+            const int64_t r0 = k * chunk, r1 = std::min(nOld, r0 + chunk);
+            CK(cudaMemcpyAsync(dOld + r0 * nComp, oldF + r0 * nComp, (size_t)(r1 - r0) * nComp * 8, cudaMemcpyHostToDevice, ctx->upStream));
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CK(cudaEventRecord(e, ctx->upStream));
+            ev.push_back(e);
+        }
+        int64_t waited = -1;
+        for (int64_t j = 0; j < nDown; j++) {
+            const int64_t i0 = j * chunk, i1 = std::min(nNew, i0 + chunk);
+            const int64_t need = hMax[(size_t)j] < 0 ? -1 : hMax[(size_t)j] / chunk;     // last upload chunk this one reads
+            for (int64_t k = waited + 1; k <= need; k++) CK(cudaStreamWaitEvent(ctx->downStream, ev[e0 + (size_t)k], 0));
+            if (need > waited) waited = need;
+            const int64_t items = (i1 - i0) * nComp;
+            k_map_field_range<<<gridFor(items, kThreads * kMapItems), kThreads, 0, ctx->downStream>>>(i0, i1, nComp, dMap, dOld, dNew);
+            ctx->launches++;
+            CK(cudaMemcpyAsync(newF + i0 * nComp, dNew + i0 * nComp, (size_t)items * 8, cudaMemcpyDeviceToHost, ctx->downStream));
+        }
     }
-    int64_t waited = -1;
-    for (int64_t j = 0; j < nDown; j++) {
-        const int64_t i0 = j * chunk, i1 = std::min(nNew, i0 + chunk);
-        const int64_t need = hMax[(size_t)j] < 0 ? -1 : hMax[(size_t)j] / chunk;     // last upload chunk this one reads
-        if (need >= nUp) FAIL(AMR_ERR_ARG, "amr_map_field: cellMap entry out of range");
-        for (int64_t k = waited + 1; k <= need; k++) CK(cudaStreamWaitEvent(ctx->downStream, ev[(size_t)k], 0));
-        if (need > waited) waited = need;
-        const int64_t items = (i1 - i0) * nComp;
-        k_map_field_range<<<gridFor(items, kThreads * kMapItems), kThreads, 0, ctx->downStream>>>(i0, i1, nComp, dMap, dOld, dNew);
-        ctx->launches++;
-        CK(cudaMemcpyAsync(newF + i0 * nComp, dNew + i0 * nComp, (size_t)items * 8, cudaMemcpyDeviceToHost, ctx->downStream));
-    }
-    CK(cudaStreamSynchronize(ctx->upStream));
-    CK(cudaStreamSynchronize(ctx->downStream));
+    cudaStreamSynchronize(ctx->upStream);
+    cudaStreamSynchronize(ctx->downStream);
     for (auto &e : ev) cudaEventDestroy(e);
+    if (rc != AMR_OK) return rc;
     CK(cudaGetLastError());
     return AMR_OK;
+}
+
+// fvMesh::mapFields maps EVERY registered field through one mapPolyMesh (MapGeometricFields over the object
+// registry): the batched entry point shares the cellMap and, for host buffers, keeps uploading field k+1 while
+// field k comes down.
+AMR_API int amr_map_fields(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nFields, const int *nComp,
+                           const double *const *oldF, double *const *newF) {
+    ENTER();
+    if (!cellMap || nFields < 0 || (nFields > 0 && (!nComp || !oldF || !newF))) FAIL(AMR_ERR_ARG, "amr_map_fields: bad arguments");
+    bool allHost = true;
+    for (int i = 0; i < nFields; i++) {
+        if (!oldF[i] || !newF[i] || nComp[i] < 1) FAIL(AMR_ERR_ARG, "amr_map_fields: null field / bad nComp");
+        if (isDevicePtr(oldF[i]) || isDevicePtr(newF[i])) allHost = false;
+    }
+    if (allHost && nFields > 0) return mapFieldsHostPipelined(ctx, nOld, nNew, cellMap, nFields, nComp, oldF, newF);
+    const int32_t *dMap = nullptr;
+    TRY(stageIn(ctx, cellMap, nNew, &dMap));
+    for (int i = 0; i < nFields; i++) {
+        const double *dOld = nullptr;
+        double *dNew = nullptr;
+        TRY(stageIn(ctx, oldF[i], nOld * nComp[i], &dOld));
+        TRY(stageOut(ctx, newF[i], nNew * nComp[i], &dNew));
+        const int64_t items = nNew * nComp[i];
+        if (items > 0) LAUNCH(k_map_field_range, gridFor(items, kThreads * kMapItems), kThreads, (int64_t)0, nNew, nComp[i], dMap, dOld, dNew);
+    }
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
 }
 
 AMR_API int amr_map_field(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nComp, const double *oldF,
@@ -1228,7 +1269,7 @@ AMR_API int amr_map_field(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_
     ENTER();
     if (!cellMap || !oldF || !newF || nComp < 1) FAIL(AMR_ERR_ARG, "amr_map_field: null pointer / bad nComp");
     if (mode == AMR_MAP_DIRECT && !isDevicePtr(oldF) && !isDevicePtr(newF) && nNew * nComp >= ((int64_t)1 << 23))
-        return mapFieldHostPipelined(ctx, nOld, nNew, cellMap, nComp, oldF, newF);
+        return mapFieldsHostPipelined(ctx, nOld, nNew, cellMap, 1, &nComp, &oldF, &newF);
     const int32_t *dMap = nullptr;
     const double *dOld = nullptr;
     double *dNew = nullptr;

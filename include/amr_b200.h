@@ -260,6 +260,12 @@ int amr_map_field(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellM
                   const double *oldF, double *newF, int mode, const int32_t *reverseCellMap,
                   const double *volOld);
 
+/* All registered fields through one map (what fvMesh::mapFields does): nFields fields with nComp[i]
+   interleaved components each, direct addressing.  Shares the cellMap upload; with host buffers field k+1
+   is uploaded while field k is downloaded (both PCIe directions busy). */
+int amr_map_fields(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nFields,
+                   const int *nComp, const double *const *oldF, double *const *newF);
+
 /* cellLevel through a refinement/unrefinement map (hexRef3D.C:1238,1255,2132-2135 +
    hexRef.C:2457-2485): new[i] = old[cellMap[i]] + refined[cellMap[i]] - unrefined[cellMap[i]].
    refinedOld / unrefinedOld: uint8 flags over old cells, nullable. */

@@ -164,3 +164,14 @@ def test_large_host_map_uses_both_pcie_directions(ctx, kind):
     assert np.array_equal(got, old[cm])
     got1 = ctx.map_field(cm, old[:, 0].copy(), ncomp=1)
     assert np.array_equal(got1, old[cm, 0])
+    # batched entry point (fvMesh::mapFields over all registered fields), host and device buffers
+    a, b = old[:, 1].copy(), old.copy()
+    oa, ob = np.empty(len(cm)), np.empty((len(cm), ncomp))
+    ctx.map_fields(cm, [a, b], n_old, len(cm), [1, ncomp], [oa, ob])
+    assert np.array_equal(oa, a[cm]) and np.array_equal(ob, b[cm])
+    import torch
+    cmd, ad, bd = torch.from_numpy(cm).cuda(), torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    oad, obd = torch.empty(len(cm), dtype=torch.float64, device="cuda"), torch.empty((len(cm), ncomp), dtype=torch.float64, device="cuda")
+    ctx.map_fields(cmd, [ad, bd], n_old, len(cm), [1, ncomp], [oad, obd])
+    torch.cuda.synchronize()
+    assert np.array_equal(oad.cpu().numpy(), oa) and np.array_equal(obd.cpu().numpy(), ob)
