@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "kernels_pipe.cuh"
 #include "lohner.cuh"
+#include "p2p.cuh"
 
 #include <algorithm>
 #include <new>
@@ -107,6 +108,13 @@ AMR_API int amr_ctx_destroy(amr_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     freeMesh(ctx);
     for (auto &bf : ctx->arena) cudaFree(bf.p);
+    if (ctx->usePeer) {
+        for (int r = 0; r < ctx->nranks; r++)
+            if (r != ctx->rank && ctx->peerHost[(size_t)r]) cudaIpcCloseMemHandle(ctx->peerHost[(size_t)r]);
+        cudaFree(ctx->peerDev); cudaFree(ctx->redVal);
+        delete (HaloPlan *)ctx->haloPlan;
+    }
+    if (ctx->region) cudaFree(ctx->region);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     cudaFree(ctx->dFlags); cudaFree(ctx->dCount);
     cudaFreeHost(ctx->hFlags); cudaFreeHost(ctx->hCount);
@@ -137,6 +145,8 @@ AMR_API int amr_comm_unique_id(void *id128) {
     return AMR_OK;
 }
 
+static int peerSetup(amr_ctx *ctx);
+
 AMR_API int amr_comm_init(amr_ctx *ctx, int nranks, int rank, const void *id128) {
     if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return AMR_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -144,7 +154,7 @@ AMR_API int amr_comm_init(amr_ctx *ctx, int nranks, int rank, const void *id128)
     memcpy(&id, id128, 128);
     NCK(ncclCommInitRank(&ctx->comm, nranks, id, rank));
     ctx->nranks = nranks; ctx->rank = rank;
-    return AMR_OK;
+    return peerSetup(ctx);
 }
 
 AMR_API int64_t amr_launch_count(const amr_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -158,12 +168,119 @@ AMR_API int64_t amr_device_bytes(const amr_ctx *ctx) { return ctx ? ctx->devByte
 
 // ============================================================================ halo swaps
 
+// ---- NVLink peer-memory transport (p2p.cuh) ----------------------------------------------------------
+
+static int peerCheckError(amr_ctx *ctx) {
+    if (!ctx->usePeer) return AMR_OK;
+    int e = 0;
+    CK(cudaMemcpyAsync(&e, ctx->region + offsetof(P2PRegionHeader, error), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (e) FAIL(AMR_ERR_STATE, "peer-memory halo swap timed out (a neighbour rank did not enter the same call)");
+    return AMR_OK;
+}
+
+// all ranks map each other's region; NCCL is only the transport for the 64-byte IPC handles
+static int peerSetup(amr_ctx *ctx) {
+    const char *mode = getenv("AMR_B200_HALO");
+    if (mode && strcmp(mode, "nccl") == 0) return AMR_OK;
+    if (ctx->nranks < 2 || ctx->nranks > kMaxRanks) return AMR_OK;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    int ok = 1;
+    if (cudaMalloc((void **)&ctx->region, (size_t)kRegionBytes) != cudaSuccess) { cudaGetLastError(); ctx->region = nullptr; ok = 0; }
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok) {
+        CK(cudaMemsetAsync(ctx->region, 0, (size_t)kRegionBytes, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (cudaIpcGetMemHandle(&mine, ctx->region) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    char *dSend = nullptr, *dAll = nullptr;
+    CK(cudaMalloc((void **)&dSend, 64));
+    CK(cudaMalloc((void **)&dAll, (size_t)64 * ctx->nranks));
+    CK(cudaMemcpyAsync(dSend, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+    NCK(ncclAllGather(dSend, dAll, 64, ncclUint8, ctx->comm, ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)ctx->nranks);
+    CK(cudaMemcpyAsync(all.data(), dAll, (size_t)64 * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->peerHost.assign((size_t)ctx->nranks, nullptr);
+    for (int r = 0; r < ctx->nranks && ok; r++) {
+        if (r == ctx->rank) { ctx->peerHost[(size_t)r] = ctx->region; continue; }
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        ctx->peerHost[(size_t)r] = (char *)p;
+    }
+    // everybody or nobody
+    CK(cudaMemcpyAsync(ctx->dFlags + 5, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    NCK(ncclAllReduce(ctx->dFlags + 5, ctx->dFlags + 5, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+    CK(cudaMemcpyAsync(&ok, ctx->dFlags + 5, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dSend); cudaFree(dAll);
+    if (!ok) {
+        for (int r = 0; r < ctx->nranks; r++)
+            if (r != ctx->rank && ctx->peerHost[(size_t)r]) cudaIpcCloseMemHandle(ctx->peerHost[(size_t)r]);
+        ctx->peerHost.clear();
+        return AMR_OK;      // NCCL path stays
+    }
+    CK(cudaMalloc((void **)&ctx->peerDev, sizeof(char *) * (size_t)ctx->nranks));
+    CK(cudaMemcpy(ctx->peerDev, ctx->peerHost.data(), sizeof(char *) * (size_t)ctx->nranks, cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void **)&ctx->redVal, 16));
+    ctx->haloPlan = new HaloPlan();
+    ctx->usePeer = true;
+    return AMR_OK;
+}
+
+// per-mesh plan: where my patch ranges land in each neighbour's boundary-face array
+static int peerPlan(amr_ctx *ctx) {
+    ctx->havePlan = false;
+    if (!ctx->usePeer || ctx->nCoupled == 0) return AMR_OK;
+    HaloPlan &P = *(HaloPlan *)ctx->haloPlan;
+    P.nPatch = 0; P.prefix[0] = 0;
+    int tooMany = 0;
+    for (const Patch &q : ctx->patches) {
+        if (q.type != AMR_PATCH_PROCESSOR || q.size == 0) continue;
+        if (P.nPatch >= 32) { tooMany = 1; break; }
+        const int k = P.nPatch++;
+        P.nbr[k] = q.nbr; P.offMine[k] = q.start - (int)ctx->f; P.size[k] = q.size; P.prefix[k + 1] = P.prefix[k] + q.size;
+    }
+    if (tooMany) return AMR_OK;
+    int32_t *dMine = nullptr, *dTheirs = nullptr;
+    CK(cudaMalloc((void **)&dMine, 32 * 4));
+    CK(cudaMalloc((void **)&dTheirs, 32 * 4));
+    CK(cudaMemcpyAsync(dMine, P.offMine, 32 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    NCK(ncclGroupStart());
+    for (int k = 0; k < P.nPatch; k++) {
+        NCK(ncclSend(dMine + k, 1, ncclInt32, P.nbr[k], ctx->comm, ctx->stream));
+        NCK(ncclRecv(dTheirs + k, 1, ncclInt32, P.nbr[k], ctx->comm, ctx->stream));
+    }
+    NCK(ncclGroupEnd());
+    CK(cudaMemcpyAsync(P.offTheirs, dTheirs, 32 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dMine); cudaFree(dTheirs);
+    ctx->havePlan = true;
+    return AMR_OK;
+}
+
 // syncTools::swapBoundaryFaceList / syncFaceList payload exchange: for every processor patch send
 // my boundary-face values [patchStart-f, +size) and receive the neighbour's into the same range
 // of `recv` (processor patch pairs list their faces in the same order on both sides).
 static int haloExchange(amr_ctx *ctx, const void *send, void *recv, size_t elemBytes) {
     if (ctx->nCoupled == 0) return AMR_OK;
     if (!ctx->comm) FAIL(AMR_ERR_STATE, "mesh has processor patches but no communicator (amr_comm_init) and no host-side neighbour values");
+    if (ctx->usePeer && ctx->havePlan && (int64_t)ctx->b * (int64_t)elemBytes <= kHaloCap) {
+        const HaloPlan &P = *(const HaloPlan *)ctx->haloPlan;
+        const unsigned epoch = ++ctx->haloEpoch;
+        const int parity = (int)(epoch & 1u);
+        const unsigned g = gridFor(P.prefix[P.nPatch]);
+        if (elemBytes == 1) k_halo_push<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, (const char *)send);
+        else if (elemBytes == 4) k_halo_push<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, (const char *)send);
+        else k_halo_push<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, (const char *)send);
+        k_halo_signal<<<1, 32, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch);
+        if (elemBytes == 1) k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
+        else if (elemBytes == 4) k_halo_unpack<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
+        else k_halo_unpack<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
+        ctx->launches += 3;
+        return AMR_OK;
+    }
     NCK(ncclGroupStart());
     for (const Patch &q : ctx->patches) {
         if (q.type != AMR_PATCH_PROCESSOR || q.size == 0) continue;
@@ -175,19 +292,50 @@ static int haloExchange(amr_ctx *ctx, const void *send, void *recv, size_t elemB
     return AMR_OK;
 }
 
+// all-rank reduction of one device word in place (reduce()/returnReduce()/gMin/gMax of the reference).
+// op: 0 max(int32), 1 sum(int64), 2 min(f64), 3 max(f64)
+static int allReduceWord(amr_ctx *ctx, void *word, int op) {
+    if (!ctx->comm || ctx->nranks < 2) return AMR_OK;
+    if (ctx->usePeer) {
+        const unsigned epoch = ++ctx->redEpoch;
+        const int parity = (int)(epoch & 1u);
+        const int is32 = (op == 0);
+        k_red_push<<<1, kMaxRanks, 0, ctx->stream>>>(ctx->peerDev, ctx->nranks, ctx->rank, parity, epoch, word, is32);
+        k_red_wait<<<1, kMaxRanks, 0, ctx->stream>>>(ctx->region, ctx->nranks, parity, epoch, op, word, is32);
+        ctx->launches += 2;
+        return AMR_OK;
+    }
+    if (op == 0) NCK(ncclAllReduce(word, word, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
+    else if (op == 1) NCK(ncclAllReduce(word, word, 1, ncclInt64, ncclSum, ctx->comm, ctx->stream));
+    else NCK(ncclAllReduce(word, word, 1, ncclFloat64, op == 2 ? ncclMin : ncclMax, ctx->comm, ctx->stream));
+    return AMR_OK;
+}
+
 // read the device flag (after an all-reduce over ranks when a communicator is attached):
 // the reduce(nChanged, sumOp) / returnReduce(bool, orOp) sites of the reference
+#define PEER_ERR_FETCH()                                                                                                  \
+    do {                                                                                                                  \
+        ctx->hFlags[9] = 0;                                                                                               \
+        if (ctx->usePeer)                                                                                                 \
+            CK(cudaMemcpyAsync(ctx->hFlags + 9, ctx->region + offsetof(P2PRegionHeader, error), sizeof(int),             \
+                               cudaMemcpyDeviceToHost, ctx->stream));                                                    \
+    } while (0)
+#define PEER_ERR_CHECK()                                                                                                  \
+    do {                                                                                                                  \
+        if (ctx->hFlags[9]) FAIL(AMR_ERR_STATE, "peer-memory halo swap timed out (a neighbour rank did not enter the same call)"); \
+    } while (0)
+
 static int globalFlag(amr_ctx *ctx, int slot, int *value) {
-    if (ctx->comm && ctx->nranks > 1)
-        NCK(ncclAllReduce(ctx->dFlags + slot, ctx->dFlags + slot, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
+    TRY(allReduceWord(ctx, ctx->dFlags + slot, 0));
     CK(cudaMemcpyAsync(ctx->hFlags + slot, ctx->dFlags + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PEER_ERR_FETCH();
     CK(cudaStreamSynchronize(ctx->stream));
+    PEER_ERR_CHECK();
     *value = ctx->hFlags[slot];
     return AMR_OK;
 }
 static int globalSum(amr_ctx *ctx, int slot, int64_t *value) {
-    if (ctx->comm && ctx->nranks > 1)
-        NCK(ncclAllReduce(ctx->dCount + slot, ctx->dCount + slot, 1, ncclInt64, ncclSum, ctx->comm, ctx->stream));
+    TRY(allReduceWord(ctx, ctx->dCount + slot, 1));
     CK(cudaMemcpyAsync(ctx->hCount + slot, ctx->dCount + slot, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     *value = ctx->hCount[slot];
@@ -229,6 +377,7 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     if (f) CK(cudaMemcpyAsync(ctx->neighbour, neighbour, (size_t)f * 4, cudaMemcpyDefault, ctx->stream));
     if (b) CK(cudaMemcpyAsync(ctx->bCoupled, coupled.data(), (size_t)b, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    TRY(peerPlan(ctx));
     TRY(sellBuildCellCells(ctx));
     int64_t m = std::max(n, p);
     ctx->flagCap = m + 16;
@@ -563,10 +712,8 @@ AMR_API int amr_normalize_range(amr_ctx *ctx, double refineThreshold, double unr
     } else {
         CK(cudaMemcpyAsync(res, mm, 16, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (ctx->comm && ctx->nranks > 1) {      // gMin / gMax
-        NCK(ncclAllReduce(res, res, 1, ncclFloat64, ncclMin, ctx->comm, ctx->stream));
-        NCK(ncclAllReduce(res + 1, res + 1, 1, ncclFloat64, ncclMax, ctx->comm, ctx->stream));
-    }
+    TRY(allReduceWord(ctx, res, 2));         // gMin
+    TRY(allReduceWord(ctx, res + 1, 3));     // gMax
     CK(cudaMemcpyAsync(mm, res, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const double minE = mm[0], maxE = mm[1];
@@ -658,12 +805,13 @@ static int emitListAsync(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *user
 // flagSlot >= 0: also fetch ctx->dFlags[flagSlot] (all-reduced over ranks) in the same round trip
 static int finishList(amr_ctx *ctx, ListJob *job, int flagSlot, int *flagValue, int64_t *nOut, bool copyOut) {
     if (flagSlot >= 0) {
-        if (ctx->comm && ctx->nranks > 1)
-            NCK(ncclAllReduce(ctx->dFlags + flagSlot, ctx->dFlags + flagSlot, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
+        TRY(allReduceWord(ctx, ctx->dFlags + flagSlot, 0));
         CK(cudaMemcpyAsync(ctx->hFlags + flagSlot, ctx->dFlags + flagSlot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaMemcpyAsync(ctx->hFlags + 8, job->dTotal, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PEER_ERR_FETCH();
     CK(cudaStreamSynchronize(ctx->stream));
+    PEER_ERR_CHECK();
     if (flagSlot >= 0 && flagValue) *flagValue = ctx->hFlags[flagSlot];
     const int32_t total = ctx->hFlags[8];
     if (nOut) *nOut = total;

@@ -50,6 +50,15 @@ struct amr_ctx {
     bool ownStream = true;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // NVLink peer-memory halos (p2p.cuh)
+    bool usePeer = false;
+    char *region = nullptr;            // my IPC-exported region
+    std::vector<char *> peerHost;      // mapped regions of all ranks (mine included)
+    char **peerDev = nullptr;          // same, on the device
+    unsigned haloEpoch = 0, redEpoch = 0;
+    void *haloPlan = nullptr;          // HaloPlan (host copy), rebuilt at amr_mesh_set
+    bool havePlan = false;
+    unsigned long long *redVal = nullptr;   // device staging word for reductions
     std::string err;
     int numSMs = 148;
     bool usePipeline = true;                       // TMA-staged SELL kernels (AMR_B200_NO_PIPELINE=1 disables)
