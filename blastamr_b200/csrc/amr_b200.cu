@@ -24,7 +24,7 @@ static bool pipeOk(const amr_ctx *ctx, const Sell &S) {
 
 template <class K, class... Args>
 static int launchPipe(amr_ctx *ctx, K kern, const Sell &S, Args... args) {
-    SellView V{S.sliceOff, S.col, S.rows, S.slices, S.maxTileInts};
+    SellView V{S.sliceOff, S.col, S.rows, S.slices, S.maxTileInts, S.sliceGhost};
     const size_t smem = pipeSmemBytes(V.stageInts);
     const void *key = (const void *)kern;
     auto it = ctx->occCache.find(key);

@@ -49,6 +49,40 @@ __device__ __forceinline__ T gatherAt(const T *__restrict__ local, const T *ghos
     return local[q];
 }
 
+// Row bodies are templated on GHOST; the kernels pick the ghost-aware body per warp slice (only slices
+// that touch a processor patch contain ghost slots -- S.sliceGhost), so a decomposed mesh runs the plain
+// body on all interior slices.  (Measured: the ghost-aware body on every slice cost +50 % on kp_estimate.)
+template <int KIND, bool GHOST>
+__device__ __forceinline__ double estimateRow(const int32_t *row, int w, int32_t c, int32_t n, const double *__restrict__ x,
+                                              const double *ghostBase, double p0, double p1, bool useOffset) {
+    const double xc = fieldXform<KIND>(x[c], p1, useOffset);
+    double eL = 0.0, eG = 0.0;   // max over internal faces / over coupled-patch faces
+    sellRow(row, w, c, [&](auto W, const int32_t *q) {
+        constexpr int NW = decltype(W)::value;
+        double v[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>(x, ghostBase, q[k], n);
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const double xv = fieldXform<KIND>(v[k], p1, useOffset);
+            double eT = fabs(xc - xv);
+            if (KIND == 1) {
+                eT = eT / fmaxFoam(fminFoam(xc, xv), p0);     // scaledDelta.C:103-104,129-131
+                eT = (q[k] == c) ? 0.0 : eT;                  // padding (0/0 guard)
+            }
+            if (GHOST && KIND == 0) {
+                const bool g = q[k] >= n;
+                eL = fmaxFoam(eL, g ? 0.0 : eT);
+                eG = fmaxFoam(eG, g ? eT : 0.0);
+            } else {
+                eL = fmaxFoam(eL, eT);
+            }
+        }
+    });
+    // delta clamps internal faces only (delta.C:103 vs :126); min(max_j d_j, .5) == max_j min(d_j, .5)
+    return (KIND == 0) ? fmaxFoam(fminFoam(eL, 0.5), eG) : eL;
+}
+
 template <int KIND, bool SCALE, bool GHOST>
 __global__ void __launch_bounds__(kPipeThreads)
 kp_estimate(SellView S, const double *__restrict__ x, const double *ghost, double p0, double p1, Thresholds thr,
@@ -58,34 +92,25 @@ kp_estimate(SellView S, const double *__restrict__ x, const double *ghost, doubl
     const double *ghostBase = ghost - n;
     sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w) {
         const int32_t c = valid ? (int32_t)c64 : n - 1;
-        const double xc = fieldXform<KIND>(x[c], p1, useOffset);
-        double eL = 0.0, eG = 0.0;   // max over internal faces / over coupled-patch faces
-        sellRow(row, w, c, [&](auto W, const int32_t *q) {
-            constexpr int NW = decltype(W)::value;
-            double v[NW];
-#pragma unroll
-            for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>(x, ghostBase, q[k], n);
-#pragma unroll
-            for (int k = 0; k < NW; k++) {
-                const double xv = fieldXform<KIND>(v[k], p1, useOffset);
-                double eT = fabs(xc - xv);
-                if (KIND == 1) {
-                    eT = eT / fmaxFoam(fminFoam(xc, xv), p0);     // scaledDelta.C:103-104,129-131
-                    eT = (q[k] == c) ? 0.0 : eT;                  // padding (0/0 guard)
-                }
-                if (GHOST && KIND == 0) {
-                    const bool g = q[k] >= n;
-                    eL = fmaxFoam(eL, g ? 0.0 : eT);
-                    eG = fmaxFoam(eG, g ? eT : 0.0);
-                } else {
-                    eL = fmaxFoam(eL, eT);
-                }
-            }
-        });
-        // delta clamps internal faces only (delta.C:103 vs :126); min(max_j d_j, .5) == max_j min(d_j, .5)
-        double e = (KIND == 0) ? fmaxFoam(fminFoam(eL, 0.5), eG) : eL;
+        double e;
+        if (GHOST && S.sliceGhost[c64 >> 5]) e = estimateRow<KIND, true>(row, w, c, n, x, ghostBase, p0, p1, useOffset);
+        else e = estimateRow<KIND, false>(row, w, c, n, x, ghostBase, p0, p1, useOffset);
         if (valid) err[c] = SCALE ? normalizeValue(e, thr) : e;
     });
+}
+
+template <bool GHOST>
+__device__ __forceinline__ unsigned extendRow(const int32_t *row, int w, int32_t c, int32_t n, unsigned m,
+                                              const u8 *__restrict__ src, const u8 *ghostBase) {
+    sellRow(row, w, c, [&](auto W, const int32_t *q) {
+        constexpr int NW = decltype(W)::value;
+        unsigned v[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>(src, ghostBase, q[k], n);
+#pragma unroll
+        for (int k = 0; k < NW; k++) m |= v[k];   // padding reads src[c] <= in[c]: no-op
+    });
+    return m;
 }
 
 template <bool GHOST>
@@ -98,17 +123,26 @@ kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, con
         unsigned m = in[c];
         // a warp whose 32 cells are all marked has nothing to gather
         if (!__all_sync(0xffffffffu, m != 0)) {
-            sellRow(row, w, c, [&](auto W, const int32_t *q) {
-                constexpr int NW = decltype(W)::value;
-                unsigned v[NW];
-#pragma unroll
-                for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>(src, ghostBase, q[k], n);
-#pragma unroll
-                for (int k = 0; k < NW; k++) m |= v[k];   // padding reads src[c] <= in[c]: no-op
-            });
+            if (GHOST && S.sliceGhost[c64 >> 5]) m = extendRow<true>(row, w, c, n, m, src, ghostBase);
+            else m = extendRow<false>(row, w, c, n, m, src, ghostBase);
         }
         if (valid) out[c] = m ? 1 : 0;
     });
+}
+
+template <bool MAXSET, bool GHOST>
+__device__ __forceinline__ int sweepRow(const int32_t *row, int w, int32_t c, int32_t n, int mine, const u8 *lf,
+                                        const u8 *ghostBase) {
+    int ext = mine;      // padding contributes the cell's own value: neutral for max and min
+    sellRow(row, w, c, [&](auto W, const int32_t *q) {
+        constexpr int NW = decltype(W)::value;
+        int v[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>(lf, ghostBase, q[k], n);
+#pragma unroll
+        for (int k = 0; k < NW; k++) ext = MAXSET ? max(ext, v[k]) : min(ext, v[k]);
+    });
+    return ext;
 }
 
 template <bool MAXSET, bool GHOST>
@@ -123,15 +157,9 @@ kp_refine_sweep(SellView S, u8 *lf, u8 *set, const u8 *ghostLf, int *changed) {
         const bool idle = MAXSET ? __all_sync(0xffffffffu, isSet != 0) : !__any_sync(0xffffffffu, isSet != 0);
         if (!idle) {
             const int mine = lf[c];
-            int ext = mine;      // padding contributes the cell's own value: neutral for max and min
-            sellRow(row, w, c, [&](auto W, const int32_t *q) {
-                constexpr int NW = decltype(W)::value;
-                int v[NW];
-#pragma unroll
-                for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>((const u8 *)lf, ghostBase, q[k], n);
-#pragma unroll
-                for (int k = 0; k < NW; k++) ext = MAXSET ? max(ext, v[k]) : min(ext, v[k]);
-            });
+            int ext;
+            if (GHOST && S.sliceGhost[c64 >> 5]) ext = sweepRow<MAXSET, true>(row, w, c, n, mine, (const u8 *)lf, ghostBase);
+            else ext = sweepRow<MAXSET, false>(row, w, c, n, mine, (const u8 *)lf, ghostBase);
             if (valid) {
                 if (MAXSET) { if (!isSet && ext > mine + 1) { set[c] = 1; lf[c] = (u8)(mine + 1); flip = 1; } }
                 else { if (isSet && mine > ext + 1) { set[c] = 0; lf[c] = (u8)(mine - 1); flip = 1; } }

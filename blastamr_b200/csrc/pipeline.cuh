@@ -51,6 +51,7 @@ struct SellView {
     const int32_t *col;
     int64_t rows, slices;
     int stageInts;             // capacity of one ring stage in int32 (>= largest tile)
+    const u8 *sliceGhost;      // [slices] or nullptr
 };
 
 // dynamic shared memory layout: [kStages][stageInts] labels | [kStages][kHdrInts] headers | barriers

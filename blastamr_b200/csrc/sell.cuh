@@ -111,7 +111,19 @@ __global__ void k_fill_tail(int32_t *__restrict__ sliceOff, int64_t slices, int 
 
 constexpr int kSliceOffPad = 16;
 
+// slices that contain at least one ghost slot (label >= rows): only those take the ghost-aware row walk
+__global__ void k_slice_ghost(const int32_t *__restrict__ col, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ deg,
+                              int64_t rows, u8 *__restrict__ sliceGhost) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int32_t *row = col + ((size_t)sliceOff[r >> 5] << 5) + (r & 31);
+    const int d = deg[r];
+    // rows are sorted ascending: a ghost slot, if any, is the last valid entry
+    if (d > 0 && row[(size_t)(d - 1) << 5] >= rows) sliceGhost[r >> 5] = 1;
+}
+
 static void sellFree(amr_ctx *ctx, Sell &S) {
+    if (S.sliceGhost) { cudaFree(S.sliceGhost); }
     if (S.sliceOff) { cudaFree(S.sliceOff); ctx->devBytes -= (int64_t)((S.slices + kSliceOffPad) * 4); }
     if (S.col) { cudaFree(S.col); ctx->devBytes -= (int64_t)(S.entries * 4 > 4 ? S.entries * 4 : 4); }
     if (S.count) { cudaFree(S.count); ctx->devBytes -= (int64_t)(S.rows > 0 ? S.rows : 1); }
@@ -168,6 +180,10 @@ static int sellBuildCellCells(amr_ctx *ctx) {
         if (b > 0 && ctx->nCoupled > 0)
             LAUNCH(k_sell_fill_coupled, gridFor(b), kThreads, ctx->owner + f, ctx->bCoupled, b, n, ctx->cc.sliceOff, cursor, ctx->cc.col);
         if (n > 0) LAUNCH(k_sell_sort_rows, gridFor(n), kThreads, ctx->cc.col, ctx->cc.sliceOff, deg, n);
+        if (cudaMalloc((void **)&ctx->cc.sliceGhost, (size_t)ctx->cc.slices + 16) == cudaSuccess) {
+            cudaMemsetAsync(ctx->cc.sliceGhost, 0, (size_t)ctx->cc.slices + 16, ctx->stream);
+            if (n > 0 && ctx->nCoupled > 0) LAUNCH(k_slice_ghost, gridFor(n), kThreads, ctx->cc.col, ctx->cc.sliceOff, deg, n, ctx->cc.sliceGhost);
+        }
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { ctx->err = std::string("sellBuildCellCells: ") + cudaGetErrorString(e); rc = AMR_ERR_CUDA; }
     }
