@@ -84,16 +84,16 @@ __device__ __forceinline__ double estimateRow(const int32_t *row, int w, int32_t
 }
 
 template <int KIND, bool SCALE, bool GHOST>
-__global__ void __launch_bounds__(kPipeThreads)
+__global__ void __launch_bounds__(kPipeThreads, (KIND == 1) ? 4 : 7)
 kp_estimate(SellView S, const double *__restrict__ x, const double *ghost, double p0, double p1, Thresholds thr,
             double *__restrict__ err) {
     const int32_t n = (int32_t)S.rows;
     const bool useOffset = fabs(p1) > kSMALL;
     const double *ghostBase = ghost - n;
-    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w) {
+    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool ghostSlice) {
         const int32_t c = valid ? (int32_t)c64 : n - 1;
         double e;
-        if (GHOST && S.sliceGhost[c64 >> 5]) e = estimateRow<KIND, true>(row, w, c, n, x, ghostBase, p0, p1, useOffset);
+        if (GHOST && ghostSlice) e = estimateRow<KIND, true>(row, w, c, n, x, ghostBase, p0, p1, useOffset);
         else e = estimateRow<KIND, false>(row, w, c, n, x, ghostBase, p0, p1, useOffset);
         if (valid) err[c] = SCALE ? normalizeValue(e, thr) : e;
     });
@@ -118,12 +118,12 @@ __global__ void __launch_bounds__(kPipeThreads, 7)
 kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, const u8 *ghost, u8 *__restrict__ out) {
     const int32_t n = (int32_t)S.rows;
     const u8 *ghostBase = ghost - n;
-    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w) {
+    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool ghostSlice) {
         const int32_t c = valid ? (int32_t)c64 : n - 1;
         unsigned m = in[c];
         // a warp whose 32 cells are all marked has nothing to gather
         if (!__all_sync(0xffffffffu, m != 0)) {
-            if (GHOST && S.sliceGhost[c64 >> 5]) m = extendRow<true>(row, w, c, n, m, src, ghostBase);
+            if (GHOST && ghostSlice) m = extendRow<true>(row, w, c, n, m, src, ghostBase);
             else m = extendRow<false>(row, w, c, n, m, src, ghostBase);
         }
         if (valid) out[c] = m ? 1 : 0;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kPipeThreads, 7)
 kp_refine_sweep(SellView S, u8 *lf, u8 *set, const u8 *ghostLf, int *changed) {
     const int32_t n = (int32_t)S.rows;
     const u8 *ghostBase = ghostLf - n;
-    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w) {
+    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool ghostSlice) {
         const int32_t c = valid ? (int32_t)c64 : n - 1;
         const int isSet = set[c];
         int flip = 0;
@@ -158,7 +158,7 @@ kp_refine_sweep(SellView S, u8 *lf, u8 *set, const u8 *ghostLf, int *changed) {
         if (!idle) {
             const int mine = lf[c];
             int ext;
-            if (GHOST && S.sliceGhost[c64 >> 5]) ext = sweepRow<MAXSET, true>(row, w, c, n, mine, (const u8 *)lf, ghostBase);
+            if (GHOST && ghostSlice) ext = sweepRow<MAXSET, true>(row, w, c, n, mine, (const u8 *)lf, ghostBase);
             else ext = sweepRow<MAXSET, false>(row, w, c, n, mine, (const u8 *)lf, ghostBase);
             if (valid) {
                 if (MAXSET) { if (!isSet && ext > mine + 1) { set[c] = 1; lf[c] = (u8)(mine + 1); flip = 1; } }
@@ -174,7 +174,7 @@ kp_select_unrefine_points(SellView S, const u8 *__restrict__ pcCount, const u8 *
                           const label *__restrict__ parentIdx, const u8 *__restrict__ lvl8,
                           const double *__restrict__ err, double unrefineLevel, const u8 *__restrict__ marked,
                           u8 *__restrict__ isSplit, u8 *__restrict__ keep) {
-    sellPipeline(S, [&](int64_t pt, bool valid, const int32_t *row, int w) {
+    sellPipeline(S, [&](int64_t pt, bool valid, const int32_t *row, int w, bool) {
         if (!valid) return;
         bool split = (pcCount[pt] == 8) && !bndPoint[pt];
         bool kp = false;

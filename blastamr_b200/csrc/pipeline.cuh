@@ -59,7 +59,7 @@ __host__ __device__ inline size_t pipeSmemBytes(int stageInts) {
     return (size_t)kStages * stageInts * 4 + (size_t)kStages * kHdrInts * 4 + 2 * kStages * 8 + 64;
 }
 
-// Body signature: void body(int64_t row, bool valid, const int32_t* rowLabels /*smem, stride 32*/, int width)
+// Body signature: void body(int64_t row, bool valid, const int32_t* rowLabels /*smem, stride 32*/, int width, bool ghostSlice)
 // called by every consumer thread once per tile (valid=false for rows >= S.rows; all 32 lanes of a
 // warp call it together so that warp collectives inside the body are legal).
 template <class Body>
@@ -101,14 +101,16 @@ __device__ __forceinline__ void sellPipeline(const SellView &S, Body body) {
         int stage = 0;
         unsigned phase = 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int64_t s = t * kTileSlices + warp;
+            // per-slice flag fetched BEFORE the wait so that its latency hides behind the tile's arrival
+            const unsigned ghostSlice = S.sliceGhost ? S.sliceGhost[s] : 0u;
             mbarWait(&full[stage], phase);
             const int32_t *h = hdr + stage * kHdrInts;
-            const int64_t s = t * kTileSlices + warp;
             const int64_t row = s * 32 + lane;
             const bool sliceValid = s < S.slices;
             int32_t base = 0, w = 0;
             if (sliceValid) { base = h[warp] - h[0]; w = h[warp + 1] - h[warp]; }
-            body(row, sliceValid && row < S.rows, ring + (size_t)stage * S.stageInts + ((size_t)base << 5) + lane, w);
+            body(row, sliceValid && row < S.rows, ring + (size_t)stage * S.stageInts + ((size_t)base << 5) + lane, w, ghostSlice != 0);
             __syncwarp();
             if (lane == 0) mbarArrive(&empty[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
