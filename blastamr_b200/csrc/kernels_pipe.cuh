@@ -57,11 +57,26 @@ __device__ __forceinline__ double estimateRow(const int32_t *row, int w, int32_t
                                               const double *ghostBase, double p0, double p1, bool useOffset) {
     const double xc = fieldXform<KIND>(x[c], p1, useOffset);
     double eL = 0.0, eG = 0.0;   // max over internal faces / over coupled-patch faces
+    if (GHOST) {
+        // slices on a processor patch (a few percent of the mesh): one neighbour at a time keeps the register
+        // footprint of this rarely taken path below that of the batched walk
+#pragma unroll 1
+        for (int j = 0; j < w; j++) {
+            const int32_t q = row[j << 5];
+            const bool g = q >= n;
+            const double xv = fieldXform<KIND>(g ? ghostBase[q] : x[q], p1, useOffset);
+            double eT = fabs(xc - xv);
+            if (KIND == 1) { eT = eT / fmaxFoam(fminFoam(xc, xv), p0); eT = (q == c) ? 0.0 : eT; }
+            if (KIND == 0 && !g) eT = fminFoam(eT, 0.5);          // delta.C:103 vs :126
+            eL = fmaxFoam(eL, eT);
+        }
+        return eL;
+    }
     sellRow(row, w, c, [&](auto W, const int32_t *q) {
         constexpr int NW = decltype(W)::value;
         double v[NW];
 #pragma unroll
-        for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>(x, ghostBase, q[k], n);
+        for (int k = 0; k < NW; k++) v[k] = x[q[k]];
 #pragma unroll
         for (int k = 0; k < NW; k++) {
             const double xv = fieldXform<KIND>(v[k], p1, useOffset);
@@ -70,17 +85,12 @@ __device__ __forceinline__ double estimateRow(const int32_t *row, int w, int32_t
                 eT = eT / fmaxFoam(fminFoam(xc, xv), p0);     // scaledDelta.C:103-104,129-131
                 eT = (q[k] == c) ? 0.0 : eT;                  // padding (0/0 guard)
             }
-            if (GHOST && KIND == 0) {
-                const bool g = q[k] >= n;
-                eL = fmaxFoam(eL, g ? 0.0 : eT);
-                eG = fmaxFoam(eG, g ? eT : 0.0);
-            } else {
-                eL = fmaxFoam(eL, eT);
-            }
+            eL = fmaxFoam(eL, eT);
         }
     });
     // delta clamps internal faces only (delta.C:103 vs :126); min(max_j d_j, .5) == max_j min(d_j, .5)
-    return (KIND == 0) ? fmaxFoam(fminFoam(eL, 0.5), eG) : eL;
+    (void)eG;
+    return (KIND == 0) ? fminFoam(eL, 0.5) : eL;
 }
 
 template <int KIND, bool SCALE, bool GHOST>
@@ -102,11 +112,16 @@ kp_estimate(SellView S, const double *__restrict__ x, const double *ghost, doubl
 template <bool GHOST>
 __device__ __forceinline__ unsigned extendRow(const int32_t *row, int w, int32_t c, int32_t n, unsigned m,
                                               const u8 *__restrict__ src, const u8 *ghostBase) {
+    if (GHOST) {
+#pragma unroll 1
+        for (int j = 0; j < w; j++) { const int32_t q = row[j << 5]; m |= (q < n) ? src[q] : ghostBase[q]; }
+        return m;
+    }
     sellRow(row, w, c, [&](auto W, const int32_t *q) {
         constexpr int NW = decltype(W)::value;
         unsigned v[NW];
 #pragma unroll
-        for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>(src, ghostBase, q[k], n);
+        for (int k = 0; k < NW; k++) v[k] = src[q[k]];
 #pragma unroll
         for (int k = 0; k < NW; k++) m |= v[k];   // padding reads src[c] <= in[c]: no-op
     });
@@ -134,11 +149,20 @@ template <bool MAXSET, bool GHOST>
 __device__ __forceinline__ int sweepRow(const int32_t *row, int w, int32_t c, int32_t n, int mine, const u8 *lf,
                                         const u8 *ghostBase) {
     int ext = mine;      // padding contributes the cell's own value: neutral for max and min
+    if (GHOST) {
+#pragma unroll 1
+        for (int j = 0; j < w; j++) {
+            const int32_t q = row[j << 5];
+            const int v = (q < n) ? lf[q] : ghostBase[q];
+            ext = MAXSET ? max(ext, v) : min(ext, v);
+        }
+        return ext;
+    }
     sellRow(row, w, c, [&](auto W, const int32_t *q) {
         constexpr int NW = decltype(W)::value;
         int v[NW];
 #pragma unroll
-        for (int k = 0; k < NW; k++) v[k] = gatherAt<GHOST>(lf, ghostBase, q[k], n);
+        for (int k = 0; k < NW; k++) v[k] = lf[q[k]];
 #pragma unroll
         for (int k = 0; k < NW; k++) ext = MAXSET ? max(ext, v[k]) : min(ext, v[k]);
     });
