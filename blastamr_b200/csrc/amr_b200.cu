@@ -292,6 +292,38 @@ static int haloExchange(amr_ctx *ctx, const void *send, void *recv, size_t elemB
     return AMR_OK;
 }
 
+// swap of "the value at the owner cell of every boundary face" (patchInternalField / owner levels / owner
+// marks): what every syncTools call site on this path sends.  Peer path: fused gather + push + signal.
+static int haloSwapCells(amr_ctx *ctx, const void *cells, size_t elemBytes, void *recv, const u8 *minus = nullptr) {
+    if (ctx->nCoupled == 0) return AMR_OK;
+    if (!ctx->comm) FAIL(AMR_ERR_STATE, "mesh has processor patches but no communicator (amr_comm_init) and no host-side neighbour values");
+    const int64_t b = ctx->b;
+    if (ctx->usePeer && ctx->havePlan && b * (int64_t)elemBytes <= kHaloCap) {
+        const HaloPlan &P = *(const HaloPlan *)ctx->haloPlan;
+        const unsigned epoch = ++ctx->haloEpoch;
+        const int parity = (int)(epoch & 1u);
+        const unsigned g = gridFor(P.prefix[P.nPatch]);
+        unsigned *counter = (unsigned *)(ctx->dFlags + 6);
+        const label *bOwner = ctx->owner + ctx->f;
+        if (elemBytes == 1) k_halo_push_cells<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
+        else if (elemBytes == 4) k_halo_push_cells<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
+        else k_halo_push_cells<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
+        if (elemBytes == 1) k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
+        else if (elemBytes == 4) k_halo_unpack<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
+        else k_halo_unpack<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
+        ctx->launches += 2;
+        return AMR_OK;
+    }
+    // NCCL path: pack into a send buffer laid out like the boundary-face array, then grouped send/recv
+    void *send = nullptr;
+    TRY(arenaAlloc(ctx, &send, (size_t)b * elemBytes));
+    if (elemBytes == 1 && minus) LAUNCH(k_pack_level_minus, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const u8 *)cells, minus, (u8 *)send);
+    else if (elemBytes == 1) LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const u8 *)cells, (u8 *)send);
+    else if (elemBytes == 4) LAUNCH(k_pack_i32, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const label *)cells, (label *)send);
+    else LAUNCH(k_pack_f64, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const double *)cells, (double *)send);
+    return haloExchange(ctx, send, recv, elemBytes);
+}
+
 // all-rank reduction of one device word in place (reduce()/returnReduce()/gMin/gMax of the reference).
 // op: 0 max(int32), 1 sum(int64), 2 min(f64), 3 max(f64)
 static int allReduceWord(amr_ctx *ctx, void *word, int op) {
@@ -357,6 +389,7 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     if (ctx->refineCell && ctx->refineCellN == n && n > 0) { pending = ctx->refineCell; pendingN = n; ctx->refineCell = nullptr; }
     freeMesh(ctx);
     ctx->nTotalCells = -1;
+    ctx->anyProtCached = -1;
     ctx->n = n; ctx->f = f; ctx->b = b; ctx->p = p;
     ctx->patches.clear();
     std::vector<u8> coupled((size_t)(b > 0 ? b : 1), 0);
@@ -568,6 +601,7 @@ AMR_API int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t
 
 AMR_API int amr_protected_cells_set(amr_ctx *ctx, const uint8_t *protectedCell) {
     ENTER();
+    ctx->anyProtCached = -1;
     if (!protectedCell) { devFree(ctx, &ctx->protCell); return AMR_OK; }
     if (!ctx->protCell) TRY(devAlloc(ctx, &ctx->protCell, ctx->n + 16));
     if (ctx->n) CK(cudaMemcpyAsync(ctx->protCell, protectedCell, (size_t)ctx->n, cudaMemcpyDefault, ctx->stream));
@@ -608,8 +642,7 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
             if (ctx->nCoupled > 0) {
                 if (nbrValues) TRY(stageIn(ctx, nbrValues, b, &ghost));
                 else {
-                    LAUNCH(k_pack_f64, gridFor(b), kThreads, b, ctx->owner + ctx->f, dx, ctx->send64);
-                    TRY(haloExchange(ctx, ctx->send64, ctx->ghost64, 8));
+                    TRY(haloSwapCells(ctx, dx, 8, ctx->ghost64));
                     ghost = ctx->ghost64;
                 }
             }
@@ -657,8 +690,7 @@ AMR_API int amr_estimate_lohner(amr_ctx *ctx, const double *x, const double *xBo
     if (ctx->nCoupled > 0) {
         if (nbrValues) TRY(stageIn(ctx, nbrValues, b, &dxn));
         else {
-            LAUNCH(k_pack_f64, gridFor(b), kThreads, b, ctx->owner + f, dx, ctx->send64);
-            TRY(haloExchange(ctx, ctx->send64, ctx->ghost64, 8));
+            TRY(haloSwapCells(ctx, dx, 8, ctx->ghost64));
             dxn = ctx->ghost64;
         }
     } else dxn = ctx->ghost64;
@@ -735,8 +767,7 @@ AMR_API int amr_normalize_range(amr_ctx *ctx, double refineThreshold, double unr
 static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res) {
     const int64_t n = ctx->n, b = ctx->b;
     if (ctx->nCoupled > 0) {
-        LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, src, ctx->send8);
-        TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
+        TRY(haloSwapCells(ctx, src, 1, ctx->ghost8));
     }
     if (pipeOk(ctx, ctx->cc)) {
         if (ctx->nCoupled > 0) TRY(launchPipe(ctx, kp_extend<true>, ctx->cc, (const u8 *)cur, src, (const u8 *)ctx->ghost8, tmp));
@@ -851,8 +882,7 @@ static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOu
             else LAUNCH((k_edge_refine_sweep<false>), gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, lf, set, ctx->dFlags);
         }
         if (ctx->nCoupled > 0) {
-            LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, lf, ctx->send8);
-            TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
+            TRY(haloSwapCells(ctx, lf, 1, ctx->ghost8));
         }
         if (n) {
             if (pipeOk(ctx, ctx->cc)) {
@@ -909,10 +939,14 @@ k_protected_spread(int64_t n, const int32_t *__restrict__ sliceOff, const int32_
 static int calcProtected(amr_ctx *ctx, u8 *unrefineable, bool *have) {
     const int64_t n = ctx->n, b = ctx->b;
     // returnReduce(protectedCell_.size(), sumOp) == 0 -> empty list (fvMeshHexRefiner.C:65-69)
-    CK(cudaMemsetAsync(ctx->dFlags + 2, 0, sizeof(int), ctx->stream));
-    if (ctx->protCell) { int one = 1; CK(cudaMemcpyAsync(ctx->dFlags + 2, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); }
-    int any = 0;
-    TRY(globalFlag(ctx, 2, &any));
+    if (ctx->anyProtCached < 0) {      // reduced once per mesh / protectedCell change (both are set collectively)
+        CK(cudaMemsetAsync(ctx->dFlags + 2, 0, sizeof(int), ctx->stream));
+        if (ctx->protCell) { int one = 1; CK(cudaMemcpyAsync(ctx->dFlags + 2, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); }
+        int anyR = 0;
+        TRY(globalFlag(ctx, 2, &anyR));
+        ctx->anyProtCached = anyR ? 1 : 0;
+    }
+    const int any = ctx->anyProtCached;
     *have = any != 0;
     if (!any) return AMR_OK;
     if (ctx->protCell) CK(cudaMemcpyAsync(unrefineable, ctx->protCell, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -920,14 +954,12 @@ static int calcProtected(amr_ctx *ctx, u8 *unrefineable, bool *have) {
     u8 *ghostLvl = ctx->flagC;   // [b] fits: flagC has max(n,p) >= ... guard below
     if (ctx->nCoupled > 0) {
         if (b > std::max(ctx->n, ctx->p)) FAIL(AMR_ERR_STATE, "scratch too small for boundary levels");
-        LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, ctx->lvl8, ctx->send8);
-        TRY(haloExchange(ctx, ctx->send8, ghostLvl, 1));
+        TRY(haloSwapCells(ctx, ctx->lvl8, 1, ghostLvl));
     }
     while (true) {
         CK(cudaMemsetAsync(ctx->dFlags + 1, 0, sizeof(int), ctx->stream));
         if (ctx->nCoupled > 0) {
-            LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, unrefineable, ctx->send8);
-            TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
+            TRY(haloSwapCells(ctx, unrefineable, 1, ctx->ghost8));
         }
         if (n) LAUNCH(k_protected_spread, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, unrefineable, ctx->ghost8, ghostLvl, ctx->dFlags + 1);
         int changed = 0;
@@ -1133,8 +1165,7 @@ static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOu
         if (p) LAUNCH(k_points_to_cells, gP, kThreads, p, EL.sliceOff, EL.col, pflag, alP, uc);
         CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(int), ctx->stream));
         if (ctx->nCoupled > 0) {
-            LAUNCH(k_pack_level_minus, gridFor(b), kThreads, b, ctx->owner + ctx->f, ctx->lvl8, uc, ctx->send8);
-            TRY(haloExchange(ctx, ctx->send8, ctx->ghost8, 1));
+            TRY(haloSwapCells(ctx, ctx->lvl8, 1, ctx->ghost8, uc));
         }
         if (n) LAUNCH(k_unrefine_sweep, gC, kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, uc, alC, ctx->ghost8, ctx->dFlags);
         // polyhedralRefinement.C:2278-2286: faceConsistentUnrefinement, then edgeConsistentUnrefinement
@@ -1307,10 +1338,9 @@ AMR_API int amr_check_levels(amr_ctx *ctx, const int32_t *cellLevel, int64_t *nB
     label *ghost = nullptr, *send = nullptr;
     if (ctx->nCoupled > 0) {
         void *q;
-        TRY(arenaAlloc(ctx, &q, (size_t)b * 4)); send = (label *)q;
         TRY(arenaAlloc(ctx, &q, (size_t)b * 4)); ghost = (label *)q;
-        LAUNCH(k_pack_i32, gridFor(b), kThreads, b, ctx->owner + ctx->f, dL, send);
-        TRY(haloExchange(ctx, send, ghost, 4));
+        (void)send;
+        TRY(haloSwapCells(ctx, dL, 4, ghost));
     }
     CK(cudaMemsetAsync(ctx->dCount, 0, 8, ctx->stream));
     if (n) LAUNCH(k_check_levels, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, dL, ghost, (unsigned long long *)ctx->dCount);

@@ -109,6 +109,7 @@ struct amr_ctx {
     bool refineCellOversize = false;   // marking held in a private (non-pool) buffer until the next amr_mesh_set
     bool errorResident = false;        // ctx->error holds the last estimate
     int64_t flagCap = 0;        // capacity (bytes) of flagA/B/C and refineCell: they are swapped by pointer
+    int anyProtCached = -1;     // returnReduce(protectedCell_.size()) > 0, cached per mesh
     int64_t nTotalCells = -1;   // mesh_.globalData().nTotalCells(), reduced once per mesh
 
     // scratch (sized at mesh_set)

@@ -57,6 +57,41 @@ __global__ void k_halo_push(HaloPlan P, char *const *__restrict__ peer, int pari
     else *reinterpret_cast<double *>(dst) = *reinterpret_cast<const double *>(src);
     __threadfence_system();
 }
+// fused pack + push + signal: value of a per-cell array at the owner of every coupled boundary face goes
+// straight into the neighbour's region; the last CTA to finish publishes the epoch (threadfence-reduction
+// pattern), so a swap is two launches (this one and k_halo_unpack).  `minus` (optional, bytes): v -= minus[o].
+template <int BYTES>
+__global__ void k_halo_push_cells(HaloPlan P, char *const *__restrict__ peer, int parity, int myRank, unsigned epoch,
+                                  const label *__restrict__ bOwner, const char *__restrict__ cells, const u8 *__restrict__ minus,
+                                  unsigned *counter) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.prefix[P.nPatch]) {
+        int q = 0;
+        while (i >= P.prefix[q + 1]) q++;
+        const int k = i - P.prefix[q];
+        const label o = bOwner[P.offMine[q] + k];
+        char *dst = peer[P.nbr[q]] + sizeof(P2PRegionHeader) + (size_t)parity * kHaloCap + (size_t)(P.offTheirs[q] + k) * BYTES;
+        if (BYTES == 1) { u8 v = (u8)cells[o]; if (minus) v = (u8)(v - minus[o]); *reinterpret_cast<u8 *>(dst) = v; }
+        else if (BYTES == 4) *reinterpret_cast<int *>(dst) = reinterpret_cast<const int *>(cells)[o];
+        else *reinterpret_cast<double *>(dst) = reinterpret_cast<const double *>(cells)[o];
+        __threadfence_system();
+    }
+    __shared__ int last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x < P.nPatch) {
+            __threadfence_system();
+            P2PRegionHeader *h = reinterpret_cast<P2PRegionHeader *>(peer[P.nbr[threadIdx.x]]);
+            stReleaseSys(&h->arrive[parity][myRank], epoch);
+        }
+        if (threadIdx.x == 0) *counter = 0;
+    }
+}
 __global__ void k_halo_signal(HaloPlan P, char *const *__restrict__ peer, int parity, int myRank, unsigned epoch) {
     const int q = threadIdx.x;
     if (q >= P.nPatch) return;
