@@ -81,7 +81,7 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
 static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->owner); devFree(ctx, &ctx->neighbour); devFree(ctx, &ctx->bCoupled);
     sellFree(ctx, ctx->cc); sellFree(ctx, ctx->pc);
-    devFree(ctx, &ctx->bndPoint);
+    devFree(ctx, &ctx->bndPoint); devFree(ctx, &ctx->pcClass); ctx->pcClassDirty = true;
     devFree(ctx, &ctx->lvl); devFree(ctx, &ctx->lvl8); devFree(ctx, &ctx->parentIdx); devFree(ctx, &ctx->pointLevel);
     devFree(ctx, &ctx->protCell);
     devFree(ctx, &ctx->error); devFree(ctx, &ctx->refineCell);
@@ -455,6 +455,7 @@ AMR_API int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_
     if (p) CK(cudaMemcpyAsync(ctx->bndPoint, bndPoint, (size_t)p, cudaMemcpyDefault, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->havePoints = true;
+    ctx->pcClassDirty = true;
     return AMR_OK;
 }
 
@@ -596,6 +597,7 @@ AMR_API int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->haveLevels = true;
+    ctx->pcClassDirty = true;
     return AMR_OK;
 }
 
@@ -1150,6 +1152,31 @@ AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nOld, int64_t nNew, cons
     return AMR_OK;
 }
 
+// split-point pre-filter (mesh-constant) and the fused U1+U2+U3 kernel.  When only a minority of the points can
+// be split points the direct kernel (threads of non-candidates exit, their rows are never read) beats the
+// TMA pipeline, which streams every tile.
+static int selectUnrefinePoints(amr_ctx *ctx, const double *dErr, double unrefineLevel, const u8 *dRc, u8 *isSplit, u8 *keep) {
+    const int64_t p = ctx->p;
+    if (!p) return AMR_OK;
+    if (ctx->pcClassDirty) {
+        if (!ctx->pcClass) TRY(devAlloc(ctx, &ctx->pcClass, p + 16));
+        CK(cudaMemsetAsync(ctx->dCount + 2, 0, 8, ctx->stream));
+        LAUNCH(k_point_class, gridFor(p), kThreads, p, (const u8 *)ctx->pc.count, (const u8 *)ctx->bndPoint,
+               (const label *)ctx->pointLevel, ctx->pcClass, (unsigned long long *)(ctx->dCount + 2));
+        CK(cudaMemcpyAsync(ctx->hCount + 2, ctx->dCount + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->nSplitCand = ctx->hCount[2];
+        ctx->pcClassDirty = false;
+    }
+    if (pipeOk(ctx, ctx->pc) && ctx->nSplitCand * 2 > p)
+        TRY(launchPipe(ctx, kp_select_unrefine_points, ctx->pc, (const u8 *)ctx->pcClass, (const label *)ctx->parentIdx,
+                       (const u8 *)ctx->lvl8, dErr, unrefineLevel, dRc, isSplit, keep));
+    else
+        LAUNCH(k_select_unrefine_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const u8 *)ctx->pcClass,
+               (const label *)ctx->parentIdx, (const u8 *)ctx->lvl8, dErr, unrefineLevel, dRc, isSplit, keep);
+    return AMR_OK;
+}
+
 // hexRef3D::consistentUnrefinement loop (hexRef3D.C:1758-1927) on point flags + ascending list
 // (hexRef3D.C:1930-1950), list compacted speculatively after each sweep (one round trip per sweep)
 static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOut, int32_t *elemsOut, int64_t *nOut,
@@ -1264,13 +1291,7 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
         CK(cudaGetLastError());
         return flushOuts(ctx);
     }
-    if (p) {
-        if (pipeOk(ctx, ctx->pc))
-            TRY(launchPipe(ctx, kp_select_unrefine_points, ctx->pc, (const u8 *)ctx->pc.count, (const u8 *)ctx->bndPoint,
-                           (const label *)ctx->parentIdx, (const u8 *)ctx->lvl8, dErr, unrefineLevel, (const u8 *)dRc, (u8 *)nullptr, pflag));
-        else LAUNCH(k_select_unrefine_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, ctx->pc.count, ctx->bndPoint,
-                    ctx->parentIdx, ctx->lvl8, dErr, unrefineLevel, dRc, (u8 *)nullptr, pflag);
-    }
+    TRY(selectUnrefinePoints(ctx, dErr, unrefineLevel, (const u8 *)dRc, (u8 *)nullptr, pflag));
     // B3: consistentUnrefinement(list, false) + ascending list   (flagA/flagB are free again)
     TRY(unrefineSweeps(ctx, ctx->pc, pflag, sweepsOut, elemsOut, nOut));
     CK(cudaGetLastError());
@@ -1307,8 +1328,7 @@ AMR_API int amr_get_split_elems(amr_ctx *ctx, int refinerKind, int32_t *elemsOut
         CK(cudaGetLastError());
         return flushOuts(ctx);
     }
-    if (p) LAUNCH(k_select_unrefine_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, ctx->pc.count, ctx->bndPoint,
-                  ctx->parentIdx, ctx->lvl8, (const double *)nullptr, 0.0, (const u8 *)nullptr, pflag, (u8 *)nullptr);
+    TRY(selectUnrefinePoints(ctx, (const double *)nullptr, 0.0, (const u8 *)nullptr, pflag, (u8 *)nullptr));
     TRY(emitList(ctx, pflag, p, elemsOut, nOut));
     CK(cudaGetLastError());
     return flushOuts(ctx);

@@ -93,6 +93,9 @@ struct amr_ctx {
     double *grad = nullptr;    // [3n]
     double *xbf = nullptr;     // [b] boundaryField of x
     u8 *bndPoint = nullptr;
+    u8 *pcClass = nullptr;     // [p] split-point pre-filter (see k_point_class); rebuilt when points/levels change
+    bool pcClassDirty = true;
+    int64_t nSplitCand = 0;
 
     // levels / history
     bool haveLevels = false, haveHistory = false;

@@ -487,13 +487,12 @@ k_max_cell_field(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t 
 // split points and cost one SELL column only.
 __global__ void __launch_bounds__(kThreads)
 k_select_unrefine_points(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-                         const u8 *__restrict__ pcCount, const u8 *__restrict__ bndPoint,
-                         const label *__restrict__ parentIdx, const u8 *__restrict__ lvl8,
+                         const u8 *__restrict__ pcClass, const label *__restrict__ parentIdx, const u8 *__restrict__ lvl8,
                          const double *__restrict__ err, double unrefineLevel, const u8 *__restrict__ marked,
                          u8 *__restrict__ isSplit, u8 *__restrict__ keep) {
     const int64_t pt = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (pt >= p) return;
-    bool split = (pcCount[pt] == 8) && !bndPoint[pt];
+    bool split = pcClass[pt] != 0;      // |pointCells| == 8, no boundary face, (pointLevel >= 1 when known)
     bool kp = false;
     if (split) {
         const int32_t base = sliceOff[pt >> 5];
@@ -502,27 +501,44 @@ k_select_unrefine_points(int64_t p, const int32_t *__restrict__ sliceOff, const 
 #pragma unroll
         for (int k = 0; k < 8; k++) q[k] = row[(size_t)k << 5];
         label par[8];
+        int l[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) par[k] = parentIdx[q[k]];
+        for (int k = 0; k < 8; k++) { par[k] = parentIdx[q[k]]; l[k] = lvl8[q[k]]; }
         bool same = par[0] >= 0;
 #pragma unroll
-        for (int k = 1; k < 8; k++) same = same && (par[k] == par[0]);
-        if (same) {
-            int l0 = lvl8[q[0]];
-#pragma unroll
-            for (int k = 1; k < 8; k++) same = same && (lvl8[q[k]] == l0);
-        }
+        for (int k = 1; k < 8; k++) same = same && (par[k] == par[0]) && (l[k] == l[0]);
         split = same;
         if (split && keep) {
+            double e[8];
+            unsigned mk[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { e[k] = err[q[k]]; mk[k] = marked[q[k]]; }
             double m = -kGREAT;
             unsigned anyMarked = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) { m = fmaxFoam(m, err[q[k]]); anyMarked |= marked[q[k]]; }
+            for (int k = 0; k < 8; k++) { m = fmaxFoam(m, e[k]); anyMarked |= mk[k]; }
             kp = (m < unrefineLevel) && !anyMarked;
         }
     }
     if (isSplit) isSplit[pt] = split;
     if (keep) keep[pt] = kp;
+}
+
+// per-point pre-filter of getSplitElems, mesh-constant: exactly 8 pointCells (hexRef3D.C:2214-2222), not on a
+// boundary face (:2279-2294) and -- when hexRef's pointLevel_ is supplied -- pointLevel >= 1: a point whose 8
+// cells share one parent is that parent's centre point, which setRefinement created with
+// pointLevel = cellLevel + 1 (hexRef3D.C:1238-1260), so level-0 points can never pass the history test.
+__global__ void __launch_bounds__(kThreads)
+k_point_class(int64_t p, const u8 *__restrict__ pcCount, const u8 *__restrict__ bndPoint, const label *__restrict__ pointLevel,
+              u8 *__restrict__ pcClass, unsigned long long *nCand) {
+    const int64_t pt = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int c = 0;
+    if (pt < p) {
+        c = (pcCount[pt] == 8) && !bndPoint[pt] && (!pointLevel || pointLevel[pt] >= 1);
+        pcClass[pt] = (u8)c;
+    }
+    const int cnt = __syncthreads_count(c);
+    if (threadIdx.x == 0 && cnt) atomicAdd(nCand, (unsigned long long)cnt);
 }
 
 // hexRef2D::getSplitElems (hexRef2D.C:2202-2342) + selectUnrefineElems filter (hexRef2D.C:1860-1906), one

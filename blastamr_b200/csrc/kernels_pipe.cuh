@@ -194,13 +194,13 @@ kp_refine_sweep(SellView S, u8 *lf, u8 *set, const u8 *ghostLf, int *changed) {
 }
 
 __global__ void __launch_bounds__(kPipeThreads, 7)
-kp_select_unrefine_points(SellView S, const u8 *__restrict__ pcCount, const u8 *__restrict__ bndPoint,
+kp_select_unrefine_points(SellView S, const u8 *__restrict__ pcClass,
                           const label *__restrict__ parentIdx, const u8 *__restrict__ lvl8,
                           const double *__restrict__ err, double unrefineLevel, const u8 *__restrict__ marked,
                           u8 *__restrict__ isSplit, u8 *__restrict__ keep) {
     sellPipeline(S, [&](int64_t pt, bool valid, const int32_t *row, int w, bool) {
         if (!valid) return;
-        bool split = (pcCount[pt] == 8) && !bndPoint[pt];
+        bool split = pcClass[pt] != 0;
         bool kp = false;
         if (split) {
             int32_t q[8];
