@@ -80,6 +80,7 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
 
 static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->owner); devFree(ctx, &ctx->neighbour); devFree(ctx, &ctx->bCoupled);
+    devFree(ctx, &ctx->cplFace); devFree(ctx, &ctx->cplCell); devFree(ctx, &ctx->cellGhost); ctx->nCplCells = 0;
     sellFree(ctx, ctx->cc); sellFree(ctx, ctx->pc);
     devFree(ctx, &ctx->bndPoint); devFree(ctx, &ctx->pcClass); ctx->pcClassDirty = true;
     devFree(ctx, &ctx->lvl); devFree(ctx, &ctx->lvl8); devFree(ctx, &ctx->parentIdx); devFree(ctx, &ctx->pointLevel);
@@ -410,6 +411,24 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     if (f) CK(cudaMemcpyAsync(ctx->neighbour, neighbour, (size_t)f * 4, cudaMemcpyDefault, ctx->stream));
     if (b) CK(cudaMemcpyAsync(ctx->bCoupled, coupled.data(), (size_t)b, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->nCoupled > 0) {
+        // compact lists of the coupled faces and of the cells that own them (host bookkeeping, once per mesh)
+        std::vector<label> bOwn((size_t)b);
+        CK(cudaMemcpy(bOwn.data(), ctx->owner + f, (size_t)b * 4, cudaMemcpyDeviceToHost));
+        std::vector<label> faces, cells;
+        faces.reserve((size_t)ctx->nCoupled);
+        for (int64_t i = 0; i < b; i++) if (coupled[(size_t)i]) { faces.push_back((label)i); cells.push_back(bOwn[(size_t)i]); }
+        std::sort(cells.begin(), cells.end());
+        cells.erase(std::unique(cells.begin(), cells.end()), cells.end());
+        ctx->nCplCells = (int64_t)cells.size();
+        TRY(devAlloc(ctx, &ctx->cplFace, (int64_t)faces.size()));
+        TRY(devAlloc(ctx, &ctx->cplCell, (int64_t)cells.size()));
+        TRY(devAlloc(ctx, &ctx->cellGhost, n + 16));
+        CK(cudaMemcpy(ctx->cplFace, faces.data(), faces.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->cplCell, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemsetAsync(ctx->cellGhost, 0, (size_t)n + 16, ctx->stream));
+        LAUNCH(k_list_to_flags, gridFor(ctx->nCplCells), kThreads, ctx->nCplCells, (const label *)ctx->cplCell, ctx->cellGhost);
+    }
     TRY(peerPlan(ctx));
     TRY(sellBuildCellCells(ctx));
     int64_t m = std::max(n, p);
@@ -651,16 +670,17 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
             const int32_t *so = ctx->cc.sliceOff, *col = ctx->cc.col;
 #define EST(K)                                                                                                   \
     do {                                                                                                         \
+        const u8 *cg = ctx->nCoupled > 0 ? (const u8 *)ctx->cellGhost : (const u8 *)nullptr;                     \
         if (pipeOk(ctx, ctx->cc)) {                                                                              \
-            if (ctx->nCoupled > 0) {                                                                             \
-                if (scale) TRY(launchPipe(ctx, kp_estimate<K, true, true>, ctx->cc, dx, ghost, p0, p1, t, target));  \
-                else TRY(launchPipe(ctx, kp_estimate<K, false, true>, ctx->cc, dx, ghost, p0, p1, t, target));       \
-            } else {                                                                                             \
-                if (scale) TRY(launchPipe(ctx, kp_estimate<K, true, false>, ctx->cc, dx, ghost, p0, p1, t, target)); \
-                else TRY(launchPipe(ctx, kp_estimate<K, false, false>, ctx->cc, dx, ghost, p0, p1, t, target));      \
-            }                                                                                                    \
-        } else if (scale) LAUNCH((k_estimate<K, true>), gridFor(n), kThreads, n, so, col, dx, ghost, p0, p1, t, target); \
-        else LAUNCH((k_estimate<K, false>), gridFor(n), kThreads, n, so, col, dx, ghost, p0, p1, t, target);      \
+            if (scale) TRY(launchPipe(ctx, kp_estimate<K, true>, ctx->cc, dx, p0, p1, t, cg, target));            \
+            else TRY(launchPipe(ctx, kp_estimate<K, false>, ctx->cc, dx, p0, p1, t, cg, target));                 \
+        } else if (scale) LAUNCH((k_estimate<K, true>), gridFor(n), kThreads, n, so, col, dx, cg, p0, p1, t, target); \
+        else LAUNCH((k_estimate<K, false>), gridFor(n), kThreads, n, so, col, dx, cg, p0, p1, t, target);        \
+        if (ctx->nCoupled > 0) {                                                                                 \
+            LAUNCH((k_fix_estimate<K>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, \
+                   (const label *)(ctx->owner + ctx->f), dx, ghost, p0, p1, target);                             \
+            if (scale) LAUNCH(k_fix_normalize, gridFor(ctx->nCplCells), kThreads, ctx->nCplCells, (const label *)ctx->cplCell, t, target); \
+        }                                                                                                        \
     } while (0)
             if (kind == AMR_EST_DELTA) EST(0);
             else if (kind == AMR_EST_SCALED_DELTA || kind == AMR_EST_DENSITY_GRADIENT) EST(1);
@@ -771,11 +791,11 @@ static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res) 
     if (ctx->nCoupled > 0) {
         TRY(haloSwapCells(ctx, src, 1, ctx->ghost8));
     }
-    if (pipeOk(ctx, ctx->cc)) {
-        if (ctx->nCoupled > 0) TRY(launchPipe(ctx, kp_extend<true>, ctx->cc, (const u8 *)cur, src, (const u8 *)ctx->ghost8, tmp));
-        else TRY(launchPipe(ctx, kp_extend<false>, ctx->cc, (const u8 *)cur, src, (const u8 *)ctx->ghost8, tmp));
-    }
+    if (pipeOk(ctx, ctx->cc)) TRY(launchPipe(ctx, kp_extend, ctx->cc, (const u8 *)cur, src, tmp));
     else LAUNCH(k_extend, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, cur, src, ctx->ghost8, tmp);
+    if (ctx->nCoupled > 0)
+        LAUNCH(k_fix_extend, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
+               (const u8 *)ctx->ghost8, tmp);
     *res = tmp;
     return AMR_OK;
 }
@@ -888,13 +908,16 @@ static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOu
         }
         if (n) {
             if (pipeOk(ctx, ctx->cc)) {
-                const bool g = ctx->nCoupled > 0;
-                if (maxSet && g) TRY(launchPipe(ctx, kp_refine_sweep<true, true>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
-                else if (maxSet) TRY(launchPipe(ctx, kp_refine_sweep<true, false>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
-                else if (g) TRY(launchPipe(ctx, kp_refine_sweep<false, true>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
-                else TRY(launchPipe(ctx, kp_refine_sweep<false, false>, ctx->cc, lf, set, (const u8 *)ctx->ghost8, ctx->dFlags));
+                if (maxSet) TRY(launchPipe(ctx, kp_refine_sweep<true>, ctx->cc, lf, set, ctx->dFlags));
+                else TRY(launchPipe(ctx, kp_refine_sweep<false>, ctx->cc, lf, set, ctx->dFlags));
             } else if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
             else LAUNCH(k_refine_sweep_min, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
+            if (ctx->nCoupled > 0) {      // hexRef.C:758-780
+                if (maxSet) LAUNCH((k_fix_refine_sweep<true>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
+                                   (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
+                else LAUNCH((k_fix_refine_sweep<false>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
+                            (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
+            }
         }
         sweeps++;
         TRY(emitListAsync(ctx, set, n, cellsOut, &job));
@@ -964,6 +987,9 @@ static int calcProtected(amr_ctx *ctx, u8 *unrefineable, bool *have) {
             TRY(haloSwapCells(ctx, unrefineable, 1, ctx->ghost8));
         }
         if (n) LAUNCH(k_protected_spread, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, unrefineable, ctx->ghost8, ghostLvl, ctx->dFlags + 1);
+        if (ctx->nCoupled > 0)
+            LAUNCH(k_fix_protected, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
+                   (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, (const u8 *)ghostLvl, unrefineable, ctx->dFlags + 1);
         int changed = 0;
         TRY(globalFlag(ctx, 1, &changed));
         if (!changed) break;
@@ -1195,6 +1221,9 @@ static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOu
             TRY(haloSwapCells(ctx, ctx->lvl8, 1, ctx->ghost8, uc));
         }
         if (n) LAUNCH(k_unrefine_sweep, gC, kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, uc, alC, ctx->ghost8, ctx->dFlags);
+        if (ctx->nCoupled > 0)      // hexRef3D.C:1855-1889
+            LAUNCH(k_fix_unrefine_sweep, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
+                   (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, uc, ctx->dFlags);
         // polyhedralRefinement.C:2278-2286: faceConsistentUnrefinement, then edgeConsistentUnrefinement
         if (edgeRule && ctx->nEdges)
             LAUNCH(k_edge_unrefine_sweep, gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, (const u8 *)ctx->lvl8, uc, ctx->dFlags);
@@ -1364,6 +1393,9 @@ AMR_API int amr_check_levels(amr_ctx *ctx, const int32_t *cellLevel, int64_t *nB
     }
     CK(cudaMemsetAsync(ctx->dCount, 0, 8, ctx->stream));
     if (n) LAUNCH(k_check_levels, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, dL, ghost, (unsigned long long *)ctx->dCount);
+    if (ctx->nCoupled > 0)
+        LAUNCH(k_fix_check_levels, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
+               dL, (const label *)ghost, (unsigned long long *)ctx->dCount);
     CK(cudaMemcpyAsync(ctx->hCount, ctx->dCount, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (nBad) *nBad = ctx->hCount[0];

@@ -73,6 +73,10 @@ struct amr_ctx {
     std::vector<Patch> patches;
     int64_t nCoupled = 0;
     u8 *bCoupled = nullptr;    // [b] boundary face lies on a processor patch
+    label *cplFace = nullptr;  // [nCoupled] boundary-face indices (face - f) of the coupled faces
+    label *cplCell = nullptr;  // [nCplCells] unique owners of coupled faces, ascending
+    int64_t nCplCells = 0;
+    u8 *cellGhost = nullptr;   // [n] cell owns a coupled face
     Sell cc;                   // cell -> face-neighbour cells (+ ghost slots n + bface for coupled faces)
     Sell pc;                   // point -> cells
     bool havePoints = false;

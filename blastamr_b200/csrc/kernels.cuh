@@ -45,8 +45,9 @@ __device__ __forceinline__ double fieldXform(double v, double offset, bool useOf
 template <int KIND, bool SCALE>
 __global__ void __launch_bounds__(kThreads)
 k_estimate(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-           const double *__restrict__ x, const double *__restrict__ ghost, double p0, double p1, Thresholds thr,
+           const double *__restrict__ x, const u8 *__restrict__ cellGhost, double p0, double p1, Thresholds thr,
            double *__restrict__ err) {
+    const double *ghost = nullptr;   // rows hold internal neighbours only; coupled faces: k_fix_estimate
     const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (c >= n) return;
     const int64_t s = c >> 5;
@@ -86,7 +87,7 @@ k_estimate(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__res
             e = fmaxFoam(e, eT);
         }
     }
-    err[c] = SCALE ? normalizeValue(e, thr) : e;
+    err[c] = (SCALE && !(cellGhost && cellGhost[c])) ? normalizeValue(e, thr) : e;
 }
 
 // fieldValue::update, fieldValue.C:68-82 (+ normalize); also the plain normalize pass (ABS=false)
@@ -786,6 +787,87 @@ k_knock_points(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *_
         }
         if (!ok) pflag[pt] = 0;
     });
+}
+
+// ------------------------------------------------------------------------------------------
+// Coupled (processor-patch) faces: boundary fix-ups
+// ------------------------------------------------------------------------------------------
+// The main kernels walk internal neighbours only; the few coupled faces are applied afterwards by
+// one thread per coupled face, exactly like the reference's second loop over boundary faces
+// (hexRef.C:758-780, delta.C:110-131, fvMeshRefiner.C:853-862).  cplFace = boundary-face indices
+// (face - f) of the coupled faces; ghost arrays are indexed by boundary face.
+
+// extendMarkedCells: a marked face on the other side marks my owner (syncFaceList orEqOp)
+__global__ void k_fix_extend(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                             const u8 *__restrict__ ghostSrc, u8 *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nC) return;
+    const label bf = cplFace[i];
+    if (ghostSrc[bf]) out[bOwner[bf]] = 1;
+}
+// hexRef::faceConsistentRefinement boundary loop, hexRef.C:758-780 (lf = level + flag)
+template <bool MAXSET>
+__global__ void k_fix_refine_sweep(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                                   const u8 *__restrict__ lvl8, const u8 *__restrict__ ghostLf, u8 *lf, u8 *set, int *changed) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nC) return;
+    const label bf = cplFace[i];
+    const label o = bOwner[bf];
+    const int ownLevel = (int)lvl8[o] + (int)set[o];
+    const int nei = ghostLf[bf];
+    if (MAXSET) { if (!set[o] && nei > ownLevel + 1) { set[o] = 1; lf[o] = (u8)(lvl8[o] + 1); *changed = 1; } }
+    else { if (set[o] && ownLevel > nei + 1) { set[o] = 0; lf[o] = lvl8[o]; *changed = 1; } }
+}
+// hexRef3D::consistentUnrefinement boundary loop, hexRef3D.C:1855-1889
+__global__ void k_fix_unrefine_sweep(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                                     const u8 *__restrict__ lvl8, const u8 *__restrict__ ghostLfm, u8 *uc, int *changed) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nC) return;
+    const label bf = cplFace[i];
+    const label o = bOwner[bf];
+    if (uc[o] && ((int)lvl8[o] - 1) < (int)ghostLfm[bf] - 1) { uc[o] = 0; *changed = 1; }
+}
+// calculateProtectedCells boundary part, fvMeshHexRefiner.C:113-128,157-170
+__global__ void k_fix_protected(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                                const u8 *__restrict__ lvl8, const u8 *__restrict__ ghostU, const u8 *__restrict__ ghostLvl,
+                                u8 *u, int *changed) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nC) return;
+    const label bf = cplFace[i];
+    const label o = bOwner[bf];
+    if (!u[o] && ghostU[bf] && (int)lvl8[o] > (int)ghostLvl[bf]) { u[o] = 1; *changed = 1; }
+}
+// checkRefinementLevels coupled part, hexRef.C:2988-3025
+__global__ void k_fix_check_levels(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                                   const label *__restrict__ lvl, const label *__restrict__ ghostLvl, unsigned long long *bad) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nC) return;
+    const label bf = cplFace[i];
+    if (abs(lvl[bOwner[bf]] - ghostLvl[bf]) > 1) atomicAdd(bad, 1ull);
+}
+// delta / scaledDelta / coded delta coupled-patch loop (delta.C:110-131, scaledDelta.C:112-136): the cells that own a
+// coupled face hold the RAW internal maximum (the main kernel does not normalise them); max is applied with an
+// integer atomicMax on the bit pattern (values are >= 0, so the order of doubles and of their bits agree: exact
+// and order-independent).  k_fix_normalize then normalises each such cell once.
+template <int KIND>
+__global__ void k_fix_estimate(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                               const double *__restrict__ x, const double *__restrict__ ghost, double p0, double p1,
+                               double *err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nC) return;
+    const label bf = cplFace[i];
+    const label o = bOwner[bf];
+    const bool useOffset = fabs(p1) > kSMALL;
+    const double fp = fieldXform<KIND>(x[o], p1, useOffset), fn = fieldXform<KIND>(ghost[bf], p1, useOffset);
+    double eT = fabs(fp - fn);                                           // delta.C:126 (no clamp)
+    if (KIND == 1) eT = eT / fmaxFoam(fminFoam(fp, fn), p0);             // scaledDelta.C:129-131
+    if (eT > 0.0) atomicMax(reinterpret_cast<unsigned long long *>(err + o), (unsigned long long)__double_as_longlong(eT));
+}
+__global__ void k_fix_normalize(int64_t nCells, const label *__restrict__ cplCell, Thresholds thr, double *err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nCells) return;
+    const label c = cplCell[i];
+    err[c] = normalizeValue(err[c], thr);
 }
 
 // ------------------------------------------------------------------------------------------

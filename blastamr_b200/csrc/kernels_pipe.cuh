@@ -49,29 +49,15 @@ __device__ __forceinline__ T gatherAt(const T *__restrict__ local, const T *ghos
     return local[q];
 }
 
-// Row bodies are templated on GHOST; the kernels pick the ghost-aware body per warp slice (only slices
-// that touch a processor patch contain ghost slots -- S.sliceGhost), so a decomposed mesh runs the plain
-// body on all interior slices.  (Measured: the ghost-aware body on every slice cost +50 % on kp_estimate.)
-template <int KIND, bool GHOST>
-__device__ __forceinline__ double estimateRow(const int32_t *row, int w, int32_t c, int32_t n, const double *__restrict__ x,
-                                              const double *ghostBase, double p0, double p1, bool useOffset) {
+// The adjacency holds internal neighbours only.  Coupled (processor-patch) faces are applied afterwards by the
+// k_fix_* kernels (kernels.cuh), one thread per coupled face -- the reference's own second loop over boundary
+// faces -- so a decomposed mesh runs exactly the single-rank kernels.  (Earlier versions kept ghost slots in the
+// rows: the ghost-aware walk cost +50 % on kp_estimate even when only 8 % of the slices had a ghost.)
+template <int KIND>
+__device__ __forceinline__ double estimateRow(const int32_t *row, int w, int32_t c, const double *__restrict__ x,
+                                              double p0, double p1, bool useOffset) {
     const double xc = fieldXform<KIND>(x[c], p1, useOffset);
-    double eL = 0.0, eG = 0.0;   // max over internal faces / over coupled-patch faces
-    if (GHOST) {
-        // slices on a processor patch (a few percent of the mesh): one neighbour at a time keeps the register
-        // footprint of this rarely taken path below that of the batched walk
-#pragma unroll 1
-        for (int j = 0; j < w; j++) {
-            const int32_t q = row[j << 5];
-            const bool g = q >= n;
-            const double xv = fieldXform<KIND>(g ? ghostBase[q] : x[q], p1, useOffset);
-            double eT = fabs(xc - xv);
-            if (KIND == 1) { eT = eT / fmaxFoam(fminFoam(xc, xv), p0); eT = (q == c) ? 0.0 : eT; }
-            if (KIND == 0 && !g) eT = fminFoam(eT, 0.5);          // delta.C:103 vs :126
-            eL = fmaxFoam(eL, eT);
-        }
-        return eL;
-    }
+    double eL = 0.0;
     sellRow(row, w, c, [&](auto W, const int32_t *q) {
         constexpr int NW = decltype(W)::value;
         double v[NW];
@@ -82,108 +68,75 @@ __device__ __forceinline__ double estimateRow(const int32_t *row, int w, int32_t
             const double xv = fieldXform<KIND>(v[k], p1, useOffset);
             double eT = fabs(xc - xv);
             if (KIND == 1) {
-                eT = eT / fmaxFoam(fminFoam(xc, xv), p0);     // scaledDelta.C:103-104,129-131
+                eT = eT / fmaxFoam(fminFoam(xc, xv), p0);     // scaledDelta.C:103-104
                 eT = (q[k] == c) ? 0.0 : eT;                  // padding (0/0 guard)
             }
             eL = fmaxFoam(eL, eT);
         }
     });
-    // delta clamps internal faces only (delta.C:103 vs :126); min(max_j d_j, .5) == max_j min(d_j, .5)
-    (void)eG;
+    // delta clamps internal faces (delta.C:103); min(max_j d_j, .5) == max_j min(d_j, .5)
     return (KIND == 0) ? fminFoam(eL, 0.5) : eL;
 }
 
-template <int KIND, bool SCALE, bool GHOST>
+// cellGhost (nullable): cells that own a coupled face keep the RAW value; k_fix_estimate / k_fix_normalize finish them
+template <int KIND, bool SCALE>
 __global__ void __launch_bounds__(kPipeThreads, (KIND == 1) ? 4 : 7)
-kp_estimate(SellView S, const double *__restrict__ x, const double *ghost, double p0, double p1, Thresholds thr,
+kp_estimate(SellView S, const double *__restrict__ x, double p0, double p1, Thresholds thr, const u8 *__restrict__ cellGhost,
             double *__restrict__ err) {
     const int32_t n = (int32_t)S.rows;
     const bool useOffset = fabs(p1) > kSMALL;
-    const double *ghostBase = ghost - n;
     sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool ghostSlice) {
         const int32_t c = valid ? (int32_t)c64 : n - 1;
-        double e;
-        if (GHOST && ghostSlice) e = estimateRow<KIND, true>(row, w, c, n, x, ghostBase, p0, p1, useOffset);
-        else e = estimateRow<KIND, false>(row, w, c, n, x, ghostBase, p0, p1, useOffset);
-        if (valid) err[c] = SCALE ? normalizeValue(e, thr) : e;
+        const double e = estimateRow<KIND>(row, w, c, x, p0, p1, useOffset);
+        if (valid) {
+            const bool raw = !SCALE || (ghostSlice && cellGhost[c]);
+            err[c] = raw ? e : normalizeValue(e, thr);
+        }
     });
 }
 
-template <bool GHOST>
-__device__ __forceinline__ unsigned extendRow(const int32_t *row, int w, int32_t c, int32_t n, unsigned m,
-                                              const u8 *__restrict__ src, const u8 *ghostBase) {
-    if (GHOST) {
-#pragma unroll 1
-        for (int j = 0; j < w; j++) { const int32_t q = row[j << 5]; m |= (q < n) ? src[q] : ghostBase[q]; }
-        return m;
-    }
-    sellRow(row, w, c, [&](auto W, const int32_t *q) {
-        constexpr int NW = decltype(W)::value;
-        unsigned v[NW];
-#pragma unroll
-        for (int k = 0; k < NW; k++) v[k] = src[q[k]];
-#pragma unroll
-        for (int k = 0; k < NW; k++) m |= v[k];   // padding reads src[c] <= in[c]: no-op
-    });
-    return m;
-}
-
-template <bool GHOST>
 __global__ void __launch_bounds__(kPipeThreads, 7)
-kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, const u8 *ghost, u8 *__restrict__ out) {
+kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, u8 *__restrict__ out) {
     const int32_t n = (int32_t)S.rows;
-    const u8 *ghostBase = ghost - n;
-    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool ghostSlice) {
+    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool) {
         const int32_t c = valid ? (int32_t)c64 : n - 1;
         unsigned m = in[c];
         // a warp whose 32 cells are all marked has nothing to gather
         if (!__all_sync(0xffffffffu, m != 0)) {
-            if (GHOST && ghostSlice) m = extendRow<true>(row, w, c, n, m, src, ghostBase);
-            else m = extendRow<false>(row, w, c, n, m, src, ghostBase);
+            sellRow(row, w, c, [&](auto W, const int32_t *q) {
+                constexpr int NW = decltype(W)::value;
+                unsigned v[NW];
+#pragma unroll
+                for (int k = 0; k < NW; k++) v[k] = src[q[k]];
+#pragma unroll
+                for (int k = 0; k < NW; k++) m |= v[k];   // padding reads src[c] <= in[c]: no-op
+            });
         }
         if (valid) out[c] = m ? 1 : 0;
     });
 }
 
-template <bool MAXSET, bool GHOST>
-__device__ __forceinline__ int sweepRow(const int32_t *row, int w, int32_t c, int32_t n, int mine, const u8 *lf,
-                                        const u8 *ghostBase) {
-    int ext = mine;      // padding contributes the cell's own value: neutral for max and min
-    if (GHOST) {
-#pragma unroll 1
-        for (int j = 0; j < w; j++) {
-            const int32_t q = row[j << 5];
-            const int v = (q < n) ? lf[q] : ghostBase[q];
-            ext = MAXSET ? max(ext, v) : min(ext, v);
-        }
-        return ext;
-    }
-    sellRow(row, w, c, [&](auto W, const int32_t *q) {
-        constexpr int NW = decltype(W)::value;
-        int v[NW];
-#pragma unroll
-        for (int k = 0; k < NW; k++) v[k] = lf[q[k]];
-#pragma unroll
-        for (int k = 0; k < NW; k++) ext = MAXSET ? max(ext, v[k]) : min(ext, v[k]);
-    });
-    return ext;
-}
-
-template <bool MAXSET, bool GHOST>
+template <bool MAXSET>
 __global__ void __launch_bounds__(kPipeThreads, 7)
-kp_refine_sweep(SellView S, u8 *lf, u8 *set, const u8 *ghostLf, int *changed) {
+kp_refine_sweep(SellView S, u8 *lf, u8 *set, int *changed) {
     const int32_t n = (int32_t)S.rows;
-    const u8 *ghostBase = ghostLf - n;
-    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool ghostSlice) {
+    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool) {
         const int32_t c = valid ? (int32_t)c64 : n - 1;
         const int isSet = set[c];
         int flip = 0;
         const bool idle = MAXSET ? __all_sync(0xffffffffu, isSet != 0) : !__any_sync(0xffffffffu, isSet != 0);
         if (!idle) {
             const int mine = lf[c];
-            int ext;
-            if (GHOST && ghostSlice) ext = sweepRow<MAXSET, true>(row, w, c, n, mine, (const u8 *)lf, ghostBase);
-            else ext = sweepRow<MAXSET, false>(row, w, c, n, mine, (const u8 *)lf, ghostBase);
+            int ext = mine;      // padding contributes the cell's own value: neutral for max and min
+            const u8 *lfr = lf;
+            sellRow(row, w, c, [&](auto W, const int32_t *q) {
+                constexpr int NW = decltype(W)::value;
+                int v[NW];
+#pragma unroll
+                for (int k = 0; k < NW; k++) v[k] = lfr[q[k]];
+#pragma unroll
+                for (int k = 0; k < NW; k++) ext = MAXSET ? max(ext, v[k]) : min(ext, v[k]);
+            });
             if (valid) {
                 if (MAXSET) { if (!isSet && ext > mine + 1) { set[c] = 1; lf[c] = (u8)(mine + 1); flip = 1; } }
                 else { if (isSet && mine > ext + 1) { set[c] = 0; lf[c] = (u8)(mine - 1); flip = 1; } }

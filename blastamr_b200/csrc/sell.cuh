@@ -122,6 +122,11 @@ __global__ void k_slice_ghost(const int32_t *__restrict__ col, const int32_t *__
     if (d > 0 && row[(size_t)(d - 1) << 5] >= rows) sliceGhost[r >> 5] = 1;
 }
 
+__global__ void k_slice_ghost_cells(const u8 *__restrict__ cellGhost, int64_t rows, u8 *__restrict__ sliceGhost) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows && cellGhost[r]) sliceGhost[r >> 5] = 1;
+}
+
 static void sellFree(amr_ctx *ctx, Sell &S) {
     if (S.sliceGhost) { cudaFree(S.sliceGhost); }
     if (S.sliceOff) { cudaFree(S.sliceOff); ctx->devBytes -= (int64_t)((S.slices + kSliceOffPad) * 4); }
@@ -173,16 +178,14 @@ static int sellBuildCellCells(amr_ctx *ctx) {
     CK(cudaMemsetAsync(deg, 0, (size_t)(n + 1) * 4, ctx->stream));
     CK(cudaMemsetAsync(cursor, 0, (size_t)(n + 1) * 4, ctx->stream));
     if (f > 0) LAUNCH(k_deg_internal, gridFor(f), kThreads, ctx->owner, ctx->neighbour, f, deg);
-    if (b > 0 && ctx->nCoupled > 0) LAUNCH(k_deg_coupled, gridFor(b), kThreads, ctx->owner + f, ctx->bCoupled, b, deg);
     int rc = sellAllocFromDeg(ctx, ctx->cc, n, deg, 1);
     if (rc == AMR_OK) {
         if (f > 0) LAUNCH(k_sell_fill_internal, gridFor(f), kThreads, ctx->owner, ctx->neighbour, f, ctx->cc.sliceOff, cursor, ctx->cc.col);
-        if (b > 0 && ctx->nCoupled > 0)
-            LAUNCH(k_sell_fill_coupled, gridFor(b), kThreads, ctx->owner + f, ctx->bCoupled, b, n, ctx->cc.sliceOff, cursor, ctx->cc.col);
         if (n > 0) LAUNCH(k_sell_sort_rows, gridFor(n), kThreads, ctx->cc.col, ctx->cc.sliceOff, deg, n);
         if (cudaMalloc((void **)&ctx->cc.sliceGhost, (size_t)ctx->cc.slices + 16) == cudaSuccess) {
             cudaMemsetAsync(ctx->cc.sliceGhost, 0, (size_t)ctx->cc.slices + 16, ctx->stream);
-            if (n > 0 && ctx->nCoupled > 0) LAUNCH(k_slice_ghost, gridFor(n), kThreads, ctx->cc.col, ctx->cc.sliceOff, deg, n, ctx->cc.sliceGhost);
+            // slices containing a cell that owns a coupled face (cellGhost is built by amr_mesh_set)
+            if (n > 0 && ctx->nCoupled > 0 && ctx->cellGhost) LAUNCH(k_slice_ghost_cells, gridFor(n), kThreads, (const u8 *)ctx->cellGhost, n, ctx->cc.sliceGhost);
         }
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { ctx->err = std::string("sellBuildCellCells: ") + cudaGetErrorString(e); rc = AMR_ERR_CUDA; }
