@@ -82,7 +82,7 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->owner); devFree(ctx, &ctx->neighbour); devFree(ctx, &ctx->bCoupled);
     devFree(ctx, &ctx->cplFace); devFree(ctx, &ctx->cplCell); devFree(ctx, &ctx->cellGhost); ctx->nCplCells = 0;
     sellFree(ctx, ctx->cc); sellFree(ctx, ctx->pc);
-    devFree(ctx, &ctx->bndPoint); devFree(ctx, &ctx->pcClass); ctx->pcClassDirty = true;
+    devFree(ctx, &ctx->bndPoint); devFree(ctx, &ctx->pcClass); devFree(ctx, &ctx->candList); ctx->pcClassDirty = true;
     devFree(ctx, &ctx->lvl); devFree(ctx, &ctx->lvl8); devFree(ctx, &ctx->parentIdx); devFree(ctx, &ctx->pointLevel);
     devFree(ctx, &ctx->protCell);
     devFree(ctx, &ctx->error); devFree(ctx, &ctx->refineCell);
@@ -1192,12 +1192,25 @@ static int selectUnrefinePoints(amr_ctx *ctx, const double *dErr, double unrefin
         CK(cudaMemcpyAsync(ctx->hCount + 2, ctx->dCount + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->nSplitCand = ctx->hCount[2];
+        devFree(ctx, &ctx->candList);
+        if (ctx->nSplitCand * 2 <= p) {       // sparse: keep an ascending candidate list (mesh-constant, like pcClass)
+            TRY(devAlloc(ctx, &ctx->candList, ctx->nSplitCand));
+            int32_t *dTotal = nullptr;
+            TRY(compactFlags(ctx, ctx->pcClass, p, ctx->candList, &dTotal));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
         ctx->pcClassDirty = false;
     }
     if (pipeOk(ctx, ctx->pc) && ctx->nSplitCand * 2 > p)
         TRY(launchPipe(ctx, kp_select_unrefine_points, ctx->pc, (const u8 *)ctx->pcClass, (const label *)ctx->parentIdx,
                        (const u8 *)ctx->lvl8, dErr, unrefineLevel, dRc, isSplit, keep));
-    else
+    else if (ctx->candList) {
+        if (isSplit) CK(cudaMemsetAsync(isSplit, 0, (size_t)p, ctx->stream));
+        if (keep) CK(cudaMemsetAsync(keep, 0, (size_t)p, ctx->stream));
+        if (ctx->nSplitCand)
+            LAUNCH(k_select_unrefine_cand, gridFor(ctx->nSplitCand), kThreads, ctx->nSplitCand, (const label *)ctx->candList, ctx->pc.sliceOff,
+                   ctx->pc.col, (const label *)ctx->parentIdx, (const u8 *)ctx->lvl8, dErr, unrefineLevel, dRc, isSplit, keep);
+    } else
         LAUNCH(k_select_unrefine_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const u8 *)ctx->pcClass,
                (const label *)ctx->parentIdx, (const u8 *)ctx->lvl8, dErr, unrefineLevel, dRc, isSplit, keep);
     return AMR_OK;

@@ -100,6 +100,7 @@ struct amr_ctx {
     u8 *pcClass = nullptr;     // [p] split-point pre-filter (see k_point_class); rebuilt when points/levels change
     bool pcClassDirty = true;
     int64_t nSplitCand = 0;
+    label *candList = nullptr;  // [nSplitCand] ascending candidate points (sparse case)
 
     // levels / history
     bool haveLevels = false, haveHistory = false;

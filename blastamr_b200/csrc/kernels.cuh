@@ -525,6 +525,43 @@ k_select_unrefine_points(int64_t p, const int32_t *__restrict__ sliceOff, const 
     if (keep) keep[pt] = kp;
 }
 
+// same, over a compact ascending list of the candidate points (sparse case: most points of a mesh cannot be
+// split points, so neither their rows nor empty CTAs are touched); non-candidates keep the pre-zeroed flag
+__global__ void __launch_bounds__(kThreads)
+k_select_unrefine_cand(int64_t nCand, const label *__restrict__ cand, const int32_t *__restrict__ sliceOff,
+                       const int32_t *__restrict__ col, const label *__restrict__ parentIdx, const u8 *__restrict__ lvl8,
+                       const double *__restrict__ err, double unrefineLevel, const u8 *__restrict__ marked,
+                       u8 *__restrict__ isSplit, u8 *__restrict__ keep) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= nCand) return;
+    const int64_t pt = cand[i];
+    const int32_t *row = col + ((size_t)sliceOff[pt >> 5] << 5) + (pt & 31);
+    int32_t q[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) q[k] = row[(size_t)k << 5];
+    label par[8];
+    int l[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { par[k] = parentIdx[q[k]]; l[k] = lvl8[q[k]]; }
+    bool split = par[0] >= 0;
+#pragma unroll
+    for (int k = 1; k < 8; k++) split = split && (par[k] == par[0]) && (l[k] == l[0]);
+    bool kp = false;
+    if (split && keep) {
+        double e[8];
+        unsigned mk[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { e[k] = err[q[k]]; mk[k] = marked[q[k]]; }
+        double m = -kGREAT;
+        unsigned anyMarked = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { m = fmaxFoam(m, e[k]); anyMarked |= mk[k]; }
+        kp = (m < unrefineLevel) && !anyMarked;
+    }
+    if (isSplit && split) isSplit[pt] = 1;
+    if (keep && kp) keep[pt] = 1;
+}
+
 // per-point pre-filter of getSplitElems, mesh-constant: exactly 8 pointCells (hexRef3D.C:2214-2222), not on a
 // boundary face (:2279-2294) and -- when hexRef's pointLevel_ is supplied -- pointLevel >= 1: a point whose 8
 // cells share one parent is that parent's centre point, which setRefinement created with
