@@ -87,7 +87,7 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->protCell);
     devFree(ctx, &ctx->error); devFree(ctx, &ctx->refineCell);
     devFree(ctx, &ctx->flagA); devFree(ctx, &ctx->flagB); devFree(ctx, &ctx->flagC); devFree(ctx, &ctx->lf);
-    devFree(ctx, &ctx->ghost8); devFree(ctx, &ctx->send8); devFree(ctx, &ctx->ghost64); devFree(ctx, &ctx->send64);
+    devFree(ctx, &ctx->ghost8); devFree(ctx, &ctx->ghost64);
     devFree(ctx, &ctx->tileCnt); devFree(ctx, &ctx->scanAux);
     devFree(ctx, &ctx->gWeights); devFree(ctx, &ctx->gSf); devFree(ctx, &ctx->gMagSf); devFree(ctx, &ctx->gDelta); devFree(ctx, &ctx->gV);
     devFree(ctx, &ctx->grad); devFree(ctx, &ctx->xbf);
@@ -171,15 +171,6 @@ AMR_API int64_t amr_device_bytes(const amr_ctx *ctx) { return ctx ? ctx->devByte
 
 // ---- NVLink peer-memory transport (p2p.cuh) ----------------------------------------------------------
 
-static int peerCheckError(amr_ctx *ctx) {
-    if (!ctx->usePeer) return AMR_OK;
-    int e = 0;
-    CK(cudaMemcpyAsync(&e, ctx->region + offsetof(P2PRegionHeader, error), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (e) FAIL(AMR_ERR_STATE, "peer-memory halo swap timed out (a neighbour rank did not enter the same call)");
-    return AMR_OK;
-}
-
 // all ranks map each other's region; NCCL is only the transport for the 64-byte IPC handles
 static int peerSetup(amr_ctx *ctx) {
     const char *mode = getenv("AMR_B200_HALO");
@@ -261,27 +252,12 @@ static int peerPlan(amr_ctx *ctx) {
     return AMR_OK;
 }
 
-// syncTools::swapBoundaryFaceList / syncFaceList payload exchange: for every processor patch send
+// NCCL transport of a swap (fallback / AMR_B200_HALO=nccl): for every processor patch send
 // my boundary-face values [patchStart-f, +size) and receive the neighbour's into the same range
 // of `recv` (processor patch pairs list their faces in the same order on both sides).
 static int haloExchange(amr_ctx *ctx, const void *send, void *recv, size_t elemBytes) {
     if (ctx->nCoupled == 0) return AMR_OK;
     if (!ctx->comm) FAIL(AMR_ERR_STATE, "mesh has processor patches but no communicator (amr_comm_init) and no host-side neighbour values");
-    if (ctx->usePeer && ctx->havePlan && (int64_t)ctx->b * (int64_t)elemBytes <= kHaloCap) {
-        const HaloPlan &P = *(const HaloPlan *)ctx->haloPlan;
-        const unsigned epoch = ++ctx->haloEpoch;
-        const int parity = (int)(epoch & 1u);
-        const unsigned g = gridFor(P.prefix[P.nPatch]);
-        if (elemBytes == 1) k_halo_push<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, (const char *)send);
-        else if (elemBytes == 4) k_halo_push<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, (const char *)send);
-        else k_halo_push<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, (const char *)send);
-        k_halo_signal<<<1, 32, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch);
-        if (elemBytes == 1) k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
-        else if (elemBytes == 4) k_halo_unpack<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
-        else k_halo_unpack<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
-        ctx->launches += 3;
-        return AMR_OK;
-    }
     NCK(ncclGroupStart());
     for (const Patch &q : ctx->patches) {
         if (q.type != AMR_PATCH_PROCESSOR || q.size == 0) continue;
@@ -370,7 +346,9 @@ static int globalFlag(amr_ctx *ctx, int slot, int *value) {
 static int globalSum(amr_ctx *ctx, int slot, int64_t *value) {
     TRY(allReduceWord(ctx, ctx->dCount + slot, 1));
     CK(cudaMemcpyAsync(ctx->hCount + slot, ctx->dCount + slot, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PEER_ERR_FETCH();
     CK(cudaStreamSynchronize(ctx->stream));
+    PEER_ERR_CHECK();
     *value = ctx->hCount[slot];
     return AMR_OK;
 }
@@ -437,8 +415,8 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     TRY(devAlloc(ctx, &ctx->lf, n + 16));
     TRY(devAlloc(ctx, &ctx->error, n));
     TRY(devAlloc(ctx, &ctx->refineCell, m + 16));
-    TRY(devAlloc(ctx, &ctx->ghost8, b + 16)); TRY(devAlloc(ctx, &ctx->send8, b + 16));
-    TRY(devAlloc(ctx, &ctx->ghost64, b + 2)); TRY(devAlloc(ctx, &ctx->send64, b + 2));
+    TRY(devAlloc(ctx, &ctx->ghost8, b + 16));
+    TRY(devAlloc(ctx, &ctx->ghost64, b + 2));
     ctx->tileCap = (m + kTile - 1) / kTile + 8;
     TRY(devAlloc(ctx, &ctx->tileCnt, ctx->tileCap));
     ctx->scanAuxCap = 2 * (ctx->tileCap / kScanTile + 1024);
@@ -787,12 +765,12 @@ AMR_API int amr_normalize_range(amr_ctx *ctx, double refineThreshold, double unr
 // one face-layer growth of `cur` (n flags) with ping-pong buffer `tmp`; src == cur.  Returns the
 // buffer holding the result in *res.
 static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res) {
-    const int64_t n = ctx->n, b = ctx->b;
+    const int64_t n = ctx->n;
     if (ctx->nCoupled > 0) {
         TRY(haloSwapCells(ctx, src, 1, ctx->ghost8));
     }
     if (pipeOk(ctx, ctx->cc)) TRY(launchPipe(ctx, kp_extend, ctx->cc, (const u8 *)cur, src, tmp));
-    else LAUNCH(k_extend, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, cur, src, ctx->ghost8, tmp);
+    else LAUNCH(k_extend, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, cur, src, tmp);
     if (ctx->nCoupled > 0)
         LAUNCH(k_fix_extend, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
                (const u8 *)ctx->ghost8, tmp);
@@ -893,7 +871,7 @@ static int emitList(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *userOut, 
 // convergence flag and the list size come back in ONE host round trip per sweep.
 static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut,
                         bool edgeRule = false) {
-    const int64_t n = ctx->n, b = ctx->b;
+    const int64_t n = ctx->n;
     int sweeps = 0;
     ListJob job;
     while (true) {
@@ -910,8 +888,8 @@ static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOu
             if (pipeOk(ctx, ctx->cc)) {
                 if (maxSet) TRY(launchPipe(ctx, kp_refine_sweep<true>, ctx->cc, lf, set, ctx->dFlags));
                 else TRY(launchPipe(ctx, kp_refine_sweep<false>, ctx->cc, lf, set, ctx->dFlags));
-            } else if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
-            else LAUNCH(k_refine_sweep_min, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->ghost8, ctx->dFlags);
+            } else if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->dFlags);
+            else LAUNCH(k_refine_sweep_min, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->dFlags);
             if (ctx->nCoupled > 0) {      // hexRef.C:758-780
                 if (maxSet) LAUNCH((k_fix_refine_sweep<true>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
                                    (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
@@ -937,8 +915,7 @@ static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOu
 // of both sides -> dedicated kernel.
 __global__ void __launch_bounds__(kThreads)
 k_protected_spread(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-                   const u8 *__restrict__ lvl8, u8 *__restrict__ u, const u8 *__restrict__ ghostU,
-                   const u8 *__restrict__ ghostLvl, int *changed) {
+                   const u8 *__restrict__ lvl8, u8 *__restrict__ u, int *changed) {
     // cell c becomes unrefineable when a face neighbour q is unrefineable and level[c] > level[q]
     // (seedFace rule, fvMeshHexRefiner.C:101-128, then both cells of a seed face are set :137-170;
     // the coarser one already is)
@@ -952,9 +929,7 @@ k_protected_spread(int64_t n, const int32_t *__restrict__ sliceOff, const int32_
         for (int j = 0; j < w; j++) {
             int32_t q = row[(size_t)j << 5];
             if (q == (int32_t)c) continue;
-            int uq, lq;
-            if (q < n) { uq = u[q]; lq = lvl8[q]; } else { uq = ghostU[q - n]; lq = ghostLvl[q - n]; }
-            if (uq && mine > lq) { flip = 1; break; }
+            if (u[q] && mine > (int)lvl8[q]) { flip = 1; break; }   // coupled faces: k_fix_protected
         }
         if (flip) u[c] = 1;
     }
@@ -986,7 +961,7 @@ static int calcProtected(amr_ctx *ctx, u8 *unrefineable, bool *have) {
         if (ctx->nCoupled > 0) {
             TRY(haloSwapCells(ctx, unrefineable, 1, ctx->ghost8));
         }
-        if (n) LAUNCH(k_protected_spread, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, unrefineable, ctx->ghost8, ghostLvl, ctx->dFlags + 1);
+        if (n) LAUNCH(k_protected_spread, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, unrefineable, ctx->dFlags + 1);
         if (ctx->nCoupled > 0)
             LAUNCH(k_fix_protected, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
                    (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, (const u8 *)ghostLvl, unrefineable, ctx->dFlags + 1);
@@ -1220,7 +1195,7 @@ static int selectUnrefinePoints(amr_ctx *ctx, const double *dErr, double unrefin
 // (hexRef3D.C:1930-1950), list compacted speculatively after each sweep (one round trip per sweep)
 static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOut, int32_t *elemsOut, int64_t *nOut,
                           bool edgeRule = false) {
-    const int64_t n = ctx->n, b = ctx->b, p = EL.rows;
+    const int64_t n = ctx->n, p = EL.rows;
     u8 *uc = ctx->flagB;     // unrefineCell
     const bool alP = (((uintptr_t)pflag) & 15) == 0, alC = (((uintptr_t)uc) & 15) == 0;
     const unsigned gP = gridFor(p, kThreads * 16), gC = gridFor(n, kThreads * 16);
@@ -1233,7 +1208,7 @@ static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOu
         if (ctx->nCoupled > 0) {
             TRY(haloSwapCells(ctx, ctx->lvl8, 1, ctx->ghost8, uc));
         }
-        if (n) LAUNCH(k_unrefine_sweep, gC, kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, uc, alC, ctx->ghost8, ctx->dFlags);
+        if (n) LAUNCH(k_unrefine_sweep, gC, kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, uc, alC, ctx->dFlags);
         if (ctx->nCoupled > 0)      // hexRef3D.C:1855-1889
             LAUNCH(k_fix_unrefine_sweep, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
                    (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, uc, ctx->dFlags);
@@ -1397,15 +1372,14 @@ AMR_API int amr_check_levels(amr_ctx *ctx, const int32_t *cellLevel, int64_t *nB
     TRY(stageIn(ctx, cellLevel, n, &dL));
     if (!dL) dL = ctx->lvl;
     if (!dL) FAIL(AMR_ERR_STATE, "amr_check_levels: no levels");
-    label *ghost = nullptr, *send = nullptr;
+    label *ghost = nullptr;
     if (ctx->nCoupled > 0) {
         void *q;
         TRY(arenaAlloc(ctx, &q, (size_t)b * 4)); ghost = (label *)q;
-        (void)send;
         TRY(haloSwapCells(ctx, dL, 4, ghost));
     }
     CK(cudaMemsetAsync(ctx->dCount, 0, 8, ctx->stream));
-    if (n) LAUNCH(k_check_levels, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, dL, ghost, (unsigned long long *)ctx->dCount);
+    if (n) LAUNCH(k_check_levels, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, dL, (unsigned long long *)ctx->dCount);
     if (ctx->nCoupled > 0)
         LAUNCH(k_fix_check_levels, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
                dL, (const label *)ghost, (unsigned long long *)ctx->dCount);

@@ -124,8 +124,8 @@ struct amr_ctx {
     u8 *flagA = nullptr, *flagB = nullptr;      // [max(n,p)]
     u8 *flagC = nullptr;                        // [max(n,p)]
     u8 *lf = nullptr;                           // [n] level +/- flag
-    u8 *ghost8 = nullptr, *send8 = nullptr;     // [b]
-    double *ghost64 = nullptr, *send64 = nullptr; // [b]
+    u8 *ghost8 = nullptr;       // [b] received byte payloads (marks, level +/- flag), boundary-face layout
+    double *ghost64 = nullptr;  // [b] received field values
     int32_t *tileCnt = nullptr;                 // compaction tile counters
     int64_t tileCap = 0;
     int32_t *scanAux = nullptr; int64_t scanAuxCap = 0;

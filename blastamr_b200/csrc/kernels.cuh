@@ -47,7 +47,6 @@ __global__ void __launch_bounds__(kThreads)
 k_estimate(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
            const double *__restrict__ x, const u8 *__restrict__ cellGhost, double p0, double p1, Thresholds thr,
            double *__restrict__ err) {
-    const double *ghost = nullptr;   // rows hold internal neighbours only; coupled faces: k_fix_estimate
     const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (c >= n) return;
     const int64_t s = c >> 5;
@@ -64,16 +63,10 @@ k_estimate(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__res
         for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
         double xq[kChunk];
 #pragma unroll
-        for (int k = 0; k < kChunk; k++) {
-            if (q[k] < n) xq[k] = x[q[k]];
-            else xq[k] = ghost[q[k] - n];
-        }
+        for (int k = 0; k < kChunk; k++) xq[k] = x[q[k]];   // internal neighbours only; coupled faces: k_fix_estimate
 #pragma unroll
         for (int k = 0; k < kChunk; k++) {
             if (q[k] == (int32_t)c) continue;   // padding
-            // local and ghost values get the same mag()/offset transform: the ghost array holds the
-            // neighbour rank's raw cell values (scaledDelta.C:116-124 reads them from the temporary
-            // field whose processor patches carry mag(field) - offset of the other side)
             double v = fieldXform<KIND>(xq[k], p1, useOffset);
             double eT;
             if (KIND == 0) {
@@ -228,7 +221,7 @@ __global__ void k_pack_u8(int64_t b, const label *__restrict__ bOwner, const u8 
 // the other side of a processor face.
 __global__ void __launch_bounds__(kThreads)
 k_extend(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-         const u8 *__restrict__ in, const u8 *__restrict__ src, const u8 *__restrict__ ghost,
+         const u8 *__restrict__ in, const u8 *__restrict__ src,
          u8 *__restrict__ out) {
     const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const unsigned live = __ballot_sync(0xffffffffu, c < n);
@@ -248,7 +241,7 @@ k_extend(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restr
 #pragma unroll
         for (int k = 0; k < kChunk; k++) {
             if (q[k] == (int32_t)c) continue;
-            m |= (q[k] < n) ? src[q[k]] : ghost[q[k] - n];
+            m |= src[q[k]];
         }
     }
     out[c] = m ? 1 : 0;
@@ -346,7 +339,7 @@ k_count_flags(int64_t n, const u8 *__restrict__ flag, unsigned long long *count)
 // (__syncthreads_or + one store per CTA: the reduce(nChanged) of hexRef.C:1424).
 __global__ void __launch_bounds__(kThreads)
 k_refine_sweep_max(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-                   u8 *__restrict__ lf, u8 *__restrict__ set, const u8 *__restrict__ ghostLf, int *changed) {
+                   u8 *__restrict__ lf, u8 *__restrict__ set, int *changed) {
     const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const unsigned live = __ballot_sync(0xffffffffu, c < n);
     int flip = 0;
@@ -367,8 +360,7 @@ k_refine_sweep_max(int64_t n, const int32_t *__restrict__ sliceOff, const int32_
                 for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
 #pragma unroll
                 for (int k = 0; k < kChunk; k++) {
-                    int v = (q[k] < n) ? lf[q[k]] : ghostLf[q[k] - n];
-                    mx = max(mx, v);
+                    mx = max(mx, (int)lf[q[k]]);
                 }
             }
             if (!isSet && mx > mine + 1) { set[c] = 1; lf[c] = (u8)(mine + 1); flip = 1; }
@@ -381,7 +373,7 @@ k_refine_sweep_max(int64_t n, const int32_t *__restrict__ sliceOff, const int32_
 // end up more than one level finer than a face neighbour.  Monotone decreasing -> greatest fixed point.
 __global__ void __launch_bounds__(kThreads)
 k_refine_sweep_min(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-                   u8 *__restrict__ lf, u8 *__restrict__ set, const u8 *__restrict__ ghostLf, int *changed) {
+                   u8 *__restrict__ lf, u8 *__restrict__ set, int *changed) {
     const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const unsigned live = __ballot_sync(0xffffffffu, c < n);
     int flip = 0;
@@ -401,8 +393,7 @@ k_refine_sweep_min(int64_t n, const int32_t *__restrict__ sliceOff, const int32_
                 for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
 #pragma unroll
                 for (int k = 0; k < kChunk; k++) {
-                    int v = (q[k] < n) ? lf[q[k]] : ghostLf[q[k] - n];
-                    mn = min(mn, v);
+                    mn = min(mn, (int)lf[q[k]]);
                 }
             }
             if (isSet && mine > mn + 1) { set[c] = 0; lf[c] = (u8)(mine - 1); flip = 1; }
@@ -416,7 +407,7 @@ k_refine_sweep_min(int64_t n, const int32_t *__restrict__ sliceOff, const int32_
 // faces once from their owner, like the reference's boundary loop)
 __global__ void __launch_bounds__(kThreads)
 k_check_levels(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-               const label *__restrict__ lvl, const label *__restrict__ ghostLvl, unsigned long long *bad) {
+               const label *__restrict__ lvl, unsigned long long *bad) {
     const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     int cnt = 0;
     if (c < n) {
@@ -429,8 +420,7 @@ k_check_levels(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *_
         for (int j = 0; j < w; j++) {
             int32_t q = row[(size_t)j << 5];
             if (q == (int32_t)c) continue;
-            if (q < n) { if (q > c && abs(mine - lvl[q]) > 1) cnt++; }
-            else if (abs(mine - ghostLvl[q - n]) > 1) cnt++;
+            if (q > c && abs(mine - lvl[q]) > 1) cnt++;     // each internal face once; coupled faces: k_fix_check_levels
         }
     }
     for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, d);
@@ -792,8 +782,7 @@ __global__ void k_pack_level_minus(int64_t b, const label *__restrict__ bOwner, 
 // In-place on uc (monotone: flags only drop).  Only marked cells can change, so only they are walked.
 __global__ void __launch_bounds__(kThreads)
 k_unrefine_sweep(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-                 const u8 *__restrict__ lvl8, u8 *uc, bool aligned, const u8 *__restrict__ ghostLfm, int *changed) {
-    const int32_t n32 = (int32_t)n;
+                 const u8 *__restrict__ lvl8, u8 *uc, bool aligned, int *changed) {
     forEachSet16(uc, n, aligned, [&](int64_t c) {
         const int32_t base = sliceOff[c >> 5];
         const int w = sliceOff[(c >> 5) + 1] - base;
@@ -802,7 +791,7 @@ k_unrefine_sweep(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t 
         int mx = 0;
         for (int j = 0; j < w; j++) {
             const int32_t q = row[(size_t)j << 5];
-            const int v = (q < n32) ? (int)lvl8[q] - (int)uc[q] : (int)ghostLfm[q - n32];
+            const int v = (int)lvl8[q] - (int)uc[q];        // coupled faces: k_fix_unrefine_sweep
             mx = max(mx, v);
         }
         if (mine < mx - 1) { uc[c] = 0; *changed = 1; }

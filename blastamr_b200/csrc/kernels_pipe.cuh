@@ -5,8 +5,7 @@
 // Instruction discipline (the first version was issue-bound, not memory-bound): the slice width is
 // warp-uniform and rows are padded with the row's own label, so a row is walked with a compile-time
 // width (switch on w, fully unrolled), no per-entry predicate, no branch between the gathers -- all
-// W loads of a row are issued back to back.  Labels are compared as 32-bit.  Meshes without
-// processor patches (GHOST=false) never test for ghost slots.
+// W loads of a row are issued back to back.  Labels are compared as 32-bit.
 #pragma once
 #include <type_traits>
 
@@ -36,17 +35,6 @@ __device__ __forceinline__ void sellRow(const int32_t *row, int w, int32_t self,
         }
     }
 #undef SELL_CASE
-}
-
-// value of a per-cell array at label q, where q >= n addresses the ghost slot of boundary face q-n.
-// ghostBase = ghost - n, so both cases are base[q] with a selected base pointer (branch-free).
-template <bool GHOST, class T>
-__device__ __forceinline__ T gatherAt(const T *__restrict__ local, const T *ghostBase, int32_t q, int32_t n) {
-    if (GHOST) {
-        const T *base = (q < n) ? local : ghostBase;
-        return base[q];
-    }
-    return local[q];
 }
 
 // The adjacency holds internal neighbours only.  Coupled (processor-patch) faces are applied afterwards by the

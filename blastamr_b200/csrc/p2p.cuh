@@ -3,9 +3,9 @@
 // NCCL's grouped send/recv walks a schedule over ALL ranks of the communicator, so a 160 KB halo swap
 // with 3 neighbours costs ~0.2 ms on 8 ranks (measured: 0.64 ms/step of pure latency).  Here every rank
 // owns one IPC-exported region (two parity buffers + flag words); a swap is
-//   k_halo_push    : store my boundary values straight into the neighbours' regions (NVLink stores)
-//   k_halo_signal  : release-store the epoch into their flag words
-//   k_halo_unpack  : acquire-spin on my own flag words, then copy the received ranges into `recv`
+//   k_halo_push_cells : gather my boundary-cell values and store them straight into the neighbours' regions
+//                       (NVLink stores); the last CTA release-stores the epoch into their flag words
+//   k_halo_unpack     : acquire-spin on my own flag words, then copy the received ranges into `recv`
 // and a reduction (the reduce()/gMin/gMax of the reference) is the same pattern to all ranks.
 // Double buffering by epoch parity makes reuse safe: a rank can be at most one exchange ahead of a
 // neighbour (it needs that neighbour's signal to finish its own wait).  Spins are bounded (~2 s) and
@@ -43,20 +43,6 @@ __device__ __forceinline__ unsigned ldAcquireSys(const unsigned *p) {
     return v;
 }
 
-template <int BYTES>
-__global__ void k_halo_push(HaloPlan P, char *const *__restrict__ peer, int parity, const char *__restrict__ send) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.prefix[P.nPatch]) return;
-    int q = 0;
-    while (i >= P.prefix[q + 1]) q++;
-    const int k = i - P.prefix[q];
-    char *dst = peer[P.nbr[q]] + sizeof(P2PRegionHeader) + (size_t)parity * kHaloCap + (size_t)(P.offTheirs[q] + k) * BYTES;
-    const char *src = send + (size_t)(P.offMine[q] + k) * BYTES;
-    if (BYTES == 1) *dst = *src;
-    else if (BYTES == 4) *reinterpret_cast<int *>(dst) = *reinterpret_cast<const int *>(src);
-    else *reinterpret_cast<double *>(dst) = *reinterpret_cast<const double *>(src);
-    __threadfence_system();
-}
 // fused pack + push + signal: value of a per-cell array at the owner of every coupled boundary face goes
 // straight into the neighbour's region; the last CTA to finish publishes the epoch (threadfence-reduction
 // pattern), so a swap is two launches (this one and k_halo_unpack).  `minus` (optional, bytes): v -= minus[o].
@@ -91,13 +77,6 @@ __global__ void k_halo_push_cells(HaloPlan P, char *const *__restrict__ peer, in
         }
         if (threadIdx.x == 0) *counter = 0;
     }
-}
-__global__ void k_halo_signal(HaloPlan P, char *const *__restrict__ peer, int parity, int myRank, unsigned epoch) {
-    const int q = threadIdx.x;
-    if (q >= P.nPatch) return;
-    __threadfence_system();
-    P2PRegionHeader *h = reinterpret_cast<P2PRegionHeader *>(peer[P.nbr[q]]);
-    stReleaseSys(&h->arrive[parity][myRank], epoch);
 }
 template <int BYTES>
 __global__ void k_halo_unpack(HaloPlan P, char *mine, int parity, unsigned epoch, char *__restrict__ recv) {

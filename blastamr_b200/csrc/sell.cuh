@@ -4,7 +4,8 @@
 // hexRef.C:709-741).  Every decision on this path is a max / OR / integer compare over a cell's
 // face neighbours, so the order inside a row never changes a result; the
 // device layout is therefore free: one warp = one slice of 32 consecutive rows, column-major,
-// padded with the row's own index, which is a no-op for every operator used here.
+// padded with the row's own index, which is a no-op for every operator used here.  Rows hold internal
+// neighbours only; processor-patch faces are applied by the boundary fix-up kernels.
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
@@ -15,12 +16,6 @@ __global__ void k_deg_internal(const label *__restrict__ owner, const label *__r
     if (i >= f) return;
     atomicAdd(&deg[owner[i]], 1);
     atomicAdd(&deg[neighbour[i]], 1);
-}
-__global__ void k_deg_coupled(const label *__restrict__ bOwner, const u8 *__restrict__ bCoupled, int64_t b,
-                              int32_t *__restrict__ deg) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b || !bCoupled[i]) return;
-    atomicAdd(&deg[bOwner[i]], 1);
 }
 // one warp per slice: width = max row length
 __global__ void k_slice_width(const int32_t *__restrict__ deg, int64_t rows, int64_t slices,
@@ -56,13 +51,6 @@ __global__ void k_sell_fill_internal(const label *__restrict__ owner, const labe
     label o = owner[i], q = neighbour[i];
     sellPut(col, sliceOff, cursor, o, q);
     sellPut(col, sliceOff, cursor, q, o);
-}
-__global__ void k_sell_fill_coupled(const label *__restrict__ bOwner, const u8 *__restrict__ bCoupled, int64_t b,
-                                    int64_t n, const int32_t *__restrict__ sliceOff, int32_t *__restrict__ cursor,
-                                    int32_t *__restrict__ col) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b || !bCoupled[i]) return;
-    sellPut(col, sliceOff, cursor, bOwner[i], (int32_t)(n + i));   // ghost slot of boundary face i
 }
 __global__ void k_sell_fill_csr(const int32_t *__restrict__ off, const int32_t *__restrict__ idx, int64_t rows,
                                 const int32_t *__restrict__ sliceOff, int32_t *__restrict__ col) {
@@ -111,17 +99,6 @@ __global__ void k_fill_tail(int32_t *__restrict__ sliceOff, int64_t slices, int 
 
 constexpr int kSliceOffPad = 16;
 
-// slices that contain at least one ghost slot (label >= rows): only those take the ghost-aware row walk
-__global__ void k_slice_ghost(const int32_t *__restrict__ col, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ deg,
-                              int64_t rows, u8 *__restrict__ sliceGhost) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    const int32_t *row = col + ((size_t)sliceOff[r >> 5] << 5) + (r & 31);
-    const int d = deg[r];
-    // rows are sorted ascending: a ghost slot, if any, is the last valid entry
-    if (d > 0 && row[(size_t)(d - 1) << 5] >= rows) sliceGhost[r >> 5] = 1;
-}
-
 __global__ void k_slice_ghost_cells(const u8 *__restrict__ cellGhost, int64_t rows, u8 *__restrict__ sliceGhost) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < rows && cellGhost[r]) sliceGhost[r >> 5] = 1;
@@ -168,10 +145,10 @@ static int sellAllocFromDeg(amr_ctx *ctx, Sell &S, int64_t rows, int32_t *deg, i
     return AMR_OK;
 }
 
-// cell -> face-neighbour cells from owner/neighbour (+ ghost slots for coupled boundary faces)
+// cell -> face-neighbour cells from owner/neighbour (internal faces only; coupled faces: k_fix_* kernels)
 static int sellBuildCellCells(amr_ctx *ctx) {
     sellFree(ctx, ctx->cc);
-    int64_t n = ctx->n, f = ctx->f, b = ctx->b;
+    int64_t n = ctx->n, f = ctx->f;
     int32_t *deg = nullptr, *cursor = nullptr;
     CK(cudaMalloc((void **)&deg, (size_t)(n + 1) * 4));
     CK(cudaMalloc((void **)&cursor, (size_t)(n + 1) * 4));
