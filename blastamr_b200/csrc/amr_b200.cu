@@ -979,9 +979,10 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
     ENTER();
     if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_select_refine: mesh not set");
     if (!ctx->haveLevels) FAIL(AMR_ERR_STATE, "amr_select_refine: levels not set");
-    if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D && refinerKind != AMR_REFINER_POLY3D)
+    if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D && refinerKind != AMR_REFINER_POLY3D &&
+        refinerKind != AMR_REFINER_POLY2D)
         FAIL(AMR_ERR_ARG, "amr_select_refine: prismatic2DRefinement (polyRefiner in 2-D) is not on the device path");
-    const bool poly = refinerKind == AMR_REFINER_POLY3D;
+    const bool poly = refinerKind == AMR_REFINER_POLY3D || refinerKind == AMR_REFINER_POLY2D;
     if (poly && ctx->optEdgeConsistency && !ctx->haveEdges)
         FAIL(AMR_ERR_STATE, "amr_select_refine: polyRefiner with edgeBasedConsistency needs amr_mesh_set_edges");
     if (nProtectedPatches > 0 && !protectedPatchIds) FAIL(AMR_ERR_ARG, "amr_select_refine: protectedPatchIds is null");
@@ -1228,19 +1229,38 @@ static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOu
     return AMR_OK;
 }
 
+// split-point markup of the two polyRefiner engines: polyhedralRefinement (faces) / prismatic2DRefinement (edges)
+static int polySplitMarkup(amr_ctx *ctx, bool prismatic, u8 *bad) {
+    const int64_t p = ctx->p;
+    if (p) CK(cudaMemsetAsync(bad, 0, (size_t)p, ctx->stream));
+    if (prismatic) {
+        if (ctx->nEdges) LAUNCH(k_edge_point_levels, gridFor(ctx->nEdges), kThreads, ctx->nEdges, (const label *)ctx->edgePts,
+                                (const label *)ctx->pointLevel, bad);
+        if (ctx->nCoupled > 0) LAUNCH(k_coupled_face_points, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, ctx->f,
+                                      (const label *)ctx->faceOff, (const label *)ctx->facePts, bad);
+    } else {
+        const int64_t nf = ctx->f + ctx->b;
+        if (nf) LAUNCH(k_face_point_levels, gridFor(nf), kThreads, nf, ctx->f, (const label *)ctx->faceOff, (const label *)ctx->facePts,
+                       (const label *)ctx->pointLevel, bad);
+    }
+    return AMR_OK;
+}
+
 AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefineLevel, uint8_t *refineCellInOut,
                                 int nBufferLayers, const int32_t *protectedPatchIds, int nProtectedPatches,
                                 int refinerKind, int32_t *elemsOut, int64_t *nOut, int *sweepsOut) {
     ENTER();
     if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_select_unrefine: mesh not set");
     if (!ctx->havePoints) FAIL(AMR_ERR_STATE, "amr_select_unrefine: point addressing not set (amr_mesh_set_points)");
-    const bool poly = refinerKind == AMR_REFINER_POLY3D;
+    const bool prismatic = refinerKind == AMR_REFINER_POLY2D;
+    const bool poly = refinerKind == AMR_REFINER_POLY3D || prismatic;
     if (!ctx->haveLevels || (!poly && !ctx->haveHistory)) FAIL(AMR_ERR_STATE, "amr_select_unrefine: levels/history not set");
     if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D && !poly)
-        FAIL(AMR_ERR_ARG, "amr_select_unrefine: prismatic2DRefinement (polyRefiner in 2-D) is not on the device path");
+        FAIL(AMR_ERR_ARG, "amr_select_unrefine: unknown refiner kind");
     if (poly) {
         if (!ctx->haveFaces || !ctx->pointLevel) FAIL(AMR_ERR_STATE, "amr_select_unrefine: polyRefiner needs amr_mesh_set_faces and pointLevel");
-        if (ctx->optEdgeConsistency && !ctx->haveEdges) FAIL(AMR_ERR_STATE, "amr_select_unrefine: edgeBasedConsistency needs amr_mesh_set_edges");
+        if ((ctx->optEdgeConsistency || prismatic) && !ctx->haveEdges)
+            FAIL(AMR_ERR_STATE, "amr_select_unrefine: edgeBasedConsistency / prismatic2DRefinement need amr_mesh_set_edges (all mesh edges)");
         if (ctx->nCoupled > 0 && nBufferLayers > 0)
             FAIL(AMR_ERR_STATE, "amr_select_unrefine: polyRefiner point buffer layers across processor patches need a shared-point plan (syncPointList); not on the device path yet");
     }
@@ -1290,10 +1310,7 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     u8 *pflag = ctx->flagC;
     if (poly) {
         u8 *bad = ctx->flagA;
-        const int64_t nf = ctx->f + ctx->b;
-        CK(cudaMemsetAsync(bad, 0, (size_t)p, ctx->stream));
-        if (nf) LAUNCH(k_face_point_levels, gridFor(nf), kThreads, nf, ctx->f, (const label *)ctx->faceOff, (const label *)ctx->facePts,
-                       (const label *)ctx->pointLevel, bad);
+        TRY(polySplitMarkup(ctx, prismatic, bad));
         if (p) LAUNCH(k_poly_select_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const label *)ctx->pointLevel, (const u8 *)bad,
                       dErr, unrefineLevel, (const u8 *)dRc, (u8 *)nullptr, pflag);
         TRY(unrefineSweeps(ctx, ctx->pc, pflag, sweepsOut, elemsOut, nOut, ctx->optEdgeConsistency != 0));
@@ -1320,13 +1337,11 @@ AMR_API int amr_get_split_elems(amr_ctx *ctx, int refinerKind, int32_t *elemsOut
     if (!ctx->havePoints) FAIL(AMR_ERR_STATE, "amr_get_split_elems: points not set");
     const int64_t p = ctx->p;
     u8 *pflag = ctx->flagC;
-    if (refinerKind == AMR_REFINER_POLY3D) {
+    if (refinerKind == AMR_REFINER_POLY3D || refinerKind == AMR_REFINER_POLY2D) {
         if (!ctx->haveFaces || !ctx->pointLevel) FAIL(AMR_ERR_STATE, "amr_get_split_elems: polyRefiner needs amr_mesh_set_faces and pointLevel");
+        if (refinerKind == AMR_REFINER_POLY2D && !ctx->haveEdges) FAIL(AMR_ERR_STATE, "amr_get_split_elems: prismatic2DRefinement needs amr_mesh_set_edges");
         u8 *bad = ctx->flagA;
-        const int64_t nf = ctx->f + ctx->b;
-        CK(cudaMemsetAsync(bad, 0, (size_t)p, ctx->stream));
-        if (nf) LAUNCH(k_face_point_levels, gridFor(nf), kThreads, nf, ctx->f, (const label *)ctx->faceOff, (const label *)ctx->facePts,
-                       (const label *)ctx->pointLevel, bad);
+        TRY(polySplitMarkup(ctx, refinerKind == AMR_REFINER_POLY2D, bad));
         if (p) LAUNCH(k_poly_select_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const label *)ctx->pointLevel, (const u8 *)bad,
                       (const double *)nullptr, 0.0, (const u8 *)nullptr, pflag, (u8 *)nullptr);
         TRY(emitList(ctx, pflag, p, elemsOut, nOut));

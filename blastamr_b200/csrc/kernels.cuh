@@ -707,6 +707,25 @@ k_face_point_levels(int64_t nFaces, int64_t f, const label *__restrict__ faceOff
     if (reject) for (label j = s; j < e; j++) bad[facePts[j]] = 1;
 }
 
+// prismatic2DRefinement split-point markup, edge-centric (prismatic2DRefinement.C:2756-2817): a point whose
+// pointEdges join two different pointLevels cannot be a split point
+__global__ void __launch_bounds__(kThreads)
+k_edge_point_levels(int64_t nEdges, const label *__restrict__ edgePts, const label *__restrict__ pointLevel, u8 *__restrict__ bad) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= nEdges) return;
+    const int2 ab = reinterpret_cast<const int2 *>(edgePts)[e];
+    if (pointLevel[ab.x] != pointLevel[ab.y]) { bad[ab.x] = 1; bad[ab.y] = 1; }
+}
+// ... and neither can a point of a processor-patch face (prismatic2DRefinement.C:2829-2849)
+__global__ void __launch_bounds__(kThreads)
+k_coupled_face_points(int64_t nCoupled, const label *__restrict__ cplFace, int64_t f, const label *__restrict__ faceOff,
+                      const label *__restrict__ facePts, u8 *__restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= nCoupled) return;
+    const int64_t face = f + cplFace[i];
+    for (label j = faceOff[face]; j < faceOff[face + 1]; j++) bad[facePts[j]] = 1;
+}
+
 // fvMeshPolyRefiner::selectUnrefinePoints (fvMeshPolyRefiner.C:48-79) intersected with the split points
 // (polyhedralRefinement.C:2196-2205)
 __global__ void __launch_bounds__(kThreads)

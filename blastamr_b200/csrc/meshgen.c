@@ -722,8 +722,9 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
         free(fill);
     }
     m->cpOff = cpo; m->cpPts = cpp;
-    /* --- 3-D faces() and edges() (flag 4): perimeter walk of every face with hanging nodes */
-    if ((flags & 4) && !o->dim2) {
+    /* --- faces() and edges() (flag 4): perimeter walk of every face with hanging nodes.  Also valid for the
+           2-D quadtree: a through-thickness side has no midpoint, in-plane sides bisect as in 3-D */
+    if (flags & 4) {
         facewalk W = {o, &H, npx, npy, FS, NULL, 0, 0};
         i64 nfaces = f + b;
         m->faceOff = (i32 *)xcalloc(nfaces + 1, 4);
@@ -799,8 +800,9 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
             }
         }
     }
-    /* --- 2-D: edges normal to the plane (one per point column and layer), edgeCells = cells around it */
-    if (o->dim2) {
+    /* --- 2-D without flag 4: only the edges normal to the plane (one per point column and layer; what the
+           2-D cutter selects from), edgeCells = cells around it */
+    if (o->dim2 && !(flags & 4)) {
         i64 ne = 0;
         for (i64 q = 0; q < p; q++) if (m->pxyz[3 * q + 2] < MZ) ne++;
         m->nedge = ne;

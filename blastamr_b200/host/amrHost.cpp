@@ -359,15 +359,14 @@ void fvMeshPolyRefiner::readDict(const dictionary &dict) {
     if (nUnrefinementBufferLayers_ < 2) nUnrefinementBufferLayers_ = 2;                                // :287-300
 }
 // fvMeshPolyRefiner::refine, fvMeshPolyRefiner.C:304-489: same driver shape as the hex refiner; the cutter-specific
-// parts (edge consistency, point buffer layers, pointLevel split points) live behind AMR_REFINER_POLY3D
+// parts (edge consistency, point buffer layers, pointLevel split points) live behind AMR_REFINER_POLY3D, or
+// AMR_REFINER_POLY2D when the constructor would have picked prismatic2DRefinement (nGeometricD == 2, :139-155)
 bool fvMeshPolyRefiner::refine(const scalarField &error, const labelList &maxCellLevel, const scalar lo, const scalar hi,
                                const scalar unref) {
-    if (amesh_.mesh().nSolutionD == 2)
-        throw FatalError("polyRefiner on a 2-D mesh uses prismatic2DRefinement, which is not on the device path (SURVEY.md 8a B4)");
     amesh_.check(amr_set_option(amesh_.gpu(), AMR_OPT_EDGE_BASED_CONSISTENCY, dict_.lookupOrDefaultBool("edgeBasedConsistency", true)),
                  "refinement::edgeBasedConsistency");
     amesh_.check(amr_set_option(amesh_.gpu(), AMR_OPT_POLY_FORCE, force_ ? 1 : 0), "fvMeshPolyRefiner::force_");
-    amesh_.kindOverride = AMR_REFINER_POLY3D;
+    amesh_.kindOverride = amesh_.mesh().nSolutionD == 2 ? AMR_REFINER_POLY2D : AMR_REFINER_POLY3D;
     return fvMeshHexRefiner::refine(error, maxCellLevel, lo, hi, unref);
 }
 

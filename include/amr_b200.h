@@ -79,7 +79,9 @@ enum {
     AMR_REFINER_POLY3D = 2,  /* polyRefiner + polyhedralRefinement (needs amr_mesh_set_edges with ALL mesh edges and
                                 amr_mesh_set_faces; single rank: the point sync of the unrefinement buffer layers,
                                 syncTools::syncPointList fvMeshRefiner.C:952-958, is not on the device path yet) */
-    AMR_REFINER_POLY2D = 3   /* polyRefiner + prismatic2DRefinement                -- next */
+    AMR_REFINER_POLY2D = 3   /* polyRefiner + prismatic2DRefinement (fvMeshPolyRefiner.C:139-155): same marking and
+                                consistency sweeps as POLY3D; split points from pointLevel over the point's edges and
+                                only processor-patch points excluded (prismatic2DRefinement.C:2744-2849) */
 };
 
 /* field-map modes */

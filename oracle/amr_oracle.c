@@ -1170,6 +1170,29 @@ OR_API void or_poly_split_points(const or_world *w, int r, boolean *isSplit) {
     free(bad);
 }
 
+/* prismatic2DRefinement::consistentUnrefinement PART 1 (prismatic2DRefinement.C:2744-2849): split point <=>
+   pointLevel > 0 and both end points of every edge using the point carry that same pointLevel; then the
+   points of processor-patch faces are removed (no other boundary exclusion: in 2-D every point lies on
+   the empty front/back patches) */
+OR_API void or_prism_split_points(const or_world *w, int r, boolean *isSplit) {
+    const or_mesh *m = &w->m[r];
+    boolean *bad = (boolean *)calloc((size_t)(m->p + 1), 1);
+    /* pointEdges walk restated edge-centric: a point fails iff one of its edges joins two different levels */
+    for (int64_t edgeI = 0; edgeI < m->nedge; edgeI++) {
+        label a = m->edgePts[2 * edgeI], b = m->edgePts[2 * edgeI + 1];
+        if (m->pointLevel[a] != m->pointLevel[b]) { bad[a] = 1; bad[b] = 1; }
+    }
+    for (int64_t pointI = 0; pointI < m->p; pointI++) isSplit[pointI] = (m->pointLevel[pointI] > 0) && !bad[pointI];
+    for (int q = 0; q < m->npatch; q++) {
+        if (m->patchType[q] != 2) continue;   /* processor */
+        for (label i = 0; i < m->patchSize[q]; i++) {
+            label faceI = m->patchStart[q] + i;
+            for (label j = m->faceOff[faceI]; j < m->faceOff[faceI + 1]; j++) isSplit[m->facePts[j]] = 0;
+        }
+    }
+    free(bad);
+}
+
 /* refinement::faceConsistentUnrefinement (refinement.C:390-508) + edgeConsistentUnrefinement (:511-604),
    maxSet = false.  Returns nChanged, or -1 on the reference's "problem" FatalError. */
 static int64_t poly_consistent_unrefinement_sweep(const or_world *w, int edgeBasedConsistency, boolean **unrefineCell) {
@@ -1217,11 +1240,13 @@ static int64_t poly_consistent_unrefinement_sweep(const or_world *w, int edgeBas
 
 /* Unrefinement branch of fvMeshPolyRefiner::refine (fvMeshPolyRefiner.C:419-472): layers x
    extendMarkedCellsAcrossPoints, set protectedPatches, selectUnrefinePoints (:48-96) ->
-   polyhedralRefinement::consistentUnrefinement (polyhedralRefinement.C:2077-2362). */
+   polyhedralRefinement::consistentUnrefinement (polyhedralRefinement.C:2077-2362), or with prismatic2D != 0
+   prismatic2DRefinement::consistentUnrefinement (prismatic2DRefinement.C:2729-2972; same loop, other
+   split-point rule). */
 OR_API int or_poly_select_unrefine(const or_world *w, const scalar *const *error, scalar unrefineLevel,
                                    int nUnrefinementBufferLayers, const label *protectedPatchIds, int nProtectedPatches,
                                    int edgeBasedConsistency, const label *const *pointGlobal, int64_t nGlobalPoints,
-                                   boolean **refineCell, boolean **unrefPoint, boolean **splitPoint) {
+                                   boolean **refineCell, boolean **unrefPoint, boolean **splitPoint, int prismatic2D) {
     int R = w->R;
     for (int i = 0; i < nUnrefinementBufferLayers; i++) extend_across_points(w, refineCell, pointGlobal, nGlobalPoints);
     for (int r = 0; r < R; r++) {
@@ -1236,7 +1261,8 @@ OR_API int or_poly_select_unrefine(const or_world *w, const scalar *const *error
         scalar *pFld = (scalar *)malloc(sizeof(scalar) * (size_t)(m->p + 1));
         boolean *isSplit = (boolean *)malloc((size_t)(m->p + 1));
         or_max_cell_field(w, r, error[r], pFld);
-        or_poly_split_points(w, r, isSplit);
+        if (prismatic2D) or_prism_split_points(w, r, isSplit);
+        else or_poly_split_points(w, r, isSplit);
         for (int64_t pointI = 0; pointI < m->p; pointI++) {
             int cand = 0;
             if (pFld[pointI] < unrefineLevel) {                       /* selectUnrefinePoints */

@@ -59,7 +59,8 @@ def lib():
         L.or_poly_split_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.or_poly_select_unrefine.restype = C.c_int
         L.or_poly_select_unrefine.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                              C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+                                              C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.or_prism_split_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.or_world_set_geometry.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.or_estimate_lohner.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.or_range_thresholds.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
@@ -236,14 +237,22 @@ class World:
         lib().or_poly_split_points(self._h, r, out.ctypes.data)
         return out
 
-    def poly_select_unrefine(self, err, refine_cell, n_layers, unrefine_level=-SQRT_SMALL, protected_patch_ids=(), edge_based=True):
+    def prism_split_points(self, r):
+        """prismatic2DRefinement split points (pointEdges rule)"""
+        out = np.zeros(self.meshes[r].p, dtype=np.uint8)
+        lib().or_prism_split_points(self._h, r, out.ctypes.data)
+        return out
+
+    def poly_select_unrefine(self, err, refine_cell, n_layers, unrefine_level=-SQRT_SMALL, protected_patch_ids=(), edge_based=True,
+                             prismatic=False):
         up = [np.zeros(m.p, dtype=np.uint8) for m in self.meshes]
         sp = [np.zeros(m.p, dtype=np.uint8) for m in self.meshes]
         ids = _i32(protected_patch_ids)
         if self.R > 1:
             raise NotImplementedError("poly unrefinement across ranks needs the shared-point plan (syncPointList)")
         sweeps = lib().or_poly_select_unrefine(self._h, _pp(err), unrefine_level, n_layers, ids.ctypes.data, len(ids),
-                                               1 if edge_based else 0, None, 0, _pp(refine_cell), _pp(up), _pp(sp))
+                                               1 if edge_based else 0, None, 0, _pp(refine_cell), _pp(up), _pp(sp),
+                                               1 if prismatic else 0)
         if sweeps < 0:
             raise RuntimeError("reference FatalError 'problem' (refinement.C:417)")
         return up, sp, sweeps

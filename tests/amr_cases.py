@@ -74,7 +74,7 @@ class OracleBackend:
         return int(self.w.protect_patches([err], ids, n_layers)[0])
 
     def select_refine(self, err, max_level, n_layers, protected_patch_ids=(), max_cells=2147483647, refine_cell_out=None, kind=0, **_):
-        if kind == 2:
+        if kind in (2, 3):
             rc, rs, sw = self.w.poly_select_refine([err], max_level, n_layers, protected_patch_ids=protected_patch_ids)
             if refine_cell_out is not None:
                 refine_cell_out[:] = rc[0]
@@ -111,11 +111,14 @@ class OracleBackend:
             return np.flatnonzero(self.w.split_edges(0)).astype(np.int32)
         if kind == 2:
             return np.flatnonzero(self.w.poly_split_points(0)).astype(np.int32)
+        if kind == 3:
+            return np.flatnonzero(self.w.prism_split_points(0)).astype(np.int32)
         return np.flatnonzero(self.w.split_points(0)).astype(np.int32)
 
     def select_unrefine(self, err, n_layers, refine_cell=None, protected_patch_ids=(), kind=0, **_):
-        if kind == 2:
-            up, sp, sw = self.w.poly_select_unrefine([err], [refine_cell], n_layers, protected_patch_ids=protected_patch_ids)
+        if kind in (2, 3):
+            up, sp, sw = self.w.poly_select_unrefine([err], [refine_cell], n_layers, protected_patch_ids=protected_patch_ids,
+                                                     prismatic=(kind == 3))
             return np.flatnonzero(up[0]).astype(np.int32), sw
         fn = self.w.hex2d_select_unrefine if kind == 1 else self.w.hex_select_unrefine
         up, sp, sw = fn([err], [refine_cell], n_layers, protected_cell=None if self.prot is None else [self.prot],

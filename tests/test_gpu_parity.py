@@ -78,7 +78,8 @@ def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, prot
     Works for the 3-D cutter (split points) and the 2-D cutter (split edges, oc.two_d)."""
     two_d = getattr(oc, "two_d", False)
     poly = refiner == "poly"
-    rk = 2 if poly else (1 if two_d else 0)       # AMR_REFINER_POLY3D / HEX2D / HEX3D
+    prismatic = poly and two_d                    # polyRefiner picks prismatic2DRefinement on 2-D meshes
+    rk = (3 if two_d else 2) if poly else (1 if two_d else 0)       # AMR_REFINER_POLY2D / POLY3D / HEX2D / HEX3D
     build = (lambda: oc.build(faces=True)) if poly else oc.build
     stats = dict(refined=0, unrefined=0, sweeps=[])
     for step in range(steps):
@@ -136,7 +137,7 @@ def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, prot
         # unrefinement on the (possibly new) mesh
         rc_ref = refine_cell.copy()
         if poly:
-            up, sp, _ = w.poly_select_unrefine([err], [rc_ref], layers_unref, protected_patch_ids=pid)
+            up, sp, _ = w.poly_select_unrefine([err], [rc_ref], layers_unref, protected_patch_ids=pid, prismatic=prismatic)
         elif two_d:
             up, sp, _ = w.hex2d_select_unrefine([err], [rc_ref], layers_unref, protected_patch_ids=pid)
         else:
@@ -151,9 +152,17 @@ def amr_loop(ctx, O, oc, field_fn, steps, maxlev, layers_ref, layers_unref, prot
         if len(pts):
             vol = m.vol.copy()
             n_old = m.n
-            cell_map, rev = oc.unrefine(m, pts)
+            elems = pts
+            if prismatic:
+                # the 2-D topology engine merges around the through-thickness edge that joins the two split points
+                inset = np.zeros(m.p, bool)
+                inset[pts] = True
+                ep = m.edge_pts.reshape(-1, 2)
+                elems = np.flatnonzero(inset[ep[:, 0]] & inset[ep[:, 1]]).astype(np.int32)
+                assert 2 * len(elems) == len(pts)
+            cell_map, rev = oc.unrefine(m, elems)
             unref_old = np.zeros(n_old, np.uint8)
-            eoff, ecells = (m.ec_off, m.ec_cells) if two_d else (m.pc_off, m.pc_cells)
+            eoff, ecells = (m.ec_off, m.ec_cells) if (two_d and not poly) else (m.pc_off, m.pc_cells)
             for pt in pts:
                 unref_old[ecells[eoff[pt]:eoff[pt + 1]]] = 1
             f_old = np.stack([x, 2 * x, -x], axis=1).copy() if n_old == len(x) else np.random.default_rng(1).random((n_old, 3))
@@ -218,6 +227,17 @@ def test_amr_loop_polyRefiner(ctx, O, n0, maxlev, layers):
     for e in range(0, m.n_edges, 7):
         cs = m.ec_cells[m.ec_off[e]:m.ec_off[e + 1]]
         assert lv[cs].max() - lv[cs].min() <= 1
+
+
+@pytest.mark.parametrize("n0,maxlev,layers", [(16, 2, (3, 2)), (20, 3, (3, 2))])
+def test_amr_loop_polyRefiner_2d_prismatic(ctx, O, n0, maxlev, layers):
+    """polyRefiner on a 2-D mesh = prismatic2DRefinement (fvMeshPolyRefiner.C:139-155): same marking and
+    face/edge consistency, split points from pointLevel over pointEdges, only processor-patch points
+    excluded (prismatic2DRefinement.C:2729-2972).  Config: tutorials/damBreak2D as shipped (polyRefiner)."""
+    oc = M.Octree(n0, n0, 1, (1.0, 1.0, 0.05), maxlev, CAVITY2D, {"frontAndBack": M.PATCH_EMPTY}, two_d=True)
+    st = amr_loop(ctx, O, oc, moving_front_2d(0.06), steps=6, maxlev=maxlev, layers_ref=layers[0], layers_unref=layers[1],
+                  kind="codedDelta", refiner="poly")
+    assert st["refined"] > 0 and st["unrefined"] > 0
 
 
 def test_amr_loop_protected_patches(ctx, O):

@@ -239,3 +239,57 @@ def test_amr_loop_on_cpu_runs_both_branches():
     oc = M.Octree(8, 8, 8, (1.0, 1.0, 1.0), 2)
     st = T.amr_loop(cases.OracleBackend(), O, oc, T.moving_front(0.06), steps=5, maxlev=2, layers_ref=1, layers_unref=1)
     assert st["refined"] > 0 and st["unrefined"] > 0
+
+
+def test_amr_loop_prismatic_on_cpu_runs_both_branches():
+    """the 2-D polyRefiner loop of the GPU suite, answered by the oracle (checks the driver and the 2-D topology engine)"""
+    import tests.test_gpu_parity as T
+    oc = M.Octree(16, 16, 1, (1.0, 1.0, 0.05), 2, T.CAVITY2D, {"frontAndBack": M.PATCH_EMPTY}, two_d=True)
+    st = T.amr_loop(cases.OracleBackend(), O, oc, T.moving_front_2d(0.06), steps=6, maxlev=2, layers_ref=3, layers_unref=2,
+                    kind="codedDelta", refiner="poly")
+    assert st["refined"] > 0 and st["unrefined"] > 0
+
+
+def _graded_quadtree(n0=12, maxlev=3):
+    sides = [("xmin", "movingWall"), ("xmax", "fixedWalls"), ("ymin", "fixedWalls"), ("ymax", "fixedWalls"),
+             ("zmin", "frontAndBack"), ("zmax", "frontAndBack")]
+    oc = M.Octree(n0, n0, 1, (1.0, 1.0, 0.05), maxlev, sides, {"frontAndBack": M.PATCH_EMPTY}, two_d=True)
+    for it in range(maxlev):
+        m = oc.build()
+        d = np.sqrt((m.cc[:, 0] - 0.4) ** 2 + (m.cc[:, 1] - 0.5) ** 2)
+        err = [np.where((np.abs(d - 0.25) < 0.08 / (it + 1)), 1.0, 0.0)]
+        _, rs, _ = O.World([m]).hex_select_refine(err, maxlev, 1)
+        oc.refine(np.flatnonzero(rs[0]).astype(np.int32))
+    return oc
+
+
+def test_prismatic_split_points_agree_with_history_rule():
+    """prismatic2DRefinement finds split points from pointLevel over the point's edges
+    (prismatic2DRefinement.C:2756-2817); hexRef2D finds split edges from the refinement history
+    (hexRef2D.C:2202-2342).  On the same quadtree the split points must be the end points of the split
+    edges -- two independent rules, one answer.  Also V - E + F - C = 1 for the 2-D faces()/edges()."""
+    oc = _graded_quadtree()
+    m_all = oc.build(faces=True)        # every mesh edge (polyRefiner)
+    m_thr = oc.build()                  # through-thickness edges only (2-D cutter)
+    assert m_all.p - m_all.n_edges + (m_all.f + m_all.b) - m_all.n == 1
+    w_all, w_thr = O.World([m_all]), O.World([m_thr])
+    sp = np.flatnonzero(w_all.prism_split_points(0))
+    err = [np.full(m_all.n, -1.0)]
+    _, se_thr, _ = w_thr.hex2d_select_unrefine(err, [np.zeros(m_thr.n, np.uint8)], 0)
+    _, se_all, _ = w_all.hex2d_select_unrefine(err, [np.zeros(m_all.n, np.uint8)], 0)
+    ends_thr = np.unique(m_thr.edge_pts.reshape(-1, 2)[np.flatnonzero(se_thr[0])].ravel())
+    ends_all = np.unique(m_all.edge_pts.reshape(-1, 2)[np.flatnonzero(se_all[0])].ravel())
+    assert len(sp) > 0
+    assert np.array_equal(sp, ends_thr)
+    assert np.array_equal(sp, ends_all)     # the 2-D cutter's rule does not care about the extra in-plane edges
+    # unrefinement through the prismatic engine keeps 2:1 over faces and 4:1 over edges
+    up, _, _ = w_all.poly_select_unrefine(err, [np.zeros(m_all.n, np.uint8)], 0, prismatic=True)
+    uc = np.zeros(m_all.n, np.int32)
+    for pt in np.flatnonzero(up[0]):
+        uc[m_all.pc_cells[m_all.pc_off[pt]:m_all.pc_off[pt + 1]]] = 1
+    lv = m_all.cell_level - uc
+    assert up[0].sum() > 0 and up[0].sum() % 2 == 0
+    assert np.abs(lv[m_all.owner[:m_all.f]] - lv[m_all.neighbour]).max() <= 1
+    for e in range(m_all.n_edges):
+        cs = m_all.ec_cells[m_all.ec_off[e]:m_all.ec_off[e + 1]]
+        assert lv[cs].max() - lv[cs].min() <= 1
