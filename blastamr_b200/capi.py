@@ -61,6 +61,17 @@ _SIGS = {
                                 C.c_void_p, C.c_void_p]),
     "amr_map_fields": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_update_levels": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5),
+    "amr_remap_labels": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "amr_remap_protected_cells": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_correct_fluxes": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7),
+    "amr_mesh_set_ls_vectors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_estimate_gradient": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                        C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_mesh_size": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_max_refinement": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_estimate_cell_size": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_multicomponent": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5),
     "amr_launch_count": (C.c_int64, [C.c_void_p]),
     "amr_device_bytes": (C.c_int64, [C.c_void_p]),
 }
@@ -326,3 +337,78 @@ class Context:
         self._ck(self.L.amr_update_levels(self._h, len(cell_map), _ptr(cell_map), _ptr(old_level), _ptr(refined_old),
                                           _ptr(unrefined_old), _ptr(out)))
         return out
+
+    # -- rows either side of the path
+    def reorder_labels(self, old_to_new, n_new, old_values):
+        """hexRef::updateMesh, reorder(reverseMap, nNew, -1, list)"""
+        out = np.empty(n_new, dtype=np.int32)
+        self._ck(self.L.amr_remap_labels(self._h, len(old_values), n_new, _ptr(old_to_new), 0, _ptr(old_values), _ptr(out)))
+        return out
+
+    def gather_labels(self, new_to_old, old_values):
+        out = np.empty(len(new_to_old), dtype=np.int32)
+        self._ck(self.L.amr_remap_labels(self._h, len(old_values), len(new_to_old), _ptr(new_to_old), 1, _ptr(old_values), _ptr(out)))
+        return out
+
+    def remap_protected_cells(self, cell_map, old_protected):
+        out = np.empty(len(cell_map), dtype=np.uint8)
+        self._ck(self.L.amr_remap_protected_cells(self._h, len(old_protected), len(cell_map), _ptr(cell_map), _ptr(old_protected),
+                                                  _ptr(out)))
+        return out
+
+    def correct_fluxes(self, face_map, reverse_face_map, U, phi, U_boundary=None, nbr_U=None):
+        """adaptiveFvMesh::updateMesh flux fix-up on the mesh held by the context; phi is rewritten in place"""
+        cnt = C.c_int64(0)
+        self._ck(self.L.amr_correct_fluxes(self._h, len(reverse_face_map), _ptr(face_map), _ptr(reverse_face_map), _ptr(U),
+                                           _ptr(U_boundary), _ptr(nbr_U), _ptr(phi), C.byref(cnt)))
+        return cnt.value
+
+    def set_ls_vectors(self, p_vectors, n_vectors):
+        self._ck(self.L.amr_mesh_set_ls_vectors(self._h, _ptr(p_vectors), _ptr(n_vectors)))
+
+    def estimate_gradient(self, x, scheme=0, x_boundary=None, nbr_values=None, total_volume=0.0, refine_threshold=0.5,
+                          unrefine_threshold=0.4, scale=True, want_grad=False):
+        """gradientRange::update: returns (error, thresholds[4], grad or None)"""
+        out = np.empty(self.n, dtype=np.float64)
+        thr = np.zeros(4)
+        grad = np.empty((self.n, 3), dtype=np.float64) if want_grad else None
+        self._ck(self.L.amr_estimate_gradient(self._h, scheme, _ptr(x), _ptr(x_boundary), _ptr(nbr_values), total_volume,
+                                              refine_threshold, unrefine_threshold, 1 if scale else 0, _ptr(thr), _ptr(grad), _ptr(out)))
+        return out, thr, grad
+
+    def mesh_size(self, geometric_d, want_dx=True, want_dX=True):
+        gd = np.asarray(geometric_d, dtype=np.int32)
+        dx = np.empty(self.n, dtype=np.float64) if want_dx else None
+        dX = np.empty((self.n, 3), dtype=np.float64) if want_dX else None
+        self._ck(self.L.amr_mesh_size(self._h, _ptr(gd), _ptr(dx), _ptr(dX)))
+        return dx, dX
+
+    def max_refinement(self, max_level, min_dx=0.0, dx=None, error=None):
+        out = np.empty(self.n, dtype=np.int32)
+        self._ck(self.L.amr_max_refinement(self._h, max_level, min_dx, _ptr(dx), _ptr(error), _ptr(out)))
+        return out
+
+    def estimate_cell_size(self, size_type, geometric_d, lower_unrefine=0.0, lower_refine=0.0, cmpts=(), min_dX=None, max_dX=None,
+                           dx=None, dX=None, error=None):
+        gd = np.asarray(geometric_d, dtype=np.int32)
+        cm = np.asarray(cmpts, dtype=np.int32)
+        lo = None if min_dX is None else np.asarray(min_dX, dtype=np.float64)
+        hi = None if max_dX is None else np.asarray(max_dX, dtype=np.float64)
+        if error is None:
+            error = np.zeros(self.n, dtype=np.float64)
+        self._ck(self.L.amr_estimate_cell_size(self._h, size_type, _ptr(gd), lower_unrefine, lower_refine, _ptr(cm), len(cm),
+                                               _ptr(lo), _ptr(hi), _ptr(dx), _ptr(dX), _ptr(error)))
+        return error
+
+    def multicomponent(self, errors, max_cell_levels=None):
+        """multicomponent::update + maxRefinement: returns (error, maxRefinement or None, waves)"""
+        k = len(errors)
+        pe = (C.c_void_p * max(k, 1))(*[_ptr(e) for e in errors])
+        out = np.empty(self.n, dtype=np.float64)
+        mr, pl = None, None
+        if max_cell_levels is not None:
+            pl = (C.c_void_p * max(k, 1))(*[_ptr(l) for l in max_cell_levels])
+            mr = np.empty(self.n, dtype=np.int32)
+        waves = C.c_int(0)
+        self._ck(self.L.amr_multicomponent(self._h, k, pe, pl, _ptr(out), _ptr(mr), C.byref(waves)))
+        return out, mr, waves.value

@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "kernels_pipe.cuh"
 #include "lohner.cuh"
+#include "fields.cuh"
 #include "p2p.cuh"
 
 #include <algorithm>
@@ -91,6 +92,7 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->tileCnt); devFree(ctx, &ctx->scanAux);
     devFree(ctx, &ctx->gWeights); devFree(ctx, &ctx->gSf); devFree(ctx, &ctx->gMagSf); devFree(ctx, &ctx->gDelta); devFree(ctx, &ctx->gV);
     devFree(ctx, &ctx->grad); devFree(ctx, &ctx->xbf);
+    devFree(ctx, &ctx->bEmpty); devFree(ctx, &ctx->lsP); devFree(ctx, &ctx->lsN); ctx->haveLs = false;
     sellFree(ctx, ctx->cf);
     ctx->haveGeom = false;
     sellFree(ctx, ctx->ec); devFree(ctx, &ctx->bndEdge); devFree(ctx, &ctx->edgePts);
@@ -284,10 +286,12 @@ static int haloSwapCells(amr_ctx *ctx, const void *cells, size_t elemBytes, void
         const label *bOwner = ctx->owner + ctx->f;
         if (elemBytes == 1) k_halo_push_cells<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
         else if (elemBytes == 4) k_halo_push_cells<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
-        else k_halo_push_cells<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
+        else if (elemBytes == 8) k_halo_push_cells<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
+        else k_halo_push_cells<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
         if (elemBytes == 1) k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
         else if (elemBytes == 4) k_halo_unpack<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
-        else k_halo_unpack<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
+        else if (elemBytes == 8) k_halo_unpack<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
+        else k_halo_unpack<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
         ctx->launches += 2;
         return AMR_OK;
     }
@@ -297,7 +301,8 @@ static int haloSwapCells(amr_ctx *ctx, const void *cells, size_t elemBytes, void
     if (elemBytes == 1 && minus) LAUNCH(k_pack_level_minus, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const u8 *)cells, minus, (u8 *)send);
     else if (elemBytes == 1) LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const u8 *)cells, (u8 *)send);
     else if (elemBytes == 4) LAUNCH(k_pack_i32, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const label *)cells, (label *)send);
-    else LAUNCH(k_pack_f64, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const double *)cells, (double *)send);
+    else if (elemBytes == 8) LAUNCH(k_pack_f64, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const double *)cells, (double *)send);
+    else LAUNCH(k_pack_vec3, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const double *)cells, (double *)send);
     return haloExchange(ctx, send, recv, elemBytes);
 }
 
@@ -371,7 +376,7 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     ctx->anyProtCached = -1;
     ctx->n = n; ctx->f = f; ctx->b = b; ctx->p = p;
     ctx->patches.clear();
-    std::vector<u8> coupled((size_t)(b > 0 ? b : 1), 0);
+    std::vector<u8> coupled((size_t)(b > 0 ? b : 1), 0), emptyFace((size_t)(b > 0 ? b : 1), 0);
     ctx->nCoupled = 0;
     for (int i = 0; i < npatch; i++) {
         Patch q{patchStart[i], patchSize[i], patchType ? patchType[i] : 0, patchNbrRank ? patchNbrRank[i] : -1};
@@ -379,15 +384,19 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
         if (q.type == AMR_PATCH_PROCESSOR) {
             for (int32_t k = 0; k < q.size; k++) coupled[(size_t)(q.start - f + k)] = 1;
             ctx->nCoupled += q.size;
+        } else if (q.type == AMR_PATCH_EMPTY) {
+            for (int32_t k = 0; k < q.size; k++) emptyFace[(size_t)(q.start - f + k)] = 1;
         }
         ctx->patches.push_back(q);
     }
     TRY(devAlloc(ctx, &ctx->owner, f + b));
     TRY(devAlloc(ctx, &ctx->neighbour, f));
     TRY(devAlloc(ctx, &ctx->bCoupled, b));
+    TRY(devAlloc(ctx, &ctx->bEmpty, b));
     CK(cudaMemcpyAsync(ctx->owner, owner, (size_t)(f + b) * 4, cudaMemcpyDefault, ctx->stream));
     if (f) CK(cudaMemcpyAsync(ctx->neighbour, neighbour, (size_t)f * 4, cudaMemcpyDefault, ctx->stream));
     if (b) CK(cudaMemcpyAsync(ctx->bCoupled, coupled.data(), (size_t)b, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) CK(cudaMemcpyAsync(ctx->bEmpty, emptyFace.data(), (size_t)b, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->nCoupled > 0) {
         // compact lists of the coupled faces and of the cells that own them (host bookkeeping, once per mesh)
@@ -725,14 +734,10 @@ AMR_API int amr_normalize(amr_ctx *ctx, double lowerRefine, double upperRefine, 
     return flushOuts(ctx);
 }
 
-AMR_API int amr_normalize_range(amr_ctx *ctx, double refineThreshold, double unrefineThreshold, int scale,
-                                double *errorInOut, double *thrOut, double *minMaxOut) {
-    ENTER();
+// gMax/gMin of the error field, the range thresholds and (optionally) normalize: gradientRange.C:102-109
+static int normalizeRange(amr_ctx *ctx, double *e, double refineThreshold, double unrefineThreshold, int scale, double *thrOut,
+                          double *minMaxOut) {
     const int64_t n = ctx->n;
-    double *dE = nullptr;
-    TRY(stageInOut(ctx, errorInOut, n, &dE));
-    double *e = dE ? dE : ctx->error;
-    if (!e) FAIL(AMR_ERR_STATE, "amr_normalize_range: no error field");
     const int nPart = (int)std::min<int64_t>((int64_t)ctx->numSMs * 8, std::max<int64_t>(1, (n + kThreads - 1) / kThreads));
     void *q;
     TRY(arenaAlloc(ctx, &q, (size_t)(2 * nPart + 2) * 8));
@@ -757,6 +762,18 @@ AMR_API int amr_normalize_range(amr_ctx *ctx, double refineThreshold, double unr
     if (thrOut) { thrOut[0] = t.lowerRefine; thrOut[1] = t.upperRefine; thrOut[2] = t.lowerUnrefine; thrOut[3] = t.upperUnrefine; }
     if (minMaxOut) { minMaxOut[0] = minE; minMaxOut[1] = maxE; }
     if (scale && n) LAUNCH((k_pointwise<false, true>), gridFor(n), kThreads, n, e, t, e);
+    return AMR_OK;
+}
+
+AMR_API int amr_normalize_range(amr_ctx *ctx, double refineThreshold, double unrefineThreshold, int scale,
+                                double *errorInOut, double *thrOut, double *minMaxOut) {
+    ENTER();
+    const int64_t n = ctx->n;
+    double *dE = nullptr;
+    TRY(stageInOut(ctx, errorInOut, n, &dE));
+    double *e = dE ? dE : ctx->error;
+    if (!e) FAIL(AMR_ERR_STATE, "amr_normalize_range: no error field");
+    TRY(normalizeRange(ctx, e, refineThreshold, unrefineThreshold, scale, thrOut, minMaxOut));
     if (dE && n && dE != ctx->error) CK(cudaMemcpyAsync(ctx->error, dE, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaGetLastError());
     return flushOuts(ctx);
@@ -1572,6 +1589,267 @@ AMR_API int amr_update_levels(amr_ctx *ctx, int64_t nNew, const int32_t *cellMap
     TRY(stageIn(ctx, unrefinedOld, nOld, &dU));
     TRY(stageOut(ctx, newLevel, nNew, &dNew));
     if (nNew) LAUNCH(k_update_levels, gridFor(nNew), kThreads, nNew, dMap, dOldL, dR, dU, dNew);
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+// ============================================================================ rows either side of the path (fields.cuh)
+
+AMR_API int amr_remap_labels(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *map, int mode, const int32_t *oldValues,
+                             int32_t *newValues) {
+    ENTER();
+    if (!map || !oldValues || !newValues) FAIL(AMR_ERR_ARG, "amr_remap_labels: null pointer");
+    if (mode != AMR_REMAP_REORDER && mode != AMR_REMAP_GATHER) FAIL(AMR_ERR_ARG, "amr_remap_labels: unknown mode");
+    const int32_t *dMap = nullptr, *dOld = nullptr;
+    int32_t *dNew = nullptr;
+    TRY(stageIn(ctx, map, mode == AMR_REMAP_REORDER ? nOld : nNew, &dMap));
+    TRY(stageIn(ctx, oldValues, nOld, &dOld));
+    TRY(stageOut(ctx, newValues, nNew, &dNew));
+    if (mode == AMR_REMAP_REORDER) {
+        if (nNew) CK(cudaMemsetAsync(dNew, 0xFF, (size_t)nNew * 4, ctx->stream));    // -1
+        if (nOld) LAUNCH(k_reorder_labels, gridFor(nOld), kThreads, nOld, dMap, dOld, dNew);
+    } else if (nNew) LAUNCH(k_gather_labels, gridFor(nNew), kThreads, nNew, dMap, dOld, dNew);
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_remap_protected_cells(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, const uint8_t *oldProtected,
+                                      uint8_t *newProtected) {
+    ENTER();
+    if (!cellMap || !oldProtected || !newProtected) FAIL(AMR_ERR_ARG, "amr_remap_protected_cells: null pointer");
+    const int32_t *dMap = nullptr;
+    const u8 *dOld = nullptr;
+    u8 *dNew = nullptr;
+    TRY(stageIn(ctx, cellMap, nNew, &dMap));
+    TRY(stageIn(ctx, oldProtected, nOld, &dOld));
+    TRY(stageOut(ctx, newProtected, nNew, &dNew));
+    if (nNew) LAUNCH(k_gather_protected, gridFor(nNew), kThreads, nNew, dMap, dOld, dNew);
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_correct_fluxes(amr_ctx *ctx, int64_t nOldFaces, const int32_t *faceMap, const int32_t *reverseFaceMap,
+                               const double *U, const double *UBoundary, const double *nbrU, double *phi, int64_t *nCorrected) {
+    ENTER();
+    if (!ctx->haveGeom) FAIL(AMR_ERR_STATE, "amr_correct_fluxes: geometry of the new mesh not set (amr_mesh_set_geometry)");
+    if (!faceMap || !reverseFaceMap || !U || !phi) FAIL(AMR_ERR_ARG, "amr_correct_fluxes: null pointer");
+    const int64_t n = ctx->n, f = ctx->f, b = ctx->b, nf = f + b;
+    const int32_t *dFm = nullptr, *dRf = nullptr;
+    const double *dU = nullptr, *dUb = nullptr, *dUn = nullptr;
+    double *dPhi = nullptr;
+    TRY(stageIn(ctx, faceMap, nf, &dFm));
+    TRY(stageIn(ctx, reverseFaceMap, nOldFaces, &dRf));
+    TRY(stageIn(ctx, U, 3 * n, &dU));
+    TRY(stageIn(ctx, UBoundary, 3 * b, &dUb));
+    TRY(stageInOut(ctx, phi, nf, &dPhi));
+    if (ctx->nCoupled > 0) {
+        if (nbrU) TRY(stageIn(ctx, nbrU, 3 * b, &dUn));
+        else {
+            void *q;
+            TRY(arenaAlloc(ctx, &q, (size_t)b * 24));
+            TRY(haloSwapCells(ctx, dU, 24, q));
+            dUn = (const double *)q;
+        }
+    }
+    void *q;
+    TRY(arenaAlloc(ctx, &q, (size_t)nf + 16));
+    u8 *fix = (u8 *)q;
+    CK(cudaMemsetAsync(fix, 0, (size_t)nf + 16, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dFlags + 10, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->dCount + 3, 0, 8, ctx->stream));
+    if (nf) {
+        LAUNCH(k_flux_mark, gridFor(nf), kThreads, nf, dFm, dRf, fix, ctx->dFlags + 10);
+        LAUNCH(k_flux_apply, gridFor(nf), kThreads, nf, f, (const label *)ctx->owner, (const label *)ctx->neighbour,
+               (const double *)ctx->gWeights, (const double *)ctx->gSf, dU, dUb, dUn, (const u8 *)ctx->bCoupled, (const u8 *)ctx->bEmpty,
+               (const u8 *)fix, dPhi, (unsigned long long *)(ctx->dCount + 3));
+    }
+    CK(cudaMemcpyAsync(ctx->hFlags + 10, ctx->dFlags + 10, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->hCount + 3, ctx->dCount + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->hFlags[10]) FAIL(AMR_ERR_INVARIANT, "Problem: should not have removed faces when refining.");   // adaptiveFvMesh.C:141-144
+    if (nCorrected) *nCorrected = ctx->hCount[3];
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_mesh_set_ls_vectors(amr_ctx *ctx, const double *pVectors, const double *nVectors) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_mesh_set_ls_vectors: call amr_mesh_set first");
+    if (!pVectors || (!nVectors && ctx->f)) FAIL(AMR_ERR_ARG, "amr_mesh_set_ls_vectors: null pointer");
+    const int64_t f = ctx->f, nf = ctx->f + ctx->b;
+    devFree(ctx, &ctx->lsP); devFree(ctx, &ctx->lsN);
+    TRY(devAlloc(ctx, &ctx->lsP, 3 * nf)); TRY(devAlloc(ctx, &ctx->lsN, 3 * f));
+    if (nf) CK(cudaMemcpyAsync(ctx->lsP, pVectors, (size_t)nf * 24, cudaMemcpyDefault, ctx->stream));
+    if (f) CK(cudaMemcpyAsync(ctx->lsN, nVectors, (size_t)f * 24, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->haveLs = true;
+    return AMR_OK;
+}
+
+AMR_API int amr_estimate_gradient(amr_ctx *ctx, int scheme, const double *x, const double *xBoundary, const double *nbrValues,
+                                  double totalVolume, double refineThreshold, double unrefineThreshold, int scale, double *thrOut,
+                                  double *gradOut, double *errorOut) {
+    ENTER();
+    if (!ctx->haveGeom) FAIL(AMR_ERR_STATE, "amr_estimate_gradient: geometry not set (amr_mesh_set_geometry)");
+    if (scheme != AMR_GRAD_GAUSS_LINEAR && scheme != AMR_GRAD_LEAST_SQUARES) FAIL(AMR_ERR_ARG, "amr_estimate_gradient: unknown gradient scheme");
+    if (scheme == AMR_GRAD_LEAST_SQUARES && !ctx->haveLs) FAIL(AMR_ERR_STATE, "amr_estimate_gradient: leastSquares vectors not set (amr_mesh_set_ls_vectors)");
+    if (!x) FAIL(AMR_ERR_ARG, "amr_estimate_gradient: x is null");
+    const int64_t n = ctx->n, f = ctx->f, b = ctx->b;
+    const double *dx = nullptr, *dxb = nullptr, *dxn = nullptr;
+    TRY(stageIn(ctx, x, n, &dx));
+    TRY(stageIn(ctx, xBoundary, b, &dxb));
+    const bool devOut = errorOut && isDevicePtr(errorOut);
+    double *target = devOut ? errorOut : ctx->error;
+    ctx->errorResident = !devOut;
+    if (ctx->nCoupled > 0) {
+        if (nbrValues) TRY(stageIn(ctx, nbrValues, b, &dxn));
+        else {
+            TRY(haloSwapCells(ctx, dx, 8, ctx->ghost64));
+            dxn = ctx->ghost64;
+        }
+    } else dxn = ctx->ghost64;
+    Geom G{ctx->gWeights, ctx->gSf, ctx->gMagSf, ctx->gDelta, ctx->gV};
+    if (b) LAUNCH(k_boundary_field, gridFor(b), kThreads, b, ctx->owner + f, dx, dxb, dxn, ctx->bCoupled, ctx->xbf);
+    if (n) {
+        if (scheme == AMR_GRAD_GAUSS_LINEAR)
+            LAUNCH(k_gauss_grad, gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
+                   (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, ctx->grad);
+        else
+            LAUNCH(k_ls_grad, gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, (const label *)ctx->owner, (const label *)ctx->neighbour,
+                   (const double *)ctx->lsP, (const double *)ctx->lsN, dx, (const double *)ctx->xbf, ctx->grad);
+        LAUNCH(k_mag_grad, gridFor(n), kThreads, n, (const double *)ctx->grad, (const double *)ctx->gV, totalVolume, target);
+    }
+    TRY(normalizeRange(ctx, target, refineThreshold, unrefineThreshold, scale, thrOut, nullptr));
+    if (gradOut && n) { CK(cudaMemcpyAsync(gradOut, ctx->grad, (size_t)n * 24, cudaMemcpyDefault, ctx->stream)); if (!isDevicePtr(gradOut)) ctx->hostTouched = true; }
+    if (errorOut && !devOut && n) { CK(cudaMemcpyAsync(errorOut, target, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream)); ctx->hostTouched = true; }
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_mesh_size(amr_ctx *ctx, const int32_t *geometricD, double *dx, double *dX) {
+    ENTER();
+    if (!ctx->haveGeom) FAIL(AMR_ERR_STATE, "amr_mesh_size: geometry not set (amr_mesh_set_geometry)");
+    if (!geometricD) FAIL(AMR_ERR_ARG, "amr_mesh_size: geometricD is null");
+    const int64_t n = ctx->n;
+    double *dDx = nullptr, *dDX = nullptr;
+    TRY(stageOut(ctx, dx, n, &dDx));
+    TRY(stageOut(ctx, dX, 3 * n, &dDX));
+    int nGeo = 0;
+    for (int k = 0; k < 3; k++) if (geometricD[k] > 0) nGeo++;
+    if (dDx && n) {
+        if (nGeo == 3) LAUNCH(k_mesh_dx_cbrt, gridFor(n), kThreads, n, (const double *)ctx->gV, dDx);
+        else LAUNCH(k_mesh_dx_planar, gridFor(n), kThreads, n, ctx->f, ctx->cf.sliceOff, ctx->cf.col, (const double *)ctx->gSf,
+                    geometricD[0] < 0 ? 1.0 : 0.0, geometricD[1] < 0 ? 1.0 : 0.0, geometricD[2] < 0 ? 1.0 : 0.0, dDx);
+    }
+    if (dDX && n) LAUNCH(k_mesh_dX, gridFor(n), kThreads, n, ctx->cf.sliceOff, ctx->cf.col, (const double *)ctx->gSf, (const double *)ctx->gV, dDX);
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_max_refinement(amr_ctx *ctx, int32_t maxLevel, double minDx, const double *dx, const double *error,
+                               int32_t *maxRefinementOut) {
+    ENTER();
+    if (!maxRefinementOut) FAIL(AMR_ERR_ARG, "amr_max_refinement: output is null");
+    const int64_t n = ctx->n;
+    int32_t *dOut = nullptr;
+    TRY(stageOut(ctx, maxRefinementOut, n, &dOut));
+    if (maxLevel >= 0 || !ctx->haveLevels) {                       // errorEstimator.C:264-267
+        if (n) LAUNCH(k_fill_labels, gridFor(n), kThreads, n, (label)maxLevel, dOut);
+    } else {
+        if (!dx) FAIL(AMR_ERR_ARG, "amr_max_refinement: dx is null (amr_mesh_size)");
+        const double *dDx = nullptr, *dErr = nullptr;
+        TRY(stageIn(ctx, dx, n, &dDx));
+        TRY(stageIn(ctx, error, n, &dErr));
+        if (!dErr) dErr = ctx->error;
+        if (!dErr) FAIL(AMR_ERR_STATE, "amr_max_refinement: no error field");
+        if (n) LAUNCH(k_max_refinement, gridFor(n), kThreads, n, (const label *)ctx->lvl, minDx, dDx, dErr, dOut);
+    }
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_estimate_cell_size(amr_ctx *ctx, int sizeType, const int32_t *geometricD, double lowerUnrefine, double lowerRefine,
+                                   const int32_t *cmpts, int nCmpts, const double *minDX, const double *maxDX, const double *dx,
+                                   const double *dX, double *errorInOut) {
+    ENTER();
+    if (!ctx->haveGeom) FAIL(AMR_ERR_STATE, "amr_estimate_cell_size: geometry not set (amr_mesh_set_geometry)");
+    if (sizeType < AMR_SIZE_VOLUME || sizeType > AMR_SIZE_CMPT) FAIL(AMR_ERR_ARG, "amr_estimate_cell_size: unknown size type");
+    if (!geometricD) FAIL(AMR_ERR_ARG, "amr_estimate_cell_size: geometricD is null");
+    const int64_t n = ctx->n;
+    CellSizeArgs A;
+    A.sizeType = sizeType;
+    for (int k = 0; k < 3; k++) { A.geoValid[k] = geometricD[k] == 1; A.cmpts[k] = 0; A.minDX[k] = 0; A.maxDX[k] = 0; }
+    A.lowerUnrefine = lowerUnrefine; A.lowerRefine = lowerRefine;
+    A.nCmpts = 0;
+    if (sizeType == AMR_SIZE_CMPT) {
+        if (nCmpts < 0 || nCmpts > 3 || (nCmpts && (!cmpts || !minDX || !maxDX))) FAIL(AMR_ERR_ARG, "amr_estimate_cell_size: bad component list");
+        A.nCmpts = nCmpts;
+        for (int i = 0; i < nCmpts; i++) {
+            if (cmpts[i] < 0 || cmpts[i] > 2) FAIL(AMR_ERR_ARG, "amr_estimate_cell_size: component out of range");
+            A.cmpts[i] = cmpts[i];
+        }
+        for (int k = 0; k < 3; k++) { A.minDX[k] = minDX[k]; A.maxDX[k] = maxDX[k]; }
+    }
+    const double *dDx = nullptr, *dDX = nullptr;
+    TRY(stageIn(ctx, dx, n, &dDx));
+    TRY(stageIn(ctx, dX, 3 * n, &dDX));
+    if (sizeType == AMR_SIZE_CHARACTERISTIC && !dDx) FAIL(AMR_ERR_ARG, "amr_estimate_cell_size: dx is null (amr_mesh_size)");
+    if ((sizeType == AMR_SIZE_MAG || sizeType == AMR_SIZE_CMPT) && !dDX) FAIL(AMR_ERR_ARG, "amr_estimate_cell_size: dX is null (amr_mesh_size)");
+    double *dE = nullptr;
+    TRY(stageInOut(ctx, errorInOut, n, &dE));
+    double *e = dE ? dE : ctx->error;
+    if (n) LAUNCH(k_cell_size, gridFor(n), kThreads, n, A, (const double *)ctx->gV, dDx, dDX, e);
+    if (dE && n && dE != ctx->error) CK(cudaMemcpyAsync(ctx->error, dE, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->errorResident = true;
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_multicomponent(amr_ctx *ctx, int nEstimators, const double *const *errors, const int32_t *const *maxCellLevels,
+                               double *errorOut, int32_t *maxRefinementOut, int *wavesOut) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_multicomponent: mesh not set");
+    if (nEstimators < 0 || (nEstimators && !errors)) FAIL(AMR_ERR_ARG, "amr_multicomponent: errors is null");
+    const int64_t n = ctx->n;
+    std::vector<const double *> dErr((size_t)nEstimators, nullptr);
+    for (int i = 0; i < nEstimators; i++) {
+        if (!errors[i]) FAIL(AMR_ERR_ARG, "amr_multicomponent: errors[i] is null");
+        TRY(stageIn(ctx, errors[i], n, &dErr[(size_t)i]));
+    }
+    // update(): error = max over the sub-estimators, starting from -1 (multicomponent.C:100-118)
+    const bool devOut = errorOut && isDevicePtr(errorOut);
+    double *target = devOut ? errorOut : ctx->error;
+    ctx->errorResident = !devOut;
+    if (n) {
+        if (nEstimators == 0) LAUNCH(k_fill_scalar, gridFor(n), kThreads, n, -1.0, target);
+        for (int i = 0; i < nEstimators; i++) LAUNCH(k_max_combine, gridFor(n), kThreads, n, dErr[(size_t)i], target, i == 0 ? 1 : 0);
+        if (errorOut && !devOut) { CK(cudaMemcpyAsync(errorOut, target, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream)); ctx->hostTouched = true; }
+    }
+    int waves = 0;
+    if (maxRefinementOut) {
+        if (nEstimators && !maxCellLevels) FAIL(AMR_ERR_ARG, "amr_multicomponent: maxCellLevels is null");
+        int32_t *dOut = nullptr;
+        TRY(stageOut(ctx, maxRefinementOut, n, &dOut));
+        if (n) CK(cudaMemsetAsync(dOut, 0, (size_t)n * 4, ctx->stream));
+        u8 *state = ctx->flagA;
+        for (int i = 0; i < nEstimators && n; i++) {
+            const int32_t *dLvl = nullptr;
+            if (!maxCellLevels[i]) FAIL(AMR_ERR_ARG, "amr_multicomponent: maxCellLevels[i] is null");
+            TRY(stageIn(ctx, maxCellLevels[i], n, &dLvl));
+            LAUNCH(k_mc_init, gridFor(n), kThreads, n, dErr[(size_t)i], state);
+            for (;;) {
+                CK(cudaMemsetAsync(ctx->dFlags + 10, 0, 2 * sizeof(int), ctx->stream));
+                LAUNCH(k_mc_wave, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, dLvl, (const label *)dOut, state, ctx->dFlags + 10);
+                CK(cudaMemcpyAsync(ctx->hFlags + 10, ctx->dFlags + 10, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                waves++;
+                if (!ctx->hFlags[11]) break;                      // nothing left undetermined
+                if (!ctx->hFlags[10]) FAIL(AMR_ERR_INVARIANT, "amr_multicomponent: wavefront made no progress");
+            }
+            LAUNCH(k_mc_apply, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, dLvl, (const u8 *)state, dOut);
+        }
+    }
+    if (wavesOut) *wavesOut = waves;
     CK(cudaGetLastError());
     return flushOuts(ctx);
 }

@@ -96,6 +96,9 @@ struct amr_ctx {
     Sell cf;                   // cell -> faces (2*face + role), ascending
     double *grad = nullptr;    // [3n]
     double *xbf = nullptr;     // [b] boundaryField of x
+    u8 *bEmpty = nullptr;      // [b] boundary face lies on an empty patch (no surface-field entries)
+    double *lsP = nullptr, *lsN = nullptr;   // leastSquaresVectors pVectors [3(f+b)], nVectors [3f]
+    bool haveLs = false;
     u8 *bndPoint = nullptr;
     u8 *pcClass = nullptr;     // [p] split-point pre-filter (see k_point_class); rebuilt when points/levels change
     bool pcClassDirty = true;

@@ -59,7 +59,12 @@ __global__ void k_halo_push_cells(HaloPlan P, char *const *__restrict__ peer, in
         char *dst = peer[P.nbr[q]] + sizeof(P2PRegionHeader) + (size_t)parity * kHaloCap + (size_t)(P.offTheirs[q] + k) * BYTES;
         if (BYTES == 1) { u8 v = (u8)cells[o]; if (minus) v = (u8)(v - minus[o]); *reinterpret_cast<u8 *>(dst) = v; }
         else if (BYTES == 4) *reinterpret_cast<int *>(dst) = reinterpret_cast<const int *>(cells)[o];
-        else *reinterpret_cast<double *>(dst) = reinterpret_cast<const double *>(cells)[o];
+        else if (BYTES == 8) *reinterpret_cast<double *>(dst) = reinterpret_cast<const double *>(cells)[o];
+        else {                                               // vector field: 3 doubles per cell
+            const double *s3 = reinterpret_cast<const double *>(cells) + 3 * (size_t)o;
+            double *d3 = reinterpret_cast<double *>(dst);
+            d3[0] = s3[0]; d3[1] = s3[1]; d3[2] = s3[2];
+        }
         __threadfence_system();
     }
     __shared__ int last;
@@ -104,7 +109,12 @@ __global__ void k_halo_unpack(HaloPlan P, char *mine, int parity, unsigned epoch
     char *dst = recv + (size_t)(P.offMine[q] + k) * BYTES;
     if (BYTES == 1) *dst = *src;
     else if (BYTES == 4) *reinterpret_cast<int *>(dst) = *reinterpret_cast<const int *>(src);
-    else *reinterpret_cast<double *>(dst) = *reinterpret_cast<const double *>(src);
+    else if (BYTES == 8) *reinterpret_cast<double *>(dst) = *reinterpret_cast<const double *>(src);
+    else {
+        const double *s3 = reinterpret_cast<const double *>(src);
+        double *d3 = reinterpret_cast<double *>(dst);
+        d3[0] = s3[0]; d3[1] = s3[1]; d3[2] = s3[2];
+    }
 }
 
 // ---- all-rank reduction of one 8-byte word.  op: 0 max(int32), 1 sum(int64), 2 min(f64), 3 max(f64)

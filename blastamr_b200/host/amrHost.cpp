@@ -67,13 +67,27 @@ void errorEstimator::read(const dictionary &dict) {          // errorEstimator.C
     lowerUnrefine_ = dict.lookupScalar("unrefineLevel");
     upperRefine_ = dict.lookupOrDefault("upperRefineLevel", GREAT);
     upperUnrefine_ = dict.lookupOrDefault("upperUnrefineLevel", GREAT);
-    if (dict.found("maxRefinement")) maxLevel_ = (label)dict.lookupLabel("maxRefinement");
-    else if (dict.found("minDx")) throw FatalError("minDx needs meshSizeObject (cellSize estimator family): host-side, not on the device path");
+    if (dict.found("maxRefinement")) { maxLevel_ = (label)dict.lookupLabel("maxRefinement"); minDx_ = -1; }     // :175-190
+    else if (dict.found("minDx")) { minDx_ = dict.lookupScalar("minDx"); maxLevel_ = -1; }
     else throw FatalError("Either maxRefinement or minDx must be specified");
     protectedPatches_ = dict.lookupOrDefault("protectedPatches", wordList{});
 }
 
-labelList errorEstimator::maxRefinement() const { return labelList((size_t)mesh_.nCells, maxLevel_); }   // errorEstimator.C:264-267
+void errorEstimator::geometricD(int32_t gd[3]) const {
+    gd[0] = 1; gd[1] = 1; gd[2] = mesh_.nSolutionD == 2 ? -1 : 1;      // the empty direction of the 2-D cases is z
+}
+// errorEstimator.C:262-292: uniform maxRefinement, or cellLevel + 1 where the cell is still wider than minDx and flagged
+labelList errorEstimator::maxRefinement() const {
+    labelList out((size_t)mesh_.nCells, maxLevel_);
+    if (maxLevel_ >= 0 || mesh_.cellLevel.empty()) return out;
+    if (mesh_.Sf.empty()) throw FatalError("errorEstimator::maxRefinement: minDx needs the mesh geometry (meshSizeObject)");
+    int32_t gd[3];
+    geometricD(gd);
+    scalarField dx((size_t)mesh_.nCells);
+    check(amr_mesh_size(gpu_, gd, dx.data(), nullptr), "meshSizeObject::dx");
+    check(amr_max_refinement(gpu_, -1, minDx_, dx.data(), error_.data(), out.data()), "errorEstimator::maxRefinement");
+    return out;
+}
 
 void errorEstimator::normalize(scalarField &error) {
     check(amr_normalize(gpu_, lowerRefine_, upperRefine_, lowerUnrefine_, upperUnrefine_, error.data()), "errorEstimator::normalize");
@@ -173,12 +187,128 @@ struct gradientRange : errorEstimator {   // gradientRange.C ("gradientRange" in
         unrefineThreshold_ = d.lookupOrDefault("unrefineThreshold", 0.4);
     }
     void update(const bool scale) override {
-        // fvc::grad stays OpenFOAM core on the host (scheme from fvSchemes); the solver registers mag(grad(f))
-        const volField &g = mesh_.lookupField("mag(grad(" + gradField_ + "))");
-        error_ = magField(g, mesh_.nCells);
         double thr[4];
-        check(amr_normalize_range(gpu_, refineThreshold_, unrefineThreshold_, scale, error_.data(), thr, nullptr), "gradientEstimator::update");
+        const word cached = "mag(grad(" + gradField_ + "))";
+        if (mesh_.fields.count(cached)) {
+            // a solver that already holds fvc::grad (any scheme) hands mag(grad(f)) over
+            error_ = magField(mesh_.lookupField(cached), mesh_.nCells);
+            check(amr_normalize_range(gpu_, refineThreshold_, unrefineThreshold_, scale, error_.data(), thr, nullptr), "gradientEstimator::update");
+        } else {
+            // fvc::grad with the case's gradScheme on the device (gradientRange.C:100)
+            const volField &x = mesh_.lookupField(gradField_);
+            if (x.nComp != 1) throw FatalError("gradientRange: " + gradField_ + " is not a volScalarField");
+            if (mesh_.Sf.empty()) throw FatalError("gradientRange: fvc::grad needs the mesh geometry");
+            int scheme = AMR_GRAD_GAUSS_LINEAR;
+            if (mesh_.gradScheme == "leastSquares") {
+                scheme = AMR_GRAD_LEAST_SQUARES;
+                if (mesh_.lsPVectors.empty()) throw FatalError("gradientRange: leastSquares needs leastSquaresVectors");
+                check(amr_mesh_set_ls_vectors(gpu_, mesh_.lsPVectors.data(), mesh_.lsNVectors.data()), "leastSquaresVectors");
+            } else if (mesh_.gradScheme != "Gauss linear") throw FatalError("gradientRange: gradScheme " + mesh_.gradScheme + " is not on the device path");
+            error_.resize((size_t)mesh_.nCells);
+            check(amr_estimate_gradient(gpu_, scheme, x.v.data(), nullptr, nullptr, 0.0, refineThreshold_, unrefineThreshold_, scale, thr,
+                                        nullptr, error_.data()), "gradientEstimator::update");
+        }
         lowerRefine_ = thr[0]; upperRefine_ = thr[1]; lowerUnrefine_ = thr[2]; upperUnrefine_ = thr[3];
+    }
+};
+struct cellSize : errorEstimator {        // cellSize.C
+    int sizeType_ = AMR_SIZE_CHARACTERISTIC;
+    labelList cmpts_;
+    double minDX_[3] = {0, 0, 0}, maxDX_[3] = {0, 0, 0};
+    cellSize(fvMeshLite &m, amr_ctx *g, const dictionary &d, const word &n) : errorEstimator(m, g, d, n) { read(d); }
+    word type() const override { return "cellSize"; }
+    static void readVector(const dictionary &d, const word &key, double v[3]) {
+        const wordList w = d.lookupWordList(key);
+        if (w.size() != 3) throw FatalError("keyword " + key + ": expected a vector");
+        for (int k = 0; k < 3; k++) v[k] = std::stod(w[(size_t)k]);
+    }
+    void read(const dictionary &d) override {                 // cellSize.C:213-232 (does not call the base read)
+        const word t = d.lookupWord("type");
+        if (t == "volume") sizeType_ = AMR_SIZE_VOLUME;
+        else if (t == "characteristic") sizeType_ = AMR_SIZE_CHARACTERISTIC;
+        else if (t == "mag") sizeType_ = AMR_SIZE_MAG;
+        else if (t == "cmpt") sizeType_ = AMR_SIZE_CMPT;
+        else throw FatalError("cellSize: unknown size type " + t + "; valid types: volume cmpt characteristic mag");     // cellSize.C:42-48
+        if (sizeType_ == AMR_SIZE_CMPT) {
+            int32_t gd[3];
+            geometricD(gd);
+            cmpts_.clear();
+            for (const word &c : d.lookupWordList("cmpts")) {           // readCmpts, cellSize.C:76-121
+                label k;
+                if (c == "x" || c == "X" || c == "0") k = 0;
+                else if (c == "y" || c == "Y" || c == "1") k = 1;
+                else if (c == "z" || c == "Z" || c == "2") k = 2;
+                else throw FatalError("Unknown component " + c + "\nValid components are: \nx/X\ny/Y\nz/Z");
+                if (gd[k] == 1 && std::find(cmpts_.begin(), cmpts_.end(), k) == cmpts_.end()) cmpts_.push_back(k);
+            }
+            readVector(d, "minDX", minDX_);
+            readVector(d, "maxDX", maxDX_);
+        } else if (sizeType_ == AMR_SIZE_VOLUME) {
+            lowerUnrefine_ = d.lookupScalar("minVolume");
+            lowerRefine_ = d.lookupScalar("maxVolume");
+        } else {
+            lowerUnrefine_ = d.lookupScalar("minDx");
+            lowerRefine_ = d.lookupScalar("maxDx");
+        }
+        maxLevel_ = (label)d.lookupOrDefaultLabel("maxRefinement", 10);
+    }
+    labelList maxRefinement() const override {                // cellSize.C:124-127
+        labelList out(mesh_.cellLevel);
+        for (label &l : out) l++;
+        return out;
+    }
+    void update(const bool) override {
+        if (mesh_.Sf.empty()) throw FatalError("cellSize: needs the mesh geometry (meshSizeObject)");
+        int32_t gd[3];
+        geometricD(gd);
+        const size_t n = (size_t)mesh_.nCells;
+        scalarField dx, dX;
+        if (sizeType_ == AMR_SIZE_CHARACTERISTIC) dx.resize(n);
+        if (sizeType_ == AMR_SIZE_MAG || sizeType_ == AMR_SIZE_CMPT) dX.resize(3 * n);
+        if (!dx.empty() || !dX.empty())
+            check(amr_mesh_size(gpu_, gd, dx.empty() ? nullptr : dx.data(), dX.empty() ? nullptr : dX.data()), "meshSizeObject");
+        error_.resize(n, 0.0);                                 // CMPT accumulates into the field it finds
+        check(amr_estimate_cell_size(gpu_, sizeType_, gd, lowerUnrefine_, lowerRefine_, cmpts_.data(), (int)cmpts_.size(), minDX_, maxDX_,
+                                     dx.empty() ? nullptr : dx.data(), dX.empty() ? nullptr : dX.data(), error_.data()), "cellSize::update");
+    }
+};
+struct multicomponent : errorEstimator {  // multicomponentError/multicomponent.C
+    wordList names_;
+    std::vector<std::unique_ptr<errorEstimator>> errors_;
+    multicomponent(fvMeshLite &m, amr_ctx *g, const dictionary &d, const word &n) : errorEstimator(m, g, d, n) {
+        for (auto &e : d.lookupEntryList("errorEstimators")) {            // :52-71
+            names_.push_back(e.first);
+            const word type = e.second.lookupWord("errorEstimator");
+            auto it = dictionaryConstructorTable().find(type);
+            if (it == dictionaryConstructorTable().end()) throw FatalError("Unknown errorEstimator type " + type);
+            errors_.push_back(it->second(m, g, e.second, e.first));
+        }
+        maxLevel_ = 0;
+        for (auto &e : errors_) maxLevel_ = std::max(maxLevel_, e->maxLevel());
+    }
+    word type() const override { return "multicomponent"; }
+    void read(const dictionary &d) override {                 // :84-96
+        auto entries = d.lookupEntryList("errorEstimators");
+        for (size_t i = 0; i < errors_.size(); i++) errors_[i]->read(entries[i].second);
+        maxLevel_ = 0;
+        for (auto &e : errors_) maxLevel_ = std::max(maxLevel_, e->maxLevel());
+    }
+    void update(const bool scale) override {                  // :99-119
+        std::vector<const double *> ptr;
+        for (auto &e : errors_) { e->update(scale); ptr.push_back(e->error().data()); }
+        error_.resize((size_t)mesh_.nCells);
+        check(amr_multicomponent(gpu_, (int)ptr.size(), ptr.data(), nullptr, error_.data(), nullptr, nullptr), "multicomponent::update");
+    }
+    labelList maxRefinement() const override {                // :122-157
+        std::vector<const double *> ptr;
+        std::vector<labelList> lv;
+        std::vector<const int32_t *> lptr;
+        for (auto &e : errors_) { ptr.push_back(e->error().data()); lv.push_back(e->maxRefinement()); }
+        for (auto &l : lv) lptr.push_back(l.data());
+        labelList out((size_t)mesh_.nCells, 0);
+        scalarField tmp((size_t)mesh_.nCells);
+        check(amr_multicomponent(gpu_, (int)ptr.size(), ptr.data(), lptr.data(), tmp.data(), out.data(), nullptr), "multicomponent::maxRefinement");
+        return out;
     }
 };
 
@@ -191,6 +321,7 @@ static void add(const word &nm) {
 static bool registered = []() {
     add<delta>("delta"); add<scaledDelta>("scaledDelta"); add<Lohner>("Lohner"); add<fieldValue>("fieldValue");
     add<gradientRange>("gradientRange"); add<densityGradient>("densityGradient");
+    add<cellSize>("cellSize"); add<multicomponent>("multicomponent");
     errorEstimator::dictionaryConstructorTable()["coded"] = [](fvMeshLite &, amr_ctx *, const dictionary &, const word &) -> std::unique_ptr<errorEstimator> {
         throw FatalError("coded errorEstimator: user C++ is compiled and run by the host (codedErrorEstimator.C); "
                          "its error_ field enters the device path through amr_normalize / amr_select_refine");

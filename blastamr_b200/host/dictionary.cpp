@@ -55,8 +55,11 @@ private:
             std::string t;
             std::vector<std::string> vals;
             bool isSub = false;
+            int depth = 0;                       // `key ( a { k v; } b { ... } );` -- PtrList<entry> values nest
             while (next(t)) {
-                if (t == ";") break;
+                if (t == ";" && depth == 0) break;
+                if (t == "(" || (t == "{" && !vals.empty())) depth++;
+                else if ((t == ")" || t == "}") && depth > 0) depth--;
                 if (t == "{" && vals.empty()) {
                     auto sub = std::make_shared<dictionary>();
                     sub->name_ = key;
@@ -118,6 +121,32 @@ wordList dictionary::lookupWordList(const word &key) const {
     if (k < t.size() && t[k] != "(" && k + 1 < t.size() && t[k + 1] == "(") k++;
     if (k >= t.size() || t[k] != "(") throw FatalError("keyword " + key + ": expected a list ( ... )");
     for (k++; k < t.size() && t[k] != ")"; k++) out.push_back(t[k]);
+    return out;
+}
+std::vector<std::pair<word, dictionary>> dictionary::lookupEntryList(const word &key) const {
+    const auto &t = tokens(key);
+    std::vector<std::pair<word, dictionary>> out;
+    size_t k = 0;
+    if (k < t.size() && t[k] != "(" && k + 1 < t.size() && t[k + 1] == "(") k++;
+    if (k >= t.size() || t[k] != "(") throw FatalError("keyword " + key + ": expected a list of entries ( name { ... } ... )");
+    k++;
+    while (k < t.size() && t[k] != ")") {
+        const word name = t[k++];
+        if (k >= t.size() || t[k] != "{") throw FatalError("keyword " + key + ": entry " + name + " is not a dictionary");
+        int depth = 1;
+        std::string body;
+        for (k++; k < t.size() && depth > 0; k++) {
+            if (t[k] == "{") depth++;
+            else if (t[k] == "}") { if (--depth == 0) break; }
+            body += t[k];
+            body += ' ';
+        }
+        if (depth != 0) throw FatalError("keyword " + key + ": missing } in entry " + name);
+        k++;
+        dictionary d = dictionary::parse(body);
+        d.name_ = name;
+        out.emplace_back(name, d);
+    }
     return out;
 }
 std::vector<word> dictionary::toc() const {

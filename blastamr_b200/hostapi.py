@@ -5,6 +5,7 @@ calls `update()` once per time step -- the call a reference user makes (`mesh.up
 from __future__ import annotations
 
 import ctypes as C
+import re
 from typing import Dict, Optional
 
 import numpy as np
@@ -79,6 +80,9 @@ class AdaptiveFvMesh:
         self.oc = octree
         self.geometry = geometry
         self.faces = faces
+        # polyRefiner on a 2-D mesh selects split POINTS (prismatic2DRefinement); the 2-D topology engine merges around
+        # the through-thickness edge joining the two split points
+        self.prismatic = bool(getattr(octree, "two_d", False)) and re.search(r"refiner\s+polyRefiner", dict_text) is not None
         self.mesh: Optional[PolyMesh] = None
         self.time_index = 0
         self._cb_r = TOPO_CB(self._on_refine)
@@ -138,6 +142,11 @@ class AdaptiveFvMesh:
         try:
             el = np.ctypeslib.as_array(elems, shape=(n,)).copy()
             n_old = self.mesh.n
+            if self.prismatic:
+                inset = np.zeros(self.mesh.p, bool)
+                inset[el] = True
+                ep = self.mesh.edge_pts.reshape(-1, 2)
+                el = np.flatnonzero(inset[ep[:, 0]] & inset[ep[:, 1]]).astype(np.int32)
             cm, rev = self.oc.unrefine(self.mesh, el)
             self._install(self.oc.build(geometry=self.geometry, faces=self.faces))
             self._ck(self.L.amrhost_set_map(self._h, n_old, len(cm), cm.ctypes.data, rev.ctypes.data))

@@ -276,6 +276,71 @@ int amr_update_levels(amr_ctx *ctx, int64_t nNew, const int32_t *cellMap, const 
 
 /* ---- diagnostics ------------------------------------------------------------------------ */
 
+/* ---------------------------------------------------------------------------------------------------
+   Rows either side of the decision path.  Same conventions as above.
+   --------------------------------------------------------------------------------------------------- */
+
+/* remap modes of amr_remap_labels */
+enum {
+    AMR_REMAP_REORDER = 0,   /* map = oldToNew[nOld] (reverseCellMap / reversePointMap): ListOps reorder(map, nNew, -1, list),
+                                hexRef.C:2463, :2529 -- negative targets are dropped, unfilled slots are -1 */
+    AMR_REMAP_GATHER = 1     /* map = newToOld[nNew] (cellMap / pointMap): new = old[map], -1 where map == -1,
+                                hexRef.C:2467-2484, :2533-2556 */
+};
+/* hexRef::updateMesh renumbering of cellLevel_ / pointLevel_ after a topology change.  Independent of the mesh
+   held by the context. */
+int amr_remap_labels(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *map, int mode, const int32_t *oldValues,
+                     int32_t *newValues);
+/* protectedCell_ renumbering, fvMeshHexRefiner.C:229-240 (refine) and :283-297 (unrefine): new = old[cellMap] where
+   cellMap >= 0, false elsewhere. */
+int amr_remap_protected_cells(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, const uint8_t *oldProtected,
+                              uint8_t *newProtected);
+
+/* Flux fix-up of adaptiveFvMesh::updateMesh (adaptiveFvMesh.C:122-291) for one flux field.  The context holds the NEW
+   mesh and its geometry (amr_mesh_set + amr_mesh_set_geometry).  phi [f+b] (surface field flattened in face order;
+   entries of empty patches are ignored) is rewritten with (linear interpolate(U) & Sf) on inflated faces
+   (faceMap == -1), faces made from a master face (reverseFaceMap[faceMap[face]] != face) and the master faces
+   themselves.  U [3n]; UBoundary [3b] boundary values of U (NULL: patch-internal value); nbrU [3b]
+   patchNeighbourField on processor patches (NULL: the library swaps it).  AMR_ERR_INVARIANT = the reference's
+   "should not have removed faces when refining".  nCorrected (nullable) = number of rewritten faces. */
+int amr_correct_fluxes(amr_ctx *ctx, int64_t nOldFaces, const int32_t *faceMap, const int32_t *reverseFaceMap, const double *U,
+                       const double *UBoundary, const double *nbrU, double *phi, int64_t *nCorrected);
+
+/* gradient schemes of amr_estimate_gradient */
+enum { AMR_GRAD_GAUSS_LINEAR = 0, AMR_GRAD_LEAST_SQUARES = 1 };
+/* leastSquaresVectors::New(mesh).pVectors() [3(f+b)] (internal + boundary, face order) and nVectors() [3f]: purely
+   geometric, computed by the host once per topology. */
+int amr_mesh_set_ls_vectors(amr_ctx *ctx, const double *pVectors, const double *nVectors);
+/* gradientEstimator::update (gradientRange.C:87-110) and the coded gradient selectors of the flame tutorials
+   (tutorials/poly_freelyPropFlame2D_H2/constant/dynamicMeshDict:35-60) in one call:
+   error = mag(fvc::grad(x)) [* V/totalVolume when totalVolume > 0], gMin/gMax over all ranks, thresholds
+   min + threshold*(max - min) (upper ones GREAT), normalize when scale != 0.  Gauss linear restates
+   gaussGrad.C (as Lohner does); leastSquares restates leastSquaresGrad.C on the host's vectors.
+   xBoundary / nbrValues as in amr_estimate_lohner.  thrOut[4], gradOut [3n] nullable. */
+int amr_estimate_gradient(amr_ctx *ctx, int scheme, const double *x, const double *xBoundary, const double *nbrValues,
+                          double totalVolume, double refineThreshold, double unrefineThreshold, int scale, double *thrOut,
+                          double *gradOut, double *errorOut);
+
+/* meshSizeObject (meshSizeObject.C:66-160): dx [n] (cbrt(V) in 3-D -- CUDA's cbrt, may differ from glibc's in the
+   last bit; the face-area form with the reference's face count otherwise) and dX [3n] = 2V / sum cmptMag(Sf).
+   geometricD[3] = mesh.geometricD() (+1 / -1).  Either output nullable. */
+int amr_mesh_size(amr_ctx *ctx, const int32_t *geometricD, double *dx, double *dX);
+/* errorEstimator::maxRefinement (errorEstimator.C:262-292): maxLevel >= 0 -> uniform list, else
+   cellLevel + (dx > minDx && error > 0).  error NULL = resident error. */
+int amr_max_refinement(amr_ctx *ctx, int32_t maxLevel, double minDx, const double *dx, const double *error,
+                       int32_t *maxRefinementOut);
+/* cellSize estimator (cellSize.C:133-210) */
+enum { AMR_SIZE_VOLUME = 0, AMR_SIZE_CHARACTERISTIC = 1, AMR_SIZE_MAG = 2, AMR_SIZE_CMPT = 3 };
+int amr_estimate_cell_size(amr_ctx *ctx, int sizeType, const int32_t *geometricD, double lowerUnrefine, double lowerRefine,
+                           const int32_t *cmpts, int nCmpts, const double *minDX, const double *maxDX, const double *dx,
+                           const double *dX, double *errorInOut);
+/* multicomponent estimator: update() = max over the sub-estimators' error fields from -1 (multicomponent.C:95-119) and
+   maxRefinement() (multicomponent.C:122-157), whose in-place ascending-cell loop is reproduced exactly by a
+   wavefront over lower-numbered neighbours.  errorOut NULL = resident error; maxRefinementOut nullable (then
+   maxCellLevels is not read); wavesOut nullable. */
+int amr_multicomponent(amr_ctx *ctx, int nEstimators, const double *const *errors, const int32_t *const *maxCellLevels,
+                       double *errorOut, int32_t *maxRefinementOut, int *wavesOut);
+
 /* number of kernels launched by this context since creation */
 int64_t amr_launch_count(const amr_ctx *ctx);
 /* bytes currently held in device memory by this context */

@@ -104,7 +104,8 @@ OR_API void or_world_free(or_world *w) {
     free(w->m); free(w);
 }
 
-/* primitiveMesh::calcCells: every face is added to its owner and (if internal) its neighbour */
+/* primitiveMesh::calcCells: first every face goes to its owner (ascending), then every internal face to its
+   neighbour (ascending) -- the order matters only for floating-point sums over cells()[c] (meshSizeObject) */
 static void build_cells(or_mesh *m) {
     free(m->cfOff); free(m->cfFaces);
     int64_t n = m->n, nf = m->f + m->b;
@@ -115,10 +116,8 @@ static void build_cells(or_mesh *m) {
     m->cfFaces = (label *)malloc(sizeof(label) * (size_t)(m->cfOff[n] ? m->cfOff[n] : 1));
     label *fill = (label *)malloc(sizeof(label) * (size_t)(n + 1));
     memcpy(fill, m->cfOff, sizeof(label) * (size_t)(n + 1));
-    for (int64_t i = 0; i < nf; i++) {
-        m->cfFaces[fill[m->owner[i]]++] = (label)i;
-        if (i < m->f) m->cfFaces[fill[m->neighbour[i]]++] = (label)i;
-    }
+    for (int64_t i = 0; i < nf; i++) m->cfFaces[fill[m->owner[i]]++] = (label)i;
+    for (int64_t i = 0; i < m->f; i++) m->cfFaces[fill[m->neighbour[i]]++] = (label)i;
     free(fill);
 }
 
@@ -1379,5 +1378,258 @@ OR_API void or_update_levels(int64_t nNew, const label *cellMap, const label *ol
     for (int64_t i = 0; i < nNew; i++) {
         label o = cellMap[i];
         newLevel[i] = oldLevel[o] + (refinedOld && refinedOld[o] ? 1 : 0) - (unrefinedOld && unrefinedOld[o] ? 1 : 0);
+    }
+}
+
+/* ======================================================================================= */
+/* NEXT ROWS: remap after a topology change (N1), flux fix-up (N2), gradient   */
+/* estimators, mesh size, multicomponent (N3).  Same status as the rest: restatements,     */
+/* parity unpinned (no reference test pins any of these).                                  */
+/* ======================================================================================= */
+
+/* ListOps reorder(oldToNew, size, -1, list) as called by hexRef::updateMesh for cellLevel_ / pointLevel_
+   (hexRef.C:2463, :2529): entries with a negative target (merged away) are dropped, unfilled slots are -1 */
+OR_API void or_reorder_labels(int64_t nOld, int64_t nNew, const label *oldToNew, const label *oldV, label *newV) {
+    for (int64_t i = 0; i < nNew; i++) newV[i] = -1;
+    for (int64_t i = 0; i < nOld; i++) { label t = oldToNew[i]; if (t >= 0) newV[t] = oldV[i]; }
+}
+/* the other branch of hexRef::updateMesh (hexRef.C:2467-2484, :2533-2556): new = old[map], -1 for inflated */
+OR_API void or_map_labels(int64_t nNew, const label *map, const label *oldV, label *newV) {
+    for (int64_t i = 0; i < nNew; i++) { label o = map[i]; newV[i] = (o == -1) ? -1 : oldV[o]; }
+}
+/* protectedCell_ renumbering, fvMeshHexRefiner.C:229-240 (refine) and :283-297 (unrefine: oldCelli >= 0 only) */
+OR_API void or_map_protected(int64_t nNew, const label *cellMap, const boolean *oldP, boolean *newP) {
+    for (int64_t i = 0; i < nNew; i++) { label o = cellMap[i]; newP[i] = (o >= 0) ? oldP[o] : 0; }
+}
+
+/* coupled flags over boundary faces */
+static unsigned char *coupled_faces(const or_mesh *m) {
+    unsigned char *coupled = (unsigned char *)calloc((size_t)(m->b + 1), 1);
+    for (int q = 0; q < m->npatch; q++) if (m->patchType[q] == 2)
+        for (label i = 0; i < m->patchSize[q]; i++) coupled[m->patchStart[q] - m->f + i] = 1;
+    return coupled;
+}
+
+/* Flux fix-up of adaptiveFvMesh::updateMesh (adaptiveFvMesh.C:122-291) for one flux field of one rank, on the
+   NEW mesh (geometry = new mesh).  phiU = fvc::interpolate(U) & Sf with linear interpolation;
+   faces rewritten: inflated/appended (faceMap == -1), face-from-master (reverseFaceMap[old] != face), and
+   the master faces themselves, except on empty patches (their patch fields have no entries).
+   U [3n]; Ub [3b] boundary values (NULL: patch-internal value); Un [3b] patchNeighbourField on coupled
+   faces.  Returns the number of rewritten faces. */
+OR_API int64_t or_correct_fluxes(const or_world *w, int r, int64_t nOldFaces, const label *faceMap,
+                                 const label *reverseFaceMap, const scalar *U, const scalar *Ub, const scalar *Un,
+                                 scalar *phi) {
+    const or_mesh *m = &w->m[r];
+    int64_t f = m->f, nf = m->f + m->b, nDone = 0;
+    (void)nOldFaces;
+    unsigned char *coupled = coupled_faces(m);
+    unsigned char *empty = (unsigned char *)calloc((size_t)(m->b + 1), 1);
+    for (int q = 0; q < m->npatch; q++) if (m->patchType[q] == 1)
+        for (label i = 0; i < m->patchSize[q]; i++) empty[m->patchStart[q] - f + i] = 1;
+    unsigned char *fix = (unsigned char *)calloc((size_t)(nf + 1), 1);
+    for (int64_t facei = 0; facei < nf; facei++) {
+        label oldFacei = faceMap[facei];
+        if (oldFacei >= 0) {
+            label masterFacei = reverseFaceMap[oldFacei];
+            if (masterFacei < 0) { free(coupled); free(empty); free(fix); return -1; }   /* :139-145 FatalError */
+            if (masterFacei != facei) { fix[masterFacei] = 1; fix[facei] = 1; }          /* :146-149, :222-226 */
+        } else if (oldFacei == -1) fix[facei] = 1;                                         /* :217-221 */
+    }
+    for (int64_t facei = 0; facei < nf; facei++) {
+        if (!fix[facei]) continue;
+        scalar Uf[3];
+        if (facei < f) {
+            label P = m->owner[facei], N = m->neighbour[facei];
+            for (int k = 0; k < 3; k++) Uf[k] = m->weights[facei] * (U[3 * P + k] - U[3 * N + k]) + U[3 * N + k];
+        } else {
+            int64_t i = facei - f;
+            if (empty[i]) continue;
+            label P = m->owner[facei];
+            for (int k = 0; k < 3; k++) {
+                if (coupled[i]) Uf[k] = m->weights[facei] * U[3 * P + k] + (1.0 - m->weights[facei]) * Un[3 * i + k];
+                else Uf[k] = Ub ? Ub[3 * i + k] : U[3 * P + k];
+            }
+        }
+        phi[facei] = Uf[0] * m->Sf[3 * facei] + Uf[1] * m->Sf[3 * facei + 1] + Uf[2] * m->Sf[3 * facei + 2];
+        nDone++;
+    }
+    free(coupled); free(empty); free(fix);
+    return nDone;
+}
+
+/* Cell gradient of a scalar field for the gradient-based selectors (gradientRange.C:100, the coded
+   selector of tutorials/poly_freelyPropFlame2D_H2/constant/dynamicMeshDict:35-40).
+   scheme 0: Gauss linear  (gaussGrad.C gradf, as in or_estimate_lohner)
+   scheme 1: leastSquares  (leastSquaresGrad.C calcGrad) with the geometric vectors of
+             leastSquaresVectors::New(mesh) supplied by the caller: lsP [3(f+b)] = pVectors incl. boundary
+             faces, lsN [3f] = nVectors.
+   Xn = patchNeighbourField over boundary faces (caller swaps), xb = boundary values (NULL: zeroGradient).
+   Output: magGrad[c] = mag(grad[c]) (* V[c]/tV when tV > 0), optionally grad [3n]. */
+OR_API void or_gradient_mag(const or_world *w, int r, int scheme, const scalar *x, const scalar *xb, const scalar *xn,
+                            const scalar *lsP, const scalar *lsN, scalar tV, scalar *grad, scalar *magGrad) {
+    const or_mesh *m = &w->m[r];
+    int64_t n = m->n, f = m->f, b = m->b;
+    unsigned char *coupled = coupled_faces(m);
+    scalar *g = (scalar *)calloc((size_t)(3 * n + 3), sizeof(scalar));
+    if (scheme == 0) {
+        for (int64_t facei = 0; facei < f; facei++) {
+            label P = m->owner[facei], N = m->neighbour[facei];
+            scalar ssf = m->weights[facei] * (x[P] - x[N]) + x[N];
+            for (int k = 0; k < 3; k++) {
+                scalar Sfssf = m->Sf[3 * facei + k] * ssf;
+                g[3 * P + k] += Sfssf;
+                g[3 * N + k] -= Sfssf;
+            }
+        }
+        for (int64_t i = 0; i < b; i++) {
+            int64_t facei = f + i;
+            label P = m->owner[facei];
+            scalar pssf;
+            if (coupled[i]) pssf = m->weights[facei] * x[P] + (1.0 - m->weights[facei]) * xn[i];
+            else pssf = xb ? xb[i] : x[P];
+            for (int k = 0; k < 3; k++) g[3 * P + k] += m->Sf[3 * facei + k] * pssf;
+        }
+        for (int64_t c = 0; c < n; c++) for (int k = 0; k < 3; k++) g[3 * c + k] /= m->V[c];
+    } else {
+        for (int64_t facei = 0; facei < f; facei++) {
+            label ownFacei = m->owner[facei], neiFacei = m->neighbour[facei];
+            scalar deltaVsf = x[neiFacei] - x[ownFacei];
+            for (int k = 0; k < 3; k++) {
+                g[3 * ownFacei + k] += lsP[3 * facei + k] * deltaVsf;
+                g[3 * neiFacei + k] -= lsN[3 * facei + k] * deltaVsf;
+            }
+        }
+        for (int64_t i = 0; i < b; i++) {
+            int64_t facei = f + i;
+            label P = m->owner[facei];
+            scalar other = coupled[i] ? xn[i] : (xb ? xb[i] : x[P]);
+            scalar d = other - x[P];
+            for (int k = 0; k < 3; k++) g[3 * P + k] += lsP[3 * facei + k] * d;
+        }
+    }
+    for (int64_t c = 0; c < n; c++) {
+        scalar v = sqrt(g[3 * c] * g[3 * c] + g[3 * c + 1] * g[3 * c + 1] + g[3 * c + 2] * g[3 * c + 2]);
+        if (tV > 0) v *= m->V[c] / tV;
+        magGrad[c] = v;
+    }
+    if (grad) memcpy(grad, g, sizeof(scalar) * (size_t)(3 * n));
+    free(coupled); free(g);
+}
+
+/* meshSizeObject::calcDx (meshSizeObject.C:66-131).  geoD = mesh.geometricD() (+1 valid, -1 empty).
+   The reference's bookkeeping is kept as written: an internal face adds its area to BOTH cells but
+   counts twice on the owner and never on the neighbour (:97-104). */
+OR_API void or_mesh_dx(const or_world *w, int r, const label *geoD, scalar *dx) {
+    const or_mesh *m = &w->m[r];
+    int64_t n = m->n, f = m->f, nf = m->f + m->b;
+    int nGeo = 0;
+    for (int k = 0; k < 3; k++) if (geoD[k] > 0) nGeo++;
+    if (nGeo == 3) { for (int64_t c = 0; c < n; c++) dx[c] = cbrt(m->V[c]); return; }
+    scalar validD[3];
+    for (int k = 0; k < 3; k++) validD[k] = geoD[k] < 0 ? 1.0 : 0.0;
+    label *nFaces = (label *)calloc((size_t)(n + 1), sizeof(label));
+    for (int64_t c = 0; c < n; c++) dx[c] = 0.0;
+    for (int64_t facei = 0; facei < nf; facei++) {
+        const scalar *S = m->Sf + 3 * facei;
+        scalar magSf = sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]);
+        scalar dot = (S[0] / magSf) * validD[0] + (S[1] / magSf) * validD[1] + (S[2] / magSf) * validD[2];
+        if (!(smag(dot) > 0.5)) continue;
+        if (facei < f) {
+            dx[m->owner[facei]] += magSf;
+            dx[m->neighbour[facei]] += magSf;
+            nFaces[m->owner[facei]]++;
+            nFaces[m->owner[facei]]++;
+        } else {
+            dx[m->owner[facei]] += magSf;
+            nFaces[m->owner[facei]]++;
+        }
+    }
+    for (int64_t c = 0; c < n; c++) dx[c] = sqrt(dx[c] / (scalar)nFaces[c]);
+    free(nFaces);
+}
+
+/* meshSizeObject::calcDX (meshSizeObject.C:134-160): dX = 2V / sum over cells()[c] of cmptMag(Sf), the sum
+   in primitiveMesh::cells() order */
+OR_API void or_mesh_dX(const or_world *w, int r, scalar *dX) {
+    const or_mesh *m = &w->m[r];
+    for (int64_t c = 0; c < m->n; c++) {
+        scalar s[3] = {0, 0, 0};
+        for (label j = m->cfOff[c]; j < m->cfOff[c + 1]; j++)
+            for (int k = 0; k < 3; k++) s[k] += smag(m->Sf[3 * (int64_t)m->cfFaces[j] + k]);
+        for (int k = 0; k < 3; k++) dX[3 * c + k] = (1.0 * (2.0 * m->V[c])) / s[k];
+    }
+}
+
+/* errorEstimator::maxRefinement (errorEstimator.C:262-292) */
+OR_API void or_max_refinement(const or_world *w, int r, label maxLevel, scalar minDx, const scalar *dx,
+                              const scalar *error, label *out) {
+    const or_mesh *m = &w->m[r];
+    if (maxLevel >= 0 || !m->cellLevel) { for (int64_t c = 0; c < m->n; c++) out[c] = maxLevel; return; }
+    for (int64_t c = 0; c < m->n; c++) {
+        out[c] = m->cellLevel[c];
+        if (dx[c] > minDx && error[c] > 0) out[c]++;
+    }
+}
+
+/* errorEstimators::cellSize::update (cellSize.C:133-210).  sizeType 0 VOLUME, 1 CHARACTERISTIC, 2 MAG, 3 CMPT.
+   CMPT accumulates into the error field it finds (the reference never resets it). */
+OR_API void or_cell_size_error(const or_world *w, int r, int sizeType, const label *geoD, scalar lowerUnrefine,
+                               scalar lowerRefine, const label *cmpts, int nCmpts, const scalar *minDX,
+                               const scalar *maxDX, const scalar *dx, const scalar *dX, scalar *error) {
+    const or_mesh *m = &w->m[r];
+    int64_t n = m->n;
+    if (sizeType == 0) for (int64_t c = 0; c < n; c++) error[c] = m->V[c];
+    else if (sizeType == 1) for (int64_t c = 0; c < n; c++) error[c] = dx[c];
+    else if (sizeType == 2) {
+        for (int64_t c = 0; c < n; c++) error[c] = 0.0;
+        for (int k = 0; k < 3; k++) if (geoD[k] == 1)
+            for (int64_t c = 0; c < n; c++) error[c] += dX[3 * c + k] * dX[3 * c + k];
+        for (int64_t c = 0; c < n; c++) error[c] = sqrt(error[c]);
+    } else {
+        for (int i = 0; i < nCmpts; i++) {
+            label k = cmpts[i];
+            for (int64_t c = 0; c < n; c++) {
+                if (dX[3 * c + k] > maxDX[k]) error[c] = smax(1.0, error[c]);
+                else if (dX[3 * c + k] < minDX[k]) error[c] = smax(-1.0, error[c]);
+                else error[c] = smax(0, error[c]);
+            }
+        }
+        return;
+    }
+    for (int64_t c = 0; c < n; c++) {
+        if (error[c] < lowerUnrefine) error[c] = -1.0;
+        else if (error[c] > lowerRefine) error[c] = 1.0;
+        else error[c] = 0.0;
+    }
+}
+
+/* errorEstimators::multicomponent::update (multicomponent.C:95-119): error = max over the sub-estimators, from -1 */
+OR_API void or_multicomponent_error(int64_t n, int nEst, const scalar *const *errors, scalar *error) {
+    for (int64_t c = 0; c < n; c++) error[c] = -1.0;
+    for (int i = 0; i < nEst; i++)
+        for (int64_t c = 0; c < n; c++) error[c] = smax(error[c], errors[i][c]);
+}
+
+/* errorEstimators::multicomponent::maxRefinement (multicomponent.C:122-157): in-place, ascending cells; a cell
+   that fires also overwrites its cellCells -- order dependent, kept as written */
+OR_API void or_multicomponent_max_refinement(const or_world *w, int r, int nEst, const scalar *const *errors,
+                                             const label *const *maxCellLevels, label *maxRefinement) {
+    const or_mesh *m = &w->m[r];
+    int64_t n = m->n, f = m->f;
+    for (int64_t c = 0; c < n; c++) maxRefinement[c] = 0;
+    for (int i = 0; i < nEst; i++) {
+        const scalar *errori = errors[i];
+        const label *maxCellLevel = maxCellLevels[i];
+        for (int64_t celli = 0; celli < n; celli++) {
+            if (errori[celli] > 0.5 && maxRefinement[celli] < maxCellLevel[celli]) {
+                maxRefinement[celli] = maxCellLevel[celli];
+                for (label j = m->cfOff[celli]; j < m->cfOff[celli + 1]; j++) {       /* cellCells via cells() */
+                    label facei = m->cfFaces[j];
+                    if (facei >= f) continue;
+                    label cellj = (m->owner[facei] == celli) ? m->neighbour[facei] : m->owner[facei];
+                    maxRefinement[cellj] = maxCellLevel[celli];
+                }
+            }
+        }
     }
 }

@@ -87,6 +87,19 @@ def lib():
         L.or_map_field_conservative.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                 C.c_void_p, C.c_void_p]
         L.or_update_levels.argtypes = [C.c_int64] + [C.c_void_p] * 5
+        L.or_reorder_labels.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.or_map_labels.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.or_map_protected.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.or_correct_fluxes.restype = C.c_int64
+        L.or_correct_fluxes.argtypes = [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 6
+        L.or_gradient_mag.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_double, C.c_void_p, C.c_void_p]
+        L.or_mesh_dx.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.or_mesh_dX.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.or_max_refinement.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.or_cell_size_error.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.or_multicomponent_error.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+        L.or_multicomponent_max_refinement.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.or_set_threads.argtypes = [C.c_int]
         L.or_max_threads.restype = C.c_int
         L.or_set_threads(1)
@@ -289,6 +302,86 @@ class World:
         lv = [_i32(a) for a in levels]
         return int(lib().or_check_levels(self._h, _pp(lv)))
 
+    # -- rows either side of the path
+    def swap_owner_values(self, vals):
+        """patchNeighbourField of a cell field over the boundary faces of every rank (python restatement of the swap:
+        processor patch pairs list their faces in the same order)"""
+        out = []
+        for r, m in enumerate(self.meshes):
+            v = np.ascontiguousarray(vals[r])
+            out.append(v[m.owner[m.f:]].copy())
+        st = [m.patch_arrays() for m in self.meshes]
+        for r, m in enumerate(self.meshes):
+            s0, sz, ty, nb = st[r]
+            for q in range(len(s0)):
+                if ty[q] != 2:
+                    continue
+                s = int(nb[q])
+                ms = self.meshes[s]
+                t0, tz, tty, tnb = st[s]
+                back = [k for k in range(len(t0)) if tty[k] == 2 and tnb[k] == r][0]
+                src = np.ascontiguousarray(vals[s])[ms.owner[t0[back]:t0[back] + tz[back]]]
+                out[r][s0[q] - m.f:s0[q] - m.f + sz[q]] = src
+        return out
+
+    def correct_fluxes(self, r, face_map, reverse_face_map, U, phi, U_boundary=None, nbr_U=None):
+        face_map, reverse_face_map = _i32(face_map), _i32(reverse_face_map)
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        return int(lib().or_correct_fluxes(self._h, r, len(reverse_face_map), face_map.ctypes.data, reverse_face_map.ctypes.data,
+                                           U.ctypes.data, None if U_boundary is None else U_boundary.ctypes.data,
+                                           None if nbr_U is None else nbr_U.ctypes.data, phi.ctypes.data))
+
+    def gradient_mag(self, r, x, scheme=0, xb=None, xn=None, ls_p=None, ls_n=None, total_volume=0.0):
+        m = self.meshes[r]
+        grad = np.empty((m.n, 3), dtype=np.float64)
+        mag = np.empty(m.n, dtype=np.float64)
+        if xn is None:
+            xn = np.zeros(max(m.b, 1))
+        lib().or_gradient_mag(self._h, r, scheme, x.ctypes.data, None if xb is None else xb.ctypes.data, xn.ctypes.data,
+                              None if ls_p is None else ls_p.ctypes.data, None if ls_n is None else ls_n.ctypes.data,
+                              total_volume, grad.ctypes.data, mag.ctypes.data)
+        return mag, grad
+
+    def mesh_dx(self, r, geometric_d):
+        gd = _i32(geometric_d)
+        out = np.empty(self.meshes[r].n, dtype=np.float64)
+        lib().or_mesh_dx(self._h, r, gd.ctypes.data, out.ctypes.data)
+        return out
+
+    def mesh_dX(self, r):
+        out = np.empty((self.meshes[r].n, 3), dtype=np.float64)
+        lib().or_mesh_dX(self._h, r, out.ctypes.data)
+        return out
+
+    def max_refinement(self, r, max_level, min_dx=0.0, dx=None, error=None):
+        out = np.empty(self.meshes[r].n, dtype=np.int32)
+        lib().or_max_refinement(self._h, r, max_level, min_dx, None if dx is None else dx.ctypes.data,
+                                None if error is None else error.ctypes.data, out.ctypes.data)
+        return out
+
+    def cell_size_error(self, r, size_type, geometric_d, lower_unrefine=0.0, lower_refine=0.0, cmpts=(), min_dX=None, max_dX=None,
+                        dx=None, dX=None, error=None):
+        gd, cm = _i32(geometric_d), _i32(cmpts)
+        lo = np.zeros(3) if min_dX is None else np.asarray(min_dX, dtype=np.float64)
+        hi = np.zeros(3) if max_dX is None else np.asarray(max_dX, dtype=np.float64)
+        if error is None:
+            error = np.zeros(self.meshes[r].n, dtype=np.float64)
+        lib().or_cell_size_error(self._h, r, size_type, gd.ctypes.data, lower_unrefine, lower_refine, cm.ctypes.data, len(cm),
+                                 lo.ctypes.data, hi.ctypes.data, None if dx is None else dx.ctypes.data,
+                                 None if dX is None else dX.ctypes.data, error.ctypes.data)
+        return error
+
+    def multicomponent(self, r, errors, max_cell_levels=None):
+        n = self.meshes[r].n
+        err = np.empty(n, dtype=np.float64)
+        lib().or_multicomponent_error(n, len(errors), _pp(errors), err.ctypes.data)
+        mr = None
+        if max_cell_levels is not None:
+            lv = [_i32(a) for a in max_cell_levels]
+            mr = np.empty(n, dtype=np.int32)
+            lib().or_multicomponent_max_refinement(self._h, r, len(errors), _pp(errors), _pp(lv), mr.ctypes.data)
+        return err, mr
+
 
 def remap_refine_cell(cell_map, reverse_map, refine_cell):
     cell_map, reverse_map = _i32(cell_map), _i32(reverse_map)
@@ -322,6 +415,28 @@ def update_levels(cell_map, old_level, refined_old=None, unrefined_old=None):
     lib().or_update_levels(len(cell_map), cell_map.ctypes.data, old_level.ctypes.data,
                            None if refined_old is None else refined_old.ctypes.data,
                            None if unrefined_old is None else unrefined_old.ctypes.data, out.ctypes.data)
+    return out
+
+
+def reorder_labels(old_to_new, n_new, old_values):
+    old_to_new, old_values = _i32(old_to_new), _i32(old_values)
+    out = np.empty(n_new, dtype=np.int32)
+    lib().or_reorder_labels(len(old_values), n_new, old_to_new.ctypes.data, old_values.ctypes.data, out.ctypes.data)
+    return out
+
+
+def gather_labels(new_to_old, old_values):
+    new_to_old, old_values = _i32(new_to_old), _i32(old_values)
+    out = np.empty(len(new_to_old), dtype=np.int32)
+    lib().or_map_labels(len(new_to_old), new_to_old.ctypes.data, old_values.ctypes.data, out.ctypes.data)
+    return out
+
+
+def remap_protected_cells(cell_map, old_protected):
+    cell_map = _i32(cell_map)
+    old_protected = np.ascontiguousarray(old_protected, dtype=np.uint8)
+    out = np.empty(len(cell_map), dtype=np.uint8)
+    lib().or_map_protected(len(cell_map), cell_map.ctypes.data, old_protected.ctypes.data, out.ctypes.data)
     return out
 
 

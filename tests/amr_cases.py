@@ -74,6 +74,10 @@ class OracleBackend:
         return int(self.w.protect_patches([err], ids, n_layers)[0])
 
     def select_refine(self, err, max_level, n_layers, protected_patch_ids=(), max_cells=2147483647, refine_cell_out=None, kind=0, **_):
+        if err is None:
+            err = self.err
+        if not np.isscalar(max_level):
+            max_level = [max_level]
         if kind in (2, 3):
             rc, rs, sw = self.w.poly_select_refine([err], max_level, n_layers, protected_patch_ids=protected_patch_ids)
             if refine_cell_out is not None:
@@ -127,3 +131,119 @@ class OracleBackend:
 
     def max_cell_field(self, v):
         return self.w.max_cell_field(0, v)
+
+    # rows either side of the path
+    def reorder_labels(self, old_to_new, n_new, old_values):
+        return self.O.reorder_labels(old_to_new, n_new, old_values)
+
+    def gather_labels(self, new_to_old, old_values):
+        return self.O.gather_labels(new_to_old, old_values)
+
+    def remap_protected_cells(self, cell_map, old_protected):
+        return self.O.remap_protected_cells(cell_map, old_protected)
+
+    def correct_fluxes(self, face_map, reverse_face_map, U, phi, U_boundary=None, nbr_U=None):
+        k = self.w.correct_fluxes(0, face_map, reverse_face_map, U, phi, U_boundary=U_boundary, nbr_U=nbr_U)
+        if k < 0:
+            from blastamr_b200.capi import AmrError
+            raise AmrError(-5, "Problem: should not have removed faces when refining.")
+        return k
+
+    def set_ls_vectors(self, p_vectors, n_vectors):
+        self.ls = (p_vectors, n_vectors)
+
+    def estimate_gradient(self, x, scheme=0, x_boundary=None, nbr_values=None, total_volume=0.0, refine_threshold=0.5,
+                          unrefine_threshold=0.4, scale=True, want_grad=False):
+        kw = dict(ls_p=self.ls[0], ls_n=self.ls[1]) if scheme == 1 else {}
+        mag, g = self.w.gradient_mag(0, x, scheme=scheme, xb=x_boundary, xn=nbr_values, total_volume=total_volume, **kw)
+        thr, _ = self.w.range_thresholds([mag], refine_threshold, unrefine_threshold)
+        if scale:
+            self.w.normalize([mag], *thr)
+        self.err = mag
+        return mag, np.asarray(thr), (g if want_grad else None)
+
+    def mesh_size(self, geometric_d, want_dx=True, want_dX=True):
+        return self.w.mesh_dx(0, geometric_d), self.w.mesh_dX(0)
+
+    def max_refinement(self, max_level, min_dx=0.0, dx=None, error=None):
+        return self.w.max_refinement(0, max_level, min_dx, dx, error)
+
+    def estimate_cell_size(self, size_type, geometric_d, **kw):
+        return self.w.cell_size_error(0, size_type, geometric_d, **kw)
+
+    def multicomponent(self, errors, max_cell_levels=None):
+        e, mr = self.w.multicomponent(0, errors, max_cell_levels)
+        self.err = e
+        return e, mr, 3
+
+
+# ---- helpers for the rows either side of the path (flux fix-up, gradients) ---------------------------------
+
+def _face_dir(Sf):
+    """0..5 = -x,+x,-y,+y,-z,+z for axis-aligned faces"""
+    ax = np.argmax(np.abs(Sf), axis=1)
+    return 2 * ax + (Sf[np.arange(len(Sf)), ax] > 0)
+
+
+def face_maps(m_old, m_new, cell_map):
+    """mapPolyMesh faceMap / reverseFaceMap of a REFINEMENT step, reconstructed from the two meshes (the
+    topology engine rebuilds faces instead of tracking them): a new face descends from the old face between
+    the old cells of its two sides (or on the same patch side of its owner's old cell); faces inside a split
+    cell are inflated (-1).  The master of an old face is its lowest-numbered descendant."""
+    own_o, nei_o = m_old.owner, m_old.neighbour
+    key_int = {(int(own_o[i]), int(nei_o[i])): i for i in range(m_old.f)}
+    dir_o = _face_dir(m_old.Sf.reshape(-1, 3)[m_old.f:])
+    key_bnd = {(int(own_o[m_old.f + i]), int(dir_o[i])): m_old.f + i for i in range(m_old.b)}
+    nf_new = m_new.f + m_new.b
+    face_map = np.full(nf_new, -1, np.int32)
+    dir_n = _face_dir(m_new.Sf.reshape(-1, 3)[m_new.f:])
+    for i in range(m_new.f):
+        a, b = int(cell_map[m_new.owner[i]]), int(cell_map[m_new.neighbour[i]])
+        if a != b:
+            face_map[i] = key_int[(min(a, b), max(a, b))]
+    for i in range(m_new.b):
+        face_map[m_new.f + i] = key_bnd[(int(cell_map[m_new.owner[m_new.f + i]]), int(dir_n[i]))]
+    rev = np.full(m_old.f + m_old.b, -1, np.int32)
+    for i in range(nf_new - 1, -1, -1):
+        if face_map[i] >= 0:
+            rev[face_map[i]] = i
+    return face_map, rev
+
+
+def ls_vectors(m, cc_nbr=None):
+    """leastSquaresVectors (OpenFOAM-v2212 leastSquaresVectors.C, restated in numpy as TEST INPUT: the library
+    takes these vectors from the host, so parity only needs both sides to see the same numbers)."""
+    n, f, b = m.n, m.f, m.b
+    C, w = m.cc, m.weights
+    magSf = m.magSf
+    Sf = m.Sf.reshape(-1, 3)
+    own, nei = m.owner, m.neighbour
+    dd = np.zeros((n, 3, 3))
+    d = C[nei] - C[own[:f]]
+    wdd = (magSf[:f] / (d * d).sum(1))[:, None, None] * d[:, :, None] * d[:, None, :]
+    np.add.at(dd, own[:f], (1 - w[:f])[:, None, None] * wdd)
+    np.add.at(dd, nei, w[:f][:, None, None] * wdd)
+    # boundary d-vectors: face centre - cell centre for plain patches (n * 1/deltaCoeffs on these box meshes),
+    # neighbour centre - cell centre on processor patches
+    nhat = Sf[f:] / magSf[f:, None]
+    pd = nhat / m.delta_coeffs[f:, None]
+    st, sz, ty, nb = m.patch_arrays()
+    coupled = np.zeros(b, bool)
+    for q in range(len(st)):
+        if ty[q] == 2:
+            coupled[st[q] - f:st[q] - f + sz[q]] = True
+    if cc_nbr is not None:
+        pd[coupled] = (cc_nbr - C[own[f:]])[coupled]
+    fac = np.where(coupled, 1 - w[f:], 1.0) * magSf[f:] / (pd * pd).sum(1)
+    np.add.at(dd, own[f:], fac[:, None, None] * pd[:, :, None] * pd[:, None, :])
+    # 2-D meshes: the empty direction carries no information; regularise like inv(symmTensorField) does
+    for k in range(3):
+        if np.all(np.abs(dd[:, k, k]) < 1e-300):
+            dd[:, k, k] = 1.0
+    inv = np.linalg.inv(dd)
+    s = magSf[:f] / (d * d).sum(1)
+    ls_p = np.zeros((f + b, 3))
+    ls_p[:f] = ((1 - w[:f]) * s)[:, None] * np.einsum("fij,fj->fi", inv[own[:f]], d)
+    ls_n = (-w[:f] * s)[:, None] * np.einsum("fij,fj->fi", inv[nei], d)
+    ls_p[f:] = fac[:, None] * np.einsum("fij,fj->fi", inv[own[f:]], pd)
+    return np.ascontiguousarray(ls_p), np.ascontiguousarray(ls_n)

@@ -124,3 +124,81 @@ def closure_unrefine(mesh, pflags):
         ok = np.ones(mesh.p, bool)
         np.logical_and.at(ok, pts, uc[mesh.pc_cells])
         pf &= ok
+
+
+# ---- rows either side of the path: independent restatements from the definitions -------------------------
+
+def coupled_mask(mesh):
+    st, sz, ty, _ = mesh.patch_arrays()
+    c = np.zeros(mesh.b, bool)
+    e = np.zeros(mesh.b, bool)
+    for q in range(len(st)):
+        (c if ty[q] == 2 else e if ty[q] == 1 else np.zeros(mesh.b, bool))[st[q] - mesh.f:st[q] - mesh.f + sz[q]] = True
+    return c, e
+
+
+def gauss_grad(mesh, x, xb=None, xn=None):
+    """Gauss linear gradient from its definition (sum of Sf*x_f over the cell's faces / V); the summation order
+    differs from the reference's, so comparisons are to round-off, not bitwise"""
+    f = mesh.f
+    own, nei, w = mesh.owner, mesh.neighbour, mesh.weights
+    Sf = mesh.Sf.reshape(-1, 3)
+    g = np.zeros((mesh.n, 3))
+    xf = w[:f] * x[own[:f]] + (1 - w[:f]) * x[nei]
+    np.add.at(g, own[:f], Sf[:f] * xf[:, None])
+    np.subtract.at(g, nei, Sf[:f] * xf[:, None])
+    cpl, _ = coupled_mask(mesh)
+    xbf = x[own[f:]].copy() if xb is None else xb.copy()
+    if xn is not None:
+        xbf[cpl] = (w[f:] * x[own[f:]] + (1 - w[f:]) * xn)[cpl]
+    np.add.at(g, own[f:], Sf[f:] * xbf[:, None])
+    return g / mesh.vol[:, None]
+
+
+def flux(mesh, U, Ub=None, Un=None):
+    """phiU = linear interpolate(U) & Sf on every face (empty-patch entries meaningless)"""
+    f = mesh.f
+    own, nei, w = mesh.owner, mesh.neighbour, mesh.weights
+    Sf = mesh.Sf.reshape(-1, 3)
+    Uf = np.empty((f + mesh.b, 3))
+    Uf[:f] = w[:f, None] * (U[own[:f]] - U[nei]) + U[nei]
+    Uf[f:] = U[own[f:]] if Ub is None else Ub
+    cpl, _ = coupled_mask(mesh)
+    if Un is not None and cpl.any():
+        Uf[f:][cpl] = (w[f:, None] * U[own[f:]] + (1 - w[f:, None]) * Un)[cpl]
+    return Uf[:, 0] * Sf[:, 0] + Uf[:, 1] * Sf[:, 1] + Uf[:, 2] * Sf[:, 2]
+
+
+def multicomponent_wavefront(mesh, errors, levels):
+    """the device algorithm for multicomponent::maxRefinement (fields.cuh k_mc_*), emulated with numpy: checks the
+    recurrence against the oracle's literal in-place loop without a GPU"""
+    n, f = mesh.n, mesh.f
+    own, nei = mesh.owner[:f], mesh.neighbour
+    nbr = [[] for _ in range(n)]
+    for a, b in zip(own, nei):
+        nbr[a].append(int(b))
+        nbr[b].append(int(a))
+    mr = np.zeros(n, np.int32)
+    waves = 0
+    for err, lv in zip(errors, levels):
+        state = np.where(err > 0.5, 2, 0).astype(np.int8)
+        while (state == 2).any():
+            new = state.copy()                      # Jacobi sweep: the most conservative schedule
+            for c in np.flatnonzero(state == 2):
+                lower = [a for a in nbr[c] if a < c]
+                max_f = max([a for a in lower if state[a] == 1], default=-1)
+                max_u = max([a for a in lower if state[a] == 2], default=-1)
+                if max_u > max_f:
+                    continue
+                seen = lv[max_f] if max_f >= 0 else mr[c]
+                new[c] = 1 if seen < lv[c] else 0
+            assert (new != state).any()
+            state = new
+            waves += 1
+        out = mr.copy()
+        for c in range(n):
+            fired = [a for a in nbr[c] + [c] if state[a] == 1]
+            if fired:
+                out[c] = lv[max(fired)]
+        mr = out
+    return mr, waves

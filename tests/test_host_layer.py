@@ -42,6 +42,10 @@ def test_dictionary_keys_and_tables():
     assert set(hostapi.selection_table("fvMeshRefiner")) >= {"hexRefiner", "polyRefiner"}
     with pytest.raises(hostapi.FatalError):
         hostapi.parse_dict_keys("a { b 1; ")
+    assert {"cellSize", "multicomponent"} <= set(est)
+    # PtrList<entry> values (multicomponent.C:52): the `;` inside the entries does not end the list
+    multi = "errorEstimator multicomponent; errorEstimators ( a { errorEstimator delta; deltaField p; } b { errorEstimator cellSize; type volume; } ); maxRefinement 2;"
+    assert set(hostapi.parse_dict_keys(multi)) == {"errorEstimator", "errorEstimators", "maxRefinement"}
 
 
 def test_no_gpu_fails_loudly():
@@ -168,4 +172,82 @@ def test_unknown_names_and_missing_keywords_raise():
     am.set_field("test", np.zeros(64))
     with pytest.raises(hostapi.FatalError, match="Either maxRefinement or minDx"):
         am.update()
+    am.close()
+
+
+CAVITY2D = [("xmin", "movingWall"), ("xmax", "fixedWalls"), ("ymin", "fixedWalls"), ("ymax", "fixedWalls"),
+            ("zmin", "frontAndBack"), ("zmax", "frontAndBack")]
+
+
+@pytest.mark.gpu
+def test_polyRefiner_2d_prismatic_through_update():
+    """tutorials/damBreak2D as shipped: `refiner polyRefiner;` on a one-cell-thick mesh with empty front/back ->
+    prismatic2DRefinement (fvMeshPolyRefiner.C:139-155); nRefinementBufferLayers raised to 3 (:267-283)"""
+    text = (DICT % dict(layers=1, maxlev=2, prot="")).replace("refiner         hexRefiner;", "refiner         polyRefiner;")
+    oc = M.Octree(24, 24, 1, (0.1, 0.1, 0.01), 2, CAVITY2D, {"frontAndBack": M.PATCH_EMPTY}, two_d=True)
+    am = hostapi.AdaptiveFvMesh(text, oc, faces=True)
+    n0 = am.n_cells
+    for _ in range(2):
+        am.set_field("test", cases.box_field(am.mesh.cc))
+        assert am.update()
+    n1 = am.n_cells
+    assert n1 > n0 and am.mesh.cell_level.max() == 2
+    m = am.mesh
+    lv = m.cell_level
+    assert np.abs(lv[m.owner[:m.f]] - lv[m.neighbour]).max() <= 1
+    for e in range(m.n_edges):
+        cs = m.ec_cells[m.ec_off[e]:m.ec_off[e + 1]]
+        assert lv[cs].max() - lv[cs].min() <= 1
+    for _ in range(4):
+        am.set_field("test", np.zeros(am.n_cells))
+        am.update()
+    assert am.n_cells < n1
+    assert any(k == "unrefine" for k, _ in am.history)
+    am.close()
+
+
+@pytest.mark.gpu
+def test_gradientRange_on_device_through_update():
+    """gradientRange with fvc::grad (Gauss linear) computed by the library: the steep part of a front is refined"""
+    text = """errorEstimator gradientRange; gradField T; refineThreshold 0.3; unrefineThreshold 0.06;
+              lowerRefineLevel 0; unrefineLevel 0; maxRefinement 2; nBufferLayers 1;"""
+    oc = M.Octree(12, 12, 12, (1.0, 1.0, 1.0), 2)
+    am = hostapi.AdaptiveFvMesh(text, oc, geometry=True)
+    n0 = am.n_cells
+    for _ in range(2):
+        am.set_field("T", cases.front_field(am.mesh.cc, r0=0.3, w=0.05))
+        assert am.update()
+    m = am.mesh
+    d = np.sqrt(((m.cc - 0.5) ** 2).sum(1))
+    assert am.n_cells > n0
+    assert (m.cell_level == 2).any()
+    assert np.abs(d[m.cell_level == 2] - 0.3).max() < 0.25       # refinement hugs the front
+    assert (m.cell_level[np.abs(d - 0.3) < 0.02] == 2).mean() > 0.9
+    am.close()
+
+
+@pytest.mark.gpu
+def test_multicomponent_cellSize_and_minDx_through_update():
+    """multicomponent of (fieldValue on a box with minDx instead of maxRefinement, cellSize characteristic):
+    cells inside the box refine until they are narrower than minDx; cellSize keeps every other cell as it is"""
+    text = """errorEstimator multicomponent;
+              errorEstimators
+              (
+                  box  { errorEstimator fieldValue; fieldName test; lowerRefineLevel 0.01; unrefineLevel 0.01; minDx 0.03; }
+                  size { errorEstimator cellSize; type characteristic; minDx 0.001; maxDx 10; }
+              );
+              lowerRefineLevel 0.01; unrefineLevel 0.01; maxRefinement 3; nBufferLayers 1;"""
+    oc = M.Octree(10, 10, 10, (1.0, 1.0, 1.0), 3)
+    am = hostapi.AdaptiveFvMesh(text, oc, geometry=True)
+    n0 = am.n_cells
+    changed = []
+    for _ in range(4):
+        inside = np.all((am.mesh.cc > 0.3) & (am.mesh.cc < 0.6), axis=1).astype(np.float64)
+        am.set_field("test", inside)
+        changed.append(am.update())
+    m = am.mesh
+    assert changed[0] and am.n_cells > n0
+    inside = np.all((m.cc > 0.3) & (m.cc < 0.6), axis=1)
+    # dx0 = 0.1 -> 0.05 -> 0.025 < minDx: exactly two levels, although maxRefinement of the outer dictionary is 3
+    assert m.cell_level[inside].max() == 2 and (m.cell_level[inside] == 2).all()
     am.close()
