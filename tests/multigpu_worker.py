@@ -51,6 +51,24 @@ def main():
         gotL = ctx.estimate_lohner(x[cg].copy(), 0.05)
         if not np.array_equal(refL, gotL):
             fails.append("Lohner")
+        # gradient selector on the decomposed mesh (8-byte swap of x, gMin/gMax over ranks) and the flux fix-up with
+        # every face rewritten (24-byte swap of U): both against the multi-rank oracle world
+        xs = [x[l.cell_global].copy() for l in loc]
+        xn = wR.swap_owner_values(xs)
+        mags = [wR.gradient_mag(r, xs[r], xn=xn[r])[0] for r in range(world)]
+        thr_w, _ = wR.range_thresholds(mags, 0.3, 0.06)
+        refg = mags[rank].copy(); wR.normalize([refg], *thr_w)
+        gotg, gthr2, _ = ctx.estimate_gradient(xs[rank], refine_threshold=0.3, unrefine_threshold=0.06)
+        if not (np.array_equal(np.asarray(thr_w), gthr2) and np.array_equal(refg, gotg)):
+            fails.append("estimate_gradient")
+        Us = [np.stack([np.sin(3 * l.cc[:, 0]), np.cos(2 * l.cc[:, 1]), l.cc[:, 2] ** 2 + shift], axis=1).copy() for l in loc]
+        Un = wR.swap_owner_values(Us)
+        fmap = np.full(me.f + me.b, -1, np.int32)
+        phi_ref = np.zeros(me.f + me.b); phi_gpu = np.zeros(me.f + me.b)
+        n_ref = wR.correct_fluxes(rank, fmap, np.zeros(1, np.int32), Us[rank], phi_ref, nbr_U=np.ascontiguousarray(Un[rank]))
+        n_gpu = ctx.correct_fluxes(fmap, np.zeros(1, np.int32), Us[rank], phi_gpu)
+        if n_ref != n_gpu or not np.array_equal(phi_ref, phi_gpu):
+            fails.append("correct_fluxes (vector halo)")
         # gradientRange thresholds (gMin/gMax over ranks)
         raw = w.estimate("delta", [x])[0]
         thr_g, mm_g = w.range_thresholds([raw], 0.5, 0.4)
