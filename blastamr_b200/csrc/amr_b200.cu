@@ -63,6 +63,14 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->numSMs = sms;
         const char *np = getenv("AMR_B200_NO_PIPELINE");
         if (np && np[0] == '1') ctx->usePipeline = false;
+        // tuning knob: "num/den" = marked fraction below which a buffer layer takes the sparse push form; "0" = never
+        const char *pf = getenv("AMR_B200_PUSH_FRACTION");
+        if (pf) {
+            int a = 0, b = 1;
+            if (sscanf(pf, "%d/%d", &a, &b) >= 1 && a >= 0 && b > 0) { ctx->pushNum = a; ctx->pushDen = b; }
+        }
+        const char *pm = getenv("AMR_B200_PUSH_MIN_CELLS");      // below this mesh size the extra launches do not pay
+        if (pm) ctx->pushMinCells = atoll(pm);
     }
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -72,7 +80,9 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
     cudaMalloc((void **)&ctx->dCount, 4 * sizeof(int64_t));
     cudaMallocHost((void **)&ctx->hFlags, 16 * sizeof(int));
     cudaMallocHost((void **)&ctx->hCount, 4 * sizeof(int64_t));
-    if (!ctx->dFlags || !ctx->dCount || !ctx->hFlags || !ctx->hCount) { delete ctx; return AMR_ERR_CUDA; }
+    cudaMallocHost((void **)&ctx->hMarked, 16 * sizeof(long long));
+    if (ctx->hMarked) for (int i = 0; i < 16; i++) ctx->hMarked[i] = -1;
+    if (!ctx->dFlags || !ctx->dCount || !ctx->hFlags || !ctx->hCount || !ctx->hMarked) { delete ctx; return AMR_ERR_CUDA; }
     cudaMemset(ctx->dFlags, 0, 16 * sizeof(int));
     cudaMemset(ctx->dCount, 0, 4 * sizeof(int64_t));
     *out = ctx;
@@ -120,7 +130,7 @@ AMR_API int amr_ctx_destroy(amr_ctx *ctx) {
     if (ctx->region) cudaFree(ctx->region);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     cudaFree(ctx->dFlags); cudaFree(ctx->dCount);
-    cudaFreeHost(ctx->hFlags); cudaFreeHost(ctx->hCount);
+    cudaFreeHost(ctx->hFlags); cudaFreeHost(ctx->hCount); cudaFreeHost(ctx->hMarked);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->upStream) cudaStreamDestroy(ctx->upStream);
     if (ctx->downStream) cudaStreamDestroy(ctx->downStream);
@@ -781,19 +791,41 @@ AMR_API int amr_normalize_range(amr_ctx *ctx, double refineThreshold, double unr
 
 // one face-layer growth of `cur` (n flags) with ping-pong buffer `tmp`; src == cur.  Returns the
 // buffer holding the result in *res.
-static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res) {
+// `site` identifies the call site (which layer of which stage): the marked fraction seen there by the PREVIOUS call
+// predicts whether the adaptive sequence is worth launching at all (AMR markings change slowly from step to step);
+// a wrong prediction only costs time, both forms give the same flags.
+static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res, int site) {
     const int64_t n = ctx->n;
     if (ctx->nCoupled > 0) {
         TRY(haloSwapCells(ctx, src, 1, ctx->ghost8));
     }
-    if (pipeOk(ctx, ctx->cc)) TRY(launchPipe(ctx, kp_extend, ctx->cc, (const u8 *)cur, src, tmp));
-    else LAUNCH(k_extend, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, cur, src, tmp);
+    const int *gate = nullptr;
+    if (ctx->pushNum > 0 && n >= ctx->pushMinCells && n > 0) {
+        const bool al = ((((uintptr_t)src) | ((uintptr_t)cur) | ((uintptr_t)tmp)) & 15) == 0;
+        unsigned long long *total = (unsigned long long *)(ctx->dCount + 1);
+        const long long seen = ctx->hMarked[site];                // marked cells at this site last time (-1: never)
+        const bool tryPush = seen < 0 || seen * ctx->pushDen < 2 * n * ctx->pushNum;   // within 2x of the threshold
+        CK(cudaMemsetAsync(total, 0, 8, ctx->stream));
+        LAUNCH(k_count_set16, gridFor(n, kThreads * 16), kThreads, n, src, al, total);
+        CK(cudaMemcpyAsync(ctx->hMarked + site, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (tryPush) {
+            int *g = ctx->dFlags + 12;
+            LAUNCH(k_push_gate, 1, 1, (const unsigned long long *)total, (long long)n, (long long)ctx->pushNum, (long long)ctx->pushDen, g);
+            LAUNCH(k_copy_flags_gated, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)cur, tmp, al, (const int *)g);
+            LAUNCH(k_extend_push, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, src, al, tmp, (const int *)g);
+            gate = g;
+        }
+    }
+    if (pipeOk(ctx, ctx->cc)) TRY(launchPipe(ctx, kp_extend, ctx->cc, (const u8 *)cur, src, tmp, gate));
+    else LAUNCH(k_extend, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, cur, src, tmp, gate);
     if (ctx->nCoupled > 0)
         LAUNCH(k_fix_extend, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
                (const u8 *)ctx->ghost8, tmp);
     *res = tmp;
     return AMR_OK;
 }
+constexpr int kSiteProtect = 0, kSiteRefine = 4, kSiteUnrefine = 8;   // 4 slots each in ctx->hMarked[16]
+static inline int siteOf(int base, int layer) { return base + (layer < 3 ? layer : 3); }
 
 AMR_API int amr_protect_patches(amr_ctx *ctx, const int32_t *patchIds, int nPatchIds, int nLayers, double *errorInOut,
                                 int64_t *nProtected) {
@@ -815,7 +847,7 @@ AMR_API int amr_protect_patches(amr_ctx *ctx, const int32_t *patchIds, int nPatc
     }
     for (int i = 0; i < nLayers; i++) {
         u8 *res;
-        TRY(extendLayer(ctx, cur, cur, tmp, &res));
+        TRY(extendLayer(ctx, cur, cur, tmp, &res, siteOf(kSiteProtect, i)));
         std::swap(cur, tmp);
     }
     CK(cudaMemsetAsync(ctx->dCount, 0, sizeof(int64_t), ctx->stream));
@@ -1027,7 +1059,7 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
     // M2: extendMarkedCells(refineCell, maxRefinement, i == 0, force = true), fvMeshHexRefiner.C:1509-1512
     for (int i = 0; i < nBufferLayers; i++) {
         u8 *res;
-        TRY(extendLayer(ctx, cur, (i == 0 && forced) ? src0 : cur, tmp, &res));
+        TRY(extendLayer(ctx, cur, (i == 0 && forced) ? src0 : cur, tmp, &res, siteOf(kSiteRefine, i)));
         std::swap(cur, tmp);
     }
     // M3: protections, fvMeshHexRefiner.C:1514-1533 (polyRefiner: patches only, fvMeshPolyRefiner.C:341-350)
@@ -1308,7 +1340,7 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     } else {
         for (int i = 0; i < nBufferLayers; i++) {
             u8 *res;
-            TRY(extendLayer(ctx, cur, cur, tmp, &res));
+            TRY(extendLayer(ctx, cur, cur, tmp, &res, siteOf(kSiteUnrefine, i)));
             std::swap(cur, tmp);
         }
     }
@@ -1489,6 +1521,31 @@ static int mapFieldsHostPipelined(amr_ctx *ctx, int64_t nOld, int64_t nNew, cons
 // fvMesh::mapFields maps EVERY registered field through one mapPolyMesh (MapGeometricFields over the object
 // registry): the batched entry point shares the cellMap and, for host buffers, keeps uploading field k+1 while
 // field k comes down.
+// fvMesh::mapFields direct injection of one field on the device
+static int launchMapField(amr_ctx *ctx, int64_t nNew, int nComp, const int32_t *dMap, const double *dOld, double *dNew) {
+    const int64_t items = nNew * nComp;
+    if (items <= 0) return AMR_OK;
+    const bool al16 = ((((uintptr_t)dOld) | ((uintptr_t)dNew)) & 15) == 0;
+    const unsigned gE = gridFor(items, kThreads * kMapItems), gP = gridFor((items + 1) / 2, kThreads * kMapItems);
+    switch (nComp) {
+    case 1: LAUNCH((k_map_field<1>), gE, kThreads, nNew, dMap, dOld, dNew); break;
+    case 3:
+        if (al16) LAUNCH((k_map_field_pair<3>), gP, kThreads, nNew, dMap, dOld, dNew);
+        else LAUNCH((k_map_field<3>), gE, kThreads, nNew, dMap, dOld, dNew);
+        break;
+    case 6:
+        if (al16) LAUNCH((k_map_field_pair<6>), gP, kThreads, nNew, dMap, dOld, dNew);
+        else LAUNCH((k_map_field<6>), gE, kThreads, nNew, dMap, dOld, dNew);
+        break;
+    case 9:
+        if (al16) LAUNCH((k_map_field_pair<9>), gP, kThreads, nNew, dMap, dOld, dNew);
+        else LAUNCH((k_map_field<9>), gE, kThreads, nNew, dMap, dOld, dNew);
+        break;
+    default: LAUNCH(k_map_field_n, gE, kThreads, nNew, nComp, dMap, dOld, dNew); break;
+    }
+    return AMR_OK;
+}
+
 AMR_API int amr_map_fields(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nFields, const int *nComp,
                            const double *const *oldF, double *const *newF) {
     ENTER();
@@ -1506,8 +1563,7 @@ AMR_API int amr_map_fields(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32
         double *dNew = nullptr;
         TRY(stageIn(ctx, oldF[i], nOld * nComp[i], &dOld));
         TRY(stageOut(ctx, newF[i], nNew * nComp[i], &dNew));
-        const int64_t items = nNew * nComp[i];
-        if (items > 0) LAUNCH(k_map_field_range, gridFor(items, kThreads * kMapItems), kThreads, (int64_t)0, nNew, nComp[i], dMap, dOld, dNew);
+        TRY(launchMapField(ctx, nNew, nComp[i], dMap, dOld, dNew));
     }
     CK(cudaGetLastError());
     return flushOuts(ctx);
@@ -1525,16 +1581,7 @@ AMR_API int amr_map_field(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_
     TRY(stageIn(ctx, cellMap, nNew, &dMap));
     TRY(stageIn(ctx, oldF, nOld * nComp, &dOld));
     TRY(stageOut(ctx, newF, nNew * nComp, &dNew));
-    int64_t items = nNew * nComp;
-    if (items > 0) {
-        switch (nComp) {
-        case 1: LAUNCH((k_map_field<1>), gridFor(items, kThreads * kMapItems), kThreads, nNew, dMap, dOld, dNew); break;
-        case 3: LAUNCH((k_map_field<3>), gridFor(items, kThreads * kMapItems), kThreads, nNew, dMap, dOld, dNew); break;
-        case 6: LAUNCH((k_map_field<6>), gridFor(items, kThreads * kMapItems), kThreads, nNew, dMap, dOld, dNew); break;
-        case 9: LAUNCH((k_map_field<9>), gridFor(items, kThreads * kMapItems), kThreads, nNew, dMap, dOld, dNew); break;
-        default: LAUNCH(k_map_field_n, gridFor(items, kThreads * kMapItems), kThreads, nNew, nComp, dMap, dOld, dNew); break;
-        }
-    }
+    TRY(launchMapField(ctx, nNew, nComp, dMap, dOld, dNew));
     if (mode == AMR_MAP_CONSERVATIVE) {
         if (!reverseCellMap || !volOld) FAIL(AMR_ERR_ARG, "amr_map_field: conservative mode needs reverseCellMap and volOld");
         // merge lists are tiny compared with the field (8 cells per unrefined parent): build the CSR on the host

@@ -96,6 +96,9 @@ struct amr_ctx {
     Sell cf;                   // cell -> faces (2*face + role), ascending
     double *grad = nullptr;    // [3n]
     double *xbf = nullptr;     // [b] boundaryField of x
+    int64_t pushMinCells = 1 << 16;
+    long long *hMarked = nullptr;   // pinned: marked cells seen per buffer-layer site by the previous call
+    int pushNum = 1, pushDen = 10;   // buffer layers take the sparse push form when marked/n < pushNum/pushDen (0 = never)
     u8 *bEmpty = nullptr;      // [b] boundary face lies on an empty patch (no surface-field entries)
     double *lsP = nullptr, *lsN = nullptr;   // leastSquaresVectors pVectors [3(f+b)], nVectors [3f]
     bool haveLs = false;

@@ -84,7 +84,8 @@ kp_estimate(SellView S, const double *__restrict__ x, double p0, double p1, Thre
 }
 
 __global__ void __launch_bounds__(kPipeThreads, 7)
-kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, u8 *__restrict__ out) {
+kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, u8 *__restrict__ out, const int *__restrict__ gate) {
+    if (gate && *gate == 1) return;                 // the sparse (push) form runs instead (k_extend_push)
     const int32_t n = (int32_t)S.rows;
     sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool) {
         const int32_t c = valid ? (int32_t)c64 : n - 1;

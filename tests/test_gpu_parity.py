@@ -333,3 +333,22 @@ def test_no_cpu_fallback_message():
     from blastamr_b200 import capi
     with pytest.raises(capi.AmrError):
         capi.Context(9999)
+
+
+@pytest.mark.parametrize("fraction", ["1/1", "1/4", "0"])
+def test_buffer_layers_sparse_push_form(O, monkeypatch, fraction):
+    """the buffer layers (fvMeshRefiner.C:794-921) have a dense (pull) and a sparse (push) device form chosen by the
+    marked fraction; force each on the small test meshes and run the whole loop, protected patches included"""
+    from blastamr_b200 import capi
+    monkeypatch.setenv("AMR_B200_PUSH_FRACTION", fraction)
+    monkeypatch.setenv("AMR_B200_PUSH_MIN_CELLS", "0")
+    c = capi.Context(0)
+    try:
+        oc = M.Octree(10, 10, 10, (1.0, 1.0, 1.0), 2)
+        st = amr_loop(c, O, oc, moving_front(0.08), steps=5, maxlev=2, layers_ref=2, layers_unref=3, protected=("movingWall",))
+        assert st["refined"] > 0
+        oc = M.Octree(20, 20, 1, (1.0, 1.0, 0.05), 2, CAVITY2D, {"frontAndBack": M.PATCH_EMPTY}, two_d=True)
+        st = amr_loop(c, O, oc, moving_front_2d(0.06), steps=5, maxlev=2, layers_ref=3, layers_unref=6, kind="codedDelta")
+        assert st["refined"] > 0 and st["unrefined"] > 0
+    finally:
+        c.close()
