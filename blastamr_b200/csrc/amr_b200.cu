@@ -93,7 +93,7 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->owner); devFree(ctx, &ctx->neighbour); devFree(ctx, &ctx->bCoupled);
     devFree(ctx, &ctx->cplFace); devFree(ctx, &ctx->cplCell); devFree(ctx, &ctx->cellGhost); ctx->nCplCells = 0;
     sellFree(ctx, ctx->cc); sellFree(ctx, ctx->pc);
-    devFree(ctx, &ctx->bndPoint); devFree(ctx, &ctx->pcClass); devFree(ctx, &ctx->candList); ctx->pcClassDirty = true;
+    devFree(ctx, &ctx->bndPoint); devFree(ctx, &ctx->pcClass); devFree(ctx, &ctx->candList); ctx->pcClassDirty = true; ctx->balancedLocal = -1;
     devFree(ctx, &ctx->lvl); devFree(ctx, &ctx->lvl8); devFree(ctx, &ctx->parentIdx); devFree(ctx, &ctx->pointLevel);
     devFree(ctx, &ctx->protCell);
     devFree(ctx, &ctx->error); devFree(ctx, &ctx->refineCell);
@@ -471,7 +471,7 @@ AMR_API int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_
     if (p) CK(cudaMemcpyAsync(ctx->bndPoint, bndPoint, (size_t)p, cudaMemcpyDefault, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->havePoints = true;
-    ctx->pcClassDirty = true;
+    ctx->pcClassDirty = true; ctx->balancedLocal = -1;
     return AMR_OK;
 }
 
@@ -613,7 +613,7 @@ AMR_API int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->haveLevels = true;
-    ctx->pcClassDirty = true;
+    ctx->pcClassDirty = true; ctx->balancedLocal = -1;
     return AMR_OK;
 }
 
@@ -824,7 +824,7 @@ static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res, 
     *res = tmp;
     return AMR_OK;
 }
-constexpr int kSiteProtect = 0, kSiteRefine = 4, kSiteUnrefine = 8;   // 4 slots each in ctx->hMarked[16]
+constexpr int kSiteProtect = 0, kSiteRefine = 4, kSiteUnrefine = 8, kSiteSweep = 12;   // 4 slots each in ctx->hMarked[16]
 static inline int siteOf(int base, int layer) { return base + (layer < 3 ? layer : 3); }
 
 AMR_API int amr_protect_patches(amr_ctx *ctx, const int32_t *patchIds, int nPatchIds, int nLayers, double *errorInOut,
@@ -923,6 +923,16 @@ static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOu
     const int64_t n = ctx->n;
     int sweeps = 0;
     ListJob job;
+    // the sparse form of the maxSet sweep is only valid on a locally 2:1-balanced mesh: verified once per mesh
+    bool pushOk = maxSet && !edgeRule && ctx->pushNum > 0 && n >= ctx->pushMinCells && n > 0 && ctx->lvl;
+    if (pushOk && ctx->balancedLocal < 0) {
+        CK(cudaMemsetAsync(ctx->dCount + 3, 0, 8, ctx->stream));
+        LAUNCH(k_check_levels, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const label *)ctx->lvl, (unsigned long long *)(ctx->dCount + 3));
+        CK(cudaMemcpyAsync(ctx->hCount + 3, ctx->dCount + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->balancedLocal = ctx->hCount[3] == 0 ? 1 : 0;
+    }
+    pushOk = pushOk && ctx->balancedLocal == 1;
     while (true) {
         CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(int), ctx->stream));
         // refinement::consistentRefinement (refinement.C:776-780): the edge rule first, then the face rule
@@ -934,10 +944,28 @@ static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOu
             TRY(haloSwapCells(ctx, lf, 1, ctx->ghost8));
         }
         if (n) {
+            const int *gate = nullptr;
+            if (pushOk) {
+                const int site = siteOf(kSiteSweep, sweeps);
+                const bool al = ((((uintptr_t)set) | ((uintptr_t)lf)) & 15) == 0;
+                unsigned long long *total = (unsigned long long *)(ctx->dCount + 1);
+                const long long seen = ctx->hMarked[site];
+                const bool tryPush = seen < 0 || seen * ctx->pushDen < 2 * n * ctx->pushNum;
+                CK(cudaMemsetAsync(total, 0, 8, ctx->stream));
+                LAUNCH(k_count_set16, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)set, al, total);
+                CK(cudaMemcpyAsync(ctx->hMarked + site, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                if (tryPush) {
+                    int *g = ctx->dFlags + 13;
+                    LAUNCH(k_push_gate, 1, 1, (const unsigned long long *)total, (long long)n, (long long)ctx->pushNum, (long long)ctx->pushDen, g);
+                    LAUNCH(k_refine_push, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, lf, set, al,
+                           ctx->dFlags, (const int *)g);
+                    gate = g;
+                }
+            }
             if (pipeOk(ctx, ctx->cc)) {
-                if (maxSet) TRY(launchPipe(ctx, kp_refine_sweep<true>, ctx->cc, lf, set, ctx->dFlags));
-                else TRY(launchPipe(ctx, kp_refine_sweep<false>, ctx->cc, lf, set, ctx->dFlags));
-            } else if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->dFlags);
+                if (maxSet) TRY(launchPipe(ctx, kp_refine_sweep<true>, ctx->cc, lf, set, ctx->dFlags, gate));
+                else TRY(launchPipe(ctx, kp_refine_sweep<false>, ctx->cc, lf, set, ctx->dFlags, gate));
+            } else if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->dFlags, gate);
             else LAUNCH(k_refine_sweep_min, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->dFlags);
             if (ctx->nCoupled > 0) {      // hexRef.C:758-780
                 if (maxSet) LAUNCH((k_fix_refine_sweep<true>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,

@@ -340,7 +340,8 @@ k_count_flags(int64_t n, const u8 *__restrict__ flag, unsigned long long *count)
 // (__syncthreads_or + one store per CTA: the reduce(nChanged) of hexRef.C:1424).
 __global__ void __launch_bounds__(kThreads)
 k_refine_sweep_max(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-                   u8 *__restrict__ lf, u8 *__restrict__ set, int *changed) {
+                   u8 *__restrict__ lf, u8 *__restrict__ set, int *changed, const int *__restrict__ gate) {
+    if (gate && *gate == 1) return;                 // the sparse (push) form runs instead (k_refine_push)
     const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const unsigned live = __ballot_sync(0xffffffffu, c < n);
     int flip = 0;
@@ -814,6 +815,28 @@ k_copy_flags_gated(int64_t n, const u8 *__restrict__ in, u8 *__restrict__ out, b
     if (base >= n) return;
     if (aligned && base + 16 <= n) *reinterpret_cast<uint4 *>(out + base) = *reinterpret_cast<const uint4 *>(in + base);
     else for (int k = 0; k < 16 && base + k < n; k++) out[base + k] = in[base + k];
+}
+// Sparse form of the maxSet = true sweep (hexRef.C:723-741).  On a mesh that is 2:1 balanced before the step (the
+// reference checks this after every topology change, hexRef.C:2934-3025) only a cell that is marked can stand more
+// than one level above a neighbour, so walking the rows of the marked cells and pushing the mark to every unmarked
+// neighbour with level + 1 < level(c) + 1 reaches the same closure.  Used only when the local mesh was verified
+// balanced (k_check_levels, once per mesh); otherwise the dense form runs.
+__global__ void __launch_bounds__(kThreads)
+k_refine_push(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *__restrict__ lvl8,
+              u8 *lf, u8 *set, bool aligned, int *changed, const int *__restrict__ gate) {
+    if (*gate != 1) return;
+    forEachSet16(set, n, aligned, [&](int64_t c) {
+        const int32_t base = sliceOff[c >> 5];
+        const int w = sliceOff[(c >> 5) + 1] - base;
+        const int32_t *row = col + ((size_t)base << 5) + (c & 31);
+        const int mine = (int)lvl8[c] + 1;
+        for (int j = 0; j < w; j++) {
+            const int32_t q = row[(size_t)j << 5];
+            if (q == (int32_t)c) continue;
+            const int lq = lvl8[q];
+            if (mine > lq + 1 && !set[q]) { set[q] = 1; lf[q] = (u8)(lq + 1); *changed = 1; }
+        }
+    });
 }
 __global__ void __launch_bounds__(kThreads)
 k_extend_push(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *__restrict__ src,

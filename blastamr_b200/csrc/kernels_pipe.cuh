@@ -107,7 +107,8 @@ kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, u8 
 
 template <bool MAXSET>
 __global__ void __launch_bounds__(kPipeThreads, 7)
-kp_refine_sweep(SellView S, u8 *lf, u8 *set, int *changed) {
+kp_refine_sweep(SellView S, u8 *lf, u8 *set, int *changed, const int *__restrict__ gate) {
+    if (gate && *gate == 1) return;                 // the sparse (push) form runs instead (k_refine_push)
     const int32_t n = (int32_t)S.rows;
     sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool) {
         const int32_t c = valid ? (int32_t)c64 : n - 1;
