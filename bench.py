@@ -464,9 +464,9 @@ def main():
         value = n_total / (ms_per_step / 1e3) / 1e6
         # Dominant kernel = the single-kernel call with the largest time.  estimate and map_field are
         # exactly one launch per call (resident path), so the CUDA-event interval is the launch time.
-        single = {"E:estimate(delta+normalize)": ("kp_estimate<0,true,false> (delta + fused normalize, TMA-staged SELL)", ab["E"], "8f + 16n"),
+        single = {"E:estimate(delta+normalize)": ("kp_estimate<0, 1>", ab["E"], "8f + 16n  (delta + fused normalize, TMA-staged SELL)"),
                   "F:map_field(scalar)": ("k_map_field<1>", 4 * n_new + 8 * n + 8 * n_new, "4n' + 8n + 8n'"),
-                  "F:map_field(vector)": ("k_map_field<3>", 4 * n_new + 3 * (8 * n + 8 * n_new), "4n' + 3(8n + 8n')")}
+                  "F:map_field(vector)": ("k_map_field_pair<3>", 4 * n_new + 3 * (8 * n + 8 * n_new), "4n' + 3(8n + 8n')")}
         dom = max(single, key=lambda k: calls[k])
         kname, kbytes, kform = single[dom]
         k_ms = calls[dom]
@@ -476,8 +476,7 @@ def main():
         if tpath.exists() and N == 400 and world == 1:
             try:
                 tj = json.loads(tpath.read_text())["traffic_bytes_per_launch"]
-                key = {"k_map_field<3>": "k_map_field<3>", "k_map_field<1>": "k_map_field<1>"}.get(kname, "kp_estimate<0, 1, 0>")
-                traffic = tj.get(key)
+                traffic = tj.get(kname)
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "kernel": kname, "achieved": (kbytes / 1e9) / (k_ms / 1e3), "peak": peak, "unit": "GB/s",

@@ -72,6 +72,10 @@ _SIGS = {
     "amr_estimate_cell_size": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_multicomponent": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5),
+    "amr_imbalance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_history_clusters": (C.c_int, [C.c_void_p] * 6),
+    "amr_history_constrain_decomposition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_proc_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "amr_launch_count": (C.c_int64, [C.c_void_p]),
     "amr_device_bytes": (C.c_int64, [C.c_void_p]),
 }
@@ -399,6 +403,29 @@ class Context:
         self._ck(self.L.amr_estimate_cell_size(self._h, size_type, _ptr(gd), lower_unrefine, lower_refine, _ptr(cm), len(cm),
                                                _ptr(lo), _ptr(hi), _ptr(dx), _ptr(dX), _ptr(error)))
         return error
+
+    def imbalance(self):
+        r, g = C.c_double(0), C.c_int64(0)
+        self._ck(self.L.amr_imbalance(self._h, C.byref(r), C.byref(g)))
+        return r.value, g.value
+
+    def history_clusters(self, clusters_in=None, want_blocked=True):
+        """markCommonCells + add: returns (cellToCluster, blockedFace, nClusters, nUnblocked)"""
+        c2c = np.empty(self.n, dtype=np.int32)
+        bl = np.empty(self.f + self.b, dtype=np.uint8) if want_blocked else None
+        nc, nu = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.amr_history_clusters(self._h, _ptr(clusters_in), _ptr(c2c), _ptr(bl), C.byref(nc), C.byref(nu)))
+        return c2c, bl, nc.value, nu.value
+
+    def constrain_decomposition(self, decomposition):
+        nch = C.c_int64(0)
+        self._ck(self.L.amr_history_constrain_decomposition(self._h, _ptr(decomposition), C.byref(nch)))
+        return nch.value
+
+    def proc_load(self, distribution, n_procs):
+        out = np.zeros(n_procs, dtype=np.int64)
+        self._ck(self.L.amr_proc_load(self._h, _ptr(distribution), n_procs, _ptr(out)))
+        return out
 
     def multicomponent(self, errors, max_cell_levels=None):
         """multicomponent::update + maxRefinement: returns (error, maxRefinement or None, waves)"""

@@ -103,6 +103,7 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->gWeights); devFree(ctx, &ctx->gSf); devFree(ctx, &ctx->gMagSf); devFree(ctx, &ctx->gDelta); devFree(ctx, &ctx->gV);
     devFree(ctx, &ctx->grad); devFree(ctx, &ctx->xbf);
     devFree(ctx, &ctx->bEmpty); devFree(ctx, &ctx->lsP); devFree(ctx, &ctx->lsN); ctx->haveLs = false;
+    devFree(ctx, &ctx->visible); devFree(ctx, &ctx->splitParent); ctx->nSplit = 0;
     sellFree(ctx, ctx->cf);
     ctx->haveGeom = false;
     sellFree(ctx, ctx->ec); devFree(ctx, &ctx->bndEdge); devFree(ctx, &ctx->edgePts);
@@ -609,6 +610,12 @@ AMR_API int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t
         TRY(stageIn(ctx, splitParent, nSplit, &dPar));
         if (nSplit > 0 && !dPar) FAIL(AMR_ERR_ARG, "amr_levels_set: splitParent is null");
         if (n) LAUNCH(k_parent_index, gridFor(n), kThreads, n, dVis, dPar, nSplit, ctx->parentIdx);
+        // the history itself stays resident for the cluster queries of the load-balance constraint
+        devFree(ctx, &ctx->visible); devFree(ctx, &ctx->splitParent);
+        TRY(devAlloc(ctx, &ctx->visible, n)); TRY(devAlloc(ctx, &ctx->splitParent, nSplit > 0 ? nSplit : 1));
+        if (n) CK(cudaMemcpyAsync(ctx->visible, dVis, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (nSplit) CK(cudaMemcpyAsync(ctx->splitParent, dPar, (size_t)nSplit * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->nSplit = nSplit;
         ctx->haveHistory = true;
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1927,4 +1934,154 @@ AMR_API int amr_multicomponent(amr_ctx *ctx, int nEstimators, const double *cons
     if (wavesOut) *wavesOut = waves;
     CK(cudaGetLastError());
     return flushOuts(ctx);
+}
+
+// ---- inputs of the load-balance decision
+
+AMR_API int amr_imbalance(amr_ctx *ctx, double *maxImbalanceRatio, int64_t *nGlobalCells) {
+    ENTER();
+    if (!maxImbalanceRatio) FAIL(AMR_ERR_ARG, "amr_imbalance: output is null");
+    const int nProcs = (ctx->comm && ctx->nranks > 1) ? ctx->nranks : 1;
+    int64_t nGlobal = ctx->n;
+    if (nProcs > 1) {
+        CK(cudaMemcpyAsync(ctx->dCount + 1, &nGlobal, 8, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(globalSum(ctx, 1, &nGlobal));                     // returnReduce(mesh_.nCells(), sumOp<label>())
+    }
+    const double ideal = (double)nGlobal / (double)nProcs;    // fvMeshBalance.C:463-464
+    double localImbalance = fabs((double)ctx->n - ideal);     // :465
+    if (nProcs > 1) {
+        void *q;
+        TRY(arenaAlloc(ctx, &q, 8));
+        CK(cudaMemcpyAsync(q, &localImbalance, 8, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(allReduceWord(ctx, q, 3));                        // returnReduce(localImbalance, maxOp<scalar>())
+        CK(cudaMemcpyAsync(&localImbalance, q, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *maxImbalanceRatio = localImbalance / ideal;              // :467
+    if (nGlobalCells) *nGlobalCells = nGlobal;
+    return AMR_OK;
+}
+
+// cellToCluster on the device (arena): hexRefRefinementHistory::markCommonCells
+static int historyClusters(amr_ctx *ctx, label **cellToClusterDev, int32_t **nClustersDev) {
+    const int64_t n = ctx->n, ns = ctx->nSplit;
+    void *q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(n > 0 ? n : 1) * 4)); label *root = (label *)q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(ns > 0 ? ns : 1) * 4)); int *firstCell = (int *)q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(n > 0 ? n : 1) * 4)); label *c2c = (label *)q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(n > 0 ? n : 1) * 4)); int32_t *firstList = (int32_t *)q;
+    if (ns) LAUNCH(k_fill_int, gridFor(ns), kThreads, ns, 0x7fffffff, firstCell);
+    u8 *isFirst = ctx->flagA;
+    int32_t *total = nullptr;
+    if (n) {
+        LAUNCH(k_history_root, gridFor(n), kThreads, n, (const label *)ctx->visible, (const label *)ctx->splitParent, root, firstCell);
+        LAUNCH(k_cluster_first_flag, gridFor(n), kThreads, n, (const label *)root, (const int *)firstCell, isFirst);
+    }
+    TRY(compactFlags(ctx, isFirst, n, firstList, &total));
+    if (n) {
+        LAUNCH(k_cluster_of_root, gridFor(n), kThreads, (const int32_t *)total, (const int32_t *)firstList, (const label *)root, firstCell);
+        LAUNCH(k_cluster_cells, gridFor(n), kThreads, n, (const label *)root, (const int *)firstCell, c2c);
+    }
+    *cellToClusterDev = c2c;
+    *nClustersDev = total;
+    return AMR_OK;
+}
+
+AMR_API int amr_history_clusters(amr_ctx *ctx, const int32_t *cellToClusterIn, int32_t *cellToClusterOut, uint8_t *blockedFace,
+                                 int64_t *nClusters, int64_t *nUnblocked) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_history_clusters: mesh not set");
+    const int64_t n = ctx->n, f = ctx->f, nf = ctx->f + ctx->b;
+    label *c2c = nullptr;
+    int32_t *total = nullptr;
+    if (cellToClusterIn) {                                    // polyRefiner: refinement::getCellClusters ids from the host (any numbering)
+        const int32_t *d = nullptr;
+        TRY(stageIn(ctx, cellToClusterIn, n, &d));
+        c2c = (label *)d;
+    } else {
+        if (!ctx->haveHistory) FAIL(AMR_ERR_STATE, "amr_history_clusters: refinement history not set (amr_levels_set)");
+        TRY(historyClusters(ctx, &c2c, &total));
+    }
+    if (cellToClusterOut && n) {
+        CK(cudaMemcpyAsync(cellToClusterOut, c2c, (size_t)n * 4, cudaMemcpyDefault, ctx->stream));
+        if (!isDevicePtr(cellToClusterOut)) ctx->hostTouched = true;
+    }
+    CK(cudaMemsetAsync(ctx->dCount + 3, 0, 8, ctx->stream));
+    if (blockedFace) {
+        u8 *dB = nullptr;
+        TRY(stageOut(ctx, blockedFace, nf, &dB));
+        if (nf) LAUNCH(k_blocked_faces, gridFor(nf), kThreads, nf, f, (const label *)ctx->owner, (const label *)ctx->neighbour, (const label *)c2c, dB,
+                       (unsigned long long *)(ctx->dCount + 3));
+    }
+    if (nClusters || nUnblocked) {
+        ctx->hFlags[10] = 0;
+        if (total) CK(cudaMemcpyAsync(ctx->hFlags + 10, total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->hCount + 3, ctx->dCount + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (nClusters) *nClusters = total ? ctx->hFlags[10] : -1;
+        if (nUnblocked) *nUnblocked = ctx->hCount[3];
+    }
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_history_constrain_decomposition(amr_ctx *ctx, int32_t *decomposition, int64_t *nChanged) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_history_constrain_decomposition: mesh not set");
+    if (!ctx->haveHistory) FAIL(AMR_ERR_STATE, "amr_history_constrain_decomposition: refinement history not set (amr_levels_set)");
+    if (!decomposition) FAIL(AMR_ERR_ARG, "amr_history_constrain_decomposition: decomposition is null");
+    const int64_t n = ctx->n, f = ctx->f;
+    label *c2c = nullptr;
+    int32_t *total = nullptr;
+    TRY(historyClusters(ctx, &c2c, &total));
+    int32_t *dDec = nullptr;
+    TRY(stageInOut(ctx, decomposition, n, &dDec));
+    void *q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(n > 0 ? n : 1) * 4)); label *decIn = (label *)q;       // the values before the loop
+    TRY(arenaAlloc(ctx, &q, (size_t)(n > 0 ? n : 1) * 4)); int *firstFace = (int *)q;       // clusters <= cells
+    TRY(arenaAlloc(ctx, &q, (size_t)(n > 0 ? n : 1) * 4)); int *clusterToProc = (int *)q;
+    u8 *changed = ctx->flagB;
+    if (n) {
+        CK(cudaMemcpyAsync(decIn, dDec, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemsetAsync(changed, 0, (size_t)n, ctx->stream));
+        LAUNCH(k_fill_int, gridFor(n), kThreads, n, 0x7fffffff, firstFace);
+    }
+    if (f) LAUNCH(k_cluster_first_face, gridFor(f), kThreads, f, (const label *)ctx->owner, (const label *)ctx->neighbour, (const label *)c2c, firstFace);
+    if (n) LAUNCH(k_cluster_proc, gridFor(n), kThreads, n, (const int *)firstFace, (const label *)ctx->owner, (const label *)decIn, clusterToProc);
+    if (f) LAUNCH(k_cluster_apply, gridFor(f), kThreads, f, (const label *)ctx->owner, (const label *)ctx->neighbour, (const label *)c2c,
+                  (const int *)clusterToProc, (const label *)decIn, dDec, changed);
+    if (nChanged) {
+        CK(cudaMemsetAsync(ctx->dCount + 3, 0, 8, ctx->stream));
+        if (n) LAUNCH(k_count_flags, gridFor(n), kThreads, n, (const u8 *)changed, (unsigned long long *)(ctx->dCount + 3));
+        CK(cudaMemcpyAsync(ctx->hCount + 3, ctx->dCount + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *nChanged = ctx->hCount[3];
+    }
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_proc_load(amr_ctx *ctx, const int32_t *distribution, int nProcs, int64_t *procLoad) {
+    ENTER();
+    if (!distribution || !procLoad || nProcs < 1 || nProcs > 8192) FAIL(AMR_ERR_ARG, "amr_proc_load: bad arguments");
+    const int64_t n = ctx->n;
+    const int32_t *dD = nullptr;
+    TRY(stageIn(ctx, distribution, n, &dD));
+    void *q;
+    TRY(arenaAlloc(ctx, &q, (size_t)nProcs * 8));
+    unsigned long long *load = (unsigned long long *)q;
+    CK(cudaMemsetAsync(load, 0, (size_t)nProcs * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dFlags + 10, 0, sizeof(int), ctx->stream));
+    if (n) {
+        const unsigned g = (unsigned)std::min<int64_t>((int64_t)ctx->numSMs * 8, (n + kThreads - 1) / kThreads);
+        k_proc_load<<<g, kThreads, (size_t)nProcs * 4, ctx->stream>>>(n, dD, nProcs, load, ctx->dFlags + 10);
+        ctx->launches++;
+    }
+    if (ctx->comm && ctx->nranks > 1)
+        for (int k = 0; k < nProcs; k++) TRY(allReduceWord(ctx, load + k, 1));     // reduce(procLoadNew, sumOp<labelList>())
+    CK(cudaMemcpyAsync(procLoad, load, (size_t)nProcs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->hFlags + 10, ctx->dFlags + 10, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->hFlags[10]) FAIL(AMR_ERR_ARG, "amr_proc_load: distribution holds a processor outside [0, nProcs)");
+    return AMR_OK;
 }

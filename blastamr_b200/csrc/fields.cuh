@@ -300,3 +300,103 @@ k_mc_apply(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__res
     }
     if (last >= 0) maxRefinement[c] = level[last];
 }
+
+// ---------------------------------------------------------------------------------------------- N4
+// hexRefRefinementHistory::markCommonCells (hexRefRefinementHistory.C:398-444), order-free form: root[c] = top-most
+// ancestor of the cell's history entry; a cluster is numbered by the rank of its LOWEST cell among the lowest cells of
+// all clusters, which is the order of first appearance over ascending cells the reference produces.
+__global__ void __launch_bounds__(kThreads)
+k_history_root(int64_t n, const label *__restrict__ visible, const label *__restrict__ splitParent, label *__restrict__ root,
+               int *__restrict__ firstCell) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    label index = visible[c];
+    if (index >= 0) {
+        label p;
+        while ((p = splitParent[index]) != -1) index = p;
+        atomicMin(&firstCell[index], (int)c);
+    }
+    root[c] = index >= 0 ? index : -1;
+}
+__global__ void __launch_bounds__(kThreads)
+k_cluster_first_flag(int64_t n, const label *__restrict__ root, const int *__restrict__ firstCell, u8 *__restrict__ isFirst) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    isFirst[c] = (root[c] >= 0 && firstCell[root[c]] == (int)c) ? 1 : 0;
+}
+// firstList = ascending first cells (compaction of isFirst): cluster id = position in that list
+__global__ void __launch_bounds__(kThreads)
+k_cluster_of_root(const int32_t *__restrict__ total, const int32_t *__restrict__ firstList, const label *__restrict__ root,
+                  int *__restrict__ clusterOfRoot) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= *total) return;
+    clusterOfRoot[root[firstList[i]]] = (int)i;      // reuses the firstCell array: entries of non-roots are never read
+}
+__global__ void __launch_bounds__(kThreads)
+k_cluster_cells(int64_t n, const label *__restrict__ root, const int *__restrict__ clusterOfRoot, label *__restrict__ cellToCluster) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    cellToCluster[c] = root[c] >= 0 ? clusterOfRoot[root[c]] : -1;
+}
+// hexRefRefinementHistory::add (:448-487) / refinement::add (refinement.C:1007-1046)
+__global__ void __launch_bounds__(kThreads)
+k_blocked_faces(int64_t nf, int64_t f, const label *__restrict__ owner, const label *__restrict__ neighbour,
+                const label *__restrict__ cellToCluster, u8 *__restrict__ blocked, unsigned long long *nUnblocked) {
+    const int64_t face = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (face >= nf) return;
+    u8 bl = 1;
+    if (face < f) {
+        const label a = cellToCluster[owner[face]], b2 = cellToCluster[neighbour[face]];
+        if (a != -1 && a == b2) { bl = 0; atomicAdd(nUnblocked, 1ull); }
+    }
+    blocked[face] = bl;
+}
+// hexRefRefinementHistory::apply (:490-545): the cluster's processor is the one given to the owner of its lowest
+// in-cluster face; every cell on an in-cluster face follows
+__global__ void __launch_bounds__(kThreads)
+k_cluster_first_face(int64_t f, const label *__restrict__ owner, const label *__restrict__ neighbour,
+                     const label *__restrict__ cellToCluster, int *__restrict__ firstFace) {
+    const int64_t face = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (face >= f) return;
+    const label a = cellToCluster[owner[face]];
+    if (a != -1 && a == cellToCluster[neighbour[face]]) atomicMin(&firstFace[a], (int)face);
+}
+__global__ void __launch_bounds__(kThreads)
+k_cluster_proc(int64_t nClusters, const int *__restrict__ firstFace, const label *__restrict__ owner,
+               const label *__restrict__ decompIn, int *__restrict__ clusterToProc) {
+    const int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (k >= nClusters) return;
+    const int ff = firstFace[k];
+    clusterToProc[k] = (ff == 0x7fffffff) ? -1 : decompIn[owner[ff]];
+}
+__global__ void __launch_bounds__(kThreads)
+k_cluster_apply(int64_t f, const label *__restrict__ owner, const label *__restrict__ neighbour,
+                const label *__restrict__ cellToCluster, const int *__restrict__ clusterToProc, const label *__restrict__ decompIn,
+                label *__restrict__ decompOut, u8 *__restrict__ changed) {
+    const int64_t face = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (face >= f) return;
+    const label own = owner[face], nei = neighbour[face];
+    const label a = cellToCluster[own];
+    if (a == -1 || a != cellToCluster[nei]) return;
+    const int proc = clusterToProc[a];
+    if (decompIn[own] != proc) { decompOut[own] = proc; changed[own] = 1; }
+    if (decompIn[nei] != proc) { decompOut[nei] = proc; changed[nei] = 1; }
+}
+// procLoadNew (fvMeshBalance.C:497-503): per-CTA shared histogram, then global atomics
+__global__ void __launch_bounds__(kThreads)
+k_proc_load(int64_t n, const label *__restrict__ distribution, int nProcs, unsigned long long *__restrict__ load, int *__restrict__ bad) {
+    extern __shared__ unsigned int hist[];
+    for (int q = threadIdx.x; q < nProcs; q += kThreads) hist[q] = 0;
+    __syncthreads();
+    for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < n; c += (int64_t)gridDim.x * kThreads) {
+        const label q = distribution[c];
+        if (q < 0 || q >= nProcs) *bad = 1;
+        else atomicAdd(&hist[q], 1u);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < nProcs; q += kThreads) if (hist[q]) atomicAdd(&load[q], (unsigned long long)hist[q]);
+}
+__global__ void k_fill_int(int64_t n, int v, int *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}

@@ -776,6 +776,51 @@ __device__ __forceinline__ void forEachSet16(const u8 *flags, int64_t N, bool al
     }
 }
 
+// Warp-balanced form: the 512 flags of a warp are scanned as above, the indices of the set ones are gathered into a
+// per-warp shared buffer and then dealt round-robin to the lanes.  Runs of consecutive set entries (the usual shape
+// of an AMR marking) would otherwise be walked serially by ONE thread with its 31 neighbours idle; dealt out, their
+// rows are also read coalesced.  Needs blockDim.x == kThreads.
+template <class Fn>
+__device__ __forceinline__ void forEachSetWarp(const u8 *flags, int64_t N, bool aligned, Fn fn) {
+    __shared__ unsigned short setIdx[kThreads / 32][512];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warpBase = ((int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31)) * 16;
+    if (warpBase >= N) return;                                     // whole warp out of range
+    const int64_t base = warpBase + (int64_t)lane * 16;
+    unsigned mask = 0;
+    if (base < N) {
+        if (aligned && base + 16 <= N) {
+            const uint4 w = *reinterpret_cast<const uint4 *>(flags + base);
+            const unsigned v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned nz = __vcmpne4(v[k], 0u);           // 0xff per non-zero byte
+                mask |= (((nz >> 0) & 1u) | ((nz >> 7) & 2u) | ((nz >> 14) & 4u) | ((nz >> 21) & 8u)) << (4 * k);
+            }
+        } else {
+            for (int k = 0; k < 16 && base + k < N; k++) mask |= (flags[base + k] ? 1u : 0u) << k;
+        }
+    }
+    const int cnt = __popc(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    int o = incl - cnt;
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        setIdx[warp][o++] = (unsigned short)(lane * 16 + k);
+    }
+    __syncwarp();
+    for (int i = lane; i < total; i += 32) fn(warpBase + setIdx[warp][i]);
+    __syncwarp();
+}
+
 // ---- sparse form of one buffer layer (fvMeshRefiner.C:866-921): when few cells are marked, walking only the rows
 // of the marked SOURCE cells and pushing the mark to their neighbours reads a fraction of the adjacency.
 // Count -> gate (device-side decision, no host round trip) -> copy in->out -> push; the dense (pull) kernel
@@ -825,16 +870,25 @@ __global__ void __launch_bounds__(kThreads)
 k_refine_push(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *__restrict__ lvl8,
               u8 *lf, u8 *set, bool aligned, int *changed, const int *__restrict__ gate) {
     if (*gate != 1) return;
-    forEachSet16(set, n, aligned, [&](int64_t c) {
+    forEachSetWarp(set, n, aligned, [&](int64_t c) {
         const int32_t base = sliceOff[c >> 5];
         const int w = sliceOff[(c >> 5) + 1] - base;
         const int32_t *row = col + ((size_t)base << 5) + (c & 31);
         const int mine = (int)lvl8[c] + 1;
-        for (int j = 0; j < w; j++) {
-            const int32_t q = row[(size_t)j << 5];
-            if (q == (int32_t)c) continue;
-            const int lq = lvl8[q];
-            if (mine > lq + 1 && !set[q]) { set[q] = 1; lf[q] = (u8)(lq + 1); *changed = 1; }
+        // batches of 8 neighbours: labels, then levels, then marks -- three rounds of independent loads per batch
+        for (int j0 = 0; j0 < w; j0 += 8) {
+            int32_t q[8];
+            int lq[8];
+            u8 sq[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+#pragma unroll
+            for (int k = 0; k < 8; k++) lq[k] = lvl8[q[k]];
+#pragma unroll
+            for (int k = 0; k < 8; k++) sq[k] = set[q[k]];
+#pragma unroll
+            for (int k = 0; k < 8; k++)      // padding (q == c) fails the level test
+                if (mine > lq[k] + 1 && !sq[k]) { set[q[k]] = 1; lf[q[k]] = (u8)(lq[k] + 1); *changed = 1; }
         }
     });
 }
@@ -842,13 +896,16 @@ __global__ void __launch_bounds__(kThreads)
 k_extend_push(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *__restrict__ src,
               bool aligned, u8 *__restrict__ out, const int *__restrict__ gate) {
     if (*gate != 1) return;
-    forEachSet16(src, n, aligned, [&](int64_t c) {
+    forEachSetWarp(src, n, aligned, [&](int64_t c) {
         const int32_t base = sliceOff[c >> 5];
         const int w = sliceOff[(c >> 5) + 1] - base;
         const int32_t *row = col + ((size_t)base << 5) + (c & 31);
-        for (int j = 0; j < w; j++) {
-            const int32_t q = row[(size_t)j << 5];
-            if (q != (int32_t)c) out[q] = 1;
+        for (int j0 = 0; j0 < w; j0 += 8) {
+            int32_t q[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+#pragma unroll
+            for (int k = 0; k < 8; k++) out[q[k]] = 1;      // padding writes c itself, which is marked already
         }
     });
 }

@@ -341,6 +341,25 @@ int amr_estimate_cell_size(amr_ctx *ctx, int sizeType, const int32_t *geometricD
 int amr_multicomponent(amr_ctx *ctx, int nEstimators, const double *const *errors, const int32_t *const *maxCellLevels,
                        double *errorOut, int32_t *maxRefinementOut, int *wavesOut);
 
+/* ---- inputs of the load-balance decision; the decomposer and the redistribution stay host ---- */
+
+/* fvMeshBalance::canBalance imbalance metric (fvMeshBalance.C:462-468): max over ranks of |nCells - ideal| / ideal with
+   ideal = nGlobalCells / nProcs.  Collective when a communicator is attached. */
+int amr_imbalance(amr_ctx *ctx, double *maxImbalanceRatio, int64_t *nGlobalCells);
+/* hexRefRefinementHistory::markCommonCells (hexRefRefinementHistory.C:398-444): cellToCluster [n] (cluster of the cell's
+   top-most ancestor, numbered in order of first appearance over ascending cells, -1 without history) and
+   ::add (:448-487): blockedFace [f+b] (1 = blocked; only internal faces between two cells of one cluster are
+   unblocked).  cellToClusterIn != NULL: use the host's clusters instead (polyRefiner, refinement::getCellClusters
+   refinement.C:607-647, whose numbering is a hash-table order; refinement::add :1007-1046 needs only equality).
+   All outputs nullable; nClusters = -1 when the clusters were given. */
+int amr_history_clusters(amr_ctx *ctx, const int32_t *cellToClusterIn, int32_t *cellToClusterOut, uint8_t *blockedFace,
+                         int64_t *nClusters, int64_t *nUnblocked);
+/* hexRefRefinementHistory::apply (:490-545): decomposition [n] in/out -- every cluster goes to the processor given to
+   the owner of its lowest in-cluster face.  nChanged (nullable) as counted by the reference. */
+int amr_history_constrain_decomposition(amr_ctx *ctx, int32_t *decomposition, int64_t *nChanged);
+/* procLoadNew of fvMeshBalance::canBalance (fvMeshBalance.C:497-503): cells per target processor, summed over ranks */
+int amr_proc_load(amr_ctx *ctx, const int32_t *distribution, int nProcs, int64_t *procLoad);
+
 /* number of kernels launched by this context since creation */
 int64_t amr_launch_count(const amr_ctx *ctx);
 /* bytes currently held in device memory by this context */

@@ -1633,3 +1633,78 @@ OR_API void or_multicomponent_max_refinement(const or_world *w, int r, int nEst,
         }
     }
 }
+
+/* ---- N4: inputs of the load-balance decision ------------------------------------------------------------ */
+
+/* hexRefRefinementHistory::markCommonCells (hexRefRefinementHistory.C:398-444): every cell whose history entry
+   exists gets the cluster of its top-most ancestor; clusters are numbered in order of first appearance over
+   ascending cells.  (mark() paints the whole tree below the root; only the entries of visible cells are read back,
+   and each of those reaches the root through parent_.)  Returns the number of clusters. */
+OR_API label or_history_clusters(const or_world *w, int r, int64_t nSplit, label *cellToCluster) {
+    const or_mesh *m = &w->m[r];
+    label clusterI = 0;
+    label *rootToCluster = (label *)malloc(sizeof(label) * (size_t)(nSplit + 1));
+    for (int64_t i = 0; i < nSplit; i++) rootToCluster[i] = -1;
+    for (int64_t cellI = 0; cellI < m->n; cellI++) {
+        label index = m->visible[cellI];
+        cellToCluster[cellI] = -1;
+        if (index >= 0) {
+            while (m->splitParent[index] != -1) index = m->splitParent[index];
+            if (rootToCluster[index] == -1) rootToCluster[index] = clusterI++;
+            cellToCluster[cellI] = rootToCluster[index];
+        }
+    }
+    free(rootToCluster);
+    return clusterI;
+}
+
+/* hexRefRefinementHistory::add (:448-487) / refinement::add (refinement.C:1007-1046): faces between two cells of one
+   cluster are unblocked, everything else (boundary faces included) stays blocked; the syncFaceList(andEqOp) that
+   follows cannot change a boundary face (both sides hold true). */
+OR_API int64_t or_blocked_faces(const or_world *w, int r, const label *cellToCluster, boolean *blockedFace) {
+    const or_mesh *m = &w->m[r];
+    int64_t nUnblocked = 0;
+    for (int64_t faceI = 0; faceI < m->f + m->b; faceI++) blockedFace[faceI] = 1;
+    for (int64_t faceI = 0; faceI < m->f; faceI++) {
+        label ownCluster = cellToCluster[m->owner[faceI]], neiCluster = cellToCluster[m->neighbour[faceI]];
+        if (ownCluster != -1 && ownCluster == neiCluster) { blockedFace[faceI] = 0; nUnblocked++; }
+    }
+    return nUnblocked;
+}
+
+/* hexRefRefinementHistory::apply (:490-545): every cluster goes to the processor its first in-cluster face's owner
+   was given.  Returns nChanged. */
+OR_API int64_t or_constrain_decomposition(const or_world *w, int r, const label *cellToCluster, label nClusters,
+                                          label *decomposition) {
+    const or_mesh *m = &w->m[r];
+    label *clusterToProc = (label *)malloc(sizeof(label) * (size_t)(nClusters + 1));
+    for (label i = 0; i < nClusters; i++) clusterToProc[i] = -1;
+    int64_t nChanged = 0;
+    for (int64_t faceI = 0; faceI < m->f; faceI++) {
+        label own = m->owner[faceI], nei = m->neighbour[faceI];
+        label ownCluster = cellToCluster[own], neiCluster = cellToCluster[nei];
+        if (ownCluster != -1 && ownCluster == neiCluster) {
+            if (clusterToProc[ownCluster] == -1) clusterToProc[ownCluster] = decomposition[own];
+            if (decomposition[own] != clusterToProc[ownCluster]) { decomposition[own] = clusterToProc[ownCluster]; nChanged++; }
+            if (decomposition[nei] != clusterToProc[ownCluster]) { decomposition[nei] = clusterToProc[ownCluster]; nChanged++; }
+        }
+    }
+    free(clusterToProc);
+    return nChanged;
+}
+
+/* fvMeshBalance::canBalance (fvMeshBalance.C:462-468): maxImbalance / idealNCells over the world */
+OR_API scalar or_imbalance(const or_world *w, int64_t *nGlobalCells) {
+    int64_t tot = 0;
+    for (int r = 0; r < w->R; r++) tot += w->m[r].n;
+    scalar ideal = (scalar)tot / (scalar)w->R, mx = 0;
+    for (int r = 0; r < w->R; r++) mx = smax(mx, smag((scalar)w->m[r].n - ideal));
+    if (nGlobalCells) *nGlobalCells = tot;
+    return mx / ideal;
+}
+
+/* procLoadNew (fvMeshBalance.C:497-503) of one rank; the caller sums over ranks */
+OR_API void or_proc_load(int64_t n, const label *distribution, int nProcs, int64_t *procLoad) {
+    for (int q = 0; q < nProcs; q++) procLoad[q] = 0;
+    for (int64_t c = 0; c < n; c++) procLoad[distribution[c]]++;
+}

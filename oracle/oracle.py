@@ -100,6 +100,15 @@ def lib():
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.or_multicomponent_error.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.or_multicomponent_max_refinement.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.or_history_clusters.restype = C.c_int32
+        L.or_history_clusters.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p]
+        L.or_blocked_faces.restype = C.c_int64
+        L.or_blocked_faces.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.or_constrain_decomposition.restype = C.c_int64
+        L.or_constrain_decomposition.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int32, C.c_void_p]
+        L.or_imbalance.restype = C.c_double
+        L.or_imbalance.argtypes = [C.c_void_p, C.c_void_p]
+        L.or_proc_load.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
         L.or_set_threads.argtypes = [C.c_int]
         L.or_max_threads.restype = C.c_int
         L.or_set_threads(1)
@@ -371,6 +380,28 @@ class World:
                                  None if dX is None else dX.ctypes.data, error.ctypes.data)
         return error
 
+    def history_clusters(self, r):
+        m = self.meshes[r]
+        c2c = np.empty(m.n, dtype=np.int32)
+        nsp = 0 if m.split_parent is None else len(m.split_parent)
+        ncl = lib().or_history_clusters(self._h, r, nsp, c2c.ctypes.data)
+        return c2c, int(ncl)
+
+    def blocked_faces(self, r, cell_to_cluster):
+        m = self.meshes[r]
+        c2c = _i32(cell_to_cluster)
+        bl = np.empty(m.f + m.b, dtype=np.uint8)
+        nu = lib().or_blocked_faces(self._h, r, c2c.ctypes.data, bl.ctypes.data)
+        return bl, int(nu)
+
+    def constrain_decomposition(self, r, cell_to_cluster, n_clusters, decomposition):
+        c2c = _i32(cell_to_cluster)
+        return int(lib().or_constrain_decomposition(self._h, r, c2c.ctypes.data, n_clusters, decomposition.ctypes.data))
+
+    def imbalance(self):
+        g = C.c_int64(0)
+        return float(lib().or_imbalance(self._h, C.byref(g))), g.value
+
     def multicomponent(self, r, errors, max_cell_levels=None):
         n = self.meshes[r].n
         err = np.empty(n, dtype=np.float64)
@@ -437,6 +468,13 @@ def remap_protected_cells(cell_map, old_protected):
     old_protected = np.ascontiguousarray(old_protected, dtype=np.uint8)
     out = np.empty(len(cell_map), dtype=np.uint8)
     lib().or_map_protected(len(cell_map), cell_map.ctypes.data, old_protected.ctypes.data, out.ctypes.data)
+    return out
+
+
+def proc_load(distribution, n_procs):
+    d = _i32(distribution)
+    out = np.zeros(n_procs, dtype=np.int64)
+    lib().or_proc_load(len(d), d.ctypes.data, n_procs, out.ctypes.data)
     return out
 
 

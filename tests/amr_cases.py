@@ -55,7 +55,7 @@ class OracleBackend:
     def set_mesh(self, m):
         self.m = m
         self.w = self.O.World([m])
-        self.n, self.p = m.n, m.p
+        self.n, self.p, self.f, self.b = m.n, m.p, m.f, m.b
 
     def set_protected_cells(self, prot):
         self.prot = prot
@@ -170,6 +170,27 @@ class OracleBackend:
 
     def estimate_cell_size(self, size_type, geometric_d, **kw):
         return self.w.cell_size_error(0, size_type, geometric_d, **kw)
+
+    def imbalance(self):
+        return self.w.imbalance()
+
+    def history_clusters(self, clusters_in=None, want_blocked=True):
+        if clusters_in is None:
+            c2c, ncl = self.w.history_clusters(0)
+        else:
+            c2c, ncl = clusters_in, -1
+        bl, nu = self.w.blocked_faces(0, c2c)
+        return c2c, bl, ncl, nu
+
+    def constrain_decomposition(self, decomposition):
+        c2c, ncl = self.w.history_clusters(0)
+        return self.w.constrain_decomposition(0, c2c, ncl, decomposition)
+
+    def proc_load(self, distribution, n_procs):
+        if len(distribution) and (distribution.min() < 0 or distribution.max() >= n_procs):
+            from blastamr_b200.capi import AmrError
+            raise AmrError(-2, "amr_proc_load: distribution holds a processor outside [0, nProcs)")
+        return self.O.proc_load(distribution, n_procs)
 
     def multicomponent(self, errors, max_cell_levels=None):
         e, mr = self.w.multicomponent(0, errors, max_cell_levels)

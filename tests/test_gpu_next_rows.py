@@ -209,3 +209,39 @@ def test_multicomponent(ctx, O, seed):
     assert np.array_equal(np.flatnonzero(rs[0]), cells)
     e_only, none, _ = ctx.multicomponent(errs[:1])
     assert none is None and np.array_equal(e_only, np.maximum(-1.0, errs[0]))
+
+
+def test_load_balance_inputs(ctx, O):
+    """N4: imbalance metric, refinement-history clusters + blockedFace, cluster-constrained decomposition, procLoadNew"""
+    oc, m = _graded(10, 3)
+    w = O.World([m])
+    ctx.set_mesh(m)
+    assert ctx.imbalance() == w.imbalance() == (0.0, m.n)
+    c2c_ref, ncl_ref = w.history_clusters(0)
+    bl_ref, nu_ref = w.blocked_faces(0, c2c_ref)
+    c2c, bl, ncl, nu = ctx.history_clusters()
+    assert ncl == ncl_ref > 0 and nu == nu_ref > 0
+    assert np.array_equal(c2c_ref, c2c) and np.array_equal(bl_ref, bl)
+    # a cluster = one level-0 cell's descendants: 8^k visible cells each (k = depth), unrefined cells have none
+    assert (c2c[m.cell_level == 0] == -1).all() and (c2c[m.cell_level > 0] >= 0).all()
+    assert (bl[m.f:] == 1).all()
+    # clusters supplied by the host (polyRefiner): same blockedFace for any relabelling
+    perm = np.random.default_rng(0).permutation(ncl).astype(np.int32)
+    relabelled = np.where(c2c >= 0, perm[np.maximum(c2c, 0)], -1).astype(np.int32)
+    _, bl2, ncl2, nu2 = ctx.history_clusters(clusters_in=relabelled)
+    assert ncl2 == -1 and nu2 == nu and np.array_equal(bl, bl2)
+    # decomposition constraint: a geometric split cuts through clusters; apply() repairs it
+    for nprocs in (2, 5):
+        dec0 = np.minimum((m.cc[:, 0] * nprocs).astype(np.int32), nprocs - 1)
+        d_ref, d_gpu = dec0.copy(), dec0.copy()
+        nch_ref = w.constrain_decomposition(0, c2c_ref, ncl_ref, d_ref)
+        nch_gpu = ctx.constrain_decomposition(d_gpu)
+        assert nch_ref == nch_gpu
+        assert np.array_equal(d_ref, d_gpu)
+        for k in np.unique(c2c[c2c >= 0])[::7]:
+            assert len(np.unique(d_gpu[c2c == k])) == 1
+        assert np.array_equal(O.proc_load(d_gpu, nprocs), ctx.proc_load(d_gpu, nprocs))
+        assert ctx.proc_load(d_gpu, nprocs).sum() == m.n
+    from blastamr_b200.capi import AmrError
+    with pytest.raises(AmrError, match="outside"):
+        ctx.proc_load(np.full(m.n, 9, np.int32), 4)

@@ -149,3 +149,4 @@ def test_gpu_test_drivers_run_on_the_oracle():
     T.test_flux_fixup_skips_empty_patches(be, O)
     T.test_mesh_size_cell_size_and_max_refinement(be, O)
     T.test_multicomponent(be, O, 0)
+    T.test_load_balance_inputs(be, O)
