@@ -825,8 +825,8 @@ __device__ __forceinline__ void forEachSetWarp(const u8 *flags, int64_t N, bool 
 // of the marked SOURCE cells and pushing the mark to their neighbours reads a fraction of the adjacency.
 // Count -> gate (device-side decision, no host round trip) -> copy in->out -> push; the dense (pull) kernel
 // returns at once when the gate chose the push form, and vice versa.  All pushes store 1: benign races.
-// Measured at 64-78 M cells: 3 % marked: 0.15 ms instead of 0.33 ms; 21 % marked: 0.7 ms instead of 0.39 ms
-// (scattered byte stores), hence the 1/10 default threshold.
+// Measured at 64-78 M cells with the warp-balanced walk: 3 % marked: 0.06 ms instead of 0.33 ms; 21 % marked
+// (clustered): 0.2 ms instead of 0.39 ms; default threshold 1/4 of the cells.
 __global__ void __launch_bounds__(kThreads)
 k_count_set16(int64_t n, const u8 *__restrict__ flags, bool aligned, unsigned long long *__restrict__ total) {
     const int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 16;
