@@ -283,8 +283,20 @@ static int haloExchange(amr_ctx *ctx, const void *send, void *recv, size_t elemB
 }
 
 // swap of "the value at the owner cell of every boundary face" (patchInternalField / owner levels / owner
-// marks): what every syncTools call site on this path sends.  Peer path: fused gather + push + signal.
-static int haloSwapCells(amr_ctx *ctx, const void *cells, size_t elemBytes, void *recv, const u8 *minus = nullptr) {
+// marks): what every syncTools call site on this path sends.  Peer path: fused gather + push + signal, and the
+// receive side (spin on the neighbours' arrival words + unpack) as a second launch that the caller may issue AFTER
+// its ghost-free main kernel (haloBegin ... main kernel ... haloEnd ... boundary fix-up): the neighbours' skew and
+// the NVLink latency then hide behind the main kernel.  A rank never pushes exchange k+1 before it unpacked
+// exchange k, so a neighbour can run at most one exchange ahead and the two parity buffers suffice.
+struct HaloToken {
+    bool pending = false;
+    unsigned epoch = 0;
+    int parity = 0;
+    size_t elemBytes = 0;
+    void *recv = nullptr;
+};
+static int haloBegin(amr_ctx *ctx, const void *cells, size_t elemBytes, void *recv, HaloToken *tok, const u8 *minus = nullptr) {
+    tok->pending = false;
     if (ctx->nCoupled == 0) return AMR_OK;
     if (!ctx->comm) FAIL(AMR_ERR_STATE, "mesh has processor patches but no communicator (amr_comm_init) and no host-side neighbour values");
     const int64_t b = ctx->b;
@@ -299,14 +311,11 @@ static int haloSwapCells(amr_ctx *ctx, const void *cells, size_t elemBytes, void
         else if (elemBytes == 4) k_halo_push_cells<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
         else if (elemBytes == 8) k_halo_push_cells<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
         else k_halo_push_cells<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
-        if (elemBytes == 1) k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
-        else if (elemBytes == 4) k_halo_unpack<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
-        else if (elemBytes == 8) k_halo_unpack<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
-        else k_halo_unpack<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, parity, epoch, (char *)recv);
-        ctx->launches += 2;
+        ctx->launches++;
+        tok->pending = true; tok->epoch = epoch; tok->parity = parity; tok->elemBytes = elemBytes; tok->recv = recv;
         return AMR_OK;
     }
-    // NCCL path: pack into a send buffer laid out like the boundary-face array, then grouped send/recv
+    // NCCL path: pack into a send buffer laid out like the boundary-face array, then grouped send/recv (complete here)
     void *send = nullptr;
     TRY(arenaAlloc(ctx, &send, (size_t)b * elemBytes));
     if (elemBytes == 1 && minus) LAUNCH(k_pack_level_minus, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const u8 *)cells, minus, (u8 *)send);
@@ -315,6 +324,23 @@ static int haloSwapCells(amr_ctx *ctx, const void *cells, size_t elemBytes, void
     else if (elemBytes == 8) LAUNCH(k_pack_f64, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const double *)cells, (double *)send);
     else LAUNCH(k_pack_vec3, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const double *)cells, (double *)send);
     return haloExchange(ctx, send, recv, elemBytes);
+}
+static int haloEnd(amr_ctx *ctx, HaloToken *tok) {
+    if (!tok->pending) return AMR_OK;
+    tok->pending = false;
+    const HaloPlan &P = *(const HaloPlan *)ctx->haloPlan;
+    const unsigned g = gridFor(P.prefix[P.nPatch]);
+    if (tok->elemBytes == 1) k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv);
+    else if (tok->elemBytes == 4) k_halo_unpack<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv);
+    else if (tok->elemBytes == 8) k_halo_unpack<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv);
+    else k_halo_unpack<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv);
+    ctx->launches++;
+    return AMR_OK;
+}
+static int haloSwapCells(amr_ctx *ctx, const void *cells, size_t elemBytes, void *recv, const u8 *minus = nullptr) {
+    HaloToken tok;
+    TRY(haloBegin(ctx, cells, elemBytes, recv, &tok, minus));
+    return haloEnd(ctx, &tok);
 }
 
 // all-rank reduction of one device word in place (reduce()/returnReduce()/gMin/gMax of the reference).
@@ -664,10 +690,11 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
         } else if (kind == AMR_EST_DELTA || kind == AMR_EST_SCALED_DELTA || kind == AMR_EST_CODED_DELTA ||
                    kind == AMR_EST_DENSITY_GRADIENT) {
             const double *ghost = nullptr;
+            HaloToken halo;
             if (ctx->nCoupled > 0) {
                 if (nbrValues) TRY(stageIn(ctx, nbrValues, b, &ghost));
                 else {
-                    TRY(haloSwapCells(ctx, dx, 8, ctx->ghost64));
+                    TRY(haloBegin(ctx, dx, 8, ctx->ghost64, &halo));      // received after the ghost-free main kernel
                     ghost = ctx->ghost64;
                 }
             }
@@ -681,6 +708,7 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
         } else if (scale) LAUNCH((k_estimate<K, true>), gridFor(n), kThreads, n, so, col, dx, cg, p0, p1, t, target); \
         else LAUNCH((k_estimate<K, false>), gridFor(n), kThreads, n, so, col, dx, cg, p0, p1, t, target);        \
         if (ctx->nCoupled > 0) {                                                                                 \
+            TRY(haloEnd(ctx, &halo));                                                                            \
             LAUNCH((k_fix_estimate<K>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, \
                    (const label *)(ctx->owner + ctx->f), dx, ghost, p0, p1, target);                             \
             if (scale) LAUNCH(k_fix_normalize, gridFor(ctx->nCplCells), kThreads, ctx->nCplCells, (const label *)ctx->cplCell, t, target); \
@@ -803,8 +831,9 @@ AMR_API int amr_normalize_range(amr_ctx *ctx, double refineThreshold, double unr
 // a wrong prediction only costs time, both forms give the same flags.
 static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res, int site) {
     const int64_t n = ctx->n;
+    HaloToken halo;
     if (ctx->nCoupled > 0) {
-        TRY(haloSwapCells(ctx, src, 1, ctx->ghost8));
+        TRY(haloBegin(ctx, src, 1, ctx->ghost8, &halo));
     }
     const int *gate = nullptr;
     if (ctx->pushNum > 0 && n >= ctx->pushMinCells && n > 0) {
@@ -825,6 +854,7 @@ static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res, 
     }
     if (pipeOk(ctx, ctx->cc)) TRY(launchPipe(ctx, kp_extend, ctx->cc, (const u8 *)cur, src, tmp, gate));
     else LAUNCH(k_extend, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, cur, src, tmp, gate);
+    TRY(haloEnd(ctx, &halo));
     if (ctx->nCoupled > 0)
         LAUNCH(k_fix_extend, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
                (const u8 *)ctx->ghost8, tmp);
@@ -947,8 +977,9 @@ static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOu
             if (maxSet) LAUNCH((k_edge_refine_sweep<true>), gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, lf, set, ctx->dFlags);
             else LAUNCH((k_edge_refine_sweep<false>), gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, lf, set, ctx->dFlags);
         }
+        HaloToken halo;
         if (ctx->nCoupled > 0) {
-            TRY(haloSwapCells(ctx, lf, 1, ctx->ghost8));
+            TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo));          // lf as it is before this sweep, like the reference's neiLevel
         }
         if (n) {
             const int *gate = nullptr;
@@ -974,6 +1005,7 @@ static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOu
                 else TRY(launchPipe(ctx, kp_refine_sweep<false>, ctx->cc, lf, set, ctx->dFlags, gate));
             } else if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->dFlags, gate);
             else LAUNCH(k_refine_sweep_min, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->dFlags);
+            TRY(haloEnd(ctx, &halo));
             if (ctx->nCoupled > 0) {      // hexRef.C:758-780
                 if (maxSet) LAUNCH((k_fix_refine_sweep<true>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
                                    (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
