@@ -41,7 +41,8 @@ struct Sell {
     int32_t *col = nullptr;       // [entries]
     u8 *count = nullptr;          // [rows] true row length (saturated at 255)
     int maxTileInts = 0;          // largest 8-slice tile, in int32 (ring stage capacity of the TMA pipeline)
-    u8 *sliceGhost = nullptr;     // [slices] slice has an entry >= rows (ghost slot of a coupled face); cell->cell only
+    u8 *sliceGhost = nullptr;     // [slices] slice holds a cell that owns a coupled face (the estimators keep those raw until
+                                  // the boundary fix-up has folded the patch faces in); cell->cell only
 };
 
 struct amr_ctx {

@@ -51,7 +51,7 @@ struct SellView {
     const int32_t *col;
     int64_t rows, slices;
     int stageInts;             // capacity of one ring stage in int32 (>= largest tile)
-    const u8 *sliceGhost;      // [slices] or nullptr
+    const u8 *sliceGhost;      // [slices] slice holds a cell that owns a coupled face, or nullptr
 };
 
 // dynamic shared memory layout: [kStages][stageInts] labels | [kStages][kHdrInts] headers | barriers
