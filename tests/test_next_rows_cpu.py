@@ -150,3 +150,10 @@ def test_gpu_test_drivers_run_on_the_oracle():
     T.test_mesh_size_cell_size_and_max_refinement(be, O)
     T.test_multicomponent(be, O, 0)
     T.test_load_balance_inputs(be, O)
+
+
+def test_full_size_driver_on_the_oracle():
+    """tests/test_gpu_full_size.py at 24^3 with the oracle as backend: the numpy stencil / dilation references of
+    that file agree with the oracle, so at 400^3 they can stand in for it"""
+    import tests.test_gpu_full_size as T
+    assert T.run(cases.OracleBackend(), 24) > 0
