@@ -36,6 +36,7 @@ _SIGS = {
     "amr_mesh_set_points": (C.c_int, [C.c_void_p] * 4),
     "amr_mesh_set_edges": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 4),
     "amr_mesh_set_faces": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_mesh_set_patch_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "amr_mesh_set_geometry": (C.c_int, [C.c_void_p] * 6),
     "amr_estimate_lohner": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
@@ -183,6 +184,8 @@ class Context:
                                                _ptr(mesh.bnd_edge)))
         if getattr(mesh, "face_off", None) is not None:
             self._ck(self.L.amr_mesh_set_faces(self._h, _ptr(mesh.face_off), _ptr(mesh.face_pts)))
+        if getattr(mesh, "patch_pt_off", None) is not None:
+            self._ck(self.L.amr_mesh_set_patch_points(self._h, _ptr(mesh.patch_pt_off), _ptr(mesh.patch_pts)))
         if getattr(mesh, "Sf", None) is not None and mesh.vol is not None:
             self._ck(self.L.amr_mesh_set_geometry(self._h, _ptr(mesh.weights), _ptr(mesh.Sf), _ptr(mesh.magSf),
                                                   _ptr(mesh.delta_coeffs), _ptr(mesh.vol)))

@@ -104,6 +104,7 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->grad); devFree(ctx, &ctx->xbf);
     devFree(ctx, &ctx->bEmpty); devFree(ctx, &ctx->lsP); devFree(ctx, &ctx->lsN); ctx->haveLs = false;
     devFree(ctx, &ctx->visible); devFree(ctx, &ctx->splitParent); ctx->nSplit = 0;
+    devFree(ctx, &ctx->ppPts); ctx->ppOff.clear();
     sellFree(ctx, ctx->cf);
     ctx->haveGeom = false;
     sellFree(ctx, ctx->ec); devFree(ctx, &ctx->bndEdge); devFree(ctx, &ctx->edgePts);
@@ -571,6 +572,57 @@ AMR_API int amr_mesh_set_faces(amr_ctx *ctx, const int32_t *faceOff, const int32
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->haveFaces = true;
     return AMR_OK;
+}
+
+AMR_API int amr_mesh_set_patch_points(amr_ctx *ctx, const int32_t *patchPointOff, const int32_t *patchPoints) {
+    ENTER();
+    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_mesh_set_patch_points: call amr_mesh_set first");
+    if (!patchPointOff) FAIL(AMR_ERR_ARG, "amr_mesh_set_patch_points: null pointer");
+    const size_t np = ctx->patches.size();
+    ctx->ppOff.assign(patchPointOff, patchPointOff + np + 1);
+    for (size_t q = 0; q < np; q++)
+        if (ctx->ppOff[q + 1] < ctx->ppOff[q] || ctx->ppOff[0] != 0) { ctx->ppOff.clear(); FAIL(AMR_ERR_ARG, "amr_mesh_set_patch_points: bad offsets"); }
+    const int64_t tot = ctx->ppOff[np];
+    if (tot > 0 && !patchPoints) { ctx->ppOff.clear(); FAIL(AMR_ERR_ARG, "amr_mesh_set_patch_points: null pointer"); }
+    devFree(ctx, &ctx->ppPts);
+    TRY(devAlloc(ctx, &ctx->ppPts, tot > 0 ? tot : 1));
+    if (tot) CK(cudaMemcpyAsync(ctx->ppPts, patchPoints, (size_t)tot * 4, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMR_OK;
+}
+
+// syncTools::syncPointList(pflag, orEqOp<bool>(), false) over the processor patches (fvMeshRefiner.C:952-958).  One
+// pairwise exchange covers points shared by two ranks; a point on an edge or corner of the decomposition reaches the
+// ranks it shares no FACE with through a common neighbour, so the exchange repeats until no rank changed (OR is
+// idempotent: same fixed point as the reference's global shared-point pass).  Collective.
+static int syncPointsOr(amr_ctx *ctx, u8 *pflag) {
+    if (!ctx->comm || ctx->nranks < 2) return AMR_OK;
+    if (ctx->nCoupled > 0 && ctx->ppOff.empty())
+        FAIL(AMR_ERR_STATE, "point sync across processor patches needs their point lists (amr_mesh_set_patch_points)");
+    const size_t np = ctx->ppOff.empty() ? 0 : ctx->patches.size();
+    const int64_t tot = np ? ctx->ppOff[np] : 0;
+    u8 *send = nullptr, *recv = nullptr;
+    void *q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(tot > 0 ? tot : 1))); send = (u8 *)q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(tot > 0 ? tot : 1))); recv = (u8 *)q;
+    for (int round = 0; round < 64; round++) {
+        CK(cudaMemsetAsync(ctx->dFlags + 11, 0, sizeof(int), ctx->stream));
+        if (tot) LAUNCH(k_pack_u8, gridFor(tot), kThreads, tot, (const label *)ctx->ppPts, (const u8 *)pflag, send);
+        NCK(ncclGroupStart());
+        for (size_t k = 0; k < np; k++) {
+            const Patch &pp = ctx->patches[k];
+            const int64_t cnt = ctx->ppOff[k + 1] - ctx->ppOff[k];
+            if (pp.type != AMR_PATCH_PROCESSOR || cnt == 0) continue;
+            NCK(ncclSend(send + ctx->ppOff[k], (size_t)cnt, ncclUint8, pp.nbr, ctx->comm, ctx->stream));
+            NCK(ncclRecv(recv + ctx->ppOff[k], (size_t)cnt, ncclUint8, pp.nbr, ctx->comm, ctx->stream));
+        }
+        NCK(ncclGroupEnd());
+        if (tot) LAUNCH(k_or_scatter, gridFor(tot), kThreads, tot, (const label *)ctx->ppPts, (const u8 *)recv, pflag, ctx->dFlags + 11);
+        int changed = 0;
+        TRY(globalFlag(ctx, 11, &changed));
+        if (!changed) return AMR_OK;
+    }
+    FAIL(AMR_ERR_INVARIANT, "point sync did not settle");
 }
 
 AMR_API int amr_set_option(amr_ctx *ctx, int option, int64_t value) {
@@ -1377,8 +1429,8 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
         if (!ctx->haveFaces || !ctx->pointLevel) FAIL(AMR_ERR_STATE, "amr_select_unrefine: polyRefiner needs amr_mesh_set_faces and pointLevel");
         if ((ctx->optEdgeConsistency || prismatic) && !ctx->haveEdges)
             FAIL(AMR_ERR_STATE, "amr_select_unrefine: edgeBasedConsistency / prismatic2DRefinement need amr_mesh_set_edges (all mesh edges)");
-        if (ctx->nCoupled > 0 && nBufferLayers > 0)
-            FAIL(AMR_ERR_STATE, "amr_select_unrefine: polyRefiner point buffer layers across processor patches need a shared-point plan (syncPointList); not on the device path yet");
+        if (ctx->nCoupled > 0 && nBufferLayers > 0 && ctx->ppOff.empty())
+            FAIL(AMR_ERR_STATE, "amr_select_unrefine: polyRefiner point buffer layers across processor patches need the patches' point lists (amr_mesh_set_patch_points)");
     }
     if (refinerKind == AMR_REFINER_HEX2D && !ctx->haveEdges) FAIL(AMR_ERR_STATE, "amr_select_unrefine: hexRef2D needs amr_mesh_set_edges");
     if (nProtectedPatches > 0 && !protectedPatchIds) FAIL(AMR_ERR_ARG, "amr_select_unrefine: protectedPatchIds is null");
@@ -1401,6 +1453,7 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
         // extendMarkedCellsAcrossPoints (fvMeshRefiner.C:924-977): cells -> points -> cells, in place (flags only grow)
         for (int i = 0; i < nBufferLayers; i++) {
             if (p) LAUNCH(k_cells_to_points_or, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const u8 *)cur, ctx->flagC);
+            TRY(syncPointsOr(ctx, ctx->flagC));                      // syncTools::syncPointList, fvMeshRefiner.C:952-958
             if (p) LAUNCH(k_points_to_cells, gridFor(p, kThreads * 16), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const u8 *)ctx->flagC,
                           (((uintptr_t)ctx->flagC) & 15) == 0, cur);
         }

@@ -101,6 +101,8 @@ struct amr_ctx {
     int balancedLocal = -1;         // internal faces of the mesh satisfy |dLevel| <= 1 (-1: not checked yet)
     long long *hMarked = nullptr;   // pinned: marked cells seen per buffer-layer site by the previous call
     int pushNum = 1, pushDen = 4;   // buffer layers take the sparse push form when marked/n < pushNum/pushDen (0 = never)
+    label *ppPts = nullptr;         // points of the processor patches, patch after patch (syncPointList pairing)
+    std::vector<int32_t> ppOff;     // [npatch+1] offsets into ppPts
     label *visible = nullptr, *splitParent = nullptr;   // refinement history (hexRefRefinementHistory), kept for cluster queries
     int64_t nSplit = 0;
     u8 *bEmpty = nullptr;      // [b] boundary face lies on an empty patch (no surface-field entries)

@@ -677,6 +677,15 @@ k_edge_unrefine_sweep(int64_t nEdges, const int32_t *__restrict__ ecOff, const i
     }
 }
 
+// syncTools::syncPointList(markedPoint, orEqOp<bool>()) (fvMeshRefiner.C:952-958), receive side: OR the neighbour's
+// values into the points of my processor patches (same point order on both sides)
+__global__ void __launch_bounds__(kThreads)
+k_or_scatter(int64_t count, const label *__restrict__ idx, const u8 *__restrict__ recv, u8 *__restrict__ pflag, int *changed) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= count) return;
+    if (recv[i] && !pflag[idx[i]]) { pflag[idx[i]] = 1; *changed = 1; }
+}
+
 // first half of fvMeshRefiner::extendMarkedCellsAcrossPoints (fvMeshRefiner.C:924-950): a point is marked
 // when any of its cells is (the second half, points -> cells, is k_points_to_cells)
 __global__ void __launch_bounds__(kThreads)

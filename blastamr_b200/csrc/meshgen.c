@@ -53,6 +53,7 @@ typedef struct mg_mesh {
     i64 nsplit;
     i32 *cellGlobal;      /* n : global cell id (decomposed meshes), else NULL */
     i32 *pointGlobal;     /* p : global point id (decomposed meshes), else NULL */
+    i32 *ppOff, *ppPts;   /* npatch+1 / ... : points of each processor patch, same order on both sides (decomposed meshes) */
     i32 *faceGlobal;      /* f+b: global face id (decomposed meshes), else NULL */
     i32 *pxyz;            /* 3p integer point coordinates in fine units (octree meshes) */
     /* fvMesh geometry (octree meshes): surfaceInterpolation::weights(), Sf(), magSf(), nonOrthDeltaCoeffs() */
@@ -90,7 +91,7 @@ MG_API void mg_mesh_free(mg_mesh *m) {
     free(m->patchType); free(m->patchNbr); free(m->cc); free(m->vol);
     free(m->pcOff); free(m->pcCells); free(m->cpOff); free(m->cpPts);
     free(m->bndPoint); free(m->cellLevel); free(m->pointLevel); free(m->visible);
-    free(m->splitParent); free(m->cellGlobal); free(m->pointGlobal); free(m->faceGlobal);
+    free(m->splitParent); free(m->cellGlobal); free(m->pointGlobal); free(m->faceGlobal); free(m->ppOff); free(m->ppPts);
     free(m->pxyz); free(m->Sf); free(m->magSf); free(m->weights); free(m->deltaCoeffs);
     free(m->edgePts); free(m->ecOff); free(m->ecCells); free(m->bndEdge); free(m->faceOff); free(m->facePts);
     free(m);
@@ -105,6 +106,7 @@ MG_API void mg_mesh_sizes(const mg_mesh *m, i64 *out) {
     out[8] = m->nedge;
     out[9] = m->ecOff ? m->ecOff[m->nedge] : 0;
     out[10] = m->faceOff ? m->faceOff[m->f + m->b] : 0;
+    out[11] = m->ppOff ? m->ppOff[m->npatch] : 0;
 }
 
 /* array access by id (Python wraps the pointers without copying) */
@@ -124,6 +126,7 @@ MG_API void *mg_mesh_array(const mg_mesh *m, int id) {
     case 21: return m->Sf; case 22: return m->magSf; case 23: return m->weights; case 24: return m->deltaCoeffs;
     case 25: return m->edgePts; case 26: return m->ecOff; case 27: return m->ecCells; case 28: return m->bndEdge;
     case 29: return m->faceOff; case 30: return m->facePts;
+    case 31: return m->ppOff; case 32: return m->ppPts;
     }
     return NULL;
 }
@@ -477,6 +480,51 @@ static inline void cell_box(const mg_oct *o, i64 c, i32 *lo, i32 *hi) {
     hi[0] = (o->cx[c] + 1) << sh; hi[1] = (o->cy[c] + 1) << sh; hi[2] = (o->cz[c] + zext(o, c)) << sh;
 }
 
+/* mesh.edges() / edgeCells() / "edge of a boundary face" from faces() and pointCells(): consecutive perimeter points,
+   unique, numbered in order of first appearance over ascending faces; cells around an edge = pointCells(a) ^ pointCells(b) */
+static void edges_from_faces(mg_mesh *m) {
+    const i64 f = m->f, nfaces = m->f + m->b;
+    const i32 *pcnt = m->pcOff;
+    phash E; ph_init(&E, m->faceOff[nfaces] + 16);
+    i64 ne = 0, ecap = 0;
+    i32 *ep = NULL; u8 *be = NULL;
+    for (i64 i = 0; i < nfaces; i++) {
+        i32 s0 = m->faceOff[i], s1 = m->faceOff[i + 1];
+        for (i32 k = s0; k < s1; k++) {
+            i32 a = m->facePts[k], c2 = m->facePts[k + 1 < s1 ? k + 1 : s0];
+            i32 lo_ = a < c2 ? a : c2, hi_ = a < c2 ? c2 : a;
+            uint64_t key = ((uint64_t)(uint32_t)lo_ << 32) | (uint32_t)hi_;
+            i32 id = ph_get(&E, key);
+            if (id < 0) {
+                if (ne == ecap) { ecap = ecap ? ecap * 2 : 1 << 16; ep = (i32 *)xrealloc(ep, ecap * 8); be = (u8 *)xrealloc(be, ecap); }
+                id = (i32)ne++;
+                ph_put(&E, key, id);
+                ep[2 * id] = lo_; ep[2 * id + 1] = hi_; be[id] = 0;
+            }
+            if (i >= f) be[id] = 1;
+        }
+    }
+    ph_free(&E);
+    m->nedge = ne; m->edgePts = ep; m->bndEdge = be;
+    m->ecOff = (i32 *)xcalloc(ne + 1, 4);
+    for (int pass = 0; pass < 2; pass++) {
+        for (i64 e = 0; e < ne; e++) {
+            i32 q = ep[2 * e], partner = ep[2 * e + 1];
+            i32 a = pcnt[q], ae = pcnt[q + 1], c2 = pcnt[partner], ce = pcnt[partner + 1];
+            i32 k = pass ? m->ecOff[e] : 0;
+            while (a < ae && c2 < ce) {
+                i32 pa = m->pcCells[a], pc = m->pcCells[c2];
+                if (pa == pc) { if (pass) m->ecCells[k] = pa; k++; a++; c2++; } else if (pa < pc) a++; else c2++;
+            }
+            if (!pass) m->ecOff[e + 1] = k;
+        }
+        if (!pass) {
+            for (i64 e = 0; e < ne; e++) m->ecOff[e + 1] += m->ecOff[e];
+            m->ecCells = (i32 *)xmalloc((m->ecOff[ne] ? m->ecOff[ne] : 1) * 4);
+        }
+    }
+}
+
 /*
  * Build the polyMesh-style arrays for the current octree.
  * flags: bit0 = build point addressing (pointCells, cellPoints, bndPoint, pointLevel).
@@ -760,45 +808,7 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
             m->faceOff[i + 1] = (i32)W.cnt;
         }
         m->facePts = W.buf;
-        /* edges: consecutive perimeter points, unique */
-        phash E; ph_init(&E, W.cnt + 16);
-        i64 ne = 0, ecap = 0;
-        i32 *ep = NULL; u8 *be = NULL;
-        for (i64 i = 0; i < nfaces; i++) {
-            i32 s0 = m->faceOff[i], s1 = m->faceOff[i + 1];
-            for (i32 k = s0; k < s1; k++) {
-                i32 a = m->facePts[k], c2 = m->facePts[k + 1 < s1 ? k + 1 : s0];
-                i32 lo_ = a < c2 ? a : c2, hi_ = a < c2 ? c2 : a;
-                uint64_t key = ((uint64_t)(uint32_t)lo_ << 32) | (uint32_t)hi_;
-                i32 id = ph_get(&E, key);
-                if (id < 0) {
-                    if (ne == ecap) { ecap = ecap ? ecap * 2 : 1 << 16; ep = (i32 *)xrealloc(ep, ecap * 8); be = (u8 *)xrealloc(be, ecap); }
-                    id = (i32)ne++;
-                    ph_put(&E, key, id);
-                    ep[2 * id] = lo_; ep[2 * id + 1] = hi_; be[id] = 0;
-                }
-                if (i >= f) be[id] = 1;
-            }
-        }
-        ph_free(&E);
-        m->nedge = ne; m->edgePts = ep; m->bndEdge = be;
-        m->ecOff = (i32 *)xcalloc(ne + 1, 4);
-        for (int pass = 0; pass < 2; pass++) {
-            for (i64 e = 0; e < ne; e++) {
-                i32 q = ep[2 * e], partner = ep[2 * e + 1];
-                i32 a = pcnt[q], ae = pcnt[q + 1], c2 = pcnt[partner], ce = pcnt[partner + 1];
-                i32 k = pass ? m->ecOff[e] : 0;
-                while (a < ae && c2 < ce) {
-                    i32 pa = m->pcCells[a], pc = m->pcCells[c2];
-                    if (pa == pc) { if (pass) m->ecCells[k] = pa; k++; a++; c2++; } else if (pa < pc) a++; else c2++;
-                }
-                if (!pass) m->ecOff[e + 1] = k;
-            }
-            if (!pass) {
-                for (i64 e = 0; e < ne; e++) m->ecOff[e + 1] += m->ecOff[e];
-                m->ecCells = (i32 *)xmalloc((m->ecOff[ne] ? m->ecOff[ne] : 1) * 4);
-            }
-        }
+        edges_from_faces(m);
     }
     /* --- 2-D without flag 4: only the edges normal to the plane (one per point column and layer; what the
            2-D cutter selects from), edgeCells = cells around it */
@@ -988,6 +998,40 @@ MG_API int mg_decompose(const mg_mesh *g, const i32 *cellRank, int nranks, mg_me
                     if (pa == pc) { if (ploc[pa] >= 0) m->bndPoint[ploc[pa]] = 1; a++; c2++; }
                     else if (pa < pc) a++; else c2++;
                 }
+            }
+            /* faces(), edges() and the point lists of the processor patches (polyRefiner across ranks) */
+            if (g->faceOff) {
+                i64 nfl = fl + bl, tot = 0;
+                m->faceOff = (i32 *)xcalloc(nfl + 1, 4);
+                for (i64 k2 = 0; k2 < nfl; k2++) { i64 gf = m->faceGlobal[k2]; tot += g->faceOff[gf + 1] - g->faceOff[gf]; m->faceOff[k2 + 1] = (i32)tot; }
+                m->facePts = (i32 *)xmalloc((tot ? tot : 1) * 4);
+                for (i64 k2 = 0; k2 < nfl; k2++) {
+                    i64 gf = m->faceGlobal[k2];
+                    i32 *dst = m->facePts + m->faceOff[k2];
+                    for (i32 j = g->faceOff[gf]; j < g->faceOff[gf + 1]; j++) *dst++ = ploc[g->facePts[j]];
+                }
+                edges_from_faces(m);
+                /* syncTools::syncPointList pairing: the points of a processor patch in ascending GLOBAL label, the same
+                   order on both sides */
+                m->ppOff = (i32 *)xcalloc(np + 1, 4);
+                i32 *tmpp = (i32 *)xmalloc((tot ? tot : 1) * 4);
+                i64 ntot = 0;
+                for (int q = 0; q < np; q++) {
+                    i64 cnt = 0;
+                    if (m->patchType[q] == 2) {
+                        for (i64 k2 = m->patchStart[q]; k2 < m->patchStart[q] + m->patchSize[q]; k2++)
+                            for (i32 j = m->faceOff[k2]; j < m->faceOff[k2 + 1]; j++) tmpp[ntot + cnt++] = m->pointGlobal[m->facePts[j]];
+                        qsort(tmpp + ntot, (size_t)cnt, 4, cmp_i32);
+                        i64 u = 0;
+                        for (i64 i = 0; i < cnt; i++) if (i == 0 || tmpp[ntot + i] != tmpp[ntot + i - 1]) tmpp[ntot + u++] = tmpp[ntot + i];
+                        cnt = u;
+                    }
+                    ntot += cnt;
+                    m->ppOff[q + 1] = (i32)ntot;
+                }
+                m->ppPts = (i32 *)xmalloc((ntot ? ntot : 1) * 4);
+                for (i64 i = 0; i < ntot; i++) m->ppPts[i] = ploc[tmpp[i]];
+                free(tmpp);
             }
             free(ploc);
         }

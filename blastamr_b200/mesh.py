@@ -87,6 +87,8 @@ class PolyMesh:
     split_parent: Optional[np.ndarray] = None
     cell_global: Optional[np.ndarray] = None
     point_global: Optional[np.ndarray] = None
+    patch_pt_off: Optional[np.ndarray] = None   # points of each processor patch (same order on both sides), CSR over patches
+    patch_pts: Optional[np.ndarray] = None
     face_global: Optional[np.ndarray] = None
     pxyz: Optional[np.ndarray] = None
     Sf: Optional[np.ndarray] = None            # float64 [f+b,3]
@@ -124,9 +126,9 @@ class PolyMesh:
 
 def _wrap(handle: int, names: Sequence[str], copy: bool = False) -> PolyMesh:
     L = lib()
-    sz = np.zeros(11, dtype=np.int64)
+    sz = np.zeros(12, dtype=np.int64)
     L.mg_mesh_sizes(handle, sz.ctypes.data)
-    n, f, b, p, npatch, nsplit, nnz_pc, nnz_cp, nedge, nnz_ec, nnz_fp = (int(x) for x in sz)
+    n, f, b, p, npatch, nsplit, nnz_pc, nnz_cp, nedge, nnz_ec, nnz_fp, nnz_pp = (int(x) for x in sz)
 
     def arr(idx, dtype, count, shape=None):
         ptr = L.mg_mesh_array(handle, idx)
@@ -161,6 +163,7 @@ def _wrap(handle: int, names: Sequence[str], copy: bool = False) -> PolyMesh:
         ec_off=arr(26, np.int32, nedge + 1) if nedge else None, ec_cells=arr(27, np.int32, nnz_ec) if nedge else None,
         bnd_edge=arr(28, np.uint8, nedge) if nedge else None,
         face_off=arr(29, np.int32, f + b + 1) if nnz_fp else None, face_pts=arr(30, np.int32, nnz_fp) if nnz_fp else None,
+        patch_pt_off=arr(31, np.int32, npatch + 1) if nnz_pp else None, patch_pts=arr(32, np.int32, nnz_pp) if nnz_pp else None,
     )
     if m.split_parent is None:
         m.split_parent = np.zeros(0, np.int32)

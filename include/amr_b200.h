@@ -77,8 +77,8 @@ enum {
     AMR_REFINER_HEX3D = 0,   /* hexRefiner + hexRef3D */
     AMR_REFINER_HEX2D = 1,   /* hexRefiner + hexRef2D (split elements are edges; needs amr_mesh_set_edges) */
     AMR_REFINER_POLY3D = 2,  /* polyRefiner + polyhedralRefinement (needs amr_mesh_set_edges with ALL mesh edges and
-                                amr_mesh_set_faces; single rank: the point sync of the unrefinement buffer layers,
-                                syncTools::syncPointList fvMeshRefiner.C:952-958, is not on the device path yet) */
+                                amr_mesh_set_faces; across ranks also amr_mesh_set_patch_points for the point sync of the
+                                unrefinement buffer layers, syncTools::syncPointList fvMeshRefiner.C:952-958) */
     AMR_REFINER_POLY2D = 3   /* polyRefiner + prismatic2DRefinement (fvMeshPolyRefiner.C:139-155): same marking and
                                 consistency sweeps as POLY3D; split points from pointLevel over the point's edges and
                                 only processor-patch points excluded (prismatic2DRefinement.C:2744-2849) */
@@ -138,6 +138,13 @@ enum {
     AMR_OPT_EDGE_BASED_CONSISTENCY = 0, /* `edgeBasedConsistency` (refinement.C:700-703), default 1 */
     AMR_OPT_POLY_FORCE = 1              /* fvMeshRefiner::force_ as passed by fvMeshPolyRefiner.C:338, default 0 */
 };
+/* Points of the processor patches, patch after patch (patchPointOff [npatch+1], zero-length ranges for other
+   patches), each list in the order that pairs it with the neighbour's list: processorPolyPatch::meshPoints() against
+   neighbPoints().  Needed only for point-based syncs across ranks (syncTools::syncPointList in
+   fvMeshRefiner::extendMarkedCellsAcrossPoints, fvMeshRefiner.C:952-958: the polyRefiner's unrefinement buffer
+   layers). */
+int amr_mesh_set_patch_points(amr_ctx *ctx, const int32_t *patchPointOff, const int32_t *patchPoints);
+
 int amr_set_option(amr_ctx *ctx, int option, int64_t value);
 
 /* hexRef::cellLevel_/pointLevel_ and the refinement history arrays visibleCells_ and

@@ -270,10 +270,14 @@ class World:
         up = [np.zeros(m.p, dtype=np.uint8) for m in self.meshes]
         sp = [np.zeros(m.p, dtype=np.uint8) for m in self.meshes]
         ids = _i32(protected_patch_ids)
+        pg, n_glob = None, 0
         if self.R > 1:
-            raise NotImplementedError("poly unrefinement across ranks needs the shared-point plan (syncPointList)")
+            # syncTools::syncPointList over ranks: shared points are identified by their global label
+            gl = [_i32(m.point_global) for m in self.meshes]
+            self._keep += gl
+            pg, n_glob = _pp(gl), int(max(int(g.max()) for g in gl if len(g)) + 1)
         sweeps = lib().or_poly_select_unrefine(self._h, _pp(err), unrefine_level, n_layers, ids.ctypes.data, len(ids),
-                                               1 if edge_based else 0, None, 0, _pp(refine_cell), _pp(up), _pp(sp),
+                                               1 if edge_based else 0, pg, n_glob, _pp(refine_cell), _pp(up), _pp(sp),
                                                1 if prismatic else 0)
         if sweeps < 0:
             raise RuntimeError("reference FatalError 'problem' (refinement.C:417)")

@@ -42,6 +42,20 @@ def graded_octree(n0=8, max_level=2, centre=(0.5, 0.5, 0.5), r0=0.3, band=0.08, 
     return oc
 
 
+def poly_balanced_octree(O, n0=10, max_level=2):
+    """an octree that is 2:1 balanced over faces AND edges (what polyRefiner produces and requires): grown from a
+    uniform box by the oracle's own polyRefiner selection around a spherical front"""
+    oc = M.Octree(n0, n0, n0, (1.0, 1.0, 1.0), max_level)
+    for _ in range(max_level):
+        m = oc.build(faces=True)
+        w = O.World([m])
+        e = w.estimate("delta", [front_field(m.cc, centre=(0.5, 0.5, 0.5), r0=0.3, w=0.03)])
+        w.normalize(e, 0.01, 1e15, 0.01, 1e15)
+        _, rs, _ = w.poly_select_refine(e, max_level, 2)
+        oc.refine(np.flatnonzero(rs[0]).astype(np.int32))
+    return oc
+
+
 class OracleBackend:
     """Same call surface as blastamr_b200.capi.Context, answered by the oracle (R = 1).
     Used on CPU only to exercise the test drivers themselves; never by the product."""

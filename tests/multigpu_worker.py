@@ -107,6 +107,32 @@ def main():
         e2g = eg.copy(); ctx.protect_patches(pid, 3, e2g)
         if not np.array_equal(e2[cg], e2g):
             fails.append("protect_patches")
+    # ---- polyRefiner across ranks: face + (local) edge consistency with halos, and the unrefinement buffer layers over
+    # POINTS, whose marks cross processor patches through syncTools::syncPointList (fvMeshRefiner.C:952-958)
+    ocp = cases.poly_balanced_octree(O)
+    gp = ocp.build(geometry=True, faces=True)
+    locp = M.decompose(gp, M.simple_ranks(gp, (1, 1, 1), PROCS[world]), world)
+    mep = locp[rank]
+    wP = O.World(locp)
+    ctx.set_mesh(mep)
+    xp = cases.front_field(gp.cc, centre=(0.62, 0.5, 0.5), r0=0.3, w=0.03)
+    eP = wP.estimate("delta", [xp[l.cell_global].copy() for l in locp])
+    wP.normalize(eP, *thr)
+    rcP, rsP, _ = wP.poly_select_refine(eP, 2, 2)
+    rc_g = np.zeros(mep.n, np.uint8)
+    cells, _ = ctx.select_refine(eP[rank], 2, 2, refine_cell_out=rc_g, kind=2)
+    if not (np.array_equal(rcP[rank], rc_g) and np.array_equal(np.flatnonzero(rsP[rank]), cells)):
+        fails.append("polyRefiner select_refine")
+    rc_ref = [r.copy() for r in rcP]
+    upP, _, _ = wP.poly_select_unrefine(eP, rc_ref, 2)
+    rc_gpu = rcP[rank].copy()
+    pts, _ = ctx.select_unrefine(eP[rank], 2, refine_cell=rc_gpu, kind=2)
+    if not np.array_equal(rc_ref[rank], rc_gpu):
+        fails.append("polyRefiner point buffer layers (syncPointList)")
+    if not np.array_equal(np.flatnonzero(upP[rank]), pts):
+        fails.append("polyRefiner unrefine points")
+    if sum(int(u.sum()) for u in upP) == 0 or all(np.array_equal(a, b) for a, b in zip(rcP, rc_ref)):
+        fails.append("polyRefiner case is trivial")
     t = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(t)
     if fails:

@@ -293,3 +293,30 @@ def test_prismatic_split_points_agree_with_history_rule():
     for e in range(m_all.n_edges):
         cs = m_all.ec_cells[m_all.ec_off[e]:m_all.ec_off[e + 1]]
         assert lv[cs].max() - lv[cs].min() <= 1
+
+
+def test_poly_point_layers_do_not_depend_on_the_decomposition():
+    """polyRefiner across ranks: the unrefinement buffer layers spread over POINTS and their marks cross processor
+    patches through syncPointList (fvMeshRefiner.C:952-958) -- gathered back to global labels, the marking is the
+    same for every decomposition (the unrefinement points themselves are not: points on processor patches can never
+    be split points)"""
+    oc = cases.poly_balanced_octree(O)
+    g = oc.build(geometry=True, faces=True)
+    x = cases.front_field(g.cc, centre=(0.62, 0.5, 0.5), r0=0.3, w=0.03)
+    marks = []
+    for world, procs in ((2, (2, 1, 1)), (4, (2, 2, 1)), (8, (2, 2, 2))):
+        loc = M.decompose(g, M.simple_ranks(g, (1, 1, 1), procs), world)
+        for r, m in enumerate(loc):                   # faces()/edges() of the sub-domains are closed polyhedral complexes
+            assert m.p - m.n_edges + (m.f + m.b) - m.n == 1
+        w = O.World(loc)
+        e = w.estimate("delta", [x[l.cell_global].copy() for l in loc])
+        w.normalize(e, 0.01, 1e15, 0.01, 1e15)
+        rc, rs, _ = w.poly_select_refine(e, 2, 2)
+        rc2 = [r.copy() for r in rc]
+        up, _, _ = w.poly_select_unrefine(e, rc2, 2)
+        assert sum(int(u.sum()) for u in up) > 0
+        glob = np.zeros(g.n, np.uint8)
+        for l, r in zip(loc, rc2):
+            glob[l.cell_global] = r
+        marks.append(glob)
+    assert marks[0].sum() > 0 and np.array_equal(marks[0], marks[1]) and np.array_equal(marks[0], marks[2])
