@@ -133,6 +133,10 @@ AMR_API int amr_ctx_destroy(amr_ctx *ctx) {
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     cudaFree(ctx->dFlags); cudaFree(ctx->dCount);
     cudaFreeHost(ctx->hFlags); cudaFreeHost(ctx->hCount); cudaFreeHost(ctx->hMarked);
+    for (auto &L : ctx->lanes) {
+        for (int k = 0; k < 2; k++) { if (L.pin[k]) cudaFreeHost(L.pin[k]); if (L.ev[k]) cudaEventDestroy(L.ev[k]); }
+        if (L.s) cudaStreamDestroy(L.s);
+    }
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->upStream) cudaStreamDestroy(ctx->upStream);
     if (ctx->downStream) cudaStreamDestroy(ctx->downStream);
@@ -431,8 +435,8 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     TRY(devAlloc(ctx, &ctx->neighbour, f));
     TRY(devAlloc(ctx, &ctx->bCoupled, b));
     TRY(devAlloc(ctx, &ctx->bEmpty, b));
-    CK(cudaMemcpyAsync(ctx->owner, owner, (size_t)(f + b) * 4, cudaMemcpyDefault, ctx->stream));
-    if (f) CK(cudaMemcpyAsync(ctx->neighbour, neighbour, (size_t)f * 4, cudaMemcpyDefault, ctx->stream));
+    TRY(uploadAuto(ctx, ctx->owner, owner, (size_t)(f + b) * 4));
+    if (f) TRY(uploadAuto(ctx, ctx->neighbour, neighbour, (size_t)f * 4));
     if (b) CK(cudaMemcpyAsync(ctx->bCoupled, coupled.data(), (size_t)b, cudaMemcpyHostToDevice, ctx->stream));
     if (b) CK(cudaMemcpyAsync(ctx->bEmpty, emptyFace.data(), (size_t)b, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -496,7 +500,7 @@ AMR_API int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_
     TRY(sellBuildFromCsr(ctx, ctx->pc, p, dOff, dIdx));
     devFree(ctx, &ctx->bndPoint);
     TRY(devAlloc(ctx, &ctx->bndPoint, p));
-    if (p) CK(cudaMemcpyAsync(ctx->bndPoint, bndPoint, (size_t)p, cudaMemcpyDefault, ctx->stream));
+    if (p) TRY(uploadAuto(ctx, ctx->bndPoint, bndPoint, (size_t)p));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->havePoints = true;
     ctx->pcClassDirty = true; ctx->balancedLocal = -1;
@@ -545,8 +549,8 @@ AMR_API int amr_mesh_set_edges(amr_ctx *ctx, int64_t nEdges, const int32_t *edge
     devFree(ctx, &ctx->bndEdge); devFree(ctx, &ctx->edgePts);
     TRY(devAlloc(ctx, &ctx->bndEdge, nEdges)); TRY(devAlloc(ctx, &ctx->edgePts, 2 * nEdges));
     if (nEdges) {
-        CK(cudaMemcpyAsync(ctx->bndEdge, bndEdge, (size_t)nEdges, cudaMemcpyDefault, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->edgePts, edgePoints, (size_t)nEdges * 8, cudaMemcpyDefault, ctx->stream));
+        TRY(uploadAuto(ctx, ctx->bndEdge, bndEdge, (size_t)nEdges));
+        TRY(uploadAuto(ctx, ctx->edgePts, edgePoints, (size_t)nEdges * 8));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     TRY(growFlagPool(ctx, nEdges + 16));
@@ -568,7 +572,7 @@ AMR_API int amr_mesh_set_faces(amr_ctx *ctx, const int32_t *faceOff, const int32
     CK(cudaStreamSynchronize(ctx->stream));
     if (nnz < 0) FAIL(AMR_ERR_ARG, "amr_mesh_set_faces: bad CSR");
     TRY(devAlloc(ctx, &ctx->facePts, nnz));
-    if (nnz) CK(cudaMemcpyAsync(ctx->facePts, facePts, (size_t)nnz * 4, cudaMemcpyDefault, ctx->stream));
+    if (nnz) TRY(uploadAuto(ctx, ctx->facePts, facePts, (size_t)nnz * 4));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->haveFaces = true;
     return AMR_OK;
@@ -643,11 +647,11 @@ AMR_API int amr_mesh_set_geometry(amr_ctx *ctx, const double *weights, const dou
     devFree(ctx, &ctx->grad); devFree(ctx, &ctx->xbf);
     TRY(devAlloc(ctx, &ctx->gWeights, nf)); TRY(devAlloc(ctx, &ctx->gSf, 3 * nf)); TRY(devAlloc(ctx, &ctx->gMagSf, nf));
     TRY(devAlloc(ctx, &ctx->gDelta, nf)); TRY(devAlloc(ctx, &ctx->gV, n)); TRY(devAlloc(ctx, &ctx->grad, 3 * n)); TRY(devAlloc(ctx, &ctx->xbf, b));
-    CK(cudaMemcpyAsync(ctx->gWeights, weights, (size_t)nf * 8, cudaMemcpyDefault, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->gSf, Sf, (size_t)nf * 24, cudaMemcpyDefault, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->gMagSf, magSf, (size_t)nf * 8, cudaMemcpyDefault, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->gDelta, nonOrthDeltaCoeffs, (size_t)nf * 8, cudaMemcpyDefault, ctx->stream));
-    if (n) CK(cudaMemcpyAsync(ctx->gV, V, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
+    TRY(uploadAuto(ctx, ctx->gWeights, weights, (size_t)nf * 8));
+    TRY(uploadAuto(ctx, ctx->gSf, Sf, (size_t)nf * 24));
+    TRY(uploadAuto(ctx, ctx->gMagSf, magSf, (size_t)nf * 8));
+    TRY(uploadAuto(ctx, ctx->gDelta, nonOrthDeltaCoeffs, (size_t)nf * 8));
+    if (n) TRY(uploadAuto(ctx, ctx->gV, V, (size_t)n * 8));
     // cell -> faces SELL, rows ascending in face label
     sellFree(ctx, ctx->cf);
     int32_t *deg = nullptr, *cursor = nullptr;
@@ -675,11 +679,11 @@ AMR_API int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t
     if (!cellLevel) FAIL(AMR_ERR_ARG, "amr_levels_set: cellLevel is null");
     int64_t n = ctx->n, p = ctx->p;
     if (!ctx->lvl) { TRY(devAlloc(ctx, &ctx->lvl, n)); TRY(devAlloc(ctx, &ctx->lvl8, n + 16)); TRY(devAlloc(ctx, &ctx->parentIdx, n)); }
-    if (n) CK(cudaMemcpyAsync(ctx->lvl, cellLevel, (size_t)n * 4, cudaMemcpyDefault, ctx->stream));
+    if (n) TRY(uploadAuto(ctx, ctx->lvl, cellLevel, (size_t)n * 4));
     if (n) LAUNCH(k_lvl_to_u8, gridFor(n), kThreads, n, ctx->lvl, ctx->lvl8);
     if (pointLevel && p) {
         if (!ctx->pointLevel) TRY(devAlloc(ctx, &ctx->pointLevel, p));
-        CK(cudaMemcpyAsync(ctx->pointLevel, pointLevel, (size_t)p * 4, cudaMemcpyDefault, ctx->stream));
+        TRY(uploadAuto(ctx, ctx->pointLevel, pointLevel, (size_t)p * 4));
     }
     ctx->haveHistory = false;
     if (visibleCells) {
@@ -707,7 +711,7 @@ AMR_API int amr_protected_cells_set(amr_ctx *ctx, const uint8_t *protectedCell) 
     ctx->anyProtCached = -1;
     if (!protectedCell) { devFree(ctx, &ctx->protCell); return AMR_OK; }
     if (!ctx->protCell) TRY(devAlloc(ctx, &ctx->protCell, ctx->n + 16));
-    if (ctx->n) CK(cudaMemcpyAsync(ctx->protCell, protectedCell, (size_t)ctx->n, cudaMemcpyDefault, ctx->stream));
+    if (ctx->n) TRY(uploadAuto(ctx, ctx->protCell, protectedCell, (size_t)ctx->n));
     CK(cudaStreamSynchronize(ctx->stream));
     return AMR_OK;
 }
@@ -1846,8 +1850,8 @@ AMR_API int amr_mesh_set_ls_vectors(amr_ctx *ctx, const double *pVectors, const 
     const int64_t f = ctx->f, nf = ctx->f + ctx->b;
     devFree(ctx, &ctx->lsP); devFree(ctx, &ctx->lsN);
     TRY(devAlloc(ctx, &ctx->lsP, 3 * nf)); TRY(devAlloc(ctx, &ctx->lsN, 3 * f));
-    if (nf) CK(cudaMemcpyAsync(ctx->lsP, pVectors, (size_t)nf * 24, cudaMemcpyDefault, ctx->stream));
-    if (f) CK(cudaMemcpyAsync(ctx->lsN, nVectors, (size_t)f * 24, cudaMemcpyDefault, ctx->stream));
+    if (nf) TRY(uploadAuto(ctx, ctx->lsP, pVectors, (size_t)nf * 24));
+    if (f) TRY(uploadAuto(ctx, ctx->lsN, nVectors, (size_t)f * 24));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->haveLs = true;
     return AMR_OK;

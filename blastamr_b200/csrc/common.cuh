@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 #include <unordered_map>
+#include <atomic>
+#include <thread>
 
 #include "amr_b200.h"
 
@@ -49,6 +51,8 @@ struct amr_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t upStream = nullptr, downStream = nullptr;   // host<->host field mapping: both PCIe directions at once
+    struct UploadLane { void *pin[2] = {nullptr, nullptr}; cudaStream_t s = nullptr; cudaEvent_t ev[2] = {nullptr, nullptr}; };
+    std::vector<UploadLane> lanes;   // pageable -> pinned -> device staging lanes (bulkUpload)
     bool ownStream = true;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -217,6 +221,65 @@ static inline bool isDevicePtr(const void *ptr) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// ---- bulk upload of pageable host arrays -------------------------------------------------
+// cudaMemcpy from pageable memory moves ~12 GB/s (one driver thread bouncing through pinned buffers); the mesh
+// addressing handed over after every topology change is several GB.  Here kUploadLanes host threads copy interleaved
+// 16 MiB chunks into their own double-buffered pinned staging and queue the DMA on their own stream, so the host
+// memcpy runs at multi-core bandwidth and overlaps the PCIe transfer.  Synchronous: complete on return.
+constexpr int kUploadLanes = 6;
+constexpr size_t kUploadChunk = (size_t)16 << 20;
+static int bulkUpload(amr_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (ctx->lanes.empty()) {
+        ctx->lanes.resize(kUploadLanes);
+        for (auto &L : ctx->lanes) {
+            for (int k = 0; k < 2; k++) {
+                if (cudaMallocHost(&L.pin[k], kUploadChunk) != cudaSuccess) { cudaGetLastError(); L.pin[k] = nullptr; }
+                cudaEventCreateWithFlags(&L.ev[k], cudaEventDisableTiming);
+            }
+            cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking);
+        }
+    }
+    bool ok = true;
+    for (auto &L : ctx->lanes) ok = ok && L.pin[0] && L.pin[1] && L.s && L.ev[0] && L.ev[1];
+    if (!ok) {          // no pinned memory to be had: plain copy
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return AMR_OK;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));       // whatever still uses dst is done
+    std::atomic<int> err{0};
+    auto work = [&](int t) {
+        if (cudaSetDevice(ctx->device) != cudaSuccess) { err = 1; return; }
+        amr_ctx::UploadLane &L = ctx->lanes[(size_t)t];
+        int slot = 0;
+        for (size_t off = (size_t)t * kUploadChunk; off < bytes; off += (size_t)kUploadLanes * kUploadChunk) {
+            const size_t len = bytes - off < kUploadChunk ? bytes - off : kUploadChunk;
+            if (cudaEventSynchronize(L.ev[slot]) != cudaSuccess) { err = 1; return; }     // the slot's previous DMA has drained
+            memcpy(L.pin[slot], (const char *)src + off, len);
+            if (cudaMemcpyAsync((char *)dst + off, L.pin[slot], len, cudaMemcpyHostToDevice, L.s) != cudaSuccess) { err = 1; return; }
+            cudaEventRecord(L.ev[slot], L.s);
+            slot ^= 1;
+        }
+        if (cudaStreamSynchronize(L.s) != cudaSuccess) err = 1;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < kUploadLanes; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    if (err) { ctx->err = "bulk upload failed"; cudaGetLastError(); return AMR_ERR_CUDA; }
+    return AMR_OK;
+}
+// host or device source -> device; large pageable sources take the staged multi-thread path
+static int uploadAuto(amr_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return AMR_OK;
+    if (bytes >= ((size_t)32 << 20)) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, src) != cudaSuccess) { cudaGetLastError(); a.type = cudaMemoryTypeUnregistered; }
+        if (a.type == cudaMemoryTypeUnregistered) return bulkUpload(ctx, dst, src, bytes);
+    }
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    return AMR_OK;
+}
+
 // ---- staging arena ---------------------------------------------------------------------
 static void arenaReset(amr_ctx *ctx) {
     if (ctx->arena.size() > 1) {
@@ -253,7 +316,7 @@ static int stageIn(amr_ctx *ctx, const T *ptr, int64_t count, const T **dev) {
     if (isDevicePtr(ptr)) { *dev = ptr; return AMR_OK; }
     void *q;
     TRY(arenaAlloc(ctx, &q, sizeof(T) * (size_t)(count > 0 ? count : 1)));
-    if (count > 0) CK(cudaMemcpyAsync(q, ptr, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    if (count > 0) TRY(uploadAuto(ctx, q, ptr, sizeof(T) * (size_t)count));
     ctx->hostTouched = true;
     *dev = (const T *)q;
     return AMR_OK;
@@ -276,7 +339,7 @@ static int stageInOut(amr_ctx *ctx, T *ptr, int64_t count, T **dev) {
     if (isDevicePtr(ptr)) { *dev = ptr; return AMR_OK; }
     void *q;
     TRY(arenaAlloc(ctx, &q, sizeof(T) * (size_t)(count > 0 ? count : 1)));
-    if (count > 0) CK(cudaMemcpyAsync(q, ptr, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    if (count > 0) TRY(uploadAuto(ctx, q, ptr, sizeof(T) * (size_t)count));
     *dev = (T *)q;
     ctx->outs.push_back({(void *)ptr, q, sizeof(T) * (size_t)(count > 0 ? count : 0)});
     return AMR_OK;
