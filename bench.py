@@ -322,6 +322,7 @@ def main():
                 touched[mesh.owner[q.start:q.start + q.size]] = True
         if touched[cells_first].any():
             raise SystemExit("bench: refinement reaches a processor patch; the per-rank topology engine cannot keep patches matched")
+    del mesh                         # M0's host arrays (~10 GB at 64 M cells) are resident on the device now; M1 is built next
     cell_map_h = octree.refine(cells_first.copy())
     mesh1 = octree.build()
     n1, f1, b1, p1 = mesh1.n, mesh1.f, mesh1.b, mesh1.p
