@@ -48,5 +48,25 @@ def load_reference_mesh(case: str) -> PolyMesh:
                     visible=np.full(n, -1, np.int32), split_parent=np.zeros(0, np.int32))
 
 
+def load_reference_faces(case: str) -> PolyMesh:
+    """A reference fixture that ships owner / neighbour / boundary only (poly3D): a mesh for the face-list kernels
+    (estimators, buffer layers, 2:1 closure on a level-0 mesh, patch protection); no point addressing, no geometry."""
+    z = np.load(GOLDEN / f"{case}_faces.npz")
+    owner, nei = z["owner"].astype(np.int32), z["neighbour"].astype(np.int32)
+    f, nf = len(nei), len(owner)
+    n = int(max(owner.max(), nei.max())) + 1            # the last cells own no face: every face of theirs has a lower owner
+    patches = [Patch(str(nm), PATCH_EMPTY if str(ty) == "empty" else PATCH_WALL, int(st), int(sz))
+               for nm, ty, st, sz in zip(z["patch_names"], z["patch_types"], z["patch_start"], z["patch_size"])]
+    return PolyMesh(n=n, f=f, b=nf - f, p=0, owner=owner, neighbour=nei, patches=patches, cc=None, vol=None,
+                    pc_off=None, pc_cells=None, cp_off=None, cp_pts=None, bnd_point=None,
+                    cell_level=np.zeros(n, np.int32), point_level=None, visible=None, split_parent=np.zeros(0, np.int32))
+
+
+def poly3d_field(n: int) -> np.ndarray:
+    """deterministic field over cell labels (the fixture has no cell centres): smooth in the label with a front"""
+    c = np.arange(n, dtype=np.float64)
+    return 1.0 + 0.5 * (1.0 + np.tanh((c - 0.45 * n) / (0.02 * n))) + 0.05 * np.sin(c * 0.013)
+
+
 def golden():
     return np.load(GOLDEN / "oracle_golden.npz")

@@ -86,6 +86,22 @@ def convert(case):
     print(case, "cells", owner.max() + 1, "faces", len(owner), "internal", len(nei), "points", len(pts), bnd)
 
 
+def convert_faces_only(case):
+    """poly3D ships without faces/points in the reference checkout (.MISSING_LARGE_BLOBS): owner / neighbour /
+    boundary are enough for every face-list kernel"""
+    pm = REF / case / "constant" / "polyMesh"
+    owner = read_labels(pm / "owner")
+    nei = read_labels(pm / "neighbour")
+    bnd = read_boundary(pm / "boundary")
+    f = min(b[2] for b in bnd)                      # foam-extend writes neighbour with nFaces entries, -1 on boundary faces
+    assert (nei[f:] == -1).all() and (nei[:f] >= 0).all() and (owner[:f] < nei[:f]).all()
+    nei = nei[:f]
+    np.savez_compressed(HERE / f"{case}_faces.npz", owner=owner, neighbour=nei,
+                        patch_names=np.array([b[0] for b in bnd]), patch_types=np.array([b[1] for b in bnd]),
+                        patch_start=np.array([b[2] for b in bnd], np.int32), patch_size=np.array([b[3] for b in bnd], np.int32))
+    print(case, "cells", owner.max() + 1, "faces", len(owner), "internal", len(nei), bnd)
+
+
 def golden_outputs():
     from tests.fixtures import load_reference_mesh
     from tests import amr_cases as cases
@@ -115,4 +131,5 @@ if __name__ == "__main__":
     if REF.exists():
         for c in ("hex3D", "hex2D"):
             convert(c)
+        convert_faces_only("poly3D")
     golden_outputs()

@@ -157,3 +157,9 @@ def test_full_size_driver_on_the_oracle():
     that file agree with the oracle, so at 400^3 they can stand in for it"""
     import tests.test_gpu_full_size as T
     assert T.run(cases.OracleBackend(), 24) > 0
+
+
+def test_poly3D_gpu_driver_on_the_oracle():
+    """tests/test_zz_gpu_reference_poly3d.py answered by the oracle: checks the test code itself"""
+    import tests.test_zz_gpu_reference_poly3d as T
+    T.test_poly3D_fixture(cases.OracleBackend(), O)

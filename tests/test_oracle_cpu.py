@@ -320,3 +320,36 @@ def test_poly_point_layers_do_not_depend_on_the_decomposition():
             glob[l.cell_global] = r
         marks.append(glob)
     assert marks[0].sum() > 0 and np.array_equal(marks[0], marks[1]) and np.array_equal(marks[0], marks[2])
+
+
+def test_reference_poly3D_fixture_face_kernels_vs_numpy():
+    """the reference's polyhedral fixture tests/testCases/poly3D (69 407 cells, 4-25 face neighbours per cell; owner /
+    neighbour / boundary only): estimators, buffer layers and the 2:1 closure of the oracle against the numpy
+    restatements from the definitions"""
+    from tests.fixtures import load_reference_faces, poly3d_field
+    m = load_reference_faces("poly3D")
+    assert (m.n, m.f, m.b) == (69407, 437334, 28778)
+    assert (m.owner[:m.f] < m.neighbour).all()                      # upper-triangular order
+    w = O.World([m])
+    x = poly3d_field(m.n)
+    assert np.array_equal(w.estimate("delta", [x])[0], NP.delta(m, x))
+    assert np.array_equal(w.estimate("codedDelta", [x])[0], NP.delta(m, x, clamp=None))
+    assert np.array_equal(w.estimate("scaledDelta", [x], min_val=1e-3, offset=0.25)[0], NP.scaled_delta(m, x, 1e-3, 0.25))
+    e = w.estimate("delta", [x])
+    w.normalize(e, 0.45, 1e15, 0.05, 1e15)
+    assert 0 < (e[0] == 1).sum() < m.n // 2
+    marked = (e[0] == 1)
+    rc, rs, _ = w.hex_select_refine(e, 2, 2)
+    assert np.array_equal(rc[0].astype(bool), NP.grow(m, NP.grow(m, marked)))
+    assert np.array_equal(rs[0], rc[0])                              # level-0 mesh: nothing for the 2:1 closure to add
+    # closure on artificial levels that are 2:1 balanced by construction (level = min over a 2-ring of a seed pattern)
+    seed = (np.arange(m.n) % 97 == 0)
+    lv = NP.grow(m, seed).astype(np.int32) + NP.grow(m, NP.grow(m, seed)).astype(np.int32)   # 0 / 1 / 2, steps of 1
+    assert np.abs(lv[m.owner[:m.f]] - lv[m.neighbour]).max() <= 1
+    m.cell_level = lv
+    w = O.World([m])
+    flags = ((np.arange(m.n) % 11 == 0) & (lv == 2)).astype(np.uint8)
+    got = flags.copy()
+    w.consistent_refinement([got], True)
+    assert np.array_equal(got.astype(bool), NP.closure_refine(m, flags.astype(bool))[0])
+    assert got.sum() > flags.sum()
