@@ -34,6 +34,13 @@
  * replace syncTools::* / reduce() calls that are already collective).
  *
  * There is no CPU fallback: without a CUDA device amr_ctx_create fails.
+ *
+ * Environment (read at amr_ctx_create / amr_comm_init; tuning and diagnosis only, results never change):
+ *   AMR_B200_HALO=nccl            processor-patch swaps and reductions over NCCL instead of NVLink peer memory
+ *   AMR_B200_NO_PIPELINE=1        direct kernels instead of the TMA-staged ones
+ *   AMR_B200_PUSH_FRACTION=a/b    marked fraction below which a buffer layer / 2:1 sweep takes its sparse form
+ *                                 (default 1/4; 0 = always dense)
+ *   AMR_B200_PUSH_MIN_CELLS=n     mesh size below which the sparse forms are not tried (default 65536)
  */
 #ifndef AMR_B200_H
 #define AMR_B200_H
