@@ -25,7 +25,9 @@ static bool pipeOk(const amr_ctx *ctx, const Sell &S) {
 
 template <class K, class... Args>
 static int launchPipe(amr_ctx *ctx, K kern, const Sell &S, Args... args) {
-    SellView V{S.sliceOff, S.col, S.rows, S.slices, S.maxTileInts, S.sliceGhost};
+    // meshes without processor patches have no cell that waits for a boundary fix-up: no per-slice flag to fetch (the
+    // flag load sits right before the tile wait and cost ~20 % of kp_estimate's stall samples, profiles/r1_ncu_full.csv)
+    SellView V{S.sliceOff, S.col, S.rows, S.slices, S.maxTileInts, ctx->nCoupled > 0 ? S.sliceGhost : (const u8 *)nullptr};
     const size_t smem = pipeSmemBytes(V.stageInts);
     const void *key = (const void *)kern;
     auto it = ctx->occCache.find(key);
