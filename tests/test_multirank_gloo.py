@@ -109,3 +109,68 @@ def test_two_rank_gloo_matches_serial_oracle():
         assert np.array_equal(rs[0][cg].astype(bool), flags_r)
         seen += len(cg)
     assert seen == g.n
+
+
+def _point_worker(rank, world, procs, port, q):
+    import torch
+    import torch.distributed as dist
+    from blastamr_b200 import mesh as M
+    from blastamr_b200.halo import point_plan, sync_points_or
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        oc = cases.poly_balanced_octree(O, n0=8, max_level=1)
+        g = oc.build(geometry=True, faces=True)
+        loc = M.decompose(g, M.simple_ranks(g, (1, 1, 1), procs), world)[rank]
+        plan = point_plan(loc)
+        marked = np.zeros(g.n, bool)
+        marked[::37] = True                                  # the same global marking on every rank
+        mc = marked[loc.cell_global]
+        # extendMarkedCellsAcrossPoints (fvMeshRefiner.C:924-977): cells -> points, sync, points -> cells
+        pts_of = np.repeat(np.arange(loc.p), np.diff(loc.pc_off))
+        pflag = np.zeros(loc.p, np.uint8)
+        np.logical_or.at(pflag, pts_of, mc[loc.pc_cells])
+        t = torch.from_numpy(pflag)
+        rounds = sync_points_or(t, plan)
+        pflag = t.numpy().astype(bool)
+        out = mc.copy()
+        out[loc.pc_cells[pflag[pts_of]]] = True
+        q.put((rank, loc.cell_global.copy(), out, rounds))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_four_rank_point_sync_reaches_edge_points():
+    """the point sync protocol of syncPointsOr (pairwise OR over processor-patch point lists until stable) on a
+    2 x 2 split, whose centre line is shared by FOUR ranks, two of which share no face: one point layer grown from a
+    global marking must equal the serial growth"""
+    import torch.multiprocessing as mp
+    from oracle import oracle as O
+    from blastamr_b200 import mesh as M
+    world, procs = 4, (2, 2, 1)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_point_worker, args=(r, world, procs, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = cases.poly_balanced_octree(O, n0=8, max_level=1).build(faces=True)
+    marked = np.zeros(g.n, bool)
+    marked[::37] = True
+    pts_of = np.repeat(np.arange(g.p), np.diff(g.pc_off))
+    pf = np.zeros(g.p, bool)
+    np.logical_or.at(pf, pts_of, marked[g.pc_cells])
+    ref = marked.copy()
+    ref[g.pc_cells[pf[pts_of]]] = True
+    glob = np.zeros(g.n, bool)
+    for rank, cg, out, rounds in res:
+        glob[cg] = out
+        assert rounds >= 2                      # at least one exchange plus the round that sees no change
+    assert np.array_equal(glob, ref) and ref.sum() > marked.sum()
