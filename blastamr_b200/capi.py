@@ -77,6 +77,7 @@ _SIGS = {
     "amr_history_clusters": (C.c_int, [C.c_void_p] * 6),
     "amr_history_constrain_decomposition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_proc_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "amr_synchronize": (C.c_int, [C.c_void_p]),
     "amr_launch_count": (C.c_int64, [C.c_void_p]),
     "amr_device_bytes": (C.c_int64, [C.c_void_p]),
 }
@@ -161,6 +162,10 @@ class Context:
 
     def comm_init(self, nranks: int, rank: int, uid: bytes):
         self._ck(self.L.amr_comm_init(self._h, nranks, rank, C.create_string_buffer(uid, 128)))
+
+    def synchronize(self):
+        """wait for the context's stream; raises what stream-ordered calls could not report (peer timeout)"""
+        self._ck(self.L.amr_synchronize(self._h))
 
     @property
     def launches(self) -> int:

@@ -191,83 +191,127 @@ AMR_API int64_t amr_device_bytes(const amr_ctx *ctx) { return ctx ? ctx->devByte
 
 // ---- NVLink peer-memory transport (p2p.cuh) ----------------------------------------------------------
 
-// all ranks map each other's region; NCCL is only the transport for the 64-byte IPC handles
+// all ranks map each other's region; NCCL is only the transport for the 64-byte IPC handles.  Every rank reaches
+// the "everybody or nobody" all-reduce whatever failed locally, so no rank is left blocked in NCCL.
 static int peerSetup(amr_ctx *ctx) {
+    if (ctx->nranks < 2) return AMR_OK;
     const char *mode = getenv("AMR_B200_HALO");
-    if (mode && strcmp(mode, "nccl") == 0) return AMR_OK;
-    if (ctx->nranks < 2 || ctx->nranks > kMaxRanks) return AMR_OK;
+    {
+        const char *ts = getenv("AMR_B200_PEER_TIMEOUT_S");
+        double sec = ts ? atof(ts) : 20.0;
+        if (!(sec > 0.0)) sec = 20.0;
+        ctx->peerTimeoutNs = (unsigned long long)(sec * 1e9);
+    }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    static_assert(offsetof(P2PRegionHeader, error) == kPeerErrOffset, "kPeerErrOffset");
+    // scratch of the set-up collectives: the one allocation whose failure cannot be agreed on
+    char *scratch = nullptr;
+    CK(cudaMalloc((void **)&scratch, (size_t)64 * (ctx->nranks + 1)));
+    char *dSend = scratch, *dAll = scratch + 64;
     int ok = 1;
-    if (cudaMalloc((void **)&ctx->region, (size_t)kRegionBytes) != cudaSuccess) { cudaGetLastError(); ctx->region = nullptr; ok = 0; }
+    if ((mode && strcmp(mode, "nccl") == 0) || ctx->nranks > kMaxRanks) ok = 0;
+    if (ok && cudaMalloc((void **)&ctx->region, (size_t)kRegionBytes) != cudaSuccess) { cudaGetLastError(); ctx->region = nullptr; ok = 0; }
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
     if (ok) {
-        CK(cudaMemsetAsync(ctx->region, 0, (size_t)kRegionBytes, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (cudaIpcGetMemHandle(&mine, ctx->region) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        if (cudaMemsetAsync(ctx->region, 0, (size_t)kRegionBytes, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaIpcGetMemHandle(&mine, ctx->region) != cudaSuccess) {
+            cudaGetLastError(); ok = 0;
+        }
     }
-    char *dSend = nullptr, *dAll = nullptr;
-    CK(cudaMalloc((void **)&dSend, 64));
-    CK(cudaMalloc((void **)&dAll, (size_t)64 * ctx->nranks));
-    CK(cudaMemcpyAsync(dSend, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
-    NCK(ncclAllGather(dSend, dAll, 64, ncclUint8, ctx->comm, ctx->stream));
     std::vector<cudaIpcMemHandle_t> all((size_t)ctx->nranks);
-    CK(cudaMemcpyAsync(all.data(), dAll, (size_t)64 * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = AMR_OK;
+    if (cudaMemcpyAsync(dSend, &mine, 64, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    if (ncclAllGather(dSend, dAll, 64, ncclUint8, ctx->comm, ctx->stream) != ncclSuccess) { ctx->err = "peerSetup: ncclAllGather failed"; rc = AMR_ERR_NCCL; }
+    if (rc == AMR_OK && (cudaMemcpyAsync(all.data(), dAll, (size_t)64 * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                         cudaStreamSynchronize(ctx->stream) != cudaSuccess)) { cudaGetLastError(); ok = 0; }
     ctx->peerHost.assign((size_t)ctx->nranks, nullptr);
-    for (int r = 0; r < ctx->nranks && ok; r++) {
+    for (int r = 0; r < ctx->nranks && ok && rc == AMR_OK; r++) {
         if (r == ctx->rank) { ctx->peerHost[(size_t)r] = ctx->region; continue; }
         void *p = nullptr;
         if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
         ctx->peerHost[(size_t)r] = (char *)p;
     }
+    if (ok && rc == AMR_OK) {
+        if (cudaMalloc((void **)&ctx->peerDev, sizeof(char *) * (size_t)ctx->nranks) != cudaSuccess ||
+            cudaMemcpy(ctx->peerDev, ctx->peerHost.data(), sizeof(char *) * (size_t)ctx->nranks, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMalloc((void **)&ctx->redVal, 16) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
     // everybody or nobody
-    CK(cudaMemcpyAsync(ctx->dFlags + 5, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    NCK(ncclAllReduce(ctx->dFlags + 5, ctx->dFlags + 5, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
-    CK(cudaMemcpyAsync(&ok, ctx->dFlags + 5, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(dSend); cudaFree(dAll);
-    if (!ok) {
-        for (int r = 0; r < ctx->nranks; r++)
+    if (rc == AMR_OK) {
+        int *word = (int *)scratch;
+        if (cudaMemcpyAsync(word, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { cudaGetLastError(); rc = AMR_ERR_CUDA; ctx->err = "peerSetup: copy failed"; }
+        else if (ncclAllReduce(word, word, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream) != ncclSuccess) { rc = AMR_ERR_NCCL; ctx->err = "peerSetup: ncclAllReduce failed"; }
+        else if (cudaMemcpyAsync(&ok, word, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                 cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); rc = AMR_ERR_CUDA; ctx->err = "peerSetup: copy failed"; }
+    }
+    cudaFree(scratch);
+    if (rc != AMR_OK || !ok) {
+        for (int r = 0; r < (int)ctx->peerHost.size(); r++)
             if (r != ctx->rank && ctx->peerHost[(size_t)r]) cudaIpcCloseMemHandle(ctx->peerHost[(size_t)r]);
         ctx->peerHost.clear();
-        return AMR_OK;      // NCCL path stays
+        if (ctx->peerDev) { cudaFree(ctx->peerDev); ctx->peerDev = nullptr; }
+        if (ctx->redVal) { cudaFree(ctx->redVal); ctx->redVal = nullptr; }
+        if (ctx->region) { cudaFree(ctx->region); ctx->region = nullptr; }
+        return rc;          // AMR_OK: the NCCL path stays
     }
-    CK(cudaMalloc((void **)&ctx->peerDev, sizeof(char *) * (size_t)ctx->nranks));
-    CK(cudaMemcpy(ctx->peerDev, ctx->peerHost.data(), sizeof(char *) * (size_t)ctx->nranks, cudaMemcpyHostToDevice));
-    CK(cudaMalloc((void **)&ctx->redVal, 16));
     ctx->haloPlan = new HaloPlan();
     ctx->usePeer = true;
     return AMR_OK;
 }
 
-// per-mesh plan: where my patch ranges land in each neighbour's boundary-face array
+// Per-mesh plan: where my patch ranges land in each neighbour's boundary-face array.  Collective over ALL ranks of
+// the communicator (amr_mesh_set after a topology change is): the ranks agree (all-reduce) whether this mesh uses
+// the peer transport or NCCL -- one rank with more patches than the plan holds, or a boundary that does not fit a
+// parity buffer, moves everybody to NCCL -- and resynchronise their exchange epochs, so that a rank that had no
+// processor patch on the previous mesh cannot wait on a stale arrival word.
 static int peerPlan(amr_ctx *ctx) {
     ctx->havePlan = false;
-    if (!ctx->usePeer || ctx->nCoupled == 0) return AMR_OK;
+    if (!ctx->usePeer) return AMR_OK;
     HaloPlan &P = *(HaloPlan *)ctx->haloPlan;
     P.nPatch = 0; P.prefix[0] = 0;
-    int tooMany = 0;
+    int ok = 1;
+    std::vector<int32_t> mine, nbrs;                 // (offset, size) per processor patch, ALL of them
     for (const Patch &q : ctx->patches) {
         if (q.type != AMR_PATCH_PROCESSOR || q.size == 0) continue;
-        if (P.nPatch >= 32) { tooMany = 1; break; }
-        const int k = P.nPatch++;
-        P.nbr[k] = q.nbr; P.offMine[k] = q.start - (int)ctx->f; P.size[k] = q.size; P.prefix[k + 1] = P.prefix[k] + q.size;
+        mine.push_back(q.start - (int32_t)ctx->f); mine.push_back(q.size); nbrs.push_back(q.nbr);
+        if (q.nbr < 0 || q.nbr >= ctx->nranks || q.nbr == ctx->rank) FAIL(AMR_ERR_ARG, "amr_mesh_set: processor patch with a bad neighbour rank");
     }
-    if (tooMany) return AMR_OK;
+    const int np = (int)nbrs.size();
+    if (np > 32) ok = 0;
+    if (ctx->b * 24 > kHaloCap) ok = 0;             // the widest payload (vector field) must fit one parity buffer
+    std::vector<int32_t> theirs((size_t)(2 * np > 0 ? 2 * np : 1), 0);
     int32_t *dMine = nullptr, *dTheirs = nullptr;
-    CK(cudaMalloc((void **)&dMine, 32 * 4));
-    CK(cudaMalloc((void **)&dTheirs, 32 * 4));
-    CK(cudaMemcpyAsync(dMine, P.offMine, 32 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    void *q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(2 * np + 4) * 4)); dMine = (int32_t *)q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(2 * np + 4) * 4)); dTheirs = (int32_t *)q;
+    if (np) CK(cudaMemcpyAsync(dMine, mine.data(), (size_t)2 * np * 4, cudaMemcpyHostToDevice, ctx->stream));
     NCK(ncclGroupStart());
-    for (int k = 0; k < P.nPatch; k++) {
-        NCK(ncclSend(dMine + k, 1, ncclInt32, P.nbr[k], ctx->comm, ctx->stream));
-        NCK(ncclRecv(dTheirs + k, 1, ncclInt32, P.nbr[k], ctx->comm, ctx->stream));
+    for (int k = 0; k < np; k++) {
+        NCK(ncclSend(dMine + 2 * k, 2, ncclInt32, nbrs[(size_t)k], ctx->comm, ctx->stream));
+        NCK(ncclRecv(dTheirs + 2 * k, 2, ncclInt32, nbrs[(size_t)k], ctx->comm, ctx->stream));
     }
     NCK(ncclGroupEnd());
-    CK(cudaMemcpyAsync(P.offTheirs, dTheirs, 32 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (np) CK(cudaMemcpyAsync(theirs.data(), dTheirs, (size_t)2 * np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    // agreement word: [0] = min(ok), [1] = max(halo epoch), [2] = max(reduction epoch)   (as -min of negatives)
+    int32_t agree[3] = {ok, -(int32_t)(ctx->haloEpoch & 0x3fffffffu), -(int32_t)(ctx->redEpoch & 0x3fffffffu)};
+    int32_t *dAgree = dMine + 2 * np;
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(dMine); cudaFree(dTheirs);
+    for (int k = 0; k < np; k++)
+        if (theirs[(size_t)2 * k + 1] != mine[(size_t)2 * k + 1]) agree[0] = 0;      // the two sides of a patch disagree on its size
+    CK(cudaMemcpyAsync(dAgree, agree, sizeof(agree), cudaMemcpyHostToDevice, ctx->stream));
+    NCK(ncclAllReduce(dAgree, dAgree, 3, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+    CK(cudaMemcpyAsync(agree, dAgree, sizeof(agree), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // common epochs: above every value any rank has used (stale arrival words are below them)
+    ctx->haloEpoch = (unsigned)(-agree[1]) + 2u;
+    ctx->redEpoch = (unsigned)(-agree[2]) + 2u;
+    if (!agree[0]) return AMR_OK;                    // agreed: NCCL transport for this mesh
+    for (int k = 0; k < np; k++) {
+        P.nbr[k] = nbrs[(size_t)k]; P.offMine[k] = mine[(size_t)2 * k]; P.size[k] = mine[(size_t)2 * k + 1];
+        P.offTheirs[k] = theirs[(size_t)2 * k]; P.prefix[k + 1] = P.prefix[k] + P.size[k];
+    }
+    P.nPatch = np;
     ctx->havePlan = true;
     return AMR_OK;
 }
@@ -295,6 +339,8 @@ static int haloExchange(amr_ctx *ctx, const void *send, void *recv, size_t elemB
 // its ghost-free main kernel (haloBegin ... main kernel ... haloEnd ... boundary fix-up): the neighbours' skew and
 // the NVLink latency then hide behind the main kernel.  A rank never pushes exchange k+1 before it unpacked
 // exchange k, so a neighbour can run at most one exchange ahead and the two parity buffers suffice.
+// The epoch advances on EVERY rank of the communicator for every exchange of a collective call, whether or not the
+// rank owns a processor patch, so all ranks stay in lockstep.
 struct HaloToken {
     bool pending = false;
     unsigned epoch = 0;
@@ -304,12 +350,14 @@ struct HaloToken {
 };
 static int haloBegin(amr_ctx *ctx, const void *cells, size_t elemBytes, void *recv, HaloToken *tok, const u8 *minus = nullptr) {
     tok->pending = false;
+    const bool peer = ctx->usePeer && ctx->havePlan;
+    unsigned epoch = 0;
+    if (peer) epoch = ++ctx->haloEpoch;
     if (ctx->nCoupled == 0) return AMR_OK;
     if (!ctx->comm) FAIL(AMR_ERR_STATE, "mesh has processor patches but no communicator (amr_comm_init) and no host-side neighbour values");
     const int64_t b = ctx->b;
-    if (ctx->usePeer && ctx->havePlan && b * (int64_t)elemBytes <= kHaloCap) {
+    if (peer) {
         const HaloPlan &P = *(const HaloPlan *)ctx->haloPlan;
-        const unsigned epoch = ++ctx->haloEpoch;
         const int parity = (int)(epoch & 1u);
         const unsigned g = gridFor(P.prefix[P.nPatch]);
         unsigned *counter = (unsigned *)(ctx->dFlags + 6);
@@ -319,6 +367,7 @@ static int haloBegin(amr_ctx *ctx, const void *cells, size_t elemBytes, void *re
         else if (elemBytes == 8) k_halo_push_cells<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
         else k_halo_push_cells<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
         ctx->launches++;
+        ctx->peerTouched = true;
         tok->pending = true; tok->epoch = epoch; tok->parity = parity; tok->elemBytes = elemBytes; tok->recv = recv;
         return AMR_OK;
     }
@@ -337,10 +386,11 @@ static int haloEnd(amr_ctx *ctx, HaloToken *tok) {
     tok->pending = false;
     const HaloPlan &P = *(const HaloPlan *)ctx->haloPlan;
     const unsigned g = gridFor(P.prefix[P.nPatch]);
-    if (tok->elemBytes == 1) k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv);
-    else if (tok->elemBytes == 4) k_halo_unpack<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv);
-    else if (tok->elemBytes == 8) k_halo_unpack<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv);
-    else k_halo_unpack<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv);
+    const unsigned long long to = ctx->peerTimeoutNs;
+    if (tok->elemBytes == 1) k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv, to);
+    else if (tok->elemBytes == 4) k_halo_unpack<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv, to);
+    else if (tok->elemBytes == 8) k_halo_unpack<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv, to);
+    else k_halo_unpack<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv, to);
     ctx->launches++;
     return AMR_OK;
 }
@@ -359,8 +409,9 @@ static int allReduceWord(amr_ctx *ctx, void *word, int op) {
         const int parity = (int)(epoch & 1u);
         const int is32 = (op == 0);
         k_red_push<<<1, kMaxRanks, 0, ctx->stream>>>(ctx->peerDev, ctx->nranks, ctx->rank, parity, epoch, word, is32);
-        k_red_wait<<<1, kMaxRanks, 0, ctx->stream>>>(ctx->region, ctx->nranks, parity, epoch, op, word, is32);
+        k_red_wait<<<1, kMaxRanks, 0, ctx->stream>>>(ctx->region, ctx->nranks, parity, epoch, op, word, is32, ctx->peerTimeoutNs);
         ctx->launches += 2;
+        ctx->peerTouched = true;
         return AMR_OK;
     }
     if (op == 0) NCK(ncclAllReduce(word, word, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
@@ -370,18 +421,10 @@ static int allReduceWord(amr_ctx *ctx, void *word, int op) {
 }
 
 // read the device flag (after an all-reduce over ranks when a communicator is attached):
-// the reduce(nChanged, sumOp) / returnReduce(bool, orOp) sites of the reference
-#define PEER_ERR_FETCH()                                                                                                  \
-    do {                                                                                                                  \
-        ctx->hFlags[9] = 0;                                                                                               \
-        if (ctx->usePeer)                                                                                                 \
-            CK(cudaMemcpyAsync(ctx->hFlags + 9, ctx->region + offsetof(P2PRegionHeader, error), sizeof(int),             \
-                               cudaMemcpyDeviceToHost, ctx->stream));                                                    \
-    } while (0)
-#define PEER_ERR_CHECK()                                                                                                  \
-    do {                                                                                                                  \
-        if (ctx->hFlags[9]) FAIL(AMR_ERR_STATE, "peer-memory halo swap timed out (a neighbour rank did not enter the same call)"); \
-    } while (0)
+// the reduce(nChanged, sumOp) / returnReduce(bool, orOp) sites of the reference.  Every host round trip also
+// fetches the peer region's error word (peerErrFetch / peerErrCheck in common.cuh).
+#define PEER_ERR_FETCH() TRY(peerErrFetch(ctx))
+#define PEER_ERR_CHECK() TRY(peerErrCheck(ctx))
 
 static int globalFlag(amr_ctx *ctx, int slot, int *value) {
     TRY(allReduceWord(ctx, ctx->dFlags + slot, 0));
@@ -402,6 +445,15 @@ static int globalSum(amr_ctx *ctx, int slot, int64_t *value) {
     return AMR_OK;
 }
 
+AMR_API int amr_synchronize(amr_ctx *ctx) {
+    if (!ctx) return AMR_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    PEER_ERR_FETCH();
+    CK(cudaStreamSynchronize(ctx->stream));
+    PEER_ERR_CHECK();
+    return AMR_OK;
+}
+
 // ============================================================================ mesh state
 
 AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t p, const int32_t *owner,
@@ -410,29 +462,35 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     ENTER();
     if (n < 0 || f < 0 || b < 0 || p < 0 || !owner || (f > 0 && !neighbour) || npatch < 0) FAIL(AMR_ERR_ARG, "amr_mesh_set: bad sizes/pointers");
     if (n >= ((int64_t)1 << 31) - 2 - b) FAIL(AMR_ERR_ARG, "amr_mesh_set: label overflow (n + b must fit int32)");
+    // validate BEFORE the current mesh is released: a failed call leaves the context as it was
+    std::vector<u8> coupled((size_t)(b > 0 ? b : 1), 0), emptyFace((size_t)(b > 0 ? b : 1), 0);
+    std::vector<Patch> patches;
+    int64_t nCoupled = 0;
+    for (int i = 0; i < npatch; i++) {
+        if (!patchStart || !patchSize) FAIL(AMR_ERR_ARG, "amr_mesh_set: patch arrays are null");
+        Patch q{patchStart[i], patchSize[i], patchType ? patchType[i] : 0, patchNbrRank ? patchNbrRank[i] : -1};
+        if (q.size < 0 || q.start < f || (int64_t)q.start + q.size > f + b) FAIL(AMR_ERR_ARG, "amr_mesh_set: patch range outside boundary faces");
+        if (q.type == AMR_PATCH_PROCESSOR) {
+            if (ctx->comm && (q.nbr < 0 || q.nbr >= ctx->nranks || q.nbr == ctx->rank)) FAIL(AMR_ERR_ARG, "amr_mesh_set: processor patch with a bad neighbour rank");
+            for (int32_t k = 0; k < q.size; k++) coupled[(size_t)(q.start - f + k)] = 1;
+            nCoupled += q.size;
+        } else if (q.type == AMR_PATCH_EMPTY) {
+            for (int32_t k = 0; k < q.size; k++) emptyFace[(size_t)(q.start - f + k)] = 1;
+        }
+        patches.push_back(q);
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     // a marking remapped through the topology change (amr_remap_refine_cell) survives the mesh switch
     u8 *pending = nullptr;
     int64_t pendingN = 0;
     if (ctx->refineCell && ctx->refineCellN == n && n > 0) { pending = ctx->refineCell; pendingN = n; ctx->refineCell = nullptr; }
+    struct PendingGuard { u8 *&p; ~PendingGuard() { if (p) cudaFree(p); } } pendingGuard{pending};   // freed on every exit path
     freeMesh(ctx);
     ctx->nTotalCells = -1;
     ctx->anyProtCached = -1;
     ctx->n = n; ctx->f = f; ctx->b = b; ctx->p = p;
-    ctx->patches.clear();
-    std::vector<u8> coupled((size_t)(b > 0 ? b : 1), 0), emptyFace((size_t)(b > 0 ? b : 1), 0);
-    ctx->nCoupled = 0;
-    for (int i = 0; i < npatch; i++) {
-        Patch q{patchStart[i], patchSize[i], patchType ? patchType[i] : 0, patchNbrRank ? patchNbrRank[i] : -1};
-        if (q.size < 0 || q.start < f || (int64_t)q.start + q.size > f + b) FAIL(AMR_ERR_ARG, "amr_mesh_set: patch range outside boundary faces");
-        if (q.type == AMR_PATCH_PROCESSOR) {
-            for (int32_t k = 0; k < q.size; k++) coupled[(size_t)(q.start - f + k)] = 1;
-            ctx->nCoupled += q.size;
-        } else if (q.type == AMR_PATCH_EMPTY) {
-            for (int32_t k = 0; k < q.size; k++) emptyFace[(size_t)(q.start - f + k)] = 1;
-        }
-        ctx->patches.push_back(q);
-    }
+    ctx->patches = patches;
+    ctx->nCoupled = nCoupled;
     TRY(devAlloc(ctx, &ctx->owner, f + b));
     TRY(devAlloc(ctx, &ctx->neighbour, f));
     TRY(devAlloc(ctx, &ctx->bCoupled, b));
@@ -478,7 +536,6 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     if (pending) {
         CK(cudaMemcpyAsync(ctx->refineCell, pending, (size_t)pendingN, cudaMemcpyDeviceToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(pending);
     }
     CK(cudaMemsetAsync(ctx->ghost8, 0, (size_t)b + 16, ctx->stream));
     CK(cudaMemsetAsync(ctx->ghost64, 0, (size_t)(b + 2) * 8, ctx->stream));

@@ -62,6 +62,8 @@ struct amr_ctx {
     std::vector<char *> peerHost;      // mapped regions of all ranks (mine included)
     char **peerDev = nullptr;          // same, on the device
     unsigned haloEpoch = 0, redEpoch = 0;
+    unsigned long long peerTimeoutNs = 20000000000ull;   // bound of the device-side spins (AMR_B200_PEER_TIMEOUT_S)
+    bool peerTouched = false;          // a peer-memory exchange was enqueued since the error word was last read
     void *haloPlan = nullptr;          // HaloPlan (host copy), rebuilt at amr_mesh_set
     bool havePlan = false;
     unsigned long long *redVal = nullptr;   // device staging word for reductions
@@ -344,6 +346,30 @@ static int stageInOut(amr_ctx *ctx, T *ptr, int64_t count, T **dev) {
     ctx->outs.push_back({(void *)ptr, q, sizeof(T) * (size_t)(count > 0 ? count : 0)});
     return AMR_OK;
 }
+// ---- peer-memory error word ---------------------------------------------------------------------------------
+// A device-side spin that timed out (p2p.cuh) raises the error word of this rank's region.  It is fetched with every
+// host round trip of a call that enqueued a peer exchange and turned into AMR_ERR_STATE; reporting clears it.  Calls
+// that are only stream-ordered (all data pointers on the device) report it at the next synchronising call or at
+// amr_synchronize, like an asynchronous CUDA error.
+constexpr size_t kPeerErrOffset = 2048;    // offsetof(P2PRegionHeader, error), asserted in amr_b200.cu
+static int peerErrFetch(amr_ctx *ctx) {
+    ctx->hFlags[9] = 0;
+    if (ctx->usePeer && ctx->peerTouched)
+        CK(cudaMemcpyAsync(ctx->hFlags + 9, ctx->region + kPeerErrOffset, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return AMR_OK;
+}
+// after the stream was synchronised
+static int peerErrCheck(amr_ctx *ctx) {
+    ctx->peerTouched = false;
+    if (ctx->hFlags[9]) {
+        ctx->hFlags[9] = 0;
+        cudaMemsetAsync(ctx->region + kPeerErrOffset, 0, sizeof(int), ctx->stream);
+        FAIL(AMR_ERR_STATE, "peer-memory halo swap / reduction timed out: a neighbour rank did not enter the same collective call "
+                            "(results of this call are invalid; AMR_B200_PEER_TIMEOUT_S sets the limit)");
+    }
+    return AMR_OK;
+}
+
 // Copy staged outputs back and make the call complete with respect to the host.  A call whose data
 // pointers were all device pointers is only stream-ordered (normal CUDA semantics for device buffers):
 // no host synchronisation, the next call on the context's stream sees the results.
@@ -352,6 +378,10 @@ static int flushOuts(amr_ctx *ctx) {
     for (auto &o : ctx->outs)
         if (o.bytes) CK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->outs.clear();
-    if (sync) CK(cudaStreamSynchronize(ctx->stream));
+    if (sync) {
+        TRY(peerErrFetch(ctx));
+        CK(cudaStreamSynchronize(ctx->stream));
+        TRY(peerErrCheck(ctx));
+    }
     return AMR_OK;
 }

@@ -864,14 +864,15 @@ MG_API mg_mesh *mg_oct_build(const mg_oct *o, int flags) {
  *    processor patch list their faces in the same order.
  * out[r] receives the local mesh of rank r.
  */
-MG_API int mg_decompose(const mg_mesh *g, const i32 *cellRank, int nranks, mg_mesh **out) {
+static int decompose_impl(const mg_mesh *g, const i32 *cellRank, int nranks, mg_mesh **out, int only) {
     i64 n = g->n, f = g->f, b = g->b, p = g->p;
     i32 *loc = (i32 *)xmalloc(n * 4);
     i64 *nloc = (i64 *)xcalloc(nranks, 8);
     for (i64 c = 0; c < n; c++) loc[c] = (i32)nloc[cellRank[c]]++;
     for (int r = 0; r < nranks; r++) {
+        if (only >= 0 && r != only) continue;
         mg_mesh *m = (mg_mesh *)xcalloc(1, sizeof(mg_mesh));
-        out[r] = m;
+        out[only >= 0 ? 0 : r] = m;
         i64 nl = nloc[r];
         m->n = nl;
         m->cellGlobal = (i32 *)xmalloc(nl * 4);
@@ -1039,6 +1040,17 @@ MG_API int mg_decompose(const mg_mesh *g, const i32 *cellRank, int nranks, mg_me
     }
     free(loc); free(nloc);
     return 0;
+}
+
+MG_API int mg_decompose(const mg_mesh *g, const i32 *cellRank, int nranks, mg_mesh **out) {
+    return decompose_impl(g, cellRank, nranks, out, -1);
+}
+/* the local mesh of ONE rank (what a rank of a decomposed run holds); same numbering as mg_decompose */
+MG_API mg_mesh *mg_decompose_one(const mg_mesh *g, const i32 *cellRank, int nranks, int rank) {
+    mg_mesh *out = NULL;
+    if (rank < 0 || rank >= nranks) return NULL;
+    decompose_impl(g, cellRank, nranks, &out, rank);
+    return out;
 }
 
 /* "simple" decomposition of an octree mesh by cell-centre position: (px py pz) slabs */

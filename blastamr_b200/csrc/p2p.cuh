@@ -8,15 +8,22 @@
 //   k_halo_unpack     : acquire-spin on my own flag words, then copy the received ranges into `recv`
 // and a reduction (the reduce()/gMin/gMax of the reference) is the same pattern to all ranks.
 // Double buffering by epoch parity makes reuse safe: a rank can be at most one exchange ahead of a
-// neighbour (it needs that neighbour's signal to finish its own wait).  Spins are bounded (~2 s) and
-// raise an error word instead of hanging the GPU.  NCCL stays as set-up transport (handle exchange)
-// and as fallback (AMR_B200_HALO=nccl, or when IPC mapping is not possible).
+// neighbour (it needs that neighbour's signal to finish its own wait).  Spins are bounded (wall-clock limit
+// from the context: AMR_B200_PEER_TIMEOUT_S, default 20 s -- long enough for rank-imbalanced host work between two
+// collective calls) and raise the region's error word instead of hanging the GPU; the host reads that word at
+// every synchronising return (flushOuts / the sweep round trips) and fails the call.  NCCL stays as set-up
+// transport (handle exchange) and as fallback (AMR_B200_HALO=nccl, or when IPC mapping is not possible).
 #pragma once
 #include "common.cuh"
 
 constexpr int kMaxRanks = 64;
 constexpr int64_t kHaloCap = (int64_t)64 << 20;        // bytes per parity buffer
-constexpr long long kSpinLimit = 4000000000LL;          // cycles (~2 s)
+
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct P2PRegionHeader {                                 // lives at the start of every rank's region
     unsigned arrive[2][kMaxRanks];                       // halo epoch written by each neighbour
@@ -84,17 +91,18 @@ __global__ void k_halo_push_cells(HaloPlan P, char *const *__restrict__ peer, in
     }
 }
 template <int BYTES>
-__global__ void k_halo_unpack(HaloPlan P, char *mine, int parity, unsigned epoch, char *__restrict__ recv) {
+__global__ void k_halo_unpack(HaloPlan P, char *mine, int parity, unsigned epoch, char *__restrict__ recv,
+                              unsigned long long timeoutNs) {
     __shared__ int ok;
     P2PRegionHeader *h = reinterpret_cast<P2PRegionHeader *>(mine);
     if (threadIdx.x == 0) {
-        int good = 1;
-        const long long t0 = clock64();
-        for (int q = 0; q < P.nPatch; q++) {
+        int good = h->error == 0;                        // an earlier timeout of this call chain: do not touch recv
+        const unsigned long long t0 = globalTimerNs();
+        for (int q = 0; q < P.nPatch && good; q++) {
+            unsigned spins = 0;
             while ((int)(ldAcquireSys(&h->arrive[parity][P.nbr[q]]) - epoch) < 0) {
-                if (clock64() - t0 > kSpinLimit) { good = 0; h->error = 1; break; }
+                if ((++spins & 1023u) == 0 && globalTimerNs() - t0 > timeoutNs) { good = 0; h->error = 1; break; }
             }
-            if (!good) break;
         }
         ok = good;
     }
@@ -128,7 +136,8 @@ __global__ void k_red_push(char *const *__restrict__ peer, int nranks, int myRan
     __threadfence_system();
     stReleaseSys(&h->redEpoch[parity][myRank], epoch);
 }
-__global__ void k_red_wait(char *mine, int nranks, int parity, unsigned epoch, int op, void *__restrict__ out, int is32) {
+__global__ void k_red_wait(char *mine, int nranks, int parity, unsigned epoch, int op, void *__restrict__ out, int is32,
+                           unsigned long long timeoutNs) {
     __shared__ unsigned long long vals[kMaxRanks];
     __shared__ int bad;
     P2PRegionHeader *h = reinterpret_cast<P2PRegionHeader *>(mine);
@@ -136,9 +145,10 @@ __global__ void k_red_wait(char *mine, int nranks, int parity, unsigned epoch, i
     if (r == 0) bad = 0;
     __syncthreads();
     if (r < nranks) {
-        const long long t0 = clock64();
+        const unsigned long long t0 = globalTimerNs();
+        unsigned spins = 0;
         while ((int)(ldAcquireSys(&h->redEpoch[parity][r]) - epoch) < 0) {
-            if (clock64() - t0 > kSpinLimit) { bad = 1; h->error = 1; break; }
+            if ((++spins & 1023u) == 0 && globalTimerNs() - t0 > timeoutNs) { bad = 1; h->error = 1; break; }
         }
         vals[r] = h->red[parity][r];
     }

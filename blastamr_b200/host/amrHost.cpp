@@ -396,7 +396,14 @@ bool fvMeshRefiner::canRefine(const bool incr) const {           // fvMeshRefine
     } else if (m.timeValue < beginRefine_ || m.timeValue > endRefine_) return false;
     else if (refineInterval_ > 0 && (m.timeIndex % refineInterval_) > 0) return false;
     if (incr) nRefinementIterations_++;
-    return m.nCells < maxCells_;                // single rank: globalData().nTotalCells()
+    // mesh_.globalData().nTotalCells() (fvMeshRefiner.C:308): all ranks must take the same branch, or only some of them
+    // would enter the collective amr_select_refine.  amr_imbalance carries the reference's
+    // returnReduce(mesh_.nCells(), sumOp<label>()) (fvMeshBalance.C:463); without a communicator it is the local count.
+    double ratio = 0;
+    int64_t nTotalCells = m.nCells;
+    amr_ctx *gpu = const_cast<adaptiveFvMesh &>(amesh_).gpu();
+    if (gpu && amr_imbalance(gpu, &ratio, &nTotalCells) != AMR_OK) nTotalCells = m.nCells;
+    return nTotalCells < maxCells_;
 }
 bool fvMeshRefiner::canUnrefine(const bool incr) const {         // fvMeshRefiner.C:313-341
     const fvMeshLite &m = amesh_.mesh();

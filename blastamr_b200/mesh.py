@@ -47,6 +47,8 @@ def lib():
         L.mg_mesh_array.argtypes = [C.c_void_p, C.c_int]
         L.mg_decompose.restype = C.c_int
         L.mg_decompose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.mg_decompose_one.restype = C.c_void_p
+        L.mg_decompose_one.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.mg_simple_ranks.argtypes = [C.c_void_p] + [C.c_double] * 3 + [C.c_int] * 3 + [C.c_void_p]
         _lib = L
     return _lib
@@ -299,3 +301,12 @@ def decompose(mesh: PolyMesh, cell_rank: np.ndarray, nranks: int) -> List[PolyMe
     lib().mg_decompose(mesh._handle, cell_rank.ctypes.data, nranks, outs)
     names = [q.name for q in mesh.patches]
     return [_wrap(outs[r], names) for r in range(nranks)]
+
+
+def decompose_one(mesh: PolyMesh, cell_rank: np.ndarray, nranks: int, rank: int) -> PolyMesh:
+    """the local mesh of one rank of `decompose` (a rank of a decomposed run never holds the others)"""
+    cell_rank = np.ascontiguousarray(cell_rank, dtype=np.int32)
+    if mesh._handle is None:
+        raise ValueError("decompose needs a generator-owned mesh")
+    h = lib().mg_decompose_one(mesh._handle, cell_rank.ctypes.data, nranks, rank)
+    return _wrap(h, [q.name for q in mesh.patches])

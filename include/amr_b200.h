@@ -37,6 +37,8 @@
  *
  * Environment (read at amr_ctx_create / amr_comm_init; tuning and diagnosis only, results never change):
  *   AMR_B200_HALO=nccl            processor-patch swaps and reductions over NCCL instead of NVLink peer memory
+ *   AMR_B200_PEER_TIMEOUT_S=s     bound of the device-side waits of the peer-memory transport (default 20 s); a
+ *                                 timeout fails the call with AMR_ERR_STATE instead of hanging the GPU
  *   AMR_B200_NO_PIPELINE=1        direct kernels instead of the TMA-staged ones
  *   AMR_B200_PUSH_FRACTION=a/b    marked fraction below which a buffer layer / 2:1 sweep takes its sparse form
  *                                 (default 1/4; 0 = always dense)
@@ -373,6 +375,11 @@ int amr_history_clusters(amr_ctx *ctx, const int32_t *cellToClusterIn, int32_t *
 int amr_history_constrain_decomposition(amr_ctx *ctx, int32_t *decomposition, int64_t *nChanged);
 /* procLoadNew of fvMeshBalance::canBalance (fvMeshBalance.C:497-503): cells per target processor, summed over ranks */
 int amr_proc_load(amr_ctx *ctx, const int32_t *distribution, int nProcs, int64_t *procLoad);
+
+/* Wait for everything enqueued on the context's stream and report what calls that were only stream-ordered (all data
+   pointers on the device) could not: a peer-memory halo swap or reduction that timed out because a neighbour rank
+   did not enter the same collective call (AMR_ERR_STATE), or a CUDA error. */
+int amr_synchronize(amr_ctx *ctx);
 
 /* number of kernels launched by this context since creation */
 int64_t amr_launch_count(const amr_ctx *ctx);

@@ -13,7 +13,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 def test_reference_arm_prints_one_json_line():
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--cpu-cells", "32"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+                        "--base", "12"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
     assert len(lines) == 1
@@ -23,6 +23,9 @@ def test_reference_arm_prints_one_json_line():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the moved front makes refinement, several 2:1 sweeps and unrefinement all fire
+    assert d["config"]["n_refine"] > 0 and d["config"]["n_unrefine"] > 0 and d["config"]["sweeps_refine_gauss_seidel"] >= 2
+    assert d["scaling"] == "strong"
 
 
 def test_committed_gpu_profile_has_the_contract_objects():
