@@ -10,9 +10,42 @@ from blastamr_b200.mesh import Patch, PolyMesh, PATCH_EMPTY, PATCH_WALL
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
 
-def load_reference_mesh(case: str) -> PolyMesh:
+def add_edges(m: PolyMesh, foff, fpts) -> PolyMesh:
+    """mesh.faces(), mesh.edges(), mesh.edgeCells() the way primitiveMesh derives them: an edge joins two consecutive
+    points of a face; edges are numbered in order of first appearance over ascending faces; the cells of an edge are
+    the cells of the faces that use it."""
+    nf, f = len(foff) - 1, m.f
+    face_of = np.repeat(np.arange(nf), np.diff(foff))
+    nxt = np.arange(len(fpts)) + 1
+    last = foff[1:] - 1
+    nxt[last] = foff[:-1]
+    a, b = fpts, fpts[nxt]
+    lo, hi = np.minimum(a, b).astype(np.int64), np.maximum(a, b).astype(np.int64)
+    key = lo * (m.p + 1) + hi
+    uk, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")          # first appearance over ascending faces
+    rank = np.empty(len(uk), np.int64)
+    rank[order] = np.arange(len(uk))
+    eid = rank[inv]
+    ne = len(uk)
+    edge_pts = np.stack([lo[first[order]], hi[first[order]]], 1).astype(np.int32)
+    pairs = [np.stack([eid, m.owner[face_of]], 1)]
+    internal = face_of < f
+    pairs.append(np.stack([eid[internal], m.neighbour[face_of[internal]]], 1))
+    ec = np.unique(np.concatenate(pairs), axis=0)
+    ec_off = np.zeros(ne + 1, np.int32)
+    np.add.at(ec_off, ec[:, 0] + 1, 1)
+    bnd_edge = np.zeros(ne, np.uint8)
+    bnd_edge[eid[~internal]] = 1
+    m.n_edges, m.edge_pts, m.ec_off, m.ec_cells, m.bnd_edge = ne, edge_pts, np.cumsum(ec_off).astype(np.int32), ec[:, 1].astype(np.int32), bnd_edge
+    m.face_off, m.face_pts = foff.astype(np.int32), fpts.astype(np.int32)
+    return m
+
+
+def load_reference_mesh(case: str, edges: bool = False) -> PolyMesh:
     """The reference's own test mesh (tests/testCases/<case>/constant/polyMesh) with the point
-    addressing derived the way primitiveMesh does (pointCells / cellPoints from faces)."""
+    addressing derived the way primitiveMesh does (pointCells / cellPoints from faces); edges=True adds
+    faces() / edges() / edgeCells() (what the polyRefiner reads)."""
     z = np.load(GOLDEN / f"{case}_mesh.npz")
     owner, nei = z["owner"], z["neighbour"]
     foff, fpts, pts = z["face_off"], z["face_pts"], z["points"]
@@ -42,10 +75,11 @@ def load_reference_mesh(case: str) -> PolyMesh:
     cc = np.zeros((n, 3))
     np.add.at(cc, cp[:, 1], pts[cp[:, 0]])
     cc /= np.diff(cp_off)[:, None]
-    return PolyMesh(n=n, f=f, b=nf - f, p=p, owner=owner.astype(np.int32), neighbour=nei.astype(np.int32), patches=patches,
-                    cc=cc, vol=None, pc_off=pc_off, pc_cells=pc_cells, cp_off=cp_off, cp_pts=cp_pts, bnd_point=bnd,
-                    cell_level=np.zeros(n, np.int32), point_level=np.zeros(p, np.int32),
-                    visible=np.full(n, -1, np.int32), split_parent=np.zeros(0, np.int32))
+    m = PolyMesh(n=n, f=f, b=nf - f, p=p, owner=owner.astype(np.int32), neighbour=nei.astype(np.int32), patches=patches,
+                 cc=cc, vol=None, pc_off=pc_off, pc_cells=pc_cells, cp_off=cp_off, cp_pts=cp_pts, bnd_point=bnd,
+                 cell_level=np.zeros(n, np.int32), point_level=np.zeros(p, np.int32),
+                 visible=np.full(n, -1, np.int32), split_parent=np.zeros(0, np.int32))
+    return add_edges(m, foff, fpts) if edges else m
 
 
 def load_reference_faces(case: str) -> PolyMesh:

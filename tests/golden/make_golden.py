@@ -102,6 +102,77 @@ def convert_faces_only(case):
     print(case, "cells", owner.max() + 1, "faces", len(owner), "internal", len(nei), bnd)
 
 
+# ---- foam-extend binary polyMesh (tests/testCases/poly2D: *.gz, `format binary`) ------------------------------
+
+def _bin_body(path):
+    import gzip
+    d = gzip.open(path).read()
+    i = d.index(b"// * * *")
+    return d[d.index(b"\n", i) + 1:]
+
+
+def _read_count(b, pos):
+    """skip white space, read an ASCII integer, skip to just after the following '('"""
+    while b[pos:pos + 1].isspace():
+        pos += 1
+    j = pos
+    while b[j:j + 1].isdigit():
+        j += 1
+    n = int(b[pos:j])
+    k = b.index(b"(", j)
+    assert b[j:k].strip() == b""
+    return n, k + 1
+
+
+def read_labels_bin(path):
+    b = _bin_body(path)
+    n, pos = _read_count(b, 0)
+    a = np.frombuffer(b, dtype="<i4", count=n, offset=pos).copy()
+    assert b[pos + 4 * n:pos + 4 * n + 1] == b")"
+    return a
+
+
+def read_faces_bin(path):
+    """faceList written face by face: `k ( <k x int32> )`"""
+    b = _bin_body(path)
+    n, pos = _read_count(b, 0)
+    off, pts = [0], []
+    for _ in range(n):
+        k, pos = _read_count(b, pos)
+        pts.append(np.frombuffer(b, dtype="<i4", count=k, offset=pos))
+        pos += 4 * k
+        assert b[pos:pos + 1] == b")"
+        pos += 1
+        off.append(off[-1] + k)
+    return np.array(off, np.int32), np.concatenate(pts).astype(np.int32)
+
+
+def read_points_bin(path):
+    b = _bin_body(path)
+    n, pos = _read_count(b, 0)
+    a = np.frombuffer(b, dtype="<f8", count=3 * n, offset=pos).reshape(n, 3).copy()
+    assert b[pos + 24 * n:pos + 24 * n + 1] == b")"
+    return a
+
+
+def convert_poly2d():
+    """the reference's polyhedral 2-D fixture (670 prismatic polyhedra, one cell thick): the mesh class of config C3
+    (poly_freelyPropFlame2D_H2) and of the reference's own unit test (adaptiveFvMeshTest.C runs on every case)"""
+    case = "poly2D"
+    pm = REF / case / "constant" / "polyMesh"
+    owner = read_labels_bin(pm / "owner.gz")
+    nei = read_labels_bin(pm / "neighbour.gz")
+    foff, fpts = read_faces_bin(pm / "faces.gz")
+    pts = read_points_bin(pm / "points.gz")
+    bnd = read_boundary(pm / "boundary")
+    f = min(b[2] for b in bnd)
+    assert len(owner) == len(foff) - 1 and len(nei) == f and (owner[:f] < nei).all() and fpts.max() == len(pts) - 1
+    np.savez_compressed(HERE / f"{case}_mesh.npz", owner=owner, neighbour=nei, face_off=foff, face_pts=fpts, points=pts,
+                        patch_names=np.array([b[0] for b in bnd]), patch_types=np.array([b[1] for b in bnd]),
+                        patch_start=np.array([b[2] for b in bnd], np.int32), patch_size=np.array([b[3] for b in bnd], np.int32))
+    print(case, "cells", owner.max() + 1, "faces", len(owner), "internal", len(nei), "points", len(pts), bnd)
+
+
 def golden_outputs():
     from tests.fixtures import load_reference_mesh
     from tests import amr_cases as cases
@@ -132,4 +203,5 @@ if __name__ == "__main__":
         for c in ("hex3D", "hex2D"):
             convert(c)
         convert_faces_only("poly3D")
+        convert_poly2d()
     golden_outputs()

@@ -202,3 +202,100 @@ def multicomponent_wavefront(mesh, errors, levels):
                 out[c] = lv[max(fired)]
         mr = out
     return mr, waves
+
+
+# ---- polyRefiner (face + edge rules) from the definitions -------------------------------------------------
+
+def _edge_ids(mesh):
+    return np.repeat(np.arange(mesh.n_edges), np.diff(mesh.ec_off))
+
+
+def closure_refine_poly(mesh, flags, edge_based=True):
+    """least fixed point of refinement::consistentRefinement (refinement.C:744-810): 2:1 over faces and, with
+    edgeBasedConsistency, over every pair of cells sharing a mesh edge.  Jacobi iteration."""
+    own, nei = mesh.owner[:mesh.f], mesh.neighbour
+    eid = _edge_ids(mesh)
+    flags = flags.astype(bool).copy()
+    while True:
+        lv = mesh.cell_level + flags
+        new = flags.copy()
+        new[nei[lv[own] > lv[nei] + 1]] = True
+        new[own[lv[nei] > lv[own] + 1]] = True
+        if edge_based:
+            mx = np.zeros(mesh.n_edges, np.int64)
+            np.maximum.at(mx, eid, lv[mesh.ec_cells])
+            new[mesh.ec_cells[lv[mesh.ec_cells] + 1 < mx[eid]]] = True
+        if (new == flags).all():
+            return flags
+        flags = new
+
+
+def balanced_poly(mesh, lv):
+    """2:1 over faces and over edge-cell pairs"""
+    own, nei = mesh.owner[:mesh.f], mesh.neighbour
+    if np.abs(lv[own] - lv[nei]).max() > 1:
+        return False
+    eid = _edge_ids(mesh)
+    mx = np.zeros(mesh.n_edges, np.int64)
+    mn = np.full(mesh.n_edges, 1 << 30, np.int64)
+    np.maximum.at(mx, eid, lv[mesh.ec_cells])
+    np.minimum.at(mn, eid, lv[mesh.ec_cells])
+    return bool((mx - mn <= 1).all())
+
+
+def grow_points(mesh, marked):
+    """fvMeshRefiner::extendMarkedCellsAcrossPoints: cells -> points -> cells"""
+    pts = np.repeat(np.arange(mesh.p), np.diff(mesh.pc_off))
+    pm = np.zeros(mesh.p, bool)
+    np.logical_or.at(pm, pts, marked[mesh.pc_cells])
+    out = marked.copy()
+    out[mesh.pc_cells[pm[pts]]] = True
+    return out
+
+
+def prism_split_points(mesh):
+    """prismatic2DRefinement.C:2756-2849: pointLevel >= 1 and every edge at the point joins equal point levels"""
+    bad = np.zeros(mesh.p, bool)
+    e = mesh.edge_pts.reshape(-1, 2)
+    d = mesh.point_level[e[:, 0]] != mesh.point_level[e[:, 1]]
+    bad[e[d, 0]] = True
+    bad[e[d, 1]] = True
+    return (mesh.point_level >= 1) & ~bad
+
+
+def poly_split_points(mesh):
+    """polyhedralRefinement.C:2110-2184: pointLevel >= 1, every face at the point has one point level, no boundary face"""
+    bad = np.zeros(mesh.p, bool)
+    nf = mesh.f + mesh.b
+    for i in range(nf):
+        ps = mesh.face_pts[mesh.face_off[i]:mesh.face_off[i + 1]]
+        if i >= mesh.f or len(set(mesh.point_level[ps].tolist())) > 1:
+            bad[ps] = True
+    return (mesh.point_level >= 1) & ~bad
+
+
+def closure_unrefine_poly(mesh, pflags, edge_based=True):
+    """greatest set of split points whose merged cells keep 2:1 over faces (and edges): Jacobi form of
+    polyhedralRefinement.C:2257-2328"""
+    own, nei = mesh.owner[:mesh.f], mesh.neighbour
+    pts = np.repeat(np.arange(mesh.p), np.diff(mesh.pc_off))
+    eid = _edge_ids(mesh)
+    pf = pflags.astype(bool).copy()
+    while True:
+        uc = np.zeros(mesh.n, bool)
+        uc[mesh.pc_cells[pf[pts]]] = True
+        lv = mesh.cell_level - uc
+        bad = np.zeros(mesh.n, bool)
+        bad[own[lv[own] < lv[nei] - 1]] = True
+        bad[nei[lv[nei] < lv[own] - 1]] = True
+        if edge_based:
+            mx = np.zeros(mesh.n_edges, np.int64)
+            np.maximum.at(mx, eid, lv[mesh.ec_cells])
+            bad[mesh.ec_cells[(lv[mesh.ec_cells] < mx[eid] - 1)]] = True
+        bad &= uc
+        if not bad.any():
+            return pf
+        uc &= ~bad
+        ok = np.ones(mesh.p, bool)
+        np.logical_and.at(ok, pts, uc[mesh.pc_cells])
+        pf &= ok
