@@ -8,6 +8,7 @@
 #include "sell.cuh"
 #include "kernels.cuh"
 #include "kernels_pipe.cuh"
+#include "kernels_sparse.cuh"
 #include "lohner.cuh"
 #include "fields.cuh"
 #include "p2p.cuh"
@@ -80,13 +81,26 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
     }
     cudaMalloc((void **)&ctx->dFlags, 16 * sizeof(int));
     cudaMalloc((void **)&ctx->dCount, 4 * sizeof(int64_t));
+    cudaMalloc((void **)&ctx->dSeq, 2 * sizeof(unsigned));
+    cudaMalloc((void **)&ctx->lbTicket, sizeof(unsigned));
+    cudaMalloc((void **)&ctx->dTotals, 8 * sizeof(int32_t));
+    cudaMalloc((void **)&ctx->dQ, 2 * (kMaxIter + 2) * sizeof(int));
+    cudaMalloc((void **)&ctx->dMarked, 16 * sizeof(unsigned long long));
     cudaMallocHost((void **)&ctx->hFlags, 16 * sizeof(int));
     cudaMallocHost((void **)&ctx->hCount, 4 * sizeof(int64_t));
-    cudaMallocHost((void **)&ctx->hMarked, 16 * sizeof(long long));
-    if (ctx->hMarked) for (int i = 0; i < 16; i++) ctx->hMarked[i] = -1;
-    if (!ctx->dFlags || !ctx->dCount || !ctx->hFlags || !ctx->hCount || !ctx->hMarked) { delete ctx; return AMR_ERR_CUDA; }
+    cudaMallocHost((void **)&ctx->hMarked, 32 * sizeof(long long));
+    cudaMallocHost((void **)&ctx->hQ, 2 * (kMaxIter + 2) * sizeof(int));
+    if (ctx->hMarked) { for (int i = 0; i < 32; i++) ctx->hMarked[i] = -1; ctx->hMarkedStage = ctx->hMarked + 16; }
+    if (!ctx->dFlags || !ctx->dCount || !ctx->hFlags || !ctx->hCount || !ctx->hMarked || !ctx->dSeq || !ctx->lbTicket || !ctx->dTotals ||
+        !ctx->dQ || !ctx->hQ || !ctx->dMarked) { delete ctx; return AMR_ERR_CUDA; }
+    ctx->dGQ = ctx->dQ + (kMaxIter + 2);
     cudaMemset(ctx->dFlags, 0, 16 * sizeof(int));
     cudaMemset(ctx->dCount, 0, 4 * sizeof(int64_t));
+    cudaMemset(ctx->dSeq, 0, 2 * sizeof(unsigned));
+    cudaMemset(ctx->lbTicket, 0, sizeof(unsigned));
+    cudaMemset(ctx->dTotals, 0, 8 * sizeof(int32_t));
+    cudaMemset(ctx->dQ, 0, 2 * (kMaxIter + 2) * sizeof(int));
+    cudaMemset(ctx->dMarked, 0, 16 * sizeof(unsigned long long));
     *out = ctx;
     return AMR_OK;
 }
@@ -101,7 +115,10 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->error); devFree(ctx, &ctx->refineCell);
     devFree(ctx, &ctx->flagA); devFree(ctx, &ctx->flagB); devFree(ctx, &ctx->flagC); devFree(ctx, &ctx->lf);
     devFree(ctx, &ctx->ghost8); devFree(ctx, &ctx->ghost64);
-    devFree(ctx, &ctx->tileCnt); devFree(ctx, &ctx->scanAux);
+    devFree(ctx, &ctx->lbStatus);
+    devFree(ctx, &ctx->queue[0]); devFree(ctx, &ctx->queue[1]); ctx->queueCap = 0;
+    devFree(ctx, &ctx->spPoint); devFree(ctx, &ctx->spCells); devFree(ctx, &ctx->cellSp); devFree(ctx, &ctx->spFlag); devFree(ctx, &ctx->spList);
+    ctx->nSp = 0; ctx->spDirty = true; ctx->balancedGlobal = -1; ctx->refineCellGen = 1;
     devFree(ctx, &ctx->gWeights); devFree(ctx, &ctx->gSf); devFree(ctx, &ctx->gMagSf); devFree(ctx, &ctx->gDelta); devFree(ctx, &ctx->gV);
     devFree(ctx, &ctx->grad); devFree(ctx, &ctx->xbf);
     devFree(ctx, &ctx->bEmpty); devFree(ctx, &ctx->lsP); devFree(ctx, &ctx->lsN); ctx->haveLs = false;
@@ -133,8 +150,9 @@ AMR_API int amr_ctx_destroy(amr_ctx *ctx) {
     }
     if (ctx->region) cudaFree(ctx->region);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
-    cudaFree(ctx->dFlags); cudaFree(ctx->dCount);
-    cudaFreeHost(ctx->hFlags); cudaFreeHost(ctx->hCount); cudaFreeHost(ctx->hMarked);
+    cudaFree(ctx->dFlags); cudaFree(ctx->dCount); cudaFree(ctx->dSeq); cudaFree(ctx->lbTicket); cudaFree(ctx->dTotals); cudaFree(ctx->dQ);
+    cudaFree(ctx->dMarked);
+    cudaFreeHost(ctx->hFlags); cudaFreeHost(ctx->hCount); cudaFreeHost(ctx->hMarked); cudaFreeHost(ctx->hQ);
     for (auto &L : ctx->lanes) {
         for (int k = 0; k < 2; k++) { if (L.pin[k]) cudaFreeHost(L.pin[k]); if (L.ev[k]) cudaEventDestroy(L.ev[k]); }
         if (L.s) cudaStreamDestroy(L.s);
@@ -293,19 +311,23 @@ static int peerPlan(amr_ctx *ctx) {
     }
     NCK(ncclGroupEnd());
     if (np) CK(cudaMemcpyAsync(theirs.data(), dTheirs, (size_t)2 * np * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    // agreement word: [0] = min(ok), [1] = max(halo epoch), [2] = max(reduction epoch)   (as -min of negatives)
-    int32_t agree[3] = {ok, -(int32_t)(ctx->haloEpoch & 0x3fffffffu), -(int32_t)(ctx->redEpoch & 0x3fffffffu)};
-    int32_t *dAgree = dMine + 2 * np;
+    // agreement word: [0] = min(ok), [1] = max(halo exchange number), [2] = max(reduction number)   (as -min of negatives)
+    unsigned seqNow[2] = {0, 0};
+    CK(cudaMemcpyAsync(seqNow, ctx->dSeq, sizeof(seqNow), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    int32_t agree[3] = {ok, -(int32_t)(seqNow[0] & 0x3fffffffu), -(int32_t)(seqNow[1] & 0x3fffffffu)};
+    int32_t *dAgree = dMine + 2 * np;
     for (int k = 0; k < np; k++)
         if (theirs[(size_t)2 * k + 1] != mine[(size_t)2 * k + 1]) agree[0] = 0;      // the two sides of a patch disagree on its size
     CK(cudaMemcpyAsync(dAgree, agree, sizeof(agree), cudaMemcpyHostToDevice, ctx->stream));
     NCK(ncclAllReduce(dAgree, dAgree, 3, ncclInt32, ncclMin, ctx->comm, ctx->stream));
     CK(cudaMemcpyAsync(agree, dAgree, sizeof(agree), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    // common epochs: above every value any rank has used (stale arrival words are below them)
-    ctx->haloEpoch = (unsigned)(-agree[1]) + 2u;
-    ctx->redEpoch = (unsigned)(-agree[2]) + 2u;
+    // common exchange numbers: above every value any rank has used (stale arrival words are below them)
+    seqNow[0] = (unsigned)(-agree[1]) + 2u;
+    seqNow[1] = (unsigned)(-agree[2]) + 2u;
+    CK(cudaMemcpyAsync(ctx->dSeq, seqNow, sizeof(seqNow), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     if (!agree[0]) return AMR_OK;                    // agreed: NCCL transport for this mesh
     for (int k = 0; k < np; k++) {
         P.nbr[k] = nbrs[(size_t)k]; P.offMine[k] = mine[(size_t)2 * k]; P.size[k] = mine[(size_t)2 * k + 1];
@@ -339,38 +361,35 @@ static int haloExchange(amr_ctx *ctx, const void *send, void *recv, size_t elemB
 // its ghost-free main kernel (haloBegin ... main kernel ... haloEnd ... boundary fix-up): the neighbours' skew and
 // the NVLink latency then hide behind the main kernel.  A rank never pushes exchange k+1 before it unpacked
 // exchange k, so a neighbour can run at most one exchange ahead and the two parity buffers suffice.
-// The epoch advances on EVERY rank of the communicator for every exchange of a collective call, whether or not the
-// rank owns a processor patch, so all ranks stay in lockstep.
+// At most one swap is in flight per context (haloBegin ... haloEnd); exchange numbers live on the device (p2p.cuh).
+// gate (optional, device int, identical on all ranks): the swap only happens when *gate != 0.
 struct HaloToken {
     bool pending = false;
-    unsigned epoch = 0;
-    int parity = 0;
     size_t elemBytes = 0;
     void *recv = nullptr;
+    const int *gate = nullptr;
 };
-static int haloBegin(amr_ctx *ctx, const void *cells, size_t elemBytes, void *recv, HaloToken *tok, const u8 *minus = nullptr) {
+static int haloBegin(amr_ctx *ctx, const void *cells, size_t elemBytes, void *recv, HaloToken *tok, const u8 *minus = nullptr,
+                     const int *gate = nullptr) {
     tok->pending = false;
-    const bool peer = ctx->usePeer && ctx->havePlan;
-    unsigned epoch = 0;
-    if (peer) epoch = ++ctx->haloEpoch;
     if (ctx->nCoupled == 0) return AMR_OK;
     if (!ctx->comm) FAIL(AMR_ERR_STATE, "mesh has processor patches but no communicator (amr_comm_init) and no host-side neighbour values");
     const int64_t b = ctx->b;
-    if (peer) {
+    if (ctx->usePeer && ctx->havePlan) {
         const HaloPlan &P = *(const HaloPlan *)ctx->haloPlan;
-        const int parity = (int)(epoch & 1u);
         const unsigned g = gridFor(P.prefix[P.nPatch]);
         unsigned *counter = (unsigned *)(ctx->dFlags + 6);
         const label *bOwner = ctx->owner + ctx->f;
-        if (elemBytes == 1) k_halo_push_cells<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
-        else if (elemBytes == 4) k_halo_push_cells<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
-        else if (elemBytes == 8) k_halo_push_cells<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
-        else k_halo_push_cells<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, parity, ctx->rank, epoch, bOwner, (const char *)cells, minus, counter);
+        if (elemBytes == 1) k_halo_push_cells<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, bOwner, (const char *)cells, minus, counter, gate);
+        else if (elemBytes == 4) k_halo_push_cells<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, bOwner, (const char *)cells, minus, counter, gate);
+        else if (elemBytes == 8) k_halo_push_cells<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, bOwner, (const char *)cells, minus, counter, gate);
+        else k_halo_push_cells<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, bOwner, (const char *)cells, minus, counter, gate);
         ctx->launches++;
         ctx->peerTouched = true;
-        tok->pending = true; tok->epoch = epoch; tok->parity = parity; tok->elemBytes = elemBytes; tok->recv = recv;
+        tok->pending = true; tok->elemBytes = elemBytes; tok->recv = recv; tok->gate = gate;
         return AMR_OK;
     }
+    if (gate) FAIL(AMR_ERR_STATE, "gated halo swap on the NCCL transport");      // callers use the host-synchronised loops there
     // NCCL path: pack into a send buffer laid out like the boundary-face array, then grouped send/recv (complete here)
     void *send = nullptr;
     TRY(arenaAlloc(ctx, &send, (size_t)b * elemBytes));
@@ -387,10 +406,11 @@ static int haloEnd(amr_ctx *ctx, HaloToken *tok) {
     const HaloPlan &P = *(const HaloPlan *)ctx->haloPlan;
     const unsigned g = gridFor(P.prefix[P.nPatch]);
     const unsigned long long to = ctx->peerTimeoutNs;
-    if (tok->elemBytes == 1) k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv, to);
-    else if (tok->elemBytes == 4) k_halo_unpack<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv, to);
-    else if (tok->elemBytes == 8) k_halo_unpack<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv, to);
-    else k_halo_unpack<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, tok->parity, tok->epoch, (char *)tok->recv, to);
+    unsigned *counter = (unsigned *)(ctx->dFlags + 7);
+    if (tok->elemBytes == 1) k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, ctx->dSeq, (char *)tok->recv, to, counter, tok->gate);
+    else if (tok->elemBytes == 4) k_halo_unpack<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, ctx->dSeq, (char *)tok->recv, to, counter, tok->gate);
+    else if (tok->elemBytes == 8) k_halo_unpack<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, ctx->dSeq, (char *)tok->recv, to, counter, tok->gate);
+    else k_halo_unpack<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, ctx->dSeq, (char *)tok->recv, to, counter, tok->gate);
     ctx->launches++;
     return AMR_OK;
 }
@@ -399,24 +419,29 @@ static int haloSwapCells(amr_ctx *ctx, const void *cells, size_t elemBytes, void
     TRY(haloBegin(ctx, cells, elemBytes, recv, &tok, minus));
     return haloEnd(ctx, &tok);
 }
+// the speculative (device-gated) loops need the peer transport; with NCCL the host-synchronised loops run
+static inline bool gatedSwapsOk(const amr_ctx *ctx) { return (!ctx->comm || ctx->nranks < 2) ? true : (ctx->usePeer && ctx->havePlan); }
 
-// all-rank reduction of one device word in place (reduce()/returnReduce()/gMin/gMax of the reference).
-// op: 0 max(int32), 1 sum(int64), 2 min(f64), 3 max(f64)
-static int allReduceWord(amr_ctx *ctx, void *word, int op) {
-    if (!ctx->comm || ctx->nranks < 2) return AMR_OK;
+// all-rank reduction of one device word (reduce()/returnReduce()/gMin/gMax of the reference): *word = op over ranks of *src
+// (src == nullptr: in place).  op: 0 max(int32), 1 sum(int64), 2 min(f64), 3 max(f64), 4 sum(int32)
+static int allReduceWord(amr_ctx *ctx, void *word, int op, const void *src = nullptr, const int *gate = nullptr) {
+    if (!ctx->comm || ctx->nranks < 2) {
+        if (src && src != word) CK(cudaMemcpyAsync(word, src, (op == 0 || op == 4) ? 4 : 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        return AMR_OK;
+    }
     if (ctx->usePeer) {
-        const unsigned epoch = ++ctx->redEpoch;
-        const int parity = (int)(epoch & 1u);
-        const int is32 = (op == 0);
-        k_red_push<<<1, kMaxRanks, 0, ctx->stream>>>(ctx->peerDev, ctx->nranks, ctx->rank, parity, epoch, word, is32);
-        k_red_wait<<<1, kMaxRanks, 0, ctx->stream>>>(ctx->region, ctx->nranks, parity, epoch, op, word, is32, ctx->peerTimeoutNs);
-        ctx->launches += 2;
+        k_red_all<<<1, kMaxRanks, 0, ctx->stream>>>(ctx->peerDev, ctx->region, ctx->nranks, ctx->rank, ctx->dSeq, op, src, word,
+                                                    ctx->peerTimeoutNs, gate);
+        ctx->launches++;
         ctx->peerTouched = true;
         return AMR_OK;
     }
-    if (op == 0) NCK(ncclAllReduce(word, word, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
-    else if (op == 1) NCK(ncclAllReduce(word, word, 1, ncclInt64, ncclSum, ctx->comm, ctx->stream));
-    else NCK(ncclAllReduce(word, word, 1, ncclFloat64, op == 2 ? ncclMin : ncclMax, ctx->comm, ctx->stream));
+    if (gate) FAIL(AMR_ERR_STATE, "gated reduction on the NCCL transport");
+    if (!src) src = word;
+    if (op == 0) NCK(ncclAllReduce(src, word, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
+    else if (op == 4) NCK(ncclAllReduce(src, word, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream));
+    else if (op == 1) NCK(ncclAllReduce(src, word, 1, ncclInt64, ncclSum, ctx->comm, ctx->stream));
+    else NCK(ncclAllReduce(src, word, 1, ncclFloat64, op == 2 ? ncclMin : ncclMax, ctx->comm, ctx->stream));
     return AMR_OK;
 }
 
@@ -529,9 +554,8 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     TRY(devAlloc(ctx, &ctx->ghost8, b + 16));
     TRY(devAlloc(ctx, &ctx->ghost64, b + 2));
     ctx->tileCap = (m + kTile - 1) / kTile + 8;
-    TRY(devAlloc(ctx, &ctx->tileCnt, ctx->tileCap));
-    ctx->scanAuxCap = 2 * (ctx->tileCap / kScanTile + 1024);
-    TRY(devAlloc(ctx, &ctx->scanAux, ctx->scanAuxCap));
+    TRY(devAlloc(ctx, &ctx->lbStatus, ctx->tileCap));
+    CK(cudaMemsetAsync(ctx->lbStatus, 0, (size_t)ctx->tileCap * 8, ctx->stream));
     CK(cudaMemsetAsync(ctx->refineCell, 0, (size_t)m + 16, ctx->stream));
     if (pending) {
         CK(cudaMemcpyAsync(ctx->refineCell, pending, (size_t)pendingN, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -562,7 +586,7 @@ AMR_API int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_
     if (p) TRY(uploadAuto(ctx, ctx->bndPoint, bndPoint, (size_t)p));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->havePoints = true;
-    ctx->pcClassDirty = true; ctx->balancedLocal = -1;
+    ctx->pcClassDirty = true; ctx->balancedLocal = -1; ctx->balancedGlobal = -1; ctx->spDirty = true;
     return AMR_OK;
 }
 
@@ -583,11 +607,10 @@ static int growFlagPool(amr_ctx *ctx, int64_t need) {
     ctx->flagCap = need;
     int64_t tiles = (need + kTile - 1) / kTile + 8;
     if (tiles > ctx->tileCap) {
-        devFree(ctx, &ctx->tileCnt); devFree(ctx, &ctx->scanAux);
+        devFree(ctx, &ctx->lbStatus);
         ctx->tileCap = tiles;
-        TRY(devAlloc(ctx, &ctx->tileCnt, ctx->tileCap));
-        ctx->scanAuxCap = 2 * (ctx->tileCap / kScanTile + 1024);
-        TRY(devAlloc(ctx, &ctx->scanAux, ctx->scanAuxCap));
+        TRY(devAlloc(ctx, &ctx->lbStatus, ctx->tileCap));
+        CK(cudaMemsetAsync(ctx->lbStatus, 0, (size_t)ctx->tileCap * 8, ctx->stream));
     }
     return AMR_OK;
 }
@@ -761,7 +784,7 @@ AMR_API int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->haveLevels = true;
-    ctx->pcClassDirty = true; ctx->balancedLocal = -1;
+    ctx->pcClassDirty = true; ctx->balancedLocal = -1; ctx->balancedGlobal = -1; ctx->spDirty = true;
     return AMR_OK;
 }
 
@@ -939,45 +962,59 @@ AMR_API int amr_normalize_range(amr_ctx *ctx, double refineThreshold, double unr
     return flushOuts(ctx);
 }
 
-// one face-layer growth of `cur` (n flags) with ping-pong buffer `tmp`; src == cur.  Returns the
-// buffer holding the result in *res.
-// `site` identifies the call site (which layer of which stage): the marked fraction seen there by the PREVIOUS call
-// predicts whether the adaptive sequence is worth launching at all (AMR markings change slowly from step to step);
-// a wrong prediction only costs time, both forms give the same flags.
-static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *src, u8 *tmp, u8 **res, int site) {
-    const int64_t n = ctx->n;
-    HaloToken halo;
-    if (ctx->nCoupled > 0) {
-        TRY(haloBegin(ctx, src, 1, ctx->ghost8, &halo));
-    }
-    const int *gate = nullptr;
-    if (ctx->pushNum > 0 && n >= ctx->pushMinCells && n > 0) {
-        const bool al = ((((uintptr_t)src) | ((uintptr_t)cur) | ((uintptr_t)tmp)) & 15) == 0;
-        unsigned long long *total = (unsigned long long *)(ctx->dCount + 1);
-        const long long seen = ctx->hMarked[site];                // marked cells at this site last time (-1: never)
-        const bool tryPush = seen < 0 || seen * ctx->pushDen < 2 * n * ctx->pushNum;   // within 2x of the threshold
-        CK(cudaMemsetAsync(total, 0, 8, ctx->stream));
-        LAUNCH(k_count_set16, gridFor(n, kThreads * 16), kThreads, n, src, al, total);
-        CK(cudaMemcpyAsync(ctx->hMarked + site, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (tryPush) {
-            int *g = ctx->dFlags + 12;
-            LAUNCH(k_push_gate, 1, 1, (const unsigned long long *)total, (long long)n, (long long)ctx->pushNum, (long long)ctx->pushDen, g);
-            LAUNCH(k_copy_flags_gated, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)cur, tmp, al, (const int *)g);
-            LAUNCH(k_extend_push, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, src, al, tmp, (const int *)g);
-            gate = g;
-        }
-    }
-    if (pipeOk(ctx, ctx->cc)) TRY(launchPipe(ctx, kp_extend, ctx->cc, (const u8 *)cur, src, tmp, gate));
-    else LAUNCH(k_extend, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, cur, src, tmp, gate);
-    TRY(haloEnd(ctx, &halo));
-    if (ctx->nCoupled > 0)
-        LAUNCH(k_fix_extend, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
-               (const u8 *)ctx->ghost8, tmp);
-    *res = tmp;
-    return AMR_OK;
-}
+// One face layer of the marking `cur`, IN PLACE (kernels_sparse.cuh (1)): sources are the cells with generation
+// 0 < v <= gen, or the non-zero cells of a separate source array (the first forced layer of the hex refiner,
+// fvMeshRefiner.C:805-823); new marks get gen + 1.  `site` identifies the call site (which layer of which stage): the
+// number of sources seen there by the PREVIOUS call picks the sparse push or the dense pull form -- AMR markings move
+// slowly from step to step, a wrong prediction only costs time, both forms give the same flags -- and every layer
+// kernel reports the exact count of this call as a by-product (read back with the call's final round trip).
 constexpr int kSiteProtect = 0, kSiteRefine = 4, kSiteUnrefine = 8, kSiteSweep = 12;   // 4 slots each in ctx->hMarked[16]
 static inline int siteOf(int base, int layer) { return base + (layer < 3 ? layer : 3); }
+
+static int sitesBegin(amr_ctx *ctx) {
+    ctx->sitesTouched = 0;
+    CK(cudaMemsetAsync(ctx->dMarked, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    return AMR_OK;
+}
+// enqueue the read-back of the counts; sitesCommit after the stream was synchronised
+static int sitesFetch(amr_ctx *ctx) {
+    if (ctx->sitesTouched) CK(cudaMemcpyAsync(ctx->hMarkedStage, ctx->dMarked, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    return AMR_OK;
+}
+static void sitesCommit(amr_ctx *ctx) {
+    for (int s = 0; s < 16; s++)
+        if (ctx->sitesTouched & (1u << s)) ctx->hMarked[s] = ctx->hMarkedStage[s];
+    ctx->sitesTouched = 0;
+}
+static inline bool sparseForm(const amr_ctx *ctx, int site, int64_t n) {
+    if (ctx->pushNum <= 0 || n < ctx->pushMinCells || n <= 0) return false;
+    if (ctx->pushNum >= ctx->pushDen) return true;                 // AMR_B200_PUSH_FRACTION >= 1: always (tests force the form)
+    const long long seen = ctx->hMarked[site];                     // sources at this site last time (-1: never seen -> dense)
+    return seen >= 0 && seen * ctx->pushDen < n * ctx->pushNum;
+}
+
+static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *srcSeparate, int gen, int site) {
+    const int64_t n = ctx->n;
+    if (gen >= 254) FAIL(AMR_ERR_ARG, "more than 253 buffer layers in one call sequence");
+    const u8 *srcArr = srcSeparate ? srcSeparate : cur;
+    const bool separate = srcSeparate != nullptr;
+    HaloToken halo;
+    if (ctx->nCoupled > 0) TRY(haloBegin(ctx, srcArr, 1, ctx->ghost8, &halo));     // the values as they are BEFORE this layer
+    unsigned long long *cnt = ctx->dMarked + site;
+    if (n > 0) {
+        if (sparseForm(ctx, site, n)) {
+            const bool al = ((((uintptr_t)srcArr) | ((uintptr_t)cur)) & 15) == 0;
+            LAUNCH(k_layer_push, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, srcArr, separate, gen, al, cur, cnt);
+        } else if (pipeOk(ctx, ctx->cc)) TRY(launchPipe(ctx, kp_layer_pull, ctx->cc, srcArr, separate, gen, cur, cnt));
+        else LAUNCH(k_layer_pull, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, srcArr, separate, gen, cur, cnt);
+        ctx->sitesTouched |= 1u << site;
+    }
+    TRY(haloEnd(ctx, &halo));
+    if (ctx->nCoupled > 0)
+        LAUNCH(k_fix_layer, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
+               (const u8 *)ctx->ghost8, separate, gen, cur);
+    return AMR_OK;
+}
 
 AMR_API int amr_protect_patches(amr_ctx *ctx, const int32_t *patchIds, int nPatchIds, int nLayers, double *errorInOut,
                                 int64_t *nProtected) {
@@ -989,7 +1026,8 @@ AMR_API int amr_protect_patches(amr_ctx *ctx, const int32_t *patchIds, int nPatc
     double *dE = nullptr;
     TRY(stageInOut(ctx, errorInOut, n, &dE));
     double *e = dE ? dE : ctx->error;
-    u8 *cur = ctx->flagA, *tmp = ctx->flagB;
+    u8 *cur = ctx->flagA;
+    TRY(sitesBegin(ctx));
     CK(cudaMemsetAsync(cur, 0, (size_t)n, ctx->stream));
     for (int k = 0; k < nPatchIds; k++) {
         int q = patchIds[k];
@@ -997,25 +1035,32 @@ AMR_API int amr_protect_patches(amr_ctx *ctx, const int32_t *patchIds, int nPatc
         const Patch &pp = ctx->patches[q];
         if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)1);
     }
+    int gen = 1;
     for (int i = 0; i < nLayers; i++) {
-        u8 *res;
-        TRY(extendLayer(ctx, cur, cur, tmp, &res, siteOf(kSiteProtect, i)));
-        std::swap(cur, tmp);
+        if (gen >= 250) {                 // renormalise the generations (errorEstimator.C:347 can ask for many layers)
+            if (n) LAUNCH(k_flags_normalize, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)cur, cur, (((uintptr_t)cur) & 15) == 0);
+            gen = 1;
+        }
+        TRY(extendLayer(ctx, cur, nullptr, gen, siteOf(kSiteProtect, i)));
+        gen++;
     }
     CK(cudaMemsetAsync(ctx->dCount, 0, sizeof(int64_t), ctx->stream));
     if (n) LAUNCH(k_zero_protected, gridFor(n), kThreads, n, cur, e, (unsigned long long *)ctx->dCount);
     if (dE && n && dE != ctx->error) CK(cudaMemcpyAsync(ctx->error, dE, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->hCount, ctx->dCount, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sitesFetch(ctx));
+    ctx->hostTouched = true;              // the count is a host output: complete on return
     CK(cudaGetLastError());
     TRY(flushOuts(ctx));
+    sitesCommit(ctx);
     if (nProtected) *nProtected = ctx->hCount[0];
     return AMR_OK;
 }
 
 // ============================================================================ stages 2+3
 
-// Ascending list from flags.  emitListAsync enqueues the compaction; finishList reads the count back
-// (one sync, shared with the caller's convergence flag when it passes extraFlagSlot >= 0) and copies
+// Ascending list from flags.  emitListAsync enqueues the (single-pass) compaction; finishList reads the count back
+// (one sync, shared with the caller's convergence flag when it passes flagSlot >= 0) and copies
 // the entries to a host destination.
 struct ListJob {
     int32_t *dList = nullptr;
@@ -1023,7 +1068,7 @@ struct ListJob {
     int32_t *userOut = nullptr;
     bool hostOut = false;
 };
-static int emitListAsync(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *userOut, ListJob *job) {
+static int listTarget(amr_ctx *ctx, int64_t N, int32_t *userOut, ListJob *job) {
     job->userOut = userOut;
     job->hostOut = userOut && !isDevicePtr(userOut);
     if (userOut) {
@@ -1031,6 +1076,10 @@ static int emitListAsync(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *user
             if (!job->dList) { void *q; TRY(arenaAlloc(ctx, &q, (size_t)(N > 0 ? N : 1) * 4)); job->dList = (int32_t *)q; }
         } else job->dList = userOut;
     }
+    return AMR_OK;
+}
+static int emitListAsync(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *userOut, ListJob *job) {
+    TRY(listTarget(ctx, N, userOut, job));
     TRY(compactFlags(ctx, flags, N, job->dList, &job->dTotal));
     return AMR_OK;
 }
@@ -1041,9 +1090,11 @@ static int finishList(amr_ctx *ctx, ListJob *job, int flagSlot, int *flagValue, 
         CK(cudaMemcpyAsync(ctx->hFlags + flagSlot, ctx->dFlags + flagSlot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaMemcpyAsync(ctx->hFlags + 8, job->dTotal, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sitesFetch(ctx));
     PEER_ERR_FETCH();
     CK(cudaStreamSynchronize(ctx->stream));
     PEER_ERR_CHECK();
+    sitesCommit(ctx);
     if (flagSlot >= 0 && flagValue) *flagValue = ctx->hFlags[flagSlot];
     const int32_t total = ctx->hFlags[8];
     if (nOut) *nOut = total;
@@ -1067,77 +1118,154 @@ static int emitList(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *userOut, 
     return finishList(ctx, &job, -1, nullptr, nOut, true);
 }
 
-// hexRef::consistentRefinement loop (hexRef.C:1421-1437) on set/lf, followed by the ascending list
-// (hexRef.C:1440-1460).  The list is compacted speculatively after every sweep so that the
-// convergence flag and the list size come back in ONE host round trip per sweep.
-static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut,
-                        bool edgeRule = false) {
+// |dLevel| <= 1 over the internal faces of this rank's mesh, checked once per mesh (hexRef::checkRefinementLevels is
+// what guarantees it in the reference: hexRef.C:2934-3025, called after every topology change)
+static int ensureBalanceChecked(amr_ctx *ctx) {
+    if (ctx->balancedLocal >= 0 || !ctx->lvl) return AMR_OK;
+    const int64_t n = ctx->n;
+    CK(cudaMemsetAsync(ctx->dCount + 3, 0, 8, ctx->stream));
+    if (n) LAUNCH(k_check_levels, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const label *)ctx->lvl, (unsigned long long *)(ctx->dCount + 3));
+    CK(cudaMemcpyAsync(ctx->hCount + 3, ctx->dCount + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->balancedLocal = ctx->hCount[3] == 0 ? 1 : 0;
+    return AMR_OK;
+}
+static int ensureQueues(amr_ctx *ctx, int64_t need) {
+    if (need <= ctx->queueCap) return AMR_OK;
+    devFree(ctx, &ctx->queue[0]); devFree(ctx, &ctx->queue[1]);
+    TRY(devAlloc(ctx, &ctx->queue[0], need)); TRY(devAlloc(ctx, &ctx->queue[1], need));
+    ctx->queueCap = need;
+    return AMR_OK;
+}
+// grid of a queue kernel: enough CTAs to fill the device, the kernels stride over the queue
+static inline unsigned queueGrid(const amr_ctx *ctx) { return (unsigned)(ctx->numSMs * 8); }
+
+// One host look at a speculatively enqueued queue loop: sizes of queues [1, issued] (summed over ranks), the list size
+// (optional) and the by-product counts in ONE round trip.  Returns the index of the first empty queue, or 0.
+static int queueLook(amr_ctx *ctx, const int *gq, int issued, const int32_t *dTotal) {
+    CK(cudaMemcpyAsync(ctx->hQ, gq, (size_t)(issued + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dTotal) CK(cudaMemcpyAsync(ctx->hFlags + 8, dTotal, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(sitesFetch(ctx));
+    PEER_ERR_FETCH();
+    CK(cudaStreamSynchronize(ctx->stream));
+    PEER_ERR_CHECK();
+    sitesCommit(ctx);
+    ctx->lookResult = 0;
+    for (int j = 1; j <= issued; j++)
+        if (ctx->hQ[j] == 0) { ctx->lookResult = j; break; }
+    return AMR_OK;
+}
+
+// hexRef::consistentRefinement(maxSet = true) as queue iterations (kernels_sparse.cuh (2)) + the ascending list
+// (hexRef.C:1440-1460).  The iterations the previous call needed are enqueued in one go, each launch gated on the
+// device by the (all-reduced) size of its queue, then the list is compacted and the host looks ONCE; only if the
+// closure needed more iterations than last time does the host look again.
+static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut) {
+    const int64_t n = ctx->n;
+    TRY(ensureQueues(ctx, n + 16));
+    const bool multi = ctx->comm && ctx->nranks > 1;
+    const bool speculate = gatedSwapsOk(ctx);
+    int *qc = ctx->dQ, *gq = multi ? ctx->dGQ : ctx->dQ;
+    const int64_t cap = ctx->queueCap;
+    const label *cf = ctx->cplFace, *bo = ctx->owner + ctx->f;
+    CK(cudaMemsetAsync(ctx->dQ, 0, 2 * (kMaxIter + 2) * sizeof(int), ctx->stream));
+    ListJob job;
+    TRY(listTarget(ctx, n, cellsOut, &job));
+    // sweep 0: the rows of all marked cells
+    {
+        HaloToken halo;
+        if (ctx->nCoupled > 0) TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo));     // lf as it is before the sweep, like the reference's neiLevel
+        if (n) LAUNCH(k_refine_push0, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, lf, set,
+                      ((((uintptr_t)set)) & 15) == 0, ctx->queue[1], qc + 1, cap);
+        TRY(haloEnd(ctx, &halo));
+        if (ctx->nCoupled > 0)
+            LAUNCH(k_fix_refine_queue, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set,
+                   ctx->queue[1], qc + 1, cap, (const int *)nullptr);
+        if (multi) TRY(allReduceWord(ctx, gq + 1, 4, qc + 1));
+    }
+    int issued = 1;                       // queues [1, issued] have been produced
+    int batch = speculate ? std::max(1, ctx->itersSeen[0] - 1) : 0;
+    int iters = 0;
+    while (true) {
+        for (int k = 0; k < batch && issued < kMaxIter; k++) {
+            const int j = issued;
+            const int *gate = gq + j;
+            const int *xgate = speculate ? gate : nullptr;             // host-checked iterations are never dead
+            HaloToken halo;
+            if (ctx->nCoupled > 0) TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo, nullptr, xgate));
+            LAUNCH(k_refine_frontier, queueGrid(ctx), kThreads, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, lf, set,
+                   (const label *)ctx->queue[j & 1], (const int *)(qc + j), ctx->queue[(j + 1) & 1], qc + j + 1, cap, gate);
+            TRY(haloEnd(ctx, &halo));
+            if (ctx->nCoupled > 0)
+                LAUNCH(k_fix_refine_queue, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set,
+                       ctx->queue[(j + 1) & 1], qc + j + 1, cap, xgate);
+            if (multi) TRY(allReduceWord(ctx, gq + j + 1, 4, qc + j + 1, xgate));
+            issued++;
+        }
+        TRY(compactFlags(ctx, set, n, job.dList, &job.dTotal));          // speculative: valid if the loop has converged
+        TRY(queueLook(ctx, gq, issued, job.dTotal));
+        if (ctx->lookResult) { iters = ctx->lookResult; break; }
+        if (issued >= kMaxIter) FAIL(AMR_ERR_INVARIANT, "2:1 closure did not settle (more queue iterations than refinement levels can need)");
+        batch = speculate ? 2 : 1;
+    }
+    ctx->itersSeen[0] = iters;
+    if (nOut) *nOut = ctx->hFlags[8];
+    TRY(finishListCopy(ctx, &job));
+    if (sweepsOut) *sweepsOut = iters;
+    return AMR_OK;
+}
+
+// hexRef::consistentRefinement loop (hexRef.C:1421-1437) with dense sweeps: maxSet = false, the polyRefiner's edge rule
+// (refinement::consistentRefinement, refinement.C:776-780: the edge rule first, then the face rule), and meshes that
+// are not 2:1 balanced.  One host round trip per sweep; the ascending list (hexRef.C:1440-1460) after the last one.
+static int refineSweepsDense(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut, bool edgeRule) {
     const int64_t n = ctx->n;
     int sweeps = 0;
-    ListJob job;
-    // the sparse form of the maxSet sweep is only valid on a locally 2:1-balanced mesh: verified once per mesh
-    bool pushOk = maxSet && !edgeRule && ctx->pushNum > 0 && n >= ctx->pushMinCells && n > 0 && ctx->lvl;
-    if (pushOk && ctx->balancedLocal < 0) {
-        CK(cudaMemsetAsync(ctx->dCount + 3, 0, 8, ctx->stream));
-        LAUNCH(k_check_levels, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const label *)ctx->lvl, (unsigned long long *)(ctx->dCount + 3));
-        CK(cudaMemcpyAsync(ctx->hCount + 3, ctx->dCount + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->balancedLocal = ctx->hCount[3] == 0 ? 1 : 0;
-    }
-    pushOk = pushOk && ctx->balancedLocal == 1;
     while (true) {
         CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(int), ctx->stream));
-        // refinement::consistentRefinement (refinement.C:776-780): the edge rule first, then the face rule
         if (edgeRule && ctx->nEdges) {
             if (maxSet) LAUNCH((k_edge_refine_sweep<true>), gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, lf, set, ctx->dFlags);
             else LAUNCH((k_edge_refine_sweep<false>), gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, lf, set, ctx->dFlags);
         }
         HaloToken halo;
-        if (ctx->nCoupled > 0) {
-            TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo));          // lf as it is before this sweep, like the reference's neiLevel
-        }
+        if (ctx->nCoupled > 0) TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo));
         if (n) {
-            const int *gate = nullptr;
-            if (pushOk) {
-                const int site = siteOf(kSiteSweep, sweeps);
-                const bool al = ((((uintptr_t)set) | ((uintptr_t)lf)) & 15) == 0;
-                unsigned long long *total = (unsigned long long *)(ctx->dCount + 1);
-                const long long seen = ctx->hMarked[site];
-                const bool tryPush = seen < 0 || seen * ctx->pushDen < 2 * n * ctx->pushNum;
-                CK(cudaMemsetAsync(total, 0, 8, ctx->stream));
-                LAUNCH(k_count_set16, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)set, al, total);
-                CK(cudaMemcpyAsync(ctx->hMarked + site, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-                if (tryPush) {
-                    int *g = ctx->dFlags + 13;
-                    LAUNCH(k_push_gate, 1, 1, (const unsigned long long *)total, (long long)n, (long long)ctx->pushNum, (long long)ctx->pushDen, g);
-                    LAUNCH(k_refine_push, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, lf, set, al,
-                           ctx->dFlags, (const int *)g);
-                    gate = g;
-                }
-            }
             if (pipeOk(ctx, ctx->cc)) {
-                if (maxSet) TRY(launchPipe(ctx, kp_refine_sweep<true>, ctx->cc, lf, set, ctx->dFlags, gate));
-                else TRY(launchPipe(ctx, kp_refine_sweep<false>, ctx->cc, lf, set, ctx->dFlags, gate));
-            } else if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->dFlags, gate);
+                if (maxSet) TRY(launchPipe(ctx, kp_refine_sweep<true>, ctx->cc, lf, set, ctx->dFlags, (const int *)nullptr));
+                else TRY(launchPipe(ctx, kp_refine_sweep<false>, ctx->cc, lf, set, ctx->dFlags, (const int *)nullptr));
+            } else if (maxSet) LAUNCH(k_refine_sweep_max, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->dFlags, (const int *)nullptr);
             else LAUNCH(k_refine_sweep_min, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, lf, set, ctx->dFlags);
-            TRY(haloEnd(ctx, &halo));
-            if (ctx->nCoupled > 0) {      // hexRef.C:758-780
-                if (maxSet) LAUNCH((k_fix_refine_sweep<true>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
-                                   (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
-                else LAUNCH((k_fix_refine_sweep<false>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
-                            (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
-            }
+        }
+        TRY(haloEnd(ctx, &halo));
+        if (ctx->nCoupled > 0 && n) {      // hexRef.C:758-780
+            if (maxSet) LAUNCH((k_fix_refine_sweep<true>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
+                               (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
+            else LAUNCH((k_fix_refine_sweep<false>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
+                        (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
         }
         sweeps++;
-        TRY(emitListAsync(ctx, set, n, cellsOut, &job));
         int changed = 0;
-        TRY(finishList(ctx, &job, 0, &changed, nOut, false));
+        TRY(globalFlag(ctx, 0, &changed));
         if (!changed) break;
         if (sweeps > 100000) FAIL(AMR_ERR_INVARIANT, "2:1 sweeps did not converge");
     }
-    TRY(finishListCopy(ctx, &job));
+    ListJob job;
+    TRY(emitListAsync(ctx, set, n, cellsOut, &job));
+    TRY(finishList(ctx, &job, -1, nullptr, nOut, true));
     if (sweepsOut) *sweepsOut = sweeps;
     return AMR_OK;
+}
+
+static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut,
+                        bool edgeRule = false) {
+    // the queue form is only valid on a locally 2:1-balanced mesh: verified once per mesh
+    bool queueOk = maxSet && !edgeRule && ctx->pushNum > 0 && ctx->n > 0 && ctx->lvl;
+    if (queueOk) {
+        TRY(ensureBalanceChecked(ctx));
+        queueOk = ctx->balancedLocal == 1;
+    }
+    if (queueOk) return refineClosureQueue(ctx, set, lf, sweepsOut, cellsOut, nOut);
+    return refineSweepsDense(ctx, maxSet, set, lf, sweepsOut, cellsOut, nOut, edgeRule);
 }
 
 // fvMeshHexRefiner::calculateProtectedCells (fvMeshHexRefiner.C:60-179): closure of protectedCell_
@@ -1212,11 +1340,12 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
     if (!ctx->haveLevels) FAIL(AMR_ERR_STATE, "amr_select_refine: levels not set");
     if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D && refinerKind != AMR_REFINER_POLY3D &&
         refinerKind != AMR_REFINER_POLY2D)
-        FAIL(AMR_ERR_ARG, "amr_select_refine: prismatic2DRefinement (polyRefiner in 2-D) is not on the device path");
+        FAIL(AMR_ERR_ARG, "amr_select_refine: unknown refiner kind");
     const bool poly = refinerKind == AMR_REFINER_POLY3D || refinerKind == AMR_REFINER_POLY2D;
     if (poly && ctx->optEdgeConsistency && !ctx->haveEdges)
         FAIL(AMR_ERR_STATE, "amr_select_refine: polyRefiner with edgeBasedConsistency needs amr_mesh_set_edges");
     if (nProtectedPatches > 0 && !protectedPatchIds) FAIL(AMR_ERR_ARG, "amr_select_refine: protectedPatchIds is null");
+    if (nBufferLayers > 250) FAIL(AMR_ERR_ARG, "amr_select_refine: more than 250 buffer layers");
     const int64_t n = ctx->n;
     const double *dErr = nullptr;
     const int32_t *dMax = nullptr;
@@ -1228,8 +1357,11 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
     TRY(stageIn(ctx, maxCellLevel, n, &dMax));
     u8 *dRcOut = nullptr;
     TRY(stageOut(ctx, refineCellOut, n, &dRcOut));
+    TRY(sitesBegin(ctx));
 
-    u8 *cur = ctx->flagA, *tmp = ctx->flagB, *src0 = ctx->flagC;
+    // the marking (the reference's refineCell) is built in place in the resident buffer and stays there for the
+    // unrefinement stage
+    u8 *cur = ctx->refineCell, *src0 = ctx->flagC;
     // hexRefiner always passes force=true (fvMeshHexRefiner.C:1511), polyRefiner passes force_ (fvMeshPolyRefiner.C:338)
     const bool forced = poly ? (ctx->optPolyForce != 0) : true;
     // M1 (+ source mask of the first forced layer)
@@ -1239,10 +1371,10 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
                       (nBufferLayers > 0 && forced) ? src0 : (u8 *)nullptr, al);
     }
     // M2: extendMarkedCells(refineCell, maxRefinement, i == 0, force = true), fvMeshHexRefiner.C:1509-1512
+    int gen = 1;
     for (int i = 0; i < nBufferLayers; i++) {
-        u8 *res;
-        TRY(extendLayer(ctx, cur, (i == 0 && forced) ? src0 : cur, tmp, &res, siteOf(kSiteRefine, i)));
-        std::swap(cur, tmp);
+        TRY(extendLayer(ctx, cur, (i == 0 && forced) ? src0 : (const u8 *)nullptr, gen, siteOf(kSiteRefine, i)));
+        gen++;
     }
     // M3: protections, fvMeshHexRefiner.C:1514-1533 (polyRefiner: patches only, fvMeshPolyRefiner.C:341-350)
     for (int k = 0; k < nProtectedPatches; k++) {
@@ -1252,17 +1384,12 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
         if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)0);
     }
     if (!poly && ctx->protCell && n) LAUNCH(k_masked_set, gridFor(n), kThreads, n, ctx->protCell, cur, (u8)0);
-    // keep the marking (the reference's refineCell) resident for the unrefinement stage: the buffer
-    // that holds it BECOMES ctx->refineCell (pointer swap, no copy)
-    if (cur == ctx->flagA) std::swap(ctx->flagA, ctx->refineCell);
-    else if (cur == ctx->flagB) std::swap(ctx->flagB, ctx->refineCell);
-    else std::swap(ctx->flagC, ctx->refineCell);
-    cur = ctx->refineCell;
     ctx->refineCellN = n;
-    if (dRcOut && n) CK(cudaMemcpyAsync(dRcOut, cur, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->refineCellGen = gen;
+    if (dRcOut && n) LAUNCH(k_flags_normalize, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)cur, dRcOut, ((((uintptr_t)cur) | ((uintptr_t)dRcOut)) & 15) == 0);
 
     // M4/M5: selectRefineCells, fvMeshHexRefiner.C:306-391
-    u8 *set = ctx->flagA;             // the ping-pong buffers are free now
+    u8 *set = ctx->flagA;
     u8 *unref = ctx->flagB;
     bool haveU = false;
     if (poly) {
@@ -1333,6 +1460,7 @@ AMR_API int amr_consistent_refinement(amr_ctx *ctx, const int32_t *cellsIn, int6
     const int64_t n = ctx->n;
     const int32_t *dIn = nullptr;
     TRY(stageIn(ctx, cellsIn, nIn, &dIn));
+    TRY(sitesBegin(ctx));
     u8 *set = ctx->flagA;
     CK(cudaMemsetAsync(set, 0, (size_t)n, ctx->stream));
     if (nIn > 0) LAUNCH(k_list_to_flags, gridFor(nIn), kThreads, nIn, dIn, set);
@@ -1381,6 +1509,7 @@ AMR_API int amr_remap_refine_cell(amr_ctx *ctx, int64_t nOld, int64_t nNew, cons
         ctx->refineCell = dNew; ctx->refineCellN = nNew;
         ctx->refineCellOversize = true;
     }
+    ctx->refineCellGen = 1;              // the remapped marking is a plain boolList again
     CK(cudaGetLastError());
     return AMR_OK;
 }
@@ -1423,8 +1552,124 @@ static int selectUnrefinePoints(amr_ctx *ctx, const double *dErr, double unrefin
     return AMR_OK;
 }
 
-// hexRef3D::consistentUnrefinement loop (hexRef3D.C:1758-1927) on point flags + ascending list
-// (hexRef3D.C:1930-1950), list compacted speculatively after each sweep (one round trip per sweep)
+// hexRef3D::getSplitElems (hexRef3D.C:2183-2321) depends on the mesh, the levels and the refinement history only: the
+// ascending split-point list, the 8 cells of every split point and the split point of every cell are built ONCE per
+// mesh (amr_mesh_set_points / amr_levels_set invalidate them).  The per-step work of the unrefinement branch then
+// never touches the pointCells addressing again.
+static int ensureSplitTable(amr_ctx *ctx) {
+    if (!ctx->spDirty) return AMR_OK;
+    const int64_t n = ctx->n, p = ctx->p;
+    devFree(ctx, &ctx->spPoint); devFree(ctx, &ctx->spCells); devFree(ctx, &ctx->cellSp); devFree(ctx, &ctx->spFlag); devFree(ctx, &ctx->spList);
+    ctx->nSp = 0;
+    u8 *isSplit = ctx->flagC;
+    TRY(selectUnrefinePoints(ctx, (const double *)nullptr, 0.0, (const u8 *)nullptr, isSplit, (u8 *)nullptr));
+    CK(cudaMemsetAsync(ctx->dCount + 2, 0, 8, ctx->stream));
+    if (p) LAUNCH(k_count_flags, gridFor(p), kThreads, p, (const u8 *)isSplit, (unsigned long long *)(ctx->dCount + 2));
+    CK(cudaMemcpyAsync(ctx->hCount + 2, ctx->dCount + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int64_t nSp = ctx->hCount[2];
+    TRY(devAlloc(ctx, &ctx->spPoint, nSp)); TRY(devAlloc(ctx, &ctx->spCells, 8 * nSp)); TRY(devAlloc(ctx, &ctx->cellSp, n + 4));
+    TRY(devAlloc(ctx, &ctx->spFlag, nSp + 16)); TRY(devAlloc(ctx, &ctx->spList, nSp));
+    CK(cudaMemsetAsync(ctx->cellSp, 0xFF, (size_t)(n + 4) * 4, ctx->stream));
+    int32_t *dTotal = nullptr;
+    TRY(compactFlags(ctx, isSplit, p, ctx->spPoint, &dTotal));
+    if (nSp) LAUNCH(k_sp_table, gridFor(nSp), kThreads, nSp, (const label *)ctx->spPoint, ctx->pc.sliceOff, ctx->pc.col, ctx->spCells, ctx->cellSp);
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nSp = nSp;
+    ctx->spDirty = false;
+    return AMR_OK;
+}
+
+// hexRef3D::selectUnrefineElems + consistentUnrefinement on the split-point table (kernels_sparse.cuh (3)) + the
+// ascending list (hexRef3D.C:1930-1950).  Same speculation as refineClosureQueue: one host look per call.
+static int unrefineClosureQueue(amr_ctx *ctx, const double *dErr, double unrefineLevel, const u8 *marked, int *sweepsOut,
+                                int32_t *elemsOut, int64_t *nOut) {
+    const int64_t n = ctx->n, nSp = ctx->nSp;
+    TRY(ensureQueues(ctx, std::max(n, nSp) + 16));
+    const bool multi = ctx->comm && ctx->nranks > 1;
+    const bool speculate = gatedSwapsOk(ctx);
+    int *qc = ctx->dQ, *gq = multi ? ctx->dGQ : ctx->dQ;
+    const int64_t cap = ctx->queueCap;
+    const label *cf = ctx->cplFace, *bo = ctx->owner + ctx->f;
+    u8 *uc = ctx->flagB, *spFlag = ctx->spFlag;
+    ListJob job;
+    TRY(listTarget(ctx, std::max<int64_t>(nSp, 1), elemsOut, &job));
+    CK(cudaMemsetAsync(ctx->dQ, 0, 2 * (kMaxIter + 2) * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(uc, 0, (size_t)n, ctx->stream));
+    CK(cudaMemsetAsync(spFlag, 1, (size_t)nSp, ctx->stream));
+    // U1 + U3: pFld < unrefineLevel and no marked cell, cell-centric (the split points themselves are mesh-constant)
+    if (n && nSp) LAUNCH(k_sp_filter, gridFor(n, kThreads * 4), kThreads, n, (const label *)ctx->cellSp, dErr, unrefineLevel, marked, spFlag);
+    // the candidates as a compact list; unrefineCell = their cells
+    int32_t *nList = nullptr;
+    TRY(compactFlagsEx(ctx, spFlag, nSp, nullptr, nullptr, nullptr, ctx->spList, &nList, 1, nullptr));
+    const unsigned qg = queueGrid(ctx);
+    if (nSp) LAUNCH(k_sp_to_cells, qg, kThreads, (const label *)ctx->spList, (const int32_t *)nList, nSp, (const label *)ctx->spCells, uc);
+    // sweep 0
+    {
+        HaloToken halo;
+        if (ctx->nCoupled > 0) TRY(haloBegin(ctx, ctx->lvl8, 1, ctx->ghost8, &halo, uc));     // cellLevel - unrefineCell (hexRef3D.C:1843-1853)
+        if (nSp) LAUNCH(k_unref_sweep0, qg, kThreads, (const label *)ctx->spList, (const int32_t *)nList, nSp, (const label *)ctx->spCells,
+                        ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, spFlag, uc, ctx->queue[1], qc + 1, cap);
+        TRY(haloEnd(ctx, &halo));
+        if (ctx->nCoupled > 0)
+            LAUNCH(k_fix_unref_queue, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, nSp,
+                   (const label *)ctx->spCells, (const label *)ctx->cellSp, spFlag, uc, ctx->queue[1], qc + 1, cap, (const int *)nullptr);
+        if (multi) TRY(allReduceWord(ctx, gq + 1, 4, qc + 1));
+    }
+    int issued = 1;
+    int batch = speculate ? std::max(1, ctx->itersSeen[1] - 1) : 0;
+    int iters = 0;
+    while (true) {
+        for (int k = 0; k < batch && issued < kMaxIter; k++) {
+            const int j = issued;
+            const int *gate = gq + j;
+            const int *xgate = speculate ? gate : nullptr;
+            HaloToken halo;
+            if (ctx->nCoupled > 0) TRY(haloBegin(ctx, ctx->lvl8, 1, ctx->ghost8, &halo, uc, xgate));
+            LAUNCH(k_unref_frontier, qg, kThreads, (const label *)ctx->queue[j & 1], (const int *)(qc + j), nSp, (const label *)ctx->spCells,
+                   (const label *)ctx->cellSp, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, spFlag, uc, ctx->queue[(j + 1) & 1], qc + j + 1, cap, gate);
+            TRY(haloEnd(ctx, &halo));
+            if (ctx->nCoupled > 0)
+                LAUNCH(k_fix_unref_queue, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, nSp,
+                       (const label *)ctx->spCells, (const label *)ctx->cellSp, spFlag, uc, ctx->queue[(j + 1) & 1], qc + j + 1, cap, xgate);
+            if (multi) TRY(allReduceWord(ctx, gq + j + 1, 4, qc + j + 1, xgate));
+            issued++;
+        }
+        // ascending point list of the surviving candidates (speculative: valid if the loop has converged)
+        TRY(compactFlagsEx(ctx, spFlag, nSp, nList, (const label *)ctx->spList, (const label *)ctx->spPoint, job.dList, &job.dTotal, 0, nullptr));
+        TRY(queueLook(ctx, gq, issued, job.dTotal));
+        if (ctx->lookResult) { iters = ctx->lookResult; break; }
+        if (issued >= kMaxIter) FAIL(AMR_ERR_INVARIANT, "unrefinement closure did not settle");
+        batch = speculate ? 2 : 1;
+    }
+    ctx->itersSeen[1] = iters;
+    // hexRef3D.C:1808-1833 "problem": only an unbalanced mesh can produce it
+    TRY(ensureBalanceChecked(ctx));
+    if (ctx->balancedLocal == 0 || ctx->nCoupled > 0) {
+        bool check = ctx->balancedLocal == 0;
+        if (ctx->nCoupled > 0 && ctx->balancedGlobal < 0) check = true;      // coupled faces not verified yet: look once
+        if (check) {
+            CK(cudaMemsetAsync(ctx->dFlags + 1, 0, sizeof(int), ctx->stream));
+            if (ctx->nCoupled > 0) TRY(haloSwapCells(ctx, ctx->lvl8, 1, ctx->ghost8, uc));
+            if (n) LAUNCH(k_unref_problem, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, (const u8 *)uc, ctx->dFlags + 1);
+            if (ctx->nCoupled > 0)
+                LAUNCH(k_fix_unref_problem, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8,
+                       (const u8 *)uc, ctx->dFlags + 1);
+            int problem = 0;
+            TRY(globalFlag(ctx, 1, &problem));
+            if (problem) FAIL(AMR_ERR_INVARIANT, "problem (hexRef3D.C:1811): an unmarked cell is more than one level coarser than a face neighbour");
+            if (ctx->balancedLocal == 1) ctx->balancedGlobal = 1;          // holds for every marking: levels alone decide it
+        }
+    }
+    if (nOut) *nOut = ctx->hFlags[8];
+    TRY(finishListCopy(ctx, &job));
+    if (sweepsOut) *sweepsOut = iters;
+    return AMR_OK;
+}
+
+// hexRef3D::consistentUnrefinement loop (hexRef3D.C:1758-1927) on point (edge) flags + ascending list
+// (hexRef3D.C:1930-1950): the generic form for split elements given by a point->cells / edge->cells addressing
+// (hexRef2D, polyRefiner).  One host round trip per sweep.
 static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOut, int32_t *elemsOut, int64_t *nOut,
                           bool edgeRule = false) {
     const int64_t n = ctx->n, p = EL.rows;
@@ -1432,7 +1677,6 @@ static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOu
     const bool alP = (((uintptr_t)pflag) & 15) == 0, alC = (((uintptr_t)uc) & 15) == 0;
     const unsigned gP = gridFor(p, kThreads * 16), gC = gridFor(n, kThreads * 16);
     int sweeps = 0;
-    ListJob job;
     while (true) {
         CK(cudaMemsetAsync(uc, 0, (size_t)n, ctx->stream));
         if (p) LAUNCH(k_points_to_cells, gP, kThreads, p, EL.sliceOff, EL.col, pflag, alP, uc);
@@ -1448,14 +1692,15 @@ static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOu
         if (edgeRule && ctx->nEdges)
             LAUNCH(k_edge_unrefine_sweep, gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, (const u8 *)ctx->lvl8, uc, ctx->dFlags);
         sweeps++;
-        TRY(emitListAsync(ctx, pflag, p, elemsOut, &job));
         int changed = 0;
-        TRY(finishList(ctx, &job, 0, &changed, nOut, false));
+        TRY(globalFlag(ctx, 0, &changed));
         if (!changed) break;
         if (p) LAUNCH(k_knock_points, gP, kThreads, p, EL.sliceOff, EL.col, pflag, alP, uc);
         if (sweeps > 100000) FAIL(AMR_ERR_INVARIANT, "unrefinement sweeps did not converge");
     }
-    TRY(finishListCopy(ctx, &job));
+    ListJob job;
+    TRY(emitListAsync(ctx, pflag, p, elemsOut, &job));
+    TRY(finishList(ctx, &job, -1, nullptr, nOut, true));
     if (sweepsOut) *sweepsOut = sweeps;
     return AMR_OK;
 }
@@ -1497,21 +1742,29 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     }
     if (refinerKind == AMR_REFINER_HEX2D && !ctx->haveEdges) FAIL(AMR_ERR_STATE, "amr_select_unrefine: hexRef2D needs amr_mesh_set_edges");
     if (nProtectedPatches > 0 && !protectedPatchIds) FAIL(AMR_ERR_ARG, "amr_select_unrefine: protectedPatchIds is null");
+    if (nBufferLayers > 200) FAIL(AMR_ERR_ARG, "amr_select_unrefine: more than 200 buffer layers");
     const int64_t n = ctx->n, p = ctx->p;
     const double *dErr = nullptr;
     TRY(stageIn(ctx, error, n, &dErr));
     if (!dErr) dErr = ctx->error;
     u8 *dRc = nullptr;
     TRY(stageInOut(ctx, refineCellInOut, n, &dRc));
-    // the marking lives in the flag-buffer pool; layers ping-pong and the result becomes ctx->refineCell
+    TRY(sitesBegin(ctx));
+    // the marking lives in the resident buffer; the layers grow it in place
+    u8 *cur = ctx->refineCell;
+    int gen = ctx->refineCellGen;
     if (dRc) {
-        if (n) CK(cudaMemcpyAsync(ctx->refineCell, dRc, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (n) LAUNCH(k_flags_normalize, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)dRc, cur, ((((uintptr_t)cur) | ((uintptr_t)dRc)) & 15) == 0);
         ctx->refineCellN = n;
+        gen = 1;
     } else if (ctx->refineCellN != n) {
         FAIL(AMR_ERR_STATE, "amr_select_unrefine: resident marking has the wrong size (amr_remap_refine_cell after the topology change)");
     }
+    if (gen + nBufferLayers >= 250) {
+        if (n) LAUNCH(k_flags_normalize, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)cur, cur, (((uintptr_t)cur) & 15) == 0);
+        gen = 1;
+    }
     // nUnrefinementBufferLayers x extendMarkedCellsAcrossFaces, fvMeshHexRefiner.C:1595-1598
-    u8 *cur = ctx->refineCell, *tmp = ctx->flagA;
     if (poly) {
         // extendMarkedCellsAcrossPoints (fvMeshRefiner.C:924-977): cells -> points -> cells, in place (flags only grow)
         for (int i = 0; i < nBufferLayers; i++) {
@@ -1522,12 +1775,11 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
         }
     } else {
         for (int i = 0; i < nBufferLayers; i++) {
-            u8 *res;
-            TRY(extendLayer(ctx, cur, cur, tmp, &res, siteOf(kSiteUnrefine, i)));
-            std::swap(cur, tmp);
+            TRY(extendLayer(ctx, cur, nullptr, gen, siteOf(kSiteUnrefine, i)));
+            gen++;
         }
     }
-    ctx->refineCell = cur; ctx->flagA = tmp;
+    ctx->refineCellGen = gen;
     // protections, fvMeshHexRefiner.C:1600-1622
     if (!poly && ctx->protCell && n) LAUNCH(k_masked_set, gridFor(n), kThreads, n, ctx->protCell, cur, (u8)1);
     for (int k = 0; k < nProtectedPatches; k++) {
@@ -1536,15 +1788,15 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
         const Patch &pp = ctx->patches[q];
         if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)1);
     }
-    if (dRc && n) CK(cudaMemcpyAsync(dRc, cur, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
-    dRc = cur;
+    if (dRc && n) LAUNCH(k_flags_normalize, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)cur, dRc, ((((uintptr_t)cur) | ((uintptr_t)dRc)) & 15) == 0);
+    const u8 *marked = cur;
     // U1+U2+U3 fused: maxCellField + getSplitElems + filter
     u8 *pflag = ctx->flagC;
     if (poly) {
         u8 *bad = ctx->flagA;
         TRY(polySplitMarkup(ctx, prismatic, bad));
         if (p) LAUNCH(k_poly_select_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const label *)ctx->pointLevel, (const u8 *)bad,
-                      dErr, unrefineLevel, (const u8 *)dRc, (u8 *)nullptr, pflag);
+                      dErr, unrefineLevel, marked, (u8 *)nullptr, pflag);
         TRY(unrefineSweeps(ctx, ctx->pc, pflag, sweepsOut, elemsOut, nOut, ctx->optEdgeConsistency != 0));
         CK(cudaGetLastError());
         return flushOuts(ctx);
@@ -1552,14 +1804,14 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     if (refinerKind == AMR_REFINER_HEX2D) {
         const int64_t ne = ctx->nEdges;
         if (ne) LAUNCH(k_select_unrefine_edges, gridFor(ne), kThreads, ne, ctx->ec.sliceOff, ctx->ec.col, ctx->ec.count, ctx->bndEdge,
-                       ctx->edgePts, ctx->pc.sliceOff, ctx->pc.col, ctx->parentIdx, ctx->lvl8, dErr, unrefineLevel, dRc, (u8 *)nullptr, pflag);
+                       ctx->edgePts, ctx->pc.sliceOff, ctx->pc.col, ctx->parentIdx, ctx->lvl8, dErr, unrefineLevel, marked, (u8 *)nullptr, pflag);
         TRY(unrefineSweeps(ctx, ctx->ec, pflag, sweepsOut, elemsOut, nOut));
         CK(cudaGetLastError());
         return flushOuts(ctx);
     }
-    TRY(selectUnrefinePoints(ctx, dErr, unrefineLevel, (const u8 *)dRc, (u8 *)nullptr, pflag));
-    // B3: consistentUnrefinement(list, false) + ascending list   (flagA/flagB are free again)
-    TRY(unrefineSweeps(ctx, ctx->pc, pflag, sweepsOut, elemsOut, nOut));
+    // hexRef3D: B3 on the mesh-constant split-point table
+    TRY(ensureSplitTable(ctx));
+    TRY(unrefineClosureQueue(ctx, dErr, unrefineLevel, marked, sweepsOut, elemsOut, nOut));
     CK(cudaGetLastError());
     return flushOuts(ctx);
 }
@@ -1592,8 +1844,13 @@ AMR_API int amr_get_split_elems(amr_ctx *ctx, int refinerKind, int32_t *elemsOut
         CK(cudaGetLastError());
         return flushOuts(ctx);
     }
-    TRY(selectUnrefinePoints(ctx, (const double *)nullptr, 0.0, (const u8 *)nullptr, pflag, (u8 *)nullptr));
-    TRY(emitList(ctx, pflag, p, elemsOut, nOut));
+    // hexRef3D: the mesh-constant list
+    TRY(ensureSplitTable(ctx));
+    if (nOut) *nOut = ctx->nSp;
+    if (elemsOut && ctx->nSp) {
+        CK(cudaMemcpyAsync(elemsOut, ctx->spPoint, (size_t)ctx->nSp * 4, cudaMemcpyDefault, ctx->stream));
+        if (!isDevicePtr(elemsOut)) ctx->hostTouched = true;
+    }
     CK(cudaGetLastError());
     return flushOuts(ctx);
 }

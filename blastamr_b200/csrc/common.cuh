@@ -22,6 +22,7 @@ constexpr int kThreads = 256;           // CTA size of the cell/point kernels (8
 constexpr int kSlice = 32;              // SELL slice height = one warp
 constexpr double kSMALL = 1e-15;
 constexpr double kGREAT = 1e15;
+constexpr int kMaxIter = 62;            // queue iterations of a closure loop enqueued before the host looks (speculation cap)
 
 struct DevBuf {
     void *p = nullptr;
@@ -61,7 +62,7 @@ struct amr_ctx {
     char *region = nullptr;            // my IPC-exported region
     std::vector<char *> peerHost;      // mapped regions of all ranks (mine included)
     char **peerDev = nullptr;          // same, on the device
-    unsigned haloEpoch = 0, redEpoch = 0;
+    unsigned *dSeq = nullptr;          // device: [0] last completed halo swap, [1] last completed reduction (p2p.cuh)
     unsigned long long peerTimeoutNs = 20000000000ull;   // bound of the device-side spins (AMR_B200_PEER_TIMEOUT_S)
     bool peerTouched = false;          // a peer-memory exchange was enqueued since the error word was last read
     void *haloPlan = nullptr;          // HaloPlan (host copy), rebuilt at amr_mesh_set
@@ -105,7 +106,12 @@ struct amr_ctx {
     double *xbf = nullptr;     // [b] boundaryField of x
     int64_t pushMinCells = 1 << 16;
     int balancedLocal = -1;         // internal faces of the mesh satisfy |dLevel| <= 1 (-1: not checked yet)
-    long long *hMarked = nullptr;   // pinned: marked cells seen per buffer-layer site by the previous call
+    int balancedGlobal = -1;        // ... and the coupled faces, on every rank
+    long long *hMarked = nullptr;   // pinned: source cells seen per buffer-layer / sweep site by the previous call
+    unsigned long long *dMarked = nullptr;   // [16] device: the counts of the current call, by site
+    long long *hMarkedStage = nullptr;       // pinned read-back staging (= hMarked + 16)
+    unsigned sitesTouched = 0;               // sites a layer kernel reported for in this call
+    int lookResult = 0;                      // queueLook: index of the first empty queue, or 0
     int pushNum = 1, pushDen = 4;   // buffer layers take the sparse push form when marked/n < pushNum/pushDen (0 = never)
     label *ppPts = nullptr;         // points of the processor patches, patch after patch (syncPointList pairing)
     std::vector<int32_t> ppOff;     // [npatch+1] offsets into ppPts
@@ -144,9 +150,27 @@ struct amr_ctx {
     u8 *lf = nullptr;                           // [n] level +/- flag
     u8 *ghost8 = nullptr;       // [b] received byte payloads (marks, level +/- flag), boundary-face layout
     double *ghost64 = nullptr;  // [b] received field values
-    int32_t *tileCnt = nullptr;                 // compaction tile counters
+    unsigned long long *lbStatus = nullptr;     // [tileCap] tile status words of the single-pass compaction (scan.cuh)
+    unsigned *lbTicket = nullptr;               // dynamic tile ticket
+    unsigned scanTag = 0;                       // per-call tag of the status words
+    int32_t *dTotals = nullptr;                 // [8] list sizes written by the compaction kernels
     int64_t tileCap = 0;
-    int32_t *scanAux = nullptr; int64_t scanAuxCap = 0;
+    // work queues of the closure loops (kernels_sparse.cuh): queue j lives in queue[j & 1], its size in dQ[j], the size
+    // summed over ranks in dGQ[j]
+    label *queue[2] = {nullptr, nullptr};
+    int64_t queueCap = 0;
+    int *dQ = nullptr, *dGQ = nullptr;          // [kMaxIter + 2] each
+    int *hQ = nullptr;                          // pinned mirror of dGQ then dQ
+    int itersSeen[2] = {-1, -1};                // iterations the refine / unrefine closure needed last time (speculation depth)
+    // split-point table of hexRef3D (mesh-constant: rebuilt when points / levels / history change)
+    bool spDirty = true;
+    int64_t nSp = 0;
+    label *spPoint = nullptr;                   // [nSp] ascending point labels (getSplitElems)
+    label *spCells = nullptr;                   // [8 * nSp] k-th cell of split point i at [k * nSp + i]
+    label *cellSp = nullptr;                    // [n] split point of the cell, or -1
+    u8 *spFlag = nullptr;                       // [nSp + 16]
+    label *spList = nullptr;                    // [nSp] compact list of the split points that passed the filter
+    int refineCellGen = 1;                      // largest generation tag in the resident marking
     int *dFlags = nullptr;                      // [16] device scalars (changed flags, counters)
     int64_t *dCount = nullptr;                  // [4]
     int *hFlags = nullptr;                      // pinned mirror

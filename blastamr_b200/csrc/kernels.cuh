@@ -213,41 +213,6 @@ __global__ void k_pack_u8(int64_t b, const label *__restrict__ bOwner, const u8 
     if (i < b) out[i] = v[bOwner[i]];
 }
 
-// One buffer layer: fvMeshRefiner::extendMarkedCells (fvMeshRefiner.C:794-863) and
-// extendMarkedCellsAcrossFaces (:866-921; errorEstimator.C:367-424).
-//   out[c] = in[c] | OR_{q in faceNbrs(c)} src[q]
-// src == in for plain growth; for the first forced layer src = "marked and can still be refined".
-// The syncFaceList(orEqOp) of the reference is the ghost term: ghost[bface] = src of the cell on
-// the other side of a processor face.
-__global__ void __launch_bounds__(kThreads)
-k_extend(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-         const u8 *__restrict__ in, const u8 *__restrict__ src,
-         u8 *__restrict__ out, const int *__restrict__ gate) {
-    if (gate && *gate == 1) return;                 // the sparse (push) form runs instead
-    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const unsigned live = __ballot_sync(0xffffffffu, c < n);
-    if (c >= n) return;
-    const int64_t s = c >> 5;
-    const int lane = (int)(c & 31);
-    const int32_t base = sliceOff[s];
-    const int w = sliceOff[s + 1] - base;
-    const int32_t *row = col + ((size_t)base << 5) + lane;
-    unsigned m = in[c];
-    // a warp whose 32 cells are all marked has nothing to gather
-    if (__all_sync(live, m != 0)) { out[c] = 1; return; }
-    for (int j0 = 0; j0 < w; j0 += kChunk) {
-        int32_t q[kChunk];
-#pragma unroll
-        for (int k = 0; k < kChunk; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
-#pragma unroll
-        for (int k = 0; k < kChunk; k++) {
-            if (q[k] == (int32_t)c) continue;
-            m |= src[q[k]];
-        }
-    }
-    out[c] = m ? 1 : 0;
-}
-
 // clear / set flags of the cells on the faces of a patch (fvMeshHexRefiner.C:1514-1523, 1612-1621,
 // errorEstimator.C:336-344)
 __global__ void k_patch_cells_set(const label *__restrict__ owner, int64_t start, int64_t size, u8 *__restrict__ flag,
@@ -830,95 +795,6 @@ __device__ __forceinline__ void forEachSetWarp(const u8 *flags, int64_t N, bool 
     __syncwarp();
 }
 
-// ---- sparse form of one buffer layer (fvMeshRefiner.C:866-921): when few cells are marked, walking only the rows
-// of the marked SOURCE cells and pushing the mark to their neighbours reads a fraction of the adjacency.
-// Count -> gate (device-side decision, no host round trip) -> copy in->out -> push; the dense (pull) kernel
-// returns at once when the gate chose the push form, and vice versa.  All pushes store 1: benign races.
-// Measured at 64-78 M cells with the warp-balanced walk: 3 % marked: 0.06 ms instead of 0.33 ms; 21 % marked
-// (clustered): 0.2 ms instead of 0.39 ms; default threshold 1/4 of the cells.
-__global__ void __launch_bounds__(kThreads)
-k_count_set16(int64_t n, const u8 *__restrict__ flags, bool aligned, unsigned long long *__restrict__ total) {
-    const int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 16;
-    int cnt = 0;
-    if (base < n) {
-        if (aligned && base + 16 <= n) {
-            const uint4 w = *reinterpret_cast<const uint4 *>(flags + base);
-            cnt = (__popc(__vcmpne4(w.x, 0u)) + __popc(__vcmpne4(w.y, 0u)) + __popc(__vcmpne4(w.z, 0u)) + __popc(__vcmpne4(w.w, 0u))) >> 3;
-        } else {
-            for (int k = 0; k < 16 && base + k < n; k++) cnt += flags[base + k] != 0;
-        }
-    }
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-    __shared__ int part[kThreads / 32];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int i = 0; i < kThreads / 32; i++) t += part[i];
-        if (t) atomicAdd(total, (unsigned long long)t);
-    }
-}
-// gate = 1 (push form) iff marked * den < n * num
-__global__ void k_push_gate(const unsigned long long *__restrict__ total, long long n, long long num, long long den, int *__restrict__ gate) {
-    *gate = ((long long)*total * den < n * num) ? 1 : 0;
-}
-__global__ void __launch_bounds__(kThreads)
-k_copy_flags_gated(int64_t n, const u8 *__restrict__ in, u8 *__restrict__ out, bool aligned, const int *__restrict__ gate) {
-    if (*gate != 1) return;
-    const int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 16;
-    if (base >= n) return;
-    if (aligned && base + 16 <= n) *reinterpret_cast<uint4 *>(out + base) = *reinterpret_cast<const uint4 *>(in + base);
-    else for (int k = 0; k < 16 && base + k < n; k++) out[base + k] = in[base + k];
-}
-// Sparse form of the maxSet = true sweep (hexRef.C:723-741).  On a mesh that is 2:1 balanced before the step (the
-// reference checks this after every topology change, hexRef.C:2934-3025) only a cell that is marked can stand more
-// than one level above a neighbour, so walking the rows of the marked cells and pushing the mark to every unmarked
-// neighbour with level + 1 < level(c) + 1 reaches the same closure.  Used only when the local mesh was verified
-// balanced (k_check_levels, once per mesh); otherwise the dense form runs.
-__global__ void __launch_bounds__(kThreads)
-k_refine_push(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *__restrict__ lvl8,
-              u8 *lf, u8 *set, bool aligned, int *changed, const int *__restrict__ gate) {
-    if (*gate != 1) return;
-    forEachSetWarp(set, n, aligned, [&](int64_t c) {
-        const int32_t base = sliceOff[c >> 5];
-        const int w = sliceOff[(c >> 5) + 1] - base;
-        const int32_t *row = col + ((size_t)base << 5) + (c & 31);
-        const int mine = (int)lvl8[c] + 1;
-        // batches of 8 neighbours: labels, then levels, then marks -- three rounds of independent loads per batch
-        for (int j0 = 0; j0 < w; j0 += 8) {
-            int32_t q[8];
-            int lq[8];
-            u8 sq[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
-#pragma unroll
-            for (int k = 0; k < 8; k++) lq[k] = lvl8[q[k]];
-#pragma unroll
-            for (int k = 0; k < 8; k++) sq[k] = set[q[k]];
-#pragma unroll
-            for (int k = 0; k < 8; k++)      // padding (q == c) fails the level test
-                if (mine > lq[k] + 1 && !sq[k]) { set[q[k]] = 1; lf[q[k]] = (u8)(lq[k] + 1); *changed = 1; }
-        }
-    });
-}
-__global__ void __launch_bounds__(kThreads)
-k_extend_push(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *__restrict__ src,
-              bool aligned, u8 *__restrict__ out, const int *__restrict__ gate) {
-    if (*gate != 1) return;
-    forEachSetWarp(src, n, aligned, [&](int64_t c) {
-        const int32_t base = sliceOff[c >> 5];
-        const int w = sliceOff[(c >> 5) + 1] - base;
-        const int32_t *row = col + ((size_t)base << 5) + (c & 31);
-        for (int j0 = 0; j0 < w; j0 += 8) {
-            int32_t q[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
-#pragma unroll
-            for (int k = 0; k < 8; k++) out[q[k]] = 1;      // padding writes c itself, which is marked already
-        }
-    });
-}
-
 // unrefineCell = union of pointCells over flagged points (hexRef3D.C:1763-1776); cells pre-zeroed
 __global__ void __launch_bounds__(kThreads)
 k_points_to_cells(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
@@ -987,14 +863,6 @@ k_knock_points(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *_
 // (hexRef.C:758-780, delta.C:110-131, fvMeshRefiner.C:853-862).  cplFace = boundary-face indices
 // (face - f) of the coupled faces; ghost arrays are indexed by boundary face.
 
-// extendMarkedCells: a marked face on the other side marks my owner (syncFaceList orEqOp)
-__global__ void k_fix_extend(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
-                             const u8 *__restrict__ ghostSrc, u8 *__restrict__ out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nC) return;
-    const label bf = cplFace[i];
-    if (ghostSrc[bf]) out[bOwner[bf]] = 1;
-}
 // hexRef::faceConsistentRefinement boundary loop, hexRef.C:758-780 (lf = level + flag)
 template <bool MAXSET>
 __global__ void k_fix_refine_sweep(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,

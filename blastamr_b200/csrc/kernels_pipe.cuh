@@ -83,28 +83,6 @@ kp_estimate(SellView S, const double *__restrict__ x, double p0, double p1, Thre
     });
 }
 
-__global__ void __launch_bounds__(kPipeThreads, 7)
-kp_extend(SellView S, const u8 *__restrict__ in, const u8 *__restrict__ src, u8 *__restrict__ out, const int *__restrict__ gate) {
-    if (gate && *gate == 1) return;                 // the sparse (push) form runs instead (k_extend_push)
-    const int32_t n = (int32_t)S.rows;
-    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool) {
-        const int32_t c = valid ? (int32_t)c64 : n - 1;
-        unsigned m = in[c];
-        // a warp whose 32 cells are all marked has nothing to gather
-        if (!__all_sync(0xffffffffu, m != 0)) {
-            sellRow(row, w, c, [&](auto W, const int32_t *q) {
-                constexpr int NW = decltype(W)::value;
-                unsigned v[NW];
-#pragma unroll
-                for (int k = 0; k < NW; k++) v[k] = src[q[k]];
-#pragma unroll
-                for (int k = 0; k < NW; k++) m |= v[k];   // padding reads src[c] <= in[c]: no-op
-            });
-        }
-        if (valid) out[c] = m ? 1 : 0;
-    });
-}
-
 template <bool MAXSET>
 __global__ void __launch_bounds__(kPipeThreads, 7)
 kp_refine_sweep(SellView S, u8 *lf, u8 *set, int *changed, const int *__restrict__ gate) {

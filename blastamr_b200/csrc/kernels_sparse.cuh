@@ -1,0 +1,421 @@
+// kernels_sparse.cuh -- the marking layers in place, and the two closure loops as work-queue (frontier) iterations.
+//
+// (1) Buffer layers in place.  The marking is a byte per cell; a cell first marked by layer k of a call sequence
+//     holds the generation k+1 (the candidates hold 1).  Layer k treats 0 < v <= gen as sources and writes gen+1,
+//     so one kernel can read and write the same array: a mark written by this layer is never taken for a source of
+//     this layer.  No ping-pong buffer, no copy; every reader of a marking tests "non-zero".  Two forms with identical
+//     results: a dense pull (every unmarked cell gathers over its row; TMA-staged) and a sparse push (the rows of the
+//     source cells only), chosen by the host from the source count the same call site reported last time.
+// (2) hexRef::consistentRefinement (hexRef.C:1402-1468), maxSet = true, on a 2:1-balanced mesh: only a MARKED cell can
+//     stand two levels above a face neighbour, and once a pair (marked c, neighbour q) has been looked at it never
+//     needs another look (levels are fixed, marks only grow).  So: sweep 0 walks the rows of all marked cells and marks
+//     the neighbours the rule forces; every newly marked cell goes to a queue; iteration j walks the rows of queue j
+//     only.  The closure is reached when the queue stays empty -- no confirming sweep over the mesh.
+// (3) hexRef3D::consistentUnrefinement (hexRef3D.C:1719-1953) on a mesh-constant split-point table (the 8 cells of
+//     every split point, each cell belonging to at most one): sweep 0 examines every cell marked for unrefinement; a
+//     cell that would end up more than one level below a neighbour knocks out its split point at once, which unmarks
+//     the point's 8 cells; the knocked points go to a queue, and iteration j looks only at the marked neighbours of the
+//     cells that queue j has just reverted.  Flags only drop and every drop is forced, so this chaotic order reaches
+//     the reference's (greatest) fixed point.
+// All queue appends are made exactly once per element (atomicOr / atomicAnd on the word that holds the flag byte).
+#pragma once
+#include "kernels.cuh"
+#include "kernels_pipe.cuh"
+
+// ---- byte flags inside 32-bit words: exact "I was first" detection without byte atomics
+__device__ __forceinline__ bool setByteOnce(u8 *flags, int64_t i) {          // 0 -> 1; true if this thread did it
+    unsigned *w = reinterpret_cast<unsigned *>(flags + (i & ~(int64_t)3));
+    const unsigned sh = 8u * (unsigned)(i & 3);
+    const unsigned old = atomicOr(w, 1u << sh);
+    return ((old >> sh) & 0xffu) == 0u;
+}
+__device__ __forceinline__ bool clearByteOnce(u8 *flags, int64_t i) {        // non-zero -> 0; true if this thread did it
+    unsigned *w = reinterpret_cast<unsigned *>(flags + (i & ~(int64_t)3));
+    const unsigned sh = 8u * (unsigned)(i & 3);
+    const unsigned old = atomicAnd(w, ~(0xffu << sh));
+    return ((old >> sh) & 0xffu) != 0u;
+}
+
+// block-level count -> one atomic per CTA
+__device__ __forceinline__ void blockAddCount(int cnt, unsigned long long *total) {
+    __shared__ int part[kThreads / 32 + 2];
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += part[i];
+        if (t) atomicAdd(total, (unsigned long long)t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// (1) buffer layers in place
+// ------------------------------------------------------------------------------------------
+
+// source test of a layer: separate source array (the forced first layer) or generation range of the marking itself
+__device__ __forceinline__ bool isSource(unsigned v, int gen, bool separate) { return separate ? v != 0u : (v != 0u && v <= (unsigned)gen); }
+
+// sparse push form: rows of the source cells; marks written are gen+1.  nSrc receives the exact number of sources.
+__global__ void __launch_bounds__(kThreads)
+k_layer_push(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *srcArr, bool separate,
+             int gen, bool aligned, u8 *cur, unsigned long long *__restrict__ nSrc) {
+    __shared__ unsigned short setIdx[kThreads / 32][512];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warpBase = ((int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31)) * 16;
+    int mine = 0;
+    if (warpBase < n) {
+        const int64_t base = warpBase + (int64_t)lane * 16;
+        unsigned mask = 0;
+        if (base < n) {
+            if (aligned && base + 16 <= n) {
+                const uint4 w = *reinterpret_cast<const uint4 *>(srcArr + base);
+                const unsigned v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int k = 0; k < 16; k++) mask |= (isSource((v[k >> 2] >> (8 * (k & 3))) & 0xffu, gen, separate) ? 1u : 0u) << k;
+            } else {
+                for (int k = 0; k < 16 && base + k < n; k++) mask |= (isSource(srcArr[base + k], gen, separate) ? 1u : 0u) << k;
+            }
+        }
+        const int cnt = __popc(mask);
+        mine = cnt;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+            int o = incl - cnt;
+            while (mask) {
+                const int k = __ffs(mask) - 1;
+                mask &= mask - 1;
+                setIdx[warp][o++] = (unsigned short)(lane * 16 + k);
+            }
+            __syncwarp();
+            const u8 tag = (u8)(gen + 1);
+            for (int i = lane; i < total; i += 32) {
+                const int64_t c = warpBase + setIdx[warp][i];
+                const int32_t b0 = sliceOff[c >> 5];
+                const int w = sliceOff[(c >> 5) + 1] - b0;
+                const int32_t *row = col + ((size_t)b0 << 5) + (c & 31);
+                for (int j0 = 0; j0 < w; j0 += 8) {
+                    int32_t q[8];
+                    u8 v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = cur[q[k]];
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if (v[k] == 0 && q[k] != (int32_t)c) cur[q[k]] = tag;      // all writers store the same tag: benign race
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (nSrc) blockAddCount(mine, nSrc);
+}
+
+// dense pull form (TMA-staged): every unmarked cell gathers the source values of its row
+__global__ void __launch_bounds__(kPipeThreads, 7)
+kp_layer_pull(SellView S, const u8 *srcArr, bool separate, int gen, u8 *cur, unsigned long long *__restrict__ nSrc) {
+    const int32_t n = (int32_t)S.rows;
+    const u8 tag = (u8)(gen + 1);
+    int mineCnt = 0;
+    sellPipeline(S, [&](int64_t c64, bool valid, const int32_t *row, int w, bool) {
+        const int32_t c = valid ? (int32_t)c64 : n - 1;
+        const unsigned own = cur[c];
+        const unsigned ownSrc = separate ? (unsigned)srcArr[c] : own;
+        if (valid && isSource(ownSrc, gen, separate)) mineCnt++;
+        unsigned hit = 0;
+        // a warp whose 32 cells are all marked has nothing to gather
+        if (!__all_sync(0xffffffffu, own != 0)) {
+            sellRow(row, w, c, [&](auto W, const int32_t *q) {
+                constexpr int NW = decltype(W)::value;
+                unsigned v[NW];
+#pragma unroll
+                for (int k = 0; k < NW; k++) v[k] = srcArr[q[k]];
+#pragma unroll
+                for (int k = 0; k < NW; k++) hit |= (isSource(v[k], gen, separate) && q[k] != c) ? 1u : 0u;
+            });
+        }
+        if (valid && own == 0 && hit) cur[c] = tag;
+    });
+    if (nSrc && threadIdx.x < kTileRows) {
+        for (int d = 16; d > 0; d >>= 1) mineCnt += __shfl_xor_sync(0xffffffffu, mineCnt, d);
+        if ((threadIdx.x & 31) == 0 && mineCnt) atomicAdd(nSrc, (unsigned long long)mineCnt);
+    }
+}
+// direct variant (tiles too large for the ring / AMR_B200_NO_PIPELINE)
+__global__ void __launch_bounds__(kThreads)
+k_layer_pull(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *srcArr, bool separate,
+             int gen, u8 *cur, unsigned long long *__restrict__ nSrc) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int mineCnt = 0;
+    if (c < n) {
+        const unsigned own = cur[c];
+        if (isSource(separate ? (unsigned)srcArr[c] : own, gen, separate)) mineCnt = 1;
+        if (own == 0) {
+            const int32_t b0 = sliceOff[c >> 5];
+            const int w = sliceOff[(c >> 5) + 1] - b0;
+            const int32_t *row = col + ((size_t)b0 << 5) + (c & 31);
+            unsigned hit = 0;
+            for (int j = 0; j < w; j++) {
+                const int32_t q = row[(size_t)j << 5];
+                if (q != (int32_t)c && isSource(srcArr[q], gen, separate)) hit = 1;
+            }
+            if (hit) cur[c] = (u8)(gen + 1);
+        }
+    }
+    if (nSrc) blockAddCount(mineCnt, nSrc);
+}
+// syncFaceList(orEqOp) part of a layer: the source value of the cell on the other side of a processor face
+__global__ void k_fix_layer(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                            const u8 *__restrict__ ghostSrc, bool separate, int gen, u8 *cur) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nC) return;
+    const label bf = cplFace[i];
+    if (isSource(ghostSrc[bf], gen, separate)) {
+        const label o = bOwner[bf];
+        if (cur[o] == 0) cur[o] = (u8)(gen + 1);
+    }
+}
+// marking -> boolList (0/1) for the caller; also the import direction
+__global__ void __launch_bounds__(kThreads)
+k_flags_normalize(int64_t n, const u8 *__restrict__ in, u8 *__restrict__ out, bool aligned) {
+    const int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 16;
+    if (base >= n) return;
+    if (aligned && base + 16 <= n) {
+        uint4 w = *reinterpret_cast<const uint4 *>(in + base);
+        w.x = __vcmpne4(w.x, 0u) & 0x01010101u; w.y = __vcmpne4(w.y, 0u) & 0x01010101u;
+        w.z = __vcmpne4(w.z, 0u) & 0x01010101u; w.w = __vcmpne4(w.w, 0u) & 0x01010101u;
+        *reinterpret_cast<uint4 *>(out + base) = w;
+    } else {
+        for (int k = 0; k < 16 && base + k < n; k++) out[base + k] = in[base + k] ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// (2) consistentRefinement as queue iterations
+// ------------------------------------------------------------------------------------------
+
+// one marked cell c: mark every unmarked face neighbour that would end up more than one level coarser
+__device__ __forceinline__ void refinePushRow(int64_t c, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+                                              const u8 *__restrict__ lvl8, u8 *lf, u8 *set, label *qOut, int *qOutCount, int64_t qCap) {
+    const int32_t b0 = sliceOff[c >> 5];
+    const int w = sliceOff[(c >> 5) + 1] - b0;
+    const int32_t *row = col + ((size_t)b0 << 5) + (c & 31);
+    const int mine = (int)lvl8[c] + 1;
+    for (int j0 = 0; j0 < w; j0 += 8) {
+        int32_t q[8];
+        int lq[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+#pragma unroll
+        for (int k = 0; k < 8; k++) lq[k] = lvl8[q[k]];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (mine > lq[k] + 1) {                                 // padding (q == c) fails this test
+                if (setByteOnce(set, q[k])) {
+                    lf[q[k]] = (u8)(lq[k] + 1);
+                    const int pos = atomicAdd(qOutCount, 1);
+                    if (pos < qCap) qOut[pos] = q[k];
+                }
+            }
+        }
+    }
+}
+// sweep 0: all marked cells (16 flags per 128-bit load, set cells dealt to the lanes of the warp)
+__global__ void __launch_bounds__(kThreads)
+k_refine_push0(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *__restrict__ lvl8,
+               u8 *lf, u8 *set, bool aligned, label *qOut, int *qOutCount, int64_t qCap) {
+    forEachSetWarp(set, n, aligned, [&](int64_t c) { refinePushRow(c, sliceOff, col, lvl8, lf, set, qOut, qOutCount, qCap); });
+}
+// iteration j >= 1: the cells queue j holds.  gate: all-reduced size of queue j (multi-rank) or qInCount itself.
+__global__ void __launch_bounds__(kThreads)
+k_refine_frontier(const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *__restrict__ lvl8, u8 *lf, u8 *set,
+                  const label *__restrict__ qIn, const int *__restrict__ qInCount, label *qOut, int *qOutCount, int64_t qCap,
+                  const int *__restrict__ gate) {
+    if (*gate == 0) return;
+    const int cnt = min(*qInCount, (int)min(qCap, (int64_t)0x7fffffff));
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < cnt; i += gridDim.x * kThreads)
+        refinePushRow(qIn[i], sliceOff, col, lvl8, lf, set, qOut, qOutCount, qCap);
+}
+// coupled faces of an iteration (hexRef.C:758-780, maxSet = true): ghostLf = level + flag of the cell across the face
+__global__ void k_fix_refine_queue(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                                   const u8 *__restrict__ lvl8, const u8 *__restrict__ ghostLf, u8 *lf, u8 *set, label *qOut,
+                                   int *qOutCount, int64_t qCap, const int *__restrict__ gate) {
+    if (gate && *gate == 0) return;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nC) return;
+    const label bf = cplFace[i];
+    const label o = bOwner[bf];
+    if ((int)ghostLf[bf] > (int)lvl8[o] + 1 && !set[o]) {           // an unmarked owner two levels below the far side
+        if (setByteOnce(set, o)) {
+            lf[o] = (u8)(lvl8[o] + 1);
+            const int pos = atomicAdd(qOutCount, 1);
+            if (pos < qCap) qOut[pos] = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// (3) consistentUnrefinement on the split-point table
+// ------------------------------------------------------------------------------------------
+
+// table from the split-point list: spCells[k * nSp + i] = k-th cell of split point i; cellSp[c] = i
+__global__ void __launch_bounds__(kThreads)
+k_sp_table(int64_t nSp, const label *__restrict__ spPoint, const int32_t *__restrict__ pcOff, const int32_t *__restrict__ pcCol,
+           label *__restrict__ spCells, label *__restrict__ cellSp) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= nSp) return;
+    const int64_t pt = spPoint[i];
+    const int32_t *row = pcCol + ((size_t)pcOff[pt >> 5] << 5) + (pt & 31);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const label c = row[(size_t)k << 5];
+        spCells[(size_t)k * nSp + i] = c;
+        cellSp[c] = (label)i;
+    }
+}
+// hexRef3D::selectUnrefineElems filter (hexRef3D.C:2336-2361) + maxCellField (fvMeshRefiner.C:110-125), cell-centric:
+// a split point is dropped when one of its cells is marked or has error >= unrefineLevel (max < level <=> all < level).
+// spFlag pre-set to 1.
+__global__ void __launch_bounds__(kThreads)
+k_sp_filter(int64_t n, const label *__restrict__ cellSp, const double *__restrict__ err, double unrefineLevel,
+            const u8 *__restrict__ marked, u8 *__restrict__ spFlag) {
+    const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (c0 >= n) return;
+    if (c0 + 4 <= n) {
+        const int4 sp = *reinterpret_cast<const int4 *>(cellSp + c0);
+        const uchar4 mk = *reinterpret_cast<const uchar4 *>(marked + c0);
+        const int s[4] = {sp.x, sp.y, sp.z, sp.w};
+        const u8 m[4] = {mk.x, mk.y, mk.z, mk.w};
+        if ((s[0] & s[1] & s[2] & s[3]) == -1) return;
+        const double2 e01 = *reinterpret_cast<const double2 *>(err + c0);
+        const double2 e23 = *reinterpret_cast<const double2 *>(err + c0 + 2);
+        const double e[4] = {e01.x, e01.y, e23.x, e23.y};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (s[k] >= 0 && (m[k] || !(e[k] < unrefineLevel))) spFlag[s[k]] = 0;
+    } else {
+        for (int64_t c = c0; c < n; c++) {
+            const label s = cellSp[c];
+            if (s >= 0 && (marked[c] || !(err[c] < unrefineLevel))) spFlag[s] = 0;
+        }
+    }
+}
+// unrefineCell = union of the cells of the listed split points (hexRef3D.C:1763-1776); uc pre-zeroed
+__global__ void __launch_bounds__(kThreads)
+k_sp_to_cells(const label *__restrict__ spList, const int32_t *__restrict__ nList, int64_t nSp, const label *__restrict__ spCells,
+              u8 *__restrict__ uc) {
+    const int cnt = *nList;
+    for (int t = blockIdx.x * kThreads + threadIdx.x; t < cnt * 8; t += gridDim.x * kThreads) {
+        const int i = spList[t >> 3];
+        uc[spCells[(size_t)(t & 7) * nSp + i]] = 1;
+    }
+}
+// knock split point i out: flag, its 8 cells, queue
+__device__ __forceinline__ void knockPoint(label i, int64_t nSp, const label *__restrict__ spCells, u8 *spFlag, u8 *uc,
+                                           label *qOut, int *qOutCount, int64_t qCap) {
+    if (clearByteOnce(spFlag, i)) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) uc[spCells[(size_t)k * nSp + i]] = 0;
+        const int pos = atomicAdd(qOutCount, 1);
+        if (pos < qCap) qOut[pos] = i;
+    }
+}
+// sweep 0: every cell of every listed split point (one thread per cell): marked cell c (final level lvl-1) against the
+// final levels lvl[q] - uc[q] of its face neighbours (hexRef3D.C:1785-1839)
+__global__ void __launch_bounds__(kThreads)
+k_unref_sweep0(const label *__restrict__ spList, const int32_t *__restrict__ nList, int64_t nSp, const label *__restrict__ spCells,
+               const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *__restrict__ lvl8, u8 *spFlag, u8 *uc,
+               label *qOut, int *qOutCount, int64_t qCap) {
+    const int cnt = *nList;
+    for (int t = blockIdx.x * kThreads + threadIdx.x; t < cnt * 8; t += gridDim.x * kThreads) {
+        const label i = spList[t >> 3];
+        const label c = spCells[(size_t)(t & 7) * nSp + i];
+        const int32_t b0 = sliceOff[c >> 5];
+        const int w = sliceOff[(c >> 5) + 1] - b0;
+        const int32_t *row = col + ((size_t)b0 << 5) + (c & 31);
+        const int mine = (int)lvl8[c] - 1;
+        int mx = 0;
+        for (int j0 = 0; j0 < w; j0 += 8) {
+            int32_t q[8];
+            int lq[8], uq[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : c;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { lq[k] = lvl8[q[k]]; uq[k] = uc[q[k]]; }
+#pragma unroll
+            for (int k = 0; k < 8; k++) mx = max(mx, lq[k] - uq[k]);
+        }
+        if (mine < mx - 1) knockPoint(i, nSp, spCells, spFlag, uc, qOut, qOutCount, qCap);
+    }
+}
+// iteration j >= 1: the cells that the knocked points of queue j reverted (uc = 0 now, final level lvl[q]) against their
+// marked neighbours: a marked neighbour c with lvl[c] - 1 < lvl[q] - 1 cannot be unrefined any more
+__global__ void __launch_bounds__(kThreads)
+k_unref_frontier(const label *__restrict__ qIn, const int *__restrict__ qInCount, int64_t nSp, const label *__restrict__ spCells,
+                 const label *__restrict__ cellSp, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
+                 const u8 *__restrict__ lvl8, u8 *spFlag, u8 *uc, label *qOut, int *qOutCount, int64_t qCap,
+                 const int *__restrict__ gate) {
+    if (*gate == 0) return;
+    const int cnt = min(*qInCount, (int)min(qCap, (int64_t)0x7fffffff));
+    for (int t = blockIdx.x * kThreads + threadIdx.x; t < cnt * 8; t += gridDim.x * kThreads) {
+        const label i = qIn[t >> 3];
+        const label q = spCells[(size_t)(t & 7) * nSp + i];
+        const int32_t b0 = sliceOff[q >> 5];
+        const int w = sliceOff[(q >> 5) + 1] - b0;
+        const int32_t *row = col + ((size_t)b0 << 5) + (q & 31);
+        const int lq = lvl8[q];
+        for (int j = 0; j < w; j++) {
+            const int32_t c = row[(size_t)j << 5];
+            if (c != q && uc[c] && (int)lvl8[c] < lq) {
+                const label sp = cellSp[c];
+                if (sp >= 0) knockPoint(sp, nSp, spCells, spFlag, uc, qOut, qOutCount, qCap);
+            }
+        }
+    }
+}
+// coupled faces of an iteration (hexRef3D.C:1855-1889): ghost = lvl - uc of the cell across the face
+__global__ void k_fix_unref_queue(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                                  const u8 *__restrict__ lvl8, const u8 *__restrict__ ghostLfm, int64_t nSp,
+                                  const label *__restrict__ spCells, const label *__restrict__ cellSp, u8 *spFlag, u8 *uc, label *qOut,
+                                  int *qOutCount, int64_t qCap, const int *__restrict__ gate) {
+    if (gate && *gate == 0) return;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nC) return;
+    const label bf = cplFace[i];
+    const label o = bOwner[bf];
+    if (uc[o] && ((int)lvl8[o] - 1) < (int)ghostLfm[bf] - 1) {
+        const label sp = cellSp[o];
+        if (sp >= 0) knockPoint(sp, nSp, spCells, spFlag, uc, qOut, qOutCount, qCap);
+    }
+}
+// "problem" of hexRef3D.C:1808-1833: an UNMARKED cell more than one level below the final level of a face neighbour.
+// Impossible on a 2:1-balanced mesh; evaluated on the final state when the mesh was found unbalanced.
+__global__ void __launch_bounds__(kThreads)
+k_unref_problem(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *__restrict__ lvl8,
+                const u8 *__restrict__ uc, int *problem) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n || uc[c]) return;
+    const int32_t b0 = sliceOff[c >> 5];
+    const int w = sliceOff[(c >> 5) + 1] - b0;
+    const int32_t *row = col + ((size_t)b0 << 5) + (c & 31);
+    const int mine = lvl8[c];
+    for (int j = 0; j < w; j++) {
+        const int32_t q = row[(size_t)j << 5];
+        if ((int)lvl8[q] - (int)uc[q] - 1 > mine) { *problem = 1; return; }
+    }
+}
+__global__ void k_fix_unref_problem(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                                    const u8 *__restrict__ lvl8, const u8 *__restrict__ ghostLfm, const u8 *__restrict__ uc, int *problem) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nC) return;
+    const label bf = cplFace[i];
+    const label o = bOwner[bf];
+    if (!uc[o] && (int)lvl8[o] < (int)ghostLfm[bf] - 1) *problem = 1;
+}

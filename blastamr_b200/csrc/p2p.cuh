@@ -6,13 +6,19 @@
 //   k_halo_push_cells : gather my boundary-cell values and store them straight into the neighbours' regions
 //                       (NVLink stores); the last CTA release-stores the epoch into their flag words
 //   k_halo_unpack     : acquire-spin on my own flag words, then copy the received ranges into `recv`
-// and a reduction (the reduce()/gMin/gMax of the reference) is the same pattern to all ranks.
-// Double buffering by epoch parity makes reuse safe: a rank can be at most one exchange ahead of a
-// neighbour (it needs that neighbour's signal to finish its own wait).  Spins are bounded (wall-clock limit
-// from the context: AMR_B200_PEER_TIMEOUT_S, default 20 s -- long enough for rank-imbalanced host work between two
-// collective calls) and raise the region's error word instead of hanging the GPU; the host reads that word at
-// every synchronising return (flushOuts / the sweep round trips) and fails the call.  NCCL stays as set-up
-// transport (handle exchange) and as fallback (AMR_B200_HALO=nccl, or when IPC mapping is not possible).
+// and a reduction (the reduce()/gMin/gMax of the reference) is the same pattern to all ranks in ONE launch.
+//
+// Exchange numbers live in DEVICE memory (seq[0] halo swaps, seq[1] reductions): a kernel reads the number of the last
+// completed exchange, uses the next one, and the receiving kernel stores it back when it is done.  The host never
+// passes an epoch, so a sweep loop can be enqueued speculatively, every launch gated by a device word that all ranks
+// hold identically (the all-reduced size of the work queues): a gated-off exchange consumes no number on any rank and
+// the parity buffers stay in step.  At most ONE halo swap is in flight per context (push ... unpack).
+// Double buffering by parity makes reuse safe: a rank can be at most one exchange ahead of a neighbour (it needs that
+// neighbour's signal to finish its own wait).  Spins are bounded (wall-clock limit from the context:
+// AMR_B200_PEER_TIMEOUT_S, default 20 s -- long enough for rank-imbalanced host work between two collective calls)
+// and raise the region's error word instead of hanging the GPU; the host reads that word at every synchronising
+// return (flushOuts / the sweep round trips) and fails the call.  NCCL stays as set-up transport (handle exchange)
+// and as fallback (AMR_B200_HALO=nccl, or when IPC mapping is not possible).
 #pragma once
 #include "common.cuh"
 
@@ -53,10 +59,14 @@ __device__ __forceinline__ unsigned ldAcquireSys(const unsigned *p) {
 // fused pack + push + signal: value of a per-cell array at the owner of every coupled boundary face goes
 // straight into the neighbour's region; the last CTA to finish publishes the epoch (threadfence-reduction
 // pattern), so a swap is two launches (this one and k_halo_unpack).  `minus` (optional, bytes): v -= minus[o].
+// gate (optional): the exchange only happens when *gate != 0 -- the same value on every rank.
 template <int BYTES>
-__global__ void k_halo_push_cells(HaloPlan P, char *const *__restrict__ peer, int parity, int myRank, unsigned epoch,
+__global__ void k_halo_push_cells(HaloPlan P, char *const *__restrict__ peer, int myRank, const unsigned *__restrict__ seq,
                                   const label *__restrict__ bOwner, const char *__restrict__ cells, const u8 *__restrict__ minus,
-                                  unsigned *counter) {
+                                  unsigned *counter, const int *__restrict__ gate) {
+    if (gate && *gate == 0) return;
+    const unsigned epoch = seq[0] + 1u;                  // stored back by k_halo_unpack, later in stream order
+    const int parity = (int)(epoch & 1u);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P.prefix[P.nPatch]) {
         int q = 0;
@@ -90,10 +100,14 @@ __global__ void k_halo_push_cells(HaloPlan P, char *const *__restrict__ peer, in
         if (threadIdx.x == 0) *counter = 0;
     }
 }
+// receive side; the last CTA stores the exchange number back (seq[0] = epoch)
 template <int BYTES>
-__global__ void k_halo_unpack(HaloPlan P, char *mine, int parity, unsigned epoch, char *__restrict__ recv,
-                              unsigned long long timeoutNs) {
+__global__ void k_halo_unpack(HaloPlan P, char *mine, unsigned *seq, char *__restrict__ recv, unsigned long long timeoutNs,
+                              unsigned *counter, const int *__restrict__ gate) {
+    if (gate && *gate == 0) return;
     __shared__ int ok;
+    const unsigned epoch = seq[0] + 1u;
+    const int parity = (int)(epoch & 1u);
     P2PRegionHeader *h = reinterpret_cast<P2PRegionHeader *>(mine);
     if (threadIdx.x == 0) {
         int good = h->error == 0;                        // an earlier timeout of this call chain: do not touch recv
@@ -107,65 +121,76 @@ __global__ void k_halo_unpack(HaloPlan P, char *mine, int parity, unsigned epoch
         ok = good;
     }
     __syncthreads();
-    if (!ok) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.prefix[P.nPatch]) return;
-    int q = 0;
-    while (i >= P.prefix[q + 1]) q++;
-    const int k = i - P.prefix[q];
-    const char *src = mine + sizeof(P2PRegionHeader) + (size_t)parity * kHaloCap + (size_t)(P.offMine[q] + k) * BYTES;
-    char *dst = recv + (size_t)(P.offMine[q] + k) * BYTES;
-    if (BYTES == 1) *dst = *src;
-    else if (BYTES == 4) *reinterpret_cast<int *>(dst) = *reinterpret_cast<const int *>(src);
-    else if (BYTES == 8) *reinterpret_cast<double *>(dst) = *reinterpret_cast<const double *>(src);
-    else {
-        const double *s3 = reinterpret_cast<const double *>(src);
-        double *d3 = reinterpret_cast<double *>(dst);
-        d3[0] = s3[0]; d3[1] = s3[1]; d3[2] = s3[2];
+    if (ok && i < P.prefix[P.nPatch]) {
+        int q = 0;
+        while (i >= P.prefix[q + 1]) q++;
+        const int k = i - P.prefix[q];
+        const char *src = mine + sizeof(P2PRegionHeader) + (size_t)parity * kHaloCap + (size_t)(P.offMine[q] + k) * BYTES;
+        char *dst = recv + (size_t)(P.offMine[q] + k) * BYTES;
+        if (BYTES == 1) *dst = *src;
+        else if (BYTES == 4) *reinterpret_cast<int *>(dst) = *reinterpret_cast<const int *>(src);
+        else if (BYTES == 8) *reinterpret_cast<double *>(dst) = *reinterpret_cast<const double *>(src);
+        else {
+            const double *s3 = reinterpret_cast<const double *>(src);
+            double *d3 = reinterpret_cast<double *>(dst);
+            d3[0] = s3[0]; d3[1] = s3[1]; d3[2] = s3[2];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) { *counter = 0; seq[0] = epoch; }
     }
 }
 
-// ---- all-rank reduction of one 8-byte word.  op: 0 max(int32), 1 sum(int64), 2 min(f64), 3 max(f64)
-__global__ void k_red_push(char *const *__restrict__ peer, int nranks, int myRank, int parity, unsigned epoch,
-                           const void *__restrict__ value, int is32) {
-    const int r = threadIdx.x;
-    if (r >= nranks) return;
-    P2PRegionHeader *h = reinterpret_cast<P2PRegionHeader *>(peer[r]);
-    h->red[parity][myRank] = is32 ? (unsigned long long)(unsigned)(*reinterpret_cast<const int *>(value))
-                                  : *reinterpret_cast<const unsigned long long *>(value);
-    __threadfence_system();
-    stReleaseSys(&h->redEpoch[parity][myRank], epoch);
-}
-__global__ void k_red_wait(char *mine, int nranks, int parity, unsigned epoch, int op, void *__restrict__ out, int is32,
-                           unsigned long long timeoutNs) {
+// ---- all-rank reduction of one 8-byte word in ONE launch (one CTA, thread r <-> rank r): push my word to every rank,
+// wait for everybody's, combine, store the result in place.  op: 0 max(int32), 1 sum(int64), 2 min(f64), 3 max(f64),
+// 4 sum(int32).  The value sent is *src (default: *word), the result goes to *word.
+__global__ void k_red_all(char *const *__restrict__ peer, char *mine, int nranks, int myRank, unsigned *seq, int op,
+                          const void *src, void *word, unsigned long long timeoutNs, const int *__restrict__ gate) {
+    if (gate && *gate == 0) return;                      // a gated-off reduction leaves *word as it is (0: cleared by the caller)
+    if (!src) src = word;
     __shared__ unsigned long long vals[kMaxRanks];
     __shared__ int bad;
-    P2PRegionHeader *h = reinterpret_cast<P2PRegionHeader *>(mine);
+    const unsigned epoch = seq[1] + 1u;
+    const int parity = (int)(epoch & 1u);
+    const bool is32 = (op == 0 || op == 4);
     const int r = threadIdx.x;
     if (r == 0) bad = 0;
     __syncthreads();
     if (r < nranks) {
+        P2PRegionHeader *h = reinterpret_cast<P2PRegionHeader *>(peer[r]);
+        h->red[parity][myRank] = is32 ? (unsigned long long)(unsigned)(*reinterpret_cast<const int *>(src))
+                                      : *reinterpret_cast<const unsigned long long *>(src);
+        __threadfence_system();
+        stReleaseSys(&h->redEpoch[parity][myRank], epoch);
+        P2PRegionHeader *me = reinterpret_cast<P2PRegionHeader *>(mine);
         const unsigned long long t0 = globalTimerNs();
         unsigned spins = 0;
-        while ((int)(ldAcquireSys(&h->redEpoch[parity][r]) - epoch) < 0) {
-            if ((++spins & 1023u) == 0 && globalTimerNs() - t0 > timeoutNs) { bad = 1; h->error = 1; break; }
+        while ((int)(ldAcquireSys(&me->redEpoch[parity][r]) - epoch) < 0) {
+            if ((++spins & 1023u) == 0 && globalTimerNs() - t0 > timeoutNs) { bad = 1; me->error = 1; break; }
         }
-        vals[r] = h->red[parity][r];
+        vals[r] = *reinterpret_cast<volatile unsigned long long *>(&me->red[parity][r]);
     }
     __syncthreads();
-    if (r == 0 && !bad) {
-        unsigned long long acc = vals[0];
-        for (int k = 1; k < nranks; k++) {
-            const unsigned long long v = vals[k];
-            if (op == 0) { int a = (int)acc, b2 = (int)v; acc = (unsigned long long)(unsigned)(a > b2 ? a : b2); }
-            else if (op == 1) acc = (unsigned long long)((long long)acc + (long long)v);
-            else {
-                const double a = __longlong_as_double((long long)acc), b2 = __longlong_as_double((long long)v);
-                const double m = (op == 2) ? ((a < b2) ? a : b2) : ((a > b2) ? a : b2);
-                acc = (unsigned long long)__double_as_longlong(m);
+    if (r == 0) {
+        if (!bad) {
+            unsigned long long acc = vals[0];
+            for (int k = 1; k < nranks; k++) {
+                const unsigned long long v = vals[k];
+                if (op == 0) { int a = (int)acc, b2 = (int)v; acc = (unsigned long long)(unsigned)(a > b2 ? a : b2); }
+                else if (op == 4) acc = (unsigned long long)(unsigned)((int)acc + (int)v);
+                else if (op == 1) acc = (unsigned long long)((long long)acc + (long long)v);
+                else {
+                    const double a = __longlong_as_double((long long)acc), b2 = __longlong_as_double((long long)v);
+                    const double m = (op == 2) ? ((a < b2) ? a : b2) : ((a > b2) ? a : b2);
+                    acc = (unsigned long long)__double_as_longlong(m);
+                }
             }
-        }
-        if (is32) *reinterpret_cast<int *>(out) = (int)acc;
-        else *reinterpret_cast<unsigned long long *>(out) = acc;
+            if (is32) *reinterpret_cast<int *>(word) = (int)acc;
+            else *reinterpret_cast<unsigned long long *>(word) = acc;
+        } else if (is32) *reinterpret_cast<int *>(word) = 0;     // a timed-out exchange ends a speculative loop; the host reports it
+        seq[1] = epoch;
     }
 }

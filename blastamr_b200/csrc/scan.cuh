@@ -63,44 +63,6 @@ __device__ __forceinline__ uint4 loadFlags16(const u8 *flags, int64_t base, int6
     return w;
 }
 
-__global__ void __launch_bounds__(kThreads) k_flag_count(const u8 *__restrict__ flags, int64_t N, bool aligned,
-                                                        int32_t *__restrict__ tileCnt) {
-    __shared__ int smem[kThreads / 32 + 1];
-    int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kFlagsPerThread;
-    int c = 0;
-    if (base < N) {
-        uint4 w = loadFlags16(flags, base, N, aligned);
-        c = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
-    }
-    // block reduce
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
-    if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int s = 0;
-        for (int i = 0; i < kThreads / 32; i++) s += smem[i];
-        tileCnt[blockIdx.x] = s;
-    }
-}
-
-__global__ void __launch_bounds__(kThreads) k_flag_scatter(const u8 *__restrict__ flags, int64_t N, bool aligned,
-                                                          const int32_t *__restrict__ tileOff,
-                                                          int32_t *__restrict__ out) {
-    __shared__ int smem[kThreads / 32 + 1];
-    int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kFlagsPerThread;
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (base < N) w = loadFlags16(flags, base, N, aligned);
-    int c = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
-    int total;
-    int pos = blockExclusiveScan(c, smem, &total) + tileOff[blockIdx.x];
-    if (c) {
-        unsigned v[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-            if ((v[k >> 2] >> (8 * (k & 3))) & 1u) out[pos++] = (int32_t)(base + k);
-    }
-}
-
 // ---- exclusive scan of int32 (multi-level, 1024 items per CTA) ---------------------------
 constexpr int kScanItems = 4;
 constexpr int kScanTile = kThreads * kScanItems;
@@ -148,17 +110,93 @@ static int deviceExclusiveScan(amr_ctx *ctx, const int32_t *in, int32_t *out, in
     return AMR_OK;
 }
 
-// flags[N] (bytes) -> ascending indices in `out`; count stored to ctx->dCount[slot] (device) via tile offsets.
-// After the call tileCnt[tiles] holds the total.
-static int compactFlags(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *out, int32_t **totalDev) {
+// ---- single-pass compaction (decoupled look-back) ---------------------------------------------------------
+// One launch turns byte flags into the ascending list: every CTA takes the next tile (dynamic ticket, so that all
+// predecessors of a tile are already running), counts its set flags, publishes the count, looks back over the
+// predecessors' published counts / inclusive prefixes until it knows its own offset, and scatters.  Status words carry
+// a per-call tag, so the status array is never cleared.  flag = 1: aggregate, 2: inclusive prefix.
+//   src (optional)  : entry i stands for element src[i]: its flag is flags[src[i]] (compaction of a list by a flag array)
+//   map (optional)  : the output is map[element] instead of the element
+//   nDev (optional) : N is read from device memory (*nDev, <= N)
+__device__ __forceinline__ unsigned long long packStatus(unsigned tag, unsigned flag, unsigned value) {
+    return ((unsigned long long)((tag << 2) | flag) << 32) | value;
+}
+__global__ void __launch_bounds__(kThreads)
+k_compact_lb(const u8 *__restrict__ flags, int64_t N, const int32_t *__restrict__ nDev, bool aligned, const label *__restrict__ src,
+             const label *__restrict__ map, unsigned long long *status, unsigned *ticket, unsigned tag, int32_t *__restrict__ out,
+             int32_t *__restrict__ total, const int *__restrict__ gate) {
+    if (gate && *gate == 0) return;
+    __shared__ int smem[kThreads / 32 + 1];
+    __shared__ unsigned sTile;
+    __shared__ int sPrefix;
+    if (nDev) N = min(N, (int64_t)*nDev);
+    const unsigned tiles = gridDim.x;
+    if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned tile = sTile;
+    const int64_t base = ((int64_t)tile * kThreads + threadIdx.x) * kFlagsPerThread;
+    unsigned bits = 0;
+    if (base < N) {
+        if (!src) {
+            const uint4 w = loadFlags16(flags, base, N, aligned);
+            const unsigned v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 16; k++) bits |= ((v[k >> 2] >> (8 * (k & 3))) & 1u) << k;
+        } else {
+            for (int k = 0; k < 16 && base + k < N; k++) bits |= (flags[src[base + k]] ? 1u : 0u) << k;
+        }
+    }
+    const int c = __popc(bits);
+    int tileTotal;
+    int pos = blockExclusiveScan(c, smem, &tileTotal);
+    if (threadIdx.x == 0) {
+        int prefix = 0;
+        if (tile == 0) {
+            atomicExch(&status[0], packStatus(tag, 2u, (unsigned)tileTotal));
+        } else {
+            atomicExch(&status[tile], packStatus(tag, 1u, (unsigned)tileTotal));
+            for (int j = (int)tile - 1; j >= 0; j--) {
+                unsigned long long sv;
+                do { sv = *reinterpret_cast<volatile unsigned long long *>(&status[j]); } while ((unsigned)(sv >> 34) != tag || ((sv >> 32) & 3u) == 0u);
+                prefix += (int)(unsigned)sv;
+                if (((sv >> 32) & 3u) == 2u) break;
+            }
+            atomicExch(&status[tile], packStatus(tag, 2u, (unsigned)(prefix + tileTotal)));
+        }
+        sPrefix = prefix;
+        if (tile == tiles - 1) {                       // every ticket has been drawn: reset for the next call
+            *ticket = 0;
+            if (total) *total = prefix + tileTotal;
+        }
+    }
+    __syncthreads();
+    pos += sPrefix;
+    if (out) {
+        while (bits) {
+            const int k = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int64_t i = src ? (int64_t)src[base + k] : base + k;
+            out[pos++] = map ? map[i] : (int32_t)i;
+        }
+    }
+}
+
+// flags[N] (bytes, any non-zero value counts) -> ascending indices in `out`; the count is stored to *totalDev (device).
+static int compactFlagsEx(amr_ctx *ctx, const u8 *flags, int64_t N, const int32_t *nDev, const label *src, const label *map,
+                          int32_t *out, int32_t **totalDev, int totalSlot, const int *gate) {
     int64_t tiles = (N + kTile - 1) / kTile;
     if (tiles < 1) tiles = 1;
     if (tiles + 2 > ctx->tileCap) FAIL(AMR_ERR_STATE, "compaction tile buffer too small");
-    bool aligned = (((uintptr_t)flags) & 15) == 0;
-    CK(cudaMemsetAsync(ctx->tileCnt + tiles, 0, sizeof(int32_t), ctx->stream));
-    LAUNCH(k_flag_count, (unsigned)tiles, kThreads, flags, N, aligned, ctx->tileCnt);
-    TRY(deviceExclusiveScan(ctx, ctx->tileCnt, ctx->tileCnt, tiles, ctx->scanAux, ctx->scanAuxCap));
-    if (out) LAUNCH(k_flag_scatter, (unsigned)tiles, kThreads, flags, N, aligned, ctx->tileCnt, out);
-    *totalDev = ctx->tileCnt + tiles;
+    const bool aligned = (((uintptr_t)flags) & 15) == 0;
+    ctx->scanTag = (ctx->scanTag + 1u) & 0x3fffffffu;
+    if (ctx->scanTag == 0) ctx->scanTag = 1;
+    int32_t *total = ctx->dTotals + totalSlot;
+    k_compact_lb<<<(unsigned)tiles, kThreads, 0, ctx->stream>>>(flags, N, nDev, aligned, src, map, ctx->lbStatus, ctx->lbTicket, ctx->scanTag,
+                                                                 out, total, gate);
+    ctx->launches++;
+    *totalDev = total;
     return AMR_OK;
+}
+static int compactFlags(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *out, int32_t **totalDev) {
+    return compactFlagsEx(ctx, flags, N, nullptr, nullptr, nullptr, out, totalDev, 0, nullptr);
 }
