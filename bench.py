@@ -665,16 +665,11 @@ def main():
         mark(1)
         nr, sw = ctx.select_refine(err0, MAX_LEVEL, LAYERS_REF, cells_out=cells_dev, refine_cell_out=rc0)
         mark(2)
-        ctx.map_field(cell_map, x, n_old=n, n_new=n1, ncomp=1, out=new1)
-        ctx.map_field(cell_map, fld3, n_old=n, n_new=n1, ncomp=3, out=new3)
-        ctx.map_field(cell_map, err0, n_old=n, n_new=n1, ncomp=1, out=err1)
-        ctx1.remap_refine_cell(cell_map, rev_map, refine_cell=rc0)
+        ctx1.map_fields_and_marking(cell_map, [x, fld3, err0], n, n1, [1, 3, 1], [new1, new3, err1], reverse_map=rev_map, refine_cell=rc0)
         mark(3)
         npts, sw2 = ctx1.select_unrefine(err1, LAYERS_UNREF, elems_out=pts_dev)
         mark(4)
-        ctx1.map_field(cell_map2, new1, n_old=n1, n_new=n2, ncomp=1, out=x2)
-        ctx1.map_field(cell_map2, new3, n_old=n1, n_new=n2, ncomp=3, out=u2)
-        ctx1.map_field(cell_map2, err1, n_old=n1, n_new=n2, ncomp=1, out=err2)
+        ctx1.map_fields(cell_map2, [new1, new3, err1], n1, n2, [1, 3, 1], [x2, u2, err2])
         mark(5)
         info.update(n_refine=nr, sweeps_refine=sw, n_unrefine=npts, sweeps_unrefine=sw2)
 
@@ -803,25 +798,16 @@ def main():
                 st["GBps"] = (by / 1e9) / (ms / 1e3) if ms > 0 else None
                 st["frac"] = st["GBps"] / peak if st["GBps"] else None
             stages[nm] = st
-        # Dominant kernel: the vector-field map of stage F, timed on its own with CUDA events right here (the stage
-        # intervals above hold several launches).  Algorithmic bytes 4n' + 3(8n + 8n').
-        kname = "k_map_field_pair<3>"
-        kbytes = 4 * n1 + 3 * (8 * n + 8 * n1)
-        ka = torch.cuda.Event(enable_timing=True)
-        kz = torch.cuda.Event(enable_timing=True)
-        reps = 10
-        ctx.map_field(cell_map, fld3, n_old=n, n_new=n1, ncomp=3, out=new3)
-        torch.cuda.synchronize()
-        ka.record()
-        for _ in range(reps):
-            ctx.map_field(cell_map, fld3, n_old=n, n_new=n1, ncomp=3, out=new3)
-        kz.record()
-        torch.cuda.synchronize()
-        k_ms = ka.elapsed_time(kz) / reps
+        # Dominant kernel: stage F is ONE launch (k_map_fields_fused: scalar + vector + error field + refineCell through one
+        # read of cellMap), so its CUDA-event interval over the timed region is the launch duration.  Algorithmic bytes:
+        # cellMap once, 5 components old + new, reverseCellMap + old and new flag.
+        kname = "k_map_fields_fused"
+        kbytes = 4 * n1 + 5 * (8 * n + 8 * n1) + (4 * n + n + n1)
+        k_ms = stage_ms[2]
         roof = {"bound": "hbm", "kernel": kname, "achieved": (kbytes / 1e9) / (k_ms / 1e3), "peak": peak, "unit": "GB/s",
                 "frac": (kbytes / 1e9) / (k_ms / 1e3) / peak,
                 "traffic": (traffic or {}).get("kernel_dram_bytes_per_launch", {}).get(kname),
-                "algorithmic_bytes": kbytes, "formula": "4n' + 3(8n + 8n')", "ms": k_ms, "peak_source": peak_src,
+                "algorithmic_bytes": kbytes, "formula": "4n' + 5(8n + 8n') + (4n + n + n')", "ms": k_ms, "peak_source": peak_src,
                 "algorithmic_step_bytes": int(sum(ab.values())),
                 "algorithmic_step_note": "bytes of the REFERENCE's dense loops (SURVEY 8d), not what the kernels move"}
         if traffic and "step_dram_bytes" in traffic:

@@ -61,6 +61,7 @@ _SIGS = {
     "amr_map_field": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_void_p]),
     "amr_map_fields": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_map_fields_and_marking": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int] + [C.c_void_p] * 6),
     "amr_update_levels": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5),
     "amr_remap_labels": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "amr_remap_protected_cells": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -342,6 +343,16 @@ class Context:
         po = (C.c_void_p * k)(*[_ptr(a) for a in olds])
         pn = (C.c_void_p * k)(*[_ptr(a) for a in outs])
         self._ck(self.L.amr_map_fields(self._h, n_old, n_new, _ptr(cell_map), k, nc, po, pn))
+        return outs
+
+    def map_fields_and_marking(self, cell_map, olds, n_old, n_new, ncomps, outs, reverse_map=None, refine_cell=None, out_marking=None):
+        """fvMesh::mapFields + the refiner's refineCell update in one pass over cellMap (reverse_map None: fields only)"""
+        k = len(olds)
+        nc = (C.c_int * max(k, 1))(*[int(c) for c in ncomps])
+        po = (C.c_void_p * max(k, 1))(*[_ptr(a) for a in olds])
+        pn = (C.c_void_p * max(k, 1))(*[_ptr(a) for a in outs])
+        self._ck(self.L.amr_map_fields_and_marking(self._h, n_old, n_new, _ptr(cell_map), k, nc, po, pn, _ptr(reverse_map),
+                                                   _ptr(refine_cell), _ptr(out_marking)))
         return outs
 
     def update_levels(self, cell_map, old_level=None, refined_old=None, unrefined_old=None):

@@ -1986,27 +1986,95 @@ static int launchMapField(amr_ctx *ctx, int64_t nNew, int nComp, const int32_t *
     return AMR_OK;
 }
 
-AMR_API int amr_map_fields(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nFields, const int *nComp,
-                           const double *const *oldF, double *const *newF) {
+// all fields (<= kMaxMapFields per launch) and, optionally, the marking through the map in one pass (k_map_fields_fused)
+static int launchMapFused(amr_ctx *ctx, int64_t nNew, const int32_t *dMap, int nFields, const int *nComp, const double *const *dOld,
+                          double *const *dNew, const int32_t *dRev, const u8 *dOldFlag, u8 *dNewFlag) {
+    if (nNew <= 0) return AMR_OK;
+    const unsigned grid = gridFor(nNew, kMapTile);
+    int done = 0;
+    bool flagsDone = dNewFlag == nullptr;
+    while (done < nFields || !flagsDone) {
+        MapFieldSet F;
+        F.nFields = 0;
+        while (done < nFields && F.nFields < kMaxMapFields) {
+            F.nc[F.nFields] = nComp[done]; F.oldF[F.nFields] = dOld[done]; F.newF[F.nFields] = dNew[done];
+            F.nFields++; done++;
+        }
+        for (int k = F.nFields; k < kMaxMapFields; k++) { F.nc[k] = 0; F.oldF[k] = nullptr; F.newF[k] = nullptr; }
+        const bool withFlags = !flagsDone;
+        LAUNCH(k_map_fields_fused, grid, kThreads, nNew, dMap, F, withFlags ? dRev : (const int32_t *)nullptr,
+               withFlags ? dOldFlag : (const u8 *)nullptr, withFlags ? dNewFlag : (u8 *)nullptr);
+        flagsDone = true;
+    }
+    return AMR_OK;
+}
+
+AMR_API int amr_map_fields_and_marking(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nFields, const int *nComp,
+                                       const double *const *oldF, double *const *newF, const int32_t *reverseCellMap,
+                                       const uint8_t *refineCell, uint8_t *newRefineCellOut) {
     ENTER();
-    if (!cellMap || nFields < 0 || (nFields > 0 && (!nComp || !oldF || !newF))) FAIL(AMR_ERR_ARG, "amr_map_fields: bad arguments");
-    bool allHost = true;
+    if (!cellMap || nFields < 0 || nOld < 0 || nNew < 0 || (nFields > 0 && (!nComp || !oldF || !newF))) FAIL(AMR_ERR_ARG, "amr_map_fields: bad arguments");
+    const bool marking = reverseCellMap != nullptr;
+    bool allHost = nFields > 0;
     for (int i = 0; i < nFields; i++) {
         if (!oldF[i] || !newF[i] || nComp[i] < 1) FAIL(AMR_ERR_ARG, "amr_map_fields: null field / bad nComp");
         if (isDevicePtr(oldF[i]) || isDevicePtr(newF[i])) allHost = false;
     }
-    if (allHost && nFields > 0) return mapFieldsHostPipelined(ctx, nOld, nNew, cellMap, nFields, nComp, oldF, newF);
-    const int32_t *dMap = nullptr;
+    if (marking && !refineCell && nOld != ctx->refineCellN) FAIL(AMR_ERR_STATE, "amr_map_fields_and_marking: resident marking has a different size than nOld");
+    if (allHost) {
+        // solver-owned host fields: chunked two-way PCIe pipeline; the marking (device resident) goes through the map on its own
+        TRY(mapFieldsHostPipelined(ctx, nOld, nNew, cellMap, nFields, nComp, oldF, newF));
+        if (!marking) return AMR_OK;
+        nFields = 0;
+    }
+    const int32_t *dMap = nullptr, *dRev = nullptr;
+    const u8 *dOldFlag = nullptr;
+    u8 *dNewFlag = nullptr;
     TRY(stageIn(ctx, cellMap, nNew, &dMap));
+    std::vector<const double *> dOld((size_t)std::max(nFields, 1), nullptr);
+    std::vector<double *> dNew((size_t)std::max(nFields, 1), nullptr);
     for (int i = 0; i < nFields; i++) {
-        const double *dOld = nullptr;
-        double *dNew = nullptr;
-        TRY(stageIn(ctx, oldF[i], nOld * nComp[i], &dOld));
-        TRY(stageOut(ctx, newF[i], nNew * nComp[i], &dNew));
-        TRY(launchMapField(ctx, nNew, nComp[i], dMap, dOld, dNew));
+        TRY(stageIn(ctx, oldF[i], nOld * nComp[i], &dOld[(size_t)i]));
+        TRY(stageOut(ctx, newF[i], nNew * nComp[i], &dNew[(size_t)i]));
+    }
+    bool oversize = false;
+    if (marking) {
+        TRY(stageIn(ctx, reverseCellMap, nOld, &dRev));
+        TRY(stageIn(ctx, refineCell, nOld, &dOldFlag));
+        if (!dOldFlag) dOldFlag = ctx->refineCell;
+        if (!dOldFlag) FAIL(AMR_ERR_STATE, "amr_map_fields_and_marking: no marking");
+        if (nNew + 16 <= ctx->flagCap) dNewFlag = ctx->flagA;        // becomes the resident marking by pointer swap
+        else {
+            CK(cudaMalloc((void **)&dNewFlag, (size_t)std::max<int64_t>(nNew + 16, ctx->flagCap)));
+            oversize = true;
+        }
+    }
+    TRY(launchMapFused(ctx, nNew, dMap, nFields, nComp, dOld.data(), dNew.data(), dRev, dOldFlag, dNewFlag));
+    if (marking) {
+        if (newRefineCellOut && nNew) {
+            CK(cudaMemcpyAsync(newRefineCellOut, dNewFlag, (size_t)nNew, cudaMemcpyDefault, ctx->stream));
+            if (!isDevicePtr(newRefineCellOut)) ctx->hostTouched = true;
+        }
+        if (oversize) {
+            // the larger buffer leaves the pool convention; amr_mesh_set of the new mesh adopts its content
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->refineCell) cudaFree(ctx->refineCell);
+            ctx->refineCell = dNewFlag;
+            ctx->refineCellOversize = true;
+        } else std::swap(ctx->flagA, ctx->refineCell);
+        ctx->refineCellN = nNew;
+        ctx->refineCellGen = 1;
     }
     CK(cudaGetLastError());
     return flushOuts(ctx);
+}
+
+// fvMesh::mapFields maps EVERY registered field through one mapPolyMesh (MapGeometricFields over the object
+// registry): the batched entry point reads the cellMap once for all fields and, for host buffers, keeps uploading
+// field k+1 while field k comes down.
+AMR_API int amr_map_fields(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nFields, const int *nComp,
+                           const double *const *oldF, double *const *newF) {
+    return amr_map_fields_and_marking(ctx, nOld, nNew, cellMap, nFields, nComp, oldF, newF, nullptr, nullptr, nullptr);
 }
 
 AMR_API int amr_map_field(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nComp, const double *oldF,

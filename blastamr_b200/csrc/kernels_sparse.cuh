@@ -419,3 +419,107 @@ __global__ void k_fix_unref_problem(int64_t nC, const label *__restrict__ cplFac
     const label o = bOwner[bf];
     if (!uc[o] && (int)lvl8[o] < (int)ghostLfm[bf] - 1) *problem = 1;
 }
+
+// ------------------------------------------------------------------------------------------
+// STAGE 4  all registered fields through the map in ONE pass
+// ------------------------------------------------------------------------------------------
+// fvMesh::mapFields maps every registered field through the same mapPolyMesh::cellMap() (MapGeometricFields over the
+// object registry); the refiner then carries refineCell through the same map (fvMeshHexRefiner.C:1562-1586).  One CTA
+// stages the cellMap entries of a tile of new cells in shared memory once and then streams every field (and the
+// marking) through them: the map is read from HBM once instead of once per field.  Multi-component fields move as
+// pairs of consecutive elements (one 128-bit store, one 128-bit load where the two sources are consecutive).
+constexpr int kMapTile = 1024;           // new cells per CTA
+constexpr int kMaxMapFields = 8;
+struct MapFieldSet {
+    int nFields;
+    int nc[kMaxMapFields];
+    const double *oldF[kMaxMapFields];
+    double *newF[kMaxMapFields];
+};
+
+template <int NC>
+__device__ __forceinline__ void mapTileField(const int *__restrict__ cm, int cnt, int64_t tile0, const double *__restrict__ oldF,
+                                             double *__restrict__ newF) {
+    const int total = cnt * NC;                              // elements of this tile; its first element index is even
+    double *dst = newF + tile0 * NC;
+    if ((((uintptr_t)oldF) | ((uintptr_t)newF)) & 15) {      // unaligned field: element form
+        for (int e = threadIdx.x; e < total; e += kThreads) {
+            const int i = e / NC;
+            dst[e] = oldF[(int64_t)cm[i] * NC + (e - i * NC)];
+        }
+        return;
+    }
+    const int pairs = total >> 1;
+    for (int p0 = threadIdx.x; p0 < pairs; p0 += 4 * kThreads) {
+        int64_t s0[4], s1[4];
+        double2 v[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int p = p0 + t * kThreads;
+            s0[t] = -1;
+            if (p < pairs) {
+                const int e = 2 * p;
+                const int i = e / NC, k = e - i * NC;
+                s0[t] = (int64_t)cm[i] * NC + k;
+                s1[t] = (k + 1 < NC) ? s0[t] + 1 : (int64_t)cm[i + 1] * NC;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            if (s0[t] < 0) continue;
+            if (s1[t] == s0[t] + 1 && !(s0[t] & 1)) v[t] = *reinterpret_cast<const double2 *>(oldF + s0[t]);
+            else { v[t].x = oldF[s0[t]]; v[t].y = oldF[s1[t]]; }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            if (s0[t] >= 0) *reinterpret_cast<double2 *>(dst + 2 * (p0 + t * kThreads)) = v[t];
+    }
+    if ((total & 1) && threadIdx.x == 0) {                   // odd tail (last tile only)
+        const int e = total - 1, i = e / NC;
+        dst[e] = oldF[(int64_t)cm[i] * NC + (e - i * NC)];
+    }
+}
+__device__ __forceinline__ void mapTileFieldN(const int *__restrict__ cm, int cnt, int64_t tile0, int nc, const double *__restrict__ oldF,
+                                              double *__restrict__ newF) {
+    const int total = cnt * nc;
+    double *dst = newF + tile0 * nc;
+    for (int e = threadIdx.x; e < total; e += kThreads) {
+        const int i = e / nc;
+        dst[e] = oldF[(int64_t)cm[i] * nc + (e - i * nc)];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_map_fields_fused(int64_t nNew, const label *__restrict__ cellMap, MapFieldSet F, const label *__restrict__ reverseCellMap,
+                   const u8 *__restrict__ oldFlag, u8 *__restrict__ newFlag) {
+    __shared__ __align__(16) int cm[kMapTile + 4];
+    const int64_t tile0 = (int64_t)blockIdx.x * kMapTile;
+    const int cnt = (int)min((int64_t)kMapTile, nNew - tile0);
+    if (cnt == kMapTile) {
+        reinterpret_cast<int4 *>(cm)[threadIdx.x] = reinterpret_cast<const int4 *>(cellMap + tile0)[threadIdx.x];
+    } else {
+        for (int i = threadIdx.x; i < cnt; i += kThreads) cm[i] = cellMap[tile0 + i];
+    }
+    if (threadIdx.x == 0) cm[cnt] = 0;                        // read (not used) by the pair walk at the tile end
+    __syncthreads();
+    for (int f = 0; f < F.nFields; f++) {
+        switch (F.nc[f]) {
+        case 1: mapTileField<1>(cm, cnt, tile0, F.oldF[f], F.newF[f]); break;
+        case 3: mapTileField<3>(cm, cnt, tile0, F.oldF[f], F.newF[f]); break;
+        case 6: mapTileField<6>(cm, cnt, tile0, F.oldF[f], F.newF[f]); break;
+        case 9: mapTileField<9>(cm, cnt, tile0, F.oldF[f], F.newF[f]); break;
+        default: mapTileFieldN(cm, cnt, tile0, F.nc[f], F.oldF[f], F.newF[f]); break;
+        }
+    }
+    if (newFlag) {
+        // refineCell through the map, fvMeshHexRefiner.C:1562-1586: new cells (no old cell, or not the cell the old one
+        // became) are marked, the others keep their flag
+        for (int i = threadIdx.x; i < cnt; i += kThreads) {
+            const int64_t c = tile0 + i;
+            const label o = cm[i];
+            u8 out = 1;
+            if (o >= 0 && (int64_t)reverseCellMap[o] == c) out = oldFlag[o] ? 1 : 0;
+            newFlag[c] = out;
+        }
+    }
+}

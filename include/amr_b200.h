@@ -284,6 +284,15 @@ int amr_map_field(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellM
 int amr_map_fields(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nFields,
                    const int *nComp, const double *const *oldF, double *const *newF);
 
+/* fvMesh::mapFields (as amr_map_fields) AND the refiner's update of refineCell through the same map
+   (fvMeshHexRefiner.C:1562-1586, as amr_remap_refine_cell) in ONE pass over cellMap: with device buffers the map is
+   read from memory once for all fields and the marking.  reverseCellMap NULL: fields only.  refineCell [nOld] NULL =
+   the resident marking of this context; the new marking (size nNew) becomes the resident one and is copied to
+   newRefineCellOut when not NULL. */
+int amr_map_fields_and_marking(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, int nFields,
+                               const int *nComp, const double *const *oldF, double *const *newF,
+                               const int32_t *reverseCellMap, const uint8_t *refineCell, uint8_t *newRefineCellOut);
+
 /* cellLevel through a refinement/unrefinement map (hexRef3D.C:1238,1255,2132-2135 +
    hexRef.C:2457-2485): new[i] = old[cellMap[i]] + refined[cellMap[i]] - unrefined[cellMap[i]].
    refinedOld / unrefinedOld: uint8 flags over old cells, nullable. */

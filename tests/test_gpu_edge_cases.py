@@ -175,3 +175,40 @@ def test_large_host_map_uses_both_pcie_directions(ctx, kind):
     ctx.map_fields(cmd, [ad, bd], n_old, len(cm), [1, ncomp], [oad, obd])
     torch.cuda.synchronize()
     assert np.array_equal(oad.cpu().numpy(), oa) and np.array_equal(obd.cpu().numpy(), ob)
+
+
+@pytest.mark.parametrize("n_old,n_new", [(5000, 7777), (1024, 1024), (300, 3), (70000, 2 * 1024 + 1)])
+def test_fused_map_of_all_fields_and_the_marking(ctx, O, n_old, n_new):
+    """amr_map_fields_and_marking on device buffers (one pass over cellMap for every field and refineCell): fields of
+    1 / 3 / 6 / 9 / 2 components, ten fields (more than one launch holds), ragged tile ends, against numpy and the
+    oracle's refineCell rule (fvMeshHexRefiner.C:1562-1586)"""
+    import torch
+    rng = np.random.default_rng(n_old + n_new)
+    cm = rng.integers(0, n_old, n_new).astype(np.int32)
+    keep = min(n_old, n_new) // 2
+    cm[:keep] = np.arange(keep)                       # an identity run, like a real refinement map
+    rev = np.full(n_old, -1, np.int32)
+    rev[cm[::-1]] = np.arange(n_new - 1, -1, -1)      # each old cell -> the LOWEST new cell made from it
+    rc = (rng.random(n_old) < 0.3).astype(np.uint8)
+    ncs = [1, 3, 6, 9, 2, 1, 3, 1, 1, 3]
+    olds = [rng.random((n_old, nc)) if nc > 1 else rng.random(n_old) for nc in ncs]
+    d_old = [torch.from_numpy(a).cuda() for a in olds]
+    d_new = [torch.empty((n_new,) + a.shape[1:], dtype=torch.float64, device="cuda") for a in olds]
+    d_cm, d_rev, d_rc = torch.from_numpy(cm).cuda(), torch.from_numpy(rev).cuda(), torch.from_numpy(rc).cuda()
+    d_out = torch.empty(n_new, dtype=torch.uint8, device="cuda")
+    ctx.set_mesh(cases.graded_octree(8, 1).build())   # any mesh: the call is independent of it (flag pool sized by it)
+    ctx.map_fields_and_marking(d_cm, d_old, n_old, n_new, ncs, d_new, reverse_map=d_rev, refine_cell=d_rc, out_marking=d_out)
+    torch.cuda.synchronize()
+    for a, d in zip(olds, d_new):
+        assert np.array_equal(d.cpu().numpy(), a[cm])
+    assert np.array_equal(d_out.cpu().numpy(), O.remap_refine_cell(cm, rev, rc))
+    # fields only (amr_map_fields), and the host-pointer route of the same entry point
+    d_new2 = [torch.zeros_like(d) for d in d_new]
+    ctx.map_fields(d_cm, d_old, n_old, n_new, ncs, d_new2)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(d_new, d_new2))
+    h_new = [np.empty((n_new,) + a.shape[1:]) for a in olds]
+    h_out = np.empty(n_new, np.uint8)
+    ctx.map_fields_and_marking(cm, olds, n_old, n_new, ncs, h_new, reverse_map=rev, refine_cell=rc, out_marking=h_out)
+    assert all(np.array_equal(h, a[cm]) for h, a in zip(h_new, olds))
+    assert np.array_equal(h_out, O.remap_refine_cell(cm, rev, rc))

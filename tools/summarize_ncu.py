@@ -1,8 +1,9 @@
 """Turn an `ncu --csv --log-file` launch list (metrics gpu__time_duration.sum, dram__bytes_read.sum,
-dram__bytes_write.sum) of `bench.py --no-cpu --no-e2e --steps K --warmup W` into the committed summaries:
-  profiles/<tag>_launches_step.csv  one row per launch of the LAST timed step, with its share of the step
-  profiles/<tag>_traffic.json       DRAM bytes per launch per kernel (read + write), what bench.py's roofline.traffic cites
-Usage: python tools/summarize_ncu.py gpurun_out/launches.csv r1"""
+dram__bytes_write.sum) of `bench.py --no-cpu --no-e2e --no-parity --steps K --warmup W` into the committed summaries:
+  profiles/<tag>_launches_step.csv  one row per launch of the LAST timed step, with its stage and its share of the step
+  profiles/<tag>_traffic.json       measured DRAM bytes (read + write) per stage, per step and per launch of each kernel:
+                                    what bench.py's roofline.traffic / stages[*].dram_bytes / roofline.step_frac cite
+Usage: python tools/summarize_ncu.py gpurun_out/launches.csv r2 [workload base shift_cells]"""
 import csv
 import io
 import json
@@ -20,7 +21,7 @@ def short(name):
     return name.split("(")[0]
 
 
-def main(path, tag):
+def main(path, tag, workload="S2", base=176, shift=4.0):
     lines = Path(path).read_text().splitlines()
     hi = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
     rows = list(csv.DictReader(io.StringIO("\n".join(lines[hi:]))))
@@ -37,27 +38,49 @@ def main(path, tag):
     ids = list(L)
     start = [i for i in ids if "kp_estimate" in L[i]["name"] or "k_estimate" in L[i]["name"]][-1]
     step = [L[i] for i in ids if i >= start]
+    # stages of bench.py's step: E | M+B | F (first fused map) | U | F2 (second fused map)
+    stage, nmap = "E", 0
+    for d in step:
+        k = short(d["name"])
+        if "estimate" in k:
+            stage = "E"
+        elif "k_map_fields_fused" in k:
+            nmap += 1
+            stage = "F" if nmap == 1 else "F2"
+        elif stage == "E":
+            stage = "M+B"
+        elif stage == "F":
+            stage = "U"
+        d["stage"] = stage
+    step = [d for d in step if not (d["stage"] == "F2" and "k_map_fields_fused" not in d["name"])]   # nothing of the step follows F2
     tot = sum(d["ms"] for d in step)
     out = ROOT / "profiles" / f"{tag}_launches_step.csv"
     with out.open("w", newline="") as fh:
         w = csv.writer(fh)
-        w.writerow(["kernel", "grid", "block", "ms", "share_of_step", "dram_read_GB", "dram_write_GB", "dram_GBps"])
+        w.writerow(["stage", "kernel", "grid", "block", "ms", "share_of_step", "dram_read_GB", "dram_write_GB", "dram_GBps"])
         for d in step:
             by = d.get("rd", 0) + d.get("wr", 0)
-            w.writerow([short(d["name"]), d["grid"], d["block"], f'{d["ms"]:.4f}', f'{d["ms"] / tot:.4f}', f'{d.get("rd", 0) / 1e9:.4f}',
+            w.writerow([d["stage"], short(d["name"]), d["grid"], d["block"], f'{d["ms"]:.4f}', f'{d["ms"] / tot:.4f}', f'{d.get("rd", 0) / 1e9:.4f}',
                         f'{d.get("wr", 0) / 1e9:.4f}', f'{by / 1e9 / (d["ms"] / 1e3):.0f}' if d["ms"] > 0 else ""])
-        w.writerow(["TOTAL", "", "", f"{tot:.4f}", "1.0", "", "", ""])
-    traffic = OrderedDict()
+        w.writerow(["", "TOTAL", "", "", f"{tot:.4f}", "1.0", "", "", ""])
+    per_kernel = OrderedDict()
+    stage_bytes, stage_ms = OrderedDict(), OrderedDict()
     for d in step:
-        k = short(d["name"])                                       # largest launch of each kernel in the step (gated launches return at once)
-        traffic[k] = max(traffic.get(k, 0.0), d.get("rd", 0) + d.get("wr", 0))
+        k = short(d["name"])                                       # largest launch of each kernel in the step
+        by = d.get("rd", 0) + d.get("wr", 0)
+        per_kernel[k] = max(per_kernel.get(k, 0.0), by)
+        stage_bytes[d["stage"]] = stage_bytes.get(d["stage"], 0.0) + by
+        stage_ms[d["stage"]] = stage_ms.get(d["stage"], 0.0) + d["ms"]
     (ROOT / "profiles" / f"{tag}_traffic.json").write_text(json.dumps({
-        "config": "bench.py default (400^3 cells per GPU; step = E, M+B on M0; F; U on M1)",
+        "workload": workload, "base": int(base), "shift_cells": float(shift),
         "source": f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none ({out.name}); "
-                  "per launch, cold cache",
-        "traffic_bytes_per_launch": traffic}, indent=1) + "\n")
+                  "per launch, cold cache, serialised",
+        "launches_in_step": len(step), "kernel_ms_in_step_serialised": tot,
+        "stage_dram_bytes": stage_bytes, "stage_kernel_ms_serialised": stage_ms, "step_dram_bytes": sum(stage_bytes.values()),
+        "kernel_dram_bytes_per_launch": per_kernel}, indent=1) + "\n")
     print(f"{len(step)} launches, {tot:.4f} ms ->", out)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "r1")
+    a = sys.argv
+    main(a[1], a[2] if len(a) > 2 else "r2", *(a[3:6]))
