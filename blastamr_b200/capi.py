@@ -58,6 +58,7 @@ _SIGS = {
     "amr_get_split_elems": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "amr_max_cell_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_check_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_check_point_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_map_field": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_void_p]),
     "amr_map_fields": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -65,6 +66,7 @@ _SIGS = {
     "amr_update_levels": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5),
     "amr_remap_labels": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "amr_remap_protected_cells": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "amr_map_old_volumes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_correct_fluxes": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7),
     "amr_mesh_set_ls_vectors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_estimate_gradient": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
@@ -323,6 +325,14 @@ class Context:
             self._ck(rc)
         return cnt.value
 
+    def check_point_levels(self, point_level=None) -> int:
+        """hexRef.C:3027-3057; returns this rank's number of inconsistent points (the call itself reports -5 when any rank has one)"""
+        cnt = C.c_int64(0)
+        rc = self.L.amr_check_point_levels(self._h, _ptr(point_level), C.byref(cnt))
+        if rc not in (AMR_OK, -5):
+            self._ck(rc)
+        return cnt.value if rc == AMR_OK else max(cnt.value, -1) if cnt.value else -1
+
     # -- stage 4
     def map_field(self, cell_map, old, n_old=None, n_new=None, ncomp=1, out=None, mode=MAP_DIRECT, reverse_map=None,
                   vol_old=None):
@@ -378,6 +388,17 @@ class Context:
         self._ck(self.L.amr_remap_protected_cells(self._h, len(old_protected), len(cell_map), _ptr(cell_map), _ptr(old_protected),
                                                   _ptr(out)))
         return out
+
+    def map_old_volumes(self, cell_map, reverse_map, olds):
+        """V0 / V00 through a topology change (fvMesh::updateMesh): returns (new volumes, number of merged-away cells)"""
+        k = len(olds)
+        n_new = len(cell_map)
+        outs = [np.empty(n_new, dtype=np.float64) for _ in olds]
+        po = (C.c_void_p * max(k, 1))(*[_ptr(a) for a in olds])
+        pn = (C.c_void_p * max(k, 1))(*[_ptr(a) for a in outs])
+        nm = C.c_int64(0)
+        self._ck(self.L.amr_map_old_volumes(self._h, len(reverse_map), n_new, _ptr(cell_map), _ptr(reverse_map), k, po, pn, C.byref(nm)))
+        return outs, nm.value
 
     def correct_fluxes(self, face_map, reverse_face_map, U, phi, U_boundary=None, nbr_U=None):
         """adaptiveFvMesh::updateMesh flux fix-up on the mesh held by the context; phi is rewritten in place"""

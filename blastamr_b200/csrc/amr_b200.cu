@@ -123,7 +123,7 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->grad); devFree(ctx, &ctx->xbf);
     devFree(ctx, &ctx->bEmpty); devFree(ctx, &ctx->lsP); devFree(ctx, &ctx->lsN); ctx->haveLs = false;
     devFree(ctx, &ctx->visible); devFree(ctx, &ctx->splitParent); ctx->nSplit = 0;
-    devFree(ctx, &ctx->ppPts); ctx->ppOff.clear();
+    devFree(ctx, &ctx->ppPts); ctx->ppOff.clear(); ctx->havePointPlan = false;
     sellFree(ctx, ctx->cf);
     ctx->haveGeom = false;
     sellFree(ctx, ctx->ec); devFree(ctx, &ctx->bndEdge); devFree(ctx, &ctx->edgePts);
@@ -147,6 +147,7 @@ AMR_API int amr_ctx_destroy(amr_ctx *ctx) {
             if (r != ctx->rank && ctx->peerHost[(size_t)r]) cudaIpcCloseMemHandle(ctx->peerHost[(size_t)r]);
         cudaFree(ctx->peerDev); cudaFree(ctx->redVal);
         delete (HaloPlan *)ctx->haloPlan;
+        delete (HaloPlan *)ctx->pointPlanPtr;
     }
     if (ctx->region) cudaFree(ctx->region);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
@@ -274,6 +275,7 @@ static int peerSetup(amr_ctx *ctx) {
         return rc;          // AMR_OK: the NCCL path stays
     }
     ctx->haloPlan = new HaloPlan();
+    ctx->pointPlanPtr = new HaloPlan();
     ctx->usePeer = true;
     return AMR_OK;
 }
@@ -660,6 +662,55 @@ AMR_API int amr_mesh_set_faces(amr_ctx *ctx, const int32_t *faceOff, const int32
     return AMR_OK;
 }
 
+// per-mesh plan of the POINT swaps (syncTools::syncPointList sites): like peerPlan, over the patches' point lists.
+// Collective: every rank of the communicator calls amr_mesh_set_patch_points (with empty lists when it has none).
+static int pointPlan(amr_ctx *ctx) {
+    ctx->havePointPlan = false;
+    if (!ctx->comm || ctx->nranks < 2 || !ctx->usePeer) return AMR_OK;
+    HaloPlan &P = *(HaloPlan *)ctx->pointPlanPtr;
+    P.nPatch = 0; P.prefix[0] = 0;
+    int ok = ctx->havePlan ? 1 : 0;
+    std::vector<int32_t> mine, nbrs;
+    const size_t npatch = ctx->patches.size();
+    for (size_t k = 0; k < npatch; k++) {
+        const Patch &q = ctx->patches[k];
+        const int32_t cnt = ctx->ppOff[k + 1] - ctx->ppOff[k];
+        if (q.type != AMR_PATCH_PROCESSOR || q.size == 0) continue;       // same patches as peerPlan's send/recv pairs
+        mine.push_back(ctx->ppOff[k]); mine.push_back(cnt); nbrs.push_back(q.nbr);
+    }
+    const int np = (int)nbrs.size();
+    if (np > 32) ok = 0;
+    if ((int64_t)ctx->ppOff[npatch] * 8 > kHaloCap) ok = 0;
+    std::vector<int32_t> theirs((size_t)(2 * np > 0 ? 2 * np : 1), 0);
+    void *q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(2 * np + 4) * 4)); int32_t *dMine = (int32_t *)q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(2 * np + 4) * 4)); int32_t *dTheirs = (int32_t *)q;
+    if (np) CK(cudaMemcpyAsync(dMine, mine.data(), (size_t)2 * np * 4, cudaMemcpyHostToDevice, ctx->stream));
+    NCK(ncclGroupStart());
+    for (int k = 0; k < np; k++) {
+        NCK(ncclSend(dMine + 2 * k, 2, ncclInt32, nbrs[(size_t)k], ctx->comm, ctx->stream));
+        NCK(ncclRecv(dTheirs + 2 * k, 2, ncclInt32, nbrs[(size_t)k], ctx->comm, ctx->stream));
+    }
+    NCK(ncclGroupEnd());
+    if (np) CK(cudaMemcpyAsync(theirs.data(), dTheirs, (size_t)2 * np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < np; k++)
+        if (theirs[(size_t)2 * k + 1] != mine[(size_t)2 * k + 1]) ok = 0;     // the two sides list different numbers of points
+    int32_t *dAgree = dMine + 2 * np;
+    CK(cudaMemcpyAsync(dAgree, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    NCK(ncclAllReduce(dAgree, dAgree, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+    CK(cudaMemcpyAsync(&ok, dAgree, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!ok) return AMR_OK;                          // agreed: NCCL transport for the point swaps of this mesh
+    for (int k = 0; k < np; k++) {
+        P.nbr[k] = nbrs[(size_t)k]; P.offMine[k] = mine[(size_t)2 * k]; P.size[k] = mine[(size_t)2 * k + 1];
+        P.offTheirs[k] = theirs[(size_t)2 * k]; P.prefix[k + 1] = P.prefix[k] + P.size[k];
+    }
+    P.nPatch = np;
+    ctx->havePointPlan = true;
+    return AMR_OK;
+}
+
 AMR_API int amr_mesh_set_patch_points(amr_ctx *ctx, const int32_t *patchPointOff, const int32_t *patchPoints) {
     ENTER();
     if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_mesh_set_patch_points: call amr_mesh_set first");
@@ -674,6 +725,47 @@ AMR_API int amr_mesh_set_patch_points(amr_ctx *ctx, const int32_t *patchPointOff
     TRY(devAlloc(ctx, &ctx->ppPts, tot > 0 ? tot : 1));
     if (tot) CK(cudaMemcpyAsync(ctx->ppPts, patchPoints, (size_t)tot * 4, cudaMemcpyDefault, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return pointPlan(ctx);
+}
+
+// swap of a per-point array over the processor patches' point lists: recv[i] = the neighbour's value at the point that
+// pairs with my i-th patch point (processorPolyPatch::meshPoints() against neighbPoints()).  Peer memory when the ranks
+// agreed on it for this mesh, else grouped ncclSend / ncclRecv.  recv is laid out like the patch point lists.
+static int pointSwap(amr_ctx *ctx, const void *values, size_t elemBytes, void *recv) {
+    const size_t np = ctx->ppOff.empty() ? 0 : ctx->patches.size();
+    const int64_t tot = np ? ctx->ppOff[np] : 0;
+    if (ctx->havePointPlan) {
+        const HaloPlan &P = *(const HaloPlan *)ctx->pointPlanPtr;
+        const unsigned g = gridFor(P.prefix[P.nPatch]);
+        unsigned *c1 = (unsigned *)(ctx->dFlags + 6), *c2 = (unsigned *)(ctx->dFlags + 7);
+        const unsigned long long to = ctx->peerTimeoutNs;
+        if (elemBytes == 1) {
+            k_halo_push_cells<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, (const label *)ctx->ppPts, (const char *)values, (const u8 *)nullptr, c1, (const int *)nullptr);
+            k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, ctx->dSeq, (char *)recv, to, c2, (const int *)nullptr);
+        } else {
+            k_halo_push_cells<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, (const label *)ctx->ppPts, (const char *)values, (const u8 *)nullptr, c1, (const int *)nullptr);
+            k_halo_unpack<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, ctx->dSeq, (char *)recv, to, c2, (const int *)nullptr);
+        }
+        ctx->launches += 2;
+        ctx->peerTouched = true;
+        return AMR_OK;
+    }
+    void *q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(tot > 0 ? tot : 1) * elemBytes));
+    char *send = (char *)q;
+    if (tot) {
+        if (elemBytes == 1) LAUNCH(k_pack_u8, gridFor(tot), kThreads, tot, (const label *)ctx->ppPts, (const u8 *)values, (u8 *)send);
+        else LAUNCH(k_pack_i32, gridFor(tot), kThreads, tot, (const label *)ctx->ppPts, (const label *)values, (label *)send);
+    }
+    NCK(ncclGroupStart());
+    for (size_t k = 0; k < np; k++) {
+        const Patch &pp = ctx->patches[k];
+        const int64_t cnt = ctx->ppOff[k + 1] - ctx->ppOff[k];
+        if (pp.type != AMR_PATCH_PROCESSOR || cnt == 0) continue;
+        NCK(ncclSend(send + (size_t)ctx->ppOff[k] * elemBytes, (size_t)cnt * elemBytes, ncclUint8, pp.nbr, ctx->comm, ctx->stream));
+        NCK(ncclRecv((char *)recv + (size_t)ctx->ppOff[k] * elemBytes, (size_t)cnt * elemBytes, ncclUint8, pp.nbr, ctx->comm, ctx->stream));
+    }
+    NCK(ncclGroupEnd());
     return AMR_OK;
 }
 
@@ -687,28 +779,59 @@ static int syncPointsOr(amr_ctx *ctx, u8 *pflag) {
         FAIL(AMR_ERR_STATE, "point sync across processor patches needs their point lists (amr_mesh_set_patch_points)");
     const size_t np = ctx->ppOff.empty() ? 0 : ctx->patches.size();
     const int64_t tot = np ? ctx->ppOff[np] : 0;
-    u8 *send = nullptr, *recv = nullptr;
     void *q;
-    TRY(arenaAlloc(ctx, &q, (size_t)(tot > 0 ? tot : 1))); send = (u8 *)q;
-    TRY(arenaAlloc(ctx, &q, (size_t)(tot > 0 ? tot : 1))); recv = (u8 *)q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(tot > 0 ? tot : 1)));
+    u8 *recv = (u8 *)q;
     for (int round = 0; round < 64; round++) {
         CK(cudaMemsetAsync(ctx->dFlags + 11, 0, sizeof(int), ctx->stream));
-        if (tot) LAUNCH(k_pack_u8, gridFor(tot), kThreads, tot, (const label *)ctx->ppPts, (const u8 *)pflag, send);
-        NCK(ncclGroupStart());
-        for (size_t k = 0; k < np; k++) {
-            const Patch &pp = ctx->patches[k];
-            const int64_t cnt = ctx->ppOff[k + 1] - ctx->ppOff[k];
-            if (pp.type != AMR_PATCH_PROCESSOR || cnt == 0) continue;
-            NCK(ncclSend(send + ctx->ppOff[k], (size_t)cnt, ncclUint8, pp.nbr, ctx->comm, ctx->stream));
-            NCK(ncclRecv(recv + ctx->ppOff[k], (size_t)cnt, ncclUint8, pp.nbr, ctx->comm, ctx->stream));
-        }
-        NCK(ncclGroupEnd());
+        TRY(pointSwap(ctx, pflag, 1, recv));
         if (tot) LAUNCH(k_or_scatter, gridFor(tot), kThreads, tot, (const label *)ctx->ppPts, (const u8 *)recv, pflag, ctx->dFlags + 11);
         int changed = 0;
         TRY(globalFlag(ctx, 11, &changed));
         if (!changed) return AMR_OK;
     }
     FAIL(AMR_ERR_INVARIANT, "point sync did not settle");
+}
+
+// "Check pointLevel is synchronized" of hexRef::checkRefinementLevels (hexRef.C:3027-3057): the reference min-syncs a
+// copy of pointLevel_ over the coupled points and aborts where the copy differs from the original, i.e. where the
+// ranks sharing a point do not all hold the same level.  Every sharer of a processor-patch point is linked to
+// another one by a patch that lists the point, so one pairwise swap over the patches' point lists finds every
+// disagreement.  Counts the points of THIS rank whose level differs from a neighbour's; collective.
+__global__ void k_point_level_mismatch(int64_t tot, const label *__restrict__ ppPts, const label *__restrict__ pointLevel,
+                                       const label *__restrict__ recv, u8 *__restrict__ badPoint) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < tot && recv[i] != pointLevel[ppPts[i]]) badPoint[ppPts[i]] = 1;
+}
+AMR_API int amr_check_point_levels(amr_ctx *ctx, const int32_t *pointLevel, int64_t *nBad) {
+    ENTER();
+    if (nBad) *nBad = 0;
+    const int64_t p = ctx->p;
+    const int32_t *dPl = nullptr;
+    TRY(stageIn(ctx, pointLevel, p, &dPl));
+    if (!dPl) dPl = ctx->pointLevel;
+    if (!dPl) FAIL(AMR_ERR_STATE, "amr_check_point_levels: no pointLevel (amr_levels_set)");
+    if (!ctx->comm || ctx->nranks < 2) return AMR_OK;            // nothing is coupled on a single rank
+    if (ctx->nCoupled > 0 && ctx->ppOff.empty())
+        FAIL(AMR_ERR_STATE, "amr_check_point_levels: the processor patches' point lists are needed (amr_mesh_set_patch_points)");
+    const size_t np = ctx->ppOff.empty() ? 0 : ctx->patches.size();
+    const int64_t tot = np ? ctx->ppOff[np] : 0;
+    void *q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(tot > 0 ? tot : 1) * 4));
+    label *recv = (label *)q;
+    u8 *bad = ctx->flagC;
+    if (p) CK(cudaMemsetAsync(bad, 0, (size_t)p, ctx->stream));
+    TRY(pointSwap(ctx, dPl, 4, recv));
+    if (tot) LAUNCH(k_point_level_mismatch, gridFor(tot), kThreads, tot, (const label *)ctx->ppPts, dPl, (const label *)recv, bad);
+    CK(cudaMemsetAsync(ctx->dCount, 0, 8, ctx->stream));
+    if (p) LAUNCH(k_count_flags, gridFor(p), kThreads, p, (const u8 *)bad, (unsigned long long *)ctx->dCount);
+    CK(cudaMemcpyAsync(ctx->hCount, ctx->dCount, 8, cudaMemcpyDeviceToHost, ctx->stream));   // this rank's count, before the reduction
+    int64_t total = 0;
+    TRY(globalSum(ctx, 0, &total));
+    if (nBad) *nBad = ctx->hCount[0] > total ? total : ctx->hCount[0];
+    CK(cudaGetLastError());
+    if (total > 0) FAIL(AMR_ERR_INVARIANT, "PointLevel is not consistent across coupled patches. (hexRef.C:3047)");
+    return AMR_OK;
 }
 
 AMR_API int amr_set_option(amr_ctx *ctx, int option, int64_t value) {
@@ -1990,7 +2113,7 @@ static int launchMapField(amr_ctx *ctx, int64_t nNew, int nComp, const int32_t *
 static int launchMapFused(amr_ctx *ctx, int64_t nNew, const int32_t *dMap, int nFields, const int *nComp, const double *const *dOld,
                           double *const *dNew, const int32_t *dRev, const u8 *dOldFlag, u8 *dNewFlag) {
     if (nNew <= 0) return AMR_OK;
-    const unsigned grid = gridFor(nNew, kMapTile);
+    const int64_t chunks = (nNew + kMapChunk - 1) / kMapChunk;
     int done = 0;
     bool flagsDone = dNewFlag == nullptr;
     while (done < nFields || !flagsDone) {
@@ -2002,7 +2125,9 @@ static int launchMapFused(amr_ctx *ctx, int64_t nNew, const int32_t *dMap, int n
         }
         for (int k = F.nFields; k < kMaxMapFields; k++) { F.nc[k] = 0; F.oldF[k] = nullptr; F.newF[k] = nullptr; }
         const bool withFlags = !flagsDone;
-        LAUNCH(k_map_fields_fused, grid, kThreads, nNew, dMap, F, withFlags ? dRev : (const int32_t *)nullptr,
+        const int nStreams = F.nFields + (withFlags ? 1 : 0);
+        if (chunks * nStreams > 0x7fffffff) FAIL(AMR_ERR_ARG, "amr_map_fields: too many cells for one launch");
+        LAUNCH(k_map_fields_fused, (unsigned)(chunks * nStreams), kThreads, nNew, dMap, F, nStreams, withFlags ? dRev : (const int32_t *)nullptr,
                withFlags ? dOldFlag : (const u8 *)nullptr, withFlags ? dNewFlag : (u8 *)nullptr);
         flagsDone = true;
     }
@@ -2179,6 +2304,66 @@ AMR_API int amr_remap_protected_cells(amr_ctx *ctx, int64_t nOld, int64_t nNew, 
     TRY(stageIn(ctx, oldProtected, nOld, &dOld));
     TRY(stageOut(ctx, newProtected, nNew, &dNew));
     if (nNew) LAUNCH(k_gather_protected, gridFor(nNew), kThreads, nNew, dMap, dOld, dNew);
+    CK(cudaGetLastError());
+    return flushOuts(ctx);
+}
+
+AMR_API int amr_map_old_volumes(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, const int32_t *reverseCellMap,
+                                int nVolumes, const double *const *oldV, double *const *newV, int64_t *nMerged) {
+    ENTER();
+    if (!cellMap || !reverseCellMap || nOld < 0 || nNew < 0 || nVolumes < 0 || (nVolumes > 0 && (!oldV || !newV)))
+        FAIL(AMR_ERR_ARG, "amr_map_old_volumes: bad arguments");
+    const int32_t *dMap = nullptr, *dRev = nullptr;
+    TRY(stageIn(ctx, cellMap, nNew, &dMap));
+    TRY(stageIn(ctx, reverseCellMap, nOld, &dRev));
+    std::vector<const double *> dOld((size_t)std::max(nVolumes, 1), nullptr);
+    std::vector<double *> dNew((size_t)std::max(nVolumes, 1), nullptr);
+    for (int k = 0; k < nVolumes; k++) {
+        if (!oldV[k] || !newV[k]) FAIL(AMR_ERR_ARG, "amr_map_old_volumes: null volume field");
+        TRY(stageIn(ctx, oldV[k], nOld, &dOld[(size_t)k]));
+        TRY(stageOut(ctx, newV[k], nNew, &dNew[(size_t)k]));
+        if (nNew) LAUNCH(k_map_old_volume, gridFor(nNew), kThreads, nNew, dMap, dOld[(size_t)k], dNew[(size_t)k]);
+    }
+    // masters of the merges, ascending, and the slot blocks of their merged cells
+    void *q;
+    const int64_t tiles = (nNew + kTile - 1) / kTile + 8;
+    if (tiles > ctx->tileCap) {                       // the map may belong to a larger mesh than the one held by the context
+        devFree(ctx, &ctx->lbStatus);
+        ctx->tileCap = tiles;
+        TRY(devAlloc(ctx, &ctx->lbStatus, ctx->tileCap));
+        CK(cudaMemsetAsync(ctx->lbStatus, 0, (size_t)ctx->tileCap * 8, ctx->stream));
+    }
+    TRY(arenaAlloc(ctx, &q, (size_t)nNew + 16)); u8 *isMaster = (u8 *)q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(nNew > 0 ? nNew : 1) * 4)); label *masters = (label *)q;
+    TRY(arenaAlloc(ctx, &q, (size_t)(nNew > 0 ? nNew : 1) * 4)); label *indexOf = (label *)q;
+    CK(cudaMemsetAsync(isMaster, 0, (size_t)nNew + 16, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dCount + 3, 0, 8, ctx->stream));
+    if (nOld) LAUNCH(k_merge_masters, gridFor(nOld), kThreads, nOld, dRev, isMaster, (unsigned long long *)(ctx->dCount + 3));
+    int32_t *nM = nullptr;
+    TRY(compactFlags(ctx, isMaster, nNew, masters, &nM));
+    CK(cudaMemcpyAsync(ctx->hFlags + 8, nM, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->hCount + 3, ctx->dCount + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int64_t nMasters = ctx->hFlags[8];
+    if (nMerged) *nMerged = ctx->hCount[3];
+    if (nMasters > 0 && nVolumes > 0) {
+        const unsigned g = (unsigned)std::min<int64_t>((int64_t)ctx->numSMs * 8, (nMasters + kThreads - 1) / kThreads);
+        LAUNCH(k_merge_index, g, kThreads, (const int32_t *)nM, (const label *)masters, indexOf);
+        TRY(arenaAlloc(ctx, &q, (size_t)nMasters * 4)); int *cursor = (int *)q;
+        int K = 8;                                    // hexRef3D merges 7 cells into the 8th; retried with the real maximum otherwise
+        for (int attempt = 0; attempt < 2; attempt++) {
+            TRY(arenaAlloc(ctx, &q, (size_t)nMasters * K * 4)); label *slots = (label *)q;
+            CK(cudaMemsetAsync(cursor, 0, (size_t)nMasters * 4, ctx->stream));
+            CK(cudaMemsetAsync(ctx->dFlags + 10, 0, sizeof(int), ctx->stream));
+            LAUNCH(k_merge_slots, gridFor(nOld), kThreads, nOld, dRev, (const label *)indexOf, K, cursor, slots, ctx->dFlags + 10);
+            CK(cudaMemcpyAsync(ctx->hFlags + 10, ctx->dFlags + 10, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->hFlags[10] > K) { K = ctx->hFlags[10]; continue; }
+            for (int k = 0; k < nVolumes; k++)
+                LAUNCH(k_merge_inject, g, kThreads, (const int32_t *)nM, (const label *)masters, K, (const int *)cursor, slots, dOld[(size_t)k], dNew[(size_t)k]);
+            break;
+        }
+    }
     CK(cudaGetLastError());
     return flushOuts(ctx);
 }

@@ -67,6 +67,8 @@ struct amr_ctx {
     bool peerTouched = false;          // a peer-memory exchange was enqueued since the error word was last read
     void *haloPlan = nullptr;          // HaloPlan (host copy), rebuilt at amr_mesh_set
     bool havePlan = false;
+    void *pointPlanPtr = nullptr;      // HaloPlan of the point swaps (syncPointList), rebuilt at amr_mesh_set_patch_points
+    bool havePointPlan = false;
     unsigned long long *redVal = nullptr;   // device staging word for reductions
     std::string err;
     int numSMs = 148;

@@ -400,3 +400,65 @@ __global__ void k_fill_int(int64_t n, int v, int *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = v;
 }
+
+// ---- old-time volumes through a topology change (fvMesh::updateMesh, OpenFOAM core; SURVEY App. A "V0/V00 additionally
+// receive merged-cell volume injection").  Direct map, then every merged-away old cell adds its volume to its master.
+// The reference adds in ascending old label.  Here the merged cells of each master are collected into a small slot
+// block (atomic cursor, any order), sorted ascending by the master's thread and added in that order: the sum order --
+// and the result, bit for bit -- is the reference's.
+__global__ void __launch_bounds__(kThreads)
+k_map_old_volume(int64_t nNew, const label *__restrict__ cellMap, const double *__restrict__ oldV, double *__restrict__ newV) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= nNew) return;
+    const label o = cellMap[i];
+    newV[i] = o > -1 ? oldV[o] : 0.0;
+}
+// merged-away old cells (reverseCellMap < -1) flag their masters
+__global__ void __launch_bounds__(kThreads)
+k_merge_masters(int64_t nOld, const label *__restrict__ reverseCellMap, u8 *__restrict__ isMaster, unsigned long long *nMerged) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int hit = 0;
+    if (c < nOld) {
+        const label r = reverseCellMap[c];
+        if (r < -1) { isMaster[-r - 2] = 1; hit = 1; }
+    }
+    const int cnt = __syncthreads_count(hit);
+    if (threadIdx.x == 0 && cnt) atomicAdd(nMerged, (unsigned long long)cnt);
+}
+__global__ void __launch_bounds__(kThreads)
+k_merge_index(const int32_t *__restrict__ nMasters, const label *__restrict__ masters, label *__restrict__ indexOf) {
+    const int cnt = *nMasters;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < cnt; i += gridDim.x * kThreads) indexOf[masters[i]] = i;
+}
+// every merged cell takes a slot of its master's block; overflow (more than K merged cells for one master) is reported
+__global__ void __launch_bounds__(kThreads)
+k_merge_slots(int64_t nOld, const label *__restrict__ reverseCellMap, const label *__restrict__ indexOf, int K, int *__restrict__ cursor,
+              label *__restrict__ slots, int *overflow) {
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= nOld) return;
+    const label r = reverseCellMap[c];
+    if (r >= -1) return;
+    const label i = indexOf[-r - 2];
+    const int pos = atomicAdd(&cursor[i], 1);
+    if (pos < K) slots[(size_t)i * K + pos] = (label)c;
+    else atomicMax(overflow, pos + 1);
+}
+__global__ void __launch_bounds__(kThreads)
+k_merge_inject(const int32_t *__restrict__ nMasters, const label *__restrict__ masters, int K, const int *__restrict__ cursor,
+               label *__restrict__ slots, const double *__restrict__ oldV, double *newV) {
+    const int cnt = *nMasters;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < cnt; i += gridDim.x * kThreads) {
+        label *row = slots + (size_t)i * K;
+        const int d = min(cursor[i], K);
+        for (int a = 1; a < d; a++) {                    // ascending old label
+            const label v = row[a];
+            int j = a - 1;
+            while (j >= 0 && row[j] > v) { row[j + 1] = row[j]; j--; }
+            row[j + 1] = v;
+        }
+        const label m = masters[i];
+        double v = newV[m];
+        for (int a = 0; a < d; a++) v += oldV[row[a]];
+        newV[m] = v;
+    }
+}

@@ -54,7 +54,7 @@ __device__ __forceinline__ void blockAddCount(int cnt, unsigned long long *total
 // ------------------------------------------------------------------------------------------
 
 // source test of a layer: separate source array (the forced first layer) or generation range of the marking itself
-__device__ __forceinline__ bool isSource(unsigned v, int gen, bool separate) { return separate ? v != 0u : (v != 0u && v <= (unsigned)gen); }
+__device__ __forceinline__ bool isSource(unsigned v, int gen, bool separate) { return separate ? v != 0u : (v - 1u) < (unsigned)gen; }
 
 // sparse push form: rows of the source cells; marks written are gen+1.  nSrc receives the exact number of sources.
 __global__ void __launch_bounds__(kThreads)
@@ -138,7 +138,8 @@ kp_layer_pull(SellView S, const u8 *srcArr, bool separate, int gen, u8 *cur, uns
 #pragma unroll
                 for (int k = 0; k < NW; k++) v[k] = srcArr[q[k]];
 #pragma unroll
-                for (int k = 0; k < NW; k++) hit |= (isSource(v[k], gen, separate) && q[k] != c) ? 1u : 0u;
+                // padding reads the cell's own value: a marked cell is never written, an unmarked one is no source
+                for (int k = 0; k < NW; k++) hit |= isSource(v[k], gen, separate) ? 1u : 0u;
             });
         }
         if (valid && own == 0 && hit) cur[c] = tag;
@@ -421,14 +422,16 @@ __global__ void k_fix_unref_problem(int64_t nC, const label *__restrict__ cplFac
 }
 
 // ------------------------------------------------------------------------------------------
-// STAGE 4  all registered fields through the map in ONE pass
+// STAGE 4  all registered fields through the map in ONE launch
 // ------------------------------------------------------------------------------------------
 // fvMesh::mapFields maps every registered field through the same mapPolyMesh::cellMap() (MapGeometricFields over the
-// object registry); the refiner then carries refineCell through the same map (fvMeshHexRefiner.C:1562-1586).  One CTA
-// stages the cellMap entries of a tile of new cells in shared memory once and then streams every field (and the
-// marking) through them: the map is read from HBM once instead of once per field.  Multi-component fields move as
-// pairs of consecutive elements (one 128-bit store, one 128-bit load where the two sources are consecutive).
-constexpr int kMapTile = 1024;           // new cells per CTA
+// object registry); the refiner then carries refineCell through the same map (fvMeshHexRefiner.C:1562-1586).  One
+// launch covers all of them: CTA b works on chunk b / nStreams of the new cells for stream b % nStreams (a field, or
+// the marking), so the CTAs that need the same piece of cellMap are adjacent in launch order and run at the same time
+// -- the piece comes from HBM once and from L2 for the other streams.  Each CTA runs the single-field code path
+// (pairs of consecutive elements: one 128-bit store, one 128-bit load where the two sources are consecutive), which
+// keeps the register count of the standalone kernels.
+constexpr int kMapChunk = 2048;          // new cells per CTA
 constexpr int kMaxMapFields = 8;
 struct MapFieldSet {
     int nFields;
@@ -438,32 +441,32 @@ struct MapFieldSet {
 };
 
 template <int NC>
-__device__ __forceinline__ void mapTileField(const int *__restrict__ cm, int cnt, int64_t tile0, const double *__restrict__ oldF,
-                                             double *__restrict__ newF) {
-    const int total = cnt * NC;                              // elements of this tile; its first element index is even
-    double *dst = newF + tile0 * NC;
+__device__ __forceinline__ void mapChunkField(const label *__restrict__ cellMap, int64_t c0, int cnt, const double *__restrict__ oldF,
+                                              double *__restrict__ newF) {
+    const int64_t e0 = c0 * NC;                              // even: c0 is a multiple of kMapChunk
+    const int total = cnt * NC;
     if ((((uintptr_t)oldF) | ((uintptr_t)newF)) & 15) {      // unaligned field: element form
         for (int e = threadIdx.x; e < total; e += kThreads) {
             const int i = e / NC;
-            dst[e] = oldF[(int64_t)cm[i] * NC + (e - i * NC)];
+            newF[e0 + e] = oldF[(int64_t)cellMap[c0 + i] * NC + (e - i * NC)];
         }
         return;
     }
     const int pairs = total >> 1;
     for (int p0 = threadIdx.x; p0 < pairs; p0 += 4 * kThreads) {
         int64_t s0[4], s1[4];
-        double2 v[4];
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             const int p = p0 + t * kThreads;
-            s0[t] = -1;
+            s0[t] = -1; s1[t] = -1;
             if (p < pairs) {
                 const int e = 2 * p;
                 const int i = e / NC, k = e - i * NC;
-                s0[t] = (int64_t)cm[i] * NC + k;
-                s1[t] = (k + 1 < NC) ? s0[t] + 1 : (int64_t)cm[i + 1] * NC;
+                s0[t] = (int64_t)cellMap[c0 + i] * NC + k;
+                s1[t] = (k + 1 < NC) ? s0[t] + 1 : (int64_t)cellMap[c0 + i + 1] * NC;
             }
         }
+        double2 v[4];
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             if (s0[t] < 0) continue;
@@ -472,54 +475,56 @@ __device__ __forceinline__ void mapTileField(const int *__restrict__ cm, int cnt
         }
 #pragma unroll
         for (int t = 0; t < 4; t++)
-            if (s0[t] >= 0) *reinterpret_cast<double2 *>(dst + 2 * (p0 + t * kThreads)) = v[t];
+            if (s0[t] >= 0) *reinterpret_cast<double2 *>(newF + e0 + 2 * (p0 + t * kThreads)) = v[t];
     }
-    if ((total & 1) && threadIdx.x == 0) {                   // odd tail (last tile only)
+    if ((total & 1) && threadIdx.x == 0) {                   // odd tail (last chunk only)
         const int e = total - 1, i = e / NC;
-        dst[e] = oldF[(int64_t)cm[i] * NC + (e - i * NC)];
+        newF[e0 + e] = oldF[(int64_t)cellMap[c0 + i] * NC + (e - i * NC)];
     }
 }
-__device__ __forceinline__ void mapTileFieldN(const int *__restrict__ cm, int cnt, int64_t tile0, int nc, const double *__restrict__ oldF,
-                                              double *__restrict__ newF) {
+__device__ __noinline__ void mapChunkFieldN(const label *__restrict__ cellMap, int64_t c0, int cnt, int nc, const double *__restrict__ oldF,
+                                            double *__restrict__ newF) {
     const int total = cnt * nc;
-    double *dst = newF + tile0 * nc;
     for (int e = threadIdx.x; e < total; e += kThreads) {
         const int i = e / nc;
-        dst[e] = oldF[(int64_t)cm[i] * nc + (e - i * nc)];
+        newF[c0 * nc + e] = oldF[(int64_t)cellMap[c0 + i] * nc + (e - i * nc)];
     }
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_map_fields_fused(int64_t nNew, const label *__restrict__ cellMap, MapFieldSet F, const label *__restrict__ reverseCellMap,
-                   const u8 *__restrict__ oldFlag, u8 *__restrict__ newFlag) {
-    __shared__ __align__(16) int cm[kMapTile + 4];
-    const int64_t tile0 = (int64_t)blockIdx.x * kMapTile;
-    const int cnt = (int)min((int64_t)kMapTile, nNew - tile0);
-    if (cnt == kMapTile) {
-        reinterpret_cast<int4 *>(cm)[threadIdx.x] = reinterpret_cast<const int4 *>(cellMap + tile0)[threadIdx.x];
-    } else {
-        for (int i = threadIdx.x; i < cnt; i += kThreads) cm[i] = cellMap[tile0 + i];
-    }
-    if (threadIdx.x == 0) cm[cnt] = 0;                        // read (not used) by the pair walk at the tile end
-    __syncthreads();
-    for (int f = 0; f < F.nFields; f++) {
-        switch (F.nc[f]) {
-        case 1: mapTileField<1>(cm, cnt, tile0, F.oldF[f], F.newF[f]); break;
-        case 3: mapTileField<3>(cm, cnt, tile0, F.oldF[f], F.newF[f]); break;
-        case 6: mapTileField<6>(cm, cnt, tile0, F.oldF[f], F.newF[f]); break;
-        case 9: mapTileField<9>(cm, cnt, tile0, F.oldF[f], F.newF[f]); break;
-        default: mapTileFieldN(cm, cnt, tile0, F.nc[f], F.oldF[f], F.newF[f]); break;
+k_map_fields_fused(int64_t nNew, const label *__restrict__ cellMap, const __grid_constant__ MapFieldSet F, int nStreams,
+                   const label *__restrict__ reverseCellMap, const u8 *__restrict__ oldFlag, u8 *__restrict__ newFlag) {
+    const int64_t chunk = blockIdx.x / nStreams;
+    const int stream = blockIdx.x - (int)chunk * nStreams;
+    const int64_t c0 = chunk * kMapChunk;
+    const int cnt = (int)min((int64_t)kMapChunk, nNew - c0);
+    if (stream < F.nFields) {
+        const double *oldF = F.oldF[stream];
+        double *newF = F.newF[stream];
+        switch (F.nc[stream]) {
+        case 1: mapChunkField<1>(cellMap, c0, cnt, oldF, newF); break;
+        case 3: mapChunkField<3>(cellMap, c0, cnt, oldF, newF); break;
+        case 6: mapChunkField<6>(cellMap, c0, cnt, oldF, newF); break;
+        case 9: mapChunkField<9>(cellMap, c0, cnt, oldF, newF); break;
+        default: mapChunkFieldN(cellMap, c0, cnt, F.nc[stream], oldF, newF); break;
         }
-    }
-    if (newFlag) {
+    } else {
         // refineCell through the map, fvMeshHexRefiner.C:1562-1586: new cells (no old cell, or not the cell the old one
-        // became) are marked, the others keep their flag
-        for (int i = threadIdx.x; i < cnt; i += kThreads) {
-            const int64_t c = tile0 + i;
-            const label o = cm[i];
-            u8 out = 1;
-            if (o >= 0 && (int64_t)reverseCellMap[o] == c) out = oldFlag[o] ? 1 : 0;
-            newFlag[c] = out;
+        // became) are marked, the others keep their flag.  The three dependent loads batched over 8 cells per thread.
+        for (int h = 0; h < kMapChunk; h += 4 * kThreads) {
+            label o[4], r[4];
+            u8 v[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) { const int i = h + threadIdx.x + t * kThreads; o[t] = (i < cnt) ? cellMap[c0 + i] : -1; }
+#pragma unroll
+            for (int t = 0; t < 4; t++) r[t] = (o[t] >= 0) ? reverseCellMap[o[t]] : -1;
+#pragma unroll
+            for (int t = 0; t < 4; t++) v[t] = (o[t] >= 0) ? oldFlag[o[t]] : (u8)1;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int i = h + threadIdx.x + t * kThreads;
+                if (i < cnt) newFlag[c0 + i] = (o[t] < 0 || (int64_t)r[t] != c0 + i) ? (u8)1 : (v[t] ? (u8)1 : (u8)0);
+            }
         }
     }
 }

@@ -39,10 +39,17 @@ __device__ __forceinline__ void mbarWait(uint64_t *bar, unsigned parity) {
             : "memory");
     } while (!ok);
 }
-// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
-                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier.  The adjacency is a pure stream
+// (every tile is read once per kernel): it goes through L2 with an evict-first policy so that it does not push out the
+// field values / flags that the gathers of neighbouring tiles are about to re-use.
+__device__ __forceinline__ uint64_t evictFirstPolicy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, unsigned bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smemAddr(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)), "l"(policy)
                  : "memory");
 }
 
@@ -82,6 +89,7 @@ __device__ __forceinline__ void sellPipeline(const SellView &S, Body body) {
     if (warp == kTileSlices) {
         // ---------------- producer warp (one elected lane drives the TMA engine)
         if (lane == 0) {
+            const uint64_t pol = evictFirstPolicy();
             int stage = 0;
             unsigned phase = 0;
             for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -91,8 +99,8 @@ __device__ __forceinline__ void sellPipeline(const SellView &S, Body body) {
                 const int32_t b0 = S.sliceOff[s0], b1 = S.sliceOff[s1];
                 const unsigned bytes = (unsigned)(b1 - b0) * 128u;
                 mbarExpectTx(&full[stage], bytes + kHdrInts * 4);
-                bulkLoad(hdr + stage * kHdrInts, S.sliceOff + s0, kHdrInts * 4, &full[stage]);
-                if (bytes) bulkLoad(ring + (size_t)stage * S.stageInts, S.col + ((size_t)b0 << 5), bytes, &full[stage]);
+                bulkLoad(hdr + stage * kHdrInts, S.sliceOff + s0, kHdrInts * 4, &full[stage], pol);
+                if (bytes) bulkLoad(ring + (size_t)stage * S.stageInts, S.col + ((size_t)b0 << 5), bytes, &full[stage], pol);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }

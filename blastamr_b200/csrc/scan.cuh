@@ -113,11 +113,14 @@ static int deviceExclusiveScan(amr_ctx *ctx, const int32_t *in, int32_t *out, in
 // ---- single-pass compaction (decoupled look-back) ---------------------------------------------------------
 // One launch turns byte flags into the ascending list: every CTA takes the next tile (dynamic ticket, so that all
 // predecessors of a tile are already running), counts its set flags, publishes the count, looks back over the
-// predecessors' published counts / inclusive prefixes until it knows its own offset, and scatters.  Status words carry
-// a per-call tag, so the status array is never cleared.  flag = 1: aggregate, 2: inclusive prefix.
+// predecessors' published counts / inclusive prefixes -- 32 at a time, one per lane of warp 0 -- until it knows its
+// own offset, and scatters.  Status words carry a per-call tag, so the status array is never cleared.
+// flag = 1: aggregate, 2: inclusive prefix.
 //   src (optional)  : entry i stands for element src[i]: its flag is flags[src[i]] (compaction of a list by a flag array)
 //   map (optional)  : the output is map[element] instead of the element
 //   nDev (optional) : N is read from device memory (*nDev, <= N)
+constexpr int kLbGroups = 4;                                   // 16-flag groups per thread
+constexpr int kLbTile = kThreads * 16 * kLbGroups;             // 16384 flags per CTA
 __device__ __forceinline__ unsigned long long packStatus(unsigned tag, unsigned flag, unsigned value) {
     return ((unsigned long long)((tag << 2) | flag) << 32) | value;
 }
@@ -134,49 +137,82 @@ k_compact_lb(const u8 *__restrict__ flags, int64_t N, const int32_t *__restrict_
     if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
     __syncthreads();
     const unsigned tile = sTile;
-    const int64_t base = ((int64_t)tile * kThreads + threadIdx.x) * kFlagsPerThread;
-    unsigned bits = 0;
-    if (base < N) {
-        if (!src) {
-            const uint4 w = loadFlags16(flags, base, N, aligned);
-            const unsigned v[4] = {w.x, w.y, w.z, w.w};
+    // thread t owns groups t, t + 256, ... of the tile (coalesced 128-bit loads); output order = group order
+    unsigned bits[kLbGroups];
+    int c = 0;
 #pragma unroll
-            for (int k = 0; k < 16; k++) bits |= ((v[k >> 2] >> (8 * (k & 3))) & 1u) << k;
-        } else {
-            for (int k = 0; k < 16 && base + k < N; k++) bits |= (flags[src[base + k]] ? 1u : 0u) << k;
+    for (int g = 0; g < kLbGroups; g++) {
+        const int64_t base = (int64_t)tile * kLbTile + ((int64_t)g * kThreads + threadIdx.x) * 16;
+        unsigned b = 0;
+        if (base < N) {
+            if (!src) {
+                const uint4 w = loadFlags16(flags, base, N, aligned);
+                const unsigned v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int k = 0; k < 16; k++) b |= ((v[k >> 2] >> (8 * (k & 3))) & 1u) << k;
+            } else {
+                for (int k = 0; k < 16 && base + k < N; k++) b |= (flags[src[base + k]] ? 1u : 0u) << k;
+            }
         }
+        bits[g] = b;
+        c += __popc(b);
     }
-    const int c = __popc(bits);
-    int tileTotal;
-    int pos = blockExclusiveScan(c, smem, &tileTotal);
-    if (threadIdx.x == 0) {
+    // per-group block scans: group g of all threads precedes group g + 1
+    int pos[kLbGroups];
+    int tileTotal = 0;
+#pragma unroll
+    for (int g = 0; g < kLbGroups; g++) {
+        int gt;
+        pos[g] = blockExclusiveScan(__popc(bits[g]), smem, &gt) + tileTotal;
+        tileTotal += gt;
+    }
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
         int prefix = 0;
         if (tile == 0) {
-            atomicExch(&status[0], packStatus(tag, 2u, (unsigned)tileTotal));
+            if (lane == 0) atomicExch(&status[0], packStatus(tag, 2u, (unsigned)tileTotal));
         } else {
-            atomicExch(&status[tile], packStatus(tag, 1u, (unsigned)tileTotal));
-            for (int j = (int)tile - 1; j >= 0; j--) {
-                unsigned long long sv;
-                do { sv = *reinterpret_cast<volatile unsigned long long *>(&status[j]); } while ((unsigned)(sv >> 34) != tag || ((sv >> 32) & 3u) == 0u);
-                prefix += (int)(unsigned)sv;
-                if (((sv >> 32) & 3u) == 2u) break;
+            if (lane == 0) atomicExch(&status[tile], packStatus(tag, 1u, (unsigned)tileTotal));
+            int j = (int)tile - 1 - lane;
+            while (true) {
+                unsigned long long sv = packStatus(tag, 2u, 0u);             // before tile 0: an inclusive prefix of zero
+                if (j >= 0) {
+                    do { sv = *reinterpret_cast<volatile unsigned long long *>(&status[j]); } while ((unsigned)(sv >> 34) != tag || ((sv >> 32) & 3u) == 0u);
+                }
+                const unsigned inclMask = __ballot_sync(0xffffffffu, ((sv >> 32) & 3u) == 2u);
+                int v = (int)(unsigned)sv;
+                if (inclMask) {
+                    const int first = __ffs(inclMask) - 1;                   // nearest predecessor that knows its inclusive prefix
+                    if (lane > first) v = 0;
+                }
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                prefix += v;
+                if (inclMask) break;
+                j -= 32;
             }
-            atomicExch(&status[tile], packStatus(tag, 2u, (unsigned)(prefix + tileTotal)));
+            if (lane == 0) atomicExch(&status[tile], packStatus(tag, 2u, (unsigned)(prefix + tileTotal)));
         }
-        sPrefix = prefix;
-        if (tile == tiles - 1) {                       // every ticket has been drawn: reset for the next call
-            *ticket = 0;
-            if (total) *total = prefix + tileTotal;
+        if (lane == 0) {
+            sPrefix = prefix;
+            if (tile == tiles - 1) {                   // every ticket has been drawn: reset for the next call
+                *ticket = 0;
+                if (total) *total = prefix + tileTotal;
+            }
         }
     }
     __syncthreads();
-    pos += sPrefix;
     if (out) {
-        while (bits) {
-            const int k = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int64_t i = src ? (int64_t)src[base + k] : base + k;
-            out[pos++] = map ? map[i] : (int32_t)i;
+#pragma unroll
+        for (int g = 0; g < kLbGroups; g++) {
+            const int64_t base = (int64_t)tile * kLbTile + ((int64_t)g * kThreads + threadIdx.x) * 16;
+            unsigned b = bits[g];
+            int p = pos[g] + sPrefix;
+            while (b) {
+                const int k = __ffs(b) - 1;
+                b &= b - 1;
+                const int64_t i = src ? (int64_t)src[base + k] : base + k;
+                out[p++] = map ? map[i] : (int32_t)i;
+            }
         }
     }
 }
@@ -184,7 +220,7 @@ k_compact_lb(const u8 *__restrict__ flags, int64_t N, const int32_t *__restrict_
 // flags[N] (bytes, any non-zero value counts) -> ascending indices in `out`; the count is stored to *totalDev (device).
 static int compactFlagsEx(amr_ctx *ctx, const u8 *flags, int64_t N, const int32_t *nDev, const label *src, const label *map,
                           int32_t *out, int32_t **totalDev, int totalSlot, const int *gate) {
-    int64_t tiles = (N + kTile - 1) / kTile;
+    int64_t tiles = (N + kLbTile - 1) / kLbTile;
     if (tiles < 1) tiles = 1;
     if (tiles + 2 > ctx->tileCap) FAIL(AMR_ERR_STATE, "compaction tile buffer too small");
     const bool aligned = (((uintptr_t)flags) & 15) == 0;

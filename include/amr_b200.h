@@ -151,7 +151,8 @@ enum {
    patches), each list in the order that pairs it with the neighbour's list: processorPolyPatch::meshPoints() against
    neighbPoints().  Needed only for point-based syncs across ranks (syncTools::syncPointList in
    fvMeshRefiner::extendMarkedCellsAcrossPoints, fvMeshRefiner.C:952-958: the polyRefiner's unrefinement buffer
-   layers). */
+   layers; the pointLevel check of hexRef.C:3027-3057).  With a communicator the call is COLLECTIVE (the ranks agree
+   on the transport of the point swaps): every rank calls it, with empty lists when it has no processor patch. */
 int amr_mesh_set_patch_points(amr_ctx *ctx, const int32_t *patchPointOff, const int32_t *patchPoints);
 
 int amr_set_option(amr_ctx *ctx, int option, int64_t value);
@@ -268,6 +269,12 @@ int amr_max_cell_field(amr_ctx *ctx, const double *vFld, double *pFld);
    nBad (host) = number of violating faces; returns AMR_ERR_INVARIANT when > 0. */
 int amr_check_levels(amr_ctx *ctx, const int32_t *cellLevel, int64_t *nBad);
 
+/* "Check pointLevel is synchronized" of hexRef::checkRefinementLevels (hexRef.C:3027-3057): every rank that shares a
+   processor-patch point must hold the same pointLevel.  pointLevel NULL = resident.  Needs amr_mesh_set_patch_points
+   on decomposed meshes; collective.  nBad (host) = points of this rank that disagree with a neighbour; returns
+   AMR_ERR_INVARIANT when any rank found one. */
+int amr_check_point_levels(amr_ctx *ctx, const int32_t *pointLevel, int64_t *nBad);
+
 /* ---- stage 4: field mapping ------------------------------------------------------------- */
 
 /* fvMesh::mapFields, reached from adaptiveFvMesh.C:293,346-348: direct addressing through
@@ -330,6 +337,14 @@ int amr_remap_protected_cells(amr_ctx *ctx, int64_t nOld, int64_t nNew, const in
    "should not have removed faces when refining".  nCorrected (nullable) = number of rewritten faces. */
 int amr_correct_fluxes(amr_ctx *ctx, int64_t nOldFaces, const int32_t *faceMap, const int32_t *reverseFaceMap, const double *U,
                        const double *UBoundary, const double *nbrU, double *phi, int64_t *nCorrected);
+
+/* Old-time volumes through a topology change: the V0 / V00 part of fvMesh::updateMesh (OpenFOAM core, reached from
+   adaptiveFvMesh.C:293): newV[i] = oldV[cellMap[i]] (0 where cellMap == -1), then every merged-away old cell
+   (reverseCellMap < -1) adds its old volume to its master -(reverseCellMap)-2, in ascending old label like the
+   reference's loop (bit-identical sums).  nVolumes fields (V0, V00) share the map.  Restated from upstream
+   fvMesh.C: parity unpinned.  nMerged (nullable) = number of merged-away cells. */
+int amr_map_old_volumes(amr_ctx *ctx, int64_t nOld, int64_t nNew, const int32_t *cellMap, const int32_t *reverseCellMap,
+                        int nVolumes, const double *const *oldV, double *const *newV, int64_t *nMerged);
 
 /* gradient schemes of amr_estimate_gradient */
 enum { AMR_GRAD_GAUSS_LINEAR = 0, AMR_GRAD_LEAST_SQUARES = 1 };

@@ -1349,6 +1349,25 @@ OR_API void or_map_field_world(const or_world *w, const int64_t *nNew, const lab
    new[m] = sum V_old[c] old[c] / sum V_old[c] over the master and every old cell merged into it
    (reverseCellMap[c] == -(m)-2); accumulation in ascending old-cell order.  No in-tree reference
    (parity unpinned); refinement children still take the parent value. */
+/*
+ * Old-time volumes V0 / V00 through a topology change: the part of fvMesh::updateMesh (OpenFOAM core, reached from
+ * adaptiveFvMesh.C:293; restated from upstream fvMesh.C "Map the old volume. Just map to new cell labels." /
+ * "Inject volume of merged cells" -- not in the reference tree, parity unpinned):
+ *   V0new[i] = cellMap[i] > -1 ? V0old[cellMap[i]] : 0
+ *   for oldCelli ascending: index = reverseCellMap[oldCelli]; if (index < -1) V0new[-index-2] += V0old[oldCelli]
+ * so the master of a merge carries the volume of all the cells merged into it.
+ */
+OR_API int64_t or_map_old_volumes(int64_t nOld, int64_t nNew, const label *cellMap, const label *reverseCellMap,
+                                  const scalar *V0old, scalar *V0new) {
+    for (int64_t i = 0; i < nNew; i++) V0new[i] = cellMap[i] > -1 ? V0old[cellMap[i]] : 0.0;
+    int64_t nMerged = 0;
+    for (int64_t oldCelli = 0; oldCelli < nOld; oldCelli++) {
+        label index = reverseCellMap[oldCelli];
+        if (index < -1) { V0new[-index - 2] += V0old[oldCelli]; nMerged++; }
+    }
+    return nMerged;
+}
+
 OR_API void or_map_field_conservative(int64_t nOld, int64_t nNew, const label *cellMap,
                                       const label *reverseCellMap, const scalar *volOld, int nComp,
                                       const scalar *oldF, scalar *newF) {

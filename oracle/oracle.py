@@ -86,6 +86,8 @@ def lib():
         L.or_map_field.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.or_map_field_conservative.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                 C.c_void_p, C.c_void_p]
+        L.or_map_old_volumes.restype = C.c_int64
+        L.or_map_old_volumes.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 4
         L.or_update_levels.argtypes = [C.c_int64] + [C.c_void_p] * 5
         L.or_reorder_labels.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.or_map_labels.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -442,6 +444,16 @@ def map_field_conservative(cell_map, reverse_map, vol_old, old, ncomp=1):
     lib().or_map_field_conservative(len(reverse_map), len(cell_map), cell_map.ctypes.data, reverse_map.ctypes.data,
                                     vol_old.ctypes.data, ncomp, old.ctypes.data, new.ctypes.data)
     return new
+
+
+def map_old_volumes(cell_map, reverse_map, v0_old):
+    """V0 / V00 through a topology change (fvMesh::updateMesh): direct map + volume of the merged cells injected"""
+    cell_map, reverse_map = _i32(cell_map), _i32(reverse_map)
+    v0_old = np.ascontiguousarray(v0_old, dtype=np.float64)
+    new = np.empty(len(cell_map), dtype=np.float64)
+    n = lib().or_map_old_volumes(len(reverse_map), len(cell_map), cell_map.ctypes.data, reverse_map.ctypes.data, v0_old.ctypes.data,
+                                 new.ctypes.data)
+    return new, int(n)
 
 
 def update_levels(cell_map, old_level, refined_old=None, unrefined_old=None):

@@ -282,3 +282,34 @@ def ls_vectors(m, cc_nbr=None):
     ls_n = (-w[:f] * s)[:, None] * np.einsum("fij,fj->fi", inv[nei], d)
     ls_p[f:] = fac[:, None] * np.einsum("fij,fj->fi", inv[own[f:]], pd)
     return np.ascontiguousarray(ls_p), np.ascontiguousarray(ls_n)
+
+
+def unrefinement_maps(n0=8, maxlev=2):
+    """a real merge of the host topology engine: (mesh before, cellMap, reverseCellMap) with several merged groups"""
+    from oracle import oracle as O
+    oc = graded_octree(n0, maxlev)
+    m = oc.build()
+    w = O.World([m])
+    up, _, _ = w.hex_select_unrefine([np.full(m.n, -1.0)], [np.zeros(m.n, np.uint8)], 0)
+    pts = np.flatnonzero(up[0]).astype(np.int32)
+    assert len(pts) > 3
+    cm, rev = oc.unrefine(m, pts)
+    return m, cm, rev
+
+
+def synthetic_merge_maps(n_old=5000, seed=3, max_group=12):
+    """general merges (groups of 2..max_group old cells with arbitrary labels into their lowest member)"""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(n_old)
+    master_of = np.arange(n_old)
+    i = 0
+    while i < n_old // 2:
+        g = int(rng.integers(2, max_group + 1))
+        grp = perm[i:i + g]
+        master_of[grp] = grp.min()
+        i += g
+    keep = master_of == np.arange(n_old)
+    cm = np.flatnonzero(keep).astype(np.int32)
+    new_id = np.cumsum(keep) - 1
+    rev = np.where(keep, new_id, -new_id[master_of] - 2).astype(np.int32)
+    return cm, rev

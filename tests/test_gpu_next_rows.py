@@ -245,3 +245,25 @@ def test_load_balance_inputs(ctx, O):
     from blastamr_b200.capi import AmrError
     with pytest.raises(AmrError, match="outside"):
         ctx.proc_load(np.full(m.n, 9, np.int32), 4)
+
+
+def test_old_volumes_through_unrefinement(ctx, O):
+    """amr_map_old_volumes (V0 / V00 of fvMesh::updateMesh) bit for bit against the oracle: a real hexRef3D merge (7 cells
+    into the 8th), general merges with groups of up to 12 cells (slot blocks retried with the real maximum), a pure
+    refinement map (nothing merged), two volume fields in one call"""
+    m, cm, rev = cases.unrefinement_maps()
+    v0 = m.vol * (1.0 + 0.1 * np.sin(np.arange(m.n)))
+    v00 = m.vol * (1.0 + 0.2 * np.cos(np.arange(m.n)))
+    (g0, g00), nm = ctx.map_old_volumes(cm, rev, [v0, v00])
+    r0, nr = O.map_old_volumes(cm, rev, v0)
+    r00, _ = O.map_old_volumes(cm, rev, v00)
+    assert nm == nr > 0 and np.array_equal(g0, r0) and np.array_equal(g00, r00)
+    assert abs(g0.sum() - v0.sum()) < 1e-12 * v0.sum()
+    cm2, rev2 = cases.synthetic_merge_maps()
+    v = np.random.default_rng(0).random(len(rev2))
+    (g,), nm2 = ctx.map_old_volumes(cm2, rev2, [v])
+    r, nr2 = O.map_old_volumes(cm2, rev2, v)
+    assert nm2 == nr2 and np.array_equal(g, r)
+    cm3 = np.concatenate([np.arange(100), np.repeat(np.arange(10), 7)]).astype(np.int32)
+    (g3,), nm3 = ctx.map_old_volumes(cm3, np.arange(100, dtype=np.int32), [v[:100].copy()])
+    assert nm3 == 0 and np.array_equal(g3, v[:100][cm3])

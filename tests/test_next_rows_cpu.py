@@ -163,3 +163,22 @@ def test_poly3D_gpu_driver_on_the_oracle():
     """tests/test_zz_gpu_reference_poly3d.py answered by the oracle: checks the test code itself"""
     import tests.test_zz_gpu_reference_poly3d as T
     T.test_poly3D_fixture(cases.OracleBackend(), O)
+
+
+def test_old_volumes_carry_the_merged_cells():
+    """V0 / V00 through an unrefinement (fvMesh::updateMesh: direct map + volume of the merged cells injected into the
+    master): total old volume is conserved, survivors keep theirs, a master holds the volume of its whole group"""
+    m, cm, rev = cases.unrefinement_maps()
+    v0 = m.vol * (1.0 + 0.1 * np.sin(np.arange(m.n)))
+    new, n_merged = O.map_old_volumes(cm, rev, v0)
+    assert n_merged == (rev < -1).sum() > 0 and n_merged % 7 == 0
+    assert abs(new.sum() - v0.sum()) < 1e-12 * v0.sum()
+    ref = v0[cm].copy()
+    np.add.at(ref, -rev[rev < -1] - 2, v0[rev < -1])
+    assert np.allclose(new, ref, rtol=1e-15, atol=0)
+    untouched = np.ones(len(cm), bool); untouched[-rev[rev < -1] - 2] = False
+    assert np.array_equal(new[untouched], v0[cm][untouched])
+    cm2, rev2 = cases.synthetic_merge_maps()
+    v = np.random.default_rng(0).random(len(rev2))
+    new2, _ = O.map_old_volumes(cm2, rev2, v)
+    assert abs(new2.sum() - v.sum()) < 1e-11
