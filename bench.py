@@ -656,22 +656,36 @@ def main():
     NEV = len(stage_names) + 1
     info = {}
 
+    # the C-ABI calls of one step, arguments converted once (what a host code in a time loop does)
+    import ctypes as C
+    thr_arr = np.asarray(THRS, dtype=np.float64)
+    no_ids = np.zeros(1, dtype=np.int32)
+    cnt_r, sw_r, cnt_u, sw_u = C.c_int64(0), C.c_int(0), C.c_int64(0), C.c_int(0)
+
+    def field_args(olds, news, ncs):
+        k = len(olds)
+        return ((C.c_int * k)(*ncs), (C.c_void_p * k)(*[a.data_ptr() for a in olds]), (C.c_void_p * k)(*[a.data_ptr() for a in news]))
+
+    fa, fa2 = field_args([x, fld3, err0], [new1, new3, err1], [1, 3, 1]), field_args([new1, new3, err1], [x2, u2, err2], [1, 3, 1])
+    call_E = ctx.prepare("amr_estimate", capi.EST["delta"], x, None, capi.SMALL, 0.0, 1, thr_arr, err0)
+    call_R = ctx.prepare("amr_select_refine", err0, capi.SQRT_SMALL, capi.GREAT, None, MAX_LEVEL, LAYERS_REF, no_ids, 0, capi.LABEL_MAX,
+                         capi.HEX3D, rc0, cells_dev, C.byref(cnt_r), C.byref(sw_r))
+    call_F = ctx1.prepare("amr_map_fields_and_marking", n, n1, cell_map, 3, fa[0], fa[1], fa[2], rev_map, rc0, None)
+    call_U = ctx1.prepare("amr_select_unrefine", err1, -capi.SQRT_SMALL, None, LAYERS_UNREF, no_ids, 0, capi.HEX3D, pts_dev,
+                          C.byref(cnt_u), C.byref(sw_u))
+    call_F2 = ctx1.prepare("amr_map_fields_and_marking", n1, n2, cell_map2, 3, fa2[0], fa2[1], fa2[2], None, None, None)
+
     def step(evs=None):
-        def mark(i):
-            if evs is not None:
-                evs[i].record()
-        mark(0)
-        ctx.estimate("delta", x, thresholds=THRS, out=err0)
-        mark(1)
-        nr, sw = ctx.select_refine(err0, MAX_LEVEL, LAYERS_REF, cells_out=cells_dev, refine_cell_out=rc0)
-        mark(2)
-        ctx1.map_fields_and_marking(cell_map, [x, fld3, err0], n, n1, [1, 3, 1], [new1, new3, err1], reverse_map=rev_map, refine_cell=rc0)
-        mark(3)
-        npts, sw2 = ctx1.select_unrefine(err1, LAYERS_UNREF, elems_out=pts_dev)
-        mark(4)
-        ctx1.map_fields(cell_map2, [new1, new3, err1], n1, n2, [1, 3, 1], [x2, u2, err2])
-        mark(5)
-        info.update(n_refine=nr, sweeps_refine=sw, n_unrefine=npts, sweeps_unrefine=sw2)
+        if evs is None:
+            call_E(); call_R(); call_F(); call_U(); call_F2()
+        else:
+            evs[0].record(); call_E()
+            evs[1].record(); call_R()
+            evs[2].record(); call_F()
+            evs[3].record(); call_U()
+            evs[4].record(); call_F2()
+            evs[5].record()
+        info.update(n_refine=cnt_r.value, sweeps_refine=sw_r.value, n_unrefine=cnt_u.value, sweeps_unrefine=sw_u.value)
 
     def barrier():
         if world > 1:

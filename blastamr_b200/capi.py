@@ -166,6 +166,22 @@ class Context:
     def comm_init(self, nranks: int, rank: int, uid: bytes):
         self._ck(self.L.amr_comm_init(self._h, nranks, rank, C.create_string_buffer(uid, 128)))
 
+    def prepare(self, name, *args):
+        """A call of C entry point `name` with its arguments converted once (arrays / tensors -> pointers): what a host
+        code does when it calls the C-ABI in a time loop.  Returns a function that makes the call and checks the
+        return code; the converted arguments (and the buffers behind them) stay referenced by it."""
+        fn = getattr(self.L, name)
+        conv = tuple(_ptr(a) if (a is None or isinstance(a, np.ndarray) or hasattr(a, "data_ptr")) else a for a in args)
+        keep = args
+        h, ck = self._h, self._ck
+
+        def call():
+            rc = fn(h, *conv)
+            if rc != AMR_OK:
+                ck(rc)
+        call.keep = keep
+        return call
+
     def synchronize(self):
         """wait for the context's stream; raises what stream-ordered calls could not report (peer timeout)"""
         self._ck(self.L.amr_synchronize(self._h))

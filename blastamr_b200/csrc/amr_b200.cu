@@ -72,6 +72,9 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
             int a = 0, b = 1;
             if (sscanf(pf, "%d/%d", &a, &b) >= 1 && a >= 0 && b > 0) { ctx->pushNum = a; ctx->pushDen = b; }
         }
+        const char *mf = getenv("AMR_B200_MAP");                 // tuning: fused (default) | fused40 | separate
+        if (mf && strcmp(mf, "fused40") == 0) ctx->mapForm = 1;
+        else if (mf && strcmp(mf, "separate") == 0) ctx->mapForm = 2;
         const char *pm = getenv("AMR_B200_PUSH_MIN_CELLS");      // below this mesh size the extra launches do not pay
         if (pm) ctx->pushMinCells = atoll(pm);
     }
@@ -420,6 +423,27 @@ static int haloSwapCells(amr_ctx *ctx, const void *cells, size_t elemBytes, void
     HaloToken tok;
     TRY(haloBegin(ctx, cells, elemBytes, recv, &tok, minus));
     return haloEnd(ctx, &tok);
+}
+// How the boundary fix-up kernel that follows haloBegin gets the ghost values (GhostLink, p2p.cuh): on the peer
+// transport the kernel does the receive side itself (no unpack launch) and, with fuseReduce, the all-reduce of the
+// sweep as well; otherwise the values are already in `recvArray` (NCCL, or supplied by the host).
+static GhostLink makeLink(amr_ctx *ctx, HaloToken *tok, const void *recvArray, bool fuseReduce) {
+    GhostLink G;
+    memset(&G, 0, sizeof(G));
+    G.seq = ctx->dSeq;
+    G.counter = (unsigned *)(ctx->dFlags + 7);
+    G.timeoutNs = ctx->peerTimeoutNs;
+    G.nranks = ctx->nranks; G.rank = ctx->rank;
+    if (tok && tok->pending) {
+        G.P = *(const HaloPlan *)ctx->haloPlan;
+        G.region = ctx->region;
+        tok->pending = false;
+    } else {
+        G.ghost = (const char *)recvArray;
+        G.region = ctx->region;
+    }
+    G.peer = (fuseReduce && ctx->comm && ctx->nranks > 1 && ctx->usePeer) ? ctx->peerDev : nullptr;
+    return G;
 }
 // the speculative (device-gated) loops need the peer transport; with NCCL the host-synchronised loops run
 static inline bool gatedSwapsOk(const amr_ctx *ctx) { return (!ctx->comm || ctx->nranks < 2) ? true : (ctx->usePeer && ctx->havePlan); }
@@ -969,9 +993,9 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
         } else if (scale) LAUNCH((k_estimate<K, true>), gridFor(n), kThreads, n, so, col, dx, cg, p0, p1, t, target); \
         else LAUNCH((k_estimate<K, false>), gridFor(n), kThreads, n, so, col, dx, cg, p0, p1, t, target);        \
         if (ctx->nCoupled > 0) {                                                                                 \
-            TRY(haloEnd(ctx, &halo));                                                                            \
-            LAUNCH((k_fix_estimate<K>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, \
-                   (const label *)(ctx->owner + ctx->f), dx, ghost, p0, p1, target);                             \
+            GhostLink G = makeLink(ctx, &halo, ghost, false);                                                    \
+            LAUNCH((k_fix_estimate_link<K>), gridFor(ctx->nCoupled), kThreads, G, ctx->nCoupled, (const label *)ctx->cplFace, \
+                   (const label *)(ctx->owner + ctx->f), dx, p0, p1, target);                                    \
             if (scale) LAUNCH(k_fix_normalize, gridFor(ctx->nCplCells), kThreads, ctx->nCplCells, (const label *)ctx->cplCell, t, target); \
         }                                                                                                        \
     } while (0)
@@ -1132,10 +1156,11 @@ static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *srcSeparate, int gen, in
         else LAUNCH(k_layer_pull, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, srcArr, separate, gen, cur, cnt);
         ctx->sitesTouched |= 1u << site;
     }
-    TRY(haloEnd(ctx, &halo));
-    if (ctx->nCoupled > 0)
-        LAUNCH(k_fix_layer, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
-               (const u8 *)ctx->ghost8, separate, gen, cur);
+    if (ctx->nCoupled > 0) {
+        GhostLink G = makeLink(ctx, &halo, ctx->ghost8, false);
+        LAUNCH(k_fix_layer_link, gridFor(ctx->nCoupled), kThreads, G, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
+               separate, gen, cur);
+    }
     return AMR_OK;
 }
 
@@ -1300,11 +1325,12 @@ static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int
         if (ctx->nCoupled > 0) TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo));     // lf as it is before the sweep, like the reference's neiLevel
         if (n) LAUNCH(k_refine_push0, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, lf, set,
                       ((((uintptr_t)set)) & 15) == 0, ctx->queue[1], qc + 1, cap);
-        TRY(haloEnd(ctx, &halo));
-        if (ctx->nCoupled > 0)
-            LAUNCH(k_fix_refine_queue, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set,
-                   ctx->queue[1], qc + 1, cap, (const int *)nullptr);
-        if (multi) TRY(allReduceWord(ctx, gq + 1, 4, qc + 1));
+        if (multi) {                  // coupled faces (hexRef.C:758-780) + reduce(nChanged): one launch on the peer transport
+            GhostLink G = makeLink(ctx, &halo, ctx->ghost8, true);
+            LAUNCH(k_fix_refine_queue_link, gridFor(std::max<int64_t>(ctx->nCoupled, 1)), kThreads, G, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, lf, set,
+                   ctx->queue[1], qc + 1, cap, gq + 1, (const int *)nullptr);
+            if (!G.peer) TRY(allReduceWord(ctx, gq + 1, 4, qc + 1));
+        }
     }
     int issued = 1;                       // queues [1, issued] have been produced
     int batch = speculate ? std::max(1, ctx->itersSeen[0] - 1) : 0;
@@ -1318,11 +1344,12 @@ static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int
             if (ctx->nCoupled > 0) TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo, nullptr, xgate));
             LAUNCH(k_refine_frontier, queueGrid(ctx), kThreads, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, lf, set,
                    (const label *)ctx->queue[j & 1], (const int *)(qc + j), ctx->queue[(j + 1) & 1], qc + j + 1, cap, gate);
-            TRY(haloEnd(ctx, &halo));
-            if (ctx->nCoupled > 0)
-                LAUNCH(k_fix_refine_queue, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set,
-                       ctx->queue[(j + 1) & 1], qc + j + 1, cap, xgate);
-            if (multi) TRY(allReduceWord(ctx, gq + j + 1, 4, qc + j + 1, xgate));
+            if (multi) {
+                GhostLink G = makeLink(ctx, &halo, ctx->ghost8, true);
+                LAUNCH(k_fix_refine_queue_link, gridFor(std::max<int64_t>(ctx->nCoupled, 1)), kThreads, G, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, lf, set,
+                       ctx->queue[(j + 1) & 1], qc + j + 1, cap, gq + j + 1, xgate);
+                if (!G.peer) TRY(allReduceWord(ctx, gq + j + 1, 4, qc + j + 1, xgate));
+            }
             issued++;
         }
         TRY(compactFlags(ctx, set, n, job.dList, &job.dTotal));          // speculative: valid if the loop has converged
@@ -1733,11 +1760,12 @@ static int unrefineClosureQueue(amr_ctx *ctx, const double *dErr, double unrefin
         if (ctx->nCoupled > 0) TRY(haloBegin(ctx, ctx->lvl8, 1, ctx->ghost8, &halo, uc));     // cellLevel - unrefineCell (hexRef3D.C:1843-1853)
         if (nSp) LAUNCH(k_unref_sweep0, qg, kThreads, (const label *)ctx->spList, (const int32_t *)nList, nSp, (const label *)ctx->spCells,
                         ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, spFlag, uc, ctx->queue[1], qc + 1, cap);
-        TRY(haloEnd(ctx, &halo));
-        if (ctx->nCoupled > 0)
-            LAUNCH(k_fix_unref_queue, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, nSp,
-                   (const label *)ctx->spCells, (const label *)ctx->cellSp, spFlag, uc, ctx->queue[1], qc + 1, cap, (const int *)nullptr);
-        if (multi) TRY(allReduceWord(ctx, gq + 1, 4, qc + 1));
+        if (multi) {                  // coupled faces (hexRef3D.C:1855-1889) + reduce(nChanged): one launch on the peer transport
+            GhostLink G = makeLink(ctx, &halo, ctx->ghost8, true);
+            LAUNCH(k_fix_unref_queue_link, gridFor(std::max<int64_t>(ctx->nCoupled, 1)), kThreads, G, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, nSp,
+                   (const label *)ctx->spCells, (const label *)ctx->cellSp, spFlag, uc, ctx->queue[1], qc + 1, cap, gq + 1, (const int *)nullptr);
+            if (!G.peer) TRY(allReduceWord(ctx, gq + 1, 4, qc + 1));
+        }
     }
     int issued = 1;
     int batch = speculate ? std::max(1, ctx->itersSeen[1] - 1) : 0;
@@ -1751,11 +1779,12 @@ static int unrefineClosureQueue(amr_ctx *ctx, const double *dErr, double unrefin
             if (ctx->nCoupled > 0) TRY(haloBegin(ctx, ctx->lvl8, 1, ctx->ghost8, &halo, uc, xgate));
             LAUNCH(k_unref_frontier, qg, kThreads, (const label *)ctx->queue[j & 1], (const int *)(qc + j), nSp, (const label *)ctx->spCells,
                    (const label *)ctx->cellSp, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, spFlag, uc, ctx->queue[(j + 1) & 1], qc + j + 1, cap, gate);
-            TRY(haloEnd(ctx, &halo));
-            if (ctx->nCoupled > 0)
-                LAUNCH(k_fix_unref_queue, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, nSp,
-                       (const label *)ctx->spCells, (const label *)ctx->cellSp, spFlag, uc, ctx->queue[(j + 1) & 1], qc + j + 1, cap, xgate);
-            if (multi) TRY(allReduceWord(ctx, gq + j + 1, 4, qc + j + 1, xgate));
+            if (multi) {
+                GhostLink G = makeLink(ctx, &halo, ctx->ghost8, true);
+                LAUNCH(k_fix_unref_queue_link, gridFor(std::max<int64_t>(ctx->nCoupled, 1)), kThreads, G, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, nSp,
+                       (const label *)ctx->spCells, (const label *)ctx->cellSp, spFlag, uc, ctx->queue[(j + 1) & 1], qc + j + 1, cap, gq + j + 1, xgate);
+                if (!G.peer) TRY(allReduceWord(ctx, gq + j + 1, 4, qc + j + 1, xgate));
+            }
             issued++;
         }
         // ascending point list of the surviving candidates (speculative: valid if the loop has converged)
@@ -2113,6 +2142,11 @@ static int launchMapField(amr_ctx *ctx, int64_t nNew, int nComp, const int32_t *
 static int launchMapFused(amr_ctx *ctx, int64_t nNew, const int32_t *dMap, int nFields, const int *nComp, const double *const *dOld,
                           double *const *dNew, const int32_t *dRev, const u8 *dOldFlag, u8 *dNewFlag) {
     if (nNew <= 0) return AMR_OK;
+    if (ctx->mapForm == 2) {          // one launch per field (re-reads cellMap): AMR_B200_MAP=separate
+        for (int i = 0; i < nFields; i++) TRY(launchMapField(ctx, nNew, nComp[i], dMap, dOld[i], dNew[i]));
+        if (dNewFlag) LAUNCH(k_remap_refine_cell, gridFor(nNew, kThreads * 4), kThreads, nNew, dMap, dRev, dOldFlag, dNewFlag);
+        return AMR_OK;
+    }
     const int64_t chunks = (nNew + kMapChunk - 1) / kMapChunk;
     int done = 0;
     bool flagsDone = dNewFlag == nullptr;
@@ -2127,8 +2161,12 @@ static int launchMapFused(amr_ctx *ctx, int64_t nNew, const int32_t *dMap, int n
         const bool withFlags = !flagsDone;
         const int nStreams = F.nFields + (withFlags ? 1 : 0);
         if (chunks * nStreams > 0x7fffffff) FAIL(AMR_ERR_ARG, "amr_map_fields: too many cells for one launch");
-        LAUNCH(k_map_fields_fused, (unsigned)(chunks * nStreams), kThreads, nNew, dMap, F, nStreams, withFlags ? dRev : (const int32_t *)nullptr,
-               withFlags ? dOldFlag : (const u8 *)nullptr, withFlags ? dNewFlag : (u8 *)nullptr);
+        if (ctx->mapForm == 1)
+            LAUNCH((k_map_fields_fused<6>), (unsigned)(chunks * nStreams), kThreads, nNew, dMap, F, nStreams, withFlags ? dRev : (const int32_t *)nullptr,
+                   withFlags ? dOldFlag : (const u8 *)nullptr, withFlags ? dNewFlag : (u8 *)nullptr);
+        else
+            LAUNCH((k_map_fields_fused<1>), (unsigned)(chunks * nStreams), kThreads, nNew, dMap, F, nStreams, withFlags ? dRev : (const int32_t *)nullptr,
+                   withFlags ? dOldFlag : (const u8 *)nullptr, withFlags ? dNewFlag : (u8 *)nullptr);
         flagsDone = true;
     }
     return AMR_OK;

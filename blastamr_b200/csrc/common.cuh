@@ -106,6 +106,7 @@ struct amr_ctx {
     Sell cf;                   // cell -> faces (2*face + role), ascending
     double *grad = nullptr;    // [3n]
     double *xbf = nullptr;     // [b] boundaryField of x
+    int mapForm = 0;                // amr_map_fields on device buffers: 0 fused, 1 fused with 40 registers, 2 one launch per field
     int64_t pushMinCells = 1 << 16;
     int balancedLocal = -1;         // internal faces of the mesh satisfy |dLevel| <= 1 (-1: not checked yet)
     int balancedGlobal = -1;        // ... and the coupled faces, on every rank

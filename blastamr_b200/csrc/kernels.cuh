@@ -9,6 +9,7 @@
 // to the reference's face loops.
 #pragma once
 #include "common.cuh"
+#include "p2p.cuh"
 
 constexpr int kChunk = 8;   // SELL columns fetched per batch (memory-level parallelism per thread)
 
@@ -907,19 +908,23 @@ __global__ void k_fix_check_levels(int64_t nC, const label *__restrict__ cplFace
 // coupled face hold the RAW internal maximum (the main kernel does not normalise them); max is applied with an
 // integer atomicMax on the bit pattern (values are >= 0, so the order of doubles and of their bits agree: exact
 // and order-independent).  k_fix_normalize then normalises each such cell once.
+// fused with the receive side of the swap (the ghost values are read in place from the peer-written parity buffer)
 template <int KIND>
-__global__ void k_fix_estimate(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
-                               const double *__restrict__ x, const double *__restrict__ ghost, double p0, double p1,
-                               double *err) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nC) return;
-    const label bf = cplFace[i];
-    const label o = bOwner[bf];
-    const bool useOffset = fabs(p1) > kSMALL;
-    const double fp = fieldXform<KIND>(x[o], p1, useOffset), fn = fieldXform<KIND>(ghost[bf], p1, useOffset);
-    double eT = fabs(fp - fn);                                           // delta.C:126 (no clamp)
-    if (KIND == 1) eT = eT / fmaxFoam(fminFoam(fp, fn), p0);             // scaledDelta.C:129-131
-    if (eT > 0.0) atomicMax(reinterpret_cast<unsigned long long *>(err + o), (unsigned long long)__double_as_longlong(eT));
+__global__ void __launch_bounds__(kThreads)
+k_fix_estimate_link(const __grid_constant__ GhostLink G, int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                    const double *__restrict__ x, double p0, double p1, double *err) {
+    const double *ghost = reinterpret_cast<const double *>(ghostAcquire(G));
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ghost && i < nC) {
+        const label bf = cplFace[i];
+        const label o = bOwner[bf];
+        const bool useOffset = fabs(p1) > kSMALL;
+        const double fp = fieldXform<KIND>(x[o], p1, useOffset), fn = fieldXform<KIND>(ghost[bf], p1, useOffset);
+        double eT = fabs(fp - fn);                                           // delta.C:126 (no clamp)
+        if (KIND == 1) eT = eT / fmaxFoam(fminFoam(fp, fn), p0);             // scaledDelta.C:129-131
+        if (eT > 0.0) atomicMax(reinterpret_cast<unsigned long long *>(err + o), (unsigned long long)__double_as_longlong(eT));
+    }
+    ghostRelease(G);
 }
 __global__ void k_fix_normalize(int64_t nCells, const label *__restrict__ cplCell, Thresholds thr, double *err) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -953,7 +958,7 @@ k_remap_refine_cell(int64_t nNew, const label *__restrict__ cellMap, const label
         u8 out;
         if (o[t] < 0) out = 1;
         else if ((int64_t)r[t] != c) out = 1;
-        else out = v[t];
+        else out = v[t] ? 1 : 0;
         newFlag[c] = out;
     }
 }

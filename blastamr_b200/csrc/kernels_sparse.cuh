@@ -21,6 +21,7 @@
 #pragma once
 #include "kernels.cuh"
 #include "kernels_pipe.cuh"
+#include "p2p.cuh"
 
 // ---- byte flags inside 32-bit words: exact "I was first" detection without byte atomics
 __device__ __forceinline__ bool setByteOnce(u8 *flags, int64_t i) {          // 0 -> 1; true if this thread did it
@@ -172,16 +173,21 @@ k_layer_pull(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__r
     }
     if (nSrc) blockAddCount(mineCnt, nSrc);
 }
-// syncFaceList(orEqOp) part of a layer: the source value of the cell on the other side of a processor face
-__global__ void k_fix_layer(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
-                            const u8 *__restrict__ ghostSrc, bool separate, int gen, u8 *cur) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nC) return;
-    const label bf = cplFace[i];
-    if (isSource(ghostSrc[bf], gen, separate)) {
-        const label o = bOwner[bf];
-        if (cur[o] == 0) cur[o] = (u8)(gen + 1);
+// syncFaceList(orEqOp) part of a layer: the source value of the cell on the other side of a processor face, fused with
+// the receive side of the swap (GhostLink, p2p.cuh): no unpack launch
+__global__ void __launch_bounds__(kThreads)
+k_fix_layer_link(const __grid_constant__ GhostLink G, int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                 bool separate, int gen, u8 *cur) {
+    const u8 *ghostSrc = reinterpret_cast<const u8 *>(ghostAcquire(G));
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ghostSrc && i < nC) {
+        const label bf = cplFace[i];
+        if (isSource(ghostSrc[bf], gen, separate)) {
+            const label o = bOwner[bf];
+            if (cur[o] == 0) cur[o] = (u8)(gen + 1);
+        }
     }
+    ghostRelease(G);
 }
 // marking -> boolList (0/1) for the caller; also the import direction
 __global__ void __launch_bounds__(kThreads)
@@ -244,22 +250,28 @@ k_refine_frontier(const int32_t *__restrict__ sliceOff, const int32_t *__restric
     for (int i = blockIdx.x * kThreads + threadIdx.x; i < cnt; i += gridDim.x * kThreads)
         refinePushRow(qIn[i], sliceOff, col, lvl8, lf, set, qOut, qOutCount, qCap);
 }
-// coupled faces of an iteration (hexRef.C:758-780, maxSet = true): ghostLf = level + flag of the cell across the face
-__global__ void k_fix_refine_queue(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
-                                   const u8 *__restrict__ lvl8, const u8 *__restrict__ ghostLf, u8 *lf, u8 *set, label *qOut,
-                                   int *qOutCount, int64_t qCap, const int *__restrict__ gate) {
+// coupled faces of an iteration (hexRef.C:758-780, maxSet = true): ghostLf = level + flag of the cell across the face;
+// fused with the receive side of the swap and with the all-reduce of the queue size (sum over ranks of
+// *qOutCount -> *gqOut): one launch instead of unpack + fix-up + reduction
+__global__ void __launch_bounds__(kThreads)
+k_fix_refine_queue_link(const __grid_constant__ GhostLink G, int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                        const u8 *__restrict__ lvl8, u8 *lf, u8 *set, label *qOut, int *qOutCount, int64_t qCap, int *gqOut,
+                        const int *__restrict__ gate) {
     if (gate && *gate == 0) return;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nC) return;
-    const label bf = cplFace[i];
-    const label o = bOwner[bf];
-    if ((int)ghostLf[bf] > (int)lvl8[o] + 1 && !set[o]) {           // an unmarked owner two levels below the far side
-        if (setByteOnce(set, o)) {
-            lf[o] = (u8)(lvl8[o] + 1);
-            const int pos = atomicAdd(qOutCount, 1);
-            if (pos < qCap) qOut[pos] = o;
+    const u8 *ghostLf = reinterpret_cast<const u8 *>(ghostAcquire(G));
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ghostLf && i < nC) {
+        const label bf = cplFace[i];
+        const label o = bOwner[bf];
+        if ((int)ghostLf[bf] > (int)lvl8[o] + 1 && !set[o]) {
+            if (setByteOnce(set, o)) {
+                lf[o] = (u8)(lvl8[o] + 1);
+                const int pos = atomicAdd(qOutCount, 1);
+                if (pos < qCap) qOut[pos] = o;
+            }
         }
     }
+    if (ghostRelease(G) && G.peer) ctaAllReduceSum(G, qOutCount, gqOut);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -381,20 +393,24 @@ k_unref_frontier(const label *__restrict__ qIn, const int *__restrict__ qInCount
         }
     }
 }
-// coupled faces of an iteration (hexRef3D.C:1855-1889): ghost = lvl - uc of the cell across the face
-__global__ void k_fix_unref_queue(int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
-                                  const u8 *__restrict__ lvl8, const u8 *__restrict__ ghostLfm, int64_t nSp,
-                                  const label *__restrict__ spCells, const label *__restrict__ cellSp, u8 *spFlag, u8 *uc, label *qOut,
-                                  int *qOutCount, int64_t qCap, const int *__restrict__ gate) {
+// coupled faces of an iteration (hexRef3D.C:1855-1889): ghost = lvl - uc of the cell across the face; fused with the
+// receive side of the swap and the all-reduce of the queue size
+__global__ void __launch_bounds__(kThreads)
+k_fix_unref_queue_link(const __grid_constant__ GhostLink G, int64_t nC, const label *__restrict__ cplFace, const label *__restrict__ bOwner,
+                       const u8 *__restrict__ lvl8, int64_t nSp, const label *__restrict__ spCells, const label *__restrict__ cellSp,
+                       u8 *spFlag, u8 *uc, label *qOut, int *qOutCount, int64_t qCap, int *gqOut, const int *__restrict__ gate) {
     if (gate && *gate == 0) return;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nC) return;
-    const label bf = cplFace[i];
-    const label o = bOwner[bf];
-    if (uc[o] && ((int)lvl8[o] - 1) < (int)ghostLfm[bf] - 1) {
-        const label sp = cellSp[o];
-        if (sp >= 0) knockPoint(sp, nSp, spCells, spFlag, uc, qOut, qOutCount, qCap);
+    const u8 *ghostLfm = reinterpret_cast<const u8 *>(ghostAcquire(G));
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ghostLfm && i < nC) {
+        const label bf = cplFace[i];
+        const label o = bOwner[bf];
+        if (uc[o] && ((int)lvl8[o] - 1) < (int)ghostLfm[bf] - 1) {
+            const label sp = cellSp[o];
+            if (sp >= 0) knockPoint(sp, nSp, spCells, spFlag, uc, qOut, qOutCount, qCap);
+        }
     }
+    if (ghostRelease(G) && G.peer) ctaAllReduceSum(G, qOutCount, gqOut);
 }
 // "problem" of hexRef3D.C:1808-1833: an UNMARKED cell more than one level below the final level of a face neighbour.
 // Impossible on a 2:1-balanced mesh; evaluated on the final state when the mesh was found unbalanced.
@@ -491,7 +507,8 @@ __device__ __noinline__ void mapChunkFieldN(const label *__restrict__ cellMap, i
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 k_map_fields_fused(int64_t nNew, const label *__restrict__ cellMap, const __grid_constant__ MapFieldSet F, int nStreams,
                    const label *__restrict__ reverseCellMap, const u8 *__restrict__ oldFlag, u8 *__restrict__ newFlag) {
     const int64_t chunk = blockIdx.x / nStreams;

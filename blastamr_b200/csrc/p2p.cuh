@@ -194,3 +194,82 @@ __global__ void k_red_all(char *const *__restrict__ peer, char *mine, int nranks
         seq[1] = epoch;
     }
 }
+
+// ---- boundary fix-up kernels fused with the receive side of a swap (and with the reduction that follows it) ----------
+// The neighbour stores the value of my boundary face bf at offset bf of my parity buffer -- the parity buffer IS the
+// ghost array in boundary-face layout -- so a fix-up kernel needs no unpack launch: it waits for the arrival words
+// itself (thread 0 of every CTA), reads the ghost values in place, and its last CTA stores the exchange number back
+// and, where the caller wants it, runs the one-word all-reduce of the sweep (queue size) right there.
+struct GhostLink {
+    const char *ghost;            // transport already delivered the values (NCCL / host-provided): boundary-face layout; else nullptr
+    HaloPlan P;                   // peer transport: the patches to wait for
+    char *region;                 // my region
+    char *const *peer;            // all regions (fused reduction), nullptr = no fused reduction
+    unsigned *seq;
+    unsigned *counter;
+    unsigned long long timeoutNs;
+    int nranks, rank;
+};
+// returns the ghost array, or nullptr after a timeout (the caller then skips its work but still calls ghostRelease)
+__device__ __forceinline__ const char *ghostAcquire(const GhostLink &G) {
+    if (G.ghost) return G.ghost;
+    __shared__ int ok;
+    const unsigned epoch = G.seq[0] + 1u;
+    const int parity = (int)(epoch & 1u);
+    if (threadIdx.x == 0) {
+        P2PRegionHeader *h = reinterpret_cast<P2PRegionHeader *>(G.region);
+        int good = h->error == 0;
+        const unsigned long long t0 = globalTimerNs();
+        for (int q = 0; q < G.P.nPatch && good; q++) {
+            unsigned spins = 0;
+            while ((int)(ldAcquireSys(&h->arrive[parity][G.P.nbr[q]]) - epoch) < 0) {
+                if ((++spins & 1023u) == 0 && globalTimerNs() - t0 > G.timeoutNs) { good = 0; h->error = 1; break; }
+            }
+        }
+        ok = good;
+    }
+    __syncthreads();
+    return ok ? G.region + sizeof(P2PRegionHeader) + (size_t)parity * kHaloCap : nullptr;
+}
+// end of a fused fix-up kernel: true in the last CTA to finish (all CTAs' writes are visible to it)
+__device__ __forceinline__ bool ghostRelease(const GhostLink &G) {
+    __shared__ int last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(G.counter, 1u) == gridDim.x - 1);
+        if (last) { *G.counter = 0; if (!G.ghost) G.seq[0] = G.seq[0] + 1u; }
+    }
+    __syncthreads();
+    return last != 0;
+}
+// all-reduce (sum, int32) of *src into *dst by ONE CTA of at least nranks threads (the last CTA of a fix-up kernel)
+__device__ __forceinline__ void ctaAllReduceSum(const GhostLink &G, const int *src, int *dst) {
+    __shared__ int vals[kMaxRanks];
+    __shared__ int bad;
+    const unsigned epoch = G.seq[1] + 1u;
+    const int parity = (int)(epoch & 1u);
+    const int r = threadIdx.x;
+    if (r == 0) bad = 0;
+    __syncthreads();
+    if (r < G.nranks) {
+        P2PRegionHeader *h = reinterpret_cast<P2PRegionHeader *>(G.peer[r]);
+        h->red[parity][G.rank] = (unsigned long long)(unsigned)(*reinterpret_cast<const volatile int *>(src));
+        __threadfence_system();
+        stReleaseSys(&h->redEpoch[parity][G.rank], epoch);
+        P2PRegionHeader *me = reinterpret_cast<P2PRegionHeader *>(G.region);
+        const unsigned long long t0 = globalTimerNs();
+        unsigned spins = 0;
+        while ((int)(ldAcquireSys(&me->redEpoch[parity][r]) - epoch) < 0) {
+            if ((++spins & 1023u) == 0 && globalTimerNs() - t0 > G.timeoutNs) { bad = 1; me->error = 1; break; }
+        }
+        vals[r] = (int)(unsigned)*reinterpret_cast<volatile unsigned long long *>(&me->red[parity][r]);
+    }
+    __syncthreads();
+    if (r == 0) {
+        int acc = 0;
+        if (!bad) for (int k = 0; k < G.nranks; k++) acc += vals[k];
+        *dst = acc;                                       // a timed-out exchange ends a speculative loop; the host reports it
+        G.seq[1] = epoch;
+    }
+}

@@ -150,6 +150,17 @@ k_compact_lb(const u8 *__restrict__ flags, int64_t N, const int32_t *__restrict_
                 const unsigned v[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                 for (int k = 0; k < 16; k++) b |= ((v[k >> 2] >> (8 * (k & 3))) & 1u) << k;
+            } else if (base + 16 <= N) {
+                int4 s4[4];                                    // 16 elements: 4 vector loads, then 16 independent flag gathers
+#pragma unroll
+                for (int k = 0; k < 4; k++) s4[k] = reinterpret_cast<const int4 *>(src + base)[k];
+                const int e[16] = {s4[0].x, s4[0].y, s4[0].z, s4[0].w, s4[1].x, s4[1].y, s4[1].z, s4[1].w,
+                                   s4[2].x, s4[2].y, s4[2].z, s4[2].w, s4[3].x, s4[3].y, s4[3].z, s4[3].w};
+                u8 f[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) f[k] = flags[e[k]];
+#pragma unroll
+                for (int k = 0; k < 16; k++) b |= (f[k] ? 1u : 0u) << k;
             } else {
                 for (int k = 0; k < 16 && base + k < N; k++) b |= (flags[src[base + k]] ? 1u : 0u) << k;
             }

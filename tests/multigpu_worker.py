@@ -133,6 +133,14 @@ def main():
         fails.append("polyRefiner unrefine points")
     if sum(int(u.sum()) for u in upP) == 0 or all(np.array_equal(a, b) for a, b in zip(rcP, rc_ref)):
         fails.append("polyRefiner case is trivial")
+    # pointLevel must agree across processor patches (hexRef.C:3027-3057): consistent as built, caught when one rank differs
+    if ctx.check_point_levels() != 0:
+        fails.append("check_point_levels on a consistent mesh")
+    pl = mep.point_level.copy()
+    if rank == 0 and mep.patch_pts is not None and len(mep.patch_pts):
+        pl[mep.patch_pts[0]] += 1
+    if ctx.check_point_levels(pl) == 0:
+        fails.append("check_point_levels missed an inconsistent point")
     t = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(t)
     if fails:
