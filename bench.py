@@ -269,6 +269,40 @@ def physical_device_index(local_rank):
     return local_rank
 
 
+def bind_host_threads(local_rank, world):
+    """NUMA-aware placement of a rank's host threads (pinned staging, upload lanes, OpenMP of the host topology engine):
+    the cores of the GPU's NUMA node, divided between the ranks that share them.  Best effort; returns a description."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        node_cpus = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(physical_device_index(local_rank))
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            node = int(Path(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node").read_text())
+            if node >= 0:
+                cpus = []
+                for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus += list(range(int(a), int(b or a) + 1))
+                node_cpus = [c for c in cpus if c in allowed]
+        except Exception:
+            node_cpus = None
+        pool = node_cpus if node_cpus else allowed
+        if world > 1 and len(pool) >= world:
+            k = len(pool) // world
+            mine = pool[local_rank * k:(local_rank + 1) * k]
+        else:
+            mine = pool
+        if mine:
+            os.sched_setaffinity(0, mine)
+        return {"cores": len(mine), "numa_local": bool(node_cpus)}
+    except Exception as e:      # noqa: BLE001
+        return {"cores": None, "error": str(e)[:80]}
+
+
 def measured_peak():
     pth = ROOT / "MEASURED_PEAKS.json"
     if pth.exists():
@@ -517,6 +551,7 @@ def main():
     procs = PROCS.get(world, (world, 1, 1))
     case = Case(args.workload, args.base, args.shift_cells)
     lcap = MAX_LEVEL if case.workload == "S2" else 1
+    host_binding = bind_host_threads(local_rank, world) if (world > 1 and rank != 0) else {"cores": len(os.sched_getaffinity(0)), "note": "rank 0 keeps all cores for the host topology engine"}
 
     def log(s):
         if rank == 0:
@@ -649,6 +684,8 @@ def main():
     err2 = torch.empty(n2, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
     setup_s = time.time() - t_setup
+    if world > 1 and rank == 0:
+        host_binding = bind_host_threads(local_rank, world)      # the host topology engine is done: rank 0 takes its share too
     log(f"setup done: local cells {n} -> {n1} -> {n2}, refine {len(cells_first)}, split points {len(pts_first)}")
 
     # one event interval per stage
@@ -838,7 +875,7 @@ def main():
                        "cells_per_gpu": [int(v) for v in S[:, 4]], "n_refine": int(S[:, 2].sum()), "n_unrefine": int(S[:, 3].sum()),
                        "refined_mesh_cells": n1_total, "merged_mesh_cells": n2_total,
                        "sweeps_refine": info["sweeps_refine"], "sweeps_unrefine": info["sweeps_unrefine"],
-                       "build": build_info, "setup_s": setup_s},
+                       "build": build_info, "setup_s": setup_s, "host_threads": host_binding},
             "decisions": {"cells_to_refine_checksum": int(sum(int(v) for v in S[:, 0]) & mask61),
                           "split_points_checksum": int(sum(int(v) for v in S[:, 1]) & mask61),
                           "timed_lists_equal_first_pass": lists_ok,

@@ -255,11 +255,21 @@ static inline bool isDevicePtr(const void *ptr) {
 // addressing handed over after every topology change is several GB.  Here kUploadLanes host threads copy interleaved
 // 16 MiB chunks into their own double-buffered pinned staging and queue the DMA on their own stream, so the host
 // memcpy runs at multi-core bandwidth and overlaps the PCIe transfer.  Synchronous: complete on return.
-constexpr int kUploadLanes = 6;
+constexpr int kUploadLanesMax = 6;
 constexpr size_t kUploadChunk = (size_t)16 << 20;
+// lanes per context: the host cores are shared by the ranks of the node (one context each): cores / ranks, at most 6
+// (AMR_B200_UPLOAD_LANES overrides)
+static int uploadLanes(const amr_ctx *ctx) {
+    const char *e = getenv("AMR_B200_UPLOAD_LANES");
+    if (e && atoi(e) > 0) return atoi(e) > 64 ? 64 : atoi(e);
+    int cores = (int)std::thread::hardware_concurrency();
+    if (cores <= 0) cores = 8;
+    int lanes = cores / (ctx->nranks > 1 ? ctx->nranks : 1);
+    return lanes < 1 ? 1 : (lanes > kUploadLanesMax ? kUploadLanesMax : lanes);
+}
 static int bulkUpload(amr_ctx *ctx, void *dst, const void *src, size_t bytes) {
     if (ctx->lanes.empty()) {
-        ctx->lanes.resize(kUploadLanes);
+        ctx->lanes.resize((size_t)uploadLanes(ctx));
         for (auto &L : ctx->lanes) {
             for (int k = 0; k < 2; k++) {
                 if (cudaMallocHost(&L.pin[k], kUploadChunk) != cudaSuccess) { cudaGetLastError(); L.pin[k] = nullptr; }
@@ -276,11 +286,12 @@ static int bulkUpload(amr_ctx *ctx, void *dst, const void *src, size_t bytes) {
     }
     CK(cudaStreamSynchronize(ctx->stream));       // whatever still uses dst is done
     std::atomic<int> err{0};
+    const size_t nLanes = ctx->lanes.size();
     auto work = [&](int t) {
         if (cudaSetDevice(ctx->device) != cudaSuccess) { err = 1; return; }
         amr_ctx::UploadLane &L = ctx->lanes[(size_t)t];
         int slot = 0;
-        for (size_t off = (size_t)t * kUploadChunk; off < bytes; off += (size_t)kUploadLanes * kUploadChunk) {
+        for (size_t off = (size_t)t * kUploadChunk; off < bytes; off += nLanes * kUploadChunk) {
             const size_t len = bytes - off < kUploadChunk ? bytes - off : kUploadChunk;
             if (cudaEventSynchronize(L.ev[slot]) != cudaSuccess) { err = 1; return; }     // the slot's previous DMA has drained
             memcpy(L.pin[slot], (const char *)src + off, len);
@@ -291,7 +302,7 @@ static int bulkUpload(amr_ctx *ctx, void *dst, const void *src, size_t bytes) {
         if (cudaStreamSynchronize(L.s) != cudaSuccess) err = 1;
     };
     std::vector<std::thread> th;
-    for (int t = 1; t < kUploadLanes; t++) th.emplace_back(work, t);
+    for (int t = 1; t < (int)nLanes; t++) th.emplace_back(work, t);
     work(0);
     for (auto &x : th) x.join();
     if (err) { ctx->err = "bulk upload failed"; cudaGetLastError(); return AMR_ERR_CUDA; }
