@@ -72,8 +72,9 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
             int a = 0, b = 1;
             if (sscanf(pf, "%d/%d", &a, &b) >= 1 && a >= 0 && b > 0) { ctx->pushNum = a; ctx->pushDen = b; }
         }
-        const char *mf = getenv("AMR_B200_MAP");                 // tuning: fused (default) | fused40 | separate
-        if (mf && strcmp(mf, "fused40") == 0) ctx->mapForm = 1;
+        const char *mf = getenv("AMR_B200_MAP");                 // tuning: fused40 (default) | fused | separate
+        if (mf && strcmp(mf, "fused") == 0) ctx->mapForm = 0;
+        else if (mf && strcmp(mf, "fused40") == 0) ctx->mapForm = 1;
         else if (mf && strcmp(mf, "separate") == 0) ctx->mapForm = 2;
         const char *pm = getenv("AMR_B200_PUSH_MIN_CELLS");      // below this mesh size the extra launches do not pay
         if (pm) ctx->pushMinCells = atoll(pm);
@@ -1266,16 +1267,18 @@ static int emitList(amr_ctx *ctx, const u8 *flags, int64_t N, int32_t *userOut, 
     return finishList(ctx, &job, -1, nullptr, nOut, true);
 }
 
-// |dLevel| <= 1 over the internal faces of this rank's mesh, checked once per mesh (hexRef::checkRefinementLevels is
-// what guarantees it in the reference: hexRef.C:2934-3025, called after every topology change)
+// |dLevel| <= 1 over the internal faces of the mesh, checked once per mesh (hexRef::checkRefinementLevels is what
+// guarantees it in the reference: hexRef.C:2934-3025, called after every topology change).  With a communicator the
+// answer is agreed over all ranks (min): it selects between loops with different collective structure, so every rank
+// must take the same one.  Collective on the first call after a mesh / level change.
 static int ensureBalanceChecked(amr_ctx *ctx) {
     if (ctx->balancedLocal >= 0 || !ctx->lvl) return AMR_OK;
     const int64_t n = ctx->n;
     CK(cudaMemsetAsync(ctx->dCount + 3, 0, 8, ctx->stream));
     if (n) LAUNCH(k_check_levels, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const label *)ctx->lvl, (unsigned long long *)(ctx->dCount + 3));
-    CK(cudaMemcpyAsync(ctx->hCount + 3, ctx->dCount + 3, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->balancedLocal = ctx->hCount[3] == 0 ? 1 : 0;
+    int64_t bad = 0;
+    TRY(globalSum(ctx, 3, &bad));              // all ranks (sum of the violating faces)
+    ctx->balancedLocal = bad == 0 ? 1 : 0;
     return AMR_OK;
 }
 static int ensureQueues(amr_ctx *ctx, int64_t need) {
@@ -1409,7 +1412,7 @@ static int refineSweepsDense(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *swe
 static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut,
                         bool edgeRule = false) {
     // the queue form is only valid on a locally 2:1-balanced mesh: verified once per mesh
-    bool queueOk = maxSet && !edgeRule && ctx->pushNum > 0 && ctx->n > 0 && ctx->lvl;
+    bool queueOk = maxSet && !edgeRule && ctx->pushNum > 0 && ctx->lvl;      // the same on every rank
     if (queueOk) {
         TRY(ensureBalanceChecked(ctx));
         queueOk = ctx->balancedLocal == 1;
@@ -1797,9 +1800,10 @@ static int unrefineClosureQueue(amr_ctx *ctx, const double *dErr, double unrefin
     ctx->itersSeen[1] = iters;
     // hexRef3D.C:1808-1833 "problem": only an unbalanced mesh can produce it
     TRY(ensureBalanceChecked(ctx));
-    if (ctx->balancedLocal == 0 || ctx->nCoupled > 0) {
+    {
+        // every rank takes the same branch: balancedLocal is agreed over the ranks, balancedGlobal is set by all together
         bool check = ctx->balancedLocal == 0;
-        if (ctx->nCoupled > 0 && ctx->balancedGlobal < 0) check = true;      // coupled faces not verified yet: look once
+        if (multi && ctx->balancedGlobal < 0) check = true;                  // coupled faces not verified yet: look once
         if (check) {
             CK(cudaMemsetAsync(ctx->dFlags + 1, 0, sizeof(int), ctx->stream));
             if (ctx->nCoupled > 0) TRY(haloSwapCells(ctx, ctx->lvl8, 1, ctx->ghost8, uc));

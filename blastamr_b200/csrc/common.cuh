@@ -106,9 +106,9 @@ struct amr_ctx {
     Sell cf;                   // cell -> faces (2*face + role), ascending
     double *grad = nullptr;    // [3n]
     double *xbf = nullptr;     // [b] boundaryField of x
-    int mapForm = 0;                // amr_map_fields on device buffers: 0 fused, 1 fused with 40 registers, 2 one launch per field
+    int mapForm = 1;                // amr_map_fields on device buffers: 0 fused (56 registers), 1 fused with 40 registers (default), 2 one launch per field
     int64_t pushMinCells = 1 << 16;
-    int balancedLocal = -1;         // internal faces of the mesh satisfy |dLevel| <= 1 (-1: not checked yet)
+    int balancedLocal = -1;         // internal faces of the mesh satisfy |dLevel| <= 1 on EVERY rank (-1: not checked yet)
     int balancedGlobal = -1;        // ... and the coupled faces, on every rank
     long long *hMarked = nullptr;   // pinned: source cells seen per buffer-layer / sweep site by the previous call
     unsigned long long *dMarked = nullptr;   // [16] device: the counts of the current call, by site
