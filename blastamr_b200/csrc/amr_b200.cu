@@ -72,6 +72,8 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
             int a = 0, b = 1;
             if (sscanf(pf, "%d/%d", &a, &b) >= 1 && a >= 0 && b > 0) { ctx->pushNum = a; ctx->pushDen = b; }
         }
+        const char *tr = getenv("AMR_B200_TRACE");
+        if (tr && tr[0]) { ctx->traceOn = true; ctx->tracePath = tr; }
         const char *mf = getenv("AMR_B200_MAP");                 // tuning: fused40 (default) | fused | separate
         if (mf && strcmp(mf, "fused") == 0) ctx->mapForm = 0;
         else if (mf && strcmp(mf, "fused40") == 0) ctx->mapForm = 1;
@@ -140,10 +142,31 @@ static void freeMesh(amr_ctx *ctx) {
     for (auto &bf : ctx->arena) ctx->devBytes += (int64_t)bf.cap;
 }
 
+static void traceDump(amr_ctx *ctx) {
+    if (!ctx->traceOn || ctx->trace.empty()) return;
+    char path[512];
+    snprintf(path, sizeof(path), "%s.%d.%p", ctx->tracePath.c_str(), ctx->rank, (void *)ctx);
+    FILE *fh = fopen(path, "w");
+    if (fh) {
+        const size_t first = ctx->trace.size() > 6000 ? ctx->trace.size() - 6000 : 0;     // the last calls
+        float prev = 0.f;
+        for (size_t i = first; i < ctx->trace.size(); i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->trace[first].ev, ctx->trace[i].ev);
+            fprintf(fh, "%8.1f %7.1f %s\n", ms * 1e3f, (ms - prev) * 1e3f, ctx->trace[i].name);
+            prev = ms;
+        }
+        fclose(fh);
+    }
+    for (auto &r : ctx->trace) cudaEventDestroy(r.ev);
+    ctx->trace.clear();
+}
+
 AMR_API int amr_ctx_destroy(amr_ctx *ctx) {
     if (!ctx) return AMR_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    traceDump(ctx);
     freeMesh(ctx);
     for (auto &bf : ctx->arena) cudaFree(bf.p);
     if (ctx->usePeer) {
@@ -208,7 +231,8 @@ AMR_API int64_t amr_device_bytes(const amr_ctx *ctx) { return ctx ? ctx->devByte
     if (!ctx) return AMR_ERR_ARG;                                                             \
     CK(cudaSetDevice(ctx->device));                                                           \
     arenaReset(ctx);                                                                          \
-    ctx->err.clear()
+    ctx->err.clear();                                                                         \
+    traceMark(ctx, __func__)
 
 // ============================================================================ halo swaps
 
@@ -391,6 +415,7 @@ static int haloBegin(amr_ctx *ctx, const void *cells, size_t elemBytes, void *re
         else if (elemBytes == 8) k_halo_push_cells<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, bOwner, (const char *)cells, minus, counter, gate);
         else k_halo_push_cells<24><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, bOwner, (const char *)cells, minus, counter, gate);
         ctx->launches++;
+        traceMark(ctx, "k_halo_push_cells");
         ctx->peerTouched = true;
         tok->pending = true; tok->elemBytes = elemBytes; tok->recv = recv; tok->gate = gate;
         return AMR_OK;
@@ -1299,6 +1324,7 @@ static int queueLook(amr_ctx *ctx, const int *gq, int issued, const int32_t *dTo
     TRY(sitesFetch(ctx));
     PEER_ERR_FETCH();
     CK(cudaStreamSynchronize(ctx->stream));
+    traceMark(ctx, "host look returned");
     PEER_ERR_CHECK();
     sitesCommit(ctx);
     ctx->lookResult = 0;

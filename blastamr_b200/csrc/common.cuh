@@ -48,8 +48,16 @@ struct Sell {
                                   // the boundary fix-up has folded the patch faces in); cell->cell only
 };
 
+struct TraceRec { const char *name; cudaEvent_t ev; };
+
 struct amr_ctx {
     int device = 0;
+    // AMR_B200_TRACE=<file prefix>: a CUDA event after every launch / host round trip of this context; the time line
+    // (name, microseconds since the first event) is written to <prefix>.<rank>.<ctx address> at amr_ctx_destroy.
+    // Diagnosis only: the events themselves cost ~1 us each.
+    bool traceOn = false;
+    std::string tracePath;
+    std::vector<TraceRec> trace;
     cudaStream_t stream = nullptr;
     cudaStream_t upStream = nullptr, downStream = nullptr;   // host<->host field mapping: both PCIe directions at once
     struct UploadLane { void *pin[2] = {nullptr, nullptr}; cudaStream_t s = nullptr; cudaEvent_t ev[2] = {nullptr, nullptr}; };
@@ -217,11 +225,20 @@ struct amr_ctx {
         if (rc_ != AMR_OK) return rc_;                                                        \
     } while (0)
 
+static inline void traceMark(amr_ctx *ctx, const char *name) {
+    if (!ctx->traceOn || ctx->trace.size() >= 200000) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, ctx->stream);
+    ctx->trace.push_back({name, e});
+}
+
 // kernel launch with bookkeeping (gpu_launches of bench.py is this counter)
 #define LAUNCH(kern, grid, block, ...)                                                        \
     do {                                                                                      \
         kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                               \
         ctx->launches++;                                                                      \
+        traceMark(ctx, #kern);                                                                \
     } while (0)
 
 static inline unsigned gridFor(int64_t items, int perBlock = kThreads) {
