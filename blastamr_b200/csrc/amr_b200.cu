@@ -45,6 +45,7 @@ static int launchPipe(amr_ctx *ctx, K kern, const Sell &S, Args... args) {
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, kPipeThreads, smem, ctx->stream>>>(V, args...);
     ctx->launches++;
+    traceMark(ctx, "pipelined SELL kernel");
     return AMR_OK;
 }
 
@@ -90,23 +91,25 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
     cudaMalloc((void **)&ctx->dSeq, 2 * sizeof(unsigned));
     cudaMalloc((void **)&ctx->lbTicket, sizeof(unsigned));
     cudaMalloc((void **)&ctx->dTotals, 8 * sizeof(int32_t));
-    cudaMalloc((void **)&ctx->dQ, 2 * (kMaxIter + 2) * sizeof(int));
-    cudaMalloc((void **)&ctx->dMarked, 16 * sizeof(unsigned long long));
+    cudaMalloc((void **)&ctx->dQ, 2 * (kMaxIter + 2) * sizeof(int) + 16 * sizeof(unsigned long long));   // queue sizes + site counts: one memset per call
     cudaMallocHost((void **)&ctx->hFlags, 16 * sizeof(int));
     cudaMallocHost((void **)&ctx->hCount, 4 * sizeof(int64_t));
     cudaMallocHost((void **)&ctx->hMarked, 32 * sizeof(long long));
     cudaMallocHost((void **)&ctx->hQ, 2 * (kMaxIter + 2) * sizeof(int));
+    cudaMallocHost((void **)&ctx->mailbox, sizeof(Mailbox));
+    if (ctx->mailbox) memset(ctx->mailbox, 0, sizeof(Mailbox));
     if (ctx->hMarked) { for (int i = 0; i < 32; i++) ctx->hMarked[i] = -1; ctx->hMarkedStage = ctx->hMarked + 16; }
     if (!ctx->dFlags || !ctx->dCount || !ctx->hFlags || !ctx->hCount || !ctx->hMarked || !ctx->dSeq || !ctx->lbTicket || !ctx->dTotals ||
-        !ctx->dQ || !ctx->hQ || !ctx->dMarked) { delete ctx; return AMR_ERR_CUDA; }
+        !ctx->dQ || !ctx->hQ || !ctx->mailbox) { delete ctx; return AMR_ERR_CUDA; }
     ctx->dGQ = ctx->dQ + (kMaxIter + 2);
+    ctx->dMarked = (unsigned long long *)(ctx->dQ + 2 * (kMaxIter + 2));
+    static_assert((2 * (kMaxIter + 2) * sizeof(int)) % 8 == 0, "site counts must be 8-byte aligned");
     cudaMemset(ctx->dFlags, 0, 16 * sizeof(int));
     cudaMemset(ctx->dCount, 0, 4 * sizeof(int64_t));
     cudaMemset(ctx->dSeq, 0, 2 * sizeof(unsigned));
     cudaMemset(ctx->lbTicket, 0, sizeof(unsigned));
     cudaMemset(ctx->dTotals, 0, 8 * sizeof(int32_t));
-    cudaMemset(ctx->dQ, 0, 2 * (kMaxIter + 2) * sizeof(int));
-    cudaMemset(ctx->dMarked, 0, 16 * sizeof(unsigned long long));
+    cudaMemset(ctx->dQ, 0, 2 * (kMaxIter + 2) * sizeof(int) + 16 * sizeof(unsigned long long));
     *out = ctx;
     return AMR_OK;
 }
@@ -149,12 +152,12 @@ static void traceDump(amr_ctx *ctx) {
     FILE *fh = fopen(path, "w");
     if (fh) {
         const size_t first = ctx->trace.size() > 6000 ? ctx->trace.size() - 6000 : 0;     // the last calls
-        float prev = 0.f;
+        double t = 0.0;
         for (size_t i = first; i < ctx->trace.size(); i++) {
             float ms = 0.f;
-            cudaEventElapsedTime(&ms, ctx->trace[first].ev, ctx->trace[i].ev);
-            fprintf(fh, "%8.1f %7.1f %s\n", ms * 1e3f, (ms - prev) * 1e3f, ctx->trace[i].name);
-            prev = ms;
+            if (i > first) cudaEventElapsedTime(&ms, ctx->trace[i - 1].ev, ctx->trace[i].ev);     // event to event: full resolution
+            t += (double)ms * 1e3;
+            fprintf(fh, "%10.1f %8.1f %s\n", t, (double)ms * 1e3, ctx->trace[i].name);
         }
         fclose(fh);
     }
@@ -179,8 +182,7 @@ AMR_API int amr_ctx_destroy(amr_ctx *ctx) {
     if (ctx->region) cudaFree(ctx->region);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     cudaFree(ctx->dFlags); cudaFree(ctx->dCount); cudaFree(ctx->dSeq); cudaFree(ctx->lbTicket); cudaFree(ctx->dTotals); cudaFree(ctx->dQ);
-    cudaFree(ctx->dMarked);
-    cudaFreeHost(ctx->hFlags); cudaFreeHost(ctx->hCount); cudaFreeHost(ctx->hMarked); cudaFreeHost(ctx->hQ);
+    cudaFreeHost(ctx->hFlags); cudaFreeHost(ctx->hCount); cudaFreeHost(ctx->hMarked); cudaFreeHost(ctx->hQ); cudaFreeHost(ctx->mailbox);
     for (auto &L : ctx->lanes) {
         for (int k = 0; k < 2; k++) { if (L.pin[k]) cudaFreeHost(L.pin[k]); if (L.ev[k]) cudaEventDestroy(L.ev[k]); }
         if (L.s) cudaStreamDestroy(L.s);
@@ -393,6 +395,12 @@ static int haloExchange(amr_ctx *ctx, const void *send, void *recv, size_t elemB
 // exchange k, so a neighbour can run at most one exchange ahead and the two parity buffers suffice.
 // At most one swap is in flight per context (haloBegin ... haloEnd); exchange numbers live on the device (p2p.cuh).
 // gate (optional, device int, identical on all ranks): the swap only happens when *gate != 0.
+// aligned destination words of a byte-payload push (k_halo_push_cells<1>)
+static inline int64_t pushWords(const HaloPlan &P) {
+    int64_t w = 0;
+    for (int q = 0; q < P.nPatch; q++) w += (P.size[q] + (P.offTheirs[q] & 3) + 3) >> 2;
+    return w;
+}
 struct HaloToken {
     bool pending = false;
     size_t elemBytes = 0;
@@ -407,7 +415,8 @@ static int haloBegin(amr_ctx *ctx, const void *cells, size_t elemBytes, void *re
     const int64_t b = ctx->b;
     if (ctx->usePeer && ctx->havePlan) {
         const HaloPlan &P = *(const HaloPlan *)ctx->haloPlan;
-        const unsigned g = gridFor(P.prefix[P.nPatch]);
+        unsigned g = gridFor(P.prefix[P.nPatch]);
+        if (elemBytes == 1) g = gridFor(pushWords(P));
         unsigned *counter = (unsigned *)(ctx->dFlags + 6);
         const label *bOwner = ctx->owner + ctx->f;
         if (elemBytes == 1) k_halo_push_cells<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, bOwner, (const char *)cells, minus, counter, gate);
@@ -790,7 +799,7 @@ static int pointSwap(amr_ctx *ctx, const void *values, size_t elemBytes, void *r
         unsigned *c1 = (unsigned *)(ctx->dFlags + 6), *c2 = (unsigned *)(ctx->dFlags + 7);
         const unsigned long long to = ctx->peerTimeoutNs;
         if (elemBytes == 1) {
-            k_halo_push_cells<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, (const label *)ctx->ppPts, (const char *)values, (const u8 *)nullptr, c1, (const int *)nullptr);
+            k_halo_push_cells<1><<<gridFor(pushWords(P)), kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, (const label *)ctx->ppPts, (const char *)values, (const u8 *)nullptr, c1, (const int *)nullptr);
             k_halo_unpack<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->region, ctx->dSeq, (char *)recv, to, c2, (const int *)nullptr);
         } else {
             k_halo_push_cells<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, (const label *)ctx->ppPts, (const char *)values, (const u8 *)nullptr, c1, (const int *)nullptr);
@@ -1146,7 +1155,8 @@ static inline int siteOf(int base, int layer) { return base + (layer < 3 ? layer
 
 static int sitesBegin(amr_ctx *ctx) {
     ctx->sitesTouched = 0;
-    CK(cudaMemsetAsync(ctx->dMarked, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    // the by-product counts of the layers AND the queue sizes of the closure loop that follows: one memset per call
+    CK(cudaMemsetAsync(ctx->dQ, 0, 2 * (kMaxIter + 2) * sizeof(int) + 16 * sizeof(unsigned long long), ctx->stream));
     return AMR_OK;
 }
 // enqueue the read-back of the counts; sitesCommit after the stream was synchronised
@@ -1319,17 +1329,40 @@ static inline unsigned queueGrid(const amr_ctx *ctx) { return (unsigned)(ctx->nu
 // One host look at a speculatively enqueued queue loop: sizes of queues [1, issued] (summed over ranks), the list size
 // (optional) and the by-product counts in ONE round trip.  Returns the index of the first empty queue, or 0.
 static int queueLook(amr_ctx *ctx, const int *gq, int issued, const int32_t *dTotal) {
-    CK(cudaMemcpyAsync(ctx->hQ, gq, (size_t)(issued + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (dTotal) CK(cudaMemcpyAsync(ctx->hFlags + 8, dTotal, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    TRY(sitesFetch(ctx));
-    PEER_ERR_FETCH();
-    CK(cudaStreamSynchronize(ctx->stream));
+    Mailbox *mb = ctx->mailbox;
+    const unsigned seq = ++ctx->mailSeq;
+    const int *errWord = (ctx->usePeer && ctx->peerTouched) ? (const int *)(ctx->region + kPeerErrOffset) : nullptr;
+    k_mailbox<<<1, 64, 0, ctx->stream>>>(gq, issued + 1, dTotal, ctx->dMarked, errWord, mb, seq);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    // poll the mailbox (a PCIe write away) instead of synchronising the stream; fall back to the stream on anything odd
+    bool arrived = false;
+    for (long spins = 0; ; spins++) {
+        if (__atomic_load_n(&mb->seq, __ATOMIC_ACQUIRE) == seq) { arrived = true; break; }
+        if ((spins & 0xfffff) == 0xfffff) {
+            const cudaError_t e = cudaStreamQuery(ctx->stream);
+            if (e == cudaSuccess) { arrived = __atomic_load_n(&mb->seq, __ATOMIC_ACQUIRE) == seq; break; }
+            if (e != cudaErrorNotReady) { ctx->err = std::string("queue loop: ") + cudaGetErrorString(e); return AMR_ERR_CUDA; }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (!arrived) CK(cudaStreamSynchronize(ctx->stream));
     traceMark(ctx, "host look returned");
-    PEER_ERR_CHECK();
-    sitesCommit(ctx);
+    ctx->peerTouched = false;
+    if (mb->peerError) {
+        cudaMemsetAsync(ctx->region + kPeerErrOffset, 0, sizeof(int), ctx->stream);
+        FAIL(AMR_ERR_STATE, "peer-memory halo swap / reduction timed out: a neighbour rank did not enter the same collective call "
+                            "(results of this call are invalid; AMR_B200_PEER_TIMEOUT_S sets the limit)");
+    }
+    for (int s2 = 0; s2 < 16; s2++)
+        if (ctx->sitesTouched & (1u << s2)) ctx->hMarked[s2] = mb->marked[s2];
+    ctx->sitesTouched = 0;
+    ctx->hFlags[8] = mb->total;
     ctx->lookResult = 0;
     for (int j = 1; j <= issued; j++)
-        if (ctx->hQ[j] == 0) { ctx->lookResult = j; break; }
+        if (mb->q[j] == 0) { ctx->lookResult = j; break; }
     return AMR_OK;
 }
 
@@ -1345,8 +1378,7 @@ static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int
     int *qc = ctx->dQ, *gq = multi ? ctx->dGQ : ctx->dQ;
     const int64_t cap = ctx->queueCap;
     const label *cf = ctx->cplFace, *bo = ctx->owner + ctx->f;
-    CK(cudaMemsetAsync(ctx->dQ, 0, 2 * (kMaxIter + 2) * sizeof(int), ctx->stream));
-    ListJob job;
+    ListJob job;                          // (queue sizes were cleared by sitesBegin at the start of the call)
     TRY(listTarget(ctx, n, cellsOut, &job));
     // sweep 0: the rows of all marked cells
     {
@@ -1773,8 +1805,7 @@ static int unrefineClosureQueue(amr_ctx *ctx, const double *dErr, double unrefin
     u8 *uc = ctx->flagB, *spFlag = ctx->spFlag;
     ListJob job;
     TRY(listTarget(ctx, std::max<int64_t>(nSp, 1), elemsOut, &job));
-    CK(cudaMemsetAsync(ctx->dQ, 0, 2 * (kMaxIter + 2) * sizeof(int), ctx->stream));
-    CK(cudaMemsetAsync(uc, 0, (size_t)n, ctx->stream));
+    CK(cudaMemsetAsync(uc, 0, (size_t)n, ctx->stream));      // (queue sizes were cleared by sitesBegin at the start of the call)
     CK(cudaMemsetAsync(spFlag, 1, (size_t)nSp, ctx->stream));
     // U1 + U3: pFld < unrefineLevel and no marked cell, cell-centric (the split points themselves are mesh-constant)
     if (n && nSp) LAUNCH(k_sp_filter, gridFor(n, kThreads * 4), kThreads, n, (const label *)ctx->cellSp, dErr, unrefineLevel, marked, spFlag);

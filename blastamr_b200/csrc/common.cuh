@@ -50,6 +50,18 @@ struct Sell {
 
 struct TraceRec { const char *name; cudaEvent_t ev; };
 
+// Pinned host memory that the last kernel of a speculative loop writes directly (zero-copy): queue sizes, list size,
+// by-product counts and the peer error word arrive with ONE store sequence over PCIe instead of four small DMA copies
+// and a stream synchronisation; the host polls `seq`.
+struct Mailbox {
+    int q[64];
+    long long marked[16];
+    int total;
+    int peerError;
+    volatile unsigned seq;
+    unsigned pad;
+};
+
 struct amr_ctx {
     int device = 0;
     // AMR_B200_TRACE=<file prefix>: a CUDA event after every launch / host round trip of this context; the time line
@@ -123,6 +135,8 @@ struct amr_ctx {
     long long *hMarkedStage = nullptr;       // pinned read-back staging (= hMarked + 16)
     unsigned sitesTouched = 0;               // sites a layer kernel reported for in this call
     int lookResult = 0;                      // queueLook: index of the first empty queue, or 0
+    Mailbox *mailbox = nullptr;              // pinned (device-visible through UVA)
+    unsigned mailSeq = 0;
     int pushNum = 1, pushDen = 4;   // buffer layers take the sparse push form when marked/n < pushNum/pushDen (0 = never)
     label *ppPts = nullptr;         // points of the processor patches, patch after patch (syncPointList pairing)
     std::vector<int32_t> ppOff;     // [npatch+1] offsets into ppPts

@@ -204,6 +204,18 @@ k_flags_normalize(int64_t n, const u8 *__restrict__ in, u8 *__restrict__ out, bo
     }
 }
 
+// the results of a speculative loop go straight to pinned host memory (Mailbox, common.cuh); the host polls seq
+__global__ void k_mailbox(const int *__restrict__ gq, int nq, const int32_t *__restrict__ total, const unsigned long long *__restrict__ marked,
+                          const int *__restrict__ peerError, Mailbox *mb, unsigned seq) {
+    const int t = threadIdx.x;
+    if (t < nq) mb->q[t] = gq[t];
+    if (t < 16) mb->marked[t] = (long long)marked[t];
+    if (t == 0) { mb->total = total ? *total : 0; mb->peerError = peerError ? *peerError : 0; }
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) mb->seq = seq;
+}
+
 // ------------------------------------------------------------------------------------------
 // (2) consistentRefinement as queue iterations
 // ------------------------------------------------------------------------------------------

@@ -58,36 +58,72 @@ __device__ __forceinline__ unsigned ldAcquireSys(const unsigned *p) {
 
 // fused pack + push + signal: value of a per-cell array at the owner of every coupled boundary face goes
 // straight into the neighbour's region; the last CTA to finish publishes the epoch (threadfence-reduction
-// pattern), so a swap is two launches (this one and k_halo_unpack).  `minus` (optional, bytes): v -= minus[o].
+// pattern), so a swap is two launches (this one and the receiving kernel).  `minus` (optional, bytes): v -= minus[o].
 // gate (optional): the exchange only happens when *gate != 0 -- the same value on every rank.
+// Byte payloads (marks, level +/- flag: every swap of the sweep loops) travel as 32-bit words: a thread owns 4
+// consecutive destination bytes, aligned in the neighbour's buffer, so NVLink carries one store per 4 faces.
+// No per-thread system fence: the CTA barrier orders every thread's stores before thread 0's fence (cumulativity),
+// and the last CTA's release store of the epoch is what the receiver acquires.
 template <int BYTES>
 __global__ void k_halo_push_cells(HaloPlan P, char *const *__restrict__ peer, int myRank, const unsigned *__restrict__ seq,
                                   const label *__restrict__ bOwner, const char *__restrict__ cells, const u8 *__restrict__ minus,
                                   unsigned *counter, const int *__restrict__ gate) {
     if (gate && *gate == 0) return;
-    const unsigned epoch = seq[0] + 1u;                  // stored back by k_halo_unpack, later in stream order
+    const unsigned epoch = seq[0] + 1u;                  // stored back by the receiving kernel, later in stream order
     const int parity = (int)(epoch & 1u);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.prefix[P.nPatch]) {
+    if (BYTES == 1) {
+        // thread i <-> the i-th aligned destination word over all patches (prefixW = prefix of the word counts)
+        int q = 0, w = i;
+        bool live = false;
+        for (; q < P.nPatch; q++) {
+            const int a = P.offTheirs[q] & 3;
+            const int words = (P.size[q] + a + 3) >> 2;
+            if (w < words) { live = true; break; }
+            w -= words;
+        }
+        if (live) {
+            const int a = P.offTheirs[q] & 3;
+            const int k0 = 4 * w - a;                    // first element of this word (may be < 0 / reach past the patch)
+            unsigned pack = 0;
+            bool full = k0 >= 0 && k0 + 4 <= P.size[q];
+            u8 vals[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int k = k0 + t;
+                if (k >= 0 && k < P.size[q]) {
+                    const label o = bOwner[P.offMine[q] + k];
+                    u8 v = (u8)cells[o];
+                    if (minus) v = (u8)(v - minus[o]);
+                    vals[t] = v;
+                }
+                pack |= (unsigned)vals[t] << (8 * t);
+            }
+            char *dst = peer[P.nbr[q]] + sizeof(P2PRegionHeader) + (size_t)parity * kHaloCap + (size_t)(P.offTheirs[q] + k0);
+            if (full) *reinterpret_cast<unsigned *>(dst) = pack;
+            else {
+#pragma unroll
+                for (int t = 0; t < 4; t++) { const int k = k0 + t; if (k >= 0 && k < P.size[q]) dst[t] = (char)vals[t]; }
+            }
+        }
+    } else if (i < P.prefix[P.nPatch]) {
         int q = 0;
         while (i >= P.prefix[q + 1]) q++;
         const int k = i - P.prefix[q];
         const label o = bOwner[P.offMine[q] + k];
         char *dst = peer[P.nbr[q]] + sizeof(P2PRegionHeader) + (size_t)parity * kHaloCap + (size_t)(P.offTheirs[q] + k) * BYTES;
-        if (BYTES == 1) { u8 v = (u8)cells[o]; if (minus) v = (u8)(v - minus[o]); *reinterpret_cast<u8 *>(dst) = v; }
-        else if (BYTES == 4) *reinterpret_cast<int *>(dst) = reinterpret_cast<const int *>(cells)[o];
+        if (BYTES == 4) *reinterpret_cast<int *>(dst) = reinterpret_cast<const int *>(cells)[o];
         else if (BYTES == 8) *reinterpret_cast<double *>(dst) = reinterpret_cast<const double *>(cells)[o];
         else {                                               // vector field: 3 doubles per cell
             const double *s3 = reinterpret_cast<const double *>(cells) + 3 * (size_t)o;
             double *d3 = reinterpret_cast<double *>(dst);
             d3[0] = s3[0]; d3[1] = s3[1]; d3[2] = s3[2];
         }
-        __threadfence_system();
     }
     __shared__ int last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        __threadfence_system();                              // this CTA's stores (ordered before by the barrier) are out
         last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     }
     __syncthreads();

@@ -241,6 +241,7 @@ static int compactFlagsEx(amr_ctx *ctx, const u8 *flags, int64_t N, const int32_
     k_compact_lb<<<(unsigned)tiles, kThreads, 0, ctx->stream>>>(flags, N, nDev, aligned, src, map, ctx->lbStatus, ctx->lbTicket, ctx->scanTag,
                                                                  out, total, gate);
     ctx->launches++;
+    traceMark(ctx, "k_compact_lb");
     *totalDev = total;
     return AMR_OK;
 }
