@@ -9,6 +9,11 @@ Workload (BASELINE.json configs[4], SURVEY.md 8(d) "C5"):
                 leaves in four levels -- and then the front MOVED by `--shift-cells` (default 4) level-3 cells, so
                 that in the timed step refinement, 2:1 propagation (several sweeps) and unrefinement all fire.
   S1 (--workload S1)  round 1's uniform level-0 box of N^3 cells (default N = 400), unshifted front.
+  P2 (--workload P2)  the polyhedral engine on the S2 case: `refiner polyRefiner` (polyhedralRefinement: cells as general
+                polyhedra over faces()/edges(), face AND edge 2:1 consistency, refinement.C:202-387; buffer layers across
+                POINTS and pointLevel-based split points on unrefinement, fvMeshPolyRefiner.C:48-96,
+                polyhedralRefinement.C:2110-2205; nUnrefinementBufferLayers >= 2, fvMeshPolyRefiner.C:287-300), default
+                base 64 (~4 M leaves: the host topology engine has to build faces() and edges() as well).
 `delta` estimator on rho, lowerRefineLevel = unrefineLevel = 0.01, maxRefinement 3, nBufferLayers 1/1, hexRefiner.
 One "step" = what adaptiveFvMesh::update() asks of the decision path in one time step:
   E    errorEstimator::update (delta + normalize)                                            on mesh M0
@@ -66,7 +71,12 @@ class Case:
     def __init__(self, workload, base, shift_cells):
         self.workload = workload
         self.base = int(base)
-        if workload == "S2":
+        self.poly = workload == "P2"
+        self.graded = workload in ("S2", "P2")
+        self.kind = 2 if self.poly else 0                       # AMR_REFINER_POLY3D / AMR_REFINER_HEX3D
+        self.layers_ref = LAYERS_REF
+        self.layers_unref = max(LAYERS_UNREF, 2) if self.poly else LAYERS_UNREF    # fvMeshPolyRefiner.C:287-300
+        if self.graded:
             self.w = 0.8 / self.base
             self.h_fine = 1.0 / (self.base << MAX_LEVEL)
             self.shift = float(shift_cells) * self.h_fine
@@ -85,11 +95,13 @@ class Case:
         return 1.0 + 0.5 * (1.0 + np.tanh((d - 0.3) / self.w))
 
     def describe(self):
-        if self.workload == "S2":
-            return (f"S2: synthetic blockMesh hex box of {self.base}^3 level-0 cells graded to maxRefinement {MAX_LEVEL} around the "
+        if self.graded:
+            engine = ("polyRefiner (polyhedralRefinement on faces()/edges(): face + edge consistency, point buffer layers, "
+                      "pointLevel split points)") if self.poly else "hexRefiner"
+            return (f"{self.workload}: synthetic blockMesh hex box of {self.base}^3 level-0 cells graded to maxRefinement {MAX_LEVEL} around the "
                     f"analytic density front by the AMR loop itself (3 refine cycles + 1 refine/unrefine cycle), front then moved "
                     f"by {self.shift_cells:g} level-{MAX_LEVEL} cells; delta estimator, thresholds {THR}, buffer layers "
-                    f"{LAYERS_REF}/{LAYERS_UNREF}, hexRefiner; 1 scalar + 1 vector + the error field mapped on refinement and on "
+                    f"{self.layers_ref}/{self.layers_unref}, {engine}; 1 scalar + 1 vector + the error field mapped on refinement and on "
                     f"unrefinement")
         return (f"S1: synthetic {self.base}^3-cell uniform blockMesh hex box, analytic density front, delta estimator, thresholds "
                 f"{THR}, maxRefinement {MAX_LEVEL}, buffer layers {LAYERS_REF}/{LAYERS_UNREF}, hexRefiner; 1 scalar + 1 vector + the "
@@ -136,42 +148,56 @@ def local_maps(n0_glob, n1_glob, cm_g, cg0, cg1):
 # (the build-up cycles run on the product for the GPU arm and on the oracle for the CPU arms)
 
 class GpuPath:
-    def __init__(self, device):
+    def __init__(self, device, case):
         from blastamr_b200 import capi
         self.capi = capi
         self.device = device
+        self.case = case
         self.ctx = capi.Context(device)
 
     def refine_decision(self, mesh, x):
         ctx = self.ctx
         ctx.set_mesh(mesh)
         ctx.estimate("delta", x, thresholds=THRS, keep_resident=True)
-        cells, _ = ctx.select_refine(None, MAX_LEVEL, LAYERS_REF, cells_out=np.empty(max(mesh.n, 1), np.int32))
+        cells, _ = ctx.select_refine(None, MAX_LEVEL, self.case.layers_ref, kind=self.case.kind, cells_out=np.empty(max(mesh.n, 1), np.int32))
         return cells.copy()
 
     def unrefine_decision_same_mesh(self):
-        pts, _ = self.ctx.select_unrefine(None, LAYERS_UNREF)
+        pts, _ = self.ctx.select_unrefine(None, self.case.layers_unref, kind=self.case.kind)
         return pts.copy()
 
     def close(self):
         self.ctx.close()
 
 
+def oracle_select_refine(w, case, e):
+    if case.poly:
+        return w.poly_select_refine(e, MAX_LEVEL, case.layers_ref)
+    return w.hex_select_refine(e, MAX_LEVEL, case.layers_ref)
+
+
+def oracle_select_unrefine(w, case, e, rc):
+    if case.poly:
+        return w.poly_select_unrefine(e, rc, case.layers_unref)
+    return w.hex_select_unrefine(e, rc, case.layers_unref)
+
+
 class OraclePath:
-    def __init__(self):
+    def __init__(self, case):
         from oracle import oracle as O
         self.O = O
+        self.case = case
 
     def refine_decision(self, mesh, x):
         w = self.O.World([mesh])
         e = w.estimate("delta", [x])
         w.normalize(e, *THRS)
-        rc, rs, _ = w.hex_select_refine(e, MAX_LEVEL, LAYERS_REF)
+        rc, rs, _ = oracle_select_refine(w, self.case, e)
         self._w, self._e, self._rc = w, e, rc
         return np.flatnonzero(rs[0]).astype(np.int32)
 
     def unrefine_decision_same_mesh(self):
-        up, _, _ = self._w.hex_select_unrefine(self._e, [self._rc[0].copy()], LAYERS_UNREF)
+        up, _, _ = oracle_select_unrefine(self._w, self.case, self._e, [self._rc[0].copy()])
         return np.flatnonzero(up[0]).astype(np.int32)
 
     def close(self):
@@ -181,21 +207,21 @@ class OraclePath:
 def build_initial(oc, path, case, log=None):
     """The mesh the timed step starts from.  S2: update() cycles of the path on the static front -- refine-only until
     maxRefinement is reached, then one full cycle whose unrefinement branch removes what the buffer layers over-refined."""
-    if case.workload != "S2":
+    if not case.graded:
         return {"cycles": 0}
     hist = []
     for _ in range(MAX_LEVEL):
-        m = oc.build(points=False)
+        m = oc.build(points=case.poly, faces=case.poly)
         cells = path.refine_decision(m, case.field(m.cc, case.c_build))
         hist.append((int(m.n), int(len(cells)), 0))
         del m
         if len(cells):
             oc.refine(cells)
-    m = oc.build(points=True)
+    m = oc.build(points=True, faces=case.poly)
     cells = path.refine_decision(m, case.field(m.cc, case.c_build))
     if len(cells):                  # rare on a static front: cut, then evaluate again on the cut mesh (build-up only; any
         oc.refine(cells)            # 2:1-balanced mesh is a valid starting point, a non-empty second list is left to the step)
-        m = oc.build(points=True)
+        m = oc.build(points=True, faces=case.poly)
         path.refine_decision(m, case.field(m.cc, case.c_build))
     pts = path.unrefine_decision_same_mesh()
     hist.append((int(m.n), int(len(cells)), int(len(pts))))
@@ -323,7 +349,7 @@ def checksum(ids):
     return int(h.sum(dtype=np.uint64) & np.uint64((1 << 61) - 1))
 
 
-def algorithmic_bytes(m0, m1, n2, sweeps_ref, sweeps_unref):
+def algorithmic_bytes(m0, m1, n2, sweeps_ref, sweeps_unref, case=None, edges=None):
     """each input array read once and each output written once per logical pass of the REFERENCE
     algorithm (dense face loops); label 4 B, scalar 8 B, flag 1 B.  m0 = (n, f), m1 = (n, f, p, nnz pointCells).
     This is what the reference's loops would move -- NOT what the kernels move (their sparse forms skip most of it);
@@ -338,6 +364,13 @@ def algorithmic_bytes(m0, m1, n2, sweeps_ref, sweeps_unref):
     U = LAYERS_UNREF * (8 * f1 + 2 * n1) + (csr + 8 * n1 + 8 * p1) + (8 * n1 + csr) + (9 * p1 + n1) + \
         sweeps_unref * ((8 * f1 + 6 * n1) + 2 * csr + 2 * p1)
     F2 = 5 * (4 * n2 + 8 * n1 + 8 * n2)
+    if case is not None and case.poly and edges is not None:
+        # polyRefiner: B2 per sweep = B1 + edgeCells CSR; buffer layers across points = cells -> points -> cells over the
+        # pointCells CSR; U3 split-point rule reads faces() + pointLevel; B4 per sweep = B3 + edgeCells CSR
+        (e0, nnz_e0), (e1, nnz_e1), nnz_f1 = edges
+        B = sweeps_ref * ((8 * f + 6 * n) + 4 * nnz_e0 + 4 * (e0 + 1))
+        U = case.layers_unref * (2 * csr + 2 * n1 + 2 * p1) + (csr + 8 * n1 + 8 * p1) + (4 * nnz_f1 + 4 * (f1 + 1) + 4 * p1 + csr) + \
+            (9 * p1 + n1) + sweeps_unref * ((8 * f1 + 6 * n1) + 2 * csr + 2 * p1 + 4 * nnz_e1 + 4 * (e1 + 1))
     return {"E": E, "M+B": M + B, "F": F, "U": U, "F2": F2}
 
 
@@ -356,12 +389,12 @@ def oracle_prepare(case, ranks, threads, log=None):
     from blastamr_b200 import mesh as M
     from oracle import oracle as O
     O.set_threads(threads)
-    lcap = MAX_LEVEL if case.workload == "S2" else 1
+    lcap = MAX_LEVEL if case.graded else 1
     oc = M.Octree(case.base, case.base, case.base, (1.0, 1.0, 1.0), lcap)
-    path = OraclePath()
+    path = OraclePath(case)
     build_initial(oc, path, case, log)
     path.close()
-    g0 = oc.build(points=False)
+    g0 = oc.build(points=case.poly, faces=case.poly)
 
     def split(g):
         if ranks > 1:
@@ -374,13 +407,13 @@ def oracle_prepare(case, ranks, threads, log=None):
     w = O.World(loc0)
     e = w.estimate("delta", xs)
     w.normalize_world(e, *THRS)
-    rc, rs, sw = w.hex_select_refine(e, MAX_LEVEL, LAYERS_REF)
+    rc, rs, sw = oracle_select_refine(w, case, e)
     if ranks > 1:
         cells = np.sort(np.concatenate([l.cell_global[np.flatnonzero(s_)] for l, s_ in zip(loc0, rs)])).astype(np.int32)
     else:
         cells = np.flatnonzero(rs[0]).astype(np.int32)
     cm_g = oc.refine(cells)
-    g1 = oc.build(points=True)
+    g1 = oc.build(points=True, faces=case.poly)
     loc1 = split(g1)
     w1 = O.World(loc1)
     cms, revs = [], []
@@ -388,12 +421,12 @@ def oracle_prepare(case, ranks, threads, log=None):
         cm, rv = local_maps(g0.n, g1.n, cm_g, l0.cell_global if ranks > 1 else None, l1.cell_global if ranks > 1 else None)
         cms.append(cm); revs.append(rv)
     f3 = [np.stack([a, 2 * a, -a], axis=1).copy() for a in xs]
-    S = dict(O=O, w=w, w1=w1, xs=xs, f3=f3, cms=cms, revs=revs, n0=int(g0.n),
+    S = dict(O=O, w=w, w1=w1, case=case, xs=xs, f3=f3, cms=cms, revs=revs, n0=int(g0.n),
              new1=[np.empty(len(c)) for c in cms], new3=[np.empty((len(c), 3)) for c in cms], err1=[np.empty(len(c)) for c in cms])
     # first pass of the unrefinement branch -> the merge maps
     w.map_field_world(cms, e, S["err1"], 1)
     rc1 = [O.remap_refine_cell(cm, rv, r) for cm, rv, r in zip(cms, revs, rc)]
-    up, _, sw2 = w1.hex_select_unrefine(S["err1"], rc1, LAYERS_UNREF)
+    up, _, sw2 = oracle_select_unrefine(w1, case, S["err1"], rc1)
     cm2s = [unrefine_maps(l1.pc_off, l1.pc_cells, np.flatnonzero(u), l1.n)[0] for l1, u in zip(loc1, up)]
     S.update(cm2s=cm2s, x2=[np.empty(len(c)) for c in cm2s], u2=[np.empty((len(c), 3)) for c in cm2s], err2=[np.empty(len(c)) for c in cm2s],
              n_refine=int(len(cells)), n_unrefine=int(sum(int(u.sum()) for u in up)), sweeps_refine=int(sw), sweeps_unrefine=int(sw2),
@@ -406,13 +439,13 @@ def oracle_step(S):
     O, w, w1 = S["O"], S["w"], S["w1"]
     e = w.estimate("delta", S["xs"])
     w.normalize_world(e, *THRS)
-    rc, rs, sw = w.hex_select_refine(e, MAX_LEVEL, LAYERS_REF)
+    rc, rs, sw = oracle_select_refine(w, S["case"], e)
     cms = S["cms"]
     w.map_field_world(cms, S["xs"], S["new1"], 1)
     w.map_field_world(cms, S["f3"], S["new3"], 3)
     w.map_field_world(cms, e, S["err1"], 1)
     rc1 = [O.remap_refine_cell(cm, rv, r) for cm, rv, r in zip(cms, S["revs"], rc)]
-    up, sp, sw2 = w1.hex_select_unrefine(S["err1"], rc1, LAYERS_UNREF)
+    up, sp, sw2 = oracle_select_unrefine(w1, S["case"], S["err1"], rc1)
     cm2s = S["cm2s"]
     w1.map_field_world(cm2s, S["new1"], S["x2"], 1)
     w1.map_field_world(cm2s, S["new3"], S["u2"], 3)
@@ -459,12 +492,13 @@ def run_reference(args):
 # ------------------------------------------------------------------------------- multi-rank plumbing (host side)
 
 MESH_KEYS = ("owner", "neighbour", "cc", "pc_off", "pc_cells", "bnd_point", "cell_level", "point_level", "visible", "split_parent",
-             "cell_global", "point_global")
+             "cell_global", "point_global", "cp_off", "cp_pts", "edge_pts", "ec_off", "ec_cells", "bnd_edge", "face_off", "face_pts",
+             "patch_pt_off", "patch_pts")
 
 
 def mesh_pack(m):
     d = {k: getattr(m, k) for k in MESH_KEYS if getattr(m, k, None) is not None}
-    d["_sizes"] = np.array([m.n, m.f, m.b, m.p], dtype=np.int64)
+    d["_sizes"] = np.array([m.n, m.f, m.b, m.p, int(getattr(m, "n_edges", 0) or 0)], dtype=np.int64)
     st, sz, ty, nb = m.patch_arrays()
     d["_patches"] = np.stack([st, sz, ty, nb]).astype(np.int32)
     return d
@@ -472,7 +506,7 @@ def mesh_pack(m):
 
 def mesh_unpack(d):
     from blastamr_b200 import mesh as M
-    n, f, b, p = (int(v) for v in d["_sizes"])
+    n, f, b, p, ne = (int(v) for v in d["_sizes"])
     pa = d["_patches"]
     patches = [M.Patch(f"patch{i}" if int(pa[2, i]) != 2 else f"procBoundaryTo{int(pa[3, i])}", int(pa[2, i]), int(pa[0, i]),
                        int(pa[1, i]), int(pa[3, i])) for i in range(pa.shape[1])]
@@ -482,6 +516,7 @@ def mesh_unpack(d):
             setattr(m, k, d[k])
     if m.split_parent is None:
         m.split_parent = np.zeros(0, np.int32)
+    m.n_edges = ne
     return m
 
 
@@ -513,7 +548,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="S2", choices=["S1", "S2"])
+    ap.add_argument("--workload", default="S2", choices=["S1", "S2", "P2"])
     ap.add_argument("--base", type=int, default=None, help="level-0 cells per side of the box (S2 default 176 -> ~64 M leaves; S1 default 400)")
     ap.add_argument("--cells", type=int, default=None, help="alias of --base (round-1 flag)")
     ap.add_argument("--shift-cells", type=float, default=4.0, help="S2: displacement of the front in level-3 cells")
@@ -526,7 +561,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.base is None:
-        args.base = args.cells if args.cells else (176 if args.workload == "S2" else 400)
+        args.base = args.cells if args.cells else {"S2": 176, "P2": 64}.get(args.workload, 400)
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -550,7 +585,7 @@ def main():
         gl = dist.new_group(backend="gloo", timeout=datetime.timedelta(hours=1))     # host-side hand-over of the sub-domains
     procs = PROCS.get(world, (world, 1, 1))
     case = Case(args.workload, args.base, args.shift_cells)
-    lcap = MAX_LEVEL if case.workload == "S2" else 1
+    lcap = MAX_LEVEL if case.graded else 1
     host_binding = bind_host_threads(local_rank, world) if (world > 1 and rank != 0) else {"cores": len(os.sched_getaffinity(0)), "note": "rank 0 keeps all cores for the host topology engine"}
 
     def log(s):
@@ -594,12 +629,13 @@ def main():
     g0 = None
     if rank == 0:
         oc = M.Octree(case.base, case.base, case.base, (1.0, 1.0, 1.0), lcap)
-        gser = GpuPath(local_rank)
+        gser = GpuPath(local_rank, case)
         build_info = build_initial(oc, gser, case, log)
-        g0 = oc.build(points=False)
+        g0 = oc.build(points=case.poly, faces=case.poly)
         log(f"M0 built: {g0.n} cells")
     mesh0, cgs0 = hand_over(g0, "M0")
     n, f, b = mesh0.n, mesh0.f, mesh0.b
+    edges0 = (int(getattr(mesh0, "n_edges", 0) or 0), int(mesh0.ec_off[-1]) if getattr(mesh0, "ec_off", None) is not None else 0)
     ctx.set_mesh(mesh0)
     x_host = np.ascontiguousarray(case.field(mesh0.cc))
     x = torch.from_numpy(x_host).to(dev)
@@ -608,7 +644,7 @@ def main():
 
     # first pass (untimed): the decision, then the host topology engine cuts M0 -> M1 and hands back the real cellMap
     ctx.estimate("delta", x, thresholds=THRS, keep_resident=True)
-    cells_first, _ = ctx.select_refine(None, MAX_LEVEL, LAYERS_REF, cells_out=np.empty(max(n, 1), dtype=np.int32))
+    cells_first, _ = ctx.select_refine(None, MAX_LEVEL, case.layers_ref, kind=case.kind, cells_out=np.empty(max(n, 1), dtype=np.int32))
     cells_first = cells_first.copy()
     gcells = mesh0.cell_global[cells_first] if world > 1 else cells_first
     decomposition_independent = None
@@ -632,7 +668,7 @@ def main():
         del g0
         gser.close()
         cm_g = oc.refine(gcells_all.copy())
-        g1 = oc.build(points=True)
+        g1 = oc.build(points=True, faces=case.poly)
         n1_glob = int(g1.n)
         log(f"M1 built: {g1.n} cells")
     del mesh0
@@ -657,6 +693,8 @@ def main():
     del g1
     n1, f1, b1, p1 = mesh1.n, mesh1.f, mesh1.b, mesh1.p
     nnz_pc1 = int(mesh1.pc_off[p1])
+    edges1 = (int(getattr(mesh1, "n_edges", 0) or 0), int(mesh1.ec_off[-1]) if getattr(mesh1, "ec_off", None) is not None else 0)
+    nnz_f1 = int(mesh1.face_off[-1]) if getattr(mesh1, "face_off", None) is not None else 0
     ctx1.set_mesh(mesh1)
     cell_map = torch.from_numpy(cell_map_h).to(dev)
     rev_map = torch.from_numpy(rev_h).to(dev)
@@ -669,10 +707,10 @@ def main():
     pts_dev = torch.empty(max(p1, 1), dtype=torch.int32, device=dev)
     # first pass of the unrefinement branch -> the merge map M1 -> M2 (local: the 8 cells around a split point collapse)
     ctx.estimate("delta", x, thresholds=THRS, out=err0)
-    ctx.select_refine(err0, MAX_LEVEL, LAYERS_REF, cells_out=cells_dev, refine_cell_out=rc0)
+    ctx.select_refine(err0, MAX_LEVEL, case.layers_ref, kind=case.kind, cells_out=cells_dev, refine_cell_out=rc0)
     ctx.map_field(cell_map, err0, n_old=n, n_new=n1, ncomp=1, out=err1)
     ctx1.remap_refine_cell(cell_map, rev_map, refine_cell=rc0)
-    pts_first, _ = ctx1.select_unrefine(err1, LAYERS_UNREF, elems_out=np.empty(max(p1, 1), dtype=np.int32))
+    pts_first, _ = ctx1.select_unrefine(err1, case.layers_unref, kind=case.kind, elems_out=np.empty(max(p1, 1), dtype=np.int32))
     pts_first = pts_first.copy()
     cm2_h, _rev2 = unrefine_maps(mesh1.pc_off, mesh1.pc_cells, pts_first, n1)
     n2 = int(len(cm2_h))
@@ -705,10 +743,10 @@ def main():
 
     fa, fa2 = field_args([x, fld3, err0], [new1, new3, err1], [1, 3, 1]), field_args([new1, new3, err1], [x2, u2, err2], [1, 3, 1])
     call_E = ctx.prepare("amr_estimate", capi.EST["delta"], x, None, capi.SMALL, 0.0, 1, thr_arr, err0)
-    call_R = ctx.prepare("amr_select_refine", err0, capi.SQRT_SMALL, capi.GREAT, None, MAX_LEVEL, LAYERS_REF, no_ids, 0, capi.LABEL_MAX,
-                         capi.HEX3D, rc0, cells_dev, C.byref(cnt_r), C.byref(sw_r))
+    call_R = ctx.prepare("amr_select_refine", err0, capi.SQRT_SMALL, capi.GREAT, None, MAX_LEVEL, case.layers_ref, no_ids, 0, capi.LABEL_MAX,
+                         case.kind, rc0, cells_dev, C.byref(cnt_r), C.byref(sw_r))
     call_F = ctx1.prepare("amr_map_fields_and_marking", n, n1, cell_map, 3, fa[0], fa[1], fa[2], rev_map, rc0, None)
-    call_U = ctx1.prepare("amr_select_unrefine", err1, -capi.SQRT_SMALL, None, LAYERS_UNREF, no_ids, 0, capi.HEX3D, pts_dev,
+    call_U = ctx1.prepare("amr_select_unrefine", err1, -capi.SQRT_SMALL, None, case.layers_unref, no_ids, 0, case.kind, pts_dev,
                           C.byref(cnt_u), C.byref(sw_u))
     call_F2 = ctx1.prepare("amr_map_fields_and_marking", n1, n2, cell_map2, 3, fa2[0], fa2[1], fa2[2], None, None, None)
 
@@ -776,11 +814,11 @@ def main():
             # lists out); the path's own intermediates (error, refineCell) stay on the device between the calls, as
             # INTEGRATION.md prescribes for the drop-in.
             ctx.estimate("delta", xh.numpy(), thresholds=THRS, out=err0)
-            cl, _ = ctx.select_refine(err0, MAX_LEVEL, LAYERS_REF, cells_out=cells_h2, refine_cell_out=rc0)
+            cl, _ = ctx.select_refine(err0, MAX_LEVEL, case.layers_ref, kind=case.kind, cells_out=cells_h2, refine_cell_out=rc0)
             ctx.map_fields(cmh.numpy(), [xh.numpy(), f3h.numpy()], n, n1, [1, 3], [n1h.numpy(), n3h.numpy()])
             ctx.map_field(cell_map, err0, n_old=n, n_new=n1, ncomp=1, out=err1)
             ctx1.remap_refine_cell(cell_map, rev_map, refine_cell=rc0)
-            pl, _ = ctx1.select_unrefine(err1, LAYERS_UNREF, elems_out=pts_h)
+            pl, _ = ctx1.select_unrefine(err1, case.layers_unref, kind=case.kind, elems_out=pts_h)
             ctx1.map_fields(cm2h.numpy(), [n1h.numpy(), n3h.numpy()], n1, n2, [1, 3], [x2h.numpy(), u2h.numpy()])
             ctx1.map_field(cell_map2, err1, n_old=n1, n_new=n2, ncomp=1, out=err2)
             return len(cl), len(pl)
@@ -803,7 +841,7 @@ def main():
     # ---- reduced-size instance of the same case against the CPU oracle (every rank checks its own sub-domain)
     parity = None
     if not args.no_parity:
-        parity = parity_check(args, case.workload, world, rank, local_rank, procs, ctx, ctx1, capi, M)
+        parity = parity_check(args, case, world, rank, local_rank, procs, ctx, ctx1, capi, M)
 
     # ---- max / sums over ranks
     if world > 1:
@@ -827,7 +865,8 @@ def main():
         lists_ok = bool((S[:, 7] == 0).all())
         parities = [a[2] for a in allsums]
         value = n_total / (ms_per_step / 1e3) / 1e6
-        ab = algorithmic_bytes((n, f), (n1, f1, p1, nnz_pc1), n2, info["sweeps_refine"], info["sweeps_unrefine"])
+        ab = algorithmic_bytes((n, f), (n1, f1, p1, nnz_pc1), n2, info["sweeps_refine"], info["sweeps_unrefine"], case,
+                               (edges0, edges1, nnz_f1))
         # measured DRAM bytes per stage of THIS command line (ncu --set full capture committed under profiles/), when the
         # capture matches the configuration; the roofline fractions of the stages and of the step come from these
         traffic = None
@@ -910,19 +949,20 @@ def main():
         dist.destroy_process_group()
 
 
-def parity_check(args, workload, world, rank, local_rank, procs, ctx, ctx1, capi, M):
+def parity_check(args, case, world, rank, local_rank, procs, ctx, ctx1, capi, M):
     """A reduced-size instance of the same case (same build-up, same moved front, same decomposition), the CUDA path
     against the CPU oracle: error field, refineCell, cellsToRefine, mapped fields, remapped refineCell, split points,
     merged fields.  Every rank builds the small global mesh itself (deterministic), runs the oracle world of ALL ranks
     and compares its own sub-domain.  Collective."""
     from oracle import oracle as O
+    workload = case.workload
     small = Case(workload, args.parity_base, args.shift_cells)
-    lcap = MAX_LEVEL if workload == "S2" else 1
+    lcap = MAX_LEVEL if small.graded else 1
     oc = M.Octree(small.base, small.base, small.base, (1.0, 1.0, 1.0), lcap)
-    ser = GpuPath(local_rank)
+    ser = GpuPath(local_rank, small)
     build_initial(oc, ser, small)
     ser.close()
-    g0 = oc.build(points=False)
+    g0 = oc.build(points=small.poly, faces=small.poly)
 
     def split(g):
         if world > 1:
@@ -934,7 +974,7 @@ def parity_check(args, workload, world, rank, local_rank, procs, ctx, ctx1, capi
     xs = [np.ascontiguousarray(small.field(l.cc)) for l in loc0]
     e = w.estimate("delta", xs)
     w.normalize_world(e, *THRS)
-    rc, rs, _ = w.hex_select_refine(e, MAX_LEVEL, LAYERS_REF)
+    rc, rs, _ = oracle_select_refine(w, small, e)
     m0 = loc0[rank]
     ctx.set_mesh(m0)
     fails = []
@@ -942,7 +982,7 @@ def parity_check(args, workload, world, rank, local_rank, procs, ctx, ctx1, capi
     if not np.array_equal(e[rank], eg):
         fails.append("error field")
     rc_g = np.zeros(m0.n, np.uint8)
-    cells, _ = ctx.select_refine(eg, MAX_LEVEL, LAYERS_REF, refine_cell_out=rc_g)
+    cells, _ = ctx.select_refine(eg, MAX_LEVEL, small.layers_ref, kind=small.kind, refine_cell_out=rc_g)
     if not np.array_equal(rc[rank], rc_g):
         fails.append("refineCell")
     if not np.array_equal(np.flatnonzero(rs[rank]), cells):
@@ -952,7 +992,7 @@ def parity_check(args, workload, world, rank, local_rank, procs, ctx, ctx1, capi
     else:
         gc = np.flatnonzero(rs[0]).astype(np.int32)
     cm_g = oc.refine(gc)
-    g1 = oc.build(points=True)
+    g1 = oc.build(points=True, faces=small.poly)
     loc1 = split(g1)
     w1 = O.World(loc1)
     cms, revs = [], []
@@ -973,8 +1013,8 @@ def parity_check(args, workload, world, rank, local_rank, procs, ctx, ctx1, capi
     ctx1.remap_refine_cell(cms[rank], revs[rank], refine_cell=rc_g, out=rc1_g)
     if not np.array_equal(rc1s[rank], rc1_g):
         fails.append("refineCell through the map")
-    up, _, _ = w1.hex_select_unrefine(err1s, [r.copy() for r in rc1s], LAYERS_UNREF)
-    pts, _ = ctx1.select_unrefine(err1, LAYERS_UNREF, refine_cell=rc1_g.copy())
+    up, _, _ = oracle_select_unrefine(w1, small, err1s, [r.copy() for r in rc1s])
+    pts, _ = ctx1.select_unrefine(err1, small.layers_unref, kind=small.kind, refine_cell=rc1_g.copy())
     if not np.array_equal(np.flatnonzero(up[rank]), pts):
         fails.append("split points")
     cm2, _ = unrefine_maps(m1.pc_off, m1.pc_cells, pts, m1.n)

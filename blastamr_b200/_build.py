@@ -111,10 +111,7 @@ def build_all(force: bool = False):
     build_cuda(force)
     build_host(force)
     if ORACLE_DIR.exists():
-        build_oracle(force)
-        ref_mk = ORACLE_DIR / "build_ref.sh"
-        if ref_mk.exists() and Path("/root/reference").exists():
-            subprocess.run(["bash", str(ref_mk)], check=False)
+        build_oracle(force)        # (no oracle/_ref: the reference needs OpenFOAM + wmake and cannot be compiled here)
 
 
 if __name__ == "__main__":

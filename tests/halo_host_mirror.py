@@ -1,4 +1,4 @@
-"""Processor-patch halo plan (host side).  Mirrors what libamr_b200.so does over NCCL in
+"""TEST SUPPORT (not part of the product): processor-patch halo plan on the host.  Mirrors what libamr_b200.so does over NCCL in
 haloExchange(): for every processor patch send the boundary-face values of the patch's face range
 and receive the neighbour's into the same range (syncTools::swapBoundaryFaceList semantics:
 non-coupled boundary faces keep their own value).  The torch.distributed version below runs on any
@@ -9,7 +9,7 @@ from typing import List, Tuple
 
 import numpy as np
 
-from .mesh import PATCH_PROCESSOR, PolyMesh
+from blastamr_b200.mesh import PATCH_PROCESSOR, PolyMesh
 
 
 def halo_plan(mesh: PolyMesh) -> List[Tuple[int, int, int]]:

@@ -23,7 +23,7 @@ def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
     from blastamr_b200 import mesh as M
-    from blastamr_b200.halo import halo_plan, swap_boundary
+    from tests.halo_host_mirror import halo_plan, swap_boundary
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -115,7 +115,7 @@ def _point_worker(rank, world, procs, port, q):
     import torch
     import torch.distributed as dist
     from blastamr_b200 import mesh as M
-    from blastamr_b200.halo import point_plan, sync_points_or
+    from tests.halo_host_mirror import point_plan, sync_points_or
     from oracle import oracle as O
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
