@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "kernels_pipe.cuh"
 #include "kernels_sparse.cuh"
+#include "kernels_linked.cuh"
 #include "lohner.cuh"
 #include "fields.cuh"
 #include "p2p.cuh"
@@ -117,6 +118,7 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
 static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->owner); devFree(ctx, &ctx->neighbour); devFree(ctx, &ctx->bCoupled);
     devFree(ctx, &ctx->cplFace); devFree(ctx, &ctx->cplCell); devFree(ctx, &ctx->cellGhost); ctx->nCplCells = 0;
+    devFree(ctx, &ctx->lkOff); devFree(ctx, &ctx->lkDst); ctx->haveLink = false;
     sellFree(ctx, ctx->cc); sellFree(ctx, ctx->pc);
     devFree(ctx, &ctx->bndPoint); devFree(ctx, &ctx->pcClass); devFree(ctx, &ctx->candList); ctx->pcClassDirty = true; ctx->balancedLocal = -1;
     devFree(ctx, &ctx->lvl); devFree(ctx, &ctx->lvl8); devFree(ctx, &ctx->parentIdx); devFree(ctx, &ctx->pointLevel);
@@ -370,6 +372,44 @@ static int peerPlan(amr_ctx *ctx) {
     return AMR_OK;
 }
 
+// Push-on-change addressing of the linked closure loops (kernels_linked.cuh): for every cell that owns processor faces,
+// where its value lives in the neighbours' ghost arrays.  Host bookkeeping, once per mesh, after peerPlan.
+static int linkPlan(amr_ctx *ctx, const std::vector<label> &bOwn, const std::vector<label> &cells) {
+    devFree(ctx, &ctx->lkOff); devFree(ctx, &ctx->lkDst);
+    ctx->haveLink = false;
+    if (!ctx->usePeer || !ctx->havePlan) return AMR_OK;
+    const char *e = getenv("AMR_B200_LINKED");               // tuning / A-B: 0 = three launches per iteration (same on every rank)
+    if (e && atoi(e) == 0) return AMR_OK;
+    const HaloPlan &P = *(const HaloPlan *)ctx->haloPlan;
+    const size_t nCpl = cells.size();
+    std::vector<int32_t> off(nCpl + 1, 0);
+    std::vector<unsigned> dst((size_t)(ctx->nCoupled > 0 ? ctx->nCoupled : 1), 0u);
+    auto slot = [&](label c) { return (size_t)(std::lower_bound(cells.begin(), cells.end(), c) - cells.begin()); };
+    for (int q = 0; q < P.nPatch; q++)
+        for (int k = 0; k < P.size[q]; k++) off[slot(bOwn[(size_t)(P.offMine[q] + k)]) + 1]++;
+    for (size_t i = 0; i < nCpl; i++) off[i + 1] += off[i];
+    std::vector<int32_t> fill(off.begin(), off.end() - 1);
+    for (int q = 0; q < P.nPatch; q++)
+        for (int k = 0; k < P.size[q]; k++) {
+            const int64_t there = (int64_t)P.offTheirs[q] + k;
+            if (there >= kHaloCap) FAIL(AMR_ERR_STATE, "linkPlan: ghost offset outside the parity buffer");
+            dst[(size_t)fill[slot(bOwn[(size_t)(P.offMine[q] + k)])]++] = ((unsigned)P.nbr[q] << 26) | (unsigned)there;
+        }
+    TRY(devAlloc(ctx, &ctx->lkOff, (int64_t)nCpl + 1));
+    TRY(devAlloc(ctx, &ctx->lkDst, (int64_t)dst.size()));
+    CK(cudaMemcpy(ctx->lkOff, off.data(), (nCpl + 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->lkDst, dst.data(), dst.size() * 4, cudaMemcpyHostToDevice));
+    ctx->haveLink = true;
+    return AMR_OK;
+}
+// the closure loops run linked when the peer transport is planned for this mesh (agreed over the ranks in peerPlan)
+static inline bool linkedOk(const amr_ctx *ctx) { return ctx->comm && ctx->nranks > 1 && ctx->usePeer && ctx->havePlan && ctx->haveLink; }
+static LinkOut makeLinkOut(const amr_ctx *ctx) {
+    LinkOut L;
+    L.cplCell = ctx->cplCell; L.off = ctx->lkOff; L.dst = ctx->lkDst; L.cellGhost = ctx->cellGhost; L.nCpl = (int)ctx->nCplCells;
+    return L;
+}
+
 // NCCL transport of a swap (fallback / AMR_B200_HALO=nccl): for every processor patch send
 // my boundary-face values [patchStart-f, +size) and receive the neighbour's into the same range
 // of `recv` (processor patch pairs list their faces in the same order on both sides).
@@ -586,11 +626,12 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     if (b) CK(cudaMemcpyAsync(ctx->bCoupled, coupled.data(), (size_t)b, cudaMemcpyHostToDevice, ctx->stream));
     if (b) CK(cudaMemcpyAsync(ctx->bEmpty, emptyFace.data(), (size_t)b, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<label> bOwn, cells;
     if (ctx->nCoupled > 0) {
         // compact lists of the coupled faces and of the cells that own them (host bookkeeping, once per mesh)
-        std::vector<label> bOwn((size_t)b);
+        bOwn.resize((size_t)b);
         CK(cudaMemcpy(bOwn.data(), ctx->owner + f, (size_t)b * 4, cudaMemcpyDeviceToHost));
-        std::vector<label> faces, cells;
+        std::vector<label> faces;
         faces.reserve((size_t)ctx->nCoupled);
         for (int64_t i = 0; i < b; i++) if (coupled[(size_t)i]) { faces.push_back((label)i); cells.push_back(bOwn[(size_t)i]); }
         std::sort(cells.begin(), cells.end());
@@ -605,6 +646,7 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
         LAUNCH(k_list_to_flags, gridFor(ctx->nCplCells), kThreads, ctx->nCplCells, (const label *)ctx->cplCell, ctx->cellGhost);
     }
     TRY(peerPlan(ctx));
+    TRY(linkPlan(ctx, bOwn, cells));
     TRY(sellBuildCellCells(ctx));
     int64_t m = std::max(n, p);
     ctx->flagCap = m + 16;
@@ -1328,12 +1370,19 @@ static inline unsigned queueGrid(const amr_ctx *ctx) { return (unsigned)(ctx->nu
 
 // One host look at a speculatively enqueued queue loop: sizes of queues [1, issued] (summed over ranks), the list size
 // (optional) and the by-product counts in ONE round trip.  Returns the index of the first empty queue, or 0.
-static int queueLook(amr_ctx *ctx, const int *gq, int issued, const int32_t *dTotal) {
+// the mailbox post rides on the compaction that ends the loop (MailArgs, scan.cuh)
+static MailArgs queueMail(amr_ctx *ctx, const int *gq, int issued) {
+    MailArgs m;
+    m.mb = ctx->mailbox;
+    m.gq = gq; m.nq = issued + 1;
+    m.marked = ctx->dMarked;
+    m.peerError = (ctx->usePeer && ctx->peerTouched) ? (const int *)(ctx->region + kPeerErrOffset) : nullptr;
+    m.seq = ++ctx->mailSeq;
+    return m;
+}
+static int queueLook(amr_ctx *ctx, int issued) {
     Mailbox *mb = ctx->mailbox;
-    const unsigned seq = ++ctx->mailSeq;
-    const int *errWord = (ctx->usePeer && ctx->peerTouched) ? (const int *)(ctx->region + kPeerErrOffset) : nullptr;
-    k_mailbox<<<1, 64, 0, ctx->stream>>>(gq, issued + 1, dTotal, ctx->dMarked, errWord, mb, seq);
-    ctx->launches++;
+    const unsigned seq = ctx->mailSeq;
     CK(cudaGetLastError());
     // poll the mailbox (a PCIe write away) instead of synchronising the stream; fall back to the stream on anything odd
     bool arrived = false;
@@ -1380,8 +1429,20 @@ static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int
     const label *cf = ctx->cplFace, *bo = ctx->owner + ctx->f;
     ListJob job;                          // (queue sizes were cleared by sitesBegin at the start of the call)
     TRY(listTarget(ctx, n, cellsOut, &job));
+    const bool linked = multi && speculate && linkedOk(ctx);
+    const unsigned nFix = linked ? gridFor(std::max<int64_t>(ctx->nCoupled, 1)) : 0u;
+    const LinkOut L = linked ? makeLinkOut(ctx) : LinkOut();
     // sweep 0: the rows of all marked cells
-    {
+    if (linked) {
+        // ONE swap for the whole closure, then one launch per iteration (kernels_linked.cuh)
+        HaloToken halo;
+        if (ctx->nCoupled > 0) TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo));
+        GhostLink G = makeLink(ctx, &halo, ctx->ghost8, true);
+        LAUNCH((k_refine_linked<true>), nFix + gridFor(std::max<int64_t>(n, 1), kThreads * 16), kThreads, G, L, nFix, ctx->nCoupled, cf, bo, n, ctx->cc.sliceOff,
+               ctx->cc.col, (const u8 *)ctx->lvl8, lf, set, ((((uintptr_t)set)) & 15) == 0, (const label *)nullptr, (const int *)nullptr, ctx->queue[1],
+               qc + 1, cap, gq + 1, (const int *)nullptr);
+        ctx->peerTouched = true;
+    } else {
         HaloToken halo;
         if (ctx->nCoupled > 0) TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo));     // lf as it is before the sweep, like the reference's neiLevel
         if (n) LAUNCH(k_refine_push0, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, lf, set,
@@ -1401,6 +1462,16 @@ static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int
             const int j = issued;
             const int *gate = gq + j;
             const int *xgate = speculate ? gate : nullptr;             // host-checked iterations are never dead
+            if (linked) {
+                GhostLink G = makeLink(ctx, nullptr, ctx->ghost8, true);
+                G.ghost = nullptr;                                     // the ghost array is the parity buffer of the closure's swap
+                LAUNCH((k_refine_linked<false>), nFix + queueGrid(ctx), kThreads, G, L, nFix, ctx->nCoupled, cf, bo, n, ctx->cc.sliceOff, ctx->cc.col,
+                       (const u8 *)ctx->lvl8, lf, set, false, (const label *)ctx->queue[j & 1], (const int *)(qc + j), ctx->queue[(j + 1) & 1], qc + j + 1,
+                       cap, gq + j + 1, gate);
+                ctx->peerTouched = true;
+                issued++;
+                continue;
+            }
             HaloToken halo;
             if (ctx->nCoupled > 0) TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo, nullptr, xgate));
             LAUNCH(k_refine_frontier, queueGrid(ctx), kThreads, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, lf, set,
@@ -1413,8 +1484,9 @@ static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int
             }
             issued++;
         }
-        TRY(compactFlags(ctx, set, n, job.dList, &job.dTotal));          // speculative: valid if the loop has converged
-        TRY(queueLook(ctx, gq, issued, job.dTotal));
+        const MailArgs mail = queueMail(ctx, gq, issued);
+        TRY(compactFlagsEx(ctx, set, n, nullptr, nullptr, nullptr, job.dList, &job.dTotal, 0, nullptr, &mail));   // speculative: valid if the loop has converged
+        TRY(queueLook(ctx, issued));
         if (ctx->lookResult) { iters = ctx->lookResult; break; }
         if (issued >= kMaxIter) FAIL(AMR_ERR_INVARIANT, "2:1 closure did not settle (more queue iterations than refinement levels can need)");
         batch = speculate ? 2 : 1;
@@ -1814,8 +1886,19 @@ static int unrefineClosureQueue(amr_ctx *ctx, const double *dErr, double unrefin
     TRY(compactFlagsEx(ctx, spFlag, nSp, nullptr, nullptr, nullptr, ctx->spList, &nList, 1, nullptr));
     const unsigned qg = queueGrid(ctx);
     if (nSp) LAUNCH(k_sp_to_cells, qg, kThreads, (const label *)ctx->spList, (const int32_t *)nList, nSp, (const label *)ctx->spCells, uc);
+    const bool linked = multi && speculate && linkedOk(ctx);
+    const unsigned nFix = linked ? gridFor(std::max<int64_t>(ctx->nCoupled, 1)) : 0u;
+    const LinkOut L = linked ? makeLinkOut(ctx) : LinkOut();
     // sweep 0
-    {
+    if (linked) {
+        HaloToken halo;
+        if (ctx->nCoupled > 0) TRY(haloBegin(ctx, ctx->lvl8, 1, ctx->ghost8, &halo, uc));     // cellLevel - unrefineCell (hexRef3D.C:1843-1853)
+        GhostLink G = makeLink(ctx, &halo, ctx->ghost8, true);
+        LAUNCH((k_unref_linked<true>), nFix + qg, kThreads, G, L, nFix, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, nSp, (const label *)ctx->spCells,
+               (const label *)ctx->cellSp, spFlag, uc, (const label *)ctx->spList, (const int *)nList, ctx->cc.sliceOff, ctx->cc.col, ctx->queue[1], qc + 1,
+               cap, gq + 1, (const int *)nullptr);
+        ctx->peerTouched = true;
+    } else {
         HaloToken halo;
         if (ctx->nCoupled > 0) TRY(haloBegin(ctx, ctx->lvl8, 1, ctx->ghost8, &halo, uc));     // cellLevel - unrefineCell (hexRef3D.C:1843-1853)
         if (nSp) LAUNCH(k_unref_sweep0, qg, kThreads, (const label *)ctx->spList, (const int32_t *)nList, nSp, (const label *)ctx->spCells,
@@ -1835,6 +1918,16 @@ static int unrefineClosureQueue(amr_ctx *ctx, const double *dErr, double unrefin
             const int j = issued;
             const int *gate = gq + j;
             const int *xgate = speculate ? gate : nullptr;
+            if (linked) {
+                GhostLink G = makeLink(ctx, nullptr, ctx->ghost8, true);
+                G.ghost = nullptr;
+                LAUNCH((k_unref_linked<false>), nFix + qg, kThreads, G, L, nFix, ctx->nCoupled, cf, bo, (const u8 *)ctx->lvl8, nSp, (const label *)ctx->spCells,
+                       (const label *)ctx->cellSp, spFlag, uc, (const label *)ctx->queue[j & 1], (const int *)(qc + j), ctx->cc.sliceOff, ctx->cc.col,
+                       ctx->queue[(j + 1) & 1], qc + j + 1, cap, gq + j + 1, gate);
+                ctx->peerTouched = true;
+                issued++;
+                continue;
+            }
             HaloToken halo;
             if (ctx->nCoupled > 0) TRY(haloBegin(ctx, ctx->lvl8, 1, ctx->ghost8, &halo, uc, xgate));
             LAUNCH(k_unref_frontier, qg, kThreads, (const label *)ctx->queue[j & 1], (const int *)(qc + j), nSp, (const label *)ctx->spCells,
@@ -1848,8 +1941,9 @@ static int unrefineClosureQueue(amr_ctx *ctx, const double *dErr, double unrefin
             issued++;
         }
         // ascending point list of the surviving candidates (speculative: valid if the loop has converged)
-        TRY(compactFlagsEx(ctx, spFlag, nSp, nList, (const label *)ctx->spList, (const label *)ctx->spPoint, job.dList, &job.dTotal, 0, nullptr));
-        TRY(queueLook(ctx, gq, issued, job.dTotal));
+        const MailArgs mail = queueMail(ctx, gq, issued);
+        TRY(compactFlagsEx(ctx, spFlag, nSp, nList, (const label *)ctx->spList, (const label *)ctx->spPoint, job.dList, &job.dTotal, 0, nullptr, &mail));
+        TRY(queueLook(ctx, issued));
         if (ctx->lookResult) { iters = ctx->lookResult; break; }
         if (issued >= kMaxIter) FAIL(AMR_ERR_INVARIANT, "unrefinement closure did not settle");
         batch = speculate ? 2 : 1;

@@ -107,6 +107,9 @@ struct amr_ctx {
     label *cplCell = nullptr;  // [nCplCells] unique owners of coupled faces, ascending
     int64_t nCplCells = 0;
     u8 *cellGhost = nullptr;   // [n] cell owns a coupled face
+    int32_t *lkOff = nullptr;  // [nCplCells + 1] push-on-change addressing of the linked closure loops (kernels_linked.cuh)
+    unsigned *lkDst = nullptr; // [nCoupled] rank << 26 | byte offset in that rank's ghost array
+    bool haveLink = false;
     Sell cc;                   // cell -> face-neighbour cells (+ ghost slots n + bface for coupled faces)
     Sell pc;                   // point -> cells
     bool havePoints = false;

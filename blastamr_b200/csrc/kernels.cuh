@@ -756,10 +756,10 @@ __device__ __forceinline__ void forEachSet16(const u8 *flags, int64_t N, bool al
 // of an AMR marking) would otherwise be walked serially by ONE thread with its 31 neighbours idle; dealt out, their
 // rows are also read coalesced.  Needs blockDim.x == kThreads.
 template <class Fn>
-__device__ __forceinline__ void forEachSetWarp(const u8 *flags, int64_t N, bool aligned, Fn fn) {
+__device__ __forceinline__ void forEachSetWarpAt(unsigned block, const u8 *flags, int64_t N, bool aligned, Fn fn) {
     __shared__ unsigned short setIdx[kThreads / 32][512];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t warpBase = ((int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31)) * 16;
+    const int64_t warpBase = ((int64_t)block * kThreads + (threadIdx.x & ~31)) * 16;
     if (warpBase >= N) return;                                     // whole warp out of range
     const int64_t base = warpBase + (int64_t)lane * 16;
     unsigned mask = 0;
@@ -794,6 +794,10 @@ __device__ __forceinline__ void forEachSetWarp(const u8 *flags, int64_t N, bool 
     __syncwarp();
     for (int i = lane; i < total; i += 32) fn(warpBase + setIdx[warp][i]);
     __syncwarp();
+}
+template <class Fn>
+__device__ __forceinline__ void forEachSetWarp(const u8 *flags, int64_t N, bool aligned, Fn fn) {
+    forEachSetWarpAt(blockIdx.x, flags, N, aligned, fn);
 }
 
 // unrefineCell = union of pointCells over flagged points (hexRef3D.C:1763-1776); cells pre-zeroed

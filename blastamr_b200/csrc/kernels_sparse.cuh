@@ -396,12 +396,21 @@ k_unref_frontier(const label *__restrict__ qIn, const int *__restrict__ qInCount
         const int w = sliceOff[(q >> 5) + 1] - b0;
         const int32_t *row = col + ((size_t)b0 << 5) + (q & 31);
         const int lq = lvl8[q];
-        for (int j = 0; j < w; j++) {
-            const int32_t c = row[(size_t)j << 5];
-            if (c != q && uc[c] && (int)lvl8[c] < lq) {
-                const label sp = cellSp[c];
-                if (sp >= 0) knockPoint(sp, nSp, spCells, spFlag, uc, qOut, qOutCount, qCap);
-            }
+        // 8 neighbours per round, loads batched (labels, then flags + levels, then the split points of the hits): the walk
+        // is a chain of dependent gathers and the queues are short, so this kernel runs at the latency of one chain
+        for (int j0 = 0; j0 < w; j0 += 8) {
+            int32_t c[8];
+            unsigned uq[8], lc[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) c[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : q;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { uq[k] = uc[c[k]]; lc[k] = lvl8[c[k]]; }
+            label sp[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) sp[k] = (c[k] != q && uq[k] && (int)lc[k] < lq) ? cellSp[c[k]] : -1;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (sp[k] >= 0) knockPoint(sp[k], nSp, spCells, spFlag, uc, qOut, qOutCount, qCap);
         }
     }
 }

@@ -124,10 +124,22 @@ constexpr int kLbTile = kThreads * 16 * kLbGroups;             // 16384 flags pe
 __device__ __forceinline__ unsigned long long packStatus(unsigned tag, unsigned flag, unsigned value) {
     return ((unsigned long long)((tag << 2) | flag) << 32) | value;
 }
+// mail (optional): the tile that learns the total also posts the results of the speculative loop that ends with this
+// compaction -- queue sizes, list size, by-product counts, peer error word -- to the pinned mailbox the host polls
+// (Mailbox, common.cuh): no separate mailbox launch.  The host reads nothing but the mailbox before the stream has
+// drained, and everything that follows is stream-ordered, so posting before the other tiles have scattered is safe.
+struct MailArgs {
+    Mailbox *mb;
+    const int *gq;
+    int nq;
+    const unsigned long long *marked;
+    const int *peerError;
+    unsigned seq;
+};
 __global__ void __launch_bounds__(kThreads)
 k_compact_lb(const u8 *__restrict__ flags, int64_t N, const int32_t *__restrict__ nDev, bool aligned, const label *__restrict__ src,
              const label *__restrict__ map, unsigned long long *status, unsigned *ticket, unsigned tag, int32_t *__restrict__ out,
-             int32_t *__restrict__ total, const int *__restrict__ gate) {
+             int32_t *__restrict__ total, const int *__restrict__ gate, const MailArgs mail) {
     if (gate && *gate == 0) return;
     __shared__ int smem[kThreads / 32 + 1];
     __shared__ unsigned sTile;
@@ -210,6 +222,15 @@ k_compact_lb(const u8 *__restrict__ flags, int64_t N, const int32_t *__restrict_
                 if (total) *total = prefix + tileTotal;
             }
         }
+        if (tile == tiles - 1 && mail.mb) {
+            Mailbox *mb = mail.mb;
+            for (int t = lane; t < mail.nq; t += 32) mb->q[t] = mail.gq[t];
+            if (lane < 16) mb->marked[lane] = (long long)mail.marked[lane];
+            if (lane == 0) { mb->total = prefix + tileTotal; mb->peerError = mail.peerError ? *mail.peerError : 0; }
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) mb->seq = mail.seq;
+        }
     }
     __syncthreads();
     if (out) {
@@ -218,6 +239,22 @@ k_compact_lb(const u8 *__restrict__ flags, int64_t N, const int32_t *__restrict_
             const int64_t base = (int64_t)tile * kLbTile + ((int64_t)g * kThreads + threadIdx.x) * 16;
             unsigned b = bits[g];
             int p = pos[g] + sPrefix;
+            if (src && b && base + 16 <= N) {
+                // list form: the 16 elements again (4 vector loads, L1/L2 hits), then all map gathers of the set entries
+                // at once -- one round of independent loads instead of a dependent src -> map chain per set entry
+                int4 s4[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) s4[k] = reinterpret_cast<const int4 *>(src + base)[k];
+                int e[16] = {s4[0].x, s4[0].y, s4[0].z, s4[0].w, s4[1].x, s4[1].y, s4[1].z, s4[1].w,
+                             s4[2].x, s4[2].y, s4[2].z, s4[2].w, s4[3].x, s4[3].y, s4[3].z, s4[3].w};
+                if (map) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) if ((b >> k) & 1u) e[k] = map[e[k]];
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k++) if ((b >> k) & 1u) out[p++] = e[k];
+                continue;
+            }
             while (b) {
                 const int k = __ffs(b) - 1;
                 b &= b - 1;
@@ -230,7 +267,7 @@ k_compact_lb(const u8 *__restrict__ flags, int64_t N, const int32_t *__restrict_
 
 // flags[N] (bytes, any non-zero value counts) -> ascending indices in `out`; the count is stored to *totalDev (device).
 static int compactFlagsEx(amr_ctx *ctx, const u8 *flags, int64_t N, const int32_t *nDev, const label *src, const label *map,
-                          int32_t *out, int32_t **totalDev, int totalSlot, const int *gate) {
+                          int32_t *out, int32_t **totalDev, int totalSlot, const int *gate, const MailArgs *mail = nullptr) {
     int64_t tiles = (N + kLbTile - 1) / kLbTile;
     if (tiles < 1) tiles = 1;
     if (tiles + 2 > ctx->tileCap) FAIL(AMR_ERR_STATE, "compaction tile buffer too small");
@@ -238,8 +275,10 @@ static int compactFlagsEx(amr_ctx *ctx, const u8 *flags, int64_t N, const int32_
     ctx->scanTag = (ctx->scanTag + 1u) & 0x3fffffffu;
     if (ctx->scanTag == 0) ctx->scanTag = 1;
     int32_t *total = ctx->dTotals + totalSlot;
+    MailArgs noMail;
+    memset(&noMail, 0, sizeof(noMail));
     k_compact_lb<<<(unsigned)tiles, kThreads, 0, ctx->stream>>>(flags, N, nDev, aligned, src, map, ctx->lbStatus, ctx->lbTicket, ctx->scanTag,
-                                                                 out, total, gate);
+                                                                 out, total, gate, mail ? *mail : noMail);
     ctx->launches++;
     traceMark(ctx, "k_compact_lb");
     *totalDev = total;
