@@ -559,6 +559,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-handover", action="store_true", help="skip the topology hand-over timing (amr_mesh_set vs amr_mesh_update)")
     args = ap.parse_args()
     if args.base is None:
         args.base = args.cells if args.cells else {"S2": 176, "P2": 64}.get(args.workload, 400)
@@ -621,6 +622,7 @@ def main():
             return mine, cgs
         return mesh_unpack(recv_arrays(dist, torch, gl, 0)), None
 
+    want_handover = (not args.no_handover) and world == 1 and not case.poly
     # ---- meshes (host bookkeeping, untimed): rank 0 owns the global octree
     t_setup = time.time()
     ctx, ctx1 = new_ctx(), new_ctx()
@@ -631,7 +633,7 @@ def main():
         oc = M.Octree(case.base, case.base, case.base, (1.0, 1.0, 1.0), lcap)
         gser = GpuPath(local_rank, case)
         build_info = build_initial(oc, gser, case, log)
-        g0 = oc.build(points=case.poly, faces=case.poly)
+        g0 = oc.build(points=case.poly or want_handover, faces=case.poly)     # (the hand-over timing carries M0's point addressing)
         log(f"M0 built: {g0.n} cells")
     mesh0, cgs0 = hand_over(g0, "M0")
     n, f, b = mesh0.n, mesh0.f, mesh0.b
@@ -671,7 +673,9 @@ def main():
         g1 = oc.build(points=True, faces=case.poly)
         n1_glob = int(g1.n)
         log(f"M1 built: {g1.n} cells")
-    del mesh0
+    do_handover = want_handover
+    if not do_handover:
+        del mesh0
     mesh1, cgs1 = hand_over(g1, "M1")
     if world > 1:
         if rank == 0:
@@ -696,6 +700,62 @@ def main():
     edges1 = (int(getattr(mesh1, "n_edges", 0) or 0), int(mesh1.ec_off[-1]) if getattr(mesh1, "ec_off", None) is not None else 0)
     nnz_f1 = int(mesh1.face_off[-1]) if getattr(mesh1, "face_off", None) is not None else 0
     ctx1.set_mesh(mesh1)
+    handover = None
+    if do_handover:
+        # N1: what the hand-over of the cut M0 -> M1 costs through the C-ABI -- the whole mesh (amr_mesh_set + points + levels)
+        # against the incremental form (amr_mesh_update + amr_mesh_update_points: maps + dirty rows).  Host arrays are
+        # pageable, as OpenFOAM's are.  The delta itself is what polyTopoChange knows; deriving it here is host bookkeeping.
+        t0 = time.time()
+        delta = M.mesh_delta(mesh0, mesh1, cell_map_h)
+        t_delta = time.time() - t0
+        ctxh = new_ctx()
+        ctxh.set_mesh(mesh0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctxh.update_mesh(mesh1, delta)
+        t_inc = time.perf_counter() - t0
+        xe = np.ascontiguousarray(case.field(mesh1.cc))
+        ea = ctx1.estimate("delta", xe, thresholds=THRS)
+        eb = ctxh.estimate("delta", xe, thresholds=THRS)
+        ca, _ = ctx1.select_refine(ea, MAX_LEVEL, case.layers_ref, kind=case.kind)
+        cb, _ = ctxh.select_refine(eb, MAX_LEVEL, case.layers_ref, kind=case.kind)
+        pa, _ = ctx1.select_unrefine(ea, case.layers_unref, kind=case.kind)
+        pb, _ = ctxh.select_unrefine(eb, case.layers_unref, kind=case.kind)
+        same = bool(np.array_equal(ea, eb) and np.array_equal(ca, cb) and np.array_equal(pa, pb))
+        # the full hand-over, call by call, twice (the second pass runs with every staging buffer in place)
+        st_, sz_, ty_, nb_ = mesh1.patch_arrays()
+        full_parts = []
+        for _rep in range(2):
+            torch.cuda.synchronize()
+            tt = [time.perf_counter()]
+            ctxh.set_mesh_raw(mesh1.n, mesh1.f, mesh1.b, mesh1.p, mesh1.owner, mesh1.neighbour, st_, sz_, ty_, nb_)
+            tt.append(time.perf_counter())
+            ctxh.set_points(mesh1.pc_off, mesh1.pc_cells, mesh1.bnd_point)
+            tt.append(time.perf_counter())
+            ctxh.set_levels(mesh1.cell_level, mesh1.point_level, mesh1.visible, mesh1.split_parent)
+            tt.append(time.perf_counter())
+            full_parts.append([1e3 * (b_ - a_) for a_, b_ in zip(tt[:-1], tt[1:])])
+        t_full = sum(full_parts[-1]) / 1e3
+        # ... and the incremental one again on the warm context: back to M0, then the update
+        ctxh.set_mesh(mesh0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctxh.update_mesh(mesh1, delta)
+        t_inc = min(t_inc, time.perf_counter() - t0)
+        ctxh.close()
+        full_bytes = int(sum(getattr(mesh1, k).nbytes for k in ("owner", "neighbour", "pc_off", "pc_cells", "bnd_point", "cell_level",
+                                                                "point_level", "visible", "split_parent") if getattr(mesh1, k, None) is not None))
+        handover = {"cut": "M0 -> M1 of this step", "full_ms": t_full * 1e3, "incremental_ms": t_inc * 1e3, "full_bytes": full_bytes,
+                    "incremental_bytes": int(delta.nbytes() + 4 * mesh1.b), "dirty_cells": int(len(delta.dirty_cells)),
+                    "dirty_points": int(len(delta.dirty_points)), "cells_new": int(mesh1.n), "points_new": int(mesh1.p),
+                    "decisions_equal_full_hand_over": same, "delta_host_s": t_delta,
+                    "full_ms_by_call": {"passes": full_parts, "calls": ["amr_mesh_set", "amr_mesh_set_points", "amr_levels_set"]},
+                    "note": "amr_mesh_set + amr_mesh_set_points + amr_levels_set of M1 against amr_mesh_update + amr_mesh_update_points from the "
+                            "resident M0 (wall clock of the synchronous C-ABI calls, pageable host arrays); estimate / cellsToRefine / split "
+                            "points on the carried adjacency compared with the fully handed-over context"}
+        log(f"hand-over of the cut: full {t_full * 1e3:.1f} ms, incremental {t_inc * 1e3:.1f} ms ({handover['incremental_bytes'] / 1e6:.0f} MB instead of "
+            f"{full_bytes / 1e6:.0f} MB), decisions equal: {same}; deriving the delta on the host took {t_delta:.1f} s")
+        del delta, xe, ea, eb, mesh0
     cell_map = torch.from_numpy(cell_map_h).to(dev)
     rev_map = torch.from_numpy(rev_h).to(dev)
     assert int(cell_map.numel()) == n1
@@ -928,6 +988,13 @@ def main():
             out["e2e"] = {"value": n_total / (e2e[0] / 1e3) / 1e6, "unit": "Mcells/s", "ms_per_step": e2e[0],
                           "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
                           "note": "per rank bytes of rank 0; host buffers for field, registered fields (both maps) and lists"}
+            if handover:
+                for k, nm in (("incremental_ms", "e2e_with_topology_handover"), ("full_ms", "e2e_with_full_mesh_upload")):
+                    ms = e2e[0] + handover[k]
+                    out[nm] = {"value": n_total / (ms / 1e3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms,
+                               "note": f"e2e step + the hand-over of the step's cut ({k}); the merge of the same step is not included"}
+        if handover:
+            out["handover"] = handover
         if not args.no_cpu and world == 1:
             cb = args.cpu_base or max(8, (case.base // 4) // 2 * 2)
             small = Case(case.workload, cb, case.shift_cells)

@@ -34,6 +34,8 @@ _SIGS = {
     "amr_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "amr_mesh_set": (C.c_int, [C.c_void_p] + [C.c_int64] * 4 + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 4),
     "amr_mesh_set_points": (C.c_int, [C.c_void_p] * 4),
+    "amr_mesh_update": (C.c_int, [C.c_void_p] + [C.c_int64] * 4 + [C.c_void_p] * 2 + [C.c_int64] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 4),
+    "amr_mesh_update_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5),
     "amr_mesh_set_edges": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 4),
     "amr_mesh_set_faces": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "amr_mesh_set_patch_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -218,6 +220,20 @@ class Context:
             nsp = 0 if sp is None else len(sp)
             self._ck(self.L.amr_levels_set(self._h, _ptr(mesh.cell_level), _ptr(mesh.point_level), _ptr(mesh.visible),
                                            _ptr(sp) if nsp else None, nsp))
+
+    def update_mesh(self, mesh, delta):
+        """Incremental hand-over after a topology change (amr_mesh_update + amr_mesh_update_points): `mesh` is the NEW mesh
+        (sizes, boundary owners, patches), `delta` a MeshDelta (blastamr_b200/mesh.py: mesh_delta)."""
+        st, sz, ty, nb = mesh.patch_arrays()
+        d = delta
+        bown = np.ascontiguousarray(mesh.owner[mesh.f:], dtype=np.int32)
+        self._ck(self.L.amr_mesh_update(self._h, mesh.n, mesh.f, mesh.b, mesh.p, _ptr(d.cell_map), _ptr(d.reverse_cell_map), len(d.dirty_cells),
+                                        _ptr(d.dirty_cells), _ptr(d.dirty_cell_off), _ptr(d.dirty_cell_nbrs), _ptr(d.dirty_cell_level),
+                                        _ptr(d.dirty_parent_index), _ptr(bown), len(st), _ptr(st), _ptr(sz), _ptr(ty), _ptr(nb)))
+        self.n, self.f, self.b, self.p = mesh.n, mesh.f, mesh.b, mesh.p
+        if d.point_map is not None:
+            self._ck(self.L.amr_mesh_update_points(self._h, _ptr(d.point_map), len(d.dirty_points), _ptr(d.dirty_points), _ptr(d.dirty_point_off),
+                                                   _ptr(d.dirty_point_cells), _ptr(d.dirty_bnd_point), _ptr(d.dirty_point_level)))
 
     def set_mesh_raw(self, n, f, b, p, owner, neighbour, patch_start, patch_size, patch_type, patch_nbr):
         self._ck(self.L.amr_mesh_set(self._h, n, f, b, p, _ptr(owner), _ptr(neighbour), len(patch_start),

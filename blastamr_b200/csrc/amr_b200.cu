@@ -74,6 +74,13 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
             int a = 0, b = 1;
             if (sscanf(pf, "%d/%d", &a, &b) >= 1 && a >= 0 && b > 0) { ctx->pushNum = a; ctx->pushDen = b; }
         }
+        const char *lf = getenv("AMR_B200_PULL_FRACTION");
+        if (lf) {
+            int a = 0, b = 1;
+            if (sscanf(lf, "%d/%d", &a, &b) >= 1 && a >= 0 && b > 0) { ctx->pullNum = a; ctx->pullDen = b; }
+        }
+        const char *ht = getenv("AMR_B200_HOSTTIME");
+        if (ht && ht[0] == '1') ctx->hostTime = true;
         const char *tr = getenv("AMR_B200_TRACE");
         if (tr && tr[0]) { ctx->traceOn = true; ctx->tracePath = tr; }
         const char *mf = getenv("AMR_B200_MAP");                 // tuning: fused40 (default) | fused | separate
@@ -116,10 +123,14 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
 }
 
 static void freeMesh(amr_ctx *ctx) {
+    if (ctx->bOwnerOwned) devFree(ctx, &ctx->bOwner);
+    ctx->bOwner = nullptr; ctx->bOwnerOwned = false; ctx->meshSet = false; ctx->faceLists = false;
     devFree(ctx, &ctx->owner); devFree(ctx, &ctx->neighbour); devFree(ctx, &ctx->bCoupled);
     devFree(ctx, &ctx->cplFace); devFree(ctx, &ctx->cplCell); devFree(ctx, &ctx->cellGhost); ctx->nCplCells = 0;
     devFree(ctx, &ctx->lkOff); devFree(ctx, &ctx->lkDst); ctx->haveLink = false;
     sellFree(ctx, ctx->cc); sellFree(ctx, ctx->pc);
+    sellFree(ctx, ctx->carry.pcOld); devFree(ctx, &ctx->carry.bndPointOld); devFree(ctx, &ctx->carry.pointLevelOld); devFree(ctx, &ctx->carry.rev);
+    ctx->carry.valid = false;
     devFree(ctx, &ctx->bndPoint); devFree(ctx, &ctx->pcClass); devFree(ctx, &ctx->candList); ctx->pcClassDirty = true; ctx->balancedLocal = -1;
     devFree(ctx, &ctx->lvl); devFree(ctx, &ctx->lvl8); devFree(ctx, &ctx->parentIdx); devFree(ctx, &ctx->pointLevel);
     devFree(ctx, &ctx->protCell);
@@ -139,6 +150,7 @@ static void freeMesh(amr_ctx *ctx) {
     ctx->haveGeom = false;
     sellFree(ctx, ctx->ec); devFree(ctx, &ctx->bndEdge); devFree(ctx, &ctx->edgePts);
     devFree(ctx, &ctx->faceOff); devFree(ctx, &ctx->facePts); ctx->haveFaces = false;
+    devFree(ctx, &ctx->polyBad); ctx->polyBadKind = -1;
     ctx->haveEdges = false; ctx->nEdges = 0;
     ctx->havePoints = ctx->haveLevels = ctx->haveHistory = false;
     ctx->occCache.clear();
@@ -458,7 +470,7 @@ static int haloBegin(amr_ctx *ctx, const void *cells, size_t elemBytes, void *re
         unsigned g = gridFor(P.prefix[P.nPatch]);
         if (elemBytes == 1) g = gridFor(pushWords(P));
         unsigned *counter = (unsigned *)(ctx->dFlags + 6);
-        const label *bOwner = ctx->owner + ctx->f;
+        const label *bOwner = ctx->bOwner;
         if (elemBytes == 1) k_halo_push_cells<1><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, bOwner, (const char *)cells, minus, counter, gate);
         else if (elemBytes == 4) k_halo_push_cells<4><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, bOwner, (const char *)cells, minus, counter, gate);
         else if (elemBytes == 8) k_halo_push_cells<8><<<g, kThreads, 0, ctx->stream>>>(P, ctx->peerDev, ctx->rank, ctx->dSeq, bOwner, (const char *)cells, minus, counter, gate);
@@ -473,11 +485,11 @@ static int haloBegin(amr_ctx *ctx, const void *cells, size_t elemBytes, void *re
     // NCCL path: pack into a send buffer laid out like the boundary-face array, then grouped send/recv (complete here)
     void *send = nullptr;
     TRY(arenaAlloc(ctx, &send, (size_t)b * elemBytes));
-    if (elemBytes == 1 && minus) LAUNCH(k_pack_level_minus, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const u8 *)cells, minus, (u8 *)send);
-    else if (elemBytes == 1) LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const u8 *)cells, (u8 *)send);
-    else if (elemBytes == 4) LAUNCH(k_pack_i32, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const label *)cells, (label *)send);
-    else if (elemBytes == 8) LAUNCH(k_pack_f64, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const double *)cells, (double *)send);
-    else LAUNCH(k_pack_vec3, gridFor(b), kThreads, b, ctx->owner + ctx->f, (const double *)cells, (double *)send);
+    if (elemBytes == 1 && minus) LAUNCH(k_pack_level_minus, gridFor(b), kThreads, b, ctx->bOwner, (const u8 *)cells, minus, (u8 *)send);
+    else if (elemBytes == 1) LAUNCH(k_pack_u8, gridFor(b), kThreads, b, ctx->bOwner, (const u8 *)cells, (u8 *)send);
+    else if (elemBytes == 4) LAUNCH(k_pack_i32, gridFor(b), kThreads, b, ctx->bOwner, (const label *)cells, (label *)send);
+    else if (elemBytes == 8) LAUNCH(k_pack_f64, gridFor(b), kThreads, b, ctx->bOwner, (const double *)cells, (double *)send);
+    else LAUNCH(k_pack_vec3, gridFor(b), kThreads, b, ctx->bOwner, (const double *)cells, (double *)send);
     return haloExchange(ctx, send, recv, elemBytes);
 }
 static int haloEnd(amr_ctx *ctx, HaloToken *tok) {
@@ -582,6 +594,59 @@ AMR_API int amr_synchronize(amr_ctx *ctx) {
 
 // ============================================================================ mesh state
 
+// coupled-face lists, transport plans: everything amr_mesh_set / amr_mesh_update derive from the boundary faces
+// (ctx->bOwner [b] on the device, ctx->patches, ctx->nCoupled are set)
+static int meshBoundarySetup(amr_ctx *ctx, const std::vector<u8> &coupled) {
+    const int64_t n = ctx->n, b = ctx->b;
+    std::vector<label> bOwn, cells;
+    if (ctx->nCoupled > 0) {
+        // compact lists of the coupled faces and of the cells that own them (host bookkeeping, once per mesh)
+        bOwn.resize((size_t)b);
+        CK(cudaMemcpy(bOwn.data(), ctx->bOwner, (size_t)b * 4, cudaMemcpyDeviceToHost));
+        std::vector<label> faces;
+        faces.reserve((size_t)ctx->nCoupled);
+        for (int64_t i = 0; i < b; i++) if (coupled[(size_t)i]) { faces.push_back((label)i); cells.push_back(bOwn[(size_t)i]); }
+        std::sort(cells.begin(), cells.end());
+        cells.erase(std::unique(cells.begin(), cells.end()), cells.end());
+        ctx->nCplCells = (int64_t)cells.size();
+        TRY(devAlloc(ctx, &ctx->cplFace, (int64_t)faces.size()));
+        TRY(devAlloc(ctx, &ctx->cplCell, (int64_t)cells.size()));
+        TRY(devAlloc(ctx, &ctx->cellGhost, n + 16));
+        CK(cudaMemcpy(ctx->cplFace, faces.data(), faces.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->cplCell, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemsetAsync(ctx->cellGhost, 0, (size_t)n + 16, ctx->stream));
+        LAUNCH(k_list_to_flags, gridFor(ctx->nCplCells), kThreads, ctx->nCplCells, (const label *)ctx->cplCell, ctx->cellGhost);
+    }
+    TRY(peerPlan(ctx));
+    TRY(linkPlan(ctx, bOwn, cells));
+    return AMR_OK;
+}
+// per-mesh scratch and resident results; `pending` = a marking remapped through the topology change (amr_remap_refine_cell)
+static int meshScratchAlloc(amr_ctx *ctx, u8 *pending, int64_t pendingN) {
+    const int64_t n = ctx->n, b = ctx->b, p = ctx->p;
+    int64_t m = std::max(n, p);
+    ctx->flagCap = m + 16;
+    TRY(devAlloc(ctx, &ctx->flagA, m + 16)); TRY(devAlloc(ctx, &ctx->flagB, m + 16)); TRY(devAlloc(ctx, &ctx->flagC, m + 16));
+    TRY(devAlloc(ctx, &ctx->lf, n + 16));
+    TRY(devAlloc(ctx, &ctx->error, n));
+    TRY(devAlloc(ctx, &ctx->refineCell, m + 16));
+    TRY(devAlloc(ctx, &ctx->ghost8, b + 16));
+    TRY(devAlloc(ctx, &ctx->ghost64, b + 2));
+    ctx->tileCap = (m + kTile - 1) / kTile + 8;
+    TRY(devAlloc(ctx, &ctx->lbStatus, ctx->tileCap));
+    CK(cudaMemsetAsync(ctx->lbStatus, 0, (size_t)ctx->tileCap * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->refineCell, 0, (size_t)m + 16, ctx->stream));
+    if (pending) {
+        CK(cudaMemcpyAsync(ctx->refineCell, pending, (size_t)pendingN, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaMemsetAsync(ctx->ghost8, 0, (size_t)b + 16, ctx->stream));
+    CK(cudaMemsetAsync(ctx->ghost64, 0, (size_t)(b + 2) * 8, ctx->stream));
+    ctx->refineCellN = n;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMR_OK;
+}
+
 AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t p, const int32_t *owner,
                          const int32_t *neighbour, int npatch, const int32_t *patchStart, const int32_t *patchSize,
                          const int32_t *patchType, const int32_t *patchNbrRank) {
@@ -606,12 +671,14 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
         patches.push_back(q);
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    hostMark(ctx, nullptr);
     // a marking remapped through the topology change (amr_remap_refine_cell) survives the mesh switch
     u8 *pending = nullptr;
     int64_t pendingN = 0;
     if (ctx->refineCell && ctx->refineCellN == n && n > 0) { pending = ctx->refineCell; pendingN = n; ctx->refineCell = nullptr; }
     struct PendingGuard { u8 *&p; ~PendingGuard() { if (p) cudaFree(p); } } pendingGuard{pending};   // freed on every exit path
     freeMesh(ctx);
+    hostMark(ctx, "amr_mesh_set: old mesh released");
     ctx->nTotalCells = -1;
     ctx->anyProtCached = -1;
     ctx->n = n; ctx->f = f; ctx->b = b; ctx->p = p;
@@ -626,48 +693,15 @@ AMR_API int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t 
     if (b) CK(cudaMemcpyAsync(ctx->bCoupled, coupled.data(), (size_t)b, cudaMemcpyHostToDevice, ctx->stream));
     if (b) CK(cudaMemcpyAsync(ctx->bEmpty, emptyFace.data(), (size_t)b, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<label> bOwn, cells;
-    if (ctx->nCoupled > 0) {
-        // compact lists of the coupled faces and of the cells that own them (host bookkeeping, once per mesh)
-        bOwn.resize((size_t)b);
-        CK(cudaMemcpy(bOwn.data(), ctx->owner + f, (size_t)b * 4, cudaMemcpyDeviceToHost));
-        std::vector<label> faces;
-        faces.reserve((size_t)ctx->nCoupled);
-        for (int64_t i = 0; i < b; i++) if (coupled[(size_t)i]) { faces.push_back((label)i); cells.push_back(bOwn[(size_t)i]); }
-        std::sort(cells.begin(), cells.end());
-        cells.erase(std::unique(cells.begin(), cells.end()), cells.end());
-        ctx->nCplCells = (int64_t)cells.size();
-        TRY(devAlloc(ctx, &ctx->cplFace, (int64_t)faces.size()));
-        TRY(devAlloc(ctx, &ctx->cplCell, (int64_t)cells.size()));
-        TRY(devAlloc(ctx, &ctx->cellGhost, n + 16));
-        CK(cudaMemcpy(ctx->cplFace, faces.data(), faces.size() * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(ctx->cplCell, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemsetAsync(ctx->cellGhost, 0, (size_t)n + 16, ctx->stream));
-        LAUNCH(k_list_to_flags, gridFor(ctx->nCplCells), kThreads, ctx->nCplCells, (const label *)ctx->cplCell, ctx->cellGhost);
-    }
-    TRY(peerPlan(ctx));
-    TRY(linkPlan(ctx, bOwn, cells));
+    ctx->bOwner = ctx->owner + f;
+    ctx->meshSet = true; ctx->faceLists = true;
+    hostMark(ctx, "amr_mesh_set: owner/neighbour uploaded");
+    TRY(meshBoundarySetup(ctx, coupled));
+    hostMark(ctx, "amr_mesh_set: boundary set-up");
     TRY(sellBuildCellCells(ctx));
-    int64_t m = std::max(n, p);
-    ctx->flagCap = m + 16;
-    TRY(devAlloc(ctx, &ctx->flagA, m + 16)); TRY(devAlloc(ctx, &ctx->flagB, m + 16)); TRY(devAlloc(ctx, &ctx->flagC, m + 16));
-    TRY(devAlloc(ctx, &ctx->lf, n + 16));
-    TRY(devAlloc(ctx, &ctx->error, n));
-    TRY(devAlloc(ctx, &ctx->refineCell, m + 16));
-    TRY(devAlloc(ctx, &ctx->ghost8, b + 16));
-    TRY(devAlloc(ctx, &ctx->ghost64, b + 2));
-    ctx->tileCap = (m + kTile - 1) / kTile + 8;
-    TRY(devAlloc(ctx, &ctx->lbStatus, ctx->tileCap));
-    CK(cudaMemsetAsync(ctx->lbStatus, 0, (size_t)ctx->tileCap * 8, ctx->stream));
-    CK(cudaMemsetAsync(ctx->refineCell, 0, (size_t)m + 16, ctx->stream));
-    if (pending) {
-        CK(cudaMemcpyAsync(ctx->refineCell, pending, (size_t)pendingN, cudaMemcpyDeviceToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    CK(cudaMemsetAsync(ctx->ghost8, 0, (size_t)b + 16, ctx->stream));
-    CK(cudaMemsetAsync(ctx->ghost64, 0, (size_t)(b + 2) * 8, ctx->stream));
-    ctx->refineCellN = n;
-    CK(cudaStreamSynchronize(ctx->stream));
+    hostMark(ctx, "amr_mesh_set: cell adjacency built");
+    TRY(meshScratchAlloc(ctx, pending, pendingN));
+    hostMark(ctx, "amr_mesh_set: scratch allocated");
     return AMR_OK;
 }
 
@@ -689,7 +723,191 @@ AMR_API int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_
     if (p) TRY(uploadAuto(ctx, ctx->bndPoint, bndPoint, (size_t)p));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->havePoints = true;
+    ctx->pcClassDirty = true; ctx->balancedLocal = -1; ctx->balancedGlobal = -1; ctx->spDirty = true; ctx->polyBadKind = -1;
+    return AMR_OK;
+}
+
+static int growFlagPool(amr_ctx *ctx, int64_t need);
+// ---- N1 (second half): incremental hand-over of the addressing after a topology change ------------------------------
+// hexRef::updateMesh (hexRef.C:2422-2608) and fvMeshHexRefiner::updateMesh (fvMeshHexRefiner.C:229-240) renumber what
+// the refiner keeps through mapPolyMesh; the addressing itself (cells(), pointCells()) is rebuilt by OpenFOAM on demand.
+// amr_mesh_set is that rebuild for the device: it uploads the whole mesh.  amr_mesh_update carries the adjacency the
+// context already holds through the change instead: the host sends the maps it has anyway and the rows that changed.
+static int parsePatches(amr_ctx *ctx, int64_t f, int64_t b, int npatch, const int32_t *patchStart, const int32_t *patchSize, const int32_t *patchType,
+                        const int32_t *patchNbrRank, std::vector<Patch> &patches, std::vector<u8> &coupled, std::vector<u8> &emptyFace, int64_t &nCoupled) {
+    coupled.assign((size_t)(b > 0 ? b : 1), 0); emptyFace.assign((size_t)(b > 0 ? b : 1), 0);
+    nCoupled = 0;
+    for (int i = 0; i < npatch; i++) {
+        if (!patchStart || !patchSize) FAIL(AMR_ERR_ARG, "patch arrays are null");
+        Patch q{patchStart[i], patchSize[i], patchType ? patchType[i] : 0, patchNbrRank ? patchNbrRank[i] : -1};
+        if (q.size < 0 || q.start < f || (int64_t)q.start + q.size > f + b) FAIL(AMR_ERR_ARG, "patch range outside boundary faces");
+        if (q.type == AMR_PATCH_PROCESSOR) {
+            if (ctx->comm && (q.nbr < 0 || q.nbr >= ctx->nranks || q.nbr == ctx->rank)) FAIL(AMR_ERR_ARG, "processor patch with a bad neighbour rank");
+            for (int32_t k = 0; k < q.size; k++) coupled[(size_t)(q.start - f + k)] = 1;
+            nCoupled += q.size;
+        } else if (q.type == AMR_PATCH_EMPTY) {
+            for (int32_t k = 0; k < q.size; k++) emptyFace[(size_t)(q.start - f + k)] = 1;
+        }
+        patches.push_back(q);
+    }
+    return AMR_OK;
+}
+static int fetchInt(amr_ctx *ctx, const int32_t *ptrHostOrDev, int64_t index, int32_t *out) {
+    if (isDevicePtr(ptrHostOrDev)) {
+        CK(cudaMemcpyAsync(out, ptrHostOrDev + index, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else *out = ptrHostOrDev[index];
+    return AMR_OK;
+}
+
+AMR_API int amr_mesh_update(amr_ctx *ctx, int64_t nNew, int64_t fNew, int64_t bNew, int64_t pNew, const int32_t *cellMap,
+                            const int32_t *reverseCellMap, int64_t nDirtyCells, const int32_t *dirtyCells, const int32_t *dirtyCellOff,
+                            const int32_t *dirtyCellNbrs, const int32_t *dirtyCellLevel, const int32_t *dirtyParentIndex,
+                            const int32_t *boundaryOwner, int npatch, const int32_t *patchStart, const int32_t *patchSize,
+                            const int32_t *patchType, const int32_t *patchNbrRank) {
+    ENTER();
+    if (!ctx->meshSet || !ctx->cc.col) FAIL(AMR_ERR_STATE, "amr_mesh_update: no mesh to update (amr_mesh_set first)");
+    if (nNew < 0 || fNew < 0 || bNew < 0 || pNew < 0 || nDirtyCells < 0 || npatch < 0 || (nNew > 0 && !cellMap) || (bNew > 0 && !boundaryOwner))
+        FAIL(AMR_ERR_ARG, "amr_mesh_update: bad sizes/pointers");
+    if (nDirtyCells > 0 && (!dirtyCells || !dirtyCellOff || !dirtyCellNbrs)) FAIL(AMR_ERR_ARG, "amr_mesh_update: dirty rows are null");
+    if (nNew >= ((int64_t)1 << 31) - 2 - bNew) FAIL(AMR_ERR_ARG, "amr_mesh_update: label overflow (n + b must fit int32)");
+    if (ctx->haveLevels && nDirtyCells > 0 && !dirtyCellLevel) FAIL(AMR_ERR_ARG, "amr_mesh_update: the context holds cell levels: dirtyCellLevel is needed");
+    const int64_t nOld = ctx->n;
+    std::vector<u8> coupled, emptyFace;
+    std::vector<Patch> patches;
+    int64_t nCoupled = 0;
+    TRY(parsePatches(ctx, fNew, bNew, npatch, patchStart, patchSize, patchType, patchNbrRank, patches, coupled, emptyFace, nCoupled));
+    hostMark(ctx, nullptr);
+    // inputs (host pointers are staged; the arena lives until the next call)
+    const int32_t *dMap = nullptr, *dRevIn = nullptr, *dDirty = nullptr, *dOff = nullptr, *dNbr = nullptr, *dLvl = nullptr, *dPar = nullptr, *dBOwn = nullptr;
+    int32_t nnz = 0;
+    if (nDirtyCells > 0) TRY(fetchInt(ctx, dirtyCellOff, nDirtyCells, &nnz));
+    if (nnz < 0) FAIL(AMR_ERR_ARG, "amr_mesh_update: bad dirty-row CSR");
+    TRY(stageIn(ctx, cellMap, nNew, &dMap));
+    TRY(stageIn(ctx, reverseCellMap, nOld, &dRevIn));
+    TRY(stageIn(ctx, dirtyCells, nDirtyCells, &dDirty));
+    TRY(stageIn(ctx, dirtyCellOff, nDirtyCells + 1, &dOff));
+    TRY(stageIn(ctx, dirtyCellNbrs, (int64_t)nnz, &dNbr));
+    TRY(stageIn(ctx, dirtyCellLevel, nDirtyCells, &dLvl));
+    TRY(stageIn(ctx, dirtyParentIndex, nDirtyCells, &dPar));
+    TRY(stageIn(ctx, boundaryOwner, bNew, &dBOwn));
+    CK(cudaStreamSynchronize(ctx->stream));
+    hostMark(ctx, "amr_mesh_update: inputs staged");
+    // what survives of the old mesh
+    Sell ccOld = ctx->cc; ctx->cc = Sell();
+    amr_ctx::Carry keep;
+    keep.valid = ctx->havePoints;
+    keep.pcOld = ctx->pc; ctx->pc = Sell();
+    keep.bndPointOld = ctx->bndPoint; ctx->bndPoint = nullptr;
+    keep.pointLevelOld = ctx->pointLevel; ctx->pointLevel = nullptr;
+    label *lvlOld = ctx->lvl, *parentOld = ctx->parentIdx;
+    ctx->lvl = nullptr; ctx->parentIdx = nullptr;
+    const bool hadLevels = ctx->haveLevels, hadHistory = ctx->haveHistory;
+    u8 *pending = nullptr;
+    int64_t pendingN = 0;
+    if (ctx->refineCell && ctx->refineCellN == nNew && nNew > 0) { pending = ctx->refineCell; pendingN = nNew; ctx->refineCell = nullptr; }
+    struct Guard {
+        amr_ctx *c; Sell &cc; amr_ctx::Carry &k; label *&l; label *&q; u8 *&pend; bool armed = true;
+        ~Guard() { if (pend) cudaFree(pend); if (l) cudaFree(l); if (q) cudaFree(q); sellFree(c, cc);
+                   if (armed) { sellFree(c, k.pcOld); if (k.bndPointOld) cudaFree(k.bndPointOld); if (k.pointLevelOld) cudaFree(k.pointLevelOld); if (k.rev) cudaFree(k.rev); } }
+    } guard{ctx, ccOld, keep, lvlOld, parentOld, pending};
+    freeMesh(ctx);
+    hostMark(ctx, "amr_mesh_update: old mesh released");
+    ctx->nTotalCells = -1;
+    ctx->anyProtCached = -1;
+    ctx->n = nNew; ctx->f = fNew; ctx->b = bNew; ctx->p = pNew;
+    ctx->patches = patches;
+    ctx->nCoupled = nCoupled;
+    TRY(devAlloc(ctx, &ctx->bOwner, bNew));
+    ctx->bOwnerOwned = true;
+    TRY(devAlloc(ctx, &ctx->bCoupled, bNew));
+    TRY(devAlloc(ctx, &ctx->bEmpty, bNew));
+    if (bNew) {
+        CK(cudaMemcpyAsync(ctx->bOwner, dBOwn, (size_t)bNew * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->bCoupled, coupled.data(), (size_t)bNew, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->bEmpty, emptyFace.data(), (size_t)bNew, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->meshSet = true; ctx->faceLists = false;
+    TRY(meshBoundarySetup(ctx, coupled));
+    // the renumbering of the cells stays on the device for the point rows (amr_mesh_update_points)
+    if (dRevIn && keep.valid) {
+        CK(cudaMalloc((void **)&keep.rev, (size_t)(nOld > 0 ? nOld : 1) * 4));
+        CK(cudaMemcpyAsync(keep.rev, dRevIn, (size_t)nOld * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    int32_t *dirtyIdx = nullptr;
+    CK(cudaMalloc((void **)&dirtyIdx, (size_t)(nNew > 0 ? nNew : 1) * 4));
+    struct IdxGuard { int32_t *p; ~IdxGuard() { cudaFree(p); } } idxGuard{dirtyIdx};
+    hostMark(ctx, "amr_mesh_update: boundary set-up");
+    TRY(sellCarryOver(ctx, ctx->cc, ccOld, nNew, dMap, dRevIn, nDirtyCells, dDirty, dOff, dNbr, nNew, 1, true, dirtyIdx));
+    hostMark(ctx, "amr_mesh_update: cell adjacency carried over");
+    if (cudaMalloc((void **)&ctx->cc.sliceGhost, (size_t)ctx->cc.slices + 16) == cudaSuccess) {
+        cudaMemsetAsync(ctx->cc.sliceGhost, 0, (size_t)ctx->cc.slices + 16, ctx->stream);
+        if (nNew > 0 && ctx->nCoupled > 0 && ctx->cellGhost) LAUNCH(k_slice_ghost_cells, gridFor(nNew), kThreads, (const u8 *)ctx->cellGhost, nNew, ctx->cc.sliceGhost);
+    }
+    // cellLevel_ and the history's parent index through the change (hexRef.C:2455-2485): kept for the clean cells
+    if (hadLevels && lvlOld) {
+        TRY(devAlloc(ctx, &ctx->lvl, nNew)); TRY(devAlloc(ctx, &ctx->lvl8, nNew + 16)); TRY(devAlloc(ctx, &ctx->parentIdx, nNew));
+        if (nNew) {
+            LAUNCH(k_upd_values<label>, gridFor(nNew), kThreads, nNew, dMap, (const int32_t *)dirtyIdx, dLvl, (const label *)lvlOld, ctx->lvl);
+            LAUNCH(k_lvl_to_u8, gridFor(nNew), kThreads, nNew, ctx->lvl, ctx->lvl8);
+            if (hadHistory && parentOld && (dPar || nDirtyCells == 0))
+                LAUNCH(k_upd_values<label>, gridFor(nNew), kThreads, nNew, dMap, (const int32_t *)dirtyIdx, dPar, (const label *)parentOld, ctx->parentIdx);
+            else CK(cudaMemsetAsync(ctx->parentIdx, 0xFF, (size_t)nNew * 4, ctx->stream));
+        }
+        ctx->haveLevels = true;
+        ctx->haveHistory = hadHistory && parentOld && (dPar || nDirtyCells == 0);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    hostMark(ctx, "amr_mesh_update: levels");
+    TRY(meshScratchAlloc(ctx, pending, pendingN));
+    hostMark(ctx, "amr_mesh_update: scratch allocated");
+    ctx->carry = keep;
+    guard.armed = false;
     ctx->pcClassDirty = true; ctx->balancedLocal = -1; ctx->balancedGlobal = -1; ctx->spDirty = true;
+    return AMR_OK;
+}
+
+AMR_API int amr_mesh_update_points(amr_ctx *ctx, const int32_t *pointMap, int64_t nDirtyPoints, const int32_t *dirtyPoints,
+                                   const int32_t *dirtyPointOff, const int32_t *dirtyPointCells, const uint8_t *dirtyBndPoint,
+                                   const int32_t *dirtyPointLevel) {
+    ENTER();
+    if (!ctx->meshSet || !ctx->carry.valid) FAIL(AMR_ERR_STATE, "amr_mesh_update_points: call amr_mesh_update first (on a context that held point addressing)");
+    const int64_t p = ctx->p;
+    if ((p > 0 && !pointMap) || nDirtyPoints < 0) FAIL(AMR_ERR_ARG, "amr_mesh_update_points: bad arguments");
+    if (nDirtyPoints > 0 && (!dirtyPoints || !dirtyPointOff || !dirtyPointCells || !dirtyBndPoint)) FAIL(AMR_ERR_ARG, "amr_mesh_update_points: dirty rows are null");
+    amr_ctx::Carry &K = ctx->carry;
+    if (K.pointLevelOld && nDirtyPoints > 0 && !dirtyPointLevel) FAIL(AMR_ERR_ARG, "amr_mesh_update_points: the context holds point levels: dirtyPointLevel is needed");
+    const int32_t *dMap = nullptr, *dDirty = nullptr, *dOff = nullptr, *dCells = nullptr, *dPl = nullptr;
+    const u8 *dBnd = nullptr;
+    int32_t nnz = 0;
+    if (nDirtyPoints > 0) TRY(fetchInt(ctx, dirtyPointOff, nDirtyPoints, &nnz));
+    if (nnz < 0) FAIL(AMR_ERR_ARG, "amr_mesh_update_points: bad dirty-row CSR");
+    TRY(stageIn(ctx, pointMap, p, &dMap));
+    TRY(stageIn(ctx, dirtyPoints, nDirtyPoints, &dDirty));
+    TRY(stageIn(ctx, dirtyPointOff, nDirtyPoints + 1, &dOff));
+    TRY(stageIn(ctx, dirtyPointCells, (int64_t)nnz, &dCells));
+    TRY(stageIn(ctx, dirtyBndPoint, nDirtyPoints, &dBnd));
+    TRY(stageIn(ctx, dirtyPointLevel, nDirtyPoints, &dPl));
+    int32_t *dirtyIdx = nullptr;
+    CK(cudaMalloc((void **)&dirtyIdx, (size_t)(p > 0 ? p : 1) * 4));
+    struct IdxGuard { int32_t *p; ~IdxGuard() { cudaFree(p); } } idxGuard{dirtyIdx};
+    sellFree(ctx, ctx->pc);
+    TRY(sellCarryOver(ctx, ctx->pc, K.pcOld, p, dMap, (const label *)K.rev, nDirtyPoints, dDirty, dOff, dCells, ctx->n, 0, false, dirtyIdx));
+    devFree(ctx, &ctx->bndPoint);
+    TRY(devAlloc(ctx, &ctx->bndPoint, p));
+    if (p) LAUNCH(k_upd_values<u8>, gridFor(p), kThreads, p, dMap, (const int32_t *)dirtyIdx, dBnd, (const u8 *)K.bndPointOld, ctx->bndPoint);
+    devFree(ctx, &ctx->pointLevel);
+    if (K.pointLevelOld) {
+        TRY(devAlloc(ctx, &ctx->pointLevel, p));
+        if (p) LAUNCH(k_upd_values<label>, gridFor(p), kThreads, p, dMap, (const int32_t *)dirtyIdx, dPl, (const label *)K.pointLevelOld, ctx->pointLevel);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    sellFree(ctx, K.pcOld); devFree(ctx, &K.bndPointOld); devFree(ctx, &K.pointLevelOld); devFree(ctx, &K.rev);
+    K.valid = false;
+    if (p + 16 > ctx->flagCap) TRY(growFlagPool(ctx, p + 16));
+    ctx->havePoints = true;
+    ctx->pcClassDirty = true; ctx->balancedLocal = -1; ctx->balancedGlobal = -1; ctx->spDirty = true; ctx->polyBadKind = -1;
     return AMR_OK;
 }
 
@@ -721,7 +939,7 @@ static int growFlagPool(amr_ctx *ctx, int64_t need) {
 AMR_API int amr_mesh_set_edges(amr_ctx *ctx, int64_t nEdges, const int32_t *edgePoints, const int32_t *ecOff,
                                const int32_t *ecCells, const uint8_t *bndEdge) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_mesh_set_edges: call amr_mesh_set first");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_mesh_set_edges: call amr_mesh_set first");
     if (nEdges < 0 || !edgePoints || !ecOff || !bndEdge) FAIL(AMR_ERR_ARG, "amr_mesh_set_edges: bad arguments");
     const int32_t *dOff = nullptr, *dIdx = nullptr;
     TRY(stageIn(ctx, ecOff, nEdges + 1, &dOff));
@@ -741,12 +959,13 @@ AMR_API int amr_mesh_set_edges(amr_ctx *ctx, int64_t nEdges, const int32_t *edge
     TRY(growFlagPool(ctx, nEdges + 16));
     ctx->nEdges = nEdges;
     ctx->haveEdges = true;
+    ctx->polyBadKind = -1;
     return AMR_OK;
 }
 
 AMR_API int amr_mesh_set_faces(amr_ctx *ctx, const int32_t *faceOff, const int32_t *facePts) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_mesh_set_faces: call amr_mesh_set first");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_mesh_set_faces: call amr_mesh_set first");
     if (!faceOff || !facePts) FAIL(AMR_ERR_ARG, "amr_mesh_set_faces: null pointer");
     const int64_t nf = ctx->f + ctx->b;
     devFree(ctx, &ctx->faceOff); devFree(ctx, &ctx->facePts);
@@ -760,6 +979,7 @@ AMR_API int amr_mesh_set_faces(amr_ctx *ctx, const int32_t *faceOff, const int32
     if (nnz) TRY(uploadAuto(ctx, ctx->facePts, facePts, (size_t)nnz * 4));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->haveFaces = true;
+    ctx->polyBadKind = -1;
     return AMR_OK;
 }
 
@@ -814,7 +1034,7 @@ static int pointPlan(amr_ctx *ctx) {
 
 AMR_API int amr_mesh_set_patch_points(amr_ctx *ctx, const int32_t *patchPointOff, const int32_t *patchPoints) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_mesh_set_patch_points: call amr_mesh_set first");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_mesh_set_patch_points: call amr_mesh_set first");
     if (!patchPointOff) FAIL(AMR_ERR_ARG, "amr_mesh_set_patch_points: null pointer");
     const size_t np = ctx->patches.size();
     ctx->ppOff.assign(patchPointOff, patchPointOff + np + 1);
@@ -946,7 +1166,8 @@ AMR_API int amr_set_option(amr_ctx *ctx, int option, int64_t value) {
 AMR_API int amr_mesh_set_geometry(amr_ctx *ctx, const double *weights, const double *Sf, const double *magSf,
                                   const double *nonOrthDeltaCoeffs, const double *V) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_mesh_set_geometry: call amr_mesh_set first");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_mesh_set_geometry: call amr_mesh_set first");
+    if (!ctx->faceLists) FAIL(AMR_ERR_STATE, "amr_mesh_set_geometry: needs owner/neighbour (amr_mesh_update hands over the cell adjacency only; face lists come with amr_mesh_set)");
     if (!weights || !Sf || !magSf || !nonOrthDeltaCoeffs || !V) FAIL(AMR_ERR_ARG, "amr_mesh_set_geometry: null pointer");
     const int64_t n = ctx->n, f = ctx->f, b = ctx->b, nf = f + b;
     devFree(ctx, &ctx->gWeights); devFree(ctx, &ctx->gSf); devFree(ctx, &ctx->gMagSf); devFree(ctx, &ctx->gDelta); devFree(ctx, &ctx->gV);
@@ -1008,7 +1229,7 @@ AMR_API int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->haveLevels = true;
-    ctx->pcClassDirty = true; ctx->balancedLocal = -1; ctx->balancedGlobal = -1; ctx->spDirty = true;
+    ctx->pcClassDirty = true; ctx->balancedLocal = -1; ctx->balancedGlobal = -1; ctx->spDirty = true; ctx->polyBadKind = -1;
     return AMR_OK;
 }
 
@@ -1033,7 +1254,7 @@ static Thresholds mkThr(const double *t) {
 AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *nbrValues, double p0, double p1, int scale,
                          const double *thr, double *errorOut) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_estimate: mesh not set");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_estimate: mesh not set");
     if (!x) FAIL(AMR_ERR_ARG, "amr_estimate: x is null");
     if (scale && !thr) FAIL(AMR_ERR_ARG, "amr_estimate: scale requested without thresholds");
     const int64_t n = ctx->n, b = ctx->b;
@@ -1072,7 +1293,7 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
         if (ctx->nCoupled > 0) {                                                                                 \
             GhostLink G = makeLink(ctx, &halo, ghost, false);                                                    \
             LAUNCH((k_fix_estimate_link<K>), gridFor(ctx->nCoupled), kThreads, G, ctx->nCoupled, (const label *)ctx->cplFace, \
-                   (const label *)(ctx->owner + ctx->f), dx, p0, p1, target);                                    \
+                   (const label *)ctx->bOwner, dx, p0, p1, target);                                    \
             if (scale) LAUNCH(k_fix_normalize, gridFor(ctx->nCplCells), kThreads, ctx->nCplCells, (const label *)ctx->cplCell, t, target); \
         }                                                                                                        \
     } while (0)
@@ -1092,7 +1313,7 @@ AMR_API int amr_estimate(amr_ctx *ctx, int kind, const double *x, const double *
 AMR_API int amr_estimate_lohner(amr_ctx *ctx, const double *x, const double *xBoundary, const double *nbrValues,
                                 double epsilon, int scale, const double *thr, double *errorOut) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_estimate_lohner: mesh not set");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_estimate_lohner: mesh not set");
     if (!ctx->haveGeom) FAIL(AMR_ERR_STATE, "amr_estimate_lohner: geometry not set (amr_mesh_set_geometry)");
     if (!x) FAIL(AMR_ERR_ARG, "amr_estimate_lohner: x is null");
     if (scale && !thr) FAIL(AMR_ERR_ARG, "amr_estimate_lohner: scale requested without thresholds");
@@ -1218,6 +1439,15 @@ static inline bool sparseForm(const amr_ctx *ctx, int site, int64_t n) {
     return seen >= 0 && seen * ctx->pushDen < n * ctx->pushNum;
 }
 
+// more than pullNum/pullDen of the cells were SOURCES at this site last time: at least that many are marked, the rows of
+// the unmarked rest are the cheaper walk (k_layer_pull_sparse).  AMR_B200_PULL_FRACTION, "0" = never.
+static inline bool sparsePullForm(const amr_ctx *ctx, int site, int64_t n) {
+    if (ctx->pullNum <= 0 || n < ctx->pushMinCells || n <= 0) return false;
+    const long long seen = ctx->hMarked[site];
+    if (ctx->pullNum >= ctx->pullDen) return true;                 // >= 1: always (tests force the form)
+    return seen >= 0 && seen * ctx->pullDen > n * ctx->pullNum;
+}
+
 static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *srcSeparate, int gen, int site) {
     const int64_t n = ctx->n;
     if (gen >= 254) FAIL(AMR_ERR_ARG, "more than 253 buffer layers in one call sequence");
@@ -1227,16 +1457,18 @@ static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *srcSeparate, int gen, in
     if (ctx->nCoupled > 0) TRY(haloBegin(ctx, srcArr, 1, ctx->ghost8, &halo));     // the values as they are BEFORE this layer
     unsigned long long *cnt = ctx->dMarked + site;
     if (n > 0) {
+        const bool al = ((((uintptr_t)srcArr) | ((uintptr_t)cur)) & 15) == 0;
         if (sparseForm(ctx, site, n)) {
-            const bool al = ((((uintptr_t)srcArr) | ((uintptr_t)cur)) & 15) == 0;
             LAUNCH(k_layer_push, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, srcArr, separate, gen, al, cur, cnt);
+        } else if (sparsePullForm(ctx, site, n)) {
+            LAUNCH(k_layer_pull_sparse, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, srcArr, separate, gen, al, cur, cnt);
         } else if (pipeOk(ctx, ctx->cc)) TRY(launchPipe(ctx, kp_layer_pull, ctx->cc, srcArr, separate, gen, cur, cnt));
         else LAUNCH(k_layer_pull, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, srcArr, separate, gen, cur, cnt);
         ctx->sitesTouched |= 1u << site;
     }
     if (ctx->nCoupled > 0) {
         GhostLink G = makeLink(ctx, &halo, ctx->ghost8, false);
-        LAUNCH(k_fix_layer_link, gridFor(ctx->nCoupled), kThreads, G, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
+        LAUNCH(k_fix_layer_link, gridFor(ctx->nCoupled), kThreads, G, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)ctx->bOwner,
                separate, gen, cur);
     }
     return AMR_OK;
@@ -1259,7 +1491,7 @@ AMR_API int amr_protect_patches(amr_ctx *ctx, const int32_t *patchIds, int nPatc
         int q = patchIds[k];
         if (q < 0 || q >= (int)ctx->patches.size()) FAIL(AMR_ERR_ARG, "amr_protect_patches: patch id out of range");
         const Patch &pp = ctx->patches[q];
-        if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)1);
+        if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->bOwner, (int64_t)pp.start - ctx->f, (int64_t)pp.size, cur, (u8)1);
     }
     int gen = 1;
     for (int i = 0; i < nLayers; i++) {
@@ -1426,7 +1658,7 @@ static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int
     const bool speculate = gatedSwapsOk(ctx);
     int *qc = ctx->dQ, *gq = multi ? ctx->dGQ : ctx->dQ;
     const int64_t cap = ctx->queueCap;
-    const label *cf = ctx->cplFace, *bo = ctx->owner + ctx->f;
+    const label *cf = ctx->cplFace, *bo = ctx->bOwner;
     ListJob job;                          // (queue sizes were cleared by sitesBegin at the start of the call)
     TRY(listTarget(ctx, n, cellsOut, &job));
     const bool linked = multi && speculate && linkedOk(ctx);
@@ -1522,9 +1754,9 @@ static int refineSweepsDense(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *swe
         TRY(haloEnd(ctx, &halo));
         if (ctx->nCoupled > 0 && n) {      // hexRef.C:758-780
             if (maxSet) LAUNCH((k_fix_refine_sweep<true>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
-                               (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
+                               (const label *)ctx->bOwner, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
             else LAUNCH((k_fix_refine_sweep<false>), gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
-                        (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
+                        (const label *)ctx->bOwner, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, lf, set, ctx->dFlags);
         }
         sweeps++;
         int changed = 0;
@@ -1605,7 +1837,7 @@ static int calcProtected(amr_ctx *ctx, u8 *unrefineable, bool *have) {
         }
         if (n) LAUNCH(k_protected_spread, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, unrefineable, ctx->dFlags + 1);
         if (ctx->nCoupled > 0)
-            LAUNCH(k_fix_protected, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
+            LAUNCH(k_fix_protected, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)ctx->bOwner,
                    (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, (const u8 *)ghostLvl, unrefineable, ctx->dFlags + 1);
         int changed = 0;
         TRY(globalFlag(ctx, 1, &changed));
@@ -1619,7 +1851,7 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
                               int nProtectedPatches, int64_t maxCells, int refinerKind, uint8_t *refineCellOut,
                               int32_t *cellsOut, int64_t *nOut, int *sweepsOut) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_select_refine: mesh not set");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_select_refine: mesh not set");
     if (!ctx->haveLevels) FAIL(AMR_ERR_STATE, "amr_select_refine: levels not set");
     if (refinerKind != AMR_REFINER_HEX3D && refinerKind != AMR_REFINER_HEX2D && refinerKind != AMR_REFINER_POLY3D &&
         refinerKind != AMR_REFINER_POLY2D)
@@ -1664,7 +1896,7 @@ AMR_API int amr_select_refine(amr_ctx *ctx, const double *error, double lo, doub
         int q = protectedPatchIds[k];
         if (q < 0 || q >= (int)ctx->patches.size()) FAIL(AMR_ERR_ARG, "amr_select_refine: patch id out of range");
         const Patch &pp = ctx->patches[q];
-        if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)0);
+        if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->bOwner, (int64_t)pp.start - ctx->f, (int64_t)pp.size, cur, (u8)0);
     }
     if (!poly && ctx->protCell && n) LAUNCH(k_masked_set, gridFor(n), kThreads, n, ctx->protCell, cur, (u8)0);
     ctx->refineCellN = n;
@@ -1873,7 +2105,7 @@ static int unrefineClosureQueue(amr_ctx *ctx, const double *dErr, double unrefin
     const bool speculate = gatedSwapsOk(ctx);
     int *qc = ctx->dQ, *gq = multi ? ctx->dGQ : ctx->dQ;
     const int64_t cap = ctx->queueCap;
-    const label *cf = ctx->cplFace, *bo = ctx->owner + ctx->f;
+    const label *cf = ctx->cplFace, *bo = ctx->bOwner;
     u8 *uc = ctx->flagB, *spFlag = ctx->spFlag;
     ListJob job;
     TRY(listTarget(ctx, std::max<int64_t>(nSp, 1), elemsOut, &job));
@@ -1994,7 +2226,7 @@ static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOu
         if (n) LAUNCH(k_unrefine_sweep, gC, kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, uc, alC, ctx->dFlags);
         if (ctx->nCoupled > 0)      // hexRef3D.C:1855-1889
             LAUNCH(k_fix_unrefine_sweep, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
-                   (const label *)(ctx->owner + ctx->f), (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, uc, ctx->dFlags);
+                   (const label *)ctx->bOwner, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, uc, ctx->dFlags);
         // polyhedralRefinement.C:2278-2286: faceConsistentUnrefinement, then edgeConsistentUnrefinement
         if (edgeRule && ctx->nEdges)
             LAUNCH(k_edge_unrefine_sweep, gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, (const u8 *)ctx->lvl8, uc, ctx->dFlags);
@@ -2013,6 +2245,20 @@ static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOu
 }
 
 // split-point markup of the two polyRefiner engines: polyhedralRefinement (faces) / prismatic2DRefinement (edges)
+static int polySplitMarkup(amr_ctx *ctx, bool prismatic, u8 *bad);
+// The markup depends on the mesh and pointLevel only: built once per mesh and engine (faces / edges / levels / point
+// hand-overs invalidate it), like the hexRefiner's split-point table.
+static int ensurePolyMarkup(amr_ctx *ctx, bool prismatic, const u8 **bad) {
+    const int kind = prismatic ? 1 : 0;
+    if (ctx->polyBadKind != kind || !ctx->polyBad) {
+        devFree(ctx, &ctx->polyBad);
+        TRY(devAlloc(ctx, &ctx->polyBad, ctx->p + 16));
+        TRY(polySplitMarkup(ctx, prismatic, ctx->polyBad));
+        ctx->polyBadKind = kind;
+    }
+    *bad = ctx->polyBad;
+    return AMR_OK;
+}
 static int polySplitMarkup(amr_ctx *ctx, bool prismatic, u8 *bad) {
     const int64_t p = ctx->p;
     if (p) CK(cudaMemsetAsync(bad, 0, (size_t)p, ctx->stream));
@@ -2033,7 +2279,7 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
                                 int nBufferLayers, const int32_t *protectedPatchIds, int nProtectedPatches,
                                 int refinerKind, int32_t *elemsOut, int64_t *nOut, int *sweepsOut) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_select_unrefine: mesh not set");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_select_unrefine: mesh not set");
     if (!ctx->havePoints) FAIL(AMR_ERR_STATE, "amr_select_unrefine: point addressing not set (amr_mesh_set_points)");
     const bool prismatic = refinerKind == AMR_REFINER_POLY2D;
     const bool poly = refinerKind == AMR_REFINER_POLY3D || prismatic;
@@ -2093,15 +2339,15 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
         int q = protectedPatchIds[k];
         if (q < 0 || q >= (int)ctx->patches.size()) FAIL(AMR_ERR_ARG, "amr_select_unrefine: patch id out of range");
         const Patch &pp = ctx->patches[q];
-        if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->owner, (int64_t)pp.start, (int64_t)pp.size, cur, (u8)1);
+        if (pp.size) LAUNCH(k_patch_cells_set, gridFor(pp.size), kThreads, ctx->bOwner, (int64_t)pp.start - ctx->f, (int64_t)pp.size, cur, (u8)1);
     }
     if (dRc && n) LAUNCH(k_flags_normalize, gridFor(n, kThreads * 16), kThreads, n, (const u8 *)cur, dRc, ((((uintptr_t)cur) | ((uintptr_t)dRc)) & 15) == 0);
     const u8 *marked = cur;
     // U1+U2+U3 fused: maxCellField + getSplitElems + filter
     u8 *pflag = ctx->flagC;
     if (poly) {
-        u8 *bad = ctx->flagA;
-        TRY(polySplitMarkup(ctx, prismatic, bad));
+        const u8 *bad = nullptr;
+        TRY(ensurePolyMarkup(ctx, prismatic, &bad));
         if (p) LAUNCH(k_poly_select_points, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const label *)ctx->pointLevel, (const u8 *)bad,
                       dErr, unrefineLevel, marked, (u8 *)nullptr, pflag);
         TRY(unrefineSweeps(ctx, ctx->pc, pflag, sweepsOut, elemsOut, nOut, ctx->optEdgeConsistency != 0));
@@ -2192,7 +2438,7 @@ AMR_API int amr_check_levels(amr_ctx *ctx, const int32_t *cellLevel, int64_t *nB
     CK(cudaMemsetAsync(ctx->dCount, 0, 8, ctx->stream));
     if (n) LAUNCH(k_check_levels, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, dL, (unsigned long long *)ctx->dCount);
     if (ctx->nCoupled > 0)
-        LAUNCH(k_fix_check_levels, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)(ctx->owner + ctx->f),
+        LAUNCH(k_fix_check_levels, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace, (const label *)ctx->bOwner,
                dL, (const label *)ghost, (unsigned long long *)ctx->dCount);
     CK(cudaMemcpyAsync(ctx->hCount, ctx->dCount, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -2607,7 +2853,7 @@ AMR_API int amr_correct_fluxes(amr_ctx *ctx, int64_t nOldFaces, const int32_t *f
 
 AMR_API int amr_mesh_set_ls_vectors(amr_ctx *ctx, const double *pVectors, const double *nVectors) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_mesh_set_ls_vectors: call amr_mesh_set first");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_mesh_set_ls_vectors: call amr_mesh_set first");
     if (!pVectors || (!nVectors && ctx->f)) FAIL(AMR_ERR_ARG, "amr_mesh_set_ls_vectors: null pointer");
     const int64_t f = ctx->f, nf = ctx->f + ctx->b;
     devFree(ctx, &ctx->lsP); devFree(ctx, &ctx->lsN);
@@ -2741,7 +2987,7 @@ AMR_API int amr_estimate_cell_size(amr_ctx *ctx, int sizeType, const int32_t *ge
 AMR_API int amr_multicomponent(amr_ctx *ctx, int nEstimators, const double *const *errors, const int32_t *const *maxCellLevels,
                                double *errorOut, int32_t *maxRefinementOut, int *wavesOut) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_multicomponent: mesh not set");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_multicomponent: mesh not set");
     if (nEstimators < 0 || (nEstimators && !errors)) FAIL(AMR_ERR_ARG, "amr_multicomponent: errors is null");
     const int64_t n = ctx->n;
     std::vector<const double *> dErr((size_t)nEstimators, nullptr);
@@ -2841,7 +3087,8 @@ static int historyClusters(amr_ctx *ctx, label **cellToClusterDev, int32_t **nCl
 AMR_API int amr_history_clusters(amr_ctx *ctx, const int32_t *cellToClusterIn, int32_t *cellToClusterOut, uint8_t *blockedFace,
                                  int64_t *nClusters, int64_t *nUnblocked) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_history_clusters: mesh not set");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_history_clusters: mesh not set");
+    if (!ctx->faceLists) FAIL(AMR_ERR_STATE, "amr_history_clusters: needs owner/neighbour (amr_mesh_update hands over the cell adjacency only; face lists come with amr_mesh_set)");
     const int64_t n = ctx->n, f = ctx->f, nf = ctx->f + ctx->b;
     label *c2c = nullptr;
     int32_t *total = nullptr;
@@ -2878,7 +3125,8 @@ AMR_API int amr_history_clusters(amr_ctx *ctx, const int32_t *cellToClusterIn, i
 
 AMR_API int amr_history_constrain_decomposition(amr_ctx *ctx, int32_t *decomposition, int64_t *nChanged) {
     ENTER();
-    if (!ctx->owner) FAIL(AMR_ERR_STATE, "amr_history_constrain_decomposition: mesh not set");
+    if (!ctx->meshSet) FAIL(AMR_ERR_STATE, "amr_history_constrain_decomposition: mesh not set");
+    if (!ctx->faceLists) FAIL(AMR_ERR_STATE, "amr_history_constrain_decomposition: needs owner/neighbour (amr_mesh_update hands over the cell adjacency only; face lists come with amr_mesh_set)");
     if (!ctx->haveHistory) FAIL(AMR_ERR_STATE, "amr_history_constrain_decomposition: refinement history not set (amr_levels_set)");
     if (!decomposition) FAIL(AMR_ERR_ARG, "amr_history_constrain_decomposition: decomposition is null");
     const int64_t n = ctx->n, f = ctx->f;

@@ -67,6 +67,8 @@ struct amr_ctx {
     // AMR_B200_TRACE=<file prefix>: a CUDA event after every launch / host round trip of this context; the time line
     // (name, microseconds since the first event) is written to <prefix>.<rank>.<ctx address> at amr_ctx_destroy.
     // Diagnosis only: the events themselves cost ~1 us each.
+    bool hostTime = false;     // AMR_B200_HOSTTIME=1: wall-clock marks of the mesh hand-over calls on stderr (diagnosis)
+    double htLast = 0.0;
     bool traceOn = false;
     std::string tracePath;
     std::vector<TraceRec> trace;
@@ -99,7 +101,9 @@ struct amr_ctx {
 
     // mesh
     int64_t n = 0, f = 0, b = 0, p = 0;
-    label *owner = nullptr, *neighbour = nullptr;
+    label *owner = nullptr, *neighbour = nullptr;   // face lists as sent by amr_mesh_set (absent after amr_mesh_update: faceLists)
+    label *bOwner = nullptr;   // [b] faceOwner of the boundary faces (= owner + f, or its own allocation after amr_mesh_update)
+    bool bOwnerOwned = false, meshSet = false, faceLists = false;
     std::vector<Patch> patches;
     int64_t nCoupled = 0;
     u8 *bCoupled = nullptr;    // [b] boundary face lies on a processor patch
@@ -113,9 +117,13 @@ struct amr_ctx {
     Sell cc;                   // cell -> face-neighbour cells (+ ghost slots n + bface for coupled faces)
     Sell pc;                   // point -> cells
     bool havePoints = false;
+    // what amr_mesh_update keeps of the OLD mesh for the amr_mesh_update_points that follows it
+    struct Carry { bool valid = false; Sell pcOld; u8 *bndPointOld = nullptr; label *pointLevelOld = nullptr; label *rev = nullptr; } carry;
     // polyRefiner
     bool haveFaces = false;
     label *faceOff = nullptr, *facePts = nullptr;
+    u8 *polyBad = nullptr;     // [p] polyRefiner split-point markup (points that cannot be split points), mesh-constant
+    int polyBadKind = -1;      // -1: not built; 0 polyhedralRefinement, 1 prismatic2DRefinement
     int optEdgeConsistency = 1, optPolyForce = 0;
     // 2-D cutter: edges as split elements
     bool haveEdges = false;
@@ -140,6 +148,7 @@ struct amr_ctx {
     int lookResult = 0;                      // queueLook: index of the first empty queue, or 0
     Mailbox *mailbox = nullptr;              // pinned (device-visible through UVA)
     unsigned mailSeq = 0;
+    int pullNum = 1, pullDen = 2;   // ... and the sparse pull form (rows of the unmarked cells) when sources/n > pullNum/pullDen
     int pushNum = 1, pushDen = 4;   // buffer layers take the sparse push form when marked/n < pushNum/pushDen (0 = never)
     label *ppPts = nullptr;         // points of the processor patches, patch after patch (syncPointList pairing)
     std::vector<int32_t> ppOff;     // [npatch+1] offsets into ppPts
@@ -242,6 +251,14 @@ struct amr_ctx {
         if (rc_ != AMR_OK) return rc_;                                                        \
     } while (0)
 
+#include <chrono>
+static inline void hostMark(amr_ctx *ctx, const char *what) {
+    if (!ctx->hostTime) return;
+    cudaStreamSynchronize(ctx->stream);
+    const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (what) fprintf(stderr, "[amr host +%8.2f ms] %s\n", 1e3 * (now - ctx->htLast), what);
+    ctx->htLast = now;
+}
 static inline void traceMark(amr_ctx *ctx, const char *name) {
     if (!ctx->traceOn || ctx->trace.size() >= 200000) return;
     cudaEvent_t e;

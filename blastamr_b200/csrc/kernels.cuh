@@ -590,6 +590,12 @@ k_select_unrefine_edges(int64_t nEdges, const int32_t *__restrict__ ecOff, const
 // of the edge's cells must satisfy the 2:1 rule on level+flag.  maxSet: a cell more than one level below the
 // edge's maximum is added; !maxSet: a marked cell more than one level above the edge's minimum is removed.
 // Same monotone closure as the face rule, so in-place chaotic iteration reaches the reference's fixed point.
+// up to 8 labels of a SELL row starting at entry j0, loaded together (independent loads); entries past the row are -1
+__device__ __forceinline__ void rowLabels8(const int32_t *row, int w, int j0, int32_t (&c)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : -1;
+}
+
 template <bool MAXSET>
 __global__ void __launch_bounds__(kThreads)
 k_edge_refine_sweep(int64_t nEdges, const int32_t *__restrict__ ecOff, const int32_t *__restrict__ ecCol,
@@ -599,20 +605,34 @@ k_edge_refine_sweep(int64_t nEdges, const int32_t *__restrict__ ecOff, const int
     const int32_t base = ecOff[e >> 5];
     const int w = ecOff[(e >> 5) + 1] - base;
     const int32_t *row = ecCol + ((size_t)base << 5) + (e & 31);
+    // labels and values are gathered 8 at a time (two dependent rounds per batch instead of two per cell); an edge of a
+    // hex mesh has at most 4 cells plus hanging-node partners, so one batch is the usual case
     int mx = 0, mn = 255;
-    for (int j = 0; j < w; j++) {
-        const int32_t c = row[(size_t)j << 5];
-        if (c < 0) break;
-        const int v = lf[c];
-        mx = max(mx, v); mn = min(mn, v);
+    int32_t c[8];
+    int v[8];
+    for (int j0 = 0; j0 < w; j0 += 8) {
+        rowLabels8(row, w, j0, c);
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = c[k] >= 0 ? (int)lf[c[k]] : -1;
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (v[k] >= 0) { mx = max(mx, v[k]); mn = min(mn, v[k]); }
     }
     if (mx - mn <= 1) return;
-    for (int j = 0; j < w; j++) {
-        const int32_t c = row[(size_t)j << 5];
-        if (c < 0) break;
-        const int v = lf[c];
-        if (MAXSET) { if (!set[c] && v + 1 < mx) { set[c] = 1; lf[c] = (u8)(v + 1); *changed = 1; } }
-        else { if (set[c] && v > mn + 1) { set[c] = 0; lf[c] = (u8)(v - 1); *changed = 1; } }
+    for (int j0 = 0; j0 < w; j0 += 8) {
+        if (w > 8) {                      // (a single batch is still in registers)
+            rowLabels8(row, w, j0, c);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = c[k] >= 0 ? (int)lf[c[k]] : -1;
+        }
+        unsigned st[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) st[k] = c[k] >= 0 ? (unsigned)set[c[k]] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (c[k] < 0) continue;
+            if (MAXSET) { if (!st[k] && v[k] + 1 < mx) { set[c[k]] = 1; lf[c[k]] = (u8)(v[k] + 1); *changed = 1; } }
+            else { if (st[k] && v[k] > mn + 1) { set[c[k]] = 0; lf[c[k]] = (u8)(v[k] - 1); *changed = 1; } }
+        }
     }
 }
 
@@ -628,18 +648,25 @@ k_edge_unrefine_sweep(int64_t nEdges, const int32_t *__restrict__ ecOff, const i
     const int32_t *row = ecCol + ((size_t)base << 5) + (e & 31);
     int mx = 0;
     unsigned any = 0;
-    for (int j = 0; j < w; j++) {
-        const int32_t c = row[(size_t)j << 5];
-        if (c < 0) break;
-        const int u = uc[c];
-        any |= u;
-        mx = max(mx, (int)lvl8[c] - u);
+    int32_t c[8];
+    int u[8], l[8];
+    for (int j0 = 0; j0 < w; j0 += 8) {
+        rowLabels8(row, w, j0, c);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { u[k] = c[k] >= 0 ? (int)uc[c[k]] : 0; l[k] = c[k] >= 0 ? (int)lvl8[c[k]] : 0; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (c[k] >= 0) { any |= (unsigned)u[k]; mx = max(mx, l[k] - u[k]); }
     }
     if (!any) return;
-    for (int j = 0; j < w; j++) {
-        const int32_t c = row[(size_t)j << 5];
-        if (c < 0) break;
-        if (uc[c] && (int)lvl8[c] - 1 < mx - 1) { uc[c] = 0; *changed = 1; }
+    for (int j0 = 0; j0 < w; j0 += 8) {
+        if (w > 8) {
+            rowLabels8(row, w, j0, c);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { u[k] = c[k] >= 0 ? (int)uc[c[k]] : 0; l[k] = c[k] >= 0 ? (int)lvl8[c[k]] : 0; }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (c[k] >= 0 && u[k] && l[k] - 1 < mx - 1) { uc[c[k]] = 0; *changed = 1; }
     }
 }
 
@@ -663,9 +690,14 @@ k_cells_to_points_or(int64_t p, const int32_t *__restrict__ pcOff, const int32_t
     const int w = pcOff[(pt >> 5) + 1] - base;
     const int32_t *row = pcCol + ((size_t)base << 5) + (pt & 31);
     unsigned m = 0;
-    for (int j = 0; j < w; j++) {
-        const int32_t c = row[(size_t)j << 5];
-        if (c >= 0) m |= marked[c];
+    for (int j0 = 0; j0 < w && !m; j0 += 8) {
+        int32_t c[8];
+        rowLabels8(row, w, j0, c);
+        unsigned v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = c[k] >= 0 ? (unsigned)marked[c[k]] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) m |= v[k];
     }
     pflag[pt] = m ? 1 : 0;
 }
@@ -808,9 +840,11 @@ k_points_to_cells(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t
         const int32_t base = sliceOff[pt >> 5];
         const int w = sliceOff[(pt >> 5) + 1] - base;
         const int32_t *row = col + ((size_t)base << 5) + (pt & 31);
-        for (int j = 0; j < w; j++) {
-            int32_t q = row[(size_t)j << 5];
-            if (q >= 0) cflag[q] = 1;
+        for (int j0 = 0; j0 < w; j0 += 8) {
+            int32_t q[8];
+            rowLabels8(row, w, j0, q);
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (q[k] >= 0) cflag[q[k]] = 1;
         }
     });
 }
@@ -852,9 +886,14 @@ k_knock_points(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *_
         const int w = sliceOff[(pt >> 5) + 1] - base;
         const int32_t *row = col + ((size_t)base << 5) + (pt & 31);
         bool ok = true;
-        for (int j = 0; j < w; j++) {
-            int32_t q = row[(size_t)j << 5];
-            if (q >= 0 && !uc[q]) { ok = false; break; }
+        for (int j0 = 0; j0 < w && ok; j0 += 8) {
+            int32_t q[8];
+            rowLabels8(row, w, j0, q);
+            unsigned u[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) u[k] = q[k] >= 0 ? (unsigned)uc[q[k]] : 1u;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (!u[k]) ok = false;
         }
         if (!ok) pflag[pt] = 0;
     });

@@ -119,6 +119,85 @@ k_layer_push(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__r
     if (nSrc) blockAddCount(mine, nSrc);
 }
 
+// sparse pull form: when MOST cells are marked already (the unrefinement layer on a graded mesh: the marking covers the
+// whole refined band), only the rows of the UNMARKED cells matter -- a 16-flags-per-load scan finds them, the warp deals
+// them to its lanes, each gathers the source values of its row.  Same result as the other two forms; reads the
+// adjacency of the unmarked cells only instead of streaming all of it.
+__global__ void __launch_bounds__(kThreads)
+k_layer_pull_sparse(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *srcArr, bool separate,
+                    int gen, bool aligned, u8 *cur, unsigned long long *__restrict__ nSrc) {
+    __shared__ unsigned short unsetIdx[kThreads / 32][512];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warpBase = ((int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31)) * 16;
+    int mine = 0;
+    if (warpBase < n) {
+        const int64_t base = warpBase + (int64_t)lane * 16;
+        unsigned zmask = 0;                                   // unmarked cells of this thread's 16
+        if (base < n) {
+            if (aligned && base + 16 <= n) {
+                const uint4 w = *reinterpret_cast<const uint4 *>(cur + base);
+                const unsigned v[4] = {w.x, w.y, w.z, w.w};
+                unsigned sv[4] = {v[0], v[1], v[2], v[3]};
+                if (separate) {
+                    const uint4 ws = *reinterpret_cast<const uint4 *>(srcArr + base);
+                    sv[0] = ws.x; sv[1] = ws.y; sv[2] = ws.z; sv[3] = ws.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const unsigned own = (v[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                    zmask |= (own == 0u ? 1u : 0u) << k;
+                    mine += isSource((sv[k >> 2] >> (8 * (k & 3))) & 0xffu, gen, separate) ? 1 : 0;
+                }
+            } else {
+                for (int k = 0; k < 16 && base + k < n; k++) {
+                    zmask |= (cur[base + k] == 0 ? 1u : 0u) << k;
+                    mine += isSource(srcArr[base + k], gen, separate) ? 1 : 0;
+                }
+            }
+        }
+        const int cnt = __popc(zmask);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+            int o = incl - cnt;
+            while (zmask) {
+                const int k = __ffs(zmask) - 1;
+                zmask &= zmask - 1;
+                unsetIdx[warp][o++] = (unsigned short)(lane * 16 + k);
+            }
+            __syncwarp();
+            const u8 tag = (u8)(gen + 1);
+            for (int i = lane; i < total; i += 32) {
+                const int64_t c = warpBase + unsetIdx[warp][i];
+                const int32_t b0 = sliceOff[c >> 5];
+                const int w = sliceOff[(c >> 5) + 1] - b0;
+                const int32_t *row = col + ((size_t)b0 << 5) + (c & 31);
+                unsigned hit = 0;
+                for (int j0 = 0; j0 < w; j0 += 8) {
+                    int32_t q[8];
+                    unsigned v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = srcArr[q[k]];
+#pragma unroll
+                    // padding reads the cell's own value: unmarked, and with a separate source array no source either (a source is
+                    // always marked: the candidates kernel writes both)
+                    for (int k = 0; k < 8; k++) hit |= (q[k] != (int32_t)c && isSource(v[k], gen, separate)) ? 1u : 0u;
+                }
+                if (hit) cur[c] = tag;
+            }
+            __syncwarp();
+        }
+    }
+    if (nSrc) blockAddCount(mine, nSrc);
+}
+
 // dense pull form (TMA-staged): every unmarked cell gathers the source values of its row
 __global__ void __launch_bounds__(kPipeThreads, 7)
 kp_layer_pull(SellView S, const u8 *srcArr, bool separate, int gen, u8 *cur, unsigned long long *__restrict__ nSrc) {

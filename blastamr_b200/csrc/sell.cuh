@@ -186,3 +186,107 @@ static int sellBuildFromCsr(amr_ctx *ctx, Sell &S, int64_t rows, const int32_t *
     cudaFree(deg);
     return rc;
 }
+
+// ---- N1: adjacency carried through a topology change (hexRef::updateMesh, hexRef.C:2422-2608) -------------------------
+// After a cut or a merge most rows of an adjacency are what they were, up to the renumbering of the labels: row r of the
+// new mesh is row map[r] of the old one with every entry e replaced by rev[e] (mapPolyMesh::cellMap / reverseCellMap;
+// rev == nullptr: labels kept, elements only appended).  Only the rows the host lists as dirty (ascending, CSR) are
+// taken from the host.  The same kernels serve cell->cell (map = cellMap) and point->cell (map = pointMap, entries
+// are cells: rev = reverseCellMap).
+__global__ void k_upd_dirty_index(int64_t nDirty, const label *__restrict__ dirty, int64_t rowsNew, int32_t *__restrict__ dirtyIdx,
+                                  int *__restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nDirty) return;
+    const label r = dirty[i];
+    if (r < 0 || r >= rowsNew || (i > 0 && dirty[i - 1] >= r)) { *bad = 1; return; }
+    dirtyIdx[r] = (int32_t)i;
+}
+__global__ void k_upd_deg(int64_t rowsNew, int64_t rowsOld, const label *__restrict__ map, const int32_t *__restrict__ dirtyIdx,
+                          const int32_t *__restrict__ dirtyOff, const u8 *__restrict__ oldCount, int32_t *__restrict__ deg,
+                          int *__restrict__ bad) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rowsNew) return;
+    const int32_t d = dirtyIdx[r];
+    if (d >= 0) {
+        const int32_t w = dirtyOff[d + 1] - dirtyOff[d];
+        if (w < 0) { *bad = 1; deg[r] = 0; return; }
+        deg[r] = w;
+        return;
+    }
+    const label ro = map[r];
+    if (ro < 0 || ro >= rowsOld) { *bad = 2; deg[r] = 0; return; }       // a clean row needs the row it came from
+    const int c = oldCount[ro];
+    if (c == 255) *bad = 3;                                              // saturated count: the old length is not known
+    deg[r] = c;
+}
+__global__ void k_upd_fill(int64_t rowsNew, const label *__restrict__ map, const int32_t *__restrict__ dirtyIdx,
+                           const int32_t *__restrict__ dirtyOff, const label *__restrict__ dirtyEntries, int64_t entryLimit,
+                           const int32_t *__restrict__ oldSliceOff, const int32_t *__restrict__ oldCol, const label *__restrict__ rev,
+                           const int32_t *__restrict__ deg, const int32_t *__restrict__ newSliceOff, int32_t *__restrict__ newCol,
+                           int *__restrict__ bad) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rowsNew) return;
+    int32_t *dst = newCol + ((size_t)newSliceOff[r >> 5] << 5) + (r & 31);
+    const int w = deg[r];
+    const int32_t d = dirtyIdx[r];
+    if (d >= 0) {
+        const label *src = dirtyEntries + dirtyOff[d];
+        for (int j = 0; j < w; j++) {
+            const label e = src[j];
+            if (e < 0 || e >= entryLimit) { *bad = 4; continue; }
+            dst[(size_t)j << 5] = e;
+        }
+        return;
+    }
+    const label ro = map[r];
+    const int32_t *src = oldCol + ((size_t)oldSliceOff[ro >> 5] << 5) + (ro & 31);
+    for (int j = 0; j < w; j++) {
+        label e = src[(size_t)j << 5];
+        if (rev) e = rev[e];
+        if (e < 0 || e >= entryLimit) { *bad = 5; continue; }            // a clean row may not point at a removed element
+        dst[(size_t)j << 5] = e;
+    }
+}
+// per-row values through the change: new[r] = dirty ? given[d] : old[map[r]]
+template <typename T>
+__global__ void k_upd_values(int64_t rowsNew, const label *__restrict__ map, const int32_t *__restrict__ dirtyIdx,
+                             const T *__restrict__ given, const T *__restrict__ oldV, T *__restrict__ newV) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rowsNew) return;
+    const int32_t d = dirtyIdx[r];
+    newV[r] = d >= 0 ? given[d] : oldV[map[r]];
+}
+
+// new adjacency from the old one + the dirty rows.  dirtyIdx [rowsNew] is scratch filled here and left for the caller.
+static int sellCarryOver(amr_ctx *ctx, Sell &out, const Sell &old, int64_t rowsNew, const label *map, const label *rev,
+                         int64_t nDirty, const label *dirty, const int32_t *dirtyOff, const label *dirtyEntries, int64_t entryLimit,
+                         int selfPad, bool sortRows, int32_t *dirtyIdx) {
+    int32_t *deg = nullptr;
+    CK(cudaMalloc((void **)&deg, (size_t)(rowsNew + 1) * 4));
+    int *bad = ctx->dFlags + 5;
+    CK(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(dirtyIdx, 0xFF, (size_t)(rowsNew > 0 ? rowsNew : 1) * 4, ctx->stream));
+    if (nDirty > 0) LAUNCH(k_upd_dirty_index, gridFor(nDirty), kThreads, nDirty, dirty, rowsNew, dirtyIdx, bad);
+    if (rowsNew > 0) LAUNCH(k_upd_deg, gridFor(rowsNew), kThreads, rowsNew, old.rows, map, (const int32_t *)dirtyIdx, dirtyOff, (const u8 *)old.count, deg, bad);
+    int rc = sellAllocFromDeg(ctx, out, rowsNew, deg, selfPad);
+    if (rc == AMR_OK && rowsNew > 0) {
+        LAUNCH(k_upd_fill, gridFor(rowsNew), kThreads, rowsNew, map, (const int32_t *)dirtyIdx, dirtyOff, dirtyEntries, entryLimit,
+               (const int32_t *)old.sliceOff, (const int32_t *)old.col, rev, (const int32_t *)deg, (const int32_t *)out.sliceOff, out.col, bad);
+        if (sortRows) LAUNCH(k_sell_sort_rows, gridFor(rowsNew), kThreads, out.col, out.sliceOff, deg, rowsNew);
+    }
+    int hBad = 0;
+    if (rc == AMR_OK) {
+        cudaError_t e = cudaMemcpyAsync(&hBad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("sellCarryOver: ") + cudaGetErrorString(e); rc = AMR_ERR_CUDA; }
+    }
+    cudaFree(deg);
+    if (rc == AMR_OK && hBad) {
+        static const char *why[] = {"", "dirty list not ascending / out of range", "a clean row has no old row (map out of range)",
+                                    "an old row is longer than 254 entries", "a dirty row holds a label out of range",
+                                    "a clean row points at a removed element: it must be listed as dirty"};
+        ctx->err = std::string("incremental adjacency update: ") + why[hBad < 6 ? hBad : 0];
+        rc = AMR_ERR_ARG;
+    }
+    return rc;
+}

@@ -310,3 +310,130 @@ def decompose_one(mesh: PolyMesh, cell_rank: np.ndarray, nranks: int, rank: int)
         raise ValueError("decompose needs a generator-owned mesh")
     h = lib().mg_decompose_one(mesh._handle, cell_rank.ctypes.data, nranks, rank)
     return _wrap(h, [q.name for q in mesh.patches])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# What a topology engine hands to amr_mesh_update / amr_mesh_update_points (include/amr_b200.h, row N1): the maps of the
+# change and the rows of the addressing that changed.  polyTopoChange knows the cells it touched; this stand-in derives
+# the same lists from the old and the new mesh (host bookkeeping, numpy).
+
+@dataclass
+class MeshDelta:
+    cell_map: np.ndarray                    # [nNew] new -> old
+    reverse_cell_map: Optional[np.ndarray]  # [nOld] old -> new (< 0 removed) or None (labels kept, cells appended)
+    dirty_cells: np.ndarray
+    dirty_cell_off: np.ndarray
+    dirty_cell_nbrs: np.ndarray
+    dirty_cell_level: np.ndarray
+    dirty_parent_index: Optional[np.ndarray]
+    point_map: Optional[np.ndarray] = None  # [pNew] new -> old or -1
+    dirty_points: Optional[np.ndarray] = None
+    dirty_point_off: Optional[np.ndarray] = None
+    dirty_point_cells: Optional[np.ndarray] = None
+    dirty_bnd_point: Optional[np.ndarray] = None
+    dirty_point_level: Optional[np.ndarray] = None
+
+    def nbytes(self) -> int:
+        return int(sum(a.nbytes for a in self.__dict__.values() if isinstance(a, np.ndarray)))
+
+
+def parent_index(mesh: PolyMesh) -> np.ndarray:
+    """history.parentIndex(c): splitCells_[visibleCells_[c]].parent_ or -1 (hexRefRefinementHistory.H:299-310)"""
+    vis = mesh.visible
+    out = np.full(mesh.n, -1, dtype=np.int32)
+    if vis is None or mesh.split_parent is None or len(mesh.split_parent) == 0:
+        return out
+    ok = vis >= 0
+    out[ok] = mesh.split_parent[vis[ok]]
+    return out
+
+
+def _rows_of(cells_sorted: np.ndarray, n: int, owner_int: np.ndarray, neighbour: np.ndarray):
+    """CSR of the internal-face neighbours of the listed cells (ascending), from the face lists"""
+    flag = np.zeros(n, dtype=bool)
+    flag[cells_sorted] = True
+    mo, mn = flag[owner_int], flag[neighbour]
+    a = np.concatenate([owner_int[mo], neighbour[mn]])
+    b = np.concatenate([neighbour[mo], owner_int[mn]])
+    order = np.lexsort((b, a))
+    a, b = a[order], b[order]
+    slot = np.full(n, -1, dtype=np.int64)
+    slot[cells_sorted] = np.arange(len(cells_sorted))
+    cnt = np.bincount(slot[a], minlength=len(cells_sorted))
+    off = np.zeros(len(cells_sorted) + 1, dtype=np.int32)
+    off[1:] = np.cumsum(cnt)
+    return off, np.ascontiguousarray(b, dtype=np.int32)
+
+
+def mesh_delta(old: PolyMesh, new: PolyMesh, cell_map: np.ndarray, reverse_cell_map: Optional[np.ndarray] = None,
+               points: bool = True) -> MeshDelta:
+    """old -> new through a cut (reverse_cell_map None: cells appended, labels kept) or a merge (reverse_cell_map given:
+    < 0 = removed, -(master)-2).  Dirty cells: every new cell whose set of face neighbours differs from its old row."""
+    n0, n1 = old.n, new.n
+    cell_map = np.ascontiguousarray(cell_map, dtype=np.int32)
+    own0, nei0 = old.owner[:old.f], old.neighbour
+    changed_old = np.zeros(n0, dtype=bool)                    # old cells that were cut / merged away / merged into
+    touched_new = np.zeros(n1, dtype=bool)
+    if reverse_cell_map is None:
+        added = np.arange(n0, n1)
+        cut = np.unique(cell_map[added]) if len(added) else np.zeros(0, np.int64)
+        changed_old[cut] = True
+        touched_new[added] = True
+        touched_new[cut] = True                               # the cut cell keeps its label (child 0)
+        rev = None
+    else:
+        rev = np.ascontiguousarray(reverse_cell_map, dtype=np.int32)
+        removed = rev < 0
+        changed_old[removed] = True
+        masters_new = (-rev[removed] - 2)
+        touched_new[masters_new] = True
+        changed_old[cell_map[masters_new]] = True
+    # old neighbours of changed cells: their rows lose / gain entries
+    m = changed_old[own0] | changed_old[nei0]
+    nb_old = np.unique(np.concatenate([own0[m], nei0[m]]))
+    nb_old = nb_old[~changed_old[nb_old]]
+    touched_new[nb_old if rev is None else rev[nb_old]] = True
+    dirty = np.flatnonzero(touched_new).astype(np.int32)
+    off, nbrs = _rows_of(dirty, n1, new.owner[:new.f], new.neighbour)
+    d = MeshDelta(cell_map=cell_map, reverse_cell_map=rev, dirty_cells=dirty, dirty_cell_off=off, dirty_cell_nbrs=nbrs,
+                  dirty_cell_level=np.ascontiguousarray(new.cell_level[dirty], dtype=np.int32),
+                  dirty_parent_index=np.ascontiguousarray(parent_index(new)[dirty], dtype=np.int32))
+    if not points or new.pc_off is None or old.pc_off is None:
+        return d
+    # points: matched by their integer coordinates (the engine renumbers the non-lattice points on every build)
+    def key(m_):
+        q = m_.pxyz.astype(np.int64)
+        return (q[:, 0] << 42) | (q[:, 1] << 21) | q[:, 2]
+    k0, k1 = key(old), key(new)
+    o0 = np.argsort(k0, kind="stable")
+    pos = np.searchsorted(k0[o0], k1)
+    pos[pos >= len(k0)] = 0
+    hit = k0[o0][pos] == k1 if len(k0) else np.zeros(len(k1), bool)
+    pmap = np.where(hit, o0[pos], -1).astype(np.int32)
+    # a kept point is clean when every cell around it survived unchanged (same count, none touched)
+    cnt1 = np.diff(new.pc_off)
+    bad = np.zeros(new.p, dtype=bool)
+    bad[pmap < 0] = True
+    cells_touched = np.zeros(n1, dtype=bool)
+    if rev is None:
+        cells_touched[np.arange(n0, n1)] = True
+        cells_touched[np.flatnonzero(changed_old)] = True
+    else:
+        cells_touched[masters_new] = True
+    pt_of_entry = np.repeat(np.arange(new.p), cnt1)
+    bad[pt_of_entry[cells_touched[new.pc_cells]]] = True
+    kept = np.flatnonzero(~bad)
+    bad[kept[np.diff(old.pc_off)[pmap[kept]] != cnt1[kept]]] = True
+    dp = np.flatnonzero(bad).astype(np.int32)
+    starts = new.pc_off[dp].astype(np.int64)
+    lens = cnt1[dp].astype(np.int64)
+    poff = np.zeros(len(dp) + 1, dtype=np.int32)
+    poff[1:] = np.cumsum(lens)
+    idx = np.repeat(starts - poff[:-1], lens) + np.arange(int(poff[-1]))
+    d.point_map = pmap
+    d.dirty_points = dp
+    d.dirty_point_off = poff
+    d.dirty_point_cells = np.ascontiguousarray(new.pc_cells[idx], dtype=np.int32)
+    d.dirty_bnd_point = np.ascontiguousarray(new.bnd_point[dp], dtype=np.uint8)
+    d.dirty_point_level = np.ascontiguousarray(new.point_level[dp], dtype=np.int32)
+    return d

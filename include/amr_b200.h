@@ -132,6 +132,36 @@ int amr_mesh_set(amr_ctx *ctx, int64_t n, int64_t f, int64_t b, int64_t p,
 int amr_mesh_set_points(amr_ctx *ctx, const int32_t *pcOff, const int32_t *pcCells,
                         const uint8_t *bndPoint);
 
+/* N1, second half: incremental hand-over of the ADDRESSING after a topology change
+   (hexRef::updateMesh hexRef.C:2422-2608, fvMeshHexRefiner::updateMesh fvMeshHexRefiner.C:229-240).  amr_mesh_set
+   re-uploads the whole mesh (4.7 GB at 64 M cells); these two calls carry the adjacency the context already holds
+   through the change.  The host sends the maps of mapPolyMesh and only the rows that changed:
+     cellMap [nNew]          new cell -> the old cell it came from (mapPolyMesh::cellMap(); read for clean cells only)
+     reverseCellMap [nOld]   old cell -> new label, < 0 = removed (mapPolyMesh::reverseCellMap()); NULL = labels kept,
+                             cells only appended (hexRef3D::setRefinement)
+     dirtyCells [nDirty]     ascending NEW labels of every cell whose set of face neighbours changed (cut or merged cells,
+                             added cells, and the cells next to them), dirtyCellOff/dirtyCellNbrs = their rows
+                             (internal-face neighbours, new labels; mesh.cellCells()), dirtyCellLevel = their
+                             cellLevel, dirtyParentIndex = history.parentIndex() or -1 (NULL: no history)
+     boundaryOwner [bNew]    faceOwner of the boundary faces (patch ranges as in amr_mesh_set)
+   A cell that is NOT listed keeps the row of cellMap[cell] with every neighbour renumbered through reverseCellMap;
+   a clean row that points at a removed cell, or a dirty list that is not ascending, fails with AMR_ERR_ARG.
+   The owner/neighbour face lists are not rebuilt: entry points that need them (amr_mesh_set_geometry and what
+   depends on it, the history-cluster queries) return AMR_ERR_STATE until the next amr_mesh_set.  The decision path
+   (estimators over faces, marking, 2:1 sweeps, unrefinement, maps) runs on the carried adjacency.
+   amr_mesh_update_points does the same for mesh.pointCells(), bndPoint and pointLevel_ (pointMap [pNew] = new point
+   -> old point; dirty points = new points, the points of cut / merged cells); it must follow amr_mesh_update when
+   the context held point addressing.  Collective like amr_mesh_set when a communicator is attached. */
+int amr_mesh_update(amr_ctx *ctx, int64_t nNew, int64_t fNew, int64_t bNew, int64_t pNew, const int32_t *cellMap,
+                    const int32_t *reverseCellMap, int64_t nDirtyCells, const int32_t *dirtyCells,
+                    const int32_t *dirtyCellOff, const int32_t *dirtyCellNbrs, const int32_t *dirtyCellLevel,
+                    const int32_t *dirtyParentIndex, const int32_t *boundaryOwner, int npatch,
+                    const int32_t *patchStart, const int32_t *patchSize, const int32_t *patchType,
+                    const int32_t *patchNbrRank);
+int amr_mesh_update_points(amr_ctx *ctx, const int32_t *pointMap, int64_t nDirtyPoints, const int32_t *dirtyPoints,
+                           const int32_t *dirtyPointOff, const int32_t *dirtyPointCells, const uint8_t *dirtyBndPoint,
+                           const int32_t *dirtyPointLevel);
+
 /* 2-D cutter (hexRef2D): split elements are mesh EDGES.  mesh.edges() end points [2*nEdges],
    mesh.edgeCells() as CSR, and the flag "edge belongs to a boundary face" (the loop over
    mesh_.faceEdges() at hexRef2D.C:2296-2311).  Only needed with AMR_REFINER_HEX2D. */

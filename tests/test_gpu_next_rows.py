@@ -267,3 +267,82 @@ def test_old_volumes_through_unrefinement(ctx, O):
     cm3 = np.concatenate([np.arange(100), np.repeat(np.arange(10), 7)]).astype(np.int32)
     (g3,), nm3 = ctx.map_old_volumes(cm3, np.arange(100, dtype=np.int32), [v[:100].copy()])
     assert nm3 == 0 and np.array_equal(g3, v[:100][cm3])
+
+
+def _decisions(c, O, m, x, thr=(0.01, 1e15, 0.01, 1e15)):
+    """the decision path on whatever mesh the context holds (estimate, marking + 2:1 closure, unrefinement, level check)"""
+    e = c.estimate("delta", x, thresholds=thr)
+    e2 = c.estimate("scaledDelta", x, p0=1e-3)
+    rc = np.zeros(m.n, np.uint8)
+    cells, _ = c.select_refine(e, 2, 2, refine_cell_out=rc)
+    pts, _ = c.select_unrefine(e, 1, refine_cell=rc.copy())
+    return e, e2, rc, cells.copy(), pts.copy(), c.check_levels()
+
+
+def test_incremental_mesh_update_equals_the_full_hand_over(O):
+    """N1, second half (include/amr_b200.h amr_mesh_update / amr_mesh_update_points): a context that carries its adjacency, levels
+    and point addressing through a cut and then through a merge must decide exactly like a context that received the whole
+    new mesh -- and like the oracle."""
+    from blastamr_b200 import capi
+    oc = cases.graded_octree(10, 2)
+    m0 = oc.build()
+    a, b = capi.Context(0), capi.Context(0)
+    try:
+        a.set_mesh(m0)
+        x0 = cases.front_field(m0.cc, centre=(0.55, 0.5, 0.5), r0=0.3, w=0.04)
+        e0 = a.estimate("delta", x0, thresholds=(0.01, 1e15, 0.01, 1e15))
+        cells, _ = a.select_refine(e0, 2, 1)
+        assert len(cells)
+        cm = oc.refine(cells.copy())
+        m1 = oc.build()
+        d1 = M.mesh_delta(m0, m1, cm)
+        assert len(d1.dirty_cells) < m1.n and len(d1.dirty_points) < m1.p
+        a.update_mesh(m1, d1)
+        b.set_mesh(m1)
+        x1 = cases.front_field(m1.cc, centre=(0.6, 0.5, 0.5), r0=0.3, w=0.04)
+        ra, rb = _decisions(a, O, m1, x1), _decisions(b, O, m1, x1)
+        for u, v in zip(ra, rb):
+            assert np.array_equal(u, v)
+        w = O.World([m1])
+        e = w.estimate("delta", [x1]); w.normalize(e, 0.01, 1e15, 0.01, 1e15)
+        rc, rs, _ = w.hex_select_refine(e, 2, 2)
+        up, _, _ = w.hex_select_unrefine(e, [rc[0].copy()], 1)
+        assert np.array_equal(e[0], ra[0]) and np.array_equal(np.flatnonzero(rs[0]), ra[3]) and np.array_equal(np.flatnonzero(up[0]), ra[4])
+        assert len(ra[4]) > 0 and ra[5] == 0
+        # the merge: labels are compacted (reverseCellMap), points renumbered
+        cm2, rev2 = oc.unrefine(m1, ra[4])
+        m2 = oc.build()
+        d2 = M.mesh_delta(m1, m2, cm2, rev2)
+        a.update_mesh(m2, d2)
+        b.set_mesh(m2)
+        x2 = cases.front_field(m2.cc, centre=(0.5, 0.55, 0.5), r0=0.3, w=0.04)
+        ra, rb = _decisions(a, O, m2, x2), _decisions(b, O, m2, x2)
+        for u, v in zip(ra, rb):
+            assert np.array_equal(u, v)
+        assert len(ra[3]) > 0
+        # what the incremental hand-over does not carry says so
+        with pytest.raises(capi.AmrError):
+            a.history_clusters()
+        # a delta that misses a changed cell is refused (a clean row would point at a removed cell), the context recovers
+        # with a full hand-over
+        cm3, rev3 = oc.unrefine(m2, ra[4][:1]) if len(ra[4]) else (None, None)
+        if cm3 is not None:
+            m3 = oc.build()
+            d3 = M.mesh_delta(m2, m3, cm3, rev3)
+            master = int(-rev3[rev3 < 0][0] - 2)                     # the merged cell: its old row holds the 7 removed siblings
+            keep = d3.dirty_cells != master
+            offs = d3.dirty_cell_off
+            sel = np.repeat(keep, np.diff(offs))
+            d3.dirty_cell_nbrs = np.ascontiguousarray(d3.dirty_cell_nbrs[sel])
+            d3.dirty_cell_off = np.concatenate([[0], np.cumsum(np.diff(offs)[keep])]).astype(np.int32)
+            d3.dirty_cells = np.ascontiguousarray(d3.dirty_cells[keep]); d3.dirty_cell_level = np.ascontiguousarray(d3.dirty_cell_level[keep])
+            d3.dirty_parent_index = np.ascontiguousarray(d3.dirty_parent_index[keep])
+            with pytest.raises(capi.AmrError):
+                a.update_mesh(m3, d3)
+            a.set_mesh(m3)
+            x3 = cases.front_field(m3.cc, centre=(0.5, 0.5, 0.55), r0=0.3, w=0.04)
+            b.set_mesh(m3)
+            for u, v in zip(_decisions(a, O, m3, x3), _decisions(b, O, m3, x3)):
+                assert np.array_equal(u, v)
+    finally:
+        a.close(); b.close()

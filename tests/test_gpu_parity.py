@@ -335,12 +335,14 @@ def test_no_cpu_fallback_message():
         capi.Context(9999)
 
 
-@pytest.mark.parametrize("fraction", ["1/1", "1/4", "0"])
-def test_buffer_layers_sparse_push_form(O, monkeypatch, fraction):
-    """the buffer layers (fvMeshRefiner.C:794-921) have a dense (pull) and a sparse (push) device form chosen by the
-    marked fraction; force each on the small test meshes and run the whole loop, protected patches included"""
+@pytest.mark.parametrize("fraction,pull", [("1/1", "0"), ("1/4", "1/2"), ("0", "0"), ("0", "1/1")])
+def test_buffer_layers_sparse_push_form(O, monkeypatch, fraction, pull):
+    """the buffer layers (fvMeshRefiner.C:794-921) have a dense (pull), a sparse push (rows of the sources) and a sparse pull
+    (rows of the unmarked cells) device form chosen by the marked fraction; force each on the small test meshes and run the
+    whole loop, protected patches included"""
     from blastamr_b200 import capi
     monkeypatch.setenv("AMR_B200_PUSH_FRACTION", fraction)
+    monkeypatch.setenv("AMR_B200_PULL_FRACTION", pull)
     monkeypatch.setenv("AMR_B200_PUSH_MIN_CELLS", "0")
     c = capi.Context(0)
     try:
