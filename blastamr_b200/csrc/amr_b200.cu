@@ -79,6 +79,8 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
             int a = 0, b = 1;
             if (sscanf(lf, "%d/%d", &a, &b) >= 1 && a >= 0 && b > 0) { ctx->pullNum = a; ctx->pullDen = b; }
         }
+        const char *fb = getenv("AMR_B200_FACE_BATCH");          // tuning / A-B: 0 = one face at a time in the Lohner / Gauss-gradient walks
+        if (fb && fb[0] == '0') ctx->faceBatch = false;
         const char *ht = getenv("AMR_B200_HOSTTIME");
         if (ht && ht[0] == '1') ctx->hostTime = true;
         const char *tr = getenv("AMR_B200_TRACE");
@@ -149,6 +151,7 @@ static void freeMesh(amr_ctx *ctx) {
     sellFree(ctx, ctx->cf);
     ctx->haveGeom = false;
     sellFree(ctx, ctx->ec); devFree(ctx, &ctx->bndEdge); devFree(ctx, &ctx->edgePts);
+    sellFree(ctx, ctx->ce); ctx->ceState = 0; ctx->balancedEdges = -1;
     devFree(ctx, &ctx->faceOff); devFree(ctx, &ctx->facePts); ctx->haveFaces = false;
     devFree(ctx, &ctx->polyBad); ctx->polyBadKind = -1;
     ctx->haveEdges = false; ctx->nEdges = 0;
@@ -960,6 +963,7 @@ AMR_API int amr_mesh_set_edges(amr_ctx *ctx, int64_t nEdges, const int32_t *edge
     ctx->nEdges = nEdges;
     ctx->haveEdges = true;
     ctx->polyBadKind = -1;
+    sellFree(ctx, ctx->ce); ctx->ceState = 0; ctx->balancedEdges = -1;
     return AMR_OK;
 }
 
@@ -1230,6 +1234,7 @@ AMR_API int amr_levels_set(amr_ctx *ctx, const int32_t *cellLevel, const int32_t
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->haveLevels = true;
     ctx->pcClassDirty = true; ctx->balancedLocal = -1; ctx->balancedGlobal = -1; ctx->spDirty = true; ctx->polyBadKind = -1;
+    ctx->balancedEdges = -1;
     return AMR_OK;
 }
 
@@ -1333,14 +1338,23 @@ AMR_API int amr_estimate_lohner(amr_ctx *ctx, const double *x, const double *xBo
     } else dxn = ctx->ghost64;
     Geom G{ctx->gWeights, ctx->gSf, ctx->gMagSf, ctx->gDelta, ctx->gV};
     Thresholds t = mkThr(thr);
-    if (b) LAUNCH(k_boundary_field, gridFor(b), kThreads, b, ctx->owner + f, dx, dxb, dxn, ctx->bCoupled, ctx->xbf);
+    if (b) LAUNCH(k_boundary_field, gridFor(b), kThreads, b, (const label *)ctx->bOwner, dx, dxb, dxn, ctx->bCoupled, ctx->xbf);
     if (n) {
+        if (ctx->faceBatch) {
+            LAUNCH(k_gauss_grad_batched, gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
+                   (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, ctx->grad);
+            if (scale) LAUNCH((k_lohner_batched<true>), gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
+                              (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, target);
+            else LAUNCH((k_lohner_batched<false>), gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
+                        (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, target);
+        } else {
         LAUNCH(k_gauss_grad, gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
                (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, ctx->grad);
         if (scale) LAUNCH((k_lohner<true>), gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
                           (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, target);
         else LAUNCH((k_lohner<false>), gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
                     (const double *)ctx->grad, (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, epsilon, t, target);
+        }
         if (errorOut && !devOut) { CK(cudaMemcpyAsync(errorOut, target, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream)); ctx->hostTouched = true; }
     }
     CK(cudaGetLastError());
@@ -1590,6 +1604,30 @@ static int ensureBalanceChecked(amr_ctx *ctx) {
     ctx->balancedLocal = bad == 0 ? 1 : 0;
     return AMR_OK;
 }
+// The polyRefiner's closure on the queue machinery needs (a) the cell -> edge-neighbour graph and (b) a mesh that is 2:1
+// balanced over every pair of cells sharing an edge (what refinement::edgeConsistentRefinement maintains).  Both are
+// established once per mesh; the verdict is agreed over the ranks (it selects between loops with different collectives).
+// AMR_B200_POLY_QUEUE=0 keeps the dense sweeps.
+static int ensureEdgeNeighbours(amr_ctx *ctx) {
+    if (ctx->balancedEdges >= 0) return AMR_OK;
+    const char *e = getenv("AMR_B200_POLY_QUEUE");
+    int ok = (e && e[0] == '0') ? 0 : 1;
+    if (ok && ctx->ceState == 0) {
+        TRY(sellBuildEdgeNeighbours(ctx, ctx->ce, ctx->ec, ctx->nEdges, ctx->n));
+        ctx->ceState = ctx->ce.col ? 1 : -1;
+    }
+    // a rank without cells has an empty graph: fine; a rank whose graph could not be built vetoes the queue form
+    if (ctx->ceState < 0 && ctx->n > 0 && ctx->nEdges > 0) ok = 0;
+    const int64_t n = ctx->n;
+    CK(cudaMemsetAsync(ctx->dCount + 3, 0, 8, ctx->stream));
+    if (ok && n && ctx->ce.col)
+        LAUNCH(k_check_levels, gridFor(n), kThreads, n, ctx->ce.sliceOff, ctx->ce.col, (const label *)ctx->lvl, (unsigned long long *)(ctx->dCount + 3));
+    if (!ok) { const long long one = 1; CK(cudaMemcpyAsync(ctx->dCount + 3, &one, 8, cudaMemcpyHostToDevice, ctx->stream)); }
+    int64_t bad = 0;
+    TRY(globalSum(ctx, 3, &bad));
+    ctx->balancedEdges = bad == 0 ? 1 : 0;
+    return AMR_OK;
+}
 static int ensureQueues(amr_ctx *ctx, int64_t need) {
     if (need <= ctx->queueCap) return AMR_OK;
     devFree(ctx, &ctx->queue[0]); devFree(ctx, &ctx->queue[1]);
@@ -1651,7 +1689,7 @@ static int queueLook(amr_ctx *ctx, int issued) {
 // (hexRef.C:1440-1460).  The iterations the previous call needed are enqueued in one go, each launch gated on the
 // device by the (all-reduced) size of its queue, then the list is compacted and the host looks ONCE; only if the
 // closure needed more iterations than last time does the host look again.
-static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut) {
+static int refineClosureQueue(amr_ctx *ctx, const Sell &A, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut) {
     const int64_t n = ctx->n;
     TRY(ensureQueues(ctx, n + 16));
     const bool multi = ctx->comm && ctx->nranks > 1;
@@ -1670,14 +1708,14 @@ static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int
         HaloToken halo;
         if (ctx->nCoupled > 0) TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo));
         GhostLink G = makeLink(ctx, &halo, ctx->ghost8, true);
-        LAUNCH((k_refine_linked<true>), nFix + gridFor(std::max<int64_t>(n, 1), kThreads * 16), kThreads, G, L, nFix, ctx->nCoupled, cf, bo, n, ctx->cc.sliceOff,
-               ctx->cc.col, (const u8 *)ctx->lvl8, lf, set, ((((uintptr_t)set)) & 15) == 0, (const label *)nullptr, (const int *)nullptr, ctx->queue[1],
+        LAUNCH((k_refine_linked<true>), nFix + gridFor(std::max<int64_t>(n, 1), kThreads * 16), kThreads, G, L, nFix, ctx->nCoupled, cf, bo, n, A.sliceOff,
+               A.col, (const u8 *)ctx->lvl8, lf, set, ((((uintptr_t)set)) & 15) == 0, (const label *)nullptr, (const int *)nullptr, ctx->queue[1],
                qc + 1, cap, gq + 1, (const int *)nullptr);
         ctx->peerTouched = true;
     } else {
         HaloToken halo;
         if (ctx->nCoupled > 0) TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo));     // lf as it is before the sweep, like the reference's neiLevel
-        if (n) LAUNCH(k_refine_push0, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, lf, set,
+        if (n) LAUNCH(k_refine_push0, gridFor(n, kThreads * 16), kThreads, n, A.sliceOff, A.col, (const u8 *)ctx->lvl8, lf, set,
                       ((((uintptr_t)set)) & 15) == 0, ctx->queue[1], qc + 1, cap);
         if (multi) {                  // coupled faces (hexRef.C:758-780) + reduce(nChanged): one launch on the peer transport
             GhostLink G = makeLink(ctx, &halo, ctx->ghost8, true);
@@ -1697,7 +1735,7 @@ static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int
             if (linked) {
                 GhostLink G = makeLink(ctx, nullptr, ctx->ghost8, true);
                 G.ghost = nullptr;                                     // the ghost array is the parity buffer of the closure's swap
-                LAUNCH((k_refine_linked<false>), nFix + queueGrid(ctx), kThreads, G, L, nFix, ctx->nCoupled, cf, bo, n, ctx->cc.sliceOff, ctx->cc.col,
+                LAUNCH((k_refine_linked<false>), nFix + queueGrid(ctx), kThreads, G, L, nFix, ctx->nCoupled, cf, bo, n, A.sliceOff, A.col,
                        (const u8 *)ctx->lvl8, lf, set, false, (const label *)ctx->queue[j & 1], (const int *)(qc + j), ctx->queue[(j + 1) & 1], qc + j + 1,
                        cap, gq + j + 1, gate);
                 ctx->peerTouched = true;
@@ -1706,7 +1744,7 @@ static int refineClosureQueue(amr_ctx *ctx, u8 *set, u8 *lf, int *sweepsOut, int
             }
             HaloToken halo;
             if (ctx->nCoupled > 0) TRY(haloBegin(ctx, lf, 1, ctx->ghost8, &halo, nullptr, xgate));
-            LAUNCH(k_refine_frontier, queueGrid(ctx), kThreads, ctx->cc.sliceOff, ctx->cc.col, (const u8 *)ctx->lvl8, lf, set,
+            LAUNCH(k_refine_frontier, queueGrid(ctx), kThreads, A.sliceOff, A.col, (const u8 *)ctx->lvl8, lf, set,
                    (const label *)ctx->queue[j & 1], (const int *)(qc + j), ctx->queue[(j + 1) & 1], qc + j + 1, cap, gate);
             if (multi) {
                 GhostLink G = makeLink(ctx, &halo, ctx->ghost8, true);
@@ -1774,12 +1812,18 @@ static int refineSweepsDense(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *swe
 static int refineSweeps(amr_ctx *ctx, int maxSet, u8 *set, u8 *lf, int *sweepsOut, int32_t *cellsOut, int64_t *nOut,
                         bool edgeRule = false) {
     // the queue form is only valid on a locally 2:1-balanced mesh: verified once per mesh
-    bool queueOk = maxSet && !edgeRule && ctx->pushNum > 0 && ctx->lvl;      // the same on every rank
-    if (queueOk) {
+    bool queueOk = maxSet && ctx->pushNum > 0 && ctx->lvl;      // the same on every rank
+    if (queueOk && edgeRule) {
+        // polyRefiner (refinement.C:744-810: edge rule + face rule per sweep): one rule on the graph of cells that share an
+        // edge, which contains the internal face pairs (sell.cuh); coupled faces as in the hexRefiner's loop
+        TRY(ensureEdgeNeighbours(ctx));
+        queueOk = ctx->balancedEdges == 1;
+        if (queueOk) return refineClosureQueue(ctx, ctx->ce, set, lf, sweepsOut, cellsOut, nOut);
+    } else if (queueOk) {
         TRY(ensureBalanceChecked(ctx));
         queueOk = ctx->balancedLocal == 1;
     }
-    if (queueOk) return refineClosureQueue(ctx, set, lf, sweepsOut, cellsOut, nOut);
+    if (queueOk) return refineClosureQueue(ctx, ctx->cc, set, lf, sweepsOut, cellsOut, nOut);
     return refineSweepsDense(ctx, maxSet, set, lf, sweepsOut, cellsOut, nOut, edgeRule);
 }
 
@@ -2888,9 +2932,12 @@ AMR_API int amr_estimate_gradient(amr_ctx *ctx, int scheme, const double *x, con
         }
     } else dxn = ctx->ghost64;
     Geom G{ctx->gWeights, ctx->gSf, ctx->gMagSf, ctx->gDelta, ctx->gV};
-    if (b) LAUNCH(k_boundary_field, gridFor(b), kThreads, b, ctx->owner + f, dx, dxb, dxn, ctx->bCoupled, ctx->xbf);
+    if (b) LAUNCH(k_boundary_field, gridFor(b), kThreads, b, (const label *)ctx->bOwner, dx, dxb, dxn, ctx->bCoupled, ctx->xbf);
     if (n) {
-        if (scheme == AMR_GRAD_GAUSS_LINEAR)
+        if (scheme == AMR_GRAD_GAUSS_LINEAR && ctx->faceBatch)
+            LAUNCH(k_gauss_grad_batched, gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
+                   (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, ctx->grad);
+        else if (scheme == AMR_GRAD_GAUSS_LINEAR)
             LAUNCH(k_gauss_grad, gridFor(n), kThreads, n, f, ctx->cf.sliceOff, ctx->cf.col, ctx->owner, ctx->neighbour, G, dx,
                    (const double *)ctx->xbf, dxn, (const u8 *)ctx->bCoupled, ctx->grad);
         else

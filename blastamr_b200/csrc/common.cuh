@@ -67,6 +67,7 @@ struct amr_ctx {
     // AMR_B200_TRACE=<file prefix>: a CUDA event after every launch / host round trip of this context; the time line
     // (name, microseconds since the first event) is written to <prefix>.<rank>.<ctx address> at amr_ctx_destroy.
     // Diagnosis only: the events themselves cost ~1 us each.
+    bool faceBatch = true;     // Lohner / Gauss gradient: faces of a cell four at a time (lohner.cuh); AMR_B200_FACE_BATCH=0: one at a time
     bool hostTime = false;     // AMR_B200_HOSTTIME=1: wall-clock marks of the mesh hand-over calls on stderr (diagnosis)
     double htLast = 0.0;
     bool traceOn = false;
@@ -129,6 +130,9 @@ struct amr_ctx {
     bool haveEdges = false;
     int64_t nEdges = 0;
     Sell ec;                   // edge -> cells
+    Sell ce;                   // cell -> cells sharing an edge (polyRefiner closure on the queue machinery), built on first use
+    int ceState = 0;           // 0 not built, 1 built, -1 not available (transient list too large): dense sweeps
+    int balancedEdges = -1;    // |dLevel| <= 1 over all pairs of cells sharing an edge, on every rank (-1: not checked yet)
     u8 *bndEdge = nullptr;
     label *edgePts = nullptr;  // [2*nEdges]
     // geometry (Lohner)

@@ -290,3 +290,118 @@ static int sellCarryOver(amr_ctx *ctx, Sell &out, const Sell &old, int64_t rowsN
     }
     return rc;
 }
+
+// ---- cell -> cells sharing an EDGE (polyRefiner) ------------------------------------------------------------------------
+// refinement::edgeConsistentRefinement (refinement.C:305-387) applies the 2:1 rule to every unordered pair of an edge's
+// cells.  Two cells that share a face share its edges, so on the internal faces the face rule is contained in the edge
+// rule, and the closure of both is the closure of ONE rule on the graph "cells that share an edge".  That graph in
+// SELL form lets the polyRefiner's refinement closure run on the hexRefiner's queue machinery (kernels_sparse.cuh (2)).
+// Built once per mesh from edgeCells: ordered pairs per edge -> rows with duplicates -> sorted, deduplicated rows.
+__global__ void k_ce_count(int64_t nEdges, const int32_t *__restrict__ ecOff, const int32_t *__restrict__ ecCol, const u8 *__restrict__ ecCount,
+                           int32_t *__restrict__ degRaw) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nEdges) return;
+    const int k = ecCount[e];
+    if (k < 2) return;
+    const int32_t *row = ecCol + ((size_t)ecOff[e >> 5] << 5) + (e & 31);
+    for (int i = 0; i < k; i++) atomicAdd(&degRaw[row[(size_t)i << 5]], k - 1);
+}
+__global__ void k_ce_fill(int64_t nEdges, const int32_t *__restrict__ ecOff, const int32_t *__restrict__ ecCol, const u8 *__restrict__ ecCount,
+                          const int64_t *__restrict__ rawOff, int32_t *__restrict__ cursor, int32_t *__restrict__ raw) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nEdges) return;
+    const int k = ecCount[e];
+    if (k < 2) return;
+    const int32_t *row = ecCol + ((size_t)ecOff[e >> 5] << 5) + (e & 31);
+    for (int i = 0; i < k; i++) {
+        const int32_t a = row[(size_t)i << 5];
+        const int pos = atomicAdd(&cursor[a], k - 1);
+        int o = 0;
+        for (int j = 0; j < k; j++) if (j != i) raw[rawOff[a] + pos + o++] = row[(size_t)j << 5];
+    }
+}
+// exclusive scan of int32 counts into int64 offsets: one block-sum pass + a serial pass over the block sums (host-free,
+// set-up path only)
+__global__ void k_ce_block_sums(const int32_t *__restrict__ deg, int64_t n, int64_t *__restrict__ blockSum) {
+    __shared__ long long part[kThreads / 32];
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    long long v = i < n ? deg[i] : 0;
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { long long t = 0; for (int k = 0; k < kThreads / 32; k++) t += part[k]; blockSum[blockIdx.x] = t; }
+}
+__global__ void k_ce_scan_blocks(int64_t *blockSum, int64_t nBlocks) {          // <<<1,1>>>: a few hundred thousand adds, once per mesh
+    long long run = 0;
+    for (int64_t i = 0; i < nBlocks; i++) { const long long v = blockSum[i]; blockSum[i] = run; run += v; }
+    blockSum[nBlocks] = run;
+}
+__global__ void k_ce_offsets(const int32_t *__restrict__ deg, int64_t n, const int64_t *__restrict__ blockSum, int64_t *__restrict__ off) {
+    __shared__ int smem[kThreads / 32 + 1];
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int v = i < n ? deg[i] : 0;
+    int total;
+    const int ex = blockExclusiveScan(v, smem, &total);
+    if (i < n) off[i] = blockSum[blockIdx.x] + ex;
+}
+// sort + unique each raw row in place (short rows); deg receives the number of distinct neighbours
+__global__ void k_ce_unique(int64_t n, const int64_t *__restrict__ rawOff, const int32_t *__restrict__ degRaw, int32_t *__restrict__ raw,
+                            int32_t *__restrict__ deg) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    int32_t *r = raw + rawOff[c];
+    const int d = degRaw[c];
+    for (int i = 1; i < d; i++) {
+        const int32_t v = r[i];
+        int j = i - 1;
+        while (j >= 0 && r[j] > v) { r[j + 1] = r[j]; j--; }
+        r[j + 1] = v;
+    }
+    int u = 0;
+    for (int i = 0; i < d; i++)
+        if (r[i] != (int32_t)c && (u == 0 || r[u - 1] != r[i])) r[u++] = r[i];
+    deg[c] = u;
+}
+__global__ void k_ce_to_sell(int64_t n, const int64_t *__restrict__ rawOff, const int32_t *__restrict__ raw, const int32_t *__restrict__ deg,
+                             const int32_t *__restrict__ sliceOff, int32_t *__restrict__ col) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int32_t *r = raw + rawOff[c];
+    int32_t *dst = col + ((size_t)sliceOff[c >> 5] << 5) + (c & 31);
+    const int d = deg[c];
+    for (int j = 0; j < d; j++) dst[(size_t)j << 5] = r[j];
+}
+// returns AMR_OK with out.col == nullptr when the transient pair list would not fit (the caller keeps the dense sweeps)
+static int sellBuildEdgeNeighbours(amr_ctx *ctx, Sell &out, const Sell &ec, int64_t nEdges, int64_t n) {
+    sellFree(ctx, out);
+    if (n <= 0 || nEdges <= 0 || !ec.col) return AMR_OK;
+    int32_t *degRaw = nullptr, *cursor = nullptr, *deg = nullptr, *raw = nullptr;
+    int64_t *rawOff = nullptr, *blockSum = nullptr;
+    const int64_t nBlocks = (n + kThreads - 1) / kThreads;
+    auto release = [&]() { cudaFree(degRaw); cudaFree(cursor); cudaFree(deg); cudaFree(raw); cudaFree(rawOff); cudaFree(blockSum); };
+    if (cudaMalloc((void **)&degRaw, (size_t)(n + 1) * 4) != cudaSuccess || cudaMalloc((void **)&cursor, (size_t)(n + 1) * 4) != cudaSuccess ||
+        cudaMalloc((void **)&deg, (size_t)(n + 1) * 4) != cudaSuccess || cudaMalloc((void **)&rawOff, (size_t)(n + 1) * 8) != cudaSuccess ||
+        cudaMalloc((void **)&blockSum, (size_t)(nBlocks + 1) * 8) != cudaSuccess) { cudaGetLastError(); release(); return AMR_OK; }
+    cudaMemsetAsync(degRaw, 0, (size_t)(n + 1) * 4, ctx->stream);
+    cudaMemsetAsync(cursor, 0, (size_t)(n + 1) * 4, ctx->stream);
+    LAUNCH(k_ce_count, gridFor(nEdges), kThreads, nEdges, (const int32_t *)ec.sliceOff, (const int32_t *)ec.col, (const u8 *)ec.count, degRaw);
+    LAUNCH(k_ce_block_sums, (unsigned)nBlocks, kThreads, (const int32_t *)degRaw, n, blockSum);
+    LAUNCH(k_ce_scan_blocks, 1, 1, blockSum, nBlocks);
+    LAUNCH(k_ce_offsets, (unsigned)nBlocks, kThreads, (const int32_t *)degRaw, n, (const int64_t *)blockSum, rawOff);
+    long long total = 0;
+    if (cudaMemcpyAsync(&total, blockSum + nBlocks, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        ctx->err = "sellBuildEdgeNeighbours: count pass failed"; cudaGetLastError(); release(); return AMR_ERR_CUDA;
+    }
+    size_t freeB = 0, totalB = 0;
+    cudaMemGetInfo(&freeB, &totalB);
+    if (total <= 0 || (size_t)total * 4 > freeB / 2 || cudaMalloc((void **)&raw, (size_t)total * 4) != cudaSuccess) { cudaGetLastError(); release(); return AMR_OK; }
+    LAUNCH(k_ce_fill, gridFor(nEdges), kThreads, nEdges, (const int32_t *)ec.sliceOff, (const int32_t *)ec.col, (const u8 *)ec.count, (const int64_t *)rawOff, cursor, raw);
+    LAUNCH(k_ce_unique, gridFor(n), kThreads, n, (const int64_t *)rawOff, (const int32_t *)degRaw, raw, deg);
+    int rc = sellAllocFromDeg(ctx, out, n, deg, 1);
+    if (rc == AMR_OK) {
+        LAUNCH(k_ce_to_sell, gridFor(n), kThreads, n, (const int64_t *)rawOff, (const int32_t *)raw, (const int32_t *)deg, (const int32_t *)out.sliceOff, out.col);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "sellBuildEdgeNeighbours: fill failed"; cudaGetLastError(); rc = AMR_ERR_CUDA; }
+    }
+    release();
+    return rc;
+}

@@ -229,6 +229,15 @@ def test_amr_loop_polyRefiner(ctx, O, n0, maxlev, layers):
         assert lv[cs].max() - lv[cs].min() <= 1
 
 
+def test_amr_loop_polyRefiner_dense_sweeps(ctx, O, monkeypatch):
+    """the polyRefiner's refinement closure has two device forms: queue iterations on the graph of cells that share an edge
+    (default on edge-balanced meshes) and dense edge + face sweeps; this forces the sweeps on the same loop"""
+    monkeypatch.setenv("AMR_B200_POLY_QUEUE", "0")
+    oc = M.Octree(8, 8, 8, (1.0, 1.0, 1.0), 2)
+    st = amr_loop(ctx, O, oc, moving_front(0.06), steps=6, maxlev=2, layers_ref=1, layers_unref=2, refiner="poly")
+    assert st["refined"] > 0 and st["unrefined"] > 0
+
+
 @pytest.mark.parametrize("n0,maxlev,layers", [(16, 2, (3, 2)), (20, 3, (3, 2))])
 def test_amr_loop_polyRefiner_2d_prismatic(ctx, O, n0, maxlev, layers):
     """polyRefiner on a 2-D mesh = prismatic2DRefinement (fvMeshPolyRefiner.C:139-155): same marking and
