@@ -79,8 +79,8 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
             int a = 0, b = 1;
             if (sscanf(lf, "%d/%d", &a, &b) >= 1 && a >= 0 && b > 0) { ctx->pullNum = a; ctx->pullDen = b; }
         }
-        const char *fb = getenv("AMR_B200_FACE_BATCH");          // tuning / A-B: 0 = one face at a time in the Lohner / Gauss-gradient walks
-        if (fb && fb[0] == '0') ctx->faceBatch = false;
+        const char *fb = getenv("AMR_B200_FACE_BATCH");          // tuning / A-B: 1 = four faces at a time in the Lohner / Gauss-gradient walks
+        if (fb && fb[0] == '1') ctx->faceBatch = true;
         const char *ht = getenv("AMR_B200_HOSTTIME");
         if (ht && ht[0] == '1') ctx->hostTime = true;
         const char *tr = getenv("AMR_B200_TRACE");
@@ -2256,23 +2256,31 @@ static int unrefineClosureQueue(amr_ctx *ctx, const double *dErr, double unrefin
 static int unrefineSweeps(amr_ctx *ctx, const Sell &EL, u8 *pflag, int *sweepsOut, int32_t *elemsOut, int64_t *nOut,
                           bool edgeRule = false) {
     const int64_t n = ctx->n, p = EL.rows;
+    // polyRefiner: the edge rule (refinement.C:511-604) + the face rule over the internal faces are ONE cell-centric rule on
+    // the graph of cells that share an edge (sell.cuh), walked for the marked cells only -- no pass over all mesh edges
+    const Sell *A = &ctx->cc;
+    bool edgeKernel = edgeRule && ctx->nEdges;
+    if (edgeKernel && ctx->lvl) {
+        TRY(ensureEdgeNeighbours(ctx));
+        if (ctx->ceState == 1) { A = &ctx->ce; edgeKernel = false; }
+    }
     u8 *uc = ctx->flagB;     // unrefineCell
     const bool alP = (((uintptr_t)pflag) & 15) == 0, alC = (((uintptr_t)uc) & 15) == 0;
     const unsigned gP = gridFor(p, kThreads * 16), gC = gridFor(n, kThreads * 16);
     int sweeps = 0;
     while (true) {
         CK(cudaMemsetAsync(uc, 0, (size_t)n, ctx->stream));
-        if (p) LAUNCH(k_points_to_cells, gP, kThreads, p, EL.sliceOff, EL.col, pflag, alP, uc);
+        if (p) LAUNCH(k_points_to_cells, gP, kThreads, p, EL.sliceOff, EL.col, pflag, alP, uc, (const u8 *)nullptr);
         CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(int), ctx->stream));
         if (ctx->nCoupled > 0) {
             TRY(haloSwapCells(ctx, ctx->lvl8, 1, ctx->ghost8, uc));
         }
-        if (n) LAUNCH(k_unrefine_sweep, gC, kThreads, n, ctx->cc.sliceOff, ctx->cc.col, ctx->lvl8, uc, alC, ctx->dFlags);
+        if (n) LAUNCH(k_unrefine_sweep, gC, kThreads, n, A->sliceOff, A->col, ctx->lvl8, uc, alC, ctx->dFlags);
         if (ctx->nCoupled > 0)      // hexRef3D.C:1855-1889
             LAUNCH(k_fix_unrefine_sweep, gridFor(ctx->nCoupled), kThreads, ctx->nCoupled, (const label *)ctx->cplFace,
                    (const label *)ctx->bOwner, (const u8 *)ctx->lvl8, (const u8 *)ctx->ghost8, uc, ctx->dFlags);
         // polyhedralRefinement.C:2278-2286: faceConsistentUnrefinement, then edgeConsistentUnrefinement
-        if (edgeRule && ctx->nEdges)
+        if (edgeKernel)
             LAUNCH(k_edge_unrefine_sweep, gridFor(ctx->nEdges), kThreads, ctx->nEdges, ctx->ec.sliceOff, ctx->ec.col, (const u8 *)ctx->lvl8, uc, ctx->dFlags);
         sweeps++;
         int changed = 0;
@@ -2365,10 +2373,12 @@ AMR_API int amr_select_unrefine(amr_ctx *ctx, const double *error, double unrefi
     if (poly) {
         // extendMarkedCellsAcrossPoints (fvMeshRefiner.C:924-977): cells -> points -> cells, in place (flags only grow)
         for (int i = 0; i < nBufferLayers; i++) {
-            if (p) LAUNCH(k_cells_to_points_or, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const u8 *)cur, ctx->flagC);
+            // flagA: the point still has an unmarked cell on this rank -- only those points have anything to scatter (the marking
+            // covers whole regions, the points that change it lie on its boundary)
+            if (p) LAUNCH(k_cells_to_points_or, gridFor(p), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const u8 *)cur, ctx->flagC, ctx->flagA);
             TRY(syncPointsOr(ctx, ctx->flagC));                      // syncTools::syncPointList, fvMeshRefiner.C:952-958
             if (p) LAUNCH(k_points_to_cells, gridFor(p, kThreads * 16), kThreads, p, ctx->pc.sliceOff, ctx->pc.col, (const u8 *)ctx->flagC,
-                          (((uintptr_t)ctx->flagC) & 15) == 0, cur);
+                          (((uintptr_t)ctx->flagC) & 15) == 0, cur, (const u8 *)ctx->flagA);
         }
     } else {
         for (int i = 0; i < nBufferLayers; i++) {

@@ -67,7 +67,7 @@ struct amr_ctx {
     // AMR_B200_TRACE=<file prefix>: a CUDA event after every launch / host round trip of this context; the time line
     // (name, microseconds since the first event) is written to <prefix>.<rank>.<ctx address> at amr_ctx_destroy.
     // Diagnosis only: the events themselves cost ~1 us each.
-    bool faceBatch = true;     // Lohner / Gauss gradient: faces of a cell four at a time (lohner.cuh); AMR_B200_FACE_BATCH=0: one at a time
+    bool faceBatch = false;    // Lohner / Gauss gradient: faces of a cell four at a time (lohner.cuh); AMR_B200_FACE_BATCH=1 selects it: measured slower (151 registers), profiles/r2_lohner_timing.json
     bool hostTime = false;     // AMR_B200_HOSTTIME=1: wall-clock marks of the mesh hand-over calls on stderr (diagnosis)
     double htLast = 0.0;
     bool traceOn = false;

@@ -683,23 +683,24 @@ k_or_scatter(int64_t count, const label *__restrict__ idx, const u8 *__restrict_
 // when any of its cells is (the second half, points -> cells, is k_points_to_cells)
 __global__ void __launch_bounds__(kThreads)
 k_cells_to_points_or(int64_t p, const int32_t *__restrict__ pcOff, const int32_t *__restrict__ pcCol,
-                     const u8 *__restrict__ marked, u8 *__restrict__ pflag) {
+                     const u8 *__restrict__ marked, u8 *__restrict__ pflag, u8 *__restrict__ pneed) {
     const int64_t pt = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (pt >= p) return;
     const int32_t base = pcOff[pt >> 5];
     const int w = pcOff[(pt >> 5) + 1] - base;
     const int32_t *row = pcCol + ((size_t)base << 5) + (pt & 31);
-    unsigned m = 0;
-    for (int j0 = 0; j0 < w && !m; j0 += 8) {
+    unsigned m = 0, un = 0;                   // a marked cell / an unmarked cell among the point's cells
+    for (int j0 = 0; j0 < w; j0 += 8) {
         int32_t c[8];
         rowLabels8(row, w, j0, c);
         unsigned v[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = c[k] >= 0 ? (unsigned)marked[c[k]] : 0u;
+        for (int k = 0; k < 8; k++) v[k] = c[k] >= 0 ? (unsigned)marked[c[k]] : 0xffffu;
 #pragma unroll
-        for (int k = 0; k < 8; k++) m |= v[k];
+        for (int k = 0; k < 8; k++) { if (v[k] == 0u) un = 1; else if (v[k] != 0xffffu) m = 1; }
     }
     pflag[pt] = m ? 1 : 0;
+    if (pneed) pneed[pt] = un ? 1 : 0;
 }
 
 // polyhedralRefinement split-point markup, face-centric (polyhedralRefinement.C:2110-2184): every point of a
@@ -835,8 +836,9 @@ __device__ __forceinline__ void forEachSetWarp(const u8 *flags, int64_t N, bool 
 // unrefineCell = union of pointCells over flagged points (hexRef3D.C:1763-1776); cells pre-zeroed
 __global__ void __launch_bounds__(kThreads)
 k_points_to_cells(int64_t p, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col,
-                  const u8 *__restrict__ pflag, bool aligned, u8 *__restrict__ cflag) {
+                  const u8 *__restrict__ pflag, bool aligned, u8 *__restrict__ cflag, const u8 *__restrict__ need) {
     forEachSet16(pflag, p, aligned, [&](int64_t pt) {
+        if (need && !need[pt]) return;          // all cells of the point are set already
         const int32_t base = sliceOff[pt >> 5];
         const int w = sliceOff[(pt >> 5) + 1] - base;
         const int32_t *row = col + ((size_t)base << 5) + (pt & 31);
@@ -868,10 +870,15 @@ k_unrefine_sweep(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t 
         const int32_t *row = col + ((size_t)base << 5) + (c & 31);
         const int mine = (int)lvl8[c] - 1;
         int mx = 0;
-        for (int j = 0; j < w; j++) {
-            const int32_t q = row[(size_t)j << 5];
-            const int v = (int)lvl8[q] - (int)uc[q];        // coupled faces: k_fix_unrefine_sweep
-            mx = max(mx, v);
+        for (int j0 = 0; j0 < w; j0 += 8) {                  // 8 neighbours per round, gathers batched (rows of the edge graph are long)
+            int32_t q[8];
+            int lq[8], uq[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { lq[k] = lvl8[q[k]]; uq[k] = uc[q[k]]; }     // coupled faces: k_fix_unrefine_sweep
+#pragma unroll
+            for (int k = 0; k < 8; k++) mx = max(mx, lq[k] - uq[k]);
         }
         if (mine < mx - 1) { uc[c] = 0; *changed = 1; }
     });
