@@ -837,9 +837,14 @@ def main():
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     barrier()
+    nvtx = os.environ.get("BENCH_NVTX") == "1"            # profiling aid: `ncu --nvtx --nvtx-include "amr_step/"` sees the timed steps only
     t_start.record()
     for k in range(args.steps):
+        if nvtx:
+            torch.cuda.nvtx.range_push("amr_step")
         step(evs[k])
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
     t_end.record()
     barrier()
     clocks = sampler.stop()

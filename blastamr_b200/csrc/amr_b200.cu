@@ -22,24 +22,33 @@
 constexpr size_t kPipeSmemLimit = 96 * 1024;   // beyond this the ring would cost too much occupancy: direct kernels
 
 static bool pipeOk(const amr_ctx *ctx, const Sell &S) {
-    return ctx->usePipeline && S.rows > 0 && pipeSmemBytes(S.maxTileInts) <= kPipeSmemLimit;
+    return ctx->usePipeline && S.rows > 0 && pipeSmemBytes(S.maxTileInts, 2) <= kPipeSmemLimit;
 }
 
 template <class K, class... Args>
 static int launchPipe(amr_ctx *ctx, K kern, const Sell &S, Args... args) {
     // meshes without processor patches have no cell that waits for a boundary fix-up: no per-slice flag to fetch (the
     // flag load sits right before the tile wait and cost ~20 % of kp_estimate's stall samples, profiles/r1_ncu_full.csv)
-    SellView V{S.sliceOff, S.col, S.rows, S.slices, S.maxTileInts, ctx->nCoupled > 0 ? S.sliceGhost : (const u8 *)nullptr};
-    const size_t smem = pipeSmemBytes(V.stageInts);
+    SellView V{S.sliceOff, S.col, S.rows, S.slices, S.maxTileInts, kStages, ctx->nCoupled > 0 ? S.sliceGhost : (const u8 *)nullptr};
+    // Ring depth: three stages unless the largest tile of THIS mesh makes them cost resident CTAs (a graded mesh has slices
+    // of width 9-24 next to the usual 6-7, and the stage is sized for the worst tile: 4 CTAs per SM instead of 7,
+    // profiles/r2_ncu_full.csv) -- then two stages, which the larger number of resident CTAs more than makes up for.
     const void *key = (const void *)kern;
     auto it = ctx->occCache.find(key);
     int perSM;
     if (it == ctx->occCache.end()) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemLimit));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kPipeThreads, smem));
+        int p3 = 0, p2 = 0;
+        if (pipeSmemBytes(V.stageInts, 3) <= kPipeSmemLimit) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p3, kern, kPipeThreads, pipeSmemBytes(V.stageInts, 3)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, kern, kPipeThreads, pipeSmemBytes(V.stageInts, 2)));
+        int stages = (p3 >= 6 || p3 >= p2) ? 3 : 2;
+        if (ctx->pipeStagesForced == 2 || ctx->pipeStagesForced == 3) stages = (ctx->pipeStagesForced == 3 && p3 < 1) ? 2 : ctx->pipeStagesForced;
+        perSM = stages == 3 ? p3 : p2;
         if (perSM < 1) perSM = 1;
-        ctx->occCache[key] = perSM;
-    } else perSM = it->second;
+        ctx->occCache[key] = perSM * 4 + stages;
+    } else perSM = it->second / 4;
+    V.stages = ctx->occCache[key] % 4;
+    const size_t smem = pipeSmemBytes(V.stageInts, V.stages);
     const int64_t ntiles = (S.slices + kTileSlices - 1) / kTileSlices;
     int64_t grid = (int64_t)ctx->numSMs * perSM;
     if (grid > ntiles) grid = ntiles;
@@ -81,6 +90,8 @@ AMR_API int amr_ctx_create(int device, amr_ctx **out) {
         }
         const char *fb = getenv("AMR_B200_FACE_BATCH");          // tuning / A-B: 1 = four faces at a time in the Lohner / Gauss-gradient walks
         if (fb && fb[0] == '1') ctx->faceBatch = true;
+        const char *ps = getenv("AMR_B200_PIPE_STAGES");          // tuning / A-B: 2 or 3 ring stages (default: chosen per mesh)
+        if (ps) ctx->pipeStagesForced = atoi(ps);
         const char *ht = getenv("AMR_B200_HOSTTIME");
         if (ht && ht[0] == '1') ctx->hostTime = true;
         const char *tr = getenv("AMR_B200_TRACE");

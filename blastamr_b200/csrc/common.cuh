@@ -95,6 +95,7 @@ struct amr_ctx {
     unsigned long long *redVal = nullptr;   // device staging word for reductions
     std::string err;
     int numSMs = 148;
+    int pipeStagesForced = 0;                      // AMR_B200_PIPE_STAGES
     bool usePipeline = true;                       // TMA-staged SELL kernels (AMR_B200_NO_PIPELINE=1 disables)
     std::unordered_map<const void *, int> occCache; // kernel -> resident CTAs per SM at the current smem size
     int64_t launches = 0;

@@ -14,7 +14,7 @@
 constexpr int kTileSlices = 8;                       // slices per tile
 constexpr int kTileRows = kTileSlices * kSlice;      // 256 rows per tile
 constexpr int kPipeThreads = kTileRows + 32;         // 8 consumer warps + 1 producer warp
-constexpr int kStages = 3;
+constexpr int kStages = 3;                           // ring depth at most; SellView::stages (2 or 3) is what a launch uses
 constexpr int kHdrInts = 12;                         // slice offsets of a tile (9 used), 48 B = 3 x 16 B
 
 __device__ __forceinline__ unsigned smemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -58,12 +58,13 @@ struct SellView {
     const int32_t *col;
     int64_t rows, slices;
     int stageInts;             // capacity of one ring stage in int32 (>= largest tile)
+    int stages;                // ring depth of this launch: 3, or 2 when three stages of this mesh's largest tile would cost resident CTAs
     const u8 *sliceGhost;      // [slices] slice holds a cell that owns a coupled face, or nullptr
 };
 
 // dynamic shared memory layout: [kStages][stageInts] labels | [kStages][kHdrInts] headers | barriers
-__host__ __device__ inline size_t pipeSmemBytes(int stageInts) {
-    return (size_t)kStages * stageInts * 4 + (size_t)kStages * kHdrInts * 4 + 2 * kStages * 8 + 64;
+__host__ __device__ inline size_t pipeSmemBytes(int stageInts, int stages = kStages) {
+    return (size_t)stages * stageInts * 4 + (size_t)kStages * kHdrInts * 4 + 2 * kStages * 8 + 64;
 }
 
 // Body signature: void body(int64_t row, bool valid, const int32_t* rowLabels /*smem, stride 32*/, int width, bool ghostSlice)
@@ -73,14 +74,15 @@ template <class Body>
 __device__ __forceinline__ void sellPipeline(const SellView &S, Body body) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     int32_t *ring = reinterpret_cast<int32_t *>(smemRaw);
-    int32_t *hdr = ring + (size_t)kStages * S.stageInts;
+    const int nStages = S.stages;
+    int32_t *hdr = ring + (size_t)nStages * S.stageInts;
     uint64_t *full = reinterpret_cast<uint64_t *>(hdr + kStages * kHdrInts);
     uint64_t *empty = full + kStages;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) { mbarInit(&full[s], 1); mbarInit(&empty[s], kTileSlices); }
+        for (int s = 0; s < nStages; s++) { mbarInit(&full[s], 1); mbarInit(&empty[s], kTileSlices); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -101,7 +103,7 @@ __device__ __forceinline__ void sellPipeline(const SellView &S, Body body) {
                 mbarExpectTx(&full[stage], bytes + kHdrInts * 4);
                 bulkLoad(hdr + stage * kHdrInts, S.sliceOff + s0, kHdrInts * 4, &full[stage], pol);
                 if (bytes) bulkLoad(ring + (size_t)stage * S.stageInts, S.col + ((size_t)b0 << 5), bytes, &full[stage], pol);
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                if (++stage == nStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else {
@@ -121,7 +123,7 @@ __device__ __forceinline__ void sellPipeline(const SellView &S, Body body) {
             body(row, sliceValid && row < S.rows, ring + (size_t)stage * S.stageInts + ((size_t)base << 5) + lane, w, ghostSlice != 0);
             __syncwarp();
             if (lane == 0) mbarArrive(&empty[stage]);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            if (++stage == nStages) { stage = 0; phase ^= 1u; }
         }
     }
 }
