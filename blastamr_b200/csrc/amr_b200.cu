@@ -29,10 +29,9 @@ template <class K, class... Args>
 static int launchPipe(amr_ctx *ctx, K kern, const Sell &S, Args... args) {
     // meshes without processor patches have no cell that waits for a boundary fix-up: no per-slice flag to fetch (the
     // flag load sits right before the tile wait and cost ~20 % of kp_estimate's stall samples, profiles/r1_ncu_full.csv)
-    SellView V{S.sliceOff, S.col, S.rows, S.slices, S.maxTileInts, kStages, ctx->nCoupled > 0 ? S.sliceGhost : (const u8 *)nullptr};
-    // Ring depth: three stages unless the largest tile of THIS mesh makes them cost resident CTAs (a graded mesh has slices
-    // of width 9-24 next to the usual 6-7, and the stage is sized for the worst tile: 4 CTAs per SM instead of 7,
-    // profiles/r2_ncu_full.csv) -- then two stages, which the larger number of resident CTAs more than makes up for.
+    SellView V{S.sliceOff, S.col, S.rows, S.slices, S.tileFirst, S.tiles, S.maxTileInts, kStages, ctx->nCoupled > 0 ? S.sliceGhost : (const u8 *)nullptr};
+    // Ring depth: three stages (two only when three do not fit at all); the stage is kept small by capping the columns of
+    // a tile (sell.cuh), not by a shallower ring.
     const void *key = (const void *)kern;
     auto it = ctx->occCache.find(key);
     int perSM;
@@ -41,7 +40,7 @@ static int launchPipe(amr_ctx *ctx, K kern, const Sell &S, Args... args) {
         int p3 = 0, p2 = 0;
         if (pipeSmemBytes(V.stageInts, 3) <= kPipeSmemLimit) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p3, kern, kPipeThreads, pipeSmemBytes(V.stageInts, 3)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, kern, kPipeThreads, pipeSmemBytes(V.stageInts, 2)));
-        int stages = (p3 >= 6 || p3 >= p2) ? 3 : 2;
+        int stages = p3 >= 1 ? 3 : 2;         // (two stages with more resident CTAs were measured SLOWER: 0.54 vs 0.35 ms for kp_estimate at 23.7 M cells)
         if (ctx->pipeStagesForced == 2 || ctx->pipeStagesForced == 3) stages = (ctx->pipeStagesForced == 3 && p3 < 1) ? 2 : ctx->pipeStagesForced;
         perSM = stages == 3 ? p3 : p2;
         if (perSM < 1) perSM = 1;
@@ -49,7 +48,7 @@ static int launchPipe(amr_ctx *ctx, K kern, const Sell &S, Args... args) {
     } else perSM = it->second / 4;
     V.stages = ctx->occCache[key] % 4;
     const size_t smem = pipeSmemBytes(V.stageInts, V.stages);
-    const int64_t ntiles = (S.slices + kTileSlices - 1) / kTileSlices;
+    const int64_t ntiles = S.tiles;
     int64_t grid = (int64_t)ctx->numSMs * perSM;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;

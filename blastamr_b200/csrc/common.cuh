@@ -43,7 +43,9 @@ struct Sell {
     int32_t *sliceOff = nullptr;  // [slices+1], exclusive prefix of the slice widths
     int32_t *col = nullptr;       // [entries]
     u8 *count = nullptr;          // [rows] true row length (saturated at 255)
-    int maxTileInts = 0;          // largest 8-slice tile, in int32 (ring stage capacity of the TMA pipeline)
+    int maxTileInts = 0;          // largest tile, in int32 (ring stage capacity of the TMA pipeline)
+    int32_t *tileFirst = nullptr; // [tiles + 1] first slice of every tile: up to 8 consecutive slices whose columns fit kTileCapCols
+    int64_t tiles = 0;
     u8 *sliceGhost = nullptr;     // [slices] slice holds a cell that owns a coupled face (the estimators keep those raw until
                                   // the boundary fix-up has folded the patch faces in); cell->cell only
 };

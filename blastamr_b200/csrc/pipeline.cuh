@@ -15,7 +15,8 @@ constexpr int kTileSlices = 8;                       // slices per tile
 constexpr int kTileRows = kTileSlices * kSlice;      // 256 rows per tile
 constexpr int kPipeThreads = kTileRows + 32;         // 8 consumer warps + 1 producer warp
 constexpr int kStages = 3;                           // ring depth at most; SellView::stages (2 or 3) is what a launch uses
-constexpr int kHdrInts = 12;                         // slice offsets of a tile (9 used), 48 B = 3 x 16 B
+constexpr int kHdrInts = 16;                         // slice offsets of a tile: 9 used, fetched from the 16-byte aligned address below the
+                                                     // tile's first slice (a TMA bulk copy needs 16-byte alignment; tiles start anywhere)
 
 __device__ __forceinline__ unsigned smemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint64_t *bar, unsigned count) {
@@ -57,6 +58,8 @@ struct SellView {
     const int32_t *sliceOff;   // [slices + 16], tail padded
     const int32_t *col;
     int64_t rows, slices;
+    const int32_t *tileFirst;  // [tiles + 1] first slice of every tile (<= 8 slices, columns capped: sell.cuh)
+    int64_t tiles;
     int stageInts;             // capacity of one ring stage in int32 (>= largest tile)
     int stages;                // ring depth of this launch: 3, or 2 when three stages of this mesh's largest tile would cost resident CTAs
     const u8 *sliceGhost;      // [slices] slice holds a cell that owns a coupled face, or nullptr
@@ -87,7 +90,7 @@ __device__ __forceinline__ void sellPipeline(const SellView &S, Body body) {
     }
     __syncthreads();
 
-    const int64_t ntiles = (S.slices + kTileSlices - 1) / kTileSlices;
+    const int64_t ntiles = S.tiles;
     if (warp == kTileSlices) {
         // ---------------- producer warp (one elected lane drives the TMA engine)
         if (lane == 0) {
@@ -96,12 +99,12 @@ __device__ __forceinline__ void sellPipeline(const SellView &S, Body body) {
             unsigned phase = 0;
             for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 mbarWait(&empty[stage], phase ^ 1u);
-                const int64_t s0 = t * kTileSlices;
-                const int64_t s1 = min(s0 + (int64_t)kTileSlices, S.slices);
+                const int64_t s0 = S.tileFirst[t];
+                const int64_t s1 = S.tileFirst[t + 1];
                 const int32_t b0 = S.sliceOff[s0], b1 = S.sliceOff[s1];
                 const unsigned bytes = (unsigned)(b1 - b0) * 128u;
                 mbarExpectTx(&full[stage], bytes + kHdrInts * 4);
-                bulkLoad(hdr + stage * kHdrInts, S.sliceOff + s0, kHdrInts * 4, &full[stage], pol);
+                bulkLoad(hdr + stage * kHdrInts, S.sliceOff + (s0 & ~(int64_t)3), kHdrInts * 4, &full[stage], pol);
                 if (bytes) bulkLoad(ring + (size_t)stage * S.stageInts, S.col + ((size_t)b0 << 5), bytes, &full[stage], pol);
                 if (++stage == nStages) { stage = 0; phase ^= 1u; }
             }
@@ -111,13 +114,14 @@ __device__ __forceinline__ void sellPipeline(const SellView &S, Body body) {
         int stage = 0;
         unsigned phase = 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const int64_t s = t * kTileSlices + warp;
-            // per-slice flag fetched BEFORE the wait so that its latency hides behind the tile's arrival
-            const unsigned ghostSlice = S.sliceGhost ? S.sliceGhost[s] : 0u;
+            // tile bounds (and the per-slice flag) fetched BEFORE the wait so that their latency hides behind the tile's arrival
+            const int64_t t0s = S.tileFirst[t], t1s = S.tileFirst[t + 1];
+            const int64_t s = t0s + warp;
+            const bool sliceValid = s < t1s;
+            const unsigned ghostSlice = (S.sliceGhost && sliceValid) ? S.sliceGhost[s] : 0u;
             mbarWait(&full[stage], phase);
-            const int32_t *h = hdr + stage * kHdrInts;
+            const int32_t *h = hdr + stage * kHdrInts + (int)(t0s & 3);
             const int64_t row = s * 32 + lane;
-            const bool sliceValid = s < S.slices;
             int32_t base = 0, w = 0;
             if (sliceValid) { base = h[warp] - h[0]; w = h[warp + 1] - h[warp]; }
             body(row, sliceValid && row < S.rows, ring + (size_t)stage * S.stageInts + ((size_t)base << 5) + lane, w, ghostSlice != 0);

@@ -9,6 +9,8 @@
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
+#include <algorithm>
+#include <vector>
 
 __global__ void k_deg_internal(const label *__restrict__ owner, const label *__restrict__ neighbour, int64_t f,
                                int32_t *__restrict__ deg) {
@@ -98,6 +100,7 @@ __global__ void k_fill_tail(int32_t *__restrict__ sliceOff, int64_t slices, int 
 }
 
 constexpr int kSliceOffPad = 16;
+constexpr int kTileCapCols = 64;        // columns (128-byte lines) of a pipeline tile: 8 KB per ring stage
 
 __global__ void k_slice_ghost_cells(const u8 *__restrict__ cellGhost, int64_t rows, u8 *__restrict__ sliceGhost) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,6 +109,7 @@ __global__ void k_slice_ghost_cells(const u8 *__restrict__ cellGhost, int64_t ro
 
 static void sellFree(amr_ctx *ctx, Sell &S) {
     if (S.sliceGhost) { cudaFree(S.sliceGhost); }
+    if (S.tileFirst) { cudaFree(S.tileFirst); }
     if (S.sliceOff) { cudaFree(S.sliceOff); ctx->devBytes -= (int64_t)((S.slices + kSliceOffPad) * 4); }
     if (S.col) { cudaFree(S.col); ctx->devBytes -= (int64_t)(S.entries * 4 > 4 ? S.entries * 4 : 4); }
     if (S.count) { cudaFree(S.count); ctx->devBytes -= (int64_t)(S.rows > 0 ? S.rows : 1); }
@@ -127,13 +131,32 @@ static int sellAllocFromDeg(amr_ctx *ctx, Sell &S, int64_t rows, int32_t *deg, i
     if (rc != AMR_OK) { cudaFree(aux); return rc; }
     int32_t total = 0;
     LAUNCH(k_fill_tail, 1, 32, S.sliceOff, S.slices, kSliceOffPad - 1);
-    CK(cudaMemsetAsync(ctx->dFlags + 4, 0, sizeof(int), ctx->stream));
-    if (S.slices > 0) LAUNCH(k_max_tile, gridFor((S.slices + 7) / 8), kThreads, S.sliceOff, S.slices, 8, ctx->dFlags + 4);
-    CK(cudaMemcpyAsync(&total, S.sliceOff + S.slices, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    int maxTile = 0;
-    CK(cudaMemcpyAsync(&maxTile, ctx->dFlags + 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    S.maxTileInts = maxTile * 32;
+    // Tiles of the TMA pipeline (pipeline.cuh): up to 8 consecutive slices whose columns fit kTileCapCols, so that the ring
+    // stage stays small on graded meshes too (a few slices next to a level jump are 9-24 columns wide; sizing the stage for
+    // the widest run of 8 slices costs resident CTAs: profiles/r2_ncu_full.csv).  Greedy and sequential: done on the host
+    // from the slice offsets (4 B per 32 rows), once per mesh.
+    {
+        std::vector<int32_t> off((size_t)S.slices + 1);
+        CK(cudaMemcpyAsync(off.data(), S.sliceOff, (size_t)(S.slices + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        total = off[(size_t)S.slices];
+        std::vector<int32_t> first;
+        first.reserve((size_t)S.slices / 8 + 2);
+        int maxCols = 0;
+        for (int64_t s0 = 0; s0 < S.slices;) {
+            int64_t s1 = s0 + 1;
+            while (s1 < S.slices && s1 - s0 < 8 && off[(size_t)s1 + 1] - off[(size_t)s0] <= kTileCapCols) s1++;
+            first.push_back((int32_t)s0);
+            maxCols = std::max(maxCols, off[(size_t)s1] - off[(size_t)s0]);
+            s0 = s1;
+        }
+        S.tiles = (int64_t)first.size();
+        first.push_back((int32_t)S.slices);
+        S.maxTileInts = maxCols * 32;
+        TRY(devAlloc(ctx, &S.tileFirst, (int64_t)first.size()));
+        CK(cudaMemcpyAsync(S.tileFirst, first.data(), first.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     cudaFree(aux);
     S.entries = (int64_t)total * 32;
     TRY(devAlloc(ctx, &S.col, S.entries));
