@@ -147,7 +147,7 @@ static void freeMesh(amr_ctx *ctx) {
     devFree(ctx, &ctx->lvl); devFree(ctx, &ctx->lvl8); devFree(ctx, &ctx->parentIdx); devFree(ctx, &ctx->pointLevel);
     devFree(ctx, &ctx->protCell);
     devFree(ctx, &ctx->error); devFree(ctx, &ctx->refineCell);
-    devFree(ctx, &ctx->flagA); devFree(ctx, &ctx->flagB); devFree(ctx, &ctx->flagC); devFree(ctx, &ctx->lf);
+    devFree(ctx, &ctx->flagA); devFree(ctx, &ctx->flagB); devFree(ctx, &ctx->flagC); devFree(ctx, &ctx->lf); devFree(ctx, &ctx->srcBits);
     devFree(ctx, &ctx->ghost8); devFree(ctx, &ctx->ghost64);
     devFree(ctx, &ctx->lbStatus);
     devFree(ctx, &ctx->queue[0]); devFree(ctx, &ctx->queue[1]); ctx->queueCap = 0;
@@ -641,6 +641,7 @@ static int meshScratchAlloc(amr_ctx *ctx, u8 *pending, int64_t pendingN) {
     ctx->flagCap = m + 16;
     TRY(devAlloc(ctx, &ctx->flagA, m + 16)); TRY(devAlloc(ctx, &ctx->flagB, m + 16)); TRY(devAlloc(ctx, &ctx->flagC, m + 16));
     TRY(devAlloc(ctx, &ctx->lf, n + 16));
+    TRY(devAlloc(ctx, &ctx->srcBits, n / 32 + 16));
     TRY(devAlloc(ctx, &ctx->error, n));
     TRY(devAlloc(ctx, &ctx->refineCell, m + 16));
     TRY(devAlloc(ctx, &ctx->ghost8, b + 16));
@@ -1485,7 +1486,9 @@ static int extendLayer(amr_ctx *ctx, u8 *cur, const u8 *srcSeparate, int gen, in
         if (sparseForm(ctx, site, n)) {
             LAUNCH(k_layer_push, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, srcArr, separate, gen, al, cur, cnt);
         } else if (sparsePullForm(ctx, site, n)) {
-            LAUNCH(k_layer_pull_sparse, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, srcArr, separate, gen, al, cur, cnt);
+            // source mask as bits (n/8 bytes: L2-resident for the gathers), then the rows of the unmarked cells
+            LAUNCH(k_pack_source_bits, gridFor((n + 31) / 32), kThreads, n, srcArr, separate, gen, al, ctx->srcBits, cnt);
+            LAUNCH(k_layer_pull_sparse, gridFor(n, kThreads * 16), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, (const unsigned *)ctx->srcBits, gen, al, cur);
         } else if (pipeOk(ctx, ctx->cc)) TRY(launchPipe(ctx, kp_layer_pull, ctx->cc, srcArr, separate, gen, cur, cnt));
         else LAUNCH(k_layer_pull, gridFor(n), kThreads, n, ctx->cc.sliceOff, ctx->cc.col, srcArr, separate, gen, cur, cnt);
         ctx->sitesTouched |= 1u << site;

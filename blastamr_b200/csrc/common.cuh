@@ -192,6 +192,7 @@ struct amr_ctx {
     u8 *flagA = nullptr, *flagB = nullptr;      // [max(n,p)]
     u8 *flagC = nullptr;                        // [max(n,p)]
     u8 *lf = nullptr;                           // [n] level +/- flag
+    unsigned *srcBits = nullptr;                // [n/32] source mask of a sparse-pull layer as bits (L2-resident gathers)
     u8 *ghost8 = nullptr;       // [b] received byte payloads (marks, level +/- flag), boundary-face layout
     double *ghost64 = nullptr;  // [b] received field values
     unsigned long long *lbStatus = nullptr;     // [tileCap] tile status words of the single-pass compaction (scan.cuh)

@@ -123,79 +123,89 @@ k_layer_push(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__r
 // whole refined band), only the rows of the UNMARKED cells matter -- a 16-flags-per-load scan finds them, the warp deals
 // them to its lanes, each gathers the source values of its row.  Same result as the other two forms; reads the
 // adjacency of the unmarked cells only instead of streaming all of it.
+// The gathers of that walk read ONE flag per neighbour: as bytes they cost a 32-byte DRAM sector each (the marking of a
+// 72 M-cell mesh does not stay in L2 next to the adjacency stream); as bits the whole source mask is n/8 bytes (9 MB) and
+// lives in L2.  k_pack_source_bits builds the mask in one streaming pass (and counts the sources on the way).
 __global__ void __launch_bounds__(kThreads)
-k_layer_pull_sparse(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const u8 *srcArr, bool separate,
-                    int gen, bool aligned, u8 *cur, unsigned long long *__restrict__ nSrc) {
+k_pack_source_bits(int64_t n, const u8 *__restrict__ srcArr, bool separate, int gen, bool aligned, unsigned *__restrict__ bits,
+                   unsigned long long *__restrict__ nSrc) {
+    const int64_t word = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t base = word * 32;
+    unsigned m = 0;
+    if (base < n) {
+        if (aligned && base + 32 <= n) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(srcArr + base), b = *reinterpret_cast<const uint4 *>(srcArr + base + 16);
+            const unsigned v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 32; k++) m |= (isSource((v[k >> 2] >> (8 * (k & 3))) & 0xffu, gen, separate) ? 1u : 0u) << k;
+        } else {
+            for (int k = 0; k < 32 && base + k < n; k++) m |= (isSource(srcArr[base + k], gen, separate) ? 1u : 0u) << k;
+        }
+        bits[word] = m;
+    }
+    if (nSrc) blockAddCount(__popc(m), nSrc);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_layer_pull_sparse(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__restrict__ col, const unsigned *__restrict__ srcBits,
+                    int gen, bool aligned, u8 *cur) {
     __shared__ unsigned short unsetIdx[kThreads / 32][512];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warpBase = ((int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31)) * 16;
-    int mine = 0;
-    if (warpBase < n) {
-        const int64_t base = warpBase + (int64_t)lane * 16;
-        unsigned zmask = 0;                                   // unmarked cells of this thread's 16
-        if (base < n) {
-            if (aligned && base + 16 <= n) {
-                const uint4 w = *reinterpret_cast<const uint4 *>(cur + base);
-                const unsigned v[4] = {w.x, w.y, w.z, w.w};
-                unsigned sv[4] = {v[0], v[1], v[2], v[3]};
-                if (separate) {
-                    const uint4 ws = *reinterpret_cast<const uint4 *>(srcArr + base);
-                    sv[0] = ws.x; sv[1] = ws.y; sv[2] = ws.z; sv[3] = ws.w;
-                }
+    if (warpBase >= n) return;
+    const int64_t base = warpBase + (int64_t)lane * 16;
+    unsigned zmask = 0;                                   // unmarked cells of this thread's 16
+    if (base < n) {
+        if (aligned && base + 16 <= n) {
+            const uint4 w = *reinterpret_cast<const uint4 *>(cur + base);
+            const unsigned v[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const unsigned own = (v[k >> 2] >> (8 * (k & 3))) & 0xffu;
-                    zmask |= (own == 0u ? 1u : 0u) << k;
-                    mine += isSource((sv[k >> 2] >> (8 * (k & 3))) & 0xffu, gen, separate) ? 1 : 0;
-                }
-            } else {
-                for (int k = 0; k < 16 && base + k < n; k++) {
-                    zmask |= (cur[base + k] == 0 ? 1u : 0u) << k;
-                    mine += isSource(srcArr[base + k], gen, separate) ? 1 : 0;
-                }
+            for (int k = 0; k < 4; k++) {
+                const unsigned z = ~__vcmpne4(v[k], 0u);         // 0xff per zero byte
+                zmask |= (((z >> 0) & 1u) | ((z >> 7) & 2u) | ((z >> 14) & 4u) | ((z >> 21) & 8u)) << (4 * k);
             }
-        }
-        const int cnt = __popc(zmask);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-            int o = incl - cnt;
-            while (zmask) {
-                const int k = __ffs(zmask) - 1;
-                zmask &= zmask - 1;
-                unsetIdx[warp][o++] = (unsigned short)(lane * 16 + k);
-            }
-            __syncwarp();
-            const u8 tag = (u8)(gen + 1);
-            for (int i = lane; i < total; i += 32) {
-                const int64_t c = warpBase + unsetIdx[warp][i];
-                const int32_t b0 = sliceOff[c >> 5];
-                const int w = sliceOff[(c >> 5) + 1] - b0;
-                const int32_t *row = col + ((size_t)b0 << 5) + (c & 31);
-                unsigned hit = 0;
-                for (int j0 = 0; j0 < w; j0 += 8) {
-                    int32_t q[8];
-                    unsigned v[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = srcArr[q[k]];
-#pragma unroll
-                    // padding reads the cell's own value: unmarked, and with a separate source array no source either (a source is
-                    // always marked: the candidates kernel writes both)
-                    for (int k = 0; k < 8; k++) hit |= (q[k] != (int32_t)c && isSource(v[k], gen, separate)) ? 1u : 0u;
-                }
-                if (hit) cur[c] = tag;
-            }
-            __syncwarp();
+        } else {
+            for (int k = 0; k < 16 && base + k < n; k++) zmask |= (cur[base + k] == 0 ? 1u : 0u) << k;
         }
     }
-    if (nSrc) blockAddCount(mine, nSrc);
+    const int cnt = __popc(zmask);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    int o = incl - cnt;
+    while (zmask) {
+        const int k = __ffs(zmask) - 1;
+        zmask &= zmask - 1;
+        unsetIdx[warp][o++] = (unsigned short)(lane * 16 + k);
+    }
+    __syncwarp();
+    const u8 tag = (u8)(gen + 1);
+    for (int i = lane; i < total; i += 32) {
+        const int64_t c = warpBase + unsetIdx[warp][i];
+        const int32_t b0 = sliceOff[c >> 5];
+        const int w = sliceOff[(c >> 5) + 1] - b0;
+        const int32_t *row = col + ((size_t)b0 << 5) + (c & 31);
+        unsigned hit = 0;
+        for (int j0 = 0; j0 < w; j0 += 8) {
+            int32_t q[8];
+            unsigned v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[k] = (j0 + k < w) ? row[(size_t)(j0 + k) << 5] : (int32_t)c;
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = srcBits[q[k] >> 5];
+#pragma unroll
+            // padding reads the cell's own bit: an unmarked cell is no source (a source is always marked: the candidates
+            // kernel writes both arrays)
+            for (int k = 0; k < 8; k++) hit |= (v[k] >> (q[k] & 31)) & 1u;
+        }
+        if (hit) cur[c] = tag;
+    }
+    __syncwarp();
 }
 
 // dense pull form (TMA-staged): every unmarked cell gathers the source values of its row
