@@ -961,7 +961,7 @@ def main():
         k_ms = stage_ms[2]
         roof = {"bound": "hbm", "kernel": kname, "achieved": (kbytes / 1e9) / (k_ms / 1e3), "peak": peak, "unit": "GB/s",
                 "frac": (kbytes / 1e9) / (k_ms / 1e3) / peak,
-                "traffic": (traffic or {}).get("kernel_dram_bytes_per_launch", {}).get(kname),
+                "traffic": next((v for k_, v in (traffic or {}).get("kernel_dram_bytes_per_launch", {}).items() if k_.startswith(kname)), None),
                 "algorithmic_bytes": kbytes, "formula": "4n' + 5(8n + 8n') + (4n + n + n')", "ms": k_ms, "peak_source": peak_src,
                 "algorithmic_step_bytes": int(sum(ab.values())),
                 "algorithmic_step_note": "bytes of the REFERENCE's dense loops (SURVEY 8d), not what the kernels move"}

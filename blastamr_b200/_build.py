@@ -30,6 +30,27 @@ def _newer(target: Path, sources) -> bool:
     return all(Path(s).stat().st_mtime <= t for s in sources)
 
 
+class _Lock:
+    """one builder at a time per target (ranks of one torchrun launch call the builders concurrently); the output is written
+    next to the target and renamed into place, so a loader never sees a half-written library"""
+
+    def __init__(self, target: Path):
+        self.path = target.with_suffix(target.suffix + ".lock")
+        self.fh = None
+
+    def __enter__(self):
+        import fcntl
+        self.fh = open(self.path, "w")
+        fcntl.flock(self.fh, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self.fh, fcntl.LOCK_UN)
+        self.fh.close()
+        return False
+
+
 def _run(cmd, **kw):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
     if r.returncode != 0:
@@ -56,8 +77,13 @@ def build_mesh(force: bool = False) -> Path:
     src = [CSRC / "meshgen.c"]
     if not force and _newer(LIB_MESH, src):
         return LIB_MESH
-    _run(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-fvisibility=hidden", "-std=gnu11",
-          "-o", str(LIB_MESH)] + [str(s) for s in src] + ["-lm"])
+    with _Lock(LIB_MESH):
+        if not force and _newer(LIB_MESH, src):
+            return LIB_MESH
+        tmp = LIB_MESH.with_suffix(f".tmp{os.getpid()}.so")
+        _run(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-fvisibility=hidden", "-std=gnu11",
+              "-o", str(tmp)] + [str(s) for s in src] + ["-lm"])
+        os.replace(tmp, LIB_MESH)
     return LIB_MESH
 
 
@@ -66,9 +92,14 @@ def build_oracle(force: bool = False) -> Path:
     csrc = [s for s in src if s.suffix == ".c"]
     if not force and _newer(LIB_ORACLE, src):
         return LIB_ORACLE
-    # -ffp-contract=off: no FMA contraction, x86-64 OpenFOAM builds have none either
-    _run(["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-std=gnu11", "-pthread",
-          "-o", str(LIB_ORACLE)] + [str(s) for s in csrc] + ["-lm"])
+    with _Lock(LIB_ORACLE):
+        if not force and _newer(LIB_ORACLE, src):
+            return LIB_ORACLE
+        tmp = LIB_ORACLE.with_suffix(f".tmp{os.getpid()}.so")
+        # -ffp-contract=off: no FMA contraction, x86-64 OpenFOAM builds have none either
+        _run(["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-std=gnu11", "-pthread",
+              "-o", str(tmp)] + [str(s) for s in csrc] + ["-lm"])
+        os.replace(tmp, LIB_ORACLE)
     return LIB_ORACLE
 
 
@@ -77,19 +108,24 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     hdr = sorted(CSRC.glob("*.cuh")) + sorted((ROOT / "include").glob("*.h"))
     if not force and _newer(LIB_CUDA, src + hdr):
         return LIB_CUDA
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    inc, libdir, libname = _nccl_paths()
-    cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", *NVCC_ARCH,
-           "-fmad=false",                      # bitwise parity of the FP64 estimators with the CPU reference
-           "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
-           "-I", str(ROOT / "include"), "-I", inc,
-           "-o", str(LIB_CUDA)] + [str(s) for s in src] + [
-           "-L", libdir, f"-l:{libname}", "-Xlinker", f"-rpath={libdir}", "-lcudart"]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    out = _run(cmd)
-    if verbose:
-        print(out)
+    with _Lock(LIB_CUDA):
+        if not force and _newer(LIB_CUDA, src + hdr):      # another rank built it while this one waited
+            return LIB_CUDA
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        inc, libdir, libname = _nccl_paths()
+        tmp = LIB_CUDA.with_suffix(f".tmp{os.getpid()}.so")
+        cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", *NVCC_ARCH,
+               "-fmad=false",                      # bitwise parity of the FP64 estimators with the CPU reference
+               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
+               "-I", str(ROOT / "include"), "-I", inc,
+               "-o", str(tmp)] + [str(s) for s in src] + [
+               "-L", libdir, f"-l:{libname}", "-Xlinker", f"-rpath={libdir}", "-lcudart"]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        out = _run(cmd)
+        os.replace(tmp, LIB_CUDA)
+        if verbose:
+            print(out)
     return LIB_CUDA
 
 
@@ -100,9 +136,14 @@ def build_host(force: bool = False) -> Path:
         return LIB_HOST
     if not force and _newer(LIB_HOST, src + hdr + [LIB_CUDA]):
         return LIB_HOST
-    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-I", str(ROOT / "include"),
-          "-I", str(ROOT / "blastamr_b200" / "host"), "-o", str(LIB_HOST)] + [str(s) for s in src] +
-         ["-L", str(LIB_CUDA.parent), "-l:libamr_b200.so", "-Wl,-rpath,$ORIGIN"])
+    with _Lock(LIB_HOST):
+        if not force and _newer(LIB_HOST, src + hdr + [LIB_CUDA]):
+            return LIB_HOST
+        tmp = LIB_HOST.with_suffix(f".tmp{os.getpid()}.so")
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-I", str(ROOT / "include"),
+              "-I", str(ROOT / "blastamr_b200" / "host"), "-o", str(tmp)] + [str(s) for s in src] +
+             ["-L", str(LIB_CUDA.parent), "-l:libamr_b200.so", "-Wl,-rpath,$ORIGIN"])
+        os.replace(tmp, LIB_HOST)
     return LIB_HOST
 
 

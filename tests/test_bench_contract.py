@@ -29,7 +29,7 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_committed_gpu_profile_has_the_contract_objects():
-    d = json.loads((ROOT / "profiles" / "r1_bench_n1.json").read_text().strip().splitlines()[-1])
+    d = json.loads((ROOT / "profiles" / "r2_bench_n1.json").read_text().strip().splitlines()[-1])
     base = json.loads((ROOT / "BASELINE.json").read_text())
     assert BASE_KEYS <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] >= 1 and d["warmup"] >= 3 and d["dtype"] == "f64" and d["data"] == "synthetic"
@@ -41,5 +41,13 @@ def test_committed_gpu_profile_has_the_contract_objects():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
     assert d["gpu_launches"] > 0
+    # round 2: the configuration the north star names (graded mesh, moved front) with checked decisions, bandwidth figures
+    # from measured DRAM bytes only, and the topology hand-over next to the step
+    assert d["scaling"] == "strong" and d["config"]["workload"].startswith("S2")
+    assert d["config"]["sweeps_refine"] >= 2 and d["config"]["n_unrefine"] > 0
+    assert d["parity"]["ok"] is True and d["decisions"]["timed_lists_equal_first_pass"] is True
+    assert all(("GBps" not in st) or st["GBps"] <= 1.2 * roof["peak"] for st in d["stages"].values())
+    assert "step_frac" not in roof or roof["step_frac"] <= 1.2
+    assert d["handover"]["decisions_equal_full_hand_over"] is True and d["handover"]["incremental_bytes"] < d["handover"]["full_bytes"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
