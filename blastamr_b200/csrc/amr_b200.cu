@@ -842,7 +842,8 @@ AMR_API int amr_mesh_update(amr_ctx *ctx, int64_t nNew, int64_t fNew, int64_t bN
         CK(cudaMemcpyAsync(ctx->bEmpty, emptyFace.data(), (size_t)bNew, cudaMemcpyHostToDevice, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->meshSet = true; ctx->faceLists = false;
+    ctx->faceLists = false;                       // (meshSet only once everything below has succeeded: a failed update leaves
+                                                  //  a context that asks for amr_mesh_set)
     TRY(meshBoundarySetup(ctx, coupled));
     // the renumbering of the cells stays on the device for the point rows (amr_mesh_update_points)
     if (dRevIn && keep.valid) {
@@ -878,6 +879,7 @@ AMR_API int amr_mesh_update(amr_ctx *ctx, int64_t nNew, int64_t fNew, int64_t bN
     hostMark(ctx, "amr_mesh_update: scratch allocated");
     ctx->carry = keep;
     guard.armed = false;
+    ctx->meshSet = true;
     ctx->pcClassDirty = true; ctx->balancedLocal = -1; ctx->balancedGlobal = -1; ctx->spDirty = true;
     return AMR_OK;
 }

@@ -43,6 +43,16 @@
  *   AMR_B200_PUSH_FRACTION=a/b    marked fraction below which a buffer layer / 2:1 sweep takes its sparse form
  *                                 (default 1/4; 0 = always dense)
  *   AMR_B200_PUSH_MIN_CELLS=n     mesh size below which the sparse forms are not tried (default 65536)
+ *   AMR_B200_PULL_FRACTION=a/b    source fraction above which a buffer layer walks the rows of the UNMARKED cells only
+ *                                 (default 1/2; 0 = never)
+ *   AMR_B200_LINKED=0             closure loops across ranks as three launches per iteration (halo push, queue kernel,
+ *                                 coupled-face fix-up) instead of one with push-on-change (same value on every rank)
+ *   AMR_B200_POLY_QUEUE=0         polyRefiner: dense edge + face sweeps instead of the queue closure on the edge graph
+ *   AMR_B200_PIPE_STAGES=2|3      ring depth of the TMA-staged kernels (default 3)
+ *   AMR_B200_FACE_BATCH=1         Lohner / Gauss gradient: four faces of a cell at a time (bitwise identical, slower)
+ *   AMR_B200_UPLOAD_LANES=n       host threads of the staged upload of pageable arrays
+ *   AMR_B200_TRACE=prefix         CUDA event after every launch, time line written at amr_ctx_destroy
+ *   AMR_B200_HOSTTIME=1           wall-clock marks of the mesh hand-over calls on stderr
  */
 #ifndef AMR_B200_H
 #define AMR_B200_H
