@@ -276,11 +276,20 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)               # the timed region is ~10 ms at 8 GPUs
+
+    def reset(self):
+        self.samples = []
+        self.reasons = set()
 
     def stop(self):
         self._halt.set()
         self.join(timeout=2)
+        if self.ok and not self.samples:           # a timed region shorter than one sampling period: the clock right at its end
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            except Exception:
+                pass
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
@@ -827,17 +836,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # Everything slow on the host (NVML start-up of the clock sampler: ~1 s, event creation) happens BEFORE the warm-up steps,
+    # so that the timed steps follow the warm-up directly: an idle second between them lets the clocks drop and skews the
+    # ranks by a millisecond, which the first timed step then pays (profiles/r2_n8_timeline.txt: 2.3 ms instead of 0.95 ms,
+    # a tenth of the whole timed region at 8 GPUs).
     sampler = ClockSampler(physical_device_index(local_rank))
-    sampler.start()
-    l0 = ctx.launches + ctx1.launches
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(NEV)] for _ in range(args.steps)]
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
-    barrier()
     nvtx = os.environ.get("BENCH_NVTX") == "1"            # profiling aid: `ncu --nvtx --nvtx-include "amr_step/"` sees the timed steps only
+    sampler.start()
+    for _ in range(args.warmup):
+        step()
+    sampler.reset()                     # clocks / throttle reasons of the timed region (from its opening barrier on) only
+    barrier()
+    l0 = ctx.launches + ctx1.launches
     t_start.record()
     for k in range(args.steps):
         if nvtx:
