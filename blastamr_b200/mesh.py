@@ -406,9 +406,12 @@ def mesh_delta(old: PolyMesh, new: PolyMesh, cell_map: np.ndarray, reverse_cell_
         return (q[:, 0] << 42) | (q[:, 1] << 21) | q[:, 2]
     k0, k1 = key(old), key(new)
     o0 = np.argsort(k0, kind="stable")
-    pos = np.searchsorted(k0[o0], k1)
+    k0s = k0[o0]
+    o1 = np.argsort(k1, kind="stable")                        # sorted queries: the search walks k0s once (cache friendly)
+    pos = np.empty(len(k1), dtype=np.int64)
+    pos[o1] = np.searchsorted(k0s, k1[o1])
     pos[pos >= len(k0)] = 0
-    hit = k0[o0][pos] == k1 if len(k0) else np.zeros(len(k1), bool)
+    hit = k0s[pos] == k1 if len(k0) else np.zeros(len(k1), bool)
     pmap = np.where(hit, o0[pos], -1).astype(np.int32)
     # a kept point is clean when every cell around it survived unchanged (same count, none touched)
     cnt1 = np.diff(new.pc_off)
