@@ -276,7 +276,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.002)               # the timed region is ~10 ms at 8 GPUs
+            time.sleep(0.004)               # the timed region is ~10 ms at 8 GPUs
 
     def reset(self):
         self.samples = []
