@@ -87,7 +87,7 @@ k_estimate(int64_t n, const int32_t *__restrict__ sliceOff, const int32_t *__res
 // fieldValue::update, fieldValue.C:68-82 (+ normalize); also the plain normalize pass (ABS=false)
 template <bool ABS, bool SCALE>
 __global__ void __launch_bounds__(kThreads)
-k_pointwise(int64_t n, const double *__restrict__ in, Thresholds thr, double *__restrict__ out) {
+k_pointwise(int64_t n, const double *in, Thresholds thr, double *out) {       // in == out for the plain normalize pass: no __restrict__
     int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (c >= n) return;
     double v = in[c];
@@ -242,9 +242,9 @@ k_zero_protected(int64_t n, const u8 *__restrict__ prot, double *__restrict__ er
 //   set[c] = cellLevel < maxRefinement && candidate && !unrefineable ;  lf[c] = cellLevel + set
 // LEVEL >= 0 restricts to cellLevel == LEVEL and ORs into set (the maxCells truncation loop :346-374).
 __global__ void __launch_bounds__(kThreads)
-k_select_filter(int64_t n, const u8 *__restrict__ cand, const label *__restrict__ lvl, const label *__restrict__ maxLvl,
-                label maxLvlUniform, const u8 *__restrict__ unrefineable, int onlyLevel, u8 *__restrict__ set,
-                u8 *__restrict__ lf, bool aligned) {
+k_select_filter(int64_t n, const u8 *cand, const label *__restrict__ lvl, const label *__restrict__ maxLvl,
+                label maxLvlUniform, const u8 *__restrict__ unrefineable, int onlyLevel, u8 *set,
+                u8 *__restrict__ lf, bool aligned) {                               // cand may be set (amr_consistent_refinement): no __restrict__ on the pair
     const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
     if (c0 >= n) return;
     const bool vec = aligned && c0 + 4 <= n;

@@ -280,7 +280,7 @@ k_fix_layer_link(const __grid_constant__ GhostLink G, int64_t nC, const label *_
 }
 // marking -> boolList (0/1) for the caller; also the import direction
 __global__ void __launch_bounds__(kThreads)
-k_flags_normalize(int64_t n, const u8 *__restrict__ in, u8 *__restrict__ out, bool aligned) {
+k_flags_normalize(int64_t n, const u8 *in, u8 *out, bool aligned) {               // used in place as well: no __restrict__
     const int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 16;
     if (base >= n) return;
     if (aligned && base + 16 <= n) {
